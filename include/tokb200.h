@@ -1,0 +1,142 @@
+/* tokb200.h — C ABI of libtokb200.so: the sm_100a kernels behind torchok_b200.
+ *
+ * The reference (eora-ai/torchok) has no FFI of its own: its hot path is torch.nn modules assembled by the
+ * registry/constructor (torchok/constructor/registry.py:45-99, torchok/tasks/classification.py:47-73) and every
+ * FLOP is dispatched by torch to cuDNN/cuBLAS/ATen.  Each entry point below names the reference call site whose
+ * torch dispatch it replaces.  The Python host (torchok_b200/_lib.py) binds these with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; nothing here allocates, frees or synchronises;
+ *   - activations are NHWC bf16 ("pixel-major"), conv weights are [Cout][R][S][Cin] bf16 (= a torch OIHW tensor in
+ *     channels_last memory format), weight gradients are fp32 in the same layout;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = success, negative = tokStatus; tok_last_error() returns a thread-local message;
+ *   - channel counts must be multiples of 8 (16-byte TMA rows).
+ */
+#ifndef TOKB200_H_
+#define TOKB200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  TOK_OK = 0,
+  TOK_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  TOK_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+  TOK_ERR_NODRIVER = -3   /* libcuda entry points unavailable (no GPU driver on this host) */
+} tokStatus;
+
+int tok_version(void);
+const char* tok_last_error(void);
+/* 0 if a CUDA device with compute capability 10.x is usable, else negative. */
+int tok_device_ok(void);
+
+/* ---- convolution (torch.nn.Conv2d inside ConvBnAct, torchok/models/modules/bricks/convbnact.py:38-53; timm
+ *      BasicBlock/Bottleneck convs built by torchok/models/backbones/resnet.py:363-405) ------------------------- */
+typedef struct {
+  int n, h, w, c;      /* input NHWC */
+  int k;               /* output channels */
+  int r, s;            /* filter */
+  int stride, pad, dil;
+} tokConvDesc;
+
+/* Output spatial size of a convolution (same arithmetic as torch.nn.Conv2d). */
+void tok_conv_out_hw(const tokConvDesc* d, int* p, int* q);
+
+/* y[n,p,q,k] = sum x[n, p*stride-pad+r*dil, q*stride-pad+s*dil, c] * w[k,r,s,c]  (+bias[k]) (+addend) (relu)
+ * If sum/sqsum are non-NULL, per-channel sums of the stored bf16 values and of their squares are ATOMICALLY ADDED
+ * to them (caller zero-fills): these are the BatchNorm batch statistics (torch.nn.BatchNorm2d training mode). */
+int tok_conv_fprop(const tokConvDesc* d, const void* x, const void* w, void* y, float* sum, float* sqsum,
+                   const void* addend, const float* bias, int relu, void* stream);
+
+/* dx = conv_transpose(dy, w).  `addend` (nullable, NHWC like dx, may alias dx) is added before the store.
+ * `ws` is scratch of tok_conv_dgrad_workspace_bytes(d) bytes (needed for strided RxS>1 filters). */
+size_t tok_conv_dgrad_workspace_bytes(const tokConvDesc* d);
+int tok_conv_dgrad(const tokConvDesc* d, const void* dy, const void* w, void* dx, const void* addend, void* ws,
+                   void* stream);
+
+/* dw[k,r,s,c] += sum_pixels dy[n,p,q,k] * x[n, ..., c]   (fp32, atomically accumulated; caller zero-fills). */
+int tok_conv_wgrad(const tokConvDesc* d, const void* x, const void* dy, float* dw, void* stream);
+
+/* ---- dense layers (torch.nn.Linear in LinearHead, torchok/models/heads/representation/linear_head.py:25-36;
+ *      PoolingLinear, torchok/models/poolings/classification/linear.py:12-19) -------------------------------- */
+/* y[m,n] = sum_k x[m,k] * w[n,k] + bias[n] ; x,w,y bf16, bias fp32 (nullable). */
+int tok_linear_fwd(int m, int n, int k, const void* x, const void* w, const float* bias, void* y, void* stream);
+/* dx[m,k] = sum_n dy[m,n] * w[n,k] */
+int tok_linear_dgrad(int m, int n, int k, const void* dy, const void* w, void* dx, void* stream);
+/* dw[n,k] += sum_m dy[m,n] * x[m,k]  (fp32, atomically accumulated) */
+int tok_linear_wgrad(int m, int n, int k, const void* x, const void* dy, float* dw, void* stream);
+
+
+/* ---- ResNet stem: 7x7 stride-2 pad-3 conv on <=4 input channels (torchok/models/backbones/resnet.py:488-490,
+ *      542-545).  The NCHW image is packed once into a zero-padded 2x2 space-to-depth NHWC16 tensor
+ *      [N][H2][W2][16]; the conv then runs as a 4-tap im2col GEMM with K = 4*64 through the common kernel. -------- */
+void tok_stem_geometry(int h, int w, int* p, int* q, int* h2, int* w2);
+int tok_stem_pack_input(int n, int c, int h, int w, int src_is_bf16, const void* src_nchw, void* xs2d, void* stream);
+/* w: fp32 [K][7][7][C] (OIHW in channels_last memory format) -> wp: bf16 [K][256] */
+int tok_stem_pack_weight(int k, int c, const float* w, void* wp, void* stream);
+int tok_stem_unpack_wgrad(int k, int c, const float* dwp, float* dw, int accumulate, void* stream);
+int tok_stem_conv_fprop(int n, int h, int w, int k, const void* xs2d, const void* wp, void* y, float* sum,
+                        float* sqsum, void* stream);
+/* dwp: fp32 [K][256], atomically accumulated (caller zero-fills) */
+int tok_stem_conv_wgrad(int n, int h, int w, int k, const void* xs2d, const void* dy, float* dwp, void* stream);
+
+/* ---- BatchNorm2d (+ReLU, +residual add) around the convs (torch.nn.BatchNorm2d in ConvBnAct,
+ *      torchok/models/modules/bricks/convbnact.py:44-53; timm block tails `x += shortcut; act(x)`) --------------- */
+/* batch statistics (sums from tok_conv_fprop) -> scale/shift, saved mean/invstd, running-stat update */
+int tok_bn_finalize_train(int C, double count, const float* sum, const float* sqsum, const float* gamma,
+                          const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                          float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+int tok_bn_finalize_eval(int C, const float* running_mean, const float* running_var, const float* gamma,
+                         const float* beta, float eps, float* scale, float* shift, void* stream);
+/* out = act(y*scale + shift (+residual)) over a [rows][C] bf16 matrix */
+int tok_bn_apply(long long rows, int C, const void* y, const float* scale, const float* shift, const void* residual,
+                 int relu, void* out, void* stream);
+/* g = (dout (+dout2)) * [out > 0] (mask skipped when out == NULL); sum_g += sum g, sum_gy += sum g*y (zero-filled
+ * by the caller) */
+int tok_bn_bwd_reduce(long long rows, int C, const void* dout, const void* dout2, const void* out, const void* y,
+                      float* sum_g, float* sum_gy, void* stream);
+int tok_bn_bwd_finalize(int C, double count, const float* sum_g, const float* sum_gy, const float* save_mean,
+                        const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1, float* coef_c0,
+                        float* dgamma, float* dbeta, int accumulate, void* stream);
+/* dy = coef_a*g + coef_c1*y + coef_c0 ; dres (nullable) receives g */
+int tok_bn_bwd_apply(long long rows, int C, const void* dout, const void* dout2, const void* out, const void* y,
+                     const float* coef_a, const float* coef_c1, const float* coef_c0, void* dy, void* dres,
+                     void* stream);
+
+/* ---- pooling (torch.nn.MaxPool2d, resnet.py:510; timm SelectAdaptivePool2d, poolings/classification/pooling.py:8-12)
+ * argmax: one byte per output element (window slot of the first maximum). */
+int tok_maxpool_fwd(int n, int h, int w, int c, int k, int s, int pad, const void* x, void* out, void* argmax,
+                    void* stream);
+int tok_maxpool_bwd(int n, int h, int w, int c, int k, int s, int pad, const void* dout, const void* argmax, void* dx,
+                    void* stream);
+/* mode 0 avg, 1 max, 2 avgmax */
+int tok_gap_fwd(int n, int hw, int c, int mode, const void* x, void* out, void* stream);
+int tok_gap_bwd(int n, int hw, int c, const void* dout, void* dx, void* stream);
+
+/* ---- loss (torch.nn.CrossEntropyLoss, torchok/losses/__init__.py:26): loss_sum += mean NLL, dlogits written in place
+ * of a separate backward; `correct` (nullable) counts rows whose argmax equals the target. */
+int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const long long* target, float* loss_sum,
+                     void* dlogits, float inv_norm, float gscale, long long ignore_index, int* correct, void* stream);
+
+/* ---- layout (task boundary is NCHW, torchok/tasks/classification.py:108-109) ------------------------------------ */
+int tok_nchw_to_nhwc(int n, int c, int hw, int cp, int src_is_bf16, const void* src, void* dst, void* stream);
+int tok_nhwc_to_nchw(int n, int c, int hw, int cp, int dst_is_bf16, const void* src, void* dst, void* stream);
+
+/* ---- optimizer steps on flat fp32 parameter arenas, fused with the bf16 shadow-weight cast
+ *      (torch.optim.SGD / Adam / AdamW registered in torchok/optim/optimizers/__init__.py:9-19) ------------------- */
+int tok_sgd_step(long long n, float* param, const float* grad, float* momentum_buf, void* shadow_bf16, float lr,
+                 float momentum, float weight_decay, float dampening, int nesterov, float grad_scale, int first_step,
+                 void* stream);
+int tok_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, int step,
+                  float grad_scale, void* stream);
+int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOKB200_H_ */

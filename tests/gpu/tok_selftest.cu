@@ -1,0 +1,702 @@
+// tok_selftest.cu — standalone bring-up / regression binary for libtokb200.so (runs on the GPU box without Python).
+// Every check calls the C ABI exactly as the Python host does and compares with a straightforward CPU loop nest.
+//   usage: tok_selftest <group> [args]     groups: gemm conv dgrad wgrad stem elem perf
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/tokb200.h"
+
+#define CK(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) {                                                                    \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);           \
+      exit(2);                                                                                  \
+    }                                                                                           \
+  } while (0)
+#define TK(x)                                                                                   \
+  do {                                                                                          \
+    int r_ = (x);                                                                               \
+    if (r_ != 0) {                                                                              \
+      printf("TOK error %d (%s) at %s:%d\n", r_, tok_last_error(), __FILE__, __LINE__);         \
+      g_fail++;                                                                                 \
+      return;                                                                                   \
+    }                                                                                           \
+  } while (0)
+
+static int g_fail = 0;
+static uint32_t g_seed = 12345;
+static float frand() {
+  g_seed = g_seed * 1664525u + 1013904223u;
+  return ((g_seed >> 8) & 0xFFFF) / 65536.0f * 2.f - 1.f;
+}
+static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  explicit DevBuf(size_t b) : bytes(b) {
+    CK(cudaMalloc(&p, b ? b : 16));
+    CK(cudaMemset(p, 0, b ? b : 16));
+  }
+  ~DevBuf() { cudaFree(p); }
+};
+// host float vector (values already bf16-representable) -> device bf16
+static void up_bf16(DevBuf& d, const std::vector<float>& h) {
+  std::vector<__nv_bfloat16> t(h.size());
+  for (size_t i = 0; i < h.size(); ++i) t[i] = __float2bfloat16(h[i]);
+  CK(cudaMemcpy(d.p, t.data(), t.size() * 2, cudaMemcpyHostToDevice));
+}
+static std::vector<float> down_bf16(const DevBuf& d, size_t n) {
+  std::vector<__nv_bfloat16> t(n);
+  CK(cudaMemcpy(t.data(), d.p, n * 2, cudaMemcpyDeviceToHost));
+  std::vector<float> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = __bfloat162float(t[i]);
+  return h;
+}
+static void up_f32(DevBuf& d, const std::vector<float>& h) {
+  CK(cudaMemcpy(d.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+}
+static std::vector<float> down_f32(const DevBuf& d, size_t n) {
+  std::vector<float> h(n);
+  CK(cudaMemcpy(h.data(), d.p, n * 4, cudaMemcpyDeviceToHost));
+  return h;
+}
+static std::vector<float> rnd(size_t n, float scale = 1.f) {
+  std::vector<float> v(n);
+  for (auto& x : v) x = bf(frand() * scale);
+  return v;
+}
+
+// compare with tolerance = atol + rtol*|ref|
+static bool compare(const char* name, const std::vector<float>& got, const std::vector<double>& ref, double atol,
+                    double rtol) {
+  double max_err = 0, max_ref = 0;
+  size_t bad = 0, first_bad = 0;
+  for (size_t i = 0; i < ref.size(); ++i) {
+    const double e = fabs((double)got[i] - ref[i]);
+    if (!(e <= atol + rtol * fabs(ref[i]))) {
+      if (!bad) first_bad = i;
+      ++bad;
+    }
+    if (e > max_err || e != e) max_err = e;
+    max_ref = std::max(max_ref, fabs(ref[i]));
+  }
+  printf("[%s] %-44s n=%zu max_err=%.4g max_ref=%.4g bad=%zu", bad ? "FAIL" : "PASS", name, ref.size(), max_err,
+         max_ref, bad);
+  if (bad) {
+    printf("  first_bad@%zu got=%.6g ref=%.6g", first_bad, got[first_bad], ref[first_bad]);
+    g_fail++;
+  }
+  printf("\n");
+  if (bad) {
+    int shown = 0;
+    for (size_t i = 0; i < ref.size() && shown < 12; ++i) {
+      const double e = fabs((double)got[i] - ref[i]);
+      if (!(e <= atol + rtol * fabs(ref[i]))) {
+        printf("      idx %zu got %.6g ref %.6g\n", i, got[i], ref[i]);
+        ++shown;
+      }
+    }
+  }
+  fflush(stdout);
+  return bad == 0;
+}
+
+// ---------------------------------------------------------------------------------------------- CPU references
+struct Conv {
+  int n, h, w, c, k, r, s, stride, pad, dil;
+  int P() const { return (h + 2 * pad - dil * (r - 1) - 1) / stride + 1; }
+  int Q() const { return (w + 2 * pad - dil * (s - 1) - 1) / stride + 1; }
+  tokConvDesc desc() const { return tokConvDesc{n, h, w, c, k, r, s, stride, pad, dil}; }
+};
+// x NHWC, w [k][r][s][c], y [n][p][q][k]
+static std::vector<double> cpu_fprop(const Conv& cv, const std::vector<float>& x, const std::vector<float>& w) {
+  const int P = cv.P(), Q = cv.Q();
+  std::vector<double> y((size_t)cv.n * P * Q * cv.k, 0.0);
+  for (int n = 0; n < cv.n; ++n)
+    for (int p = 0; p < P; ++p)
+      for (int q = 0; q < Q; ++q)
+        for (int k = 0; k < cv.k; ++k) {
+          double acc = 0;
+          for (int r = 0; r < cv.r; ++r) {
+            const int hh = p * cv.stride - cv.pad + r * cv.dil;
+            if (hh < 0 || hh >= cv.h) continue;
+            for (int s = 0; s < cv.s; ++s) {
+              const int ww = q * cv.stride - cv.pad + s * cv.dil;
+              if (ww < 0 || ww >= cv.w) continue;
+              const float* xp = &x[(((size_t)n * cv.h + hh) * cv.w + ww) * cv.c];
+              const float* wp = &w[(((size_t)k * cv.r + r) * cv.s + s) * cv.c];
+              for (int c = 0; c < cv.c; ++c) acc += (double)xp[c] * wp[c];
+            }
+          }
+          y[(((size_t)n * P + p) * Q + q) * cv.k + k] = acc;
+        }
+  return y;
+}
+static std::vector<double> cpu_dgrad(const Conv& cv, const std::vector<float>& dy, const std::vector<float>& w) {
+  const int P = cv.P(), Q = cv.Q();
+  std::vector<double> dx((size_t)cv.n * cv.h * cv.w * cv.c, 0.0);
+  for (int n = 0; n < cv.n; ++n)
+    for (int p = 0; p < P; ++p)
+      for (int q = 0; q < Q; ++q)
+        for (int k = 0; k < cv.k; ++k) {
+          const double g = dy[(((size_t)n * P + p) * Q + q) * cv.k + k];
+          for (int r = 0; r < cv.r; ++r) {
+            const int hh = p * cv.stride - cv.pad + r * cv.dil;
+            if (hh < 0 || hh >= cv.h) continue;
+            for (int s = 0; s < cv.s; ++s) {
+              const int ww = q * cv.stride - cv.pad + s * cv.dil;
+              if (ww < 0 || ww >= cv.w) continue;
+              double* dp = &dx[(((size_t)n * cv.h + hh) * cv.w + ww) * cv.c];
+              const float* wp = &w[(((size_t)k * cv.r + r) * cv.s + s) * cv.c];
+              for (int c = 0; c < cv.c; ++c) dp[c] += g * wp[c];
+            }
+          }
+        }
+  return dx;
+}
+static std::vector<double> cpu_wgrad(const Conv& cv, const std::vector<float>& x, const std::vector<float>& dy) {
+  const int P = cv.P(), Q = cv.Q();
+  std::vector<double> dw((size_t)cv.k * cv.r * cv.s * cv.c, 0.0);
+  for (int n = 0; n < cv.n; ++n)
+    for (int p = 0; p < P; ++p)
+      for (int q = 0; q < Q; ++q)
+        for (int k = 0; k < cv.k; ++k) {
+          const double g = dy[(((size_t)n * P + p) * Q + q) * cv.k + k];
+          for (int r = 0; r < cv.r; ++r) {
+            const int hh = p * cv.stride - cv.pad + r * cv.dil;
+            if (hh < 0 || hh >= cv.h) continue;
+            for (int s = 0; s < cv.s; ++s) {
+              const int ww = q * cv.stride - cv.pad + s * cv.dil;
+              if (ww < 0 || ww >= cv.w) continue;
+              const float* xp = &x[(((size_t)n * cv.h + hh) * cv.w + ww) * cv.c];
+              double* wp = &dw[(((size_t)k * cv.r + r) * cv.s + s) * cv.c];
+              for (int c = 0; c < cv.c; ++c) wp[c] += g * xp[c];
+            }
+          }
+        }
+  return dw;
+}
+
+// ---------------------------------------------------------------------------------------------- tests
+static void test_linear(int m, int n, int k) {
+  char name[128];
+  auto x = rnd((size_t)m * k), w = rnd((size_t)n * k, 0.25f);
+  std::vector<float> bias(n);
+  for (auto& b : bias) b = frand();
+  DevBuf dx((size_t)m * k * 2), dw((size_t)n * k * 2), db((size_t)n * 4), dy((size_t)m * n * 2);
+  up_bf16(dx, x);
+  up_bf16(dw, w);
+  up_f32(db, bias);
+  TK(tok_linear_fwd(m, n, k, dx.p, dw.p, (const float*)db.p, dy.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> ref((size_t)m * n);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j) {
+      double a = bias[j];
+      for (int t = 0; t < k; ++t) a += (double)x[(size_t)i * k + t] * w[(size_t)j * k + t];
+      ref[(size_t)i * n + j] = a;
+    }
+  snprintf(name, sizeof(name), "linear_fwd m=%d n=%d k=%d", m, n, k);
+  compare(name, down_bf16(dy, (size_t)m * n), ref, 0.02, 0.01);
+
+  // dgrad: dx = dy * w
+  auto g = rnd((size_t)m * n);
+  DevBuf dg((size_t)m * n * 2), ddx((size_t)m * k * 2);
+  up_bf16(dg, g);
+  TK(tok_linear_dgrad(m, n, k, dg.p, dw.p, ddx.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> rdx((size_t)m * k, 0.0);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j)
+      for (int t = 0; t < k; ++t) rdx[(size_t)i * k + t] += (double)g[(size_t)i * n + j] * w[(size_t)j * k + t];
+  snprintf(name, sizeof(name), "linear_dgrad (MN-major B) m=%d n=%d k=%d", m, n, k);
+  compare(name, down_bf16(ddx, (size_t)m * k), rdx, 0.03, 0.01);
+
+  // wgrad: dw = dy^T x
+  DevBuf ddw((size_t)n * k * 4);
+  TK(tok_linear_wgrad(m, n, k, dx.p, dg.p, (float*)ddw.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> rdw((size_t)n * k, 0.0);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j)
+      for (int t = 0; t < k; ++t) rdw[(size_t)j * k + t] += (double)g[(size_t)i * n + j] * x[(size_t)i * k + t];
+  snprintf(name, sizeof(name), "linear_wgrad (MN-major A,B) m=%d n=%d k=%d", m, n, k);
+  compare(name, down_f32(ddw, (size_t)n * k), rdw, 1e-2, 1e-3);
+}
+
+static void test_fprop(const Conv& cv, bool extras) {
+  char name[160];
+  const int P = cv.P(), Q = cv.Q();
+  const size_t M = (size_t)cv.n * P * Q;
+  auto x = rnd((size_t)cv.n * cv.h * cv.w * cv.c), w = rnd((size_t)cv.k * cv.r * cv.s * cv.c, 0.25f);
+  DevBuf dx(x.size() * 2), dw(w.size() * 2), dy(M * cv.k * 2), dsum(cv.k * 4), dsq(cv.k * 4), dadd(M * cv.k * 2);
+  up_bf16(dx, x);
+  up_bf16(dw, w);
+  auto add = rnd(M * cv.k);
+  up_bf16(dadd, add);
+  tokConvDesc d = cv.desc();
+  TK(tok_conv_fprop(&d, dx.p, dw.p, dy.p, (float*)dsum.p, (float*)dsq.p, extras ? dadd.p : nullptr, nullptr,
+                    extras ? 1 : 0, nullptr));
+  CK(cudaDeviceSynchronize());
+  auto ref = cpu_fprop(cv, x, w);
+  if (extras)
+    for (size_t i = 0; i < ref.size(); ++i) ref[i] = std::max(0.0, ref[i] + add[i]);
+  snprintf(name, sizeof(name), "fprop n%d %dx%d c%d k%d %dx%d s%d p%d%s", cv.n, cv.h, cv.w, cv.c, cv.k, cv.r, cv.s,
+           cv.stride, cv.pad, extras ? " +addend+relu" : "");
+  auto got = down_bf16(dy, M * cv.k);
+  compare(name, got, ref, 0.03, 0.01);
+  // statistics must be the column sums of the stored values
+  std::vector<double> rs(cv.k, 0.0), rq(cv.k, 0.0);
+  for (size_t i = 0; i < M; ++i)
+    for (int k = 0; k < cv.k; ++k) {
+      rs[k] += got[i * cv.k + k];
+      rq[k] += (double)got[i * cv.k + k] * got[i * cv.k + k];
+    }
+  compare("  column sum", down_f32(dsum, cv.k), rs, 1e-2, 1e-3);
+  compare("  column sum of squares", down_f32(dsq, cv.k), rq, 1e-2, 1e-3);
+}
+
+static void test_dgrad(const Conv& cv, bool with_addend) {
+  char name[160];
+  const int P = cv.P(), Q = cv.Q();
+  const size_t M = (size_t)cv.n * P * Q;
+  const size_t nx = (size_t)cv.n * cv.h * cv.w * cv.c;
+  auto g = rnd(M * cv.k), w = rnd((size_t)cv.k * cv.r * cv.s * cv.c, 0.25f);
+  auto add = rnd(nx);
+  DevBuf dg(g.size() * 2), dw(w.size() * 2), ddx(nx * 2);
+  tokConvDesc d = cv.desc();
+  DevBuf ws(tok_conv_dgrad_workspace_bytes(&d));
+  up_bf16(dg, g);
+  up_bf16(dw, w);
+  if (with_addend) up_bf16(ddx, add);  // in-place accumulate
+  TK(tok_conv_dgrad(&d, dg.p, dw.p, ddx.p, with_addend ? ddx.p : nullptr, ws.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  auto ref = cpu_dgrad(cv, g, w);
+  if (with_addend)
+    for (size_t i = 0; i < ref.size(); ++i) ref[i] += add[i];
+  snprintf(name, sizeof(name), "dgrad n%d %dx%d c%d k%d %dx%d s%d p%d%s", cv.n, cv.h, cv.w, cv.c, cv.k, cv.r, cv.s,
+           cv.stride, cv.pad, with_addend ? " +addend(in place)" : "");
+  compare(name, down_bf16(ddx, nx), ref, 0.05, 0.01);
+}
+
+static void test_wgrad(const Conv& cv) {
+  char name[160];
+  const int P = cv.P(), Q = cv.Q();
+  const size_t M = (size_t)cv.n * P * Q;
+  auto x = rnd((size_t)cv.n * cv.h * cv.w * cv.c), g = rnd(M * cv.k);
+  const size_t nw = (size_t)cv.k * cv.r * cv.s * cv.c;
+  DevBuf dx(x.size() * 2), dg(g.size() * 2), ddw(nw * 4);
+  up_bf16(dx, x);
+  up_bf16(dg, g);
+  tokConvDesc d = cv.desc();
+  TK(tok_conv_wgrad(&d, dx.p, dg.p, (float*)ddw.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  auto ref = cpu_wgrad(cv, x, g);
+  snprintf(name, sizeof(name), "wgrad n%d %dx%d c%d k%d %dx%d s%d p%d", cv.n, cv.h, cv.w, cv.c, cv.k, cv.r, cv.s,
+           cv.stride, cv.pad);
+  compare(name, down_f32(ddw, nw), ref, 2e-2, 2e-3);
+}
+
+static void test_stem(int n, int h, int w, int cin, int k) {
+  char name[160];
+  Conv cv{n, h, w, cin, k, 7, 7, 2, 3, 1};
+  const int P = cv.P(), Q = cv.Q();
+  int p2, q2, H2, W2;
+  tok_stem_geometry(h, w, &p2, &q2, &H2, &W2);
+  printf("stem geometry: P=%d Q=%d (expected %d %d) H2=%d W2=%d\n", p2, q2, P, Q, H2, W2);
+  // NCHW fp32 image, values bf16-representable
+  std::vector<float> img((size_t)n * cin * h * w);
+  for (auto& v : img) v = bf(frand());
+  std::vector<float> x_nhwc((size_t)n * h * w * cin);
+  for (int a = 0; a < n; ++a)
+    for (int c = 0; c < cin; ++c)
+      for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j)
+          x_nhwc[(((size_t)a * h + i) * w + j) * cin + c] = img[(((size_t)a * cin + c) * h + i) * w + j];
+  std::vector<float> wt((size_t)k * 49 * cin);
+  for (auto& v : wt) v = bf(frand() * 0.25f);
+  DevBuf dimg(img.size() * 4), dxs((size_t)n * H2 * W2 * 16 * 2), dwt(wt.size() * 4), dwp((size_t)k * 256 * 2);
+  const size_t M = (size_t)n * P * Q;
+  DevBuf dy(M * k * 2), dsum(k * 4), dsq(k * 4);
+  up_f32(dimg, img);
+  up_f32(dwt, wt);
+  TK(tok_stem_pack_input(n, cin, h, w, 0, dimg.p, dxs.p, nullptr));
+  TK(tok_stem_pack_weight(k, cin, (const float*)dwt.p, dwp.p, nullptr));
+  TK(tok_stem_conv_fprop(n, h, w, k, dxs.p, dwp.p, dy.p, (float*)dsum.p, (float*)dsq.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  auto ref = cpu_fprop(cv, x_nhwc, wt);
+  snprintf(name, sizeof(name), "stem fprop n%d %dx%d c%d k%d (s2d + overlapping im2col map)", n, h, w, cin, k);
+  compare(name, down_bf16(dy, M * k), ref, 0.03, 0.01);
+  // wgrad
+  auto g = rnd(M * k);
+  DevBuf dg(g.size() * 2), ddwp((size_t)k * 256 * 4), ddw(wt.size() * 4);
+  up_bf16(dg, g);
+  TK(tok_stem_conv_wgrad(n, h, w, k, dxs.p, dg.p, (float*)ddwp.p, nullptr));
+  TK(tok_stem_unpack_wgrad(k, cin, (const float*)ddwp.p, (float*)ddw.p, 0, nullptr));
+  CK(cudaDeviceSynchronize());
+  auto rdw = cpu_wgrad(cv, x_nhwc, g);
+  snprintf(name, sizeof(name), "stem wgrad n%d %dx%d c%d k%d", n, h, w, cin, k);
+  compare(name, down_f32(ddw, wt.size()), rdw, 2e-2, 2e-3);
+}
+
+// ---- elementwise ------------------------------------------------------------------------------------------------
+static void test_bn(long long rows, int C) {
+  char name[128];
+  const size_t n = (size_t)rows * C;
+  auto y = rnd(n, 2.f), res = rnd(n), dout = rnd(n);
+  std::vector<float> gamma(C), beta(C), rm(C), rv(C);
+  for (int c = 0; c < C; ++c) {
+    gamma[c] = 0.5f + fabsf(frand());
+    beta[c] = 0.1f * frand();
+    rm[c] = 0.1f * frand();
+    rv[c] = 0.5f + fabsf(frand());
+  }
+  // forward reference
+  std::vector<double> mean(C, 0), var(C, 0);
+  for (size_t i = 0; i < n; ++i) mean[i % C] += y[i];
+  for (int c = 0; c < C; ++c) mean[c] /= rows;
+  for (size_t i = 0; i < n; ++i) var[i % C] += (y[i] - mean[i % C]) * (y[i] - mean[i % C]);
+  for (int c = 0; c < C; ++c) var[c] /= rows;
+  const double eps = 1e-5;
+  std::vector<double> ref(n);
+  for (size_t i = 0; i < n; ++i) {
+    const int c = i % C;
+    ref[i] = std::max(0.0, (y[i] - mean[c]) / sqrt(var[c] + eps) * gamma[c] + beta[c] + res[i]);
+  }
+  DevBuf dy_(n * 2), dres(n * 2), dout_(n * 2), o(n * 2), sum(C * 4), sq(C * 4), dg(C * 4), db(C * 4), drm(C * 4),
+      drv(C * 4), sc(C * 4), sh(C * 4), sm(C * 4), si(C * 4);
+  up_bf16(dy_, y);
+  up_bf16(dres, res);
+  up_bf16(dout_, dout);
+  up_f32(dg, gamma);
+  up_f32(db, beta);
+  up_f32(drm, rm);
+  up_f32(drv, rv);
+  std::vector<float> hs(C, 0), hq(C, 0);
+  {
+    std::vector<double> s(C, 0), q(C, 0);
+    for (size_t i = 0; i < n; ++i) {
+      s[i % C] += y[i];
+      q[i % C] += (double)y[i] * y[i];
+    }
+    for (int c = 0; c < C; ++c) {
+      hs[c] = (float)s[c];
+      hq[c] = (float)q[c];
+    }
+  }
+  up_f32(sum, hs);
+  up_f32(sq, hq);
+  TK(tok_bn_finalize_train(C, (double)rows, (float*)sum.p, (float*)sq.p, (float*)dg.p, (float*)db.p, 1e-5f, 0.1f,
+                           (float*)drm.p, (float*)drv.p, (float*)sc.p, (float*)sh.p, (float*)sm.p, (float*)si.p,
+                           nullptr));
+  TK(tok_bn_apply(rows, C, dy_.p, (float*)sc.p, (float*)sh.p, dres.p, 1, o.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  snprintf(name, sizeof(name), "bn_apply(+res+relu) rows=%lld C=%d", rows, C);
+  auto out = down_bf16(o, n);
+  compare(name, out, ref, 0.03, 0.01);
+  std::vector<double> rrm(C), rrv(C);
+  for (int c = 0; c < C; ++c) {
+    rrm[c] = 0.9 * rm[c] + 0.1 * mean[c];
+    rrv[c] = 0.9 * rv[c] + 0.1 * var[c] * rows / (rows - 1.0);
+  }
+  compare("  running_mean", down_f32(drm, C), rrm, 1e-4, 1e-3);
+  compare("  running_var", down_f32(drv, C), rrv, 1e-4, 1e-3);
+
+  // backward reference (uses the device's own bf16 output as the ReLU mask, like the real pipeline)
+  std::vector<double> sg(C, 0), sgx(C, 0), g(n);
+  for (size_t i = 0; i < n; ++i) {
+    const int c = i % C;
+    g[i] = out[i] > 0 ? dout[i] : 0.0;
+    sg[c] += g[i];
+    sgx[c] += g[i] * (y[i] - mean[c]) / sqrt(var[c] + eps);
+  }
+  std::vector<double> rdy(n);
+  for (size_t i = 0; i < n; ++i) {
+    const int c = i % C;
+    const double is = 1.0 / sqrt(var[c] + eps), xh = (y[i] - mean[c]) * is;
+    rdy[i] = gamma[c] * is * (g[i] - sg[c] / rows - xh * sgx[c] / rows);
+  }
+  DevBuf sg_(C * 4), sgy_(C * 4), ca(C * 4), c1(C * 4), c0(C * 4), dgam(C * 4), dbet(C * 4), ddy(n * 2), dr(n * 2);
+  TK(tok_bn_bwd_reduce(rows, C, dout_.p, nullptr, o.p, dy_.p, (float*)sg_.p, (float*)sgy_.p, nullptr));
+  TK(tok_bn_bwd_finalize(C, (double)rows, (float*)sg_.p, (float*)sgy_.p, (float*)sm.p, (float*)si.p, (float*)dg.p,
+                         (float*)ca.p, (float*)c1.p, (float*)c0.p, (float*)dgam.p, (float*)dbet.p, 0, nullptr));
+  TK(tok_bn_bwd_apply(rows, C, dout_.p, nullptr, o.p, dy_.p, (float*)ca.p, (float*)c1.p, (float*)c0.p, ddy.p, dr.p,
+                      nullptr));
+  CK(cudaDeviceSynchronize());
+  snprintf(name, sizeof(name), "bn_bwd dy rows=%lld C=%d", rows, C);
+  compare(name, down_bf16(ddy, n), rdy, 0.02, 0.02);
+  compare("  dgamma", down_f32(dgam, C), sgx, 2e-2, 5e-3);
+  compare("  dbeta", down_f32(dbet, C), sg, 2e-2, 5e-3);
+  compare("  dres (masked grad)", down_bf16(dr, n), g, 1e-6, 0);
+}
+
+static void test_pool(int n, int h, int w, int c) {
+  char name[128];
+  auto x = rnd((size_t)n * h * w * c);
+  // plant ties (ReLU-style zeros)
+  for (size_t i = 0; i < x.size(); i += 3) x[i] = 0.f;
+  const int P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
+  const size_t no = (size_t)n * P * Q * c;
+  auto g = rnd(no);
+  DevBuf dx(x.size() * 2), o(no * 2), arg(no), dg(no * 2), ddx(x.size() * 2);
+  up_bf16(dx, x);
+  up_bf16(dg, g);
+  TK(tok_maxpool_fwd(n, h, w, c, 3, 2, 1, dx.p, o.p, arg.p, nullptr));
+  TK(tok_maxpool_bwd(n, h, w, c, 3, 2, 1, dg.p, arg.p, ddx.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> ref(no), rdx(x.size(), 0.0);
+  for (int a = 0; a < n; ++a)
+    for (int p = 0; p < P; ++p)
+      for (int q = 0; q < Q; ++q)
+        for (int ch = 0; ch < c; ++ch) {
+          double best = -INFINITY;
+          size_t bi = 0;
+          for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+              const int hh = 2 * p - 1 + r, ww = 2 * q - 1 + s;
+              if (hh < 0 || hh >= h || ww < 0 || ww >= w) continue;
+              const size_t idx = (((size_t)a * h + hh) * w + ww) * c + ch;
+              if (x[idx] > best) {
+                best = x[idx];
+                bi = idx;
+              }
+            }
+          const size_t oi = (((size_t)a * P + p) * Q + q) * c + ch;
+          ref[oi] = best;
+          rdx[bi] += g[oi];
+        }
+  snprintf(name, sizeof(name), "maxpool3x3s2 fwd n%d %dx%d c%d", n, h, w, c);
+  compare(name, down_bf16(o, no), ref, 0, 0);
+  compare("  maxpool bwd (first-max tie rule)", down_bf16(ddx, x.size()), rdx, 0.02, 0.01);
+
+  // global average pool
+  const int HW = h * w;
+  DevBuf go((size_t)n * c * 2), gdx(x.size() * 2);
+  TK(tok_gap_fwd(n, HW, c, 0, dx.p, go.p, nullptr));
+  auto gg = rnd((size_t)n * c);
+  DevBuf dgg(gg.size() * 2);
+  up_bf16(dgg, gg);
+  TK(tok_gap_bwd(n, HW, c, dgg.p, gdx.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> gref((size_t)n * c, 0.0), gdref(x.size());
+  for (int a = 0; a < n; ++a)
+    for (int i = 0; i < HW; ++i)
+      for (int ch = 0; ch < c; ++ch) {
+        gref[(size_t)a * c + ch] += x[((size_t)a * HW + i) * c + ch] / (double)HW;
+        gdref[((size_t)a * HW + i) * c + ch] = gg[(size_t)a * c + ch] / (double)HW;
+      }
+  compare("gap fwd", down_bf16(go, (size_t)n * c), gref, 0.01, 0.01);
+  compare("gap bwd", down_bf16(gdx, x.size()), gdref, 1e-3, 0.01);
+}
+
+static void test_xent(int rows, int C) {
+  auto lg = rnd((size_t)rows * C, 4.f);
+  std::vector<long long> tgt(rows);
+  for (int i = 0; i < rows; ++i) tgt[i] = (long long)(fabsf(frand()) * (C - 1));
+  tgt[1] = -100;  // ignored row
+  DevBuf dl(lg.size() * 2), dt(rows * 8), loss(4), dd(lg.size() * 2), corr(4);
+  up_bf16(dl, lg);
+  CK(cudaMemcpy(dt.p, tgt.data(), rows * 8, cudaMemcpyHostToDevice));
+  const int valid = rows - 1;
+  TK(tok_softmax_xent(rows, C, C, dl.p, (const long long*)dt.p, (float*)loss.p, dd.p, 1.f / valid, 1.f / valid, -100,
+                      (int*)corr.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  double rl = 0;
+  std::vector<double> rd(lg.size(), 0.0);
+  int rcorr = 0;
+  for (int i = 0; i < rows; ++i) {
+    if (tgt[i] < 0) continue;
+    double mx = -1e30;
+    int am = 0;
+    for (int c = 0; c < C; ++c)
+      if (lg[(size_t)i * C + c] > mx) {
+        mx = lg[(size_t)i * C + c];
+        am = c;
+      }
+    double se = 0;
+    for (int c = 0; c < C; ++c) se += exp(lg[(size_t)i * C + c] - mx);
+    rl += (log(se) + mx - lg[(size_t)i * C + tgt[i]]) / valid;
+    for (int c = 0; c < C; ++c)
+      rd[(size_t)i * C + c] = (exp(lg[(size_t)i * C + c] - mx) / se - (c == tgt[i] ? 1.0 : 0.0)) / valid;
+    rcorr += am == tgt[i];
+  }
+  compare("softmax_xent loss", down_f32(loss, 1), std::vector<double>{rl}, 1e-3, 1e-3);
+  compare("softmax_xent dlogits", down_bf16(dd, lg.size()), rd, 1e-4, 0.01);
+  int hc = 0;
+  CK(cudaMemcpy(&hc, corr.p, 4, cudaMemcpyDeviceToHost));
+  printf("[%s] softmax_xent correct count got=%d ref=%d\n", hc == rcorr ? "PASS" : "FAIL", hc, rcorr);
+  if (hc != rcorr) g_fail++;
+}
+
+static void test_layout(int n, int c, int h, int w) {
+  const int hw = h * w, cp = (c + 7) / 8 * 8;
+  std::vector<float> src((size_t)n * c * hw);
+  for (auto& v : src) v = bf(frand());
+  DevBuf ds(src.size() * 4), dn((size_t)n * hw * cp * 2), back(src.size() * 4);
+  up_f32(ds, src);
+  TK(tok_nchw_to_nhwc(n, c, hw, cp, 0, ds.p, dn.p, nullptr));
+  TK(tok_nhwc_to_nchw(n, c, hw, cp, 0, dn.p, back.p, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> ref((size_t)n * hw * cp, 0.0);
+  for (int a = 0; a < n; ++a)
+    for (int ch = 0; ch < c; ++ch)
+      for (int i = 0; i < hw; ++i) ref[((size_t)a * hw + i) * cp + ch] = src[((size_t)a * c + ch) * hw + i];
+  compare("nchw->nhwc (padded C)", down_bf16(dn, ref.size()), ref, 0, 0);
+  std::vector<double> r2(src.begin(), src.end());
+  compare("nhwc->nchw round trip", down_f32(back, src.size()), r2, 0, 0);
+}
+
+static void test_optim(long long n) {
+  std::vector<float> p(n), g(n), m(n), v(n);
+  for (long long i = 0; i < n; ++i) {
+    p[i] = frand();
+    g[i] = frand();
+    m[i] = frand() * 0.1f;
+    v[i] = fabsf(frand()) * 0.01f;
+  }
+  DevBuf dp(n * 4), dg(n * 4), dm(n * 4), dv(n * 4), sh(n * 2);
+  up_f32(dp, p);
+  up_f32(dg, g);
+  up_f32(dm, m);
+  TK(tok_sgd_step(n, (float*)dp.p, (float*)dg.p, (float*)dm.p, sh.p, 0.1f, 0.9f, 1e-4f, 0.f, 1, 1.f, 0, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> rp(n);
+  for (long long i = 0; i < n; ++i) {
+    const double d = g[i] + 1e-4 * p[i], b = 0.9 * m[i] + d;
+    rp[i] = p[i] - 0.1 * (d + 0.9 * b);
+  }
+  compare("sgd nesterov step", down_f32(dp, n), rp, 1e-6, 1e-5);
+  compare("  bf16 shadow", down_bf16(sh, n), rp, 1e-6, 8e-3);
+  up_f32(dp, p);
+  up_f32(dm, m);
+  up_f32(dv, v);
+  TK(tok_adam_step(n, (float*)dp.p, (float*)dg.p, (float*)dm.p, (float*)dv.p, sh.p, 1e-3f, 0.9f, 0.999f, 1e-8f, 1e-2f, 0,
+                   3, 1.f, nullptr));
+  CK(cudaDeviceSynchronize());
+  for (long long i = 0; i < n; ++i) {
+    const double d = g[i] + 1e-2 * p[i];
+    const double mi = 0.9 * m[i] + 0.1 * d, vi = 0.999 * v[i] + 0.001 * d * d;
+    const double bc1 = 1 - pow(0.9, 3), bc2 = 1 - pow(0.999, 3);
+    rp[i] = p[i] - 1e-3 / bc1 * mi / (sqrt(vi) / sqrt(bc2) + 1e-8);
+  }
+  compare("adam step", down_f32(dp, n), rp, 1e-6, 1e-4);
+}
+
+// ---- perf -------------------------------------------------------------------------------------------------------
+static void perf_conv(const char* tag, const Conv& cv, int iters) {
+  const int P = cv.P(), Q = cv.Q();
+  const size_t M = (size_t)cv.n * P * Q, nx = (size_t)cv.n * cv.h * cv.w * cv.c;
+  const size_t nw = (size_t)cv.k * cv.r * cv.s * cv.c;
+  DevBuf dx(nx * 2), dw(nw * 2), dy(M * cv.k * 2), dsum(cv.k * 4), dsq(cv.k * 4), ddx(nx * 2), ddw(nw * 4);
+  tokConvDesc d = cv.desc();
+  DevBuf ws(tok_conv_dgrad_workspace_bytes(&d));
+  {  // non-trivial data so that power draw is realistic
+    std::vector<__nv_bfloat16> t(std::max(nx, std::max(nw, M * cv.k)));
+    for (auto& v : t) v = __float2bfloat16(frand());
+    CK(cudaMemcpy(dx.p, t.data(), nx * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw.p, t.data(), nw * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dy.p, t.data(), M * cv.k * 2, cudaMemcpyHostToDevice));
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const double flop = 2.0 * M * cv.k * cv.r * cv.s * cv.c;
+  float ms[3] = {0, 0, 0};
+  for (int which = 0; which < 3; ++which) {
+    for (int it = -2; it < iters; ++it) {
+      if (it == 0) CK(cudaEventRecord(e0));
+      if (which == 0) TK(tok_conv_fprop(&d, dx.p, dw.p, dy.p, (float*)dsum.p, (float*)dsq.p, nullptr, nullptr, 0, nullptr));
+      if (which == 1) TK(tok_conv_dgrad(&d, dy.p, dw.p, ddx.p, nullptr, ws.p, nullptr));
+      if (which == 2) TK(tok_conv_wgrad(&d, dx.p, dy.p, (float*)ddw.p, nullptr));
+    }
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms[which], e0, e1));
+    ms[which] /= iters;
+  }
+  printf("PERF %-28s M=%zu K=%d N=%d | fprop %.3f ms %.0f TF/s | dgrad %.3f ms %.0f TF/s | wgrad %.3f ms %.0f TF/s\n",
+         tag, M, cv.r * cv.s * cv.c, cv.k, ms[0], flop / ms[0] * 1e-9, ms[1], flop / ms[1] * 1e-9, ms[2],
+         flop / ms[2] * 1e-9);
+  fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+  const std::string grp = argc > 1 ? argv[1] : "all";
+  if (tok_device_ok() != 0) {
+    printf("device check failed: %s\n", tok_last_error());
+    return 3;
+  }
+  if (grp == "gemm" || grp == "all") {
+    test_linear(128, 64, 64);
+    test_linear(128, 128, 128);
+    test_linear(300, 136, 192);
+    test_linear(256, 1000, 2048);
+  }
+  if (grp == "conv" || grp == "all") {
+    test_fprop(Conv{2, 9, 9, 64, 72, 1, 1, 1, 0, 1}, false);
+    test_fprop(Conv{3, 10, 10, 64, 64, 3, 3, 1, 1, 1}, false);
+    test_fprop(Conv{3, 10, 10, 64, 64, 3, 3, 1, 1, 1}, true);
+    test_fprop(Conv{2, 12, 12, 128, 136, 3, 3, 2, 1, 1}, false);
+    test_fprop(Conv{2, 12, 12, 64, 64, 1, 1, 2, 0, 1}, false);
+    test_fprop(Conv{2, 14, 14, 256, 256, 3, 3, 1, 1, 1}, false);
+    test_fprop(Conv{1, 7, 7, 72, 40, 3, 3, 1, 1, 1}, false);
+  }
+  if (grp == "dgrad" || grp == "all") {
+    test_dgrad(Conv{2, 9, 9, 64, 72, 1, 1, 1, 0, 1}, false);
+    test_dgrad(Conv{3, 10, 10, 64, 128, 3, 3, 1, 1, 1}, false);
+    test_dgrad(Conv{3, 10, 10, 128, 64, 3, 3, 1, 1, 1}, true);
+    test_dgrad(Conv{2, 12, 12, 64, 64, 1, 1, 2, 0, 1}, false);
+    test_dgrad(Conv{2, 12, 12, 64, 64, 1, 1, 2, 0, 1}, true);
+    test_dgrad(Conv{2, 12, 12, 128, 136, 3, 3, 2, 1, 1}, false);
+  }
+  if (grp == "wgrad" || grp == "all") {
+    test_wgrad(Conv{2, 9, 9, 64, 72, 1, 1, 1, 0, 1});
+    test_wgrad(Conv{3, 10, 10, 64, 64, 3, 3, 1, 1, 1});
+    test_wgrad(Conv{2, 12, 12, 128, 136, 3, 3, 2, 1, 1});
+    test_wgrad(Conv{2, 12, 12, 64, 64, 1, 1, 2, 0, 1});
+    test_wgrad(Conv{4, 28, 28, 128, 128, 3, 3, 1, 1, 1});
+  }
+  if (grp == "stem" || grp == "all") {
+    test_stem(2, 32, 32, 3, 64);
+    test_stem(1, 30, 22, 1, 64);
+  }
+  if (grp == "elem" || grp == "all") {
+    test_bn(1000, 64);
+    test_bn(333, 2048);
+    test_bn(500, 72);
+    test_pool(2, 16, 16, 64);
+    test_pool(1, 9, 11, 8);
+    test_xent(16, 1000);
+    test_xent(7, 10);
+    test_layout(2, 3, 9, 7);
+    test_layout(2, 70, 5, 5);
+    test_optim(10007);
+  }
+  if (grp == "perf") {
+    const int it = 10;
+    perf_conv("l1 1x1 64->256 @56", Conv{256, 56, 56, 64, 256, 1, 1, 1, 0, 1}, it);
+    perf_conv("l1 1x1 256->64 @56", Conv{256, 56, 56, 256, 64, 1, 1, 1, 0, 1}, it);
+    perf_conv("l1 3x3 64->64 @56", Conv{256, 56, 56, 64, 64, 3, 3, 1, 1, 1}, it);
+    perf_conv("l2 3x3 128->128 @28", Conv{256, 28, 28, 128, 128, 3, 3, 1, 1, 1}, it);
+    perf_conv("l2 3x3s2 128->128 @56", Conv{256, 56, 56, 128, 128, 3, 3, 2, 1, 1}, it);
+    perf_conv("l3 3x3 256->256 @14", Conv{256, 14, 14, 256, 256, 3, 3, 1, 1, 1}, it);
+    perf_conv("l3 1x1 1024->256 @14", Conv{256, 14, 14, 1024, 256, 1, 1, 1, 0, 1}, it);
+    perf_conv("l3 1x1 256->1024 @14", Conv{256, 14, 14, 256, 1024, 1, 1, 1, 0, 1}, it);
+    perf_conv("l4 3x3 512->512 @7", Conv{256, 7, 7, 512, 512, 3, 3, 1, 1, 1}, it);
+    perf_conv("l4 1x1 512->2048 @7", Conv{256, 7, 7, 512, 2048, 1, 1, 1, 0, 1}, it);
+    perf_conv("ds 1x1s2 256->512 @56", Conv{256, 56, 56, 256, 512, 1, 1, 2, 0, 1}, it);
+  }
+  printf("SELFTEST %s: %s (%d failures)\n", grp.c_str(), g_fail ? "FAILED" : "OK", g_fail);
+  return g_fail ? 1 : 0;
+}

@@ -1,0 +1,429 @@
+// tok_api.cu — C ABI: argument checking, TMA tensor-map construction, kernel dispatch for the tensor-core ops.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/tokb200.h"
+#include "tok_conv.cuh"
+#include "tok_internal.h"
+
+namespace tok {
+cudaError_t launch_conv_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvFwdParams& p, int bn, bool b_mn,
+                            cudaStream_t st);
+cudaError_t launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const ConvWgradParams& p, int bn,
+                              int splits, cudaStream_t st);
+void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
+                        int sh, int sw, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ---- driver entry points (resolved lazily so the library loads on hosts without libcuda) -------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+
+static int resolve_driver() {
+  if (g_encode_tiled && g_encode_im2col) return TOK_OK;
+  void* f1 = nullptr;
+  void* f2 = nullptr;
+  cudaDriverEntryPointQueryResult q1, q2;
+  cudaError_t e1 = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q1);
+  cudaError_t e2 = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q2);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || !f1 || !f2) {
+    cudaGetLastError();
+    return set_error(TOK_ERR_NODRIVER, "cuTensorMapEncode* entry points unavailable (%s)",
+                     cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(f1);
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(f2);
+  return TOK_OK;
+}
+
+// 2-D bf16 matrix [rows][cols] with row pitch ld (elements); box = (64 cols, box_rows), 128-byte swizzle.
+int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  int rc = resolve_driver();
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15))
+    return set_error(TOK_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte multiple pitch (ld=%lld)", ld);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(TOK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+  return TOK_OK;
+}
+
+// NHWC bf16 tensor walked in im2col mode: `pixels` consecutive conv-output positions x 64 channels per load.
+// dims = (C, W, H, N) extents, strides = byte strides of W, H, N (explicit so that overlapping views are possible).
+int make_tmap_im2col_ex(CUtensorMap* tm, const void* base, const cuuint64_t dims[4], const cuuint64_t strides[3],
+                        const PixelSrc& s, int pixels) {
+  int rc = resolve_driver();
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+    return set_error(TOK_ERR_INVALID, "im2col TMA operand needs 16-byte aligned base and strides");
+  const int w = (int)dims[1], h = (int)dims[2];
+  int lower[2] = {-s.pad, -s.pad};
+  int upper[2] = {(-s.pad + (s.Q - 1) * s.stride) - (w - 1), (-s.pad + (s.P - 1) * s.stride) - (h - 1)};
+  for (int i = 0; i < 2; ++i)
+    if (lower[i] < -128 || lower[i] > 127 || upper[i] < -128 || upper[i] > 127)
+      return set_error(TOK_ERR_INVALID, "im2col corner out of range (lower %d upper %d)", lower[i], upper[i]);
+  cuuint32_t estr[4] = {1, (cuuint32_t)s.stride, (cuuint32_t)s.stride, 1};
+  CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                               upper, 64, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(TOK_ERR_CUDA,
+                     "cuTensorMapEncodeIm2col failed (%d) dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu lower=%d,%d "
+                     "upper=%d,%d stride=%d",
+                     (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                     (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+                     (unsigned long long)strides[2], lower[0], lower[1], upper[0], upper[1], s.stride);
+  return TOK_OK;
+}
+int make_tmap_im2col(CUtensorMap* tm, const void* base, int n, int h, int w, int c, const PixelSrc& s, int pixels) {
+  if ((c * 2) & 15) return set_error(TOK_ERR_INVALID, "im2col TMA operand needs C %% 8 == 0 (C=%d)", c);
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  return make_tmap_im2col_ex(tm, base, dims, strides, s, pixels);
+}
+
+static int check_desc(const tokConvDesc* d) {
+  if (!d) return set_error(TOK_ERR_INVALID, "null conv descriptor");
+  if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->c <= 0 || d->k <= 0 || d->r <= 0 || d->s <= 0 || d->stride <= 0 ||
+      d->dil <= 0 || d->pad < 0)
+    return set_error(TOK_ERR_INVALID, "bad conv descriptor");
+  if ((d->c % 8) || (d->k % 8)) return set_error(TOK_ERR_INVALID, "channel counts must be multiples of 8 (c=%d k=%d)", d->c, d->k);
+  return TOK_OK;
+}
+
+static int pick_bn(int n) { return n <= 64 ? 64 : 128; }
+
+// Generic "pixels x weights" launch used by fprop, dgrad and linear.
+static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long long M, const void* wmat,
+                      long long w_rows, long long w_cols, bool b_mn, int N, int flip, ConvFwdParams p,
+                      cudaStream_t st) {
+  CUtensorMap tmB;
+  const int bn = pick_bn(N);
+  int rc = make_tmap_2d(&tmB, wmat, w_rows, w_cols, w_cols, b_mn ? 64 : bn);
+  if (rc) return rc;
+  p.M = (int)M;
+  p.N = N;
+  p.Cin = ac;
+  p.a = src;
+  p.flip_taps = flip;
+  mn_desc_geometry(&p.mn_lbo, &p.mn_sbo, &p.mn_kadv);
+  cudaError_t e = launch_conv_fwd(tmA, tmB, p, bn, b_mn, st);
+  if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv_fwd launch: %s", cudaGetErrorString(e));
+  return TOK_OK;
+}
+static int run_fwd(const void* a, int an, int ah, int aw, int ac, const PixelSrc& src, long long M, const void* wmat,
+                   long long w_rows, long long w_cols, bool b_mn, int N, int flip, ConvFwdParams p, cudaStream_t st) {
+  CUtensorMap tmA;
+  int rc;
+  if (src.im2col)
+    rc = make_tmap_im2col(&tmA, a, an, ah, aw, ac, src, 128);
+  else
+    rc = make_tmap_2d(&tmA, a, M, ac, ac, 128);
+  if (rc) return rc;
+  return run_fwd_tm(tmA, ac, src, M, wmat, w_rows, w_cols, b_mn, N, flip, p, st);
+}
+
+static int pick_splits(long long tiles, int total_chunks, int* chunks_per_split) {
+  // Aim for ~2 waves of 2 CTAs/SM while keeping at least 8 K-blocks per CTA.
+  long long target = 148 * 4;
+  int splits = (int)((target + tiles - 1) / tiles);
+  int max_splits = (total_chunks + 7) / 8;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int cps = (total_chunks + splits - 1) / splits;
+  splits = (total_chunks + cps - 1) / cps;
+  *chunks_per_split = cps;
+  return splits;
+}
+
+static int run_wgrad_tm(const CUtensorMap& tmX, int xc, const PixelSrc& src, const void* dy, long long Mpix, int Cout,
+                        float* dw, cudaStream_t st) {
+  CUtensorMap tmDY;
+  int rc = make_tmap_2d(&tmDY, dy, Mpix, Cout, Cout, 64);
+  if (rc) return rc;
+  ConvWgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.Mpix = (int)Mpix;
+  p.Cout = Cout;
+  p.Cin = xc;
+  p.x = src;
+  p.dw = dw;
+  p.ldw = (long long)src.R * src.S * xc;
+  mn_desc_geometry(&p.mn_lbo, &p.mn_sbo, &p.mn_kadv);
+  const int bn = pick_bn(xc);
+  const long long tiles = (long long)src.R * src.S * ((Cout + 127) / 128) * ((xc + bn - 1) / bn);
+  const int total_chunks = (int)((Mpix + 63) / 64);
+  const int splits = pick_splits(tiles, total_chunks, &p.chunks_per_split);
+  cudaError_t e = launch_conv_wgrad(tmDY, tmX, p, bn, splits, st);
+  if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv_wgrad launch: %s", cudaGetErrorString(e));
+  return TOK_OK;
+}
+static int run_wgrad(const void* x, int xn, int xh, int xw, int xc, const PixelSrc& src, const void* dy, long long Mpix,
+                     int Cout, float* dw, cudaStream_t st) {
+  CUtensorMap tmX;
+  int rc;
+  if (src.im2col)
+    rc = make_tmap_im2col(&tmX, x, xn, xh, xw, xc, src, 64);
+  else
+    rc = make_tmap_2d(&tmX, x, Mpix, xc, xc, 64);
+  if (rc) return rc;
+  return run_wgrad_tm(tmX, xc, src, dy, Mpix, Cout, dw, st);
+}
+
+// ---- ResNet stem (7x7 stride 2 pad 3, <=4 input channels) on the 2x2 space-to-depth packed input ---------------
+// xs2d is [N][H2][W2][16]; four horizontally adjacent packed pixels are one 64-element im2col row, so the tensor map
+// is an OVERLAPPING view: dims (64, Q, H2, N) with a W stride of one packed pixel (32 bytes).
+static void stem_geom(int h, int w, int* P, int* Q, int* H2, int* W2) {
+  *P = (h + 6 - 7) / 2 + 1;
+  *Q = (w + 6 - 7) / 2 + 1;
+  *H2 = *P + 3;
+  *W2 = *Q + 3;
+}
+static int stem_tmap(CUtensorMap* tm, const void* xs2d, int n, int h, int w, PixelSrc* src, int pixels) {
+  int P, Q, H2, W2;
+  stem_geom(h, w, &P, &Q, &H2, &W2);
+  memset(src, 0, sizeof(*src));
+  src->im2col = 1;
+  src->P = P;
+  src->Q = Q;
+  src->stride = 1;
+  src->pad = 0;
+  src->dil = 1;
+  src->R = 4;
+  src->S = 1;
+  cuuint64_t dims[4] = {64, (cuuint64_t)Q, (cuuint64_t)H2, (cuuint64_t)n};
+  cuuint64_t strides[3] = {32, (cuuint64_t)W2 * 32, (cuuint64_t)H2 * W2 * 32};
+  return make_tmap_im2col_ex(tm, xs2d, dims, strides, *src, pixels);
+}
+
+static PixelSrc conv_src(const tokConvDesc* d, int P, int Q) {
+  PixelSrc s;
+  s.im2col = !(d->r == 1 && d->s == 1 && d->stride == 1 && d->pad == 0);
+  s.P = P;
+  s.Q = Q;
+  s.stride = d->stride;
+  s.pad = d->pad;
+  s.dil = d->dil;
+  s.R = d->r;
+  s.S = d->s;
+  return s;
+}
+
+}  // namespace tok
+
+using namespace tok;
+
+extern "C" {
+
+int tok_version(void) { return 1; }
+const char* tok_last_error(void) { return g_err; }
+
+int tok_device_ok(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_error(TOK_ERR_CUDA, "no CUDA device (%s)", cudaGetErrorString(e));
+  }
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return set_error(TOK_ERR_INVALID, "device compute capability %d.x is not sm_100", major);
+  return resolve_driver();
+}
+
+void tok_conv_out_hw(const tokConvDesc* d, int* p, int* q) {
+  *p = (d->h + 2 * d->pad - d->dil * (d->r - 1) - 1) / d->stride + 1;
+  *q = (d->w + 2 * d->pad - d->dil * (d->s - 1) - 1) / d->stride + 1;
+}
+
+int tok_conv_fprop(const tokConvDesc* d, const void* x, const void* w, void* y, float* sum, float* sqsum,
+                   const void* addend, const float* bias, int relu, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  int P, Q;
+  tok_conv_out_hw(d, &P, &Q);
+  if (P <= 0 || Q <= 0) return set_error(TOK_ERR_INVALID, "empty conv output");
+  if ((sum == nullptr) != (sqsum == nullptr)) return set_error(TOK_ERR_INVALID, "sum and sqsum must be given together");
+  PixelSrc src = conv_src(d, P, Q);
+  ConvFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = static_cast<__nv_bfloat16*>(y);
+  p.ldo = d->k;
+  p.addend = static_cast<const __nv_bfloat16*>(addend);
+  p.col_sum = sum;
+  p.col_sqsum = sqsum;
+  p.bias = bias;
+  p.relu = relu;
+  const long long M = (long long)d->n * P * Q;
+  return run_fwd(x, d->n, d->h, d->w, d->c, src, M, w, d->k, (long long)d->r * d->s * d->c, false, d->k, 0, p,
+                 static_cast<cudaStream_t>(stream));
+}
+
+size_t tok_conv_dgrad_workspace_bytes(const tokConvDesc* d) {
+  if (!d) return 0;
+  if (d->stride > 1 && !(d->r == 1 && d->s == 1)) return (size_t)d->n * d->h * d->w * d->k * 2;
+  return 0;
+}
+
+int tok_conv_dgrad(const tokConvDesc* d, const void* dy, const void* w, void* dx, const void* addend, void* ws,
+                   void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  int P, Q;
+  tok_conv_out_hw(d, &P, &Q);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = static_cast<__nv_bfloat16*>(dx);
+  p.ldo = d->c;
+  p.addend = static_cast<const __nv_bfloat16*>(addend);
+  const long long wcols = (long long)d->r * d->s * d->c;
+  if (d->r == 1 && d->s == 1) {
+    if (d->pad != 0) return set_error(TOK_ERR_INVALID, "1x1 conv with padding is not supported");
+    PixelSrc src;
+    memset(&src, 0, sizeof(src));
+    src.R = src.S = 1;
+    src.stride = 1;
+    src.dil = 1;
+    if (d->stride > 1) {
+      // GEMM over the P*Q output pixels, rows scattered to the (stride*p, stride*q) positions of dx.
+      if (addend != dx) {
+        cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->c * 2, st);
+        if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+        if (addend != nullptr) return set_error(TOK_ERR_INVALID, "strided 1x1 dgrad: addend must be NULL or alias dx");
+      }
+      p.scatter = 1;
+      p.sc_P = P;
+      p.sc_Q = Q;
+      p.sc_H = d->h;
+      p.sc_W = d->w;
+      p.sc_sh = d->stride;
+      p.sc_sw = d->stride;
+    }
+    return run_fwd(dy, d->n, P, Q, d->k, src, (long long)d->n * P * Q, w, d->k, wcols, true, d->c, 0, p, st);
+  }
+  // RxS filter: stride-1 correlation of (zero-dilated) dy with the flipped filter.
+  const int pad_h = (d->r - 1) * d->dil - d->pad;
+  const int pad_w = (d->s - 1) * d->dil - d->pad;
+  if (pad_h != pad_w || pad_h < 0) return set_error(TOK_ERR_INVALID, "unsupported padding for dgrad");
+  const void* src_ptr = dy;
+  int sh = P, sw = Q;
+  if (d->stride > 1) {
+    if (!ws) return set_error(TOK_ERR_INVALID, "dgrad workspace required");
+    cudaError_t e = cudaMemsetAsync(ws, 0, tok_conv_dgrad_workspace_bytes(d), st);
+    if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    launch_dilate_rows(static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(ws), d->n, P, Q, d->k, d->h,
+                       d->w, d->stride, d->stride, st);
+    src_ptr = ws;
+    sh = d->h;
+    sw = d->w;
+  }
+  PixelSrc src;
+  src.im2col = 1;
+  src.P = d->h;
+  src.Q = d->w;
+  src.stride = 1;
+  src.pad = pad_h;
+  src.dil = d->dil;
+  src.R = d->r;
+  src.S = d->s;
+  return run_fwd(src_ptr, d->n, sh, sw, d->k, src, (long long)d->n * d->h * d->w, w, d->k, wcols, true, d->c, 1, p, st);
+}
+
+int tok_conv_wgrad(const tokConvDesc* d, const void* x, const void* dy, float* dw, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  int P, Q;
+  tok_conv_out_hw(d, &P, &Q);
+  PixelSrc src = conv_src(d, P, Q);
+  return run_wgrad(x, d->n, d->h, d->w, d->c, src, dy, (long long)d->n * P * Q, d->k, dw,
+                   static_cast<cudaStream_t>(stream));
+}
+
+static PixelSrc flat_src() {
+  PixelSrc s;
+  memset(&s, 0, sizeof(s));
+  s.R = s.S = 1;
+  s.stride = 1;
+  s.dil = 1;
+  return s;
+}
+
+void tok_stem_geometry(int h, int w, int* p, int* q, int* h2, int* w2) { stem_geom(h, w, p, q, h2, w2); }
+
+int tok_stem_conv_fprop(int n, int h, int w, int k, const void* xs2d, const void* wp, void* y, float* sum,
+                        float* sqsum, void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || k <= 0 || (k % 8)) return set_error(TOK_ERR_INVALID, "stem: bad shape");
+  CUtensorMap tmA;
+  PixelSrc src;
+  int rc = stem_tmap(&tmA, xs2d, n, h, w, &src, 128);
+  if (rc) return rc;
+  ConvFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = static_cast<__nv_bfloat16*>(y);
+  p.ldo = k;
+  p.col_sum = sum;
+  p.col_sqsum = sqsum;
+  return run_fwd_tm(tmA, 64, src, (long long)n * src.P * src.Q, wp, k, 256, false, k, 0, p,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int tok_stem_conv_wgrad(int n, int h, int w, int k, const void* xs2d, const void* dy, float* dwp, void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || k <= 0 || (k % 8)) return set_error(TOK_ERR_INVALID, "stem: bad shape");
+  CUtensorMap tmX;
+  PixelSrc src;
+  int rc = stem_tmap(&tmX, xs2d, n, h, w, &src, 64);
+  if (rc) return rc;
+  return run_wgrad_tm(tmX, 64, src, dy, (long long)n * src.P * src.Q, k, dwp, static_cast<cudaStream_t>(stream));
+}
+
+int tok_linear_fwd(int m, int n, int k, const void* x, const void* w, const float* bias, void* y, void* stream) {
+  if (m <= 0 || n <= 0 || k <= 0 || (n % 8) || (k % 8)) return set_error(TOK_ERR_INVALID, "linear: n and k must be positive multiples of 8");
+  ConvFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = static_cast<__nv_bfloat16*>(y);
+  p.ldo = n;
+  p.bias = bias;
+  return run_fwd(x, 1, 1, m, k, flat_src(), m, w, n, k, false, n, 0, p, static_cast<cudaStream_t>(stream));
+}
+
+int tok_linear_dgrad(int m, int n, int k, const void* dy, const void* w, void* dx, void* stream) {
+  if (m <= 0 || n <= 0 || k <= 0 || (n % 8) || (k % 8)) return set_error(TOK_ERR_INVALID, "linear: n and k must be positive multiples of 8");
+  ConvFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = static_cast<__nv_bfloat16*>(dx);
+  p.ldo = k;
+  return run_fwd(dy, 1, 1, m, n, flat_src(), m, w, n, k, true, k, 0, p, static_cast<cudaStream_t>(stream));
+}
+
+int tok_linear_wgrad(int m, int n, int k, const void* x, const void* dy, float* dw, void* stream) {
+  if (m <= 0 || n <= 0 || k <= 0 || (n % 8) || (k % 8)) return set_error(TOK_ERR_INVALID, "linear: n and k must be positive multiples of 8");
+  return run_wgrad(x, 1, 1, m, k, flat_src(), dy, m, n, dw, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

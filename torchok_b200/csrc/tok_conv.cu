@@ -1,0 +1,432 @@
+// tok_conv.cu — im2col-free implicit-GEMM convolution for sm_100a.
+//
+//   conv_fwd_kernel   : forward and data-gradient.  Pixels are GEMM rows (M), output channels are GEMM columns (N),
+//                       the reduction runs over (filter tap, input-channel block).  A tiles arrive by TMA im2col
+//                       (or plain 2-D TMA for 1x1/linear), B tiles by 2-D TMA from the [Cout][R*S*Cin] weight
+//                       matrix, tcgen05.mma accumulates into TMEM, 4 epilogue warps drain TMEM -> bf16 -> HBM and
+//                       produce the BatchNorm batch statistics (sum, sum of squares per channel) on the way out.
+//   conv_wgrad_kernel : weight gradient.  Output channels are GEMM rows, input channels GEMM columns, pixels are the
+//                       reduction; both operands are "MN-major" views of the same NHWC tiles.  Split-K over pixels,
+//                       fp32 reductions into the [Cout][R*S*Cin] gradient.
+//
+// Reference call sites this replaces (all torch.nn.Conv2d dispatches): torchok/models/modules/bricks/convbnact.py:38-53,
+// torchok/models/backbones/resnet.py:480-510 and the timm BasicBlock/Bottleneck convs built in resnet.py:363-405.
+#include <stdlib.h>
+
+#include "tok_conv.cuh"
+#include "tok_ptx.cuh"
+
+namespace tok {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATile = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kNumThreads = 192;               // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
+
+__device__ __forceinline__ void pixel_coords(const PixelSrc& s, int m, int& w, int& h, int& n) {
+  const int pq = s.P * s.Q;
+  n = m / pq;
+  const int rem = m - n * pq;
+  const int p = rem / s.Q;
+  const int q = rem - p * s.Q;
+  w = q * s.stride - s.pad;
+  h = p * s.stride - s.pad;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const ConvFwdParams p) {
+  constexpr int kBTile = BN * kBlockK * 2;
+  constexpr int kStage = kATile + kBTile;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStage);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_sum = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_sq = s_sum + BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int n_t = blockIdx.x % n_tiles;
+  const int m_t = blockIdx.x / n_tiles;
+  const int m0 = m_t * kBlockM;
+  const int n0 = n_t * BN;
+  const int cin_chunks = (p.Cin + kBlockK - 1) / kBlockK;
+  const int taps = p.a.R * p.a.S;
+  const int num_kb = taps * cin_chunks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) s_sum[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int w0 = 0, h0 = 0, img = 0;
+      if (p.a.im2col) pixel_coords(p.a, m0, w0, h0, img);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStage;
+        uint8_t* sb = sa + kATile;
+        mbar_arrive_expect_tx(&full_bar[stage], kStage);
+        const int tap = kb / cin_chunks;
+        const int kc = (kb - tap * cin_chunks) * kBlockK;
+        if (p.a.im2col) {
+          const int r = tap / p.a.S;
+          const int s = tap - r * p.a.S;
+          tma_load_im2col_4d(&tmA, &full_bar[stage], sa, kc, w0, h0, img, static_cast<uint16_t>(s * p.a.dil),
+                             static_cast<uint16_t>(r * p.a.dil));
+        } else {
+          tma_load_2d(&tmA, &full_bar[stage], sa, kc, m0);
+        }
+        const int wtap = p.flip_taps ? (taps - 1 - tap) : tap;
+        if (!B_MN) {
+          // weight matrix seen as [N rows][taps*Cin] : K-major B tile
+          tma_load_2d(&tmB, &full_bar[stage], sb, wtap * p.Cin + kc, n0);
+        } else {
+          // weight matrix seen as [K rows = reduction channel][taps*N] : MN-major B tile, 64-column chunks
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, wtap * p.N + n0 + j * 64, kc);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * kStage);
+        const uint32_t b_addr = a_addr + kATile;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * p.mn_kadv, p.mn_lbo, p.mn_sbo)
+                                      : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: TMEM -> regs -> bf16 -> HBM (+stats)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    long long out_row = m;
+    if (p.scatter && row_ok) {
+      const int pq = p.sc_P * p.sc_Q;
+      const int img = m / pq;
+      const int rem = m - img * pq;
+      const int pp = rem / p.sc_Q;
+      const int qq = rem - pp * p.sc_Q;
+      out_row = (static_cast<long long>(img) * p.sc_H + static_cast<long long>(pp) * p.sc_sh) * p.sc_W +
+                static_cast<long long>(qq) * p.sc_sw;
+    }
+    const bool want_stats = p.col_sum != nullptr;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) continue;  // warp-uniform
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+      }
+      const long long off = out_row * p.ldo + col0;
+      if (p.addend != nullptr && row_ok) {
+        const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (col0 + g * 8 < p.N) {
+            const uint4 a = __ldg(ap + g);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[g * 8 + 2 * e] += bf16_lo(aw[e]);
+              v[g * 8 + 2 * e + 1] += bf16_hi(aw[e]);
+            }
+          }
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      if (row_ok) {
+        uint4* op = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (col0 + g * 8 < p.N) op[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+      }
+      if (want_stats) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float lo = row_ok ? bf16_lo(packed[j]) : 0.f;
+          const float hi = row_ok ? bf16_hi(packed[j]) : 0.f;
+          s1[2 * j] = lo;
+          s1[2 * j + 1] = hi;
+          s2[2 * j] = lo * lo;
+          s2[2 * j + 1] = hi * hi;
+        }
+        const float t1 = warp_transpose_reduce32(s1, lane);
+        const float t2 = warp_transpose_reduce32(s2, lane);
+        atomicAdd(&s_sum[c * 32 + lane], t1);
+        atomicAdd(&s_sq[c * 32 + lane], t2);
+      }
+    }
+    tc_fence_before();
+    if (want_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < BN; i += 128) {
+        if (n0 + i < p.N) {
+          atomicAdd(p.col_sum + n0 + i, s_sum[i]);
+          atomicAdd(p.col_sqsum + n0 + i, s_sq[i]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// grid.x = tap + taps * (n_tile + n_tiles * m_tile), grid.y = split index over 64-pixel K blocks.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const ConvWgradParams p) {
+  constexpr int kBTile = BN * kBlockK * 2;
+  constexpr int kStage = kATile + kBTile;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStage);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = p.x.R * p.x.S;
+  const int n_tiles = (p.Cin + BN - 1) / BN;
+  int t = blockIdx.x;
+  const int tap = t % taps;
+  t /= taps;
+  const int n_t = t % n_tiles;
+  const int m_t = t / n_tiles;
+  const int m0 = m_t * kBlockM;  // output-channel offset
+  const int n0 = n_t * BN;       // input-channel offset
+  const int total_chunks = (p.Mpix + kBlockK - 1) / kBlockK;
+  const int kb_begin = blockIdx.y * p.chunks_per_split;
+  const int kb_end = min(kb_begin + p.chunks_per_split, total_chunks);
+  const int num_kb = kb_end - kb_begin;
+  if (num_kb <= 0) return;  // uniform for the whole CTA; nothing allocated yet
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const int r = tap / p.x.S;
+      const int s = tap - r * p.x.S;
+      for (int i = 0; i < num_kb; ++i) {
+        const int stage = i % STAGES;
+        const uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStage;
+        uint8_t* sb = sa + kATile;
+        mbar_arrive_expect_tx(&full_bar[stage], kStage);
+        const int pix0 = (kb_begin + i) * kBlockK;
+        tma_load_2d(&tmDY, &full_bar[stage], sa, m0, pix0);
+        tma_load_2d(&tmDY, &full_bar[stage], sa + 8192, m0 + 64, pix0);
+        if (p.x.im2col) {
+          int w0, h0, img;
+          pixel_coords(p.x, pix0, w0, h0, img);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_im2col_4d(&tmX, &full_bar[stage], sb + j * 8192, n0 + j * 64, w0, h0, img,
+                               static_cast<uint16_t>(s * p.x.dil), static_cast<uint16_t>(r * p.x.dil));
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmX, &full_bar[stage], sb + j * 8192, n0 + j * 64, pix0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, true, true);
+      for (int i = 0; i < num_kb; ++i) {
+        const int stage = i % STAGES;
+        const uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * kStage);
+        const uint32_t b_addr = a_addr + kATile;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t adesc = make_smem_desc_sw128(a_addr + k * p.mn_kadv, p.mn_lbo, p.mn_sbo);
+          const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * p.mn_kadv, p.mn_lbo, p.mn_sbo);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (co < p.Cout) {
+        float* dst = p.dw + static_cast<long long>(co) * p.ldw + static_cast<long long>(tap) * p.Cin + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.Cin) atomicAdd(dst + j, __uint_as_float(r[j]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Host side
+void mn_desc_geometry(int* lbo, int* sbo, int* kadv) {
+  static int v[3] = {-1, -1, -1};
+  if (v[0] < 0) {
+    const char* e;
+    v[0] = (e = getenv("TOK_MN_LBO")) ? atoi(e) : 8192;
+    v[1] = (e = getenv("TOK_MN_SBO")) ? atoi(e) : 1024;
+    v[2] = (e = getenv("TOK_MN_KADV")) ? atoi(e) : 2048;
+  }
+  *lbo = v[0];
+  *sbo = v[1];
+  *kadv = v[2];
+}
+template <int BN, int STAGES>
+constexpr int conv_smem_bytes() {
+  return STAGES * (kATile + BN * kBlockK * 2) + (2 * STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
+}
+
+template <int BN, int STAGES, bool B_MN>
+static cudaError_t launch_fwd_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvFwdParams& p,
+                                cudaStream_t st) {
+  constexpr int smem = conv_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<BN, STAGES, B_MN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  conv_fwd_kernel<BN, STAGES, B_MN><<<m_tiles * n_tiles, kNumThreads, smem, st>>>(tmA, tmB, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvFwdParams& p, int bn,
+                            bool b_mn, cudaStream_t st) {
+  if (bn == 64) return b_mn ? launch_fwd_t<64, 4, true>(tmA, tmB, p, st) : launch_fwd_t<64, 4, false>(tmA, tmB, p, st);
+  if (bn == 128)
+    return b_mn ? launch_fwd_t<128, 3, true>(tmA, tmB, p, st) : launch_fwd_t<128, 3, false>(tmA, tmB, p, st);
+  return cudaErrorInvalidValue;
+}
+
+template <int BN, int STAGES>
+static cudaError_t launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const ConvWgradParams& p,
+                                  int splits, cudaStream_t st) {
+  constexpr int smem = conv_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(conv_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int taps = p.x.R * p.x.S;
+  const int m_tiles = (p.Cout + kBlockM - 1) / kBlockM;
+  const int n_tiles = (p.Cin + BN - 1) / BN;
+  dim3 grid(taps * m_tiles * n_tiles, splits);
+  conv_wgrad_kernel<BN, STAGES><<<grid, kNumThreads, smem, st>>>(tmDY, tmX, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const ConvWgradParams& p, int bn,
+                              int splits, cudaStream_t st) {
+  if (bn == 64) return launch_wgrad_t<64, 4>(tmDY, tmX, p, splits, st);
+  if (bn == 128) return launch_wgrad_t<128, 3>(tmDY, tmX, p, splits, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace tok

@@ -1,0 +1,56 @@
+// tok_conv.cuh — parameter blocks shared by the tcgen05 implicit-GEMM kernels and their host launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tok {
+
+// How the pixel operand (activations / output gradients, NHWC bf16) is fetched by TMA.
+struct PixelSrc {
+  int im2col;   // 0: plain 2-D tile of a [rows][C] matrix, 1: TMA im2col walk over an NHWC tensor
+  int P, Q;     // conv output spatial size (rows of the GEMM are (n, p, q) flattened)
+  int stride;   // traversal stride
+  int pad;      // lower padding (the lower corner is -pad)
+  int dil;      // dilation
+  int R, S;     // filter taps
+};
+
+// Forward / data-gradient implicit GEMM:  out[m, n] = sum_{tap, c} A_tap[m, c] * Wmat[n, wtap*Cin + c]
+struct ConvFwdParams {
+  int M;        // GEMM rows = N_img * P * Q
+  int N;        // GEMM cols = output channels
+  int Cin;      // channels per tap
+  PixelSrc a;
+  int flip_taps;  // dgrad: weight tap index = R*S-1-tap
+  // epilogue
+  __nv_bfloat16* out;
+  long long ldo;              // elements between consecutive output rows
+  const __nv_bfloat16* addend;  // optional, read at the same (row, col) as out before the store
+  float* col_sum;             // optional per-column sum of the *stored* (bf16-rounded) values
+  float* col_sqsum;           // optional per-column sum of squares
+  const float* bias;          // optional per-column bias added before rounding
+  int relu;                   // optional ReLU before rounding
+  // optional row scatter: GEMM row (n,p,q) is written to row (n*sc_H + p*sc_sh)*sc_W + q*sc_sw
+  int scatter, sc_P, sc_Q, sc_H, sc_W, sc_sh, sc_sw;
+  // MN-major operand descriptor geometry (bytes): chunk distance, 8-row group distance, advance per 16-row MMA step.
+  int mn_lbo, mn_sbo, mn_kadv;
+};
+
+// Weight-gradient implicit GEMM:  dW[co, tap*Cin + ci] += sum_{pix in split} dy[pix, co] * x_tap[pix, ci]
+struct ConvWgradParams {
+  int Mpix;     // number of output pixels (rows of dy)
+  int Cout;
+  int Cin;
+  PixelSrc x;   // how x_tap rows are fetched (pixelsPerColumn = 64)
+  float* dw;    // [Cout][R*S*Cin] fp32, accumulated with atomics (caller zero-fills)
+  long long ldw;
+  int chunks_per_split;  // number of 64-pixel K blocks handled by one CTA
+  int mn_lbo, mn_sbo, mn_kadv;
+};
+
+// Defaults 8192 / 1024 / 2048; TOK_MN_LBO / TOK_MN_SBO / TOK_MN_KADV override them (bring-up aid).
+void mn_desc_geometry(int* lbo, int* sbo, int* kadv);
+
+}  // namespace tok

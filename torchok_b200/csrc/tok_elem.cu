@@ -1,0 +1,903 @@
+// tok_elem.cu — HBM-bound passes around the tensor-core kernels: BatchNorm finalize/apply/backward with fused
+// ReLU and residual add, pooling, softmax cross-entropy, layout packing, optimizer steps.
+// Layout everywhere: NHWC bf16, i.e. a [rows = N*H*W][C] matrix with C contiguous; 8 channels (16 bytes) per access.
+//
+// Reference call sites: torch.nn.BatchNorm2d + ReLU in ConvBnAct (torchok/models/modules/bricks/convbnact.py:44-53),
+// timm block tails `x += shortcut; act(x)` built by torchok/models/backbones/resnet.py:363-405, the stem maxpool
+// (resnet.py:510), SelectAdaptivePool2d (torchok/models/poolings/classification/pooling.py:8-12),
+// torch.nn.CrossEntropyLoss (torchok/losses/__init__.py:26).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/tokb200.h"
+#include "tok_internal.h"
+#include "tok_ptx.cuh"
+
+namespace tok {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+static inline int elem_grid(long long work_items, int block) {
+  long long b = (work_items + block - 1) / block;
+  const long long cap = 148LL * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------ dgrad helper
+// dst[n, p*sh, q*sw, :] = src[n, p, q, :]  (dst pre-zeroed): zero-dilation of an output gradient.
+__global__ void dilate_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total, int P,
+                                   int Q, int cvec, int H, int W, int sh, int sw) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    const int q = (int)(pix % Q);
+    pix /= Q;
+    const int p = (int)(pix % P);
+    const long long n = pix / P;
+    dst[((n * H + (long long)p * sh) * W + (long long)q * sw) * cvec + cv] = src[i];
+  }
+}
+void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
+                        int sh, int sw, cudaStream_t st) {
+  const long long total = (long long)n * p * q * (c / 8);
+  dilate_rows_kernel<<<elem_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
+                                                            reinterpret_cast<uint4*>(dst), total, p, q, c / 8, H, W,
+                                                            sh, sw);
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm forward
+// Training-mode statistics -> per-channel affine (scale, shift); running-stat update as torch.nn.BatchNorm2d:
+// biased variance normalises, unbiased variance feeds running_var.
+__global__ void bn_finalize_train_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum, float count,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                         float momentum, float* running_mean, float* running_var,
+                                         float* __restrict__ scale, float* __restrict__ shift,
+                                         float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = sum[c] / count;
+  float var = sqsum[c] / count - mean * mean;
+  var = fmaxf(var, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - mean * g * invstd;
+  save_mean[c] = mean;
+  save_invstd[c] = invstd;
+  if (running_mean) {
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+__global__ void bn_finalize_eval_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                        float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(running_var[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f;
+  const float b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - running_mean[c] * g * invstd;
+}
+
+// out = act(y * scale[c] + shift[c] (+ residual)).  One 16-byte vector (8 channels) per thread per iteration.
+template <bool HAS_RES, bool RELU>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res,
+                                                       uint4* __restrict__ out, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, long long total, int cvec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool invariant = (stride % cvec) == 0;
+  float sc[8], sf[8];
+  int cv = (int)(i % cvec);
+  if (invariant) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + cv * 8 + j);
+      sf[j] = __ldg(shift + cv * 8 + j);
+    }
+  }
+  for (; i < total; i += stride) {
+    if (!invariant) {
+      cv = (int)(i % cvec);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(scale + cv * 8 + j);
+        sf[j] = __ldg(shift + cv * 8 + j);
+      }
+    }
+    float f[8];
+    unpack8(ldg_stream(y + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sf[j]);
+    if (HAS_RES) {
+      float r[8];
+      unpack8(ldg_stream(res + i), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    if (RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    out[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm backward
+// Pass 1: g = (dout (+dout2)) * [out > 0];  sum_g[c] += sum g ; sum_gy[c] += sum g*y   (fp32 atomics).
+// A 256-thread block is (rows_per_block x cvec_b) with the channel vector fixed per thread.
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2, const uint4* __restrict__ out,
+                     const uint4* __restrict__ y, float* __restrict__ sum_g, float* __restrict__ sum_gy,
+                     long long rows, int cvec, int cvec_b, int rows_per_cta) {
+  extern __shared__ float red[];  // [cvec_b*8][2]
+  const int rlanes = 256 / cvec_b;
+  const int cl = threadIdx.x % cvec_b;
+  const int rl = threadIdx.x / cvec_b;
+  const int cv = blockIdx.y * cvec_b + cl;
+  for (int i = threadIdx.x; i < cvec_b * 16; i += 256) red[i] = 0.f;
+  __syncthreads();
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  if (rl < rlanes && cv < cvec) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    long long r1 = r0 + rows_per_cta;
+    if (r1 > rows) r1 = rows;
+    for (long long r = r0 + rl; r < r1; r += rlanes) {
+      const long long idx = r * cvec + cv;
+      float g[8], yy[8];
+      unpack8(ldg_stream(dout + idx), g);
+      if (dout2) {
+        float g2[8];
+        unpack8(ldg_stream(dout2 + idx), g2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += g2[j];
+      }
+      if (out) {
+        float o[8];
+        unpack8(ldg_stream(out + idx), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+      }
+      unpack8(ldg_stream(y + idx), yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += g[j];
+        a2[j] = fmaf(g[j], yy[j], a2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[(cl * 8 + j) * 2], a1[j]);
+      atomicAdd(&red[(cl * 8 + j) * 2 + 1], a2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cvec_b * 8; i += 256) {
+    const int c = blockIdx.y * cvec_b * 8 + i;
+    if (c < cvec * 8) {
+      atomicAdd(sum_g + c, red[i * 2]);
+      atomicAdd(sum_gy + c, red[i * 2 + 1]);
+    }
+  }
+}
+
+// Coefficients of the data gradient  dy = a*g + c1*y + c0  and the parameter gradients.
+//   xhat = (y-mean)*invstd ; sum_gx = invstd*(sum_gy - mean*sum_g)
+//   dy = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sum_g, const float* __restrict__ sum_gy,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const float* __restrict__ gamma, float count, float* __restrict__ coef_a,
+                                       float* __restrict__ coef_c1, float* __restrict__ coef_c0, float* dgamma,
+                                       float* dbeta, int accumulate, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sg = sum_g[c];
+  const float mu = mean[c];
+  const float is = invstd[c];
+  const float sgx = is * (sum_gy[c] - mu * sg);
+  const float g = gamma ? gamma[c] : 1.f;
+  const float a = g * is;
+  const float k1 = sg / count;
+  const float k2 = sgx / count;
+  coef_a[c] = a;
+  coef_c1[c] = -a * k2 * is;
+  coef_c0[c] = -a * k1 + a * k2 * is * mu;
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + sgx : sgx;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + sg : sg;
+}
+
+// Pass 2: dy = a*g + c1*y + c0 ; optionally also stores g (the gradient that flows to the residual branch).
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2, const uint4* __restrict__ out,
+                    const uint4* __restrict__ y, const float* __restrict__ coef_a, const float* __restrict__ coef_c1,
+                    const float* __restrict__ coef_c0, uint4* __restrict__ dy, uint4* __restrict__ dres,
+                    long long total, int cvec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool invariant = (stride % cvec) == 0;
+  float ca[8], c1[8], c0[8];
+  int cv = (int)(i % cvec);
+  if (invariant) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ca[j] = __ldg(coef_a + cv * 8 + j);
+      c1[j] = __ldg(coef_c1 + cv * 8 + j);
+      c0[j] = __ldg(coef_c0 + cv * 8 + j);
+    }
+  }
+  for (; i < total; i += stride) {
+    if (!invariant) {
+      cv = (int)(i % cvec);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ca[j] = __ldg(coef_a + cv * 8 + j);
+        c1[j] = __ldg(coef_c1 + cv * 8 + j);
+        c0[j] = __ldg(coef_c0 + cv * 8 + j);
+      }
+    }
+    float g[8], yy[8];
+    unpack8(ldg_stream(dout + i), g);
+    if (dout2) {
+      float g2[8];
+      unpack8(ldg_stream(dout2 + i), g2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += g2[j];
+    }
+    if (out) {
+      float o[8];
+      unpack8(ldg_stream(out + i), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+    }
+    unpack8(ldg_stream(y + i), yy);
+    if (dres) dres[i] = pack8(g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) yy[j] = fmaf(ca[j], g[j], fmaf(c1[j], yy[j], c0[j]));
+    dy[i] = pack8(yy);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+// Max pool, NHWC, window k x k, stride s, padding pd (implicit -inf). First maximum in (r, s) scan order wins, as in
+// ATen's max_pool2d; the winner's window slot (r*k + s) is stored for the backward pass.
+__global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, uint2* __restrict__ arg,
+                                   long long total, int H, int W, int P, int Q, int cvec, int k, int s, int pd) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long t = i / cvec;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const long long n = t / P;
+    float best[8];
+    uint32_t bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+    for (int r = 0; r < k; ++r) {
+      const int h = p * s - pd + r;
+      if (h < 0 || h >= H) continue;
+      for (int c = 0; c < k; ++c) {
+        const int w = q * s - pd + c;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(__ldg(x + ((n * H + h) * W + w) * cvec + cv), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (f[j] > best[j] || f[j] != f[j]) {
+            best[j] = f[j];
+            bi[j] = r * k + c;
+          }
+        }
+      }
+    }
+    out[i] = pack8(best);
+    arg[i] = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24),
+                        bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
+  }
+}
+
+// dx[n,h,w,c] = sum over windows (p,q) that contain (h,w) of dout[n,p,q,c] * [arg[n,p,q,c] == slot of (h,w)].
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ dout, const uint2* __restrict__ arg,
+                                   uint4* __restrict__ dx, long long total, int H, int W, int P, int Q, int cvec,
+                                   int k, int s, int pd) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long t = i / cvec;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const long long n = t / H;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // windows p with p*s - pd <= h <= p*s - pd + k - 1
+    int p_lo = (h + pd - (k - 1) + s - 1) / s;
+    if (h + pd - (k - 1) < 0) p_lo = 0;
+    int p_hi = (h + pd) / s;
+    if (p_hi > P - 1) p_hi = P - 1;
+    int q_lo = (w + pd - (k - 1) + s - 1) / s;
+    if (w + pd - (k - 1) < 0) q_lo = 0;
+    int q_hi = (w + pd) / s;
+    if (q_hi > Q - 1) q_hi = Q - 1;
+    for (int p = p_lo; p <= p_hi; ++p) {
+      const int r = h - (p * s - pd);
+      for (int q = q_lo; q <= q_hi; ++q) {
+        const int c = w - (q * s - pd);
+        const uint32_t slot = r * k + c;
+        const long long o = ((n * P + p) * Q + q) * cvec + cv;
+        const uint2 a = __ldg(arg + o);
+        float g[8];
+        unpack8(__ldg(dout + o), g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (((a.x >> (8 * j)) & 0xFF) == slot) acc[j] += g[j];
+          if (((a.y >> (8 * j)) & 0xFF) == slot) acc[4 + j] += g[4 + j];
+        }
+      }
+    }
+    dx[i] = pack8(acc);
+  }
+}
+
+// Global average (and/or max) pool over HW: x [N][HW][C] -> out [N][C].
+// mode 0 avg, 1 max, 2 avgmax = 0.5*(avg+max).  (timm SelectAdaptivePool2d, pooling.py:8-12)
+__global__ void gap_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int N, int HW, int cvec,
+                               int mode) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)N * cvec) return;
+  const int cv = (int)(i % cvec);
+  const long long n = i / cvec;
+  float s[8], m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s[j] = 0.f;
+    m[j] = -INFINITY;
+  }
+  for (int r = 0; r < HW; ++r) {
+    float f[8];
+    unpack8(__ldg(x + (n * HW + r) * cvec + cv), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      m[j] = fmaxf(m[j], f[j]);
+    }
+  }
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float avg = s[j] / HW;
+    o[j] = mode == 0 ? avg : (mode == 1 ? m[j] : 0.5f * (avg + m[j]));
+  }
+  out[i] = pack8(o);
+}
+// Backward of the average pool: dx[n, r, c] = dout[n, c] / HW.
+__global__ void gap_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ dx, long long total, int HW,
+                               int cvec) {
+  const float inv = 1.f / HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    const long long n = i / ((long long)cvec * HW);
+    float f[8];
+    unpack8(__ldg(dout + n * cvec + cv), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= inv;
+    dx[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cross entropy
+// One block per row. loss_sum += -log softmax(logits[row])[target] / norm ; dlogits = (softmax - onehot) * gscale.
+// Rows whose target == ignore_index contribute nothing (torch.nn.CrossEntropyLoss semantics).
+__global__ void __launch_bounds__(256)
+softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ target,
+                    float* __restrict__ loss_sum, __nv_bfloat16* __restrict__ dlogits, int C, long long ld,
+                    float inv_norm, float gscale, long long ignore_index, int* __restrict__ correct) {
+  __shared__ float sred[32];
+  __shared__ int sidx[32];
+  const long long row = blockIdx.x;
+  const __nv_bfloat16* lp = logits + row * ld;
+  const long long tgt = target[row];
+  float mx = -INFINITY;
+  int amax = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = __bfloat162float(lp[c]);
+    if (v > mx) {
+      mx = v;
+      amax = c;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (ov > mx || (ov == mx && oi < amax)) {
+      mx = ov;
+      amax = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sred[threadIdx.x >> 5] = mx;
+    sidx[threadIdx.x >> 5] = amax;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : -INFINITY;
+    int vi = threadIdx.x < (blockDim.x >> 5) ? sidx[threadIdx.x] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+      if (ov > v || (ov == v && oi < vi)) {
+        v = ov;
+        vi = oi;
+      }
+    }
+    if (threadIdx.x == 0) {
+      sred[0] = v;
+      sidx[0] = vi;
+    }
+  }
+  __syncthreads();
+  mx = sred[0];
+  amax = sidx[0];
+  __syncthreads();
+  float se = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) se += __expf(__bfloat162float(lp[c]) - mx);
+  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = se;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) sred[0] = v;
+  }
+  __syncthreads();
+  se = sred[0];
+  const bool ignored = (tgt == ignore_index);
+  if (threadIdx.x == 0 && !ignored) {
+    const float lt = __bfloat162float(lp[tgt]);
+    atomicAdd(loss_sum, (logf(se) + mx - lt) * inv_norm);
+    if (correct && amax == (int)tgt) atomicAdd(correct, 1);
+  }
+  if (dlogits) {
+    __nv_bfloat16* dp = dlogits + row * ld;
+    const float inv = 1.f / se;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float g = 0.f;
+      if (!ignored) {
+        g = __expf(__bfloat162float(lp[c]) - mx) * inv;
+        if (c == tgt) g -= 1.f;
+        g *= gscale;
+      }
+      dp[c] = __float2bfloat16(g);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ layout packing
+// NCHW (fp32 or bf16) -> NHWC bf16 with the channel count padded to Cp (zeros), via a 32x32 shared-memory transpose.
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW,
+                                    int Cp) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, hw = hw0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && hw < HW) ? (float)src[(n * C + c) * HW + hw] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int hw = hw0 + j, c = c0 + threadIdx.x;
+    if (hw < HW && c < Cp) dst[(n * HW + hw) * Cp + c] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+// NHWC bf16 (pitch Cp) -> NCHW (fp32 or bf16), first C channels.
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, T* __restrict__ dst, int C, int HW,
+                                    int Cp) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int hw = hw0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (hw < HW && c < C) ? __bfloat162float(src[(n * HW + hw) * Cp + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, hw = hw0 + threadIdx.x;
+    if (c < C && hw < HW) dst[(n * C + c) * HW + hw] = (T)tile[threadIdx.x][j];
+  }
+}
+
+// Stem input packing: NCHW image (C<=4 channels used) -> zero-padded 2x2 space-to-depth NHWC16 bf16.
+//   dst[n, h2, w2, (dh*2+dw)*4 + c] = src[n, c, 2*h2+dh-pad, 2*w2+dw-pad]   (0 outside the image / for c >= C)
+// A 7x7 stride-2 pad-3 convolution over src equals a 4x4 stride-1 pad-0 convolution over dst (16 channels); because
+// the 4 horizontal taps are 4 adjacent NHWC16 pixels (64 contiguous elements) the conv kernel fetches them as ONE
+// 64-"channel" im2col row, so the stem runs through the same tcgen05 pipeline as every other conv.
+template <typename T>
+__global__ void stem_s2d_pack_kernel(const T* __restrict__ src, uint4* __restrict__ dst, int N, int C, int H, int W,
+                                     int H2, int W2, int pad) {
+  const long long total = (long long)N * H2 * W2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w2 = (int)(i % W2);
+    long long t = i / W2;
+    const int h2 = (int)(t % H2);
+    const long long n = t / H2;
+    float f[16];
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        const int h = 2 * h2 + dh - pad, w = 2 * w2 + dw - pad;
+        const bool in = h >= 0 && h < H && w >= 0 && w < W;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          f[(dh * 2 + dw) * 4 + c] = (in && c < C) ? (float)src[((n * C + c) * H + h) * W + w] : 0.f;
+      }
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = f[j];
+      b[j] = f[8 + j];
+    }
+    dst[i * 2] = pack8(a);
+    dst[i * 2 + 1] = pack8(b);
+  }
+}
+
+// Stem weights: fp32 [K][7][7][C] (channels_last OIHW) -> bf16 [K][4][4][16] matching stem_s2d_pack_kernel.
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int K, int R,
+                                        int S, int C) {
+  const int total = K * 256;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i / 256, rem = i % 256;
+    const int r2 = rem / 64, s2 = (rem / 16) % 4, e = rem % 16;
+    const int dh = e / 8, dw = (e / 4) % 2, c = e % 4;
+    const int r = 2 * r2 + dh, s = 2 * s2 + dw;
+    float v = 0.f;
+    if (r < R && s < S && c < C) v = w[((k * R + r) * S + s) * C + c];
+    wp[i] = __float2bfloat16(v);
+  }
+}
+// Inverse gather for the gradient: dw[K][7][7][C] (+)= dwp[K][4][4][16].
+__global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int K, int R, int S,
+                                         int C, int accumulate) {
+  const int total = K * R * S * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C;
+    int t = i / C;
+    const int s = t % S;
+    t /= S;
+    const int r = t % R;
+    const int k = t / R;
+    const float v = dwp[k * 256 + (r / 2) * 64 + (s / 2) * 16 + ((r % 2) * 2 + (s % 2)) * 4 + c];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer
+// SGD with momentum (torch.optim.SGD semantics: d = g + wd*p ; buf = mu*buf + (1-damp)*d ; p -= lr*(nesterov ? d+mu*buf : buf))
+// fused with the fp32 -> bf16 shadow-weight cast used by the next forward.  `first` = momentum buffer is uninitialised.
+__global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                __nv_bfloat16* __restrict__ shadow, long long n, float lr, float mu, float wd,
+                                float damp, int nesterov, float gscale, int first) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i];
+    float d = g[i] * gscale + wd * w;
+    if (mu != 0.f) {
+      const float b = first ? d : mu * buf[i] + (1.f - damp) * d;
+      buf[i] = b;
+      d = nesterov ? d + mu * b : b;
+    }
+    w -= lr * d;
+    p[i] = w;
+    if (shadow) shadow[i] = __float2bfloat16(w);
+  }
+}
+// Adam / AdamW (torch.optim.Adam semantics, amsgrad off). bc1 = 1-beta1^t, bc2 = 1-beta2^t computed by the host.
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float lr,
+                                 float b1, float b2, float eps, float wd, int decoupled, float bc1, float bc2,
+                                 float gscale) {
+  const float step = lr / bc1;
+  const float rbc2 = rsqrtf(bc2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i];
+    float d = g[i] * gscale;
+    if (decoupled)
+      w *= 1.f - lr * wd;
+    else
+      d += wd * w;
+    const float mi = b1 * m[i] + (1.f - b1) * d;
+    const float vi = b2 * v[i] + (1.f - b2) * d * d;
+    m[i] = mi;
+    v[i] = vi;
+    w -= step * mi / (sqrtf(vi) * rbc2 + eps);
+    p[i] = w;
+    if (shadow) shadow[i] = __float2bfloat16(w);
+  }
+}
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+}  // namespace tok
+
+using namespace tok;
+
+#define TOK_VEC_CHECK(c)                                                                         \
+  if ((c) <= 0 || ((c) % 8) != 0) return set_error(TOK_ERR_INVALID, "channel count must be a positive multiple of 8 (got %d)", (int)(c))
+
+extern "C" {
+
+int tok_bn_finalize_train(int C, double count, const float* sum, const float* sqsum, const float* gamma,
+                          const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                          float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+  if (C <= 0 || count <= 0) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
+  bn_finalize_train_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sum, sqsum, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
+      save_invstd, C);
+  TOK_CHECK_LAUNCH("bn_finalize_train");
+  return TOK_OK;
+}
+
+int tok_bn_finalize_eval(int C, const float* running_mean, const float* running_var, const float* gamma,
+                         const float* beta, float eps, float* scale, float* shift, void* stream) {
+  if (C <= 0) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
+  bn_finalize_eval_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, gamma, beta,
+                                                                               eps, scale, shift, C);
+  TOK_CHECK_LAUNCH("bn_finalize_eval");
+  return TOK_OK;
+}
+
+int tok_bn_apply(long long rows, int C, const void* y, const float* scale, const float* shift, const void* residual,
+                 int relu, void* out, void* stream) {
+  TOK_VEC_CHECK(C);
+  if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_apply: no rows");
+  const int cvec = C / 8;
+  const long long total = rows * cvec;
+  const int grid = elem_grid(total, 256 * 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint4* yp = (const uint4*)y;
+  const uint4* rp = (const uint4*)residual;
+  uint4* op = (uint4*)out;
+  if (residual && relu)
+    bn_apply_kernel<true, true><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec);
+  else if (residual)
+    bn_apply_kernel<true, false><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec);
+  else if (relu)
+    bn_apply_kernel<false, true><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec);
+  else
+    bn_apply_kernel<false, false><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec);
+  TOK_CHECK_LAUNCH("bn_apply");
+  return TOK_OK;
+}
+
+int tok_bn_bwd_reduce(long long rows, int C, const void* dout, const void* dout2, const void* out, const void* y,
+                      float* sum_g, float* sum_gy, void* stream) {
+  TOK_VEC_CHECK(C);
+  if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_reduce: no rows");
+  const int cvec = C / 8;
+  const int cvec_b = cvec < 256 ? cvec : 256;
+  const int gy = (cvec + cvec_b - 1) / cvec_b;
+  long long ctas = 148LL * 8 / gy;
+  if (ctas < 1) ctas = 1;
+  const int rlanes = 256 / cvec_b;
+  long long min_rows = (long long)rlanes * 4;
+  long long rows_per_cta = (rows + ctas - 1) / ctas;
+  if (rows_per_cta < min_rows) rows_per_cta = min_rows;
+  ctas = (rows + rows_per_cta - 1) / rows_per_cta;
+  dim3 grid((unsigned)ctas, gy);
+  bn_bwd_reduce_kernel<<<grid, 256, cvec_b * 16 * sizeof(float), (cudaStream_t)stream>>>(
+      (const uint4*)dout, (const uint4*)dout2, (const uint4*)out, (const uint4*)y, sum_g, sum_gy, rows, cvec, cvec_b,
+      (int)rows_per_cta);
+  TOK_CHECK_LAUNCH("bn_bwd_reduce");
+  return TOK_OK;
+}
+
+int tok_bn_bwd_finalize(int C, double count, const float* sum_g, const float* sum_gy, const float* save_mean,
+                        const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1, float* coef_c0,
+                        float* dgamma, float* dbeta, int accumulate, void* stream) {
+  if (C <= 0 || count <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_finalize: bad size");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sum_g, sum_gy, save_mean, save_invstd, gamma, (float)count, coef_a, coef_c1, coef_c0, dgamma, dbeta, accumulate,
+      C);
+  TOK_CHECK_LAUNCH("bn_bwd_finalize");
+  return TOK_OK;
+}
+
+int tok_bn_bwd_apply(long long rows, int C, const void* dout, const void* dout2, const void* out, const void* y,
+                     const float* coef_a, const float* coef_c1, const float* coef_c0, void* dy, void* dres,
+                     void* stream) {
+  TOK_VEC_CHECK(C);
+  if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_apply: no rows");
+  const int cvec = C / 8;
+  const long long total = rows * cvec;
+  bn_bwd_apply_kernel<<<elem_grid(total, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)dout, (const uint4*)dout2, (const uint4*)out, (const uint4*)y, coef_a, coef_c1, coef_c0,
+      (uint4*)dy, (uint4*)dres, total, cvec);
+  TOK_CHECK_LAUNCH("bn_bwd_apply");
+  return TOK_OK;
+}
+
+int tok_maxpool_fwd(int n, int h, int w, int c, int k, int s, int pad, const void* x, void* out, void* argmax,
+                    void* stream) {
+  TOK_VEC_CHECK(c);
+  if (k <= 0 || k > 15 || s <= 0) return set_error(TOK_ERR_INVALID, "maxpool: bad window");
+  const int P = (h + 2 * pad - k) / s + 1, Q = (w + 2 * pad - k) / s + 1;
+  const long long total = (long long)n * P * Q * (c / 8);
+  maxpool_fwd_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out,
+                                                                             (uint2*)argmax, total, h, w, P, Q, c / 8,
+                                                                             k, s, pad);
+  TOK_CHECK_LAUNCH("maxpool_fwd");
+  return TOK_OK;
+}
+
+int tok_maxpool_bwd(int n, int h, int w, int c, int k, int s, int pad, const void* dout, const void* argmax, void* dx,
+                    void* stream) {
+  TOK_VEC_CHECK(c);
+  if (k <= 0 || k > 15 || s <= 0) return set_error(TOK_ERR_INVALID, "maxpool: bad window");
+  const int P = (h + 2 * pad - k) / s + 1, Q = (w + 2 * pad - k) / s + 1;
+  const long long total = (long long)n * h * w * (c / 8);
+  maxpool_bwd_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint2*)argmax,
+                                                                             (uint4*)dx, total, h, w, P, Q, c / 8, k,
+                                                                             s, pad);
+  TOK_CHECK_LAUNCH("maxpool_bwd");
+  return TOK_OK;
+}
+
+int tok_gap_fwd(int n, int hw, int c, int mode, const void* x, void* out, void* stream) {
+  TOK_VEC_CHECK(c);
+  if (mode < 0 || mode > 2) return set_error(TOK_ERR_INVALID, "gap: mode must be 0 (avg), 1 (max) or 2 (avgmax)");
+  const long long total = (long long)n * (c / 8);
+  gap_fwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, n,
+                                                                                   hw, c / 8, mode);
+  TOK_CHECK_LAUNCH("gap_fwd");
+  return TOK_OK;
+}
+
+int tok_gap_bwd(int n, int hw, int c, const void* dout, void* dx, void* stream) {
+  TOK_VEC_CHECK(c);
+  const long long total = (long long)n * hw * (c / 8);
+  gap_bwd_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (uint4*)dx, total, hw,
+                                                                         c / 8);
+  TOK_CHECK_LAUNCH("gap_bwd");
+  return TOK_OK;
+}
+
+int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const long long* target, float* loss_sum,
+                     void* dlogits, float inv_norm, float gscale, long long ignore_index, int* correct,
+                     void* stream) {
+  if (rows <= 0 || C <= 0) return set_error(TOK_ERR_INVALID, "softmax_xent: bad size");
+  softmax_xent_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, loss_sum,
+                                                             (__nv_bfloat16*)dlogits, C, ld, inv_norm, gscale,
+                                                             ignore_index, correct);
+  TOK_CHECK_LAUNCH("softmax_xent");
+  return TOK_OK;
+}
+
+int tok_nchw_to_nhwc(int n, int c, int hw, int cp, int src_is_bf16, const void* src, void* dst, void* stream) {
+  if (n <= 0 || c <= 0 || hw <= 0 || cp < c) return set_error(TOK_ERR_INVALID, "nchw_to_nhwc: bad size");
+  dim3 grid((hw + 31) / 32, (cp + 31) / 32, n), block(32, 8);
+  if (src_is_bf16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src,
+                                                                                 (__nv_bfloat16*)dst, c, hw, cp);
+  else
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, (__nv_bfloat16*)dst, c, hw,
+                                                                         cp);
+  TOK_CHECK_LAUNCH("nchw_to_nhwc");
+  return TOK_OK;
+}
+
+int tok_nhwc_to_nchw(int n, int c, int hw, int cp, int dst_is_bf16, const void* src, void* dst, void* stream) {
+  if (n <= 0 || c <= 0 || hw <= 0 || cp < c) return set_error(TOK_ERR_INVALID, "nhwc_to_nchw: bad size");
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  if (dst_is_bf16)
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src,
+                                                                                 (__nv_bfloat16*)dst, c, hw, cp);
+  else
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (float*)dst, c, hw,
+                                                                         cp);
+  TOK_CHECK_LAUNCH("nhwc_to_nchw");
+  return TOK_OK;
+}
+
+int tok_stem_pack_input(int n, int c, int h, int w, int src_is_bf16, const void* src, void* dst, void* stream) {
+  if (n <= 0 || c <= 0 || c > 4 || h <= 0 || w <= 0) return set_error(TOK_ERR_INVALID, "stem_pack_input: needs 1..4 channels");
+  const int P = (h - 1) / 2 + 1, Q = (w - 1) / 2 + 1, H2 = P + 3, W2 = Q + 3;
+  const long long total = (long long)n * H2 * W2;
+  if (src_is_bf16)
+    stem_s2d_pack_kernel<__nv_bfloat16><<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, (uint4*)dst, n, c, h, w, H2, W2, 3);
+  else
+    stem_s2d_pack_kernel<float><<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)src, (uint4*)dst,
+                                                                                        n, c, h, w, H2, W2, 3);
+  TOK_CHECK_LAUNCH("stem_pack_input");
+  return TOK_OK;
+}
+
+int tok_stem_pack_weight(int k, int c, const float* w, void* wp, void* stream) {
+  if (k <= 0 || c <= 0 || c > 4) return set_error(TOK_ERR_INVALID, "stem_pack_weight: needs 1..4 channels");
+  stem_pack_weight_kernel<<<(k * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, k, 7, 7, c);
+  TOK_CHECK_LAUNCH("stem_pack_weight");
+  return TOK_OK;
+}
+
+int tok_stem_unpack_wgrad(int k, int c, const float* dwp, float* dw, int accumulate, void* stream) {
+  if (k <= 0 || c <= 0 || c > 4) return set_error(TOK_ERR_INVALID, "stem_unpack_wgrad: needs 1..4 channels");
+  stem_unpack_wgrad_kernel<<<(k * 49 * c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dwp, dw, k, 7, 7, c,
+                                                                                      accumulate);
+  TOK_CHECK_LAUNCH("stem_unpack_wgrad");
+  return TOK_OK;
+}
+
+int tok_sgd_step(long long n, float* param, const float* grad, float* momentum_buf, void* shadow_bf16, float lr,
+                 float momentum, float weight_decay, float dampening, int nesterov, float grad_scale, int first_step,
+                 void* stream) {
+  if (n <= 0) return TOK_OK;
+  sgd_step_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf,
+                                                                          (__nv_bfloat16*)shadow_bf16, n, lr, momentum,
+                                                                          weight_decay, dampening, nesterov,
+                                                                          grad_scale, first_step);
+  TOK_CHECK_LAUNCH("sgd_step");
+  return TOK_OK;
+}
+
+int tok_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, int step,
+                  float grad_scale, void* stream) {
+  if (n <= 0) return TOK_OK;
+  if (step <= 0) return set_error(TOK_ERR_INVALID, "adam: step must be >= 1");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_step_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, decoupled,
+      bc1, bc2, grad_scale);
+  TOK_CHECK_LAUNCH("adam_step");
+  return TOK_OK;
+}
+
+int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream) {
+  if (n <= 0) return TOK_OK;
+  cast_f32_bf16_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  TOK_CHECK_LAUNCH("cast_f32_bf16");
+  return TOK_OK;
+}
+
+}  // extern "C"
