@@ -86,8 +86,9 @@ int tok_stem_conv_wgrad(int n, int h, int w, int k, const void* xs2d, const void
 
 /* ---- BatchNorm2d (+ReLU, +residual add) around the convs (torch.nn.BatchNorm2d in ConvBnAct,
  *      torchok/models/modules/bricks/convbnact.py:44-53; timm block tails `x += shortcut; act(x)`) --------------- */
-/* batch statistics (sums from tok_conv_fprop) -> scale/shift, saved mean/invstd, running-stat update */
-int tok_bn_finalize_train(int C, double count, const float* sum, const float* sqsum, const float* gamma,
+/* batch statistics (sums from tok_conv_fprop) -> scale/shift, saved mean/invstd, running-stat update.
+ * sum/sqsum are CONSUMED: they are reset to zero so the same accumulators can be reused by the next step. */
+int tok_bn_finalize_train(int C, double count, float* sum, float* sqsum, const float* gamma,
                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                           float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
 int tok_bn_finalize_eval(int C, const float* running_mean, const float* running_var, const float* gamma,
@@ -99,7 +100,8 @@ int tok_bn_apply(long long rows, int C, const void* y, const float* scale, const
  * by the caller) */
 int tok_bn_bwd_reduce(long long rows, int C, const void* dout, const void* dout2, const void* out, const void* y,
                       float* sum_g, float* sum_gy, void* stream);
-int tok_bn_bwd_finalize(int C, double count, const float* sum_g, const float* sum_gy, const float* save_mean,
+/* sum_g/sum_gy are CONSUMED (reset to zero) like the forward accumulators. */
+int tok_bn_bwd_finalize(int C, double count, float* sum_g, float* sum_gy, const float* save_mean,
                         const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1, float* coef_c0,
                         float* dgamma, float* dbeta, int accumulate, void* stream);
 /* dy = coef_a*g + coef_c1*y + coef_c0 ; dres (nullable) receives g */
@@ -117,10 +119,12 @@ int tok_maxpool_bwd(int n, int h, int w, int c, int k, int s, int pad, const voi
 int tok_gap_fwd(int n, int hw, int c, int mode, const void* x, void* out, void* stream);
 int tok_gap_bwd(int n, int hw, int c, const void* dout, void* dx, void* stream);
 
-/* ---- loss (torch.nn.CrossEntropyLoss, torchok/losses/__init__.py:26): loss_sum += mean NLL, dlogits written in place
- * of a separate backward; `correct` (nullable) counts rows whose argmax equals the target. */
+/* ---- loss (torch.nn.CrossEntropyLoss, torchok/losses/__init__.py:26): *loss_sum += inv_norm * sum NLL (nullable);
+ * dlogits (nullable) = (softmax - onehot) * gscale * (*gscale_dev if non-NULL: the upstream scalar gradient, read on
+ * the device so no host sync is needed); `correct` (nullable) counts rows whose argmax equals the target. */
 int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const long long* target, float* loss_sum,
-                     void* dlogits, float inv_norm, float gscale, long long ignore_index, int* correct, void* stream);
+                     void* dlogits, float inv_norm, float gscale, const float* gscale_dev, long long ignore_index,
+                     int* correct, void* stream);
 
 /* ---- layout (task boundary is NCHW, torchok/tasks/classification.py:108-109) ------------------------------------ */
 int tok_nchw_to_nhwc(int n, int c, int hw, int cp, int src_is_bf16, const void* src, void* dst, void* stream);

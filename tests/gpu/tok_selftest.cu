@@ -509,7 +509,7 @@ static void test_xent(int rows, int C) {
   up_bf16(dl, lg);
   CK(cudaMemcpy(dt.p, tgt.data(), rows * 8, cudaMemcpyHostToDevice));
   const int valid = rows - 1;
-  TK(tok_softmax_xent(rows, C, C, dl.p, (const long long*)dt.p, (float*)loss.p, dd.p, 1.f / valid, 1.f / valid, -100,
+  TK(tok_softmax_xent(rows, C, C, dl.p, (const long long*)dt.p, (float*)loss.p, dd.p, 1.f / valid, 1.f / valid, nullptr, -100,
                       (int*)corr.p, nullptr));
   CK(cudaDeviceSynchronize());
   double rl = 0;

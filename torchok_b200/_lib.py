@@ -1,0 +1,138 @@
+"""ctypes binding of libtokb200.so (include/tokb200.h).
+
+The reference has no FFI: torchok modules call torch.nn and torch dispatches to cuDNN/cuBLAS
+(e.g. torchok/models/modules/bricks/convbnact.py:38-53).  This file is the stub a maintainer would add to call the
+sm_100a kernels instead; see INTEGRATION.md.  There is NO CPU fallback: if the shared library is missing every call
+raises `TokLibraryError`.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, 'libtokb200.so')
+HEADER_PATH = os.path.join(_ROOT, 'include', 'tokb200.h')
+
+
+class TokLibraryError(RuntimeError):
+    pass
+
+
+class TokError(RuntimeError):
+    """A libtokb200 entry point returned a negative tokStatus."""
+
+
+class tokConvDesc(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ('n', 'h', 'w', 'c', 'k', 'r', 's', 'stride', 'pad', 'dil')]
+
+
+_vp, _i, _ll, _f, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t
+_pd = C.POINTER(tokConvDesc)
+_pi = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes).  Status-returning functions (restype int, name not in _RAW) are wrapped to raise.
+_SIGS = {
+    'tok_version': (_i, []),
+    'tok_last_error': (C.c_char_p, []),
+    'tok_device_ok': (_i, []),
+    'tok_conv_out_hw': (None, [_pd, _pi, _pi]),
+    'tok_conv_fprop': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'tok_conv_dgrad_workspace_bytes': (_sz, [_pd]),
+    'tok_conv_dgrad': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_conv_wgrad': (_i, [_pd, _vp, _vp, _vp, _vp]),
+    'tok_linear_fwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'tok_linear_dgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    'tok_linear_wgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    'tok_stem_geometry': (None, [_i, _i, _pi, _pi, _pi, _pi]),
+    'tok_stem_pack_input': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'tok_stem_pack_weight': (_i, [_i, _i, _vp, _vp, _vp]),
+    'tok_stem_unpack_wgrad': (_i, [_i, _i, _vp, _vp, _i, _vp]),
+    'tok_stem_conv_fprop': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_stem_conv_wgrad': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'tok_bn_finalize_train': (_i, [_i, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_bn_finalize_eval': (_i, [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    'tok_bn_apply': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    'tok_bn_bwd_reduce': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_bn_bwd_finalize': (_i, [_i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'tok_bn_bwd_apply': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_maxpool_fwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'tok_maxpool_bwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'tok_gap_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
+    'tok_gap_bwd': (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    'tok_softmax_xent': (_i, [_i, _i, _ll, _vp, _vp, _vp, _vp, _f, _f, _vp, _ll, _vp, _vp]),
+    'tok_nchw_to_nhwc': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'tok_nhwc_to_nchw': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'tok_sgd_step': (_i, [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),
+    'tok_adam_step': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _i, _f, _vp]),
+    'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
+}
+_RAW = {'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+        'tok_stem_geometry'}
+
+
+def header_symbols(path=HEADER_PATH):
+    """Every function name declared in include/tokb200.h (used by the symbol-coverage test)."""
+    text = open(path).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(tok_[a-z0-9_]+)\s*\(', text)))
+
+
+class _Lib:
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise TokLibraryError(
+                f'{path} is missing: build it with `make` (or `python -c "import __graft_entry__ as g; g.build()"`). '
+                'torchok_b200 has no CPU or torch.nn fallback for its kernels.')
+        self._dll = C.CDLL(path)
+        self.path = path
+        self.launches = 0  # kernels-launching ABI calls made through this binding (bench.py's gpu_launches claim)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(self._dll, name)
+            fn.restype = res
+            fn.argtypes = args
+            if res is _i and name not in _RAW:
+                fn = self._checked(name, fn)
+            setattr(self, name, fn)
+
+    def _checked(self, name, fn):
+        def call(*a):
+            rc = fn(*a)
+            self.launches += 1
+            if rc != 0:
+                raise TokError(f'{name} failed ({rc}): {self._dll.tok_last_error().decode()}')
+            return rc
+        call.__name__ = name
+        return call
+
+    def has(self, name):
+        try:
+            getattr(self._dll, name)
+            return True
+        except AttributeError:
+            return False
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                _lib = _Lib(LIB_PATH)
+    return _lib
+
+
+def build(verbose=False):
+    """Compile libtokb200.so for sm_100a in-tree (Makefile at the repo root)."""
+    out = subprocess.run(['make', '-C', _ROOT, '-j8'], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise TokLibraryError('make failed:\n' + out.stdout[-4000:] + out.stderr[-4000:])
+    if verbose:
+        print(out.stdout[-2000:])
+    return LIB_PATH

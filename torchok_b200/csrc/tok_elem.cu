@@ -69,7 +69,7 @@ void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int
 // ------------------------------------------------------------------------------------------------ BatchNorm forward
 // Training-mode statistics -> per-channel affine (scale, shift); running-stat update as torch.nn.BatchNorm2d:
 // biased variance normalises, unbiased variance feeds running_var.
-__global__ void bn_finalize_train_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum, float count,
+__global__ void bn_finalize_train_kernel(float* __restrict__ sum, float* __restrict__ sqsum, float count,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* running_mean, float* running_var,
                                          float* __restrict__ scale, float* __restrict__ shift,
@@ -79,6 +79,8 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ sum, const fl
   const float mean = sum[c] / count;
   float var = sqsum[c] / count - mean * mean;
   var = fmaxf(var, 0.f);
+  sum[c] = 0.f;  // consumed: the accumulators are handed back zeroed for the next step (no memset launches)
+  sqsum[c] = 0.f;
   const float invstd = rsqrtf(var + eps);
   const float g = gamma ? gamma[c] : 1.f;
   const float b = beta ? beta[c] : 0.f;
@@ -211,7 +213,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ d
 // Coefficients of the data gradient  dy = a*g + c1*y + c0  and the parameter gradients.
 //   xhat = (y-mean)*invstd ; sum_gx = invstd*(sum_gy - mean*sum_g)
 //   dy = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M)
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sum_g, const float* __restrict__ sum_gy,
+__global__ void bn_bwd_finalize_kernel(float* __restrict__ sum_g, float* __restrict__ sum_gy,
                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                        const float* __restrict__ gamma, float count, float* __restrict__ coef_a,
                                        float* __restrict__ coef_c1, float* __restrict__ coef_c0, float* dgamma,
@@ -222,6 +224,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sum_g, const fl
   const float mu = mean[c];
   const float is = invstd[c];
   const float sgx = is * (sum_gy[c] - mu * sg);
+  sum_g[c] = 0.f;  // consumed (see bn_finalize_train_kernel)
+  sum_gy[c] = 0.f;
   const float g = gamma ? gamma[c] : 1.f;
   const float a = g * is;
   const float k1 = sg / count;
@@ -424,8 +428,10 @@ __global__ void gap_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict
 __global__ void __launch_bounds__(256)
 softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ target,
                     float* __restrict__ loss_sum, __nv_bfloat16* __restrict__ dlogits, int C, long long ld,
-                    float inv_norm, float gscale, long long ignore_index, int* __restrict__ correct) {
+                    float inv_norm, float gscale, const float* __restrict__ gscale_dev, long long ignore_index,
+                    int* __restrict__ correct) {
   __shared__ float sred[32];
+  if (gscale_dev) gscale *= __ldg(gscale_dev);
   __shared__ int sidx[32];
   const long long row = blockIdx.x;
   const __nv_bfloat16* lp = logits + row * ld;
@@ -487,7 +493,7 @@ softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const long long* _
   const bool ignored = (tgt == ignore_index);
   if (threadIdx.x == 0 && !ignored) {
     const float lt = __bfloat162float(lp[tgt]);
-    atomicAdd(loss_sum, (logf(se) + mx - lt) * inv_norm);
+    if (loss_sum) atomicAdd(loss_sum, (logf(se) + mx - lt) * inv_norm);
     if (correct && amax == (int)tgt) atomicAdd(correct, 1);
   }
   if (dlogits) {
@@ -667,7 +673,7 @@ using namespace tok;
 
 extern "C" {
 
-int tok_bn_finalize_train(int C, double count, const float* sum, const float* sqsum, const float* gamma,
+int tok_bn_finalize_train(int C, double count, float* sum, float* sqsum, const float* gamma,
                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                           float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
   if (C <= 0 || count <= 0) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
@@ -732,7 +738,7 @@ int tok_bn_bwd_reduce(long long rows, int C, const void* dout, const void* dout2
   return TOK_OK;
 }
 
-int tok_bn_bwd_finalize(int C, double count, const float* sum_g, const float* sum_gy, const float* save_mean,
+int tok_bn_bwd_finalize(int C, double count, float* sum_g, float* sum_gy, const float* save_mean,
                         const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1, float* coef_c0,
                         float* dgamma, float* dbeta, int accumulate, void* stream) {
   if (C <= 0 || count <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_finalize: bad size");
@@ -803,12 +809,12 @@ int tok_gap_bwd(int n, int hw, int c, const void* dout, void* dx, void* stream) 
 }
 
 int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const long long* target, float* loss_sum,
-                     void* dlogits, float inv_norm, float gscale, long long ignore_index, int* correct,
-                     void* stream) {
+                     void* dlogits, float inv_norm, float gscale, const float* gscale_dev, long long ignore_index,
+                     int* correct, void* stream) {
   if (rows <= 0 || C <= 0) return set_error(TOK_ERR_INVALID, "softmax_xent: bad size");
   softmax_xent_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, loss_sum,
                                                              (__nv_bfloat16*)dlogits, C, ld, inv_norm, gscale,
-                                                             ignore_index, correct);
+                                                             gscale_dev, ignore_index, correct);
   TOK_CHECK_LAUNCH("softmax_xent");
   return TOK_OK;
 }

@@ -1,0 +1,472 @@
+"""Host-side launch layer: torch tensors in, libtokb200.so (sm_100a CUDA behind the C ABI) out.
+
+Everything here is plumbing: shape bookkeeping, output allocation through torch's caching allocator, the current CUDA
+stream, and `torch.autograd.Function`s whose forward/backward are sequences of C-ABI calls.  No arithmetic on
+activations or weights is done by torch ops in this file.
+
+Layout contract: an activation is a bf16 tensor of logical shape (N, C, H, W) whose memory is NHWC ("channels_last")
+with a channel pitch Cp that is a multiple of 8 (Cp == C for every ResNet tensor; HRNet's 18/36-channel branches are
+views `[:, :C]` of a Cp-channel buffer whose pad lanes are zero).  The reference keeps NCHW fp32/AMP tensors
+(torchok/tasks/classification.py:108-119); logical shapes are identical, so reference-side code that looks at
+`.shape` keeps working.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import lib, tokConvDesc
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def ceil8(c):
+    return (c + 7) // 8 * 8
+
+
+def require_cuda(t, what='tensor'):
+    if not t.is_cuda:
+        raise RuntimeError(f'torchok_b200: {what} is on {t.device}; the sm_100a kernels need a CUDA tensor '
+                           '(there is no CPU fallback — use oracle/ for CPU reference results)')
+
+
+# ------------------------------------------------------------------------------------------------------ layout
+def nhwc_empty(n, c, h, w, device, cp=None):
+    """bf16 (n, c, h, w) tensor backed by an NHWC buffer of channel pitch cp (default ceil8(c))."""
+    cp = cp or ceil8(c)
+    buf = torch.empty((n, h, w, cp), dtype=BF16, device=device)
+    t = buf.permute(0, 3, 1, 2)
+    return t if cp == c else t[:, :c]
+
+
+def nhwc_zeros(n, c, h, w, device, cp=None):
+    cp = cp or ceil8(c)
+    buf = torch.zeros((n, h, w, cp), dtype=BF16, device=device)
+    t = buf.permute(0, 3, 1, 2)
+    return t if cp == c else t[:, :c]
+
+
+def nhwc_pitch(x):
+    """Channel pitch of a 4-D tensor if its memory is NHWC-with-pitch as produced by this module, else None."""
+    if x.dim() != 4 or x.dtype != BF16:
+        return None
+    n, c, h, w = x.shape
+    s = x.stride()
+    if c > 1 and s[1] != 1:
+        return None
+    if w > 1:
+        cp = s[3]
+    elif h > 1:
+        cp = s[2]
+    elif n > 1:
+        cp = s[0]
+    else:
+        cp = ceil8(c)
+    if cp % 8 or cp < c:
+        return None
+    if (w > 1 and s[3] != cp) or (h > 1 and s[2] != w * cp) or (n > 1 and s[0] != h * w * cp):
+        return None
+    if x.data_ptr() % 16:
+        return None
+    return cp
+
+
+def to_nhwc(x):
+    """Any (N,C,H,W) float tensor -> bf16 NHWC-with-pitch (no-op if it already is)."""
+    require_cuda(x, 'activation')
+    if nhwc_pitch(x) is not None:
+        return x
+    n, c, h, w = x.shape
+    if x.dtype not in (F32, BF16):
+        x = x.float()
+    x = x.contiguous()
+    out = nhwc_empty(n, c, h, w, x.device)
+    lib().tok_nchw_to_nhwc(n, c, h * w, ceil8(c), int(x.dtype == BF16), _p(x), _p(out), _st())
+    return out
+
+
+def to_nchw(x, dtype=F32):
+    """bf16 NHWC-with-pitch -> contiguous NCHW tensor of `dtype` (fp32 or bf16)."""
+    cp = nhwc_pitch(x)
+    if cp is None:
+        raise RuntimeError('to_nchw expects an NHWC bf16 activation')
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, h, w), dtype=dtype, device=x.device)
+    lib().tok_nhwc_to_nchw(n, c, h * w, cp, int(dtype == BF16), _p(x), _p(out), _st())
+    return out
+
+
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.dtype = x.dtype
+        return to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return to_nchw(to_nhwc(g), ctx.dtype if ctx.dtype in (F32, BF16) else F32).to(ctx.dtype)
+
+
+class _ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return to_nchw(x, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return to_nhwc(g), None
+
+
+def to_nhwc_autograd(x):
+    if nhwc_pitch(x) is not None:
+        return x
+    return _ToNHWC.apply(x) if x.requires_grad else to_nhwc(x)
+
+
+def to_nchw_autograd(x, dtype=F32):
+    return _ToNCHW.apply(x, dtype)
+
+
+# ------------------------------------------------------------------------------------------------------ weights
+def cast_bf16(src_f32, dst_bf16=None):
+    """fp32 -> bf16 elementwise over the flat storage (memory layout preserved)."""
+    if dst_bf16 is None:
+        dst_bf16 = torch.empty_like(src_f32, dtype=BF16)
+    lib().tok_cast_f32_bf16(src_f32.numel(), _p(src_f32), _p(dst_bf16), _st())
+    return dst_bf16
+
+
+def is_krsc(w):
+    """True if a (K,C,R,S) weight tensor is stored [K][R][S][C] densely."""
+    return w.permute(0, 2, 3, 1).is_contiguous()
+
+
+def shadow_of(param):
+    """bf16 copy of an fp32 master parameter, same memory order.  Arena-managed parameters carry a persistent
+    shadow that the optimizer kernel refreshes (`_tok_shadow`); otherwise the cast runs now."""
+    sh = getattr(param, '_tok_shadow', None)
+    if sh is not None:
+        return sh
+    require_cuda(param, 'parameter')
+    return cast_bf16(param.detach())
+
+
+def grad_buffer(param):
+    """fp32 gradient accumulator of a parameter (same memory order); created zero-filled on first use."""
+    if param.grad is None:
+        param.grad = torch.zeros_like(param)  # preserve_format keeps [K][R][S][C]
+    return param.grad
+
+
+# ------------------------------------------------------------------------------------------------------ conv
+def conv_desc(n, h, w, c, k, r, s, stride, pad, dil):
+    d = tokConvDesc(n, h, w, c, k, r, s, stride, pad, dil)
+    p, q = C.c_int(), C.c_int()
+    lib().tok_conv_out_hw(C.byref(d), C.byref(p), C.byref(q))
+    return d, p.value, q.value
+
+
+def conv_fprop(d, x, w, y, stats=None, addend=None, bias=None, relu=False):
+    lib().tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), _p(stats[0]) if stats is not None else None,
+                         _p(stats[1]) if stats is not None else None, _p(addend), _p(bias), int(relu), _st())
+
+
+def conv_dgrad(d, dy, w, dx, addend=None):
+    nbytes = lib().tok_conv_dgrad_workspace_bytes(C.byref(d))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device) if nbytes else None
+    lib().tok_conv_dgrad(C.byref(d), _p(dy), _p(w), _p(dx), _p(addend), _p(ws), _st())
+
+
+def conv_wgrad(d, x, dy, dw):
+    lib().tok_conv_wgrad(C.byref(d), _p(x), _p(dy), _p(dw), _st())
+
+
+# ------------------------------------------------------------------------------------------------------ BN state
+class BNState:
+    """What a BatchNorm2d module lends to the fused conv+BN unit (torch.nn.BatchNorm2d semantics,
+    torchok/models/modules/bricks/convbnact.py:44-46)."""
+    __slots__ = ('weight', 'bias', 'running_mean', 'running_var', 'eps', 'momentum', 'training', 'acc', 'cp')
+
+    def __init__(self, weight, bias, running_mean, running_var, eps, momentum, training, acc, cp):
+        self.weight, self.bias, self.running_mean, self.running_var = weight, bias, running_mean, running_var
+        self.eps, self.momentum, self.training, self.acc, self.cp = eps, momentum, training, acc, cp
+
+
+def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
+    """conv -> BatchNorm (batch stats in training) -> (+residual) -> (ReLU).
+
+    x: NHWC activation; d: tokConvDesc for x; w: bf16 [Kp][R][S][Cp] weights; bn: BNState.
+    Returns (out, saved) where saved = (x, y, out_or_None, small) feeds `unit_backward`.
+    """
+    L = lib()
+    n, kp, (p, q) = d.n, d.k, pq
+    dev = x.device
+    y = torch.empty((n, p, q, kp), dtype=BF16, device=dev)
+    small = torch.empty((4, kp), dtype=F32, device=dev)  # scale, shift, save_mean, save_invstd
+    rows = n * p * q
+    st = _st()
+    if bn.training:
+        acc = bn.acc
+        L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), None, None, 0, st)
+        L.tok_bn_finalize_train(kp, float(rows), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias), bn.eps,
+                                bn.momentum, _p(bn.running_mean), _p(bn.running_var), _p(small[0]), _p(small[1]),
+                                _p(small[2]), _p(small[3]), st)
+    else:
+        L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), None, None, None, None, 0, st)
+        L.tok_bn_finalize_eval(kp, _p(bn.running_mean), _p(bn.running_var), _p(bn.weight), _p(bn.bias), bn.eps,
+                               _p(small[0]), _p(small[1]), st)
+    out = torch.empty_like(y) if keep else y
+    L.tok_bn_apply(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), int(relu), _p(out), st)
+    saved = (x, y, out if relu else None, small) if keep else None
+    return out.permute(0, 3, 1, 2), saved
+
+
+def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=None, want_dres=False,
+                  wgrad_into=None, dgamma=None, dbeta=None):
+    """Backward of `unit_forward`.  Returns (dx or None, dres or None).  Parameter gradients are ACCUMULATED into
+    wgrad_into / dgamma / dbeta (fp32, may be None for frozen parameters)."""
+    L = lib()
+    x, y, out, small = saved
+    kp = d.k
+    rows = y.numel() // kp
+    dev = y.device
+    st = _st()
+    acc = bn.acc
+    coefs = torch.empty((3, kp), dtype=F32, device=dev)
+    L.tok_bn_bwd_reduce(rows, kp, _p(dout), _p(dout2), _p(out), _p(y), _p(acc[2]), _p(acc[3]), st)
+    if bn.training:
+        L.tok_bn_bwd_finalize(kp, float(rows), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
+                              _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, st)
+    else:
+        # frozen statistics: dy = g * gamma * invstd; xhat uses the running stats
+        stats = torch.empty((2, kp), dtype=F32, device=dev)
+        L.tok_bn_finalize_eval(kp, _p(bn.running_mean), _p(bn.running_var), None, None, bn.eps, _p(stats[0]),
+                               _p(stats[1]), st)  # stats[0] = invstd, stats[1] = -mean*invstd
+        raise NotImplementedError('backward through eval-mode BatchNorm is not implemented yet')
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if want_dres else None
+    L.tok_bn_bwd_apply(rows, kp, _p(dout), _p(dout2), _p(out), _p(y), _p(coefs[0]), _p(coefs[1]), _p(coefs[2]),
+                       _p(dy), _p(dres), st)
+    dx = None
+    if need_dx:
+        dx = torch.empty((d.n, d.h, d.w, d.c), dtype=BF16, device=dev)
+        conv_dgrad(d, dy, w, dx, dx_addend)
+        dx = dx.permute(0, 3, 1, 2)
+    if wgrad_into is not None:
+        L.tok_conv_wgrad(C.byref(d), _p(x), _p(dy), _p(wgrad_into), st)
+    return dx, (dres.permute(0, 3, 1, 2) if dres is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------------ pooling
+def maxpool_fwd(x, k, s, pad, want_arg=True):
+    n, c, h, w = x.shape
+    cp = nhwc_pitch(x)
+    p, q = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    out = torch.empty((n, p, q, cp), dtype=BF16, device=x.device)
+    arg = torch.empty((n, p, q, cp), dtype=torch.uint8, device=x.device)
+    lib().tok_maxpool_fwd(n, h, w, cp, k, s, pad, _p(x), _p(out), _p(arg), _st())
+    o = out.permute(0, 3, 1, 2)
+    return (o if cp == c else o[:, :c]), arg
+
+
+def maxpool_bwd(dout, arg, xshape, cp, k, s, pad):
+    n, c, h, w = xshape
+    dx = torch.empty((n, h, w, cp), dtype=BF16, device=dout.device)
+    lib().tok_maxpool_bwd(n, h, w, cp, k, s, pad, _p(dout), _p(arg), _p(dx), _st())
+    o = dx.permute(0, 3, 1, 2)
+    return o if cp == c else o[:, :c]
+
+
+class MaxPoolFn(torch.autograd.Function):
+    """torch.nn.MaxPool2d (torchok/models/backbones/resnet.py:510)."""
+
+    @staticmethod
+    def forward(ctx, x, k, s, pad):
+        x = to_nhwc(x)
+        out, arg = maxpool_fwd(x, k, s, pad)
+        ctx.save_for_backward(arg)
+        ctx.meta = (tuple(x.shape), nhwc_pitch(x), k, s, pad)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        shape, cp, k, s, pad = ctx.meta
+        return maxpool_bwd(_dense_grad(g, cp), arg, shape, cp, k, s, pad), None, None, None
+
+
+def _dense_grad(g, cp=None):
+    """Incoming gradient -> NHWC bf16 with the producer's pitch (autograd may hand us anything)."""
+    g = to_nhwc(g) if nhwc_pitch(g) is None else g
+    if cp is not None and nhwc_pitch(g) != cp:
+        n, c, h, w = g.shape
+        buf = nhwc_zeros(n, c, h, w, g.device, cp)
+        buf.copy_(g)
+        g = buf
+    return g
+
+
+POOL_MODES = {'avg': 0, 'max': 1, 'avgmax': 2}
+
+
+class GlobalPoolFn(torch.autograd.Function):
+    """timm SelectAdaptivePool2d(output_size=1, flatten=True) (torchok/models/poolings/classification/pooling.py:8-12).
+    Output: (N, C) bf16."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        x = to_nhwc(x)
+        n, c, h, w = x.shape
+        cp = nhwc_pitch(x)
+        out = torch.empty((n, cp), dtype=BF16, device=x.device)
+        lib().tok_gap_fwd(n, h * w, cp, POOL_MODES[mode], _p(x), _p(out), _st())
+        ctx.meta = (n, c, h, w, cp, mode)
+        if mode != 'avg':
+            ctx.save_for_backward(x, out)
+        return out if cp == c else out[:, :c]
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w, cp, mode = ctx.meta
+        if mode != 'avg':
+            raise NotImplementedError("backward of pooling_type 'max'/'avgmax' is not implemented")
+        if cp != c:
+            gp = torch.zeros((n, cp), dtype=BF16, device=g.device)
+            gp[:, :c] = g
+            g = gp
+        g = g.to(BF16).contiguous()
+        dx = torch.empty((n, h, w, cp), dtype=BF16, device=g.device)
+        lib().tok_gap_bwd(n, h * w, cp, _p(g), _p(dx), _st())
+        o = dx.permute(0, 3, 1, 2)
+        return (o if cp == c else o[:, :c]), None
+
+
+# ------------------------------------------------------------------------------------------------------ linear
+class LinearFn(torch.autograd.Function):
+    """torch.nn.Linear (torchok/models/heads/representation/linear_head.py:25-31).  x (M, K) bf16, weight (N, K)
+    fp32 master (bf16 shadow used), bias fp32.  N is padded to a multiple of 8 inside; K must be one."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        require_cuda(x, 'linear input')
+        m, k = x.shape
+        n = weight.shape[0]
+        if k % 8:
+            raise ValueError(f'linear: in_features must be a multiple of 8 (got {k})')
+        np_ = ceil8(n)
+        x = x.to(BF16).contiguous()
+        w = padded_linear_shadow(weight)
+        b = bias
+        if bias is not None and np_ != n:
+            b = torch.zeros(np_, dtype=F32, device=x.device)
+            b[:n] = bias.detach()
+        elif bias is not None:
+            b = bias.detach().float()
+        y = torch.empty((m, np_), dtype=BF16, device=x.device)
+        lib().tok_linear_fwd(m, np_, k, _p(x), _p(w), _p(b), _p(y), _st())
+        ctx.save_for_backward(x, w)
+        ctx.params = (weight, bias)
+        ctx.dims = (m, n, np_, k)
+        return y if np_ == n else y[:, :n]
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        weight, bias = ctx.params
+        m, n, np_, k = ctx.dims
+        L = lib()
+        st = _st()
+        if np_ != n or g.dtype != BF16 or not g.is_contiguous():
+            gp = torch.zeros((m, np_), dtype=BF16, device=g.device) if np_ != n else None
+            if gp is not None:
+                gp[:, :n] = g
+                g = gp
+            else:
+                g = g.to(BF16).contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((m, k), dtype=BF16, device=g.device)
+            L.tok_linear_dgrad(m, np_, k, _p(g), _p(w), _p(dx), st)
+        if weight.requires_grad:
+            gw = grad_buffer(weight)
+            if np_ == n:
+                L.tok_linear_wgrad(m, np_, k, _p(x), _p(g), _p(gw), st)
+            else:
+                tmp = torch.zeros((np_, k), dtype=F32, device=g.device)
+                L.tok_linear_wgrad(m, np_, k, _p(x), _p(g), _p(tmp), st)
+                gw += tmp[:n]
+        if bias is not None and bias.requires_grad:
+            acc = torch.zeros((2, np_), dtype=F32, device=g.device)
+            L.tok_bn_bwd_reduce(m, np_, _p(g), None, None, _p(g), _p(acc[0]), _p(acc[1]), st)
+            grad_buffer(bias).add_(acc[0, :n])
+        return dx, None, None
+
+
+def padded_linear_shadow(weight):
+    n, k = weight.shape
+    np_ = ceil8(n)
+    if np_ == n:
+        return shadow_of(weight)
+    w = torch.zeros((np_, k), dtype=BF16, device=weight.device)
+    cast_bf16(weight.detach().contiguous(), w[:n])
+    return w
+
+
+def linear(x, weight, bias=None):
+    return LinearFn.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------------ loss
+class SoftmaxXentFn(torch.autograd.Function):
+    """torch.nn.CrossEntropyLoss(reduction='mean') (torchok/losses/__init__.py:26) on (rows, C) logits.
+    `correct` (optional int32 scalar tensor) is incremented by the number of rows whose argmax equals the target."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index, correct):
+        require_cuda(logits, 'logits')
+        rows, c = logits.shape
+        lg = logits
+        if lg.dtype != BF16 or lg.stride(1) != 1:
+            lg = lg.to(BF16).contiguous()
+        target = target.long().contiguous()
+        loss = torch.zeros((), dtype=F32, device=lg.device)
+        lib().tok_softmax_xent(rows, c, lg.stride(0), _p(lg), _p(target), _p(loss), None, 1.0 / rows, 0.0, None,
+                               ignore_index, _p(correct), _st())
+        ctx.save_for_backward(lg, target)
+        ctx.meta = (rows, c, ignore_index, logits.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, target = ctx.saved_tensors
+        rows, c, ignore_index, in_dtype = ctx.meta
+        ld = lg.stride(0)
+        dlog = torch.empty((rows, ld), dtype=BF16, device=lg.device)
+        if ld != c:
+            dlog.zero_()
+        # g is the scalar JointLoss weight chain (torchok/losses/base.py:80); read on the device by the kernel.
+        g = g.to(F32).contiguous()
+        lib().tok_softmax_xent(rows, c, ld, _p(lg), _p(target), None, _p(dlog), 0.0, 1.0 / rows, _p(g), ignore_index,
+                               None, _st())
+        d = dlog if ld == c else dlog[:, :c]
+        return (d if in_dtype == BF16 else d.to(in_dtype)), None, None, None
+
+
+def softmax_xent(logits, target, ignore_index=-100, correct=None):
+    return SoftmaxXentFn.apply(logits, target, ignore_index, correct)
+
+
+def l2_normalize(x):
+    raise NotImplementedError('l2_normalize kernel not built yet')
+
+
+def softmax_xent_nhwc(logits, target, ignore_index=-100):
+    raise NotImplementedError('softmax_xent_nhwc kernel not built yet')

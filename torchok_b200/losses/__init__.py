@@ -1,0 +1,3 @@
+from ..constructor import LOSSES
+from .base import JointLoss  # noqa: F401
+from .classification import CrossEntropyLoss  # noqa: F401

@@ -1,0 +1,404 @@
+"""Parameter-holding layers and the fused autograd Functions built on libtokb200.
+
+`Conv2d` / `BatchNorm2d` subclass the torch modules only to keep parameter names, shapes, init code and
+`isinstance` checks of reference-style code working (state-dict contract); their arithmetic never goes
+through torch.nn.functional.  The unit of execution is conv -> BN -> (+shortcut) -> (ReLU)
+(torchok/models/modules/bricks/convbnact.py:48-53; timm BasicBlock/Bottleneck as built by
+torchok/models/backbones/resnet.py:363-405), run as a sequence of C-ABI calls by one autograd Function per unit, per
+residual block, or per stem.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from ... import kernels as K
+from ..._lib import lib
+
+BF16, F32 = K.BF16, K.F32
+
+
+def _single(v, what):
+    if isinstance(v, (tuple, list)):
+        if len(set(v)) != 1:
+            raise NotImplementedError(f'{what} must be the same along H and W (got {v})')
+        v = v[0]
+    return int(v)
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d parameters (weight OIHW fp32, optional bias) stored in [K][R][S][C] memory; computed by
+    tok_conv_fprop / tok_conv_dgrad / tok_conv_wgrad."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 padding_mode='zeros', device=None, dtype=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         padding_mode, device, dtype)
+        if groups != 1:
+            raise NotImplementedError('torchok_b200.Conv2d: grouped convolution is out of scope (SURVEY §2)')
+        if padding_mode != 'zeros' or isinstance(padding, str):
+            raise NotImplementedError('torchok_b200.Conv2d: only explicit zero padding')
+        self.tok_stride = _single(self.stride, 'stride')
+        self.tok_pad = _single(self.padding, 'padding')
+        self.tok_dil = _single(self.dilation, 'dilation')
+        self.cin_p, self.cout_p = K.ceil8(in_channels), K.ceil8(out_channels)
+        self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
+        self._descs = {}
+
+    def desc(self, x):
+        n, _, h, w = x.shape
+        key = (n, h, w)
+        hit = self._descs.get(key)
+        if hit is None:
+            r, s = self.kernel_size
+            d, p, q = K.conv_desc(n, h, w, self.cin_p, self.cout_p, r, s, self.tok_stride, self.tok_pad, self.tok_dil)
+            hit = self._descs[key] = (d, (p, q))
+        return hit
+
+    @property
+    def padded(self):
+        return self.cin_p != self.in_channels or self.cout_p != self.out_channels
+
+    def shadow(self):
+        """bf16 [Kp][R][S][Cp] weights for the kernels."""
+        w = self.weight
+        if not K.is_krsc(w):
+            w.data = w.data.contiguous(memory_format=torch.channels_last)
+            if not K.is_krsc(w):  # 1x1 / single-channel corner cases of torch's stride normalisation
+                w.data = w.data.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        if not self.padded:
+            return K.shadow_of(w)
+        r, s = self.kernel_size
+        full = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=BF16, device=w.device)
+        tmp = K.cast_bf16(w.detach())
+        full[:self.out_channels, :, :, :self.in_channels] = tmp.permute(0, 2, 3, 1)
+        return full
+
+    def wgrad_target(self):
+        """(buffer the wgrad kernel accumulates into, finish()) — the parameter's own fp32 .grad when unpadded."""
+        if not self.weight.requires_grad:
+            return None, None
+        g = K.grad_buffer(self.weight)
+        if not self.padded and K.is_krsc(g):
+            return g, None
+        r, s = self.kernel_size
+        tmp = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=F32, device=g.device)
+
+        def finish():
+            g.add_(tmp[:self.out_channels, :, :, :self.in_channels].permute(0, 3, 1, 2))
+        return tmp, finish
+
+    def forward(self, x):
+        return ConvFn.apply(x, self, False, self.weight, self.bias)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d parameters/buffers; the statistics, normalisation and backward run in tok_bn_* kernels fused
+    around the producing convolution."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True, device=None,
+                 dtype=None):
+        super().__init__(num_features, eps, momentum, affine, track_running_stats, device, dtype)
+        if not (affine and track_running_stats) or momentum is None:
+            raise NotImplementedError('torchok_b200.BatchNorm2d: affine=True, track_running_stats=True, momentum set')
+        self.cp = K.ceil8(num_features)
+        # fwd sum / sqsum, bwd sum_g / sum_gy: zero between uses (the finalize kernels hand them back zeroed)
+        self.register_buffer('_tok_acc', torch.zeros(4, self.cp), persistent=False)
+        self._pending_batches = 0
+        self._register_state_dict_hook(_flush_batches)
+
+    def state(self):
+        if self._tok_acc.dtype != F32:
+            self._tok_acc = self._tok_acc.float()
+        if self.cp != self.num_features:
+            raise NotImplementedError('BatchNorm2d with a channel count that is not a multiple of 8 goes through '
+                                      'PaddedBatchNorm state (see state_padded)')
+        if self.training:
+            self._pending_batches += 1
+        return K.BNState(self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+                         self.training, self._tok_acc, self.cp)
+
+    def forward(self, x):
+        raise NotImplementedError('torchok_b200.BatchNorm2d is executed fused with its producer conv '
+                                  '(use conv_bn_act / ConvBnAct), not stand-alone')
+
+
+def _flush_batches(module, state_dict, prefix, local_metadata):
+    if module._pending_batches:
+        module.num_batches_tracked += module._pending_batches
+        module._pending_batches = 0
+        state_dict[prefix + 'num_batches_tracked'] = module.num_batches_tracked
+    return state_dict
+
+
+def _bn_grads(bn):
+    gw = K.grad_buffer(bn.weight) if bn.weight.requires_grad else None
+    gb = K.grad_buffer(bn.bias) if bn.bias.requires_grad else None
+    return gw, gb
+
+
+def _unit_fwd(x, conv, bn, relu, residual, keep):
+    d, pq = conv.desc(x)
+    return K.unit_forward(x, d, pq, conv.shadow(), bn.state(), relu, residual, keep), d
+
+
+def _unit_bwd(saved, d, conv, bn, dout, **kw):
+    wbuf, finish = conv.wgrad_target()
+    gw, gb = _bn_grads(bn)
+    st = K.BNState(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, bn.training,
+                   bn._tok_acc, bn.cp)
+    out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb, **kw)
+    if finish:
+        finish()
+    return out
+
+
+def _params(*mods):
+    ps = []
+    for m in mods:
+        if m is not None:
+            ps.extend(p for p in m.parameters(recurse=False))
+    return ps
+
+
+# ------------------------------------------------------------------------------------------------------ single unit
+class ConvBnActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, conv, bn, relu, keep, *params):
+        x = K.to_nhwc(x)
+        if residual is not None:
+            residual = K.to_nhwc(residual)
+        (out, saved), d = _unit_fwd(x, conv, bn, relu, residual, keep)
+        if keep:
+            ctx.mods = (conv, bn, d, residual is not None)
+            ctx.has_out = saved[2] is not None
+            ctx.save_for_backward(*[t for t in saved if t is not None])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        conv, bn, d, has_res = ctx.mods
+        t = list(ctx.saved_tensors)
+        saved = (t[0], t[1], t[2] if ctx.has_out else None, t[-1])
+        dout = K._dense_grad(dout, d.k)
+        dx, dres = _unit_bwd(saved, d, conv, bn, dout, need_dx=ctx.needs_input_grad[0], want_dres=has_res)
+        return (dx, dres, None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 6)
+
+
+def conv_bn_act(x, conv, bn, relu=True, residual=None):
+    params = _params(conv, bn)
+    keep = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+    return ConvBnActFn.apply(x, residual, conv, bn, relu, keep, *params)
+
+
+class ConvFn(torch.autograd.Function):
+    """Plain convolution (+bias) (+ReLU) without normalisation: heads and FPN-style convs."""
+
+    @staticmethod
+    def forward(ctx, x, conv, relu, weight, bias):
+        x = K.to_nhwc(x)
+        d, (p, q) = conv.desc(x)
+        w = conv.shadow()
+        b = bias
+        if bias is not None:
+            b = bias.detach().float()
+            if conv.cout_p != conv.out_channels:
+                b = torch.zeros(conv.cout_p, dtype=F32, device=x.device)
+                b[:conv.out_channels] = bias.detach()
+        y = torch.empty((d.n, p, q, d.k), dtype=BF16, device=x.device)
+        K.conv_fprop(d, x, w, y, bias=b, relu=relu)
+        ctx.conv, ctx.d, ctx.relu = conv, d, relu
+        ctx.save_for_backward(x, y if relu else None)
+        out = y.permute(0, 3, 1, 2)
+        return out if conv.cout_p == conv.out_channels else out[:, :conv.out_channels]
+
+    @staticmethod
+    def backward(ctx, dout):
+        conv, d = ctx.conv, ctx.d
+        x, y = ctx.saved_tensors
+        if ctx.relu:
+            raise NotImplementedError('backward of conv+ReLU without BatchNorm')
+        dy = K._dense_grad(dout, d.k)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxb = torch.empty((d.n, d.h, d.w, d.c), dtype=BF16, device=dy.device)
+            K.conv_dgrad(d, dy, conv.shadow(), dxb)
+            dx = dxb.permute(0, 3, 1, 2)
+            if conv.cin_p != conv.in_channels:
+                dx = dx[:, :conv.in_channels]
+        wbuf, finish = conv.wgrad_target()
+        if wbuf is not None:
+            K.conv_wgrad(d, x, dy, wbuf)
+            if finish:
+                finish()
+        if conv.bias is not None and conv.bias.requires_grad:
+            rows = dy.numel() // d.k
+            acc = torch.zeros((2, d.k), dtype=F32, device=dy.device)
+            lib().tok_bn_bwd_reduce(rows, d.k, K._p(dy), None, None, K._p(dy), K._p(acc[0]), K._p(acc[1]), K._st())
+            K.grad_buffer(conv.bias).add_(acc[0, :conv.out_channels])
+        return dx, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------ residual block
+class ResidualBlockFn(torch.autograd.Function):
+    """A whole timm BasicBlock / Bottleneck (torchok/models/backbones/resnet.py:14, built at :393-398):
+    units[0..n-2] are conv+BN+ReLU, units[n-1] is conv+BN, then `+ shortcut` and ReLU; shortcut = x or
+    downsample conv+BN.  One Function per block so that the two gradient paths into x are merged by the dgrad
+    epilogue (`addend`) instead of a separate add pass."""
+
+    @staticmethod
+    def forward(ctx, x, block, keep, *params):
+        x = K.to_nhwc(x)
+        units = block.tok_units()
+        ds = block.tok_downsample()
+        saved_all, descs = [], []
+        sc = x
+        if ds is not None:
+            (sc, sv), d = _unit_fwd(x, ds[0], ds[1], False, None, keep)
+            saved_all.append(sv)
+            descs.append(d)
+        h = x
+        for conv, bn in units[:-1]:
+            (h, sv), d = _unit_fwd(h, conv, bn, True, None, keep)
+            saved_all.append(sv)
+            descs.append(d)
+        conv, bn = units[-1]
+        (out, sv), d = _unit_fwd(h, conv, bn, True, sc, keep)
+        saved_all.append(sv)
+        descs.append(d)
+        if keep:
+            flat, layout = [], []
+            for sv in saved_all:
+                layout.append(tuple(t is not None for t in sv))
+                flat.extend(t for t in sv if t is not None)
+            ctx.save_for_backward(*flat)
+            ctx.layout, ctx.descs, ctx.block = layout, descs, block
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        block, descs = ctx.block, ctx.descs
+        units = block.tok_units()
+        ds = block.tok_downsample()
+        it = iter(ctx.saved_tensors)
+        saved_all = [tuple(next(it) if present else None for present in lay) for lay in ctx.layout]
+        off = 1 if ds is not None else 0
+        dout = K._dense_grad(dout, descs[-1].k)
+        # last unit: ReLU mask from the block output, g flows to the shortcut
+        conv, bn = units[-1]
+        dh, g = _unit_bwd(saved_all[-1], descs[-1], conv, bn, dout, want_dres=True)
+        for i in range(len(units) - 2, 0, -1):
+            conv, bn = units[i]
+            dh, _ = _unit_bwd(saved_all[off + i], descs[off + i], conv, bn, dh)
+        need_dx = ctx.needs_input_grad[0]
+        addend = g
+        if ds is not None:
+            addend, _ = _unit_bwd(saved_all[0], descs[0], ds[0], ds[1], g, need_dx=need_dx)
+        conv, bn = units[0]
+        dx, _ = _unit_bwd(saved_all[off], descs[off], conv, bn, dh, need_dx=need_dx, dx_addend=addend)
+        return (dx, None, None) + (None,) * (len(ctx.needs_input_grad) - 3)
+
+
+def residual_block(x, block):
+    params = [p for p in block.parameters()]
+    keep = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+    return ResidualBlockFn.apply(x, block, keep, *params)
+
+
+# ------------------------------------------------------------------------------------------------------ ResNet stem
+class StemFn(torch.autograd.Function):
+    """conv 7x7 s2 p3 (Cin <= 4) -> BN -> ReLU -> maxpool 3x3 s2 p1 (torchok/models/backbones/resnet.py:488-490,510,
+    542-545).  Returns (act1, pooled); the image is consumed straight from its NCHW fp32/bf16 layout."""
+
+    @staticmethod
+    def forward(ctx, image, conv, bn, pool, keep, *params):
+        K.require_cuda(image, 'image')
+        L = lib()
+        st = K._st()
+        n, c, h, w = image.shape
+        if image.dtype not in (F32, BF16):
+            image = image.float()
+        image = image.contiguous()
+        k = conv.out_channels
+        P, Q, H2, W2 = (C.c_int() for _ in range(4))
+        L.tok_stem_geometry(h, w, C.byref(P), C.byref(Q), C.byref(H2), C.byref(W2))
+        P, Q, H2, W2 = P.value, Q.value, H2.value, W2.value
+        dev = image.device
+        xs2d = torch.empty((n, H2, W2, 16), dtype=BF16, device=dev)
+        L.tok_stem_pack_input(n, c, h, w, int(image.dtype == BF16), K._p(image), K._p(xs2d), st)
+        wp = torch.empty((k, 256), dtype=BF16, device=dev)
+        wt = conv.weight
+        if not K.is_krsc(wt):
+            wt.data = wt.data.contiguous(memory_format=torch.channels_last)
+        L.tok_stem_pack_weight(k, c, K._p(wt), K._p(wp), st)
+        bs = bn.state()
+        y = torch.empty((n, P, Q, k), dtype=BF16, device=dev)
+        small = torch.empty((4, k), dtype=F32, device=dev)
+        rows = n * P * Q
+        if bs.training:
+            L.tok_stem_conv_fprop(n, h, w, k, K._p(xs2d), K._p(wp), K._p(y), K._p(bs.acc[0]), K._p(bs.acc[1]), st)
+            L.tok_bn_finalize_train(k, float(rows), K._p(bs.acc[0]), K._p(bs.acc[1]), K._p(bs.weight), K._p(bs.bias),
+                                    bs.eps, bs.momentum, K._p(bs.running_mean), K._p(bs.running_var), K._p(small[0]),
+                                    K._p(small[1]), K._p(small[2]), K._p(small[3]), st)
+        else:
+            L.tok_stem_conv_fprop(n, h, w, k, K._p(xs2d), K._p(wp), K._p(y), None, None, st)
+            L.tok_bn_finalize_eval(k, K._p(bs.running_mean), K._p(bs.running_var), K._p(bs.weight), K._p(bs.bias),
+                                   bs.eps, K._p(small[0]), K._p(small[1]), st)
+        act = torch.empty_like(y) if keep else y
+        L.tok_bn_apply(rows, k, K._p(y), K._p(small[0]), K._p(small[1]), None, 1, K._p(act), st)
+        act = act.permute(0, 3, 1, 2)
+        pk, ps, pp = pool
+        pooled, arg = K.maxpool_fwd(act, pk, ps, pp)
+        if keep:
+            ctx.save_for_backward(xs2d, y, act, small, arg)
+            ctx.meta = (conv, bn, pool, (n, c, h, w), (P, Q))
+        return act, pooled
+
+    @staticmethod
+    def backward(ctx, d_act, d_pooled):
+        conv, bn, (pk, ps, pp), (n, c, h, w), (P, Q) = ctx.meta
+        xs2d, y, act, small, arg = ctx.saved_tensors
+        L = lib()
+        st = K._st()
+        k = conv.out_channels
+        dev = y.device
+        rows = n * P * Q
+        dout = K.maxpool_bwd(K._dense_grad(d_pooled, k), arg, (n, k, P, Q), k, pk, ps, pp)
+        dout2 = K._dense_grad(d_act, k) if d_act is not None else None
+        acc = bn._tok_acc
+        gw, gb = _bn_grads(bn)
+        coefs = torch.empty((3, k), dtype=F32, device=dev)
+        L.tok_bn_bwd_reduce(rows, k, K._p(dout), K._p(dout2), K._p(act), K._p(y), K._p(acc[2]), K._p(acc[3]), st)
+        L.tok_bn_bwd_finalize(k, float(rows), K._p(acc[2]), K._p(acc[3]), K._p(small[2]), K._p(small[3]),
+                              K._p(bn.weight), K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(gw), K._p(gb), 1,
+                              st)
+        dy = torch.empty_like(y)
+        L.tok_bn_bwd_apply(rows, k, K._p(dout), K._p(dout2), K._p(act), K._p(y), K._p(coefs[0]), K._p(coefs[1]),
+                           K._p(coefs[2]), K._p(dy), None, st)
+        if conv.weight.requires_grad:
+            dwp = torch.zeros((k, 256), dtype=F32, device=dev)
+            L.tok_stem_conv_wgrad(n, h, w, k, K._p(xs2d), K._p(dy), K._p(dwp), st)
+            L.tok_stem_unpack_wgrad(k, c, K._p(dwp), K._p(K.grad_buffer(conv.weight)), 1, st)
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError('gradient w.r.t. the input image is not produced by the stem kernel')
+        return (None,) * len(ctx.needs_input_grad)
+
+
+def stem(image, conv, bn, pool=(3, 2, 1)):
+    params = _params(conv, bn)
+    keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return StemFn.apply(image, conv, bn, pool, keep, *params)
+
+
+# ------------------------------------------------------------------------------------------------------ small modules
+class ReLU(nn.ReLU):
+    """Marker module: the ReLU itself is applied inside the fused unit that precedes it."""
+
+    def forward(self, x):
+        return x
+
+
+class MaxPool2d(nn.MaxPool2d):
+    def forward(self, x):
+        return K.MaxPoolFn.apply(x, _single(self.kernel_size, 'kernel_size'), _single(self.stride, 'stride'),
+                                 _single(self.padding, 'padding'))
