@@ -138,6 +138,17 @@ int tok_sgd_step(long long n, float* param, const float* grad, float* momentum_b
 int tok_adam_step(long long n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, int step,
                   float grad_scale, void* stream);
+/* Graph-replayable forms used by the CUDA-stream step loop (replaces Lightning's optimizer_step around
+ * torchok/tasks/base.py:125-133): the learning rate and the step counter live in device memory (lr_dev[0];
+ * step_dev[0] is advanced by one on the device before it is used, so bias correction / first-step momentum follow
+ * the replay count), and with zero_grad != 0 the consumed gradient arena is cleared for the next step's atomic
+ * accumulation. */
+int tok_sgd_step_dev(long long n, float* param, float* grad, float* momentum_buf, void* shadow_bf16,
+                     const float* lr_dev, int* step_dev, float momentum, float weight_decay, float dampening,
+                     int nesterov, float grad_scale, int zero_grad, void* stream);
+int tok_adam_step_dev(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                      const float* lr_dev, int* step_dev, float beta1, float beta2, float eps, float weight_decay,
+                      int decoupled, float grad_scale, int zero_grad, void* stream);
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream);
 
 #ifdef __cplusplus

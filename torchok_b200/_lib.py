@@ -67,6 +67,8 @@ _SIGS = {
     'tok_nhwc_to_nchw': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_sgd_step': (_i, [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),
     'tok_adam_step': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _i, _f, _vp]),
+    'tok_sgd_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _i, _vp]),
+    'tok_adam_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
 }
 _RAW = {'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',

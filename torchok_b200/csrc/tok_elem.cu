@@ -658,6 +658,58 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
     if (shadow) shadow[i] = __float2bfloat16(w);
   }
 }
+// Graph-replayable variants: lr and the step counter are read from device memory (the counter is advanced by
+// step_advance_kernel just before), and the consumed gradient is zeroed for the next step's atomic accumulation.
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+
+__global__ void sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf,
+                                    __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
+                                    const int* __restrict__ step_dev, float mu, float wd, float damp, int nesterov,
+                                    float gscale, int zero_grad) {
+  const float lr = __ldg(lr_dev);
+  const bool first = __ldg(step_dev) <= 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i];
+    float d = g[i] * gscale + wd * w;
+    if (zero_grad) g[i] = 0.f;
+    if (mu != 0.f) {
+      const float b = first ? d : mu * buf[i] + (1.f - damp) * d;
+      buf[i] = b;
+      d = nesterov ? d + mu * b : b;
+    }
+    w -= lr * d;
+    p[i] = w;
+    if (shadow) shadow[i] = __float2bfloat16(w);
+  }
+}
+__global__ void adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                     float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n,
+                                     const float* __restrict__ lr_dev, const int* __restrict__ step_dev, float b1,
+                                     float b2, float eps, float wd, int decoupled, float gscale, int zero_grad) {
+  const float lr = __ldg(lr_dev);
+  const float t = (float)__ldg(step_dev);
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step = lr / bc1;
+  const float rbc2 = rsqrtf(bc2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float w = p[i];
+    float d = g[i] * gscale;
+    if (zero_grad) g[i] = 0.f;
+    if (decoupled)
+      w *= 1.f - lr * wd;
+    else
+      d += wd * w;
+    const float mi = b1 * m[i] + (1.f - b1) * d;
+    const float vi = b2 * v[i] + (1.f - b2) * d * d;
+    m[i] = mi;
+    v[i] = vi;
+    w -= step * mi / (sqrtf(vi) * rbc2 + eps);
+    p[i] = w;
+    if (shadow) shadow[i] = __float2bfloat16(w);
+  }
+}
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -896,6 +948,32 @@ int tok_adam_step(long long n, float* param, const float* grad, float* exp_avg, 
       param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, decoupled,
       bc1, bc2, grad_scale);
   TOK_CHECK_LAUNCH("adam_step");
+  return TOK_OK;
+}
+
+int tok_sgd_step_dev(long long n, float* param, float* grad, float* momentum_buf, void* shadow_bf16,
+                     const float* lr_dev, int* step_dev, float momentum, float weight_decay, float dampening,
+                     int nesterov, float grad_scale, int zero_grad, void* stream) {
+  if (n <= 0) return TOK_OK;
+  if (!lr_dev || !step_dev) return set_error(TOK_ERR_INVALID, "sgd_step_dev: lr_dev and step_dev are required");
+  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  sgd_step_dev_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, momentum_buf, (__nv_bfloat16*)shadow_bf16, n, lr_dev, step_dev, momentum, weight_decay, dampening,
+      nesterov, grad_scale, zero_grad);
+  TOK_CHECK_LAUNCH("sgd_step_dev");
+  return TOK_OK;
+}
+
+int tok_adam_step_dev(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                      const float* lr_dev, int* step_dev, float beta1, float beta2, float eps, float weight_decay,
+                      int decoupled, float grad_scale, int zero_grad, void* stream) {
+  if (n <= 0) return TOK_OK;
+  if (!lr_dev || !step_dev) return set_error(TOK_ERR_INVALID, "adam_step_dev: lr_dev and step_dev are required");
+  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  adam_step_dev_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr_dev, step_dev, beta1, beta2, eps,
+      weight_decay, decoupled, grad_scale, zero_grad);
+  TOK_CHECK_LAUNCH("adam_step_dev");
   return TOK_OK;
 }
 

@@ -1,0 +1,326 @@
+"""The CUDA-stream step loop that replaces Lightning's fit loop for the hot path.
+
+Reference behaviour replaced (torchok/tasks/base.py:125-133 `training_step`, :163-173 per-step all_gather, Lightning's
+automatic optimisation + DDP): per step  zero_grad -> forward_with_gt -> JointLoss -> backward -> (gradient
+all-reduce) -> optimizer.step.  Here:
+
+  * `ParamArena` re-homes every trainable parameter into ONE flat fp32 buffer (memory order preserved, so conv
+    weights stay [K][R][S][C]), with a matching flat fp32 gradient arena the wgrad kernels accumulate into and a flat
+    bf16 shadow arena the conv/linear kernels read.  state_dict keys / shapes are unchanged.
+  * `ArenaSGD` / `ArenaAdam` run torch.optim.SGD / Adam(W) arithmetic over the whole arena in one kernel that also
+    refreshes the bf16 shadow and clears the consumed gradient (tok_sgd_step_dev / tok_adam_step_dev) — one parameter
+    group with shared hyper-parameters, which is what the reference's Constructor builds from the example YAMLs
+    (constructor.py:151-156).
+  * data parallelism = one process per GPU; gradients are summed with ONE NCCL all-reduce per gradient bucket
+    (contiguous slices of the gradient arena) issued on a communication stream as soon as the backward pass has
+    produced every gradient of the bucket; BatchNorm statistics stay local (sync_batchnorm default False,
+    config_structure.py:170).  The reference's per-step loss all_gather (base.py:170) is dropped: the loss stays on
+    the device and is reduced only when read.
+  * the whole step (forward, loss, backward, all-reduce, optimizer) is captured once into a CUDA graph and replayed.
+"""
+import math
+import os
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import kernels as K
+from ._lib import lib
+
+F32, BF16 = torch.float32, torch.bfloat16
+_ALIGN = 64  # elements; keeps every bf16 shadow 128-byte aligned for TMA
+
+
+def _round_up(n, a):
+    return (n + a - 1) // a * a
+
+
+class ParamArena:
+    def __init__(self, module, bucket_mb=32.0):
+        params, seen = [], set()
+        for p in module.parameters():
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        if not params:
+            raise ValueError('ParamArena: module has no trainable parameters')
+        dev = params[0].device
+        K.require_cuda(params[0], 'parameter')
+        offs, total = [], 0
+        for p in params:
+            if p.dtype != F32:
+                raise TypeError('ParamArena expects fp32 master parameters')
+            if not torch.ops.aten.is_non_overlapping_and_dense(p):
+                p.data = p.data.contiguous()
+            offs.append(total)
+            total += _round_up(p.numel(), _ALIGN)
+        self.params, self.offsets, self.numel = params, offs, total
+        self.master = torch.zeros(total, dtype=F32, device=dev)
+        self.grad = torch.zeros(total, dtype=F32, device=dev)
+        self.shadow = torch.zeros(total, dtype=BF16, device=dev)
+        for p, off in zip(params, offs):
+            shape, stride = tuple(p.shape), tuple(p.stride())
+            view = torch.as_strided(self.master, shape, stride, off)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = torch.as_strided(self.grad, shape, stride, off)
+            p._tok_shadow = torch.as_strided(self.shadow, shape, stride, off)
+        self.refresh_shadow()
+        # gradient buckets: contiguous arena slices, cut at parameter boundaries
+        limit = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.buckets = []  # (begin, end, [param indices])
+        begin, members = 0, []
+        for i, (p, off) in enumerate(zip(params, offs)):
+            end = off + _round_up(p.numel(), _ALIGN)
+            members.append(i)
+            if end - begin >= limit or i == len(params) - 1:
+                self.buckets.append((begin, end, members))
+                begin, members = end, []
+        for b, (_, _, members) in enumerate(self.buckets):
+            for i in members:
+                params[i]._tok_bucket = (self, b)
+        self._pending = [len(m) for _, _, m in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self.reducer = None
+
+    def refresh_shadow(self):
+        K.cast_bf16(self.master, self.shadow)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    # -- bucket readiness (called from the backward Functions through kernels.grad_ready) --------------------------
+    def begin_step(self):
+        self._pending = [len(m) for _, _, m in self.buckets]
+        self._launched = [False] * len(self.buckets)
+
+    def ready(self, b):
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self.reducer is not None and not self._launched[b]:
+            self._launched[b] = True
+            self.reducer.launch(b)
+
+    def finish(self):
+        """Reduce whatever has not been reduced yet (parameters whose backward did not announce itself)."""
+        if self.reducer is not None:
+            for b in range(len(self.buckets)):
+                if not self._launched[b]:
+                    self._launched[b] = True
+                    self.reducer.launch(b)
+            self.reducer.join()
+
+
+class BucketAllReduce:
+    """One NCCL all-reduce (sum) per gradient bucket, on a side stream, overlapped with the rest of backward."""
+
+    def __init__(self, arena, group=None):
+        self.arena, self.group = arena, group
+        self.world = dist.get_world_size(group)
+        self.comm_stream = torch.cuda.Stream()
+        self._events = []
+        arena.reducer = self
+
+    def launch(self, b):
+        begin, end, _ = self.arena.buckets[b]
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.arena.grad[begin:end], op=dist.ReduceOp.SUM, group=self.group)
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+
+class _ArenaOptimizer:
+    def __init__(self, arena, lr):
+        self.arena = arena
+        dev = arena.master.device
+        self.lr_dev = torch.tensor([float(lr)], dtype=F32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._lr = float(lr)
+        self.grad_scale = 1.0
+
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        """Schedulers write here; the value reaches the (possibly graph-captured) kernel through device memory."""
+        self._lr = float(value)
+        self.lr_dev.fill_(self._lr)
+
+    @property
+    def param_groups(self):  # enough of the torch.optim surface for lr schedulers that only touch 'lr'
+        return [{'lr': self._lr, 'params': self.arena.params}]
+
+    def zero_grad(self, set_to_none=False):
+        self.arena.zero_grad()
+
+
+class ArenaSGD(_ArenaOptimizer):
+    """torch.optim.SGD (registered in torchok/optim/optimizers/__init__.py:9-19) over the flat arena."""
+
+    def __init__(self, arena, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, **unused):
+        super().__init__(arena, lr)
+        self.momentum, self.dampening, self.weight_decay, self.nesterov = momentum, dampening, weight_decay, nesterov
+        self.buf = torch.zeros_like(arena.master) if momentum != 0 else None
+
+    def step(self):
+        a = self.arena
+        lib().tok_sgd_step_dev(a.numel, K._p(a.master), K._p(a.grad), K._p(self.buf), K._p(a.shadow),
+                               K._p(self.lr_dev), K._p(self.step_dev), self.momentum, self.weight_decay,
+                               self.dampening, int(self.nesterov), self.grad_scale, 1, K._st())
+
+
+class ArenaAdam(_ArenaOptimizer):
+    """torch.optim.Adam / AdamW (amsgrad off) over the flat arena."""
+
+    def __init__(self, arena, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, **unused):
+        super().__init__(arena, lr)
+        self.betas, self.eps, self.weight_decay, self.decoupled = tuple(betas), eps, weight_decay, decoupled
+        self.exp_avg = torch.zeros_like(arena.master)
+        self.exp_avg_sq = torch.zeros_like(arena.master)
+
+    def step(self):
+        a = self.arena
+        lib().tok_adam_step_dev(a.numel, K._p(a.master), K._p(a.grad), K._p(self.exp_avg), K._p(self.exp_avg_sq),
+                                K._p(a.shadow), K._p(self.lr_dev), K._p(self.step_dev), self.betas[0], self.betas[1],
+                                self.eps, self.weight_decay, int(self.decoupled), self.grad_scale, 1, K._st())
+
+
+def build_optimizer(arena, name, params):
+    params = dict(params or {})
+    if name == 'SGD':
+        return ArenaSGD(arena, **params)
+    if name == 'Adam':
+        return ArenaAdam(arena, decoupled=False, **params)
+    if name == 'AdamW':
+        params.setdefault('weight_decay', 1e-2)
+        return ArenaAdam(arena, decoupled=True, **params)
+    raise NotImplementedError(f'optimizer {name}: the arena step kernels cover SGD, Adam and AdamW')
+
+
+class StreamLoop:
+    """Drives `task.training_step` as a captured CUDA graph.
+
+        loop = StreamLoop(task, optimizer=dict(name='SGD', params=dict(lr=0.1, momentum=0.9, weight_decay=1e-4)))
+        loss = loop.train_step({'image': pinned_cpu_or_cuda_tensor, 'target': ...})   # device scalar
+
+    With torch.distributed initialised (NCCL), gradients are averaged over ranks bucket by bucket.
+    """
+
+    def __init__(self, task, optimizer=None, use_graph=True, bucket_mb=32.0, warmup=3):
+        self.task = task
+        self.device = next(task.parameters()).device
+        K.require_cuda(next(task.parameters()), 'task')
+        lib()  # fail now, loudly, if the extension is missing
+        if optimizer is None:
+            opt_cfg = (task.hparams.get('optimization') or [None])[0]
+            if opt_cfg is None:
+                raise ValueError('StreamLoop needs an optimizer (argument or hparams.optimization[0].optimizer)')
+            optimizer = opt_cfg['optimizer']
+        self.arena = ParamArena(task, bucket_mb=bucket_mb)
+        self.optimizer = build_optimizer(self.arena, optimizer['name'], optimizer.get('params'))
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            BucketAllReduce(self.arena)
+            self.optimizer.grad_scale = 1.0 / self.world
+            with torch.no_grad():  # replicas start from rank 0's weights (DDP's initial broadcast)
+                dist.broadcast(self.arena.master, 0)
+                for b in task.buffers():
+                    if b.is_cuda and b.is_floating_point():
+                        dist.broadcast(b, 0)
+            self.arena.refresh_shadow()
+        self.use_graph = use_graph and os.environ.get('TOK_NO_GRAPH', '0') != '1'
+        self.warmup = warmup
+        self.graph = None
+        self.static = None
+        self.loss = None
+        self.outputs = None
+        self.steps = 0
+        self.stream = torch.cuda.Stream()
+        self._bns = [m for m in task.modules() if isinstance(m, nn.BatchNorm2d) and hasattr(m, '_pending_batches')]
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _eager_step(self, batch):
+        self.arena.begin_step()
+        out = self.task.training_step(batch)
+        out['loss'].backward()
+        self.arena.finish()
+        self.optimizer.step()
+        return out
+
+    def _stage(self, batch):
+        """Copy a batch (pinned host or device tensors) into the static device buffers the graph reads."""
+        if self.static is None:
+            self.static = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                           for k, v in batch.items() if torch.is_tensor(v)}
+        for k, dst in self.static.items():
+            src = batch[k]
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        return self.static
+
+    def train_step(self, batch):
+        self.task.train()
+        if not self.use_graph:
+            dev_batch = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v)
+                         for k, v in batch.items()}
+            out = self._eager_step(dev_batch)
+            self.steps += 1
+            self.loss = out['loss'].detach()
+            return self.loss
+        cur = torch.cuda.current_stream()
+        if self.graph is None:
+            # Warm-up steps (needed before capture: lazy kernel attributes, allocator pools, NCCL channels) run on
+            # a snapshot of the training state which is restored afterwards, so the first replay below IS step 1.
+            static = self._stage(batch)
+            snap = self._snapshot()
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                for _ in range(self.warmup):
+                    self._eager_step(static)
+            cur.wait_stream(self.stream)
+            torch.cuda.synchronize()
+            self._restore(snap)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                out = self._eager_step(static)
+                self.loss = out['loss'].detach()
+            self.graph = g
+            self._restore(snap)
+            del snap
+        self._stage(batch)
+        self.graph.replay()
+        self.steps += 1
+        for m in self._bns:
+            m._pending_batches += 1
+        return self.loss
+
+    def _state_tensors(self):
+        opt = self.optimizer
+        ts = [self.arena.master, self.arena.grad, opt.step_dev]
+        ts += [t for t in (getattr(opt, 'buf', None), getattr(opt, 'exp_avg', None), getattr(opt, 'exp_avg_sq', None))
+               if t is not None]
+        ts += [b for b in self.task.buffers() if b.is_cuda]
+        return ts
+
+    def _snapshot(self):
+        return [t.clone() for t in self._state_tensors()], [m._pending_batches for m in self._bns]
+
+    def _restore(self, snap):
+        tensors, pending = snap
+        with torch.no_grad():
+            for dst, src in zip(self._state_tensors(), tensors):
+                dst.copy_(src)
+        for m, n in zip(self._bns, pending):
+            m._pending_batches = n
+        self.arena.refresh_shadow()
+        torch.cuda.synchronize()
+
+    def set_lr(self, lr):
+        self.optimizer.lr = lr

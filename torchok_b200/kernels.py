@@ -159,6 +159,13 @@ def shadow_of(param):
     return cast_bf16(param.detach())
 
 
+def grad_ready(param):
+    """Tell the gradient-bucket reducer (engine.ParamArena) that this parameter's gradient is complete."""
+    b = getattr(param, '_tok_bucket', None)
+    if b is not None:
+        b[0].ready(b[1])
+
+
 def grad_buffer(param):
     """fp32 gradient accumulator of a parameter (same memory order); created zero-filled on first use."""
     if param.grad is None:
@@ -407,6 +414,9 @@ class LinearFn(torch.autograd.Function):
             acc = torch.zeros((2, np_), dtype=F32, device=g.device)
             L.tok_bn_bwd_reduce(m, np_, _p(g), None, None, _p(g), _p(acc[0]), _p(acc[1]), st)
             grad_buffer(bias).add_(acc[0, :n])
+        grad_ready(weight)
+        if bias is not None:
+            grad_ready(bias)
         return dx, None, None
 
 

@@ -150,6 +150,9 @@ def _unit_bwd(saved, d, conv, bn, dout, **kw):
     out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb, **kw)
     if finish:
         finish()
+    K.grad_ready(conv.weight)
+    K.grad_ready(bn.weight)
+    K.grad_ready(bn.bias)
     return out
 
 
@@ -236,6 +239,9 @@ class ConvFn(torch.autograd.Function):
             acc = torch.zeros((2, d.k), dtype=F32, device=dy.device)
             lib().tok_bn_bwd_reduce(rows, d.k, K._p(dy), None, None, K._p(dy), K._p(acc[0]), K._p(acc[1]), K._st())
             K.grad_buffer(conv.bias).add_(acc[0, :conv.out_channels])
+        K.grad_ready(conv.weight)
+        if conv.bias is not None:
+            K.grad_ready(conv.bias)
         return dx, None, None, None, None
 
 
@@ -379,6 +385,8 @@ class StemFn(torch.autograd.Function):
             dwp = torch.zeros((k, 256), dtype=F32, device=dev)
             L.tok_stem_conv_wgrad(n, h, w, k, K._p(xs2d), K._p(dy), K._p(dwp), st)
             L.tok_stem_unpack_wgrad(k, c, K._p(dwp), K._p(K.grad_buffer(conv.weight)), 1, st)
+        for prm in (conv.weight, bn.weight, bn.bias):
+            K.grad_ready(prm)
         if ctx.needs_input_grad[0]:
             raise NotImplementedError('gradient w.r.t. the input image is not produced by the stem kernel')
         return (None,) * len(ctx.needs_input_grad)
