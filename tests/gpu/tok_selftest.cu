@@ -651,6 +651,8 @@ int main(int argc, char** argv) {
     test_fprop(Conv{2, 12, 12, 64, 64, 1, 1, 2, 0, 1}, false);
     test_fprop(Conv{2, 14, 14, 256, 256, 3, 3, 1, 1, 1}, false);
     test_fprop(Conv{1, 7, 7, 72, 40, 3, 3, 1, 1, 1}, false);
+    test_fprop(Conv{148, 16, 16, 64, 256, 1, 1, 1, 0, 1}, false);   // 128x256 tiles (persistent kernel), stats
+    test_fprop(Conv{37, 16, 16, 64, 264, 3, 3, 1, 1, 1}, true);     // 128x256 tiles with a ragged N edge + extras
   }
   if (grp == "dgrad" || grp == "all") {
     test_dgrad(Conv{2, 9, 9, 64, 72, 1, 1, 1, 0, 1}, false);
@@ -659,6 +661,8 @@ int main(int argc, char** argv) {
     test_dgrad(Conv{2, 12, 12, 64, 64, 1, 1, 2, 0, 1}, false);
     test_dgrad(Conv{2, 12, 12, 64, 64, 1, 1, 2, 0, 1}, true);
     test_dgrad(Conv{2, 12, 12, 128, 136, 3, 3, 2, 1, 1}, false);
+    test_dgrad(Conv{148, 16, 16, 256, 64, 1, 1, 1, 0, 1}, true);    // MN-major B with 128x256 tiles + addend
+    test_dgrad(Conv{37, 16, 16, 256, 64, 3, 3, 1, 1, 1}, false);
   }
   if (grp == "wgrad" || grp == "all") {
     test_wgrad(Conv{2, 9, 9, 64, 72, 1, 1, 1, 0, 1});

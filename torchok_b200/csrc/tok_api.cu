@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/tokb200.h"
@@ -12,6 +13,8 @@
 namespace tok {
 cudaError_t launch_conv_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvFwdParams& p, int bn, bool b_mn,
                             cudaStream_t st);
+cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                    const ConvFwdParams& p, int bn, bool b_mn, cudaStream_t st);
 cudaError_t launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const ConvWgradParams& p, int bn,
                               int splits, cudaStream_t st);
 void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
@@ -117,12 +120,30 @@ static int check_desc(const tokConvDesc* d) {
 
 static int pick_bn(int n) { return n <= 64 ? 64 : 128; }
 
+// Persistent kernel: a 128x256 tile halves the L2->SM operand traffic per FLOP (the 128x128 tile is L2-bandwidth
+// bound at ~1/3 of the tensor peak); it is chosen when it does not cost wave-quantisation efficiency on 148 SMs.
+static int pick_bn_persist(long long M, int N) {
+  if (N <= 64) return 64;
+  const int forced = getenv("TOK_CONV_BN") ? atoi(getenv("TOK_CONV_BN")) : 0;
+  if (forced == 128 || (forced == 256 && N > 128)) return forced;
+  if (N <= 128) return 128;
+  const long long m_tiles = (M + 127) / 128;
+  auto eff = [&](int bn) {
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long long waves = (tiles + 147) / 148;
+    const double useful = (double)N / (((N + bn - 1) / bn) * bn);
+    return useful * (double)tiles / (double)(waves * 148);
+  };
+  return eff(256) >= 0.85 * eff(128) ? 256 : 128;
+}
+
 // Generic "pixels x weights" launch used by fprop, dgrad and linear.
 static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long long M, const void* wmat,
                       long long w_rows, long long w_cols, bool b_mn, int N, int flip, ConvFwdParams p,
                       cudaStream_t st) {
   CUtensorMap tmB;
-  const int bn = pick_bn(N);
+  static const bool v1 = getenv("TOK_CONV_V1") != nullptr;  // bring-up aid: the one-tile-per-CTA kernel
+  const int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N);
   int rc = make_tmap_2d(&tmB, wmat, w_rows, w_cols, w_cols, b_mn ? 64 : bn);
   if (rc) return rc;
   p.M = (int)M;
@@ -131,7 +152,18 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
   p.a = src;
   p.flip_taps = flip;
   mn_desc_geometry(&p.mn_lbo, &p.mn_sbo, &p.mn_kadv);
-  cudaError_t e = launch_conv_fwd(tmA, tmB, p, bn, b_mn, st);
+  cudaError_t e;
+  if (v1) {
+    e = launch_conv_fwd(tmA, tmB, p, bn, b_mn, st);
+  } else {
+    // output tile store: [M][N] matrix with pitch ldo, 64-column x 128-row boxes (unused by the scatter path)
+    CUtensorMap tmC = tmA;
+    if (!p.scatter) {
+      rc = make_tmap_2d(&tmC, p.out, M, N, p.ldo, 128);
+      if (rc) return rc;
+    }
+    e = launch_conv_fwd_persist(tmA, tmB, tmC, p, bn, b_mn, st);
+  }
   if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv_fwd launch: %s", cudaGetErrorString(e));
   return TOK_OK;
 }

@@ -235,6 +235,319 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Persistent variant of conv_fwd_kernel: one CTA per SM walks the (n_tile, m_tile) list; the accumulator is
+// double-buffered in TMEM so the MMA warp runs tile i+1 while the epilogue warps drain tile i; the bf16 tile is staged
+// in 128B-swizzled shared memory and written with ONE TMA store per 64-column half (coalesced, edge-clipped by the
+// tensor map); BatchNorm statistics are accumulated in shared memory across all tiles of the same n_tile and flushed
+// with one global atomic per channel.  `p.scatter` (strided 1x1 dgrad) keeps the direct row-scatter store.
+template <int BN, int STAGES, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmC, const ConvFwdParams p) {
+  constexpr int kBTile = BN * kBlockK * 2;
+  constexpr int kStage = kATile + kBTile;
+  constexpr int kCTile = kBlockM * BN * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_c = smem + STAGES * kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + kCTile);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  // statistics partials: [4 epilogue warps][sum | sqsum][BN]; every (warp, channel) slot has ONE owner lane, so the
+  // cross-tile accumulation needs no shared-memory atomics (fp32 ATOMS is a CAS spin loop)
+  float* s_part = reinterpret_cast<float*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int total_tiles = n_tiles * m_tiles;
+  const int cin_chunks = (p.Cin + kBlockK - 1) / kBlockK;
+  const int taps = p.a.R * p.a.S;
+  const int num_kb = taps * cin_chunks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < 8 * BN; i += 128) s_part[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t / m_tiles) * BN;
+        const int m0 = (t % m_tiles) * kBlockM;
+        int w0 = 0, h0 = 0, img = 0;
+        if (p.a.im2col) pixel_coords(p.a, m0, w0, h0, img);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int stage = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStage;
+          uint8_t* sb = sa + kATile;
+          mbar_arrive_expect_tx(&full_bar[stage], kStage);
+          const int tap = kb / cin_chunks;
+          const int kc = (kb - tap * cin_chunks) * kBlockK;
+          if (p.a.im2col) {
+            const int r = tap / p.a.S;
+            const int s = tap - r * p.a.S;
+            tma_load_im2col_4d(&tmA, &full_bar[stage], sa, kc, w0, h0, img, static_cast<uint16_t>(s * p.a.dil),
+                               static_cast<uint16_t>(r * p.a.dil));
+          } else {
+            tma_load_2d(&tmA, &full_bar[stage], sa, kc, m0);
+          }
+          const int wtap = p.flip_taps ? (taps - 1 - tap) : tap;
+          if (!B_MN) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, wtap * p.Cin + kc, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, wtap * p.N + n0 + j * 64, kc);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
+      uint32_t it = 0;
+      int li = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+        const int buf = li & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((li >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int stage = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStage);
+          const uint32_t b_addr = a_addr + kATile;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * p.mn_kadv, p.mn_lbo, p.mn_sbo)
+                                        : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(acc, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue warps (TMEM lane quarter = warp & 3)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool want_stats = p.col_sum != nullptr;
+    const bool leader = threadIdx.x == 64;
+    int li = 0;
+    int prev_n0 = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+      const int n0 = (t / m_tiles) * BN;
+      const int m0 = (t % m_tiles) * kBlockM;
+      const int buf = li & 1;
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+      // the staging tile must have been read by the previous TMA store; statistics of a finished n_tile are flushed
+      if (leader) tma_store_wait_read();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (want_stats && prev_n0 >= 0 && prev_n0 != n0) {
+        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            t1 += s_part[(w * 2) * BN + i];
+            t2 += s_part[(w * 2 + 1) * BN + i];
+            s_part[(w * 2) * BN + i] = 0.f;
+            s_part[(w * 2 + 1) * BN + i] = 0.f;
+          }
+          if (prev_n0 + i < p.N) {
+            atomicAdd(p.col_sum + prev_n0 + i, t1);
+            atomicAdd(p.col_sqsum + prev_n0 + i, t2);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      prev_n0 = n0;
+      long long out_row = m;
+      if (p.scatter && row_ok) {
+        const int pq = p.sc_P * p.sc_Q;
+        const int img = m / pq;
+        const int rem = m - img * pq;
+        const int pp = rem / p.sc_Q;
+        const int qq = rem - pp * p.sc_Q;
+        out_row = (static_cast<long long>(img) * p.sc_H + static_cast<long long>(pp) * p.sc_sh) * p.sc_W +
+                  static_cast<long long>(qq) * p.sc_sw;
+      }
+      mbar_wait(&tmem_full_bar[buf], (li >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+        const long long off = out_row * p.ldo + col0;
+        if (p.addend != nullptr && row_ok) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (col0 + g * 8 < p.N) {
+              const uint4 a = __ldg(ap + g);
+              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[g * 8 + 2 * e] += bf16_lo(aw[e]);
+                v[g * 8 + 2 * e + 1] += bf16_hi(aw[e]);
+              }
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        if (p.scatter) {
+          if (row_ok && col0 < p.N) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (col0 + g * 8 < p.N)
+                op[g] = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+          }
+        } else {
+          // 128B-swizzled staging: 64-column halves of [128 rows][128 B]; 16-byte chunk index XOR (row & 7)
+          uint8_t* half = smem_c + (c >> 1) * (kBlockM * 128) + row * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = ((c & 1) * 4 + g) ^ (row & 7);
+            *reinterpret_cast<uint4*>(half + chunk * 16) =
+                make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (!p.scatter) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            if (n0 + j * 64 < p.N) tma_store_2d(&tmC, smem_c + j * (kBlockM * 128), n0 + j * 64, m0);
+          tma_store_commit();
+        }
+        if (want_stats) {
+          // per-channel sum / sum of squares of the STORED bf16 values, read back from the staged tile:
+          // thread -> (16-byte chunk = 8 channels, row group); rows >= M are skipped
+          const int te = threadIdx.x - 64;
+          const int chunk = te & 7;
+          const int rg = te >> 3;  // 16 row groups
+          int rows_valid = p.M - m0;
+          if (rows_valid > kBlockM) rows_valid = kBlockM;
+#pragma unroll 1
+          for (int h = 0; h < BN / 64; ++h) {
+            if (n0 + h * 64 >= p.N) break;
+            float a1[8], a2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+            const uint8_t* base = smem_c + h * (kBlockM * 128);
+#pragma unroll 4
+            for (int r = rg; r < rows_valid; r += 16) {
+              const uint4 vv = *reinterpret_cast<const uint4*>(base + r * 128 + ((chunk ^ (r & 7)) * 16));
+              const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = bf16_lo(w4[e]), hi = bf16_hi(w4[e]);
+                a1[2 * e] += lo;
+                a1[2 * e + 1] += hi;
+                a2[2 * e] = fmaf(lo, lo, a2[2 * e]);
+                a2[2 * e + 1] = fmaf(hi, hi, a2[2 * e + 1]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], 8);
+              a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], 8);
+              a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], 16);
+              a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], 16);
+            }
+            if (lane < 8) {
+              float* d1 = s_part + (q * 2) * BN + h * 64 + chunk * 8;
+              float* d2 = d1 + BN;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                d1[j] += a1[j];
+                d2[j] += a2[j];
+              }
+            }
+          }
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
+    if (want_stats && prev_n0 >= 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < BN; i += 128) {
+        if (prev_n0 + i < p.N) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            t1 += s_part[(w * 2) * BN + i];
+            t2 += s_part[(w * 2 + 1) * BN + i];
+          }
+          atomicAdd(p.col_sum + prev_n0 + i, t1);
+          atomicAdd(p.col_sqsum + prev_n0 + i, t2);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // grid.x = tap + taps * (n_tile + n_tiles * m_tile), grid.y = split index over 64-pixel K blocks.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -376,6 +689,55 @@ void mn_desc_geometry(int* lbo, int* sbo, int* kadv) {
 template <int BN, int STAGES>
 constexpr int conv_smem_bytes() {
   return STAGES * (kATile + BN * kBlockK * 2) + (2 * STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
+}
+
+template <int BN, int STAGES>
+constexpr int conv_persist_smem_bytes() {
+  return STAGES * (kATile + BN * kBlockK * 2) + kBlockM * BN * 2 + (2 * STAGES + 4) * 8 + 16 + 8 * BN * 4 + 1024;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES, bool B_MN>
+static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                    const ConvFwdParams& p, cudaStream_t st) {
+  constexpr int smem = conv_persist_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_persist_kernel<BN, STAGES, B_MN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_fwd_persist_kernel<BN, STAGES, B_MN><<<grid, kNumThreads, smem, st>>>(tmA, tmB, tmC, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                    const ConvFwdParams& p, int bn, bool b_mn, cudaStream_t st) {
+  if (bn == 64)
+    return b_mn ? launch_persist_t<64, 6, true>(tmA, tmB, tmC, p, st)
+                : launch_persist_t<64, 6, false>(tmA, tmB, tmC, p, st);
+  if (bn == 128)
+    return b_mn ? launch_persist_t<128, 4, true>(tmA, tmB, tmC, p, st)
+                : launch_persist_t<128, 4, false>(tmA, tmB, tmC, p, st);
+  if (bn == 256)
+    return b_mn ? launch_persist_t<256, 3, true>(tmA, tmB, tmC, p, st)
+                : launch_persist_t<256, 3, false>(tmA, tmB, tmC, p, st);
+  return cudaErrorInvalidValue;
 }
 
 template <int BN, int STAGES, bool B_MN>
