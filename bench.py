@@ -199,6 +199,18 @@ def run_ours(args):
     task = tb.TASKS.get(cfg.task.name)(cfg, **cfg.task.params).to(dev)
     loop = StreamLoop(task, use_graph=not args.no_graph)
     B = args.batch
+    if args.profile_step:
+        loop.use_graph = False
+        x = torch.randn(B, 3, args.size, args.size, device=dev)
+        y = torch.randint(0, NUM_CLASSES, (B,), device=dev)
+        for _ in range(3):
+            loop.train_step({'image': x, 'target': y})
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        loop.train_step({'image': x, 'target': y})
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     g = torch.Generator().manual_seed(42 + rank)
     host_img = [torch.randn(B, 3, args.size, args.size, generator=g).pin_memory() for _ in range(2)]
     host_tgt = [torch.randint(0, NUM_CLASSES, (B,), generator=g).pin_memory() for _ in range(2)]
@@ -328,6 +340,9 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=32)
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--profile-step', action='store_true',
+                    help='ncu aid: warm up eagerly, then run ONE eager step between cudaProfilerStart/Stop and exit '
+                         '(use with ncu --profile-from-start off); prints no bench line')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
