@@ -109,6 +109,19 @@ int tok_bn_bwd_apply(long long rows, int C, const void* dout, const void* dout2,
                      const float* coef_a, const float* coef_c1, const float* coef_c0, void* dy, void* dres,
                      void* stream);
 
+/* Second-generation passes (tok_bn2.cu): the backward no longer re-reads the activation to rebuild the ReLU mask.
+ * mask_mode 0: no activation; 1: plain conv->BN->ReLU unit, mask = (y*scale + shift > 0) recomputed from the forward's
+ * scale/shift; 2: residual tail, mask = bits (1 bit per element, one byte per 8-channel vector, written by
+ * tok_bn_apply_bits which computes out = relu(y*scale + shift + residual)). */
+int tok_bn_apply_bits(long long rows, int C, const void* y, const float* scale, const float* shift,
+                      const void* residual, void* out, void* bits, void* stream);
+int tok_bn_bwd_reduce2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
+                       const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
+                       void* stream);
+int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
+                      const void* bits, const float* scale, const float* shift, const float* coef_a,
+                      const float* coef_c1, const float* coef_c0, void* dy, void* dres, void* stream);
+
 /* ---- pooling (torch.nn.MaxPool2d, resnet.py:510; timm SelectAdaptivePool2d, poolings/classification/pooling.py:8-12)
  * argmax: one byte per output element (window slot of the first maximum). */
 int tok_maxpool_fwd(int n, int h, int w, int c, int k, int s, int pad, const void* x, void* out, void* argmax,

@@ -1,0 +1,360 @@
+// tok_bn2.cu — second-generation BatchNorm passes: minimum-traffic forward apply (+ReLU bit mask) and backward
+// reduce / apply that recover the ReLU mask without re-reading the activation.
+//
+// Reference call sites: torch.nn.BatchNorm2d + ReLU inside ConvBnAct (torchok/models/modules/bricks/convbnact.py:44-53)
+// and the timm block tails `x += shortcut; x = act(x)` (blocks built by torchok/models/backbones/resnet.py:363-405);
+// autograd's BatchNorm / ReLU backward is what the *_bwd_* kernels restate.
+//
+// Traffic per element of a [rows][C] bf16 tensor (2 B):
+//   forward  apply          : read y (+residual), write out (+1 bit when the unit is a residual tail)
+//   backward reduce (pass 1): read dout, y (+1 bit)                       — was dout, out, y
+//   backward apply  (pass 2): read dout, y (+1 bit), write dy (+dres)     — was dout, out, y
+// ReLU mask sources: MASK_NONE (no activation), MASK_Y (plain conv->BN->ReLU: out > 0 <=> scale*y+shift > 0, recomputed
+// with the forward's own fp32 scale/shift and the same fmaf), MASK_BITS (residual tails: 1 bit / element written by
+// the forward pass, 8 channels per byte in vector order).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tokb200.h"
+#include "tok_internal.h"
+#include "tok_ptx.cuh"
+
+namespace tok {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u8(const uint8_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+constexpr int kUnroll = 4;
+
+enum { MASK_NONE = 0, MASK_Y = 1, MASK_BITS = 2 };
+
+// One thread owns one 8-channel vector column (cv) and walks rows rl, rl+rlanes, ... of its CTA's row range.
+struct Map {
+  int cl, rl, rlanes, cv;
+  bool active;
+  long long r0, r1;
+};
+__device__ __forceinline__ Map make_map(long long rows, int cvec, int cvec_b, int rows_per_cta) {
+  Map m;
+  m.rlanes = 256 / cvec_b;
+  m.cl = threadIdx.x % cvec_b;
+  m.rl = threadIdx.x / cvec_b;
+  m.cv = blockIdx.y * cvec_b + m.cl;
+  m.active = m.rl < m.rlanes && m.cv < cvec;
+  m.r0 = (long long)blockIdx.x * rows_per_cta;
+  m.r1 = m.r0 + rows_per_cta;
+  if (m.r1 > rows) m.r1 = rows;
+  return m;
+}
+
+template <int MASK>
+__device__ __forceinline__ void apply_mask(float (&g)[8], const float (&yy)[8], const float (&sc)[8],
+                                           const float (&sf)[8], uint32_t bits) {
+  if (MASK == MASK_Y) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = fmaf(yy[j], sc[j], sf[j]) > 0.f ? g[j] : 0.f;
+  } else if (MASK == MASK_BITS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = ((bits >> j) & 1u) ? g[j] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward apply + bits
+// out = relu(y*scale + shift + residual), bits[vector] = (out > 0) per channel.
+__global__ void __launch_bounds__(256)
+bn_apply_bits_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
+                     uint8_t* __restrict__ bits, const float* __restrict__ scale, const float* __restrict__ shift,
+                     long long rows, int cvec, int cvec_b, int rows_per_cta) {
+  const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
+  if (!m.active) return;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + m.cv * 8 + j);
+    sf[j] = __ldg(shift + m.cv * 8 + j);
+  }
+  const long long step = (long long)m.rlanes * kUnroll;
+  for (long long r = m.r0 + m.rl; r < m.r1; r += step) {
+    uint4 vy[kUnroll], vr[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long rr = r + (long long)u * m.rlanes;
+      if (rr < m.r1) {
+        vy[u] = ldg_stream(y + rr * cvec + m.cv);
+        vr[u] = ldg_stream(res + rr * cvec + m.cv);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long rr = r + (long long)u * m.rlanes;
+      if (rr < m.r1) {
+        float f[8], q[8];
+        unpack8(vy[u], f);
+        unpack8(vr[u], q);
+        uint32_t b = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaxf(fmaf(f[j], sc[j], sf[j]) + q[j], 0.f);
+          b |= (f[j] > 0.f ? 1u : 0u) << j;
+        }
+        out[rr * cvec + m.cv] = pack8(f);
+        bits[rr * cvec + m.cv] = (uint8_t)b;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward pass 1
+template <int MASK, bool HAS2>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2, const uint4* __restrict__ y,
+                      const uint8_t* __restrict__ bits, const float* __restrict__ scale,
+                      const float* __restrict__ shift, float* __restrict__ sum_g, float* __restrict__ sum_gy,
+                      long long rows, int cvec, int cvec_b, int rows_per_cta) {
+  __shared__ float part[256 * 16];
+  const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  if (m.active) {
+    float sc[8], sf[8];
+    if (MASK == MASK_Y) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(scale + m.cv * 8 + j);
+        sf[j] = __ldg(shift + m.cv * 8 + j);
+      }
+    }
+    const long long step = (long long)m.rlanes * kUnroll;
+    for (long long r = m.r0 + m.rl; r < m.r1; r += step) {
+      uint4 vg[kUnroll], vy[kUnroll], v2[kUnroll];
+      uint32_t vb[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long rr = r + (long long)u * m.rlanes;
+        const long long idx = rr * cvec + m.cv;
+        if (rr < m.r1) {
+          vg[u] = ldg_stream(dout + idx);
+          vy[u] = ldg_stream(y + idx);
+          if (HAS2) v2[u] = ldg_stream(dout2 + idx);
+          if (MASK == MASK_BITS) vb[u] = ldg_stream_u8(bits + idx);
+        } else {
+          vg[u] = make_uint4(0, 0, 0, 0);
+          vy[u] = make_uint4(0, 0, 0, 0);
+          if (HAS2) v2[u] = make_uint4(0, 0, 0, 0);
+          if (MASK == MASK_BITS) vb[u] = 0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float g[8], yy[8];
+        unpack8(vg[u], g);
+        unpack8(vy[u], yy);
+        if (HAS2) {
+          float g2[8];
+          unpack8(v2[u], g2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += g2[j];
+        }
+        apply_mask<MASK>(g, yy, sc, sf, MASK == MASK_BITS ? vb[u] : 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a1[j] += g[j];
+          a2[j] = fmaf(g[j], yy[j], a2[j]);
+        }
+      }
+    }
+  }
+  // CTA reduction without shared-memory atomics: part[thread][16], then one thread per (channel-vector, slot)
+  float* mine = part + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mine[j] = a1[j];
+    mine[8 + j] = a2[j];
+  }
+  __syncthreads();
+  const int rlanes = 256 / cvec_b;
+  for (int o = threadIdx.x; o < cvec_b * 16; o += 256) {
+    float t = 0.f;
+    for (int rl = 0; rl < rlanes; ++rl) t += part[rl * cvec_b * 16 + o];
+    const int cl = o >> 4, k = o & 15;
+    const int c = (blockIdx.y * cvec_b + cl) * 8 + (k & 7);
+    if (c < cvec * 8) atomicAdd((k < 8 ? sum_g : sum_gy) + c, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward pass 2
+// dy = a*g + c1*y + c0 ; dres (optional) = g
+template <int MASK, bool HAS2, bool DRES>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2, const uint4* __restrict__ y,
+                     const uint8_t* __restrict__ bits, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ coef_a,
+                     const float* __restrict__ coef_c1, const float* __restrict__ coef_c0, uint4* __restrict__ dy,
+                     uint4* __restrict__ dres, long long rows, int cvec, int cvec_b, int rows_per_cta) {
+  const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
+  if (!m.active) return;
+  float sc[8], sf[8], ca[8], c1[8], c0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (MASK == MASK_Y) {
+      sc[j] = __ldg(scale + m.cv * 8 + j);
+      sf[j] = __ldg(shift + m.cv * 8 + j);
+    }
+    ca[j] = __ldg(coef_a + m.cv * 8 + j);
+    c1[j] = __ldg(coef_c1 + m.cv * 8 + j);
+    c0[j] = __ldg(coef_c0 + m.cv * 8 + j);
+  }
+  const long long step = (long long)m.rlanes * kUnroll;
+  for (long long r = m.r0 + m.rl; r < m.r1; r += step) {
+    uint4 vg[kUnroll], vy[kUnroll], v2[kUnroll];
+    uint32_t vb[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long rr = r + (long long)u * m.rlanes;
+      const long long idx = rr * cvec + m.cv;
+      if (rr < m.r1) {
+        vg[u] = ldg_stream(dout + idx);
+        vy[u] = ldg_stream(y + idx);
+        if (HAS2) v2[u] = ldg_stream(dout2 + idx);
+        if (MASK == MASK_BITS) vb[u] = ldg_stream_u8(bits + idx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long rr = r + (long long)u * m.rlanes;
+      if (rr < m.r1) {
+        const long long idx = rr * cvec + m.cv;
+        float g[8], yy[8];
+        unpack8(vg[u], g);
+        unpack8(vy[u], yy);
+        if (HAS2) {
+          float g2[8];
+          unpack8(v2[u], g2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += g2[j];
+        }
+        apply_mask<MASK>(g, yy, sc, sf, MASK == MASK_BITS ? vb[u] : 0u);
+        if (DRES) dres[idx] = pack8(g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yy[j] = fmaf(ca[j], g[j], fmaf(c1[j], yy[j], c0[j]));
+        dy[idx] = pack8(yy);
+      }
+    }
+  }
+}
+
+struct Grid2 {
+  dim3 grid;
+  int cvec, cvec_b, rows_per_cta;
+};
+Grid2 plan(long long rows, int C, int ctas_per_sm) {
+  Grid2 g;
+  g.cvec = C / 8;
+  g.cvec_b = g.cvec < 256 ? g.cvec : 256;
+  const int gy = (g.cvec + g.cvec_b - 1) / g.cvec_b;
+  const int rlanes = 256 / g.cvec_b;
+  long long ctas = 148LL * ctas_per_sm / gy;
+  if (ctas < 1) ctas = 1;
+  long long rpc = (rows + ctas - 1) / ctas;
+  const long long quantum = (long long)rlanes * kUnroll;
+  rpc = (rpc + quantum - 1) / quantum * quantum;  // whole unrolled iterations: no ragged tail inside a CTA
+  ctas = (rows + rpc - 1) / rpc;
+  g.grid = dim3((unsigned)ctas, gy);
+  g.rows_per_cta = (int)rpc;
+  return g;
+}
+
+}  // namespace
+}  // namespace tok
+
+using namespace tok;
+
+extern "C" {
+
+int tok_bn_apply_bits(long long rows, int C, const void* y, const float* scale, const float* shift,
+                      const void* residual, void* out, void* bits, void* stream) {
+  if (C <= 0 || (C % 8)) return set_error(TOK_ERR_INVALID, "bn_apply_bits: C must be a positive multiple of 8 (got %d)", C);
+  if (rows <= 0 || !residual || !bits) return set_error(TOK_ERR_INVALID, "bn_apply_bits: rows, residual and bits are required");
+  const Grid2 g = plan(rows, C, 6);
+  bn_apply_bits_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)y, (const uint4*)residual, (uint4*)out,
+                                                                (uint8_t*)bits, scale, shift, rows, g.cvec, g.cvec_b,
+                                                                g.rows_per_cta);
+  TOK_CHECK_LAUNCH("bn_apply_bits");
+  return TOK_OK;
+}
+
+#define TOK_BN2_DISPATCH_MASK(KERNEL, ...)                                                    \
+  do {                                                                                        \
+    if (mask_mode == MASK_NONE) { KERNEL(MASK_NONE, __VA_ARGS__); }                           \
+    else if (mask_mode == MASK_Y) { KERNEL(MASK_Y, __VA_ARGS__); }                            \
+    else { KERNEL(MASK_BITS, __VA_ARGS__); }                                                  \
+  } while (0)
+
+int tok_bn_bwd_reduce2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
+                       const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
+                       void* stream) {
+  if (C <= 0 || (C % 8)) return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: C must be a positive multiple of 8 (got %d)", C);
+  if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: no rows");
+  if (mask_mode < 0 || mask_mode > 2 || (mask_mode == MASK_BITS && !bits) || (mask_mode == MASK_Y && (!scale || !shift)))
+    return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: mask_mode %d needs its operands", mask_mode);
+  const Grid2 g = plan(rows, C, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+#define K_REDUCE(M, H2)                                                                                        \
+  bn_bwd_reduce2_kernel<M, H2><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y, \
+                                                       (const uint8_t*)bits, scale, shift, sum_g, sum_gy, rows, \
+                                                       g.cvec, g.cvec_b, g.rows_per_cta)
+  if (dout2) TOK_BN2_DISPATCH_MASK(K_REDUCE, true);
+  else TOK_BN2_DISPATCH_MASK(K_REDUCE, false);
+#undef K_REDUCE
+  TOK_CHECK_LAUNCH("bn_bwd_reduce2");
+  return TOK_OK;
+}
+
+int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
+                      const void* bits, const float* scale, const float* shift, const float* coef_a,
+                      const float* coef_c1, const float* coef_c0, void* dy, void* dres, void* stream) {
+  if (C <= 0 || (C % 8)) return set_error(TOK_ERR_INVALID, "bn_bwd_apply2: C must be a positive multiple of 8 (got %d)", C);
+  if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_apply2: no rows");
+  if (mask_mode < 0 || mask_mode > 2 || (mask_mode == MASK_BITS && !bits) || (mask_mode == MASK_Y && (!scale || !shift)))
+    return set_error(TOK_ERR_INVALID, "bn_bwd_apply2: mask_mode %d needs its operands", mask_mode);
+  const Grid2 g = plan(rows, C, 6);
+  cudaStream_t st = (cudaStream_t)stream;
+#define K_APPLY(M, H2, DR)                                                                                          \
+  bn_bwd_apply2_kernel<M, H2, DR><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y,  \
+                                                          (const uint8_t*)bits, scale, shift, coef_a, coef_c1,      \
+                                                          coef_c0, (uint4*)dy, (uint4*)dres, rows, g.cvec, g.cvec_b, \
+                                                          g.rows_per_cta)
+  if (dout2 && dres) TOK_BN2_DISPATCH_MASK(K_APPLY, true, true);
+  else if (dout2) TOK_BN2_DISPATCH_MASK(K_APPLY, true, false);
+  else if (dres) TOK_BN2_DISPATCH_MASK(K_APPLY, false, true);
+  else TOK_BN2_DISPATCH_MASK(K_APPLY, false, false);
+#undef K_APPLY
+  TOK_CHECK_LAUNCH("bn_bwd_apply2");
+  return TOK_OK;
+}
+
+}  // extern "C"

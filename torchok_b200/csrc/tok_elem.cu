@@ -662,51 +662,109 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
 // step_advance_kernel just before), and the consumed gradient is zeroed for the next step's atomic accumulation.
 __global__ void step_advance_kernel(int* step) { *step += 1; }
 
-__global__ void sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf,
-                                    __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
-                                    const int* __restrict__ step_dev, float mu, float wd, float damp, int nesterov,
-                                    float gscale, int zero_grad) {
-  const float lr = __ldg(lr_dev);
-  const bool first = __ldg(step_dev) <= 1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float w = p[i];
-    float d = g[i] * gscale + wd * w;
-    if (zero_grad) g[i] = 0.f;
-    if (mu != 0.f) {
-      const float b = first ? d : mu * buf[i] + (1.f - damp) * d;
-      buf[i] = b;
-      d = nesterov ? d + mu * b : b;
-    }
-    w -= lr * d;
+// The *_dev kernels process 4 parameters per thread with 16-byte accesses (the arenas are 256-byte aligned and padded
+// to 64 elements); a scalar tail covers n % 4.
+struct SgdArgs {
+  float lr, mu, wd, damp, gscale;
+  int nesterov, first, zero_grad;
+};
+__device__ __forceinline__ float sgd_one(float w, float g, float* buf, const SgdArgs& a) {
+  float d = g * a.gscale + a.wd * w;
+  if (a.mu != 0.f) {
+    const float b = a.first ? d : a.mu * (*buf) + (1.f - a.damp) * d;
+    *buf = b;
+    d = a.nesterov ? d + a.mu * b : b;
+  }
+  return w - a.lr * d;
+}
+__global__ void __launch_bounds__(256)
+sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf,
+                    __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
+                    const int* __restrict__ step_dev, float mu, float wd, float damp, int nesterov, float gscale,
+                    int zero_grad) {
+  SgdArgs a;
+  a.lr = __ldg(lr_dev);
+  a.first = __ldg(step_dev) <= 1;
+  a.mu = mu; a.wd = wd; a.damp = damp; a.gscale = gscale; a.nesterov = nesterov; a.zero_grad = zero_grad;
+  const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)buf | ((uintptr_t)shadow << 1)) & 15) == 0;
+  const long long n4 = aligned ? (n >> 2) : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 w = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mu != 0.f && !a.first) b = reinterpret_cast<float4*>(buf)[i];
+    w.x = sgd_one(w.x, gg.x, &b.x, a);
+    w.y = sgd_one(w.y, gg.y, &b.y, a);
+    w.z = sgd_one(w.z, gg.z, &b.z, a);
+    w.w = sgd_one(w.w, gg.w, &b.w, a);
+    if (mu != 0.f) reinterpret_cast<float4*>(buf)[i] = b;
+    reinterpret_cast<float4*>(p)[i] = w;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float b = (mu != 0.f && !a.first) ? buf[i] : 0.f;
+    const float w = sgd_one(p[i], g[i], &b, a);
+    if (mu != 0.f) buf[i] = b;
     p[i] = w;
+    if (zero_grad) g[i] = 0.f;
     if (shadow) shadow[i] = __float2bfloat16(w);
   }
 }
-__global__ void adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                     float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n,
-                                     const float* __restrict__ lr_dev, const int* __restrict__ step_dev, float b1,
-                                     float b2, float eps, float wd, int decoupled, float gscale, int zero_grad) {
-  const float lr = __ldg(lr_dev);
+struct AdamArgs {
+  float lr, b1, b2, eps, wd, gscale, step, rbc2;
+  int decoupled;
+};
+__device__ __forceinline__ float adam_one(float w, float g, float* m, float* v, const AdamArgs& a) {
+  float d = g * a.gscale;
+  if (a.decoupled)
+    w *= 1.f - a.lr * a.wd;
+  else
+    d += a.wd * w;
+  const float mi = a.b1 * (*m) + (1.f - a.b1) * d;
+  const float vi = a.b2 * (*v) + (1.f - a.b2) * d * d;
+  *m = mi;
+  *v = vi;
+  return w - a.step * mi / (sqrtf(vi) * a.rbc2 + a.eps);
+}
+__global__ void __launch_bounds__(256)
+adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                     __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
+                     const int* __restrict__ step_dev, float b1, float b2, float eps, float wd, int decoupled,
+                     float gscale, int zero_grad) {
+  AdamArgs a;
+  a.lr = __ldg(lr_dev);
   const float t = (float)__ldg(step_dev);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
-  const float step = lr / bc1;
-  const float rbc2 = rsqrtf(bc2);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float w = p[i];
-    float d = g[i] * gscale;
-    if (zero_grad) g[i] = 0.f;
-    if (decoupled)
-      w *= 1.f - lr * wd;
-    else
-      d += wd * w;
-    const float mi = b1 * m[i] + (1.f - b1) * d;
-    const float vi = b2 * v[i] + (1.f - b2) * d * d;
+  a.step = a.lr / bc1;
+  a.rbc2 = rsqrtf(bc2);
+  a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd; a.gscale = gscale; a.decoupled = decoupled;
+  const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | ((uintptr_t)shadow << 1)) & 15) == 0;
+  const long long n4 = aligned ? (n >> 2) : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 w = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    w.x = adam_one(w.x, gg.x, &mm.x, &vv.x, a);
+    w.y = adam_one(w.y, gg.y, &mm.y, &vv.y, a);
+    w.z = adam_one(w.z, gg.z, &mm.z, &vv.z, a);
+    w.w = adam_one(w.w, gg.w, &mm.w, &vv.w, a);
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    reinterpret_cast<float4*>(p)[i] = w;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float mi = m[i], vi = v[i];
+    const float w = adam_one(p[i], g[i], &mi, &vi, a);
     m[i] = mi;
     v[i] = vi;
-    w -= step * mi / (sqrtf(vi) * rbc2 + eps);
     p[i] = w;
+    if (zero_grad) g[i] = 0.f;
     if (shadow) shadow[i] = __float2bfloat16(w);
   }
 }

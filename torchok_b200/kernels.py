@@ -207,11 +207,16 @@ class BNState:
         self.eps, self.momentum, self.training, self.acc, self.cp = eps, momentum, training, acc, cp
 
 
+MASK_NONE, MASK_Y, MASK_BITS = 0, 1, 2
+
+
 def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
     """conv -> BatchNorm (batch stats in training) -> (+residual) -> (ReLU).
 
     x: NHWC activation; d: tokConvDesc for x; w: bf16 [Kp][R][S][Cp] weights; bn: BNState.
-    Returns (out, saved) where saved = (x, y, out_or_None, small) feeds `unit_backward`.
+    Returns (out, saved) where saved = (x, y, bits_or_None, small, mask_mode) feeds `unit_backward`.  The backward
+    never re-reads `out`: a plain ReLU unit rebuilds its mask from y and the forward's scale/shift (MASK_Y), a
+    residual tail stores one bit per element (MASK_BITS).
     """
     L = lib()
     n, kp, (p, q) = d.n, d.k, pq
@@ -231,8 +236,16 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
         L.tok_bn_finalize_eval(kp, _p(bn.running_mean), _p(bn.running_var), _p(bn.weight), _p(bn.bias), bn.eps,
                                _p(small[0]), _p(small[1]), st)
     out = torch.empty_like(y) if keep else y
-    L.tok_bn_apply(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), int(relu), _p(out), st)
-    saved = (x, y, out if relu else None, small) if keep else None
+    bits, mode = None, MASK_NONE
+    if keep and relu and residual is not None:
+        bits = torch.empty((rows * kp // 8,), dtype=torch.uint8, device=dev)
+        mode = MASK_BITS
+        L.tok_bn_apply_bits(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), _p(out), _p(bits), st)
+    else:
+        if relu:
+            mode = MASK_Y
+        L.tok_bn_apply(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), int(relu), _p(out), st)
+    saved = (x, y, bits, small, mode) if keep else None
     return out.permute(0, 3, 1, 2), saved
 
 
@@ -241,27 +254,23 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
     """Backward of `unit_forward`.  Returns (dx or None, dres or None).  Parameter gradients are ACCUMULATED into
     wgrad_into / dgamma / dbeta (fp32, may be None for frozen parameters)."""
     L = lib()
-    x, y, out, small = saved
+    x, y, bits, small, mode = saved
     kp = d.k
     rows = y.numel() // kp
     dev = y.device
     st = _st()
     acc = bn.acc
-    coefs = torch.empty((3, kp), dtype=F32, device=dev)
-    L.tok_bn_bwd_reduce(rows, kp, _p(dout), _p(dout2), _p(out), _p(y), _p(acc[2]), _p(acc[3]), st)
-    if bn.training:
-        L.tok_bn_bwd_finalize(kp, float(rows), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
-                              _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, st)
-    else:
-        # frozen statistics: dy = g * gamma * invstd; xhat uses the running stats
-        stats = torch.empty((2, kp), dtype=F32, device=dev)
-        L.tok_bn_finalize_eval(kp, _p(bn.running_mean), _p(bn.running_var), None, None, bn.eps, _p(stats[0]),
-                               _p(stats[1]), st)  # stats[0] = invstd, stats[1] = -mean*invstd
+    if not bn.training:
         raise NotImplementedError('backward through eval-mode BatchNorm is not implemented yet')
+    coefs = torch.empty((3, kp), dtype=F32, device=dev)
+    L.tok_bn_bwd_reduce2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
+                         _p(acc[2]), _p(acc[3]), st)
+    L.tok_bn_bwd_finalize(kp, float(rows), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
+                          _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, st)
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
-    L.tok_bn_bwd_apply(rows, kp, _p(dout), _p(dout2), _p(out), _p(y), _p(coefs[0]), _p(coefs[1]), _p(coefs[2]),
-                       _p(dy), _p(dres), st)
+    L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
+                        _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
     dx = None
     if need_dx:
         dx = torch.empty((d.n, d.h, d.w, d.c), dtype=BF16, device=dev)

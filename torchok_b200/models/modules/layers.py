@@ -174,15 +174,15 @@ class ConvBnActFn(torch.autograd.Function):
         (out, saved), d = _unit_fwd(x, conv, bn, relu, residual, keep)
         if keep:
             ctx.mods = (conv, bn, d, residual is not None)
-            ctx.has_out = saved[2] is not None
-            ctx.save_for_backward(*[t for t in saved if t is not None])
+            ctx.has_bits, ctx.mode = saved[2] is not None, saved[4]
+            ctx.save_for_backward(*[t for t in saved[:4] if t is not None])
         return out
 
     @staticmethod
     def backward(ctx, dout):
         conv, bn, d, has_res = ctx.mods
         t = list(ctx.saved_tensors)
-        saved = (t[0], t[1], t[2] if ctx.has_out else None, t[-1])
+        saved = (t[0], t[1], t[2] if ctx.has_bits else None, t[-1], ctx.mode)
         dout = K._dense_grad(dout, d.k)
         dx, dres = _unit_bwd(saved, d, conv, bn, dout, need_dx=ctx.needs_input_grad[0], want_dres=has_res)
         return (dx, dres, None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 6)
@@ -275,8 +275,8 @@ class ResidualBlockFn(torch.autograd.Function):
         if keep:
             flat, layout = [], []
             for sv in saved_all:
-                layout.append(tuple(t is not None for t in sv))
-                flat.extend(t for t in sv if t is not None)
+                layout.append((tuple(t is not None for t in sv[:4]), sv[4]))
+                flat.extend(t for t in sv[:4] if t is not None)
             ctx.save_for_backward(*flat)
             ctx.layout, ctx.descs, ctx.block = layout, descs, block
         return out
@@ -287,7 +287,7 @@ class ResidualBlockFn(torch.autograd.Function):
         units = block.tok_units()
         ds = block.tok_downsample()
         it = iter(ctx.saved_tensors)
-        saved_all = [tuple(next(it) if present else None for present in lay) for lay in ctx.layout]
+        saved_all = [tuple(next(it) if present else None for present in lay) + (mode,) for lay, mode in ctx.layout]
         off = 1 if ds is not None else 0
         dout = K._dense_grad(dout, descs[-1].k)
         # last unit: ReLU mask from the block output, g flows to the shortcut
@@ -319,6 +319,7 @@ class StemFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, conv, bn, pool, keep, *params):
         K.require_cuda(image, 'image')
+        ctx.set_materialize_grads(False)  # `act` is usually unused: do not build (and convert) a zero gradient for it
         L = lib()
         st = K._st()
         n, c, h, w = image.shape
@@ -356,31 +357,38 @@ class StemFn(torch.autograd.Function):
         pk, ps, pp = pool
         pooled, arg = K.maxpool_fwd(act, pk, ps, pp)
         if keep:
-            ctx.save_for_backward(xs2d, y, act, small, arg)
+            ctx.save_for_backward(xs2d, y, small, arg)
             ctx.meta = (conv, bn, pool, (n, c, h, w), (P, Q))
         return act, pooled
 
     @staticmethod
     def backward(ctx, d_act, d_pooled):
         conv, bn, (pk, ps, pp), (n, c, h, w), (P, Q) = ctx.meta
-        xs2d, y, act, small, arg = ctx.saved_tensors
+        xs2d, y, small, arg = ctx.saved_tensors
         L = lib()
         st = K._st()
         k = conv.out_channels
         dev = y.device
         rows = n * P * Q
-        dout = K.maxpool_bwd(K._dense_grad(d_pooled, k), arg, (n, k, P, Q), k, pk, ps, pp)
-        dout2 = K._dense_grad(d_act, k) if d_act is not None else None
+        if d_pooled is None and d_act is None:
+            return (None,) * len(ctx.needs_input_grad)
+        if d_pooled is not None:
+            dout = K.maxpool_bwd(K._dense_grad(d_pooled, k), arg, (n, k, P, Q), k, pk, ps, pp)
+            dout2 = K._dense_grad(d_act, k) if d_act is not None else None
+        else:
+            dout, dout2 = K._dense_grad(d_act, k), None
         acc = bn._tok_acc
         gw, gb = _bn_grads(bn)
         coefs = torch.empty((3, k), dtype=F32, device=dev)
-        L.tok_bn_bwd_reduce(rows, k, K._p(dout), K._p(dout2), K._p(act), K._p(y), K._p(acc[2]), K._p(acc[3]), st)
+        # ReLU mask rebuilt from y and the forward's scale/shift (MASK_Y): `act` is not kept for the backward
+        L.tok_bn_bwd_reduce2(rows, k, K._p(dout), K._p(dout2), K._p(y), K.MASK_Y, None, K._p(small[0]),
+                             K._p(small[1]), K._p(acc[2]), K._p(acc[3]), st)
         L.tok_bn_bwd_finalize(k, float(rows), K._p(acc[2]), K._p(acc[3]), K._p(small[2]), K._p(small[3]),
                               K._p(bn.weight), K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(gw), K._p(gb), 1,
                               st)
         dy = torch.empty_like(y)
-        L.tok_bn_bwd_apply(rows, k, K._p(dout), K._p(dout2), K._p(act), K._p(y), K._p(coefs[0]), K._p(coefs[1]),
-                           K._p(coefs[2]), K._p(dy), None, st)
+        L.tok_bn_bwd_apply2(rows, k, K._p(dout), K._p(dout2), K._p(y), K.MASK_Y, None, K._p(small[0]),
+                            K._p(small[1]), K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(dy), None, st)
         if conv.weight.requires_grad:
             dwp = torch.zeros((k, 256), dtype=F32, device=dev)
             L.tok_stem_conv_wgrad(n, h, w, k, K._p(xs2d), K._p(dy), K._p(dwp), st)
