@@ -14,7 +14,8 @@ namespace tok {
 cudaError_t launch_conv_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvFwdParams& p, int bn, bool b_mn,
                             cudaStream_t st);
 cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                                    const ConvFwdParams& p, int bn, bool b_mn, cudaStream_t st);
+                                    const CUtensorMap& tmD, const ConvFwdParams& p, int bn, bool b_mn,
+                                    cudaStream_t st);
 cudaError_t launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const ConvWgradParams& p, int bn,
                               int splits, cudaStream_t st);
 void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
@@ -157,12 +158,17 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
     e = launch_conv_fwd(tmA, tmB, p, bn, b_mn, st);
   } else {
     // output tile store: [M][N] matrix with pitch ldo, 64-column x 128-row boxes (unused by the scatter path)
-    CUtensorMap tmC = tmA;
+    // the optional addend tile is fetched through a map of the same geometry (unused by the scatter path)
+    CUtensorMap tmC = tmA, tmD = tmA;
     if (!p.scatter) {
       rc = make_tmap_2d(&tmC, p.out, M, N, p.ldo, 128);
       if (rc) return rc;
+      if (p.addend) {
+        rc = make_tmap_2d(&tmD, p.addend, M, N, p.ldo, 128);
+        if (rc) return rc;
+      }
     }
-    e = launch_conv_fwd_persist(tmA, tmB, tmC, p, bn, b_mn, st);
+    e = launch_conv_fwd_persist(tmA, tmB, tmC, tmD, p, bn, b_mn, st);
   }
   if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv_fwd launch: %s", cudaGetErrorString(e));
   return TOK_OK;
@@ -180,8 +186,9 @@ static int run_fwd(const void* a, int an, int ah, int aw, int ac, const PixelSrc
 }
 
 static int pick_splits(long long tiles, int total_chunks, int* chunks_per_split) {
-  // Aim for ~2 waves of 2 CTAs/SM while keeping at least 8 K-blocks per CTA.
-  long long target = 148 * 4;
+  // One wave of 2 CTAs/SM (every extra split costs a full tile of fp32 reductions), at least 8 K-blocks per CTA.
+  static const int per_sm = getenv("TOK_WGRAD_CTAS_PER_SM") ? atoi(getenv("TOK_WGRAD_CTAS_PER_SM")) : 2;
+  long long target = 148LL * per_sm;
   int splits = (int)((target + tiles - 1) / tiles);
   int max_splits = (total_chunks + 7) / 8;
   if (splits > max_splits) splits = max_splits;
