@@ -34,6 +34,11 @@ const char* tok_last_error(void);
 /* 0 if a CUDA device with compute capability 10.x is usable, else negative. */
 int tok_device_ok(void);
 
+/* Bring-up aid: with TOK_CONV_PROFILE=1 in the environment the persistent conv kernel records per-CTA cycle counts
+ * of its epilogue phases (16 int64 per CTA: two observer threads x 8 slots); this copies the last launch's counters
+ * to the host and returns the number of entries written (0 when profiling is off). */
+int tok_debug_conv_profile(long long* host_out, int max_entries);
+
 /* ---- convolution (torch.nn.Conv2d inside ConvBnAct, torchok/models/modules/bricks/convbnact.py:38-53; timm
  *      BasicBlock/Bottleneck convs built by torchok/models/backbones/resnet.py:363-405) ------------------------- */
 typedef struct {

@@ -625,6 +625,26 @@ static void perf_conv(const char* tag, const Conv& cv, int iters) {
     CK(cudaEventElapsedTime(&ms[which], e0, e1));
     ms[which] /= iters;
   }
+  if (getenv("TOK_CONV_PROFILE")) {
+    // epilogue phase breakdown of one fprop and one dgrad-with-addend launch (cycles per tile, CTA 0 and CTA 73)
+    const char* names[6] = {"wait_free", "wait_acc", "wait_addend", "chunks", "bar_staged", "store+stats"};
+    for (int which = 0; which < 2; ++which) {
+      if (which == 0) TK(tok_conv_fprop(&d, dx.p, dw.p, dy.p, (float*)dsum.p, (float*)dsq.p, nullptr, nullptr, 0, nullptr));
+      if (which == 1) TK(tok_conv_dgrad(&d, dy.p, dw.p, ddx.p, ddx.p, ws.p, nullptr));
+      std::vector<long long> h(148 * 16);
+      const int n = tok_debug_conv_profile(h.data(), 148 * 16);
+      for (int cta : {0, 73}) {
+        if (n < (cta + 1) * 16) continue;
+        for (int ob = 0; ob < 2; ++ob) {
+          const long long* e = h.data() + cta * 16 + ob * 8;
+          const double tiles = e[6] > 0 ? (double)e[6] : 1.0;
+          printf("PROF %-24s %s cta%d obs%d tiles=%lld |", tag, which ? "dgrad+add" : "fprop+stat", cta, ob, e[6]);
+          for (int i = 0; i < 6; ++i) printf(" %s %.0f", names[i], e[i] / tiles);
+          printf("\n");
+        }
+      }
+    }
+  }
   printf("PERF %-28s M=%zu K=%d N=%d | fprop %.3f ms %.0f TF/s | dgrad %.3f ms %.0f TF/s | wgrad %.3f ms %.0f TF/s\n",
          tag, M, cv.r * cv.s * cv.c, cv.k, ms[0], flop / ms[0] * 1e-9, ms[1], flop / ms[1] * 1e-9, ms[2],
          flop / ms[2] * 1e-9);

@@ -38,6 +38,7 @@ _SIGS = {
     'tok_version': (_i, []),
     'tok_last_error': (C.c_char_p, []),
     'tok_device_ok': (_i, []),
+    'tok_debug_conv_profile': (_i, [_vp, _i]),
     'tok_conv_out_hw': (None, [_pd, _pi, _pi]),
     'tok_conv_fprop': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'tok_conv_dgrad_workspace_bytes': (_sz, [_pd]),
@@ -74,7 +75,7 @@ _SIGS = {
     'tok_adam_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
 }
-_RAW = {'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+_RAW = {'tok_debug_conv_profile', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}
 
 

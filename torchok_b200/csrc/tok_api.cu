@@ -38,6 +38,7 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static long long* g_prof_buf = nullptr;
 static EncodeTiledFn g_encode_tiled = nullptr;
 static EncodeIm2colFn g_encode_im2col = nullptr;
 
@@ -123,11 +124,15 @@ static int pick_bn(int n) { return n <= 64 ? 64 : 128; }
 
 // Persistent kernel: a 128x256 tile halves the L2->SM operand traffic per FLOP (the 128x128 tile is L2-bandwidth
 // bound at ~1/3 of the tensor peak); it is chosen when it does not cost wave-quantisation efficiency on 148 SMs.
-static int pick_bn_persist(long long M, int N) {
+static int pick_bn_persist(long long M, int N, long long k_total) {
   if (N <= 64) return 64;
   const int forced = getenv("TOK_CONV_BN") ? atoi(getenv("TOK_CONV_BN")) : 0;
   if (forced == 128 || (forced == 256 && N > 128)) return forced;
   if (N <= 128) return 128;
+  // Short reductions are bound by the epilogue / HBM, not by the tensor pipe: the 128x128 tile double-buffers its
+  // staging (and addend) tiles so stores drain behind the next tile, which the 128x256 tile has no room for.
+  static const long long small_k = getenv("TOK_CONV_SMALLK") ? atoll(getenv("TOK_CONV_SMALLK")) : 512;
+  if (k_total <= small_k) return 128;
   const long long m_tiles = (M + 127) / 128;
   auto eff = [&](int bn) {
     const long long tiles = m_tiles * ((N + bn - 1) / bn);
@@ -144,7 +149,7 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
                       cudaStream_t st) {
   CUtensorMap tmB;
   static const bool v1 = getenv("TOK_CONV_V1") != nullptr;  // bring-up aid: the one-tile-per-CTA kernel
-  const int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N);
+  const int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N, (long long)src.R * src.S * ac);
   int rc = make_tmap_2d(&tmB, wmat, w_rows, w_cols, w_cols, b_mn ? 64 : bn);
   if (rc) return rc;
   p.M = (int)M;
@@ -153,6 +158,14 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
   p.a = src;
   p.flip_taps = flip;
   mn_desc_geometry(&p.mn_lbo, &p.mn_sbo, &p.mn_kadv);
+  // TOK_CONV_PROFILE=1: the epilogue phase counters of every launch land in a static device buffer which
+  // tok_debug_conv_profile() copies out (bring-up aid; not part of the production path)
+  static const bool want_prof = getenv("TOK_CONV_PROFILE") != nullptr;
+  if (want_prof && !v1) {
+    if (!g_prof_buf) cudaMalloc(&g_prof_buf, 148 * 16 * sizeof(long long));
+    cudaMemsetAsync(g_prof_buf, 0, 148 * 16 * sizeof(long long), st);
+    p.prof = g_prof_buf;
+  }
   cudaError_t e;
   if (v1) {
     e = launch_conv_fwd(tmA, tmB, p, bn, b_mn, st);
@@ -293,6 +306,14 @@ int tok_device_ok(void) {
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (major != 10) return set_error(TOK_ERR_INVALID, "device compute capability %d.x is not sm_100", major);
   return resolve_driver();
+}
+
+int tok_debug_conv_profile(long long* host_out, int max_entries) {
+  if (!g_prof_buf) return 0;
+  const int n = max_entries < 148 * 16 ? max_entries : 148 * 16;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host_out, g_prof_buf, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return n;
 }
 
 void tok_conv_out_hw(const tokConvDesc* d, int* p, int* q) {

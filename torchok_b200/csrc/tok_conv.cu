@@ -236,40 +236,48 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // ------------------------------------------------------------------------------------------------------------------
 // Persistent variant of conv_fwd_kernel: one CTA per SM walks the (n_tile, m_tile) list.
-//   warp 0      TMA producer (operand ring)
+//   warp 0      TMA producer: operand ring, and (ABUFS == 2) the addend tile of each output tile, one tile ahead
 //   warp 1      MMA issuer; the accumulator is double-buffered in TMEM so tile i+1 is computed while tile i drains
 //   warps 2..9  EIGHT epilogue warps: TMEM lane quarter = warp & 3, column half = (warp - 2) >> 2.  The bf16 tile is
 //               staged in 128B-swizzled shared memory and written with one TMA store per 64-column block (coalesced,
-//               edge-clipped by the tensor map).  An `addend` tile (residual gradient of a dgrad) is TMA-LOADED into the
-//               same staging buffer before the epilogue and updated in place, so no thread ever waits on a global load.
-//               BatchNorm statistics are read back from the staged tile: warp w owns 16-byte chunk w (8 channels) of
-//               every 64-column block, so each (channel, statistic) has exactly one owner lane and the running sums
-//               live in shared memory without atomics until one global atomic per channel at the end of an n_tile.
+//               edge-clipped by the tensor map).  With CBUFS == 2 the staging tile is double-buffered, so the store of
+//               tile i drains while tile i+1 is converted.  An `addend` tile (residual gradient of a dgrad) arrives by
+//               TMA too — prefetched into its own double buffer (ABUFS == 2) or, for the 128x256 tile that has no
+//               shared memory to spare, loaded into the staging buffer and updated in place — so no thread ever waits
+//               on a global load.  BatchNorm statistics are read back from the staged tile: warp w owns 16-byte chunk
+//               w (8 channels) of every 64-column block, so each (channel, statistic) has exactly one owner lane and
+//               the running sums live in shared memory without atomics until one global atomic per channel at the
+//               end of an n_tile.
 // `p.scatter` (strided 1x1 dgrad) keeps the direct row-scatter store.
 constexpr int kEpiWarps = 8;
 constexpr int kPersistThreads = 64 + 32 * kEpiWarps;  // 320
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int BN, int STAGES, bool B_MN>
+template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
                         const ConvFwdParams p) {
+  static_assert(CBUFS == 1 || CBUFS == 2, "staging buffers");
+  static_assert(ABUFS == 0 || ABUFS == 2, "addend buffers");
   constexpr int kBTile = BN * kBlockK * 2;
   constexpr int kStage = kATile + kBTile;
   constexpr int kCTile = kBlockM * BN * 2;
+  constexpr int kBlocks = BN / 64;              // 64-column staging blocks per tile
   constexpr int kChunks = BN / 32;              // 32-column TMEM chunks per tile
-  constexpr int kChunksPerWarp = (kChunks + 1) / 2;
+  constexpr int kChunksPerWarp = kChunks / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_c = smem + STAGES * kStage;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + kCTile);
+  uint8_t* smem_d = smem_c + CBUFS * kCTile;    // prefetched addend tiles (ABUFS of them)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_d + ABUFS * kCTile);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* addend_bar = tmem_empty_bar + 2;      // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(addend_bar + 1);
+  uint64_t* addend_full_bar = tmem_empty_bar + 2; // [2]
+  uint64_t* addend_empty_bar = addend_full_bar + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(addend_empty_bar + 2);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);  // [sum | sqsum][BN], one owner lane per slot
 
   const int warp = threadIdx.x >> 5;
@@ -280,6 +288,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int cin_chunks = (p.Cin + kBlockK - 1) / kBlockK;
   const int taps = p.a.R * p.a.S;
   const int num_kb = taps * cin_chunks;
+  const bool has_addend = p.addend != nullptr && !p.scatter;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -293,8 +302,9 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&addend_full_bar[i], 1);
+      mbar_init(&addend_empty_bar[i], kEpiWarps);
     }
-    mbar_init(addend_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -312,9 +322,24 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 0) {
     if (elect_one()) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int li = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
         const int n0 = (t / m_tiles) * BN;
         const int m0 = (t % m_tiles) * kBlockM;
+        if (ABUFS == 2 && has_addend) {
+          // addend tile of THIS output tile; the epilogue is at most two tiles behind, so this runs a tile ahead
+          const int ab = li & 1;
+          mbar_wait(&addend_empty_bar[ab], ((li >> 1) & 1) ^ 1);
+          uint32_t bytes = 0;
+#pragma unroll
+          for (int j = 0; j < kBlocks; ++j)
+            if (n0 + j * 64 < p.N) bytes += kBlockM * 128;
+          mbar_arrive_expect_tx(&addend_full_bar[ab], bytes);
+#pragma unroll
+          for (int j = 0; j < kBlocks; ++j)
+            if (n0 + j * 64 < p.N)
+              tma_load_2d(&tmD, &addend_full_bar[ab], smem_d + ab * kCTile + j * (kBlockM * 128), n0 + j * 64, m0);
+        }
         int w0 = 0, h0 = 0, img = 0;
         if (p.a.im2col) pixel_coords(p.a, m0, w0, h0, img);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -381,45 +406,86 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int ew = warp - 2;                // 0..7: 16-byte chunk owned in the statistics pass
     const int row = q * 32 + lane;
     const bool want_stats = p.col_sum != nullptr;
-    const bool has_addend = p.addend != nullptr && !p.scatter;
     const bool leader = threadIdx.x == 64;
     int li = 0;
     int prev_n0 = -1;
+    // BatchNorm statistics: per-thread partial sums over the rows {lane, lane+32, lane+64, lane+96} of 16-byte chunk
+    // `ew` of every 64-column block, carried in REGISTERS across all tiles of an n_tile ([0..7] sums, [8..15] squares)
+    float sacc[kBlocks][16];
+#pragma unroll
+    for (int h = 0; h < kBlocks; ++h) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sacc[h][j] = 0.f;
+    }
+    // cross-lane reduction of the partials (halving exchange: lane pair (2k, 2k+1) ends with the total of value k),
+    // owner lanes publish to shared memory, then one global atomic per channel
+    const uint32_t s_stat_s = smem_u32(s_stat);
+    auto flush_stats = [&](int n0_done) {
+      const int k = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+#pragma unroll
+      for (int h = 0; h < kBlocks; ++h) {
+#pragma unroll
+        for (int s = 16, cnt = 8; s >= 2; s >>= 1, cnt >>= 1) {
+          const bool upper = (lane & s) != 0;
+#pragma unroll
+          for (int i = 0; i < cnt; ++i) {
+            const float send = upper ? sacc[h][i] : sacc[h][i + cnt];
+            const float keep = upper ? sacc[h][i + cnt] : sacc[h][i];
+            sacc[h][i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+          }
+        }
+        const float tot = sacc[h][0] + __shfl_xor_sync(0xffffffffu, sacc[h][0], 1);
+        if ((lane & 1) == 0) sts_f32(s_stat_s + ((k >> 3) * BN + h * 64 + ew * 8 + (k & 7)) * 4, tot);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sacc[h][j] = 0.f;
+      }
+      epi_bar();
+      for (int i = threadIdx.x - 64; i < BN; i += 32 * kEpiWarps) {
+        if (n0_done + i < p.N) {
+          atomicAdd(p.col_sum + n0_done + i, lds_f32(s_stat_s + i * 4));
+          atomicAdd(p.col_sqsum + n0_done + i, lds_f32(s_stat_s + (BN + i) * 4));
+        }
+      }
+    };
+    const bool prof = p.prof != nullptr && (threadIdx.x == 64 || threadIdx.x == 96 + 128);
+    long long pt[6] = {0, 0, 0, 0, 0, 0};
+    long long tp = prof ? clock64() : 0;
+#define TOK_PROF(i)                      \
+  if (prof) {                            \
+    const long long now = clock64();     \
+    pt[i] += now - tp;                   \
+    tp = now;                            \
+  }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
       const int n0 = (t / m_tiles) * BN;
       const int m0 = (t % m_tiles) * kBlockM;
       const int buf = li & 1;
       const int m = m0 + row;
       const bool row_ok = m < p.M;
-      // (A) every epilogue thread has finished reading the staging tile (statistics pass of the previous tile)
-      epi_bar();
+      uint8_t* cbuf = smem_c + (CBUFS == 2 ? (li & 1) * kCTile : 0);
+      // (A) single staging buffer: every epilogue thread must have finished reading it (statistics pass of the
+      //     previous tile).  With two buffers the readers of this buffer (two tiles ago) are behind barrier (B) of
+      //     the previous tile already.
+      if (CBUFS == 1) epi_bar();
       if (leader) {
-        tma_store_wait_read();  // ... and so has the previous TMA store
-        if (has_addend) {
+        // the TMA store that last read this staging buffer must have drained it
+        if (CBUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else tma_store_wait_read();
+        if (ABUFS == 0 && has_addend) {
           uint32_t bytes = 0;
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
+          for (int j = 0; j < kBlocks; ++j)
             if (n0 + j * 64 < p.N) bytes += kBlockM * 128;
-          mbar_arrive_expect_tx(addend_bar, bytes);
+          mbar_arrive_expect_tx(&addend_full_bar[0], bytes);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            if (n0 + j * 64 < p.N) tma_load_2d(&tmD, addend_bar, smem_c + j * (kBlockM * 128), n0 + j * 64, m0);
+          for (int j = 0; j < kBlocks; ++j)
+            if (n0 + j * 64 < p.N) tma_load_2d(&tmD, &addend_full_bar[0], cbuf + j * (kBlockM * 128), n0 + j * 64, m0);
         }
       }
-      if (want_stats && prev_n0 >= 0 && prev_n0 != n0) {
-        // statistics of a finished n_tile: one global atomic per channel, slots reset by their reader
-        for (int i = threadIdx.x - 64; i < BN; i += 32 * kEpiWarps) {
-          const float t1 = s_stat[i], t2 = s_stat[BN + i];
-          s_stat[i] = 0.f;
-          s_stat[BN + i] = 0.f;
-          if (prev_n0 + i < p.N) {
-            atomicAdd(p.col_sum + prev_n0 + i, t1);
-            atomicAdd(p.col_sqsum + prev_n0 + i, t2);
-          }
-        }
-      }
+      if (want_stats && prev_n0 >= 0 && prev_n0 != n0) flush_stats(prev_n0);  // rare: a finished n_tile
       prev_n0 = n0;
       epi_bar();  // (B) staging buffer free for this tile's writers; statistics slots consistent
+      TOK_PROF(0)
       long long out_row = m;
       if (p.scatter && row_ok) {
         const int pq = p.sc_P * p.sc_Q;
@@ -432,30 +498,54 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       mbar_wait(&tmem_full_bar[buf], (li >> 1) & 1);
       tc_fence_after();
-      if (has_addend) mbar_wait(addend_bar, li & 1);
+      TOK_PROF(1)
+      const uint32_t cbuf_s = smem_u32(cbuf);
+      uint32_t abuf_s = cbuf_s;  // in-place addend by default
+      if (has_addend) {
+        if (ABUFS == 2) {
+          mbar_wait(&addend_full_bar[li & 1], (li >> 1) & 1);
+          abuf_s = smem_u32(smem_d + (li & 1) * kCTile);
+        } else {
+          mbar_wait(&addend_full_bar[0], li & 1);
+        }
+      }
+      TOK_PROF(2)
+      // TMEM loads are issued two at a time before the wait (the chunks are independent; two keeps the register
+      // footprint of the 256-column tile inside the 168-register budget of a 320-thread CTA)
+      constexpr int kInFlight = kChunksPerWarp < 2 ? kChunksPerWarp : 2;
 #pragma unroll 1
-      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
-        const int c = cc * 2 + half;
-        if (c >= kChunks) break;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 32, r);
-        tmem_ld_wait();
+      for (int c0 = 0; c0 < kChunksPerWarp; c0 += kInFlight) {
+      uint32_t r[kInFlight][32];
+#pragma unroll
+      for (int cc = 0; cc < kInFlight; ++cc)
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ((c0 + cc) * 2 + half) * 32,
+                           r[cc]);
+      tmem_ld_wait();
+      if (c0 + kInFlight >= kChunksPerWarp) {
+        // accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
+#pragma unroll
+      for (int cc = 0; cc < kInFlight; ++cc) {
+        const int c = (c0 + cc) * 2 + half;
         const int col0 = n0 + c * 32;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
         }
         // 128B-swizzled staging: 64-column blocks of [128 rows][128 B]; 16-byte chunk index XOR (row & 7)
-        uint8_t* blk = smem_c + (c >> 1) * (kBlockM * 128) + row * 128;
+        const int blk_off = (c >> 1) * (kBlockM * 128) + row * 128;
         if (has_addend) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int chunk = ((c & 1) * 4 + g) ^ (row & 7);
-            const uint4 a = *reinterpret_cast<const uint4*>(blk + chunk * 16);
+            const uint4 a = lds128(abuf_s + blk_off + chunk * 16);
             const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -499,22 +589,25 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int chunk = ((c & 1) * 4 + g) ^ (row & 7);
-            *reinterpret_cast<uint4*>(blk + chunk * 16) =
-                make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+            sts128(cbuf_s + blk_off + chunk * 16,
+                   make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]));
           }
         }
       }
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
+      if (ABUFS == 2 && has_addend) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&addend_empty_bar[li & 1]);
+      }
+      TOK_PROF(3)
       if (!p.scatter) {
         fence_proxy_async_smem();
-        epi_bar();
+        epi_bar();  // (C) tile staged
+        TOK_PROF(4)
         if (leader) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            if (n0 + j * 64 < p.N) tma_store_2d(&tmC, smem_c + j * (kBlockM * 128), n0 + j * 64, m0);
+          for (int j = 0; j < kBlocks; ++j)
+            if (n0 + j * 64 < p.N) tma_store_2d(&tmC, cbuf + j * (kBlockM * 128), n0 + j * 64, m0);
           tma_store_commit();
         }
         if (want_stats) {
@@ -522,61 +615,39 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           // warp ew owns 16-byte chunk ew of each 64-column block; lane l reads rows l, l+32, l+64, l+96
           int rows_valid = p.M - m0;
           if (rows_valid > kBlockM) rows_valid = kBlockM;
-#pragma unroll 1
-          for (int h = 0; h < BN / 64; ++h) {
-            if (n0 + h * 64 >= p.N) break;
-            float a[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = 0.f;
-            const uint8_t* base = smem_c + h * (kBlockM * 128);
+          for (int rr = 0; rr < 4; ++rr) {
+            const int r2 = lane + rr * 32;
+            uint4 vv[kBlocks];
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const int r2 = lane + rr * 32;
-              if (r2 < rows_valid) {
-                const uint4 vv = *reinterpret_cast<const uint4*>(base + r2 * 128 + ((ew ^ (r2 & 7)) * 16));
-                const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
+            for (int h = 0; h < kBlocks; ++h)
+              vv[h] = r2 < rows_valid ? lds128(cbuf_s + h * (kBlockM * 128) + r2 * 128 + ((ew ^ (r2 & 7)) * 16))
+                                      : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float lo = bf16_lo(w4[e]), hi = bf16_hi(w4[e]);
-                  a[2 * e] += lo;
-                  a[2 * e + 1] += hi;
-                  a[8 + 2 * e] = fmaf(lo, lo, a[8 + 2 * e]);
-                  a[8 + 2 * e + 1] = fmaf(hi, hi, a[8 + 2 * e + 1]);
-                }
+            for (int h = 0; h < kBlocks; ++h) {
+              const uint32_t w4[4] = {vv[h].x, vv[h].y, vv[h].z, vv[h].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = bf16_lo(w4[e]), hi = bf16_hi(w4[e]);
+                sacc[h][2 * e] += lo;
+                sacc[h][2 * e + 1] += hi;
+                sacc[h][8 + 2 * e] = fmaf(lo, lo, sacc[h][8 + 2 * e]);
+                sacc[h][8 + 2 * e + 1] = fmaf(hi, hi, sacc[h][8 + 2 * e + 1]);
               }
-            }
-            // 16 values x 32 lanes -> lane pair (2k, 2k+1) ends with the total of value k (halving exchange)
-#pragma unroll
-            for (int s = 16, cnt = 8; s >= 2; s >>= 1, cnt >>= 1) {
-              const bool upper = (lane & s) != 0;
-#pragma unroll
-              for (int i = 0; i < cnt; ++i) {
-                const float send = upper ? a[i] : a[i + cnt];
-                const float keep = upper ? a[i + cnt] : a[i];
-                a[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-              }
-            }
-            a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-            // value index held by this lane: bit3 <- lane&16, bit2 <- lane&8, bit1 <- lane&4, bit0 <- lane&2
-            if ((lane & 1) == 0) {
-              const int k = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              float* dst = s_stat + (k >> 3) * BN + h * 64 + ew * 8 + (k & 7);
-              *dst += a[0];
             }
           }
         }
+        TOK_PROF(5)
       }
     }
+    if (prof) {
+      long long* dst = p.prof + (blockIdx.x * 2 + (threadIdx.x == 64 ? 0 : 1)) * 8;
+      for (int i = 0; i < 6; ++i) dst[i] = pt[i];
+      dst[6] = li;
+    }
+#undef TOK_PROF
     if (leader) tma_store_wait_all();
-    if (want_stats && prev_n0 >= 0) {
-      epi_bar();
-      for (int i = threadIdx.x - 64; i < BN; i += 32 * kEpiWarps) {
-        if (prev_n0 + i < p.N) {
-          atomicAdd(p.col_sum + prev_n0 + i, s_stat[i]);
-          atomicAdd(p.col_sqsum + prev_n0 + i, s_stat[BN + i]);
-        }
-      }
-    }
+    if (want_stats && prev_n0 >= 0) flush_stats(prev_n0);
   }
   __syncthreads();
   if (warp == 1) {
@@ -740,9 +811,10 @@ constexpr int conv_smem_bytes() {
   return STAGES * (kATile + BN * kBlockK * 2) + (2 * STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CBUFS, int ABUFS>
 constexpr int conv_persist_smem_bytes() {
-  return STAGES * (kATile + BN * kBlockK * 2) + kBlockM * BN * 2 + (2 * STAGES + 5) * 8 + 16 + 2 * BN * 4 + 1024;
+  return STAGES * (kATile + BN * kBlockK * 2) + (CBUFS + ABUFS) * kBlockM * BN * 2 + (2 * STAGES + 8) * 8 + 16 +
+         2 * BN * 4 + 1024;
 }
 
 int num_sms() {
@@ -756,13 +828,14 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, bool B_MN>
+template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS>
 static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                     const CUtensorMap& tmD, const ConvFwdParams& p, cudaStream_t st) {
-  constexpr int smem = conv_persist_smem_bytes<BN, STAGES>();
+  constexpr int smem = conv_persist_smem_bytes<BN, STAGES, CBUFS, ABUFS>();
+  static_assert(smem <= 232448, "persistent conv kernel exceeds the 227 KB shared-memory limit");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_persist_kernel<BN, STAGES, B_MN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -771,22 +844,35 @@ static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& t
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fwd_persist_kernel<BN, STAGES, B_MN><<<grid, kPersistThreads, smem, st>>>(tmA, tmB, tmC, tmD, p);
+  conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS><<<grid, kPersistThreads, smem, st>>>(tmA, tmB, tmC, tmD, p);
   return cudaGetLastError();
 }
 
+// Tile configurations (shared memory: operand ring + staging + addend buffers):
+//   BN  64: 6 x 24 KB ring, 2 staging, 2 addend (when the launch has an addend)          = 208 KB
+//   BN 128: 4 x 32 KB ring, 2 staging            | 3 x 32 KB ring, 2 staging, 2 addend   = 192 / 224 KB
+//   BN 256: 3 x 48 KB ring, 1 staging, addend loaded in place                            = 208 KB
 cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                     const CUtensorMap& tmD, const ConvFwdParams& p, int bn, bool b_mn,
                                     cudaStream_t st) {
-  if (bn == 64)
-    return b_mn ? launch_persist_t<64, 6, true>(tmA, tmB, tmC, tmD, p, st)
-                : launch_persist_t<64, 6, false>(tmA, tmB, tmC, tmD, p, st);
-  if (bn == 128)
-    return b_mn ? launch_persist_t<128, 4, true>(tmA, tmB, tmC, tmD, p, st)
-                : launch_persist_t<128, 4, false>(tmA, tmB, tmC, tmD, p, st);
+  const bool add = p.addend != nullptr && !p.scatter;
+  if (bn == 64) {
+    if (add)
+      return b_mn ? launch_persist_t<64, 6, true, 2, 2>(tmA, tmB, tmC, tmD, p, st)
+                  : launch_persist_t<64, 6, false, 2, 2>(tmA, tmB, tmC, tmD, p, st);
+    return b_mn ? launch_persist_t<64, 6, true, 2, 0>(tmA, tmB, tmC, tmD, p, st)
+                : launch_persist_t<64, 6, false, 2, 0>(tmA, tmB, tmC, tmD, p, st);
+  }
+  if (bn == 128) {
+    if (add)
+      return b_mn ? launch_persist_t<128, 3, true, 2, 2>(tmA, tmB, tmC, tmD, p, st)
+                  : launch_persist_t<128, 3, false, 2, 2>(tmA, tmB, tmC, tmD, p, st);
+    return b_mn ? launch_persist_t<128, 4, true, 2, 0>(tmA, tmB, tmC, tmD, p, st)
+                : launch_persist_t<128, 4, false, 2, 0>(tmA, tmB, tmC, tmD, p, st);
+  }
   if (bn == 256)
-    return b_mn ? launch_persist_t<256, 3, true>(tmA, tmB, tmC, tmD, p, st)
-                : launch_persist_t<256, 3, false>(tmA, tmB, tmC, tmD, p, st);
+    return b_mn ? launch_persist_t<256, 3, true, 1, 0>(tmA, tmB, tmC, tmD, p, st)
+                : launch_persist_t<256, 3, false, 1, 0>(tmA, tmB, tmC, tmD, p, st);
   return cudaErrorInvalidValue;
 }
 

@@ -36,6 +36,8 @@ struct ConvFwdParams {
   int scatter, sc_P, sc_Q, sc_H, sc_W, sc_sh, sc_sw;
   // MN-major operand descriptor geometry (bytes): chunk distance, 8-row group distance, advance per 16-row MMA step.
   int mn_lbo, mn_sbo, mn_kadv;
+  // bring-up aid (TOK_CONV_PROFILE=1): per-CTA cycle counts of the epilogue phases, 8 slots per CTA
+  long long* prof;
 };
 
 // Weight-gradient implicit GEMM:  dW[co, tap*Cin + ci] += sum_{pix in split} dy[pix, co] * x_tap[pix, ci]
