@@ -127,6 +127,10 @@ int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2
                       const void* bits, const float* scale, const float* shift, const float* coef_a,
                       const float* coef_c1, const float* coef_c0, void* dy, void* dres, void* stream);
 
+/* dst[n, p*stride, q*stride, :] += src_compact[n, p, q, :] (NHWC bf16, P = (h-1)/stride+1): merges the compact data
+ * gradient of a strided 1x1 downsample conv (timm downsample_conv, resnet.py:14) into the block-input gradient. */
+int tok_strided_add(int n, int h, int w, int c, int stride, const void* src_compact, void* dst, void* stream);
+
 /* ---- pooling (torch.nn.MaxPool2d, resnet.py:510; timm SelectAdaptivePool2d, poolings/classification/pooling.py:8-12)
  * argmax: one byte per output element (window slot of the first maximum). */
 int tok_maxpool_fwd(int n, int h, int w, int c, int k, int s, int pad, const void* x, void* out, void* argmax,
@@ -143,6 +147,21 @@ int tok_gap_bwd(int n, int hw, int c, const void* dout, void* dx, void* stream);
 int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const long long* target, float* loss_sum,
                      void* dlogits, float inv_norm, float gscale, const float* gscale_dev, long long ignore_index,
                      int* correct, void* stream);
+
+/* ---- retrieval metric (IndexBasedMeter.compute, torchok/metrics/index_base_metric.py:170-270: normalise ->
+ *      faiss IndexFlatIP/L2 .search(q, k+1) in batches, :444-545).  Three steps, all on the device:
+ *      1. tok_l2_normalize_rows: xn = x / |x| per row (normalize != 0; SURVEY S6: the reference's golden answers encode
+ *         row-wise cosine) or a copy; also writes a zero-padded bf16 copy with pitch ld_bf16 and the squared norms.
+ *      2. tok_topk_candidates: S = Q * G^T on tcgen05 with a fused running top-kp per query row (kp in {8,16,32}); S is
+ *         never materialised.  g_sqnorm == NULL ranks by inner product, otherwise by -(|g|^2 - 2 q.g) (= L2 order).
+ *      3. tok_topk_rerank: exact fp32 re-scoring of the kp candidates and emission of the best k in faiss order
+ *         (IP descending / squared L2 ascending, ties -> lower index; missing entries -1 / -+inf), int64 indices. */
+int tok_l2_normalize_rows(int n, int d, int normalize, const float* x, float* xn, void* xn_bf16, int ld_bf16,
+                          float* sqnorm, void* stream);
+int tok_topk_candidates(int nq, int ng, int d, int kp, const void* q_bf16, const void* g_bf16, const float* g_sqnorm,
+                        float* cand_score, int* cand_idx, void* stream);
+int tok_topk_rerank(int nq, int d, int kp, int k, int metric, const float* q_f32, const float* g_f32,
+                    const int* cand_idx, float* out_score, long long* out_idx, void* stream);
 
 /* ---- layout (task boundary is NCHW, torchok/tasks/classification.py:108-109) ------------------------------------ */
 int tok_nchw_to_nhwc(int n, int c, int hw, int cp, int src_is_bf16, const void* src, void* dst, void* stream);

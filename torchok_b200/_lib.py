@@ -62,11 +62,15 @@ _SIGS = {
     'tok_bn_apply_bits': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_reduce2': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_apply2': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_strided_add': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_maxpool_fwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_maxpool_bwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_gap_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_gap_bwd': (_i, [_i, _i, _i, _vp, _vp, _vp]),
     'tok_softmax_xent': (_i, [_i, _i, _ll, _vp, _vp, _vp, _vp, _f, _f, _vp, _ll, _vp, _vp]),
+    'tok_l2_normalize_rows': (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'tok_topk_candidates': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_topk_rerank': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_nchw_to_nhwc': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_nhwc_to_nchw': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_sgd_step': (_i, [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),

@@ -199,10 +199,12 @@ static int run_fwd(const void* a, int an, int ah, int aw, int ac, const PixelSrc
 }
 
 static int pick_splits(long long tiles, int total_chunks, int* chunks_per_split) {
-  // One wave of 2 CTAs/SM (every extra split costs a full tile of fp32 reductions), at least 8 K-blocks per CTA.
-  static const int per_sm = getenv("TOK_WGRAD_CTAS_PER_SM") ? atoi(getenv("TOK_WGRAD_CTAS_PER_SM")) : 2;
-  long long target = 148LL * per_sm;
-  int splits = (int)((target + tiles - 1) / tiles);
+  // ONE wave: tiles x splits must not exceed the resident CTAs (2 per SM; 1 per SM when the tiles alone fill half the
+  // chip, since every extra split costs a full tile of fp32 reductions), and at least 8 K-blocks per CTA.
+  static const int forced = getenv("TOK_WGRAD_CTAS_PER_SM") ? atoi(getenv("TOK_WGRAD_CTAS_PER_SM")) : 0;
+  const int per_sm = forced > 0 ? forced : (tiles >= 74 ? 1 : 2);
+  const long long capacity = 148LL * per_sm;
+  int splits = (int)(capacity / tiles);  // floor: never spill into a second wave
   int max_splits = (total_chunks + 7) / 8;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

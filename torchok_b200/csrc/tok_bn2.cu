@@ -267,6 +267,29 @@ bn_bwd_apply2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ d
   }
 }
 
+// dst[n, p*s, q*s, :] += src[n, p, q, :]  — merges the compact data gradient of a strided 1x1 (downsample) conv
+// into the full-resolution gradient of the block input (replaces a zero-filled scatter + full-size addend read)
+__global__ void __launch_bounds__(256)
+strided_add_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total, int P, int Q, int cvec,
+                   int H, int W, int s) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    const int q = (int)(pix % Q);
+    pix /= Q;
+    const int p = (int)(pix % P);
+    const long long n = pix / P;
+    const long long o = ((n * H + (long long)p * s) * W + (long long)q * s) * cvec + cv;
+    float a[8], b[8];
+    unpack8(ldg_stream(src + i), a);
+    unpack8(dst[o], b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] += a[j];
+    dst[o] = pack8(b);
+  }
+}
+
 struct Grid2 {
   dim3 grid;
   int cvec, cvec_b, rows_per_cta;
@@ -304,6 +327,19 @@ int tok_bn_apply_bits(long long rows, int C, const void* y, const float* scale, 
                                                                 (uint8_t*)bits, scale, shift, rows, g.cvec, g.cvec_b,
                                                                 g.rows_per_cta);
   TOK_CHECK_LAUNCH("bn_apply_bits");
+  return TOK_OK;
+}
+
+int tok_strided_add(int n, int h, int w, int c, int stride, const void* src_compact, void* dst, void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8) || stride <= 0)
+    return set_error(TOK_ERR_INVALID, "strided_add: bad shape (c must be a positive multiple of 8)");
+  const int P = (h - 1) / stride + 1, Q = (w - 1) / stride + 1;
+  const long long total = (long long)n * P * Q * (c / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  strided_add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src_compact, (uint4*)dst, total,
+                                                                       P, Q, c / 8, h, w, stride);
+  TOK_CHECK_LAUNCH("strided_add");
   return TOK_OK;
 }
 

@@ -250,7 +250,7 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
 
 
 def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=None, want_dres=False,
-                  wgrad_into=None, dgamma=None, dbeta=None):
+                  wgrad_into=None, dgamma=None, dbeta=None, compact_dx=False):
     """Backward of `unit_forward`.  Returns (dx or None, dres or None).  Parameter gradients are ACCUMULATED into
     wgrad_into / dgamma / dbeta (fp32, may be None for frozen parameters)."""
     L = lib()
@@ -272,13 +272,26 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
     L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                         _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
     dx = None
-    if need_dx:
+    if need_dx and compact_dx:
+        # strided 1x1 conv: the data gradient lives on the (p*stride, q*stride) sub-lattice only; return it compact
+        # ([N, P, Q, C] = a plain GEMM) and let the caller merge it with tok_strided_add
+        assert d.r == 1 and d.s == 1 and d.pad == 0 and dx_addend is None
+        dx = torch.empty((d.n, y.shape[1], y.shape[2], d.c), dtype=BF16, device=dev)
+        L.tok_linear_dgrad(rows, kp, d.c, _p(dy), _p(w), _p(dx), st)
+    elif need_dx:
         dx = torch.empty((d.n, d.h, d.w, d.c), dtype=BF16, device=dev)
         conv_dgrad(d, dy, w, dx, dx_addend)
         dx = dx.permute(0, 3, 1, 2)
     if wgrad_into is not None:
         L.tok_conv_wgrad(C.byref(d), _p(x), _p(dy), _p(wgrad_into), st)
     return dx, (dres.permute(0, 3, 1, 2) if dres is not None else None)
+
+
+def strided_add(dst, src_compact, stride):
+    """dst[n, :, p*stride, q*stride] += src_compact[n, p, q, :]  (dst: NHWC-backed (N,C,H,W); src: [N,P,Q,C])."""
+    n, c, h, w = dst.shape
+    lib().tok_strided_add(n, h, w, nhwc_pitch(dst), stride, _p(src_compact), _p(dst), _st())
+    return dst
 
 
 # ------------------------------------------------------------------------------------------------------ pooling

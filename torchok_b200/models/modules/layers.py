@@ -297,11 +297,19 @@ class ResidualBlockFn(torch.autograd.Function):
             conv, bn = units[i]
             dh, _ = _unit_bwd(saved_all[off + i], descs[off + i], conv, bn, dh)
         need_dx = ctx.needs_input_grad[0]
-        addend = g
+        addend, compact = g, None
         if ds is not None:
-            addend, _ = _unit_bwd(saved_all[0], descs[0], ds[0], ds[1], g, need_dx=need_dx)
+            dd = descs[0]
+            if dd.stride > 1 and dd.r == 1 and dd.s == 1 and dd.pad == 0:
+                # strided 1x1 shortcut: compact GEMM now, merged into dx below (no zero-filled scatter tensor)
+                compact, _ = _unit_bwd(saved_all[0], dd, ds[0], ds[1], g, need_dx=need_dx, compact_dx=True)
+                addend = None
+            else:
+                addend, _ = _unit_bwd(saved_all[0], dd, ds[0], ds[1], g, need_dx=need_dx)
         conv, bn = units[0]
         dx, _ = _unit_bwd(saved_all[off], descs[off], conv, bn, dh, need_dx=need_dx, dx_addend=addend)
+        if compact is not None and dx is not None:
+            K.strided_add(dx, compact, descs[0].stride)
         return (dx, None, None) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
