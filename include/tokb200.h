@@ -148,6 +148,30 @@ int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const lo
                      void* dlogits, float inv_norm, float gscale, const float* gscale_dev, long long ignore_index,
                      int* correct, void* stream);
 
+/* ---- embedding heads and the pairwise loss (tok_heads.cu) ------------------------------------------------------------
+ * F.normalize (LinearHead(normalize=True), linear_head.py:33-35; ArcFaceHead, arcface_head.py:125-126):
+ *   xhat = scale * x / max(|x|, 1e-12) per row, bf16 with pitch ld_out (pad columns zeroed), inv_norm = 1/max(|x|,eps);
+ *   backward dx = scale*inv_norm*(g - u(u.g)), u = x/|x|; dx is bf16 (stored) or fp32 (accumulated if `accumulate`). */
+int tok_rownorm_fwd(int rows, int d, const void* x, int x_is_bf16, float scale, void* xhat_bf16, int ld_out,
+                    float* inv_norm, void* stream);
+int tok_rownorm_bwd(int rows, int d, const void* x, int x_is_bf16, const float* inv_norm, float scale, const void* g,
+                    int g_is_bf16, int ld_g, void* dx, int dx_is_bf16, int accumulate, void* stream);
+/* ArcFaceHead.__add_margin (arcface_head.py:95-108).  `logits` = scale*cosine comes from tok_linear_fwd on
+ * xs = scale*x_hat and wh = w_hat; the forward replaces the target column of each row by scale*phi(cos_t) (cos_t
+ * recomputed in fp32 and saved), the backward multiplies dlogits[r, target] by dphi/dcos. */
+int tok_arcface_margin_fwd(int rows, int d, int ld_x, const void* xs_bf16, const void* wh_bf16,
+                           const long long* target, int num_classes, void* logits_bf16, long long ld_logits,
+                           float scale, float margin, int easy_margin, float* cos_t, void* stream);
+int tok_arcface_margin_bwd(int rows, const long long* target, int num_classes, const float* cos_t,
+                           void* dlogits_bf16, long long ld_logits, float scale, float margin, int easy_margin,
+                           void* stream);
+/* ContrastiveLoss.calc_loss (losses/representation/pairwise.py:126-136): S = cdist(emb1, emb2) (B x M, fp32),
+ * loss_rows[i] = sum_j (1-R)relu(margin-S)^2 + R S^2; backward given d(loss_rows). */
+int tok_contrastive_fwd(int B, int M, int d, const float* emb1, const float* emb2, const float* R, float margin,
+                        float* S, float* loss_rows, void* stream);
+int tok_contrastive_bwd(int B, int M, int d, const float* emb1, const float* emb2, const float* R, const float* S,
+                        const float* grad_rows, float margin, float* d_emb1, float* d_emb2, void* stream);
+
 /* ---- retrieval metric (IndexBasedMeter.compute, torchok/metrics/index_base_metric.py:170-270: normalise ->
  *      faiss IndexFlatIP/L2 .search(q, k+1) in batches, :444-545).  Three steps, all on the device:
  *      1. tok_l2_normalize_rows: xn = x / |x| per row (normalize != 0; SURVEY S6: the reference's golden answers encode

@@ -280,3 +280,34 @@ def dedegenerate_(model, seed=0):
                 m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
                 m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
     return model
+
+
+# ---- pairwise path (torchok/losses/representation/pairwise.py:9-136, torchok/tasks/pairwise_task.py:87-107) --------
+class ContrastiveLoss(nn.Module):
+    """S = cdist(emb1, emb2); L_i = sum_j (1-R) relu(mu-S)^2 + R S^2; optional L1/L2 regulariser; mean/sum."""
+
+    def __init__(self, margin, reg=None, reduction='mean', eps=1e-3):
+        super().__init__()
+        self.margin, self.reg, self.reduction, self.eps = margin, reg, reduction, eps
+
+    def forward(self, emb1, emb2, R):
+        S = torch.cdist(emb1, emb2, p=2, compute_mode='donot_use_mm_for_euclid_dist')
+        L = ((1. - R) * F.relu(self.margin - S).pow(2) + R * S.pow(2)).sum(1)
+        if self.reg == 'L1':
+            L = L + self.eps * emb1.abs().sum(1)
+        elif self.reg == 'L2':
+            L = L + self.eps * torch.norm(emb1, p=None, dim=1)
+        elif self.reg is not None:
+            raise ValueError(f'Unknown regularization type: {self.reg}')
+        if self.reduction == 'mean':
+            return L.mean()
+        if self.reduction == 'sum':
+            return L.sum()
+        raise ValueError(f'Unknown reduction type: {self.reduction}')
+
+
+def calc_relevance_matrix(y, num_classes):
+    """pairwise_task.py:87-107: one-hot -> y y^T > 0."""
+    if y.ndim == 1:
+        y = torch.zeros(y.shape[0], num_classes).scatter_(1, y[:, None], 1)
+    return torch.where(torch.matmul(y, y.transpose(1, 0)) > 0, 1., 0.)

@@ -68,6 +68,12 @@ _SIGS = {
     'tok_gap_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_gap_bwd': (_i, [_i, _i, _i, _vp, _vp, _vp]),
     'tok_softmax_xent': (_i, [_i, _i, _ll, _vp, _vp, _vp, _vp, _f, _f, _vp, _ll, _vp, _vp]),
+    'tok_rownorm_fwd': (_i, [_i, _i, _vp, _i, _f, _vp, _i, _vp, _vp]),
+    'tok_rownorm_bwd': (_i, [_i, _i, _vp, _i, _vp, _f, _vp, _i, _i, _vp, _i, _i, _vp]),
+    'tok_arcface_margin_fwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _ll, _f, _f, _i, _vp, _vp]),
+    'tok_arcface_margin_bwd': (_i, [_i, _vp, _i, _vp, _vp, _ll, _f, _f, _i, _vp]),
+    'tok_contrastive_fwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    'tok_contrastive_bwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     'tok_l2_normalize_rows': (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'tok_topk_candidates': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_topk_rerank': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -496,8 +496,134 @@ def softmax_xent(logits, target, ignore_index=-100, correct=None):
     return SoftmaxXentFn.apply(logits, target, ignore_index, correct)
 
 
+class RowNormFn(torch.autograd.Function):
+    """F.normalize(x, p=2, dim=1) on (rows, d) bf16/fp32 input -> bf16 (linear_head.py:33-35)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        require_cuda(x, 'embeddings')
+        if x.dtype not in (BF16, F32):
+            x = x.float()
+        x = x.contiguous()
+        rows, d = x.shape
+        out = torch.empty((rows, d), dtype=BF16, device=x.device)
+        inv = torch.empty((rows,), dtype=F32, device=x.device)
+        lib().tok_rownorm_fwd(rows, d, _p(x), int(x.dtype == BF16), 1.0, _p(out), d, _p(inv), _st())
+        ctx.save_for_backward(x, inv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, inv = ctx.saved_tensors
+        rows, d = x.shape
+        if g.dtype not in (BF16, F32):
+            g = g.float()
+        g = g.contiguous()
+        dx = torch.empty((rows, d), dtype=x.dtype, device=x.device)
+        lib().tok_rownorm_bwd(rows, d, _p(x), int(x.dtype == BF16), _p(inv), 1.0, _p(g), int(g.dtype == BF16), d,
+                              _p(dx), int(x.dtype == BF16), 0, _st())
+        return dx
+
+
 def l2_normalize(x):
-    raise NotImplementedError('l2_normalize kernel not built yet')
+    return RowNormFn.apply(x)
+
+
+class ArcFaceFn(torch.autograd.Function):
+    """Training branch of ArcFaceHead.forward (arcface_head.py:125-128): scale * where(onehot, phi(cos), cos) with
+    cos = normalize(x) @ normalize(W)^T.  x (B, D) bf16/fp32, weight (C, D) fp32 master, target (B,) int64."""
+
+    @staticmethod
+    def forward(ctx, x, weight, target, scale, margin, easy_margin):
+        require_cuda(x, 'ArcFace input')
+        L = lib()
+        st = _st()
+        if x.dtype not in (BF16, F32):
+            x = x.float()
+        x = x.contiguous()
+        b, d = x.shape
+        c = weight.shape[0]
+        dp, cp = ceil8(d), ceil8(c)
+        dev = x.device
+        w = weight.detach().contiguous()
+        xs = torch.empty((b, dp), dtype=BF16, device=dev)        # scale * x_hat
+        x_inv = torch.empty((b,), dtype=F32, device=dev)
+        wh = torch.zeros((cp, dp), dtype=BF16, device=dev)       # w_hat (pad rows stay zero)
+        w_inv = torch.empty((c,), dtype=F32, device=dev)
+        L.tok_rownorm_fwd(b, d, _p(x), int(x.dtype == BF16), float(scale), _p(xs), dp, _p(x_inv), st)
+        L.tok_rownorm_fwd(c, d, _p(w), 0, 1.0, _p(wh), dp, _p(w_inv), st)
+        logits = torch.empty((b, cp), dtype=BF16, device=dev)
+        L.tok_linear_fwd(b, cp, dp, _p(xs), _p(wh), None, _p(logits), st)
+        target = target.long().contiguous()
+        cos_t = torch.zeros((b,), dtype=F32, device=dev)
+        L.tok_arcface_margin_fwd(b, dp, dp, _p(xs), _p(wh), _p(target), c, _p(logits), cp, float(scale),
+                                 float(margin), int(easy_margin), _p(cos_t), st)
+        ctx.save_for_backward(x, xs, x_inv, wh, w_inv, target, cos_t)
+        ctx.meta = (weight, b, d, c, dp, cp, float(scale), float(margin), int(easy_margin))
+        return logits if cp == c else logits[:, :c]
+
+    @staticmethod
+    def backward(ctx, g):
+        x, xs, x_inv, wh, w_inv, target, cos_t = ctx.saved_tensors
+        weight, b, d, c, dp, cp, scale, margin, easy = ctx.meta
+        L = lib()
+        st = _st()
+        dev = x.device
+        dl = torch.zeros((b, cp), dtype=BF16, device=dev) if cp != c else torch.empty((b, cp), dtype=BF16, device=dev)
+        dl[:, :c] = g  # private copy: the target column is rescaled in place
+        L.tok_arcface_margin_bwd(b, _p(target), c, _p(cos_t), _p(dl), cp, scale, margin, easy, st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxs = torch.empty((b, dp), dtype=BF16, device=dev)   # gradient w.r.t. xs = scale * x_hat
+            L.tok_linear_dgrad(b, cp, dp, _p(dl), _p(wh), _p(dxs), st)
+            dx = torch.empty((b, d), dtype=x.dtype, device=dev)
+            L.tok_rownorm_bwd(b, d, _p(x), int(x.dtype == BF16), _p(x_inv), scale, _p(dxs), 1, dp, _p(dx),
+                              int(x.dtype == BF16), 0, st)
+        if weight.requires_grad:
+            dwh = torch.zeros((cp, dp), dtype=F32, device=dev)   # gradient w.r.t. w_hat
+            L.tok_linear_wgrad(b, cp, dp, _p(xs), _p(dl), _p(dwh), st)
+            gw = grad_buffer(weight)
+            L.tok_rownorm_bwd(c, d, _p(weight.detach().contiguous()), 0, _p(w_inv), 1.0, _p(dwh), 0, dp, _p(gw), 0, 1, st)
+            grad_ready(weight)
+        return dx, None, None, None, None, None
+
+
+def arcface(x, weight, target, scale, margin, easy_margin=False):
+    return ArcFaceFn.apply(x, weight, target, scale, margin, easy_margin)
+
+
+class ContrastiveFn(torch.autograd.Function):
+    """ContrastiveLoss.calc_loss (losses/representation/pairwise.py:126-136) -> per-row loss (B,) fp32."""
+
+    @staticmethod
+    def forward(ctx, emb1, emb2, R, margin):
+        require_cuda(emb1, 'emb1')
+        e1, e2 = emb1.float().contiguous(), emb2.float().contiguous()
+        R = R.float().contiguous()
+        b, d = e1.shape
+        m = e2.shape[0]
+        S = torch.empty((b, m), dtype=F32, device=e1.device)
+        rows = torch.empty((b,), dtype=F32, device=e1.device)
+        lib().tok_contrastive_fwd(b, m, d, _p(e1), _p(e2), _p(R), float(margin), _p(S), _p(rows), _st())
+        ctx.save_for_backward(e1, e2, R, S)
+        ctx.meta = (float(margin), emb1.dtype, emb2.dtype)
+        return rows
+
+    @staticmethod
+    def backward(ctx, g):
+        e1, e2, R, S = ctx.saved_tensors
+        margin, t1, t2 = ctx.meta
+        b, d = e1.shape
+        m = e2.shape[0]
+        g = g.float().contiguous()
+        d1 = torch.empty_like(e1) if ctx.needs_input_grad[0] else None
+        d2 = torch.empty_like(e2) if ctx.needs_input_grad[1] else None
+        lib().tok_contrastive_bwd(b, m, d, _p(e1), _p(e2), _p(R), _p(S), _p(g), margin, _p(d1), _p(d2), _st())
+        return (d1.to(t1) if d1 is not None else None), (d2.to(t2) if d2 is not None else None), None, None
+
+
+def contrastive_rows(emb1, emb2, R, margin):
+    return ContrastiveFn.apply(emb1, emb2, R, margin)
 
 
 def softmax_xent_nhwc(logits, target, ignore_index=-100):

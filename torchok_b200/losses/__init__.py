@@ -1,3 +1,4 @@
 from ..constructor import LOSSES
 from .base import JointLoss  # noqa: F401
 from .classification import CrossEntropyLoss  # noqa: F401
+from . import pairwise  # noqa: F401

@@ -1,1 +1,2 @@
 from .classification import ClassificationHead, LinearHead  # noqa: F401
+from . import arcface  # noqa: F401
