@@ -148,6 +148,26 @@ int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const lo
                      void* dlogits, float inv_norm, float gscale, const float* gscale_dev, long long ignore_index,
                      int* correct, void* stream);
 
+/* ---- HRNet / segmentation passes (tok_seg.cu) ---------------------------------------------------------------------------
+ * timm HighResolutionModule fuse (torchok/models/backbones/hrnet.py:167-192): out = relu(sum_t nearest_up(term_t)), term t
+ * at resolution (h >> shifts[t], w >> shifts[t]); bits (nullable) = ReLU mask, 1 bit/element.  Backward per term. */
+int tok_fuse_sum_fwd(int n, int h, int w, int c, int nterms, const void* const* terms, const int* shifts, int relu,
+                     void* out, void* bits, void* stream);
+int tok_fuse_sum_bwd(int n, int h, int w, int c, int shift, const void* dout, const void* bits, void* dterm,
+                     void* stream);
+/* F.interpolate(mode='bilinear', align_corners=False) (necks/segmentation/hrnet.py:35-38, heads/segmentation/base.py:37)
+ * writing into channels [dst_c_offset, dst_c_offset + c) of a dst_c-channel NHWC tensor (= the torch.cat of the neck). */
+int tok_bilinear_fwd(int n, int hi, int wi, int c, int ho, int wo, const void* src, void* dst, int dst_c,
+                     int dst_c_offset, void* stream);
+int tok_bilinear_bwd(int n, int hi, int wi, int c, int ho, int wo, const void* dout, int dout_c, int dout_c_offset,
+                     void* dsrc, void* stream);
+/* CrossEntropyLoss over many short rows (segmentation logits, C <= 64, row pitch ld): forward (dlogits == NULL) adds the
+ * NLL sum and the number of non-ignored rows to loss_sum / count; backward writes (softmax - onehot) * gscale *
+ * (*gscale_dev) * (*inv_count_dev). */
+int tok_softmax_xent_small(long long rows, int C, int ld, const void* logits, const long long* target,
+                           float* loss_sum, float* count, void* dlogits, const float* inv_count_dev, float gscale,
+                           const float* gscale_dev, long long ignore_index, void* stream);
+
 /* ---- embedding heads and the pairwise loss (tok_heads.cu) ------------------------------------------------------------
  * F.normalize (LinearHead(normalize=True), linear_head.py:33-35; ArcFaceHead, arcface_head.py:125-126):
  *   xhat = scale * x / max(|x|, 1e-12) per row, bf16 with pitch ld_out (pad columns zeroed), inv_norm = 1/max(|x|,eps);

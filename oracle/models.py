@@ -311,3 +311,232 @@ def calc_relevance_matrix(y, num_classes):
     if y.ndim == 1:
         y = torch.zeros(y.shape[0], num_classes).scatter_(1, y[:, None], 1)
     return torch.where(torch.matmul(y, y.transpose(1, 0)) > 0, 1., 0.)
+
+
+# ---- HRNet (torchok/models/backbones/hrnet.py:49-255 + timm 0.6.13 HighResolutionModule / cfg_cls, Appendix A.2) --------
+def _hr_stage(modules, branches, block, blocks, channels):
+    return dict(NUM_MODULES=modules, NUM_BRANCHES=branches, BLOCK=block, NUM_BLOCKS=tuple(blocks),
+                NUM_CHANNELS=tuple(channels))
+
+
+def _hr_cfg(c, s1_blocks=4, s1_ch=64, blocks=4, mods=(1, 4, 3)):
+    return dict(STEM_WIDTH=64, STAGE1=_hr_stage(1, 1, 'BOTTLENECK', (s1_blocks,), (s1_ch,)),
+                STAGE2=_hr_stage(mods[0], 2, 'BASIC', (blocks,) * 2, (c, 2 * c)),
+                STAGE3=_hr_stage(mods[1], 3, 'BASIC', (blocks,) * 3, (c, 2 * c, 4 * c)),
+                STAGE4=_hr_stage(mods[2], 4, 'BASIC', (blocks,) * 4, (c, 2 * c, 4 * c, 8 * c)))
+
+
+HRNET_CFGS = dict(hrnet_w18_small=_hr_cfg(16, 1, 32, 2, (1, 1, 1)), hrnet_w18_small_v2=_hr_cfg(18, 2, 64, 2, (1, 3, 2)),
+                  hrnet_w18=_hr_cfg(18), hrnet_w32=_hr_cfg(32))
+_HR_BLOCKS = {'BASIC': BasicBlock, 'BOTTLENECK': Bottleneck}
+
+
+class _CB(nn.Sequential):
+    """Conv2d -> BatchNorm2d [-> ReLU | Upsample] evaluated with the precision policy of this file."""
+
+    def forward(self, x):
+        x = self[1](conv(self[0], x))
+        for m in list(self)[2:]:
+            x = m(x)
+        return q(x)
+
+
+def _cb(cin, cout, k, s, p, tail=None):
+    mods = [nn.Conv2d(cin, cout, k, s, p, bias=False), nn.BatchNorm2d(cout)]
+    if tail is not None:
+        mods.append(tail)
+    return _CB(*mods)
+
+
+def _hr_layer(block, cin, planes, n, stride=1):
+    ds = None
+    if stride != 1 or cin != planes * block.expansion:
+        ds = nn.Sequential(nn.Conv2d(cin, planes * block.expansion, 1, stride, bias=False),
+                           nn.BatchNorm2d(planes * block.expansion))
+    layers = [block(cin, planes, stride, ds)]
+    layers += [block(planes * block.expansion, planes) for _ in range(1, n)]
+    return nn.Sequential(*layers)
+
+
+class HighResolutionModule(nn.Module):
+    def __init__(self, num_branches, block, num_blocks, num_inchannels, num_channels, multi_scale_output=True):
+        super().__init__()
+        self.num_branches, self.num_inchannels = num_branches, list(num_inchannels)
+        branches = []
+        for i in range(num_branches):
+            branches.append(_hr_layer(block, self.num_inchannels[i], num_channels[i], num_blocks[i]))
+            self.num_inchannels[i] = num_channels[i] * block.expansion
+        self.branches = nn.ModuleList(branches)
+        ch = self.num_inchannels
+        if num_branches == 1:
+            self.fuse_layers = nn.Identity()
+        else:
+            rows = []
+            for i in range(num_branches if multi_scale_output else 1):
+                row = []
+                for j in range(num_branches):
+                    if j > i:
+                        row.append(_cb(ch[j], ch[i], 1, 1, 0, nn.Upsample(scale_factor=2 ** (j - i), mode='nearest')))
+                    elif j == i:
+                        row.append(nn.Identity())
+                    else:
+                        chain = []
+                        for k in range(i - j):
+                            last = k == i - j - 1
+                            chain.append(_cb(ch[j], ch[i] if last else ch[j], 3, 2, 1, None if last else nn.ReLU()))
+                        row.append(nn.Sequential(*chain))
+                rows.append(nn.ModuleList(row))
+            self.fuse_layers = nn.ModuleList(rows)
+
+    def forward(self, x):
+        if self.num_branches == 1:
+            return [self.branches[0](x[0])]
+        x = [b(x[i]) for i, b in enumerate(self.branches)]
+        out = []
+        for i, row in enumerate(self.fuse_layers):
+            y = x[0] if i == 0 else row[0](x[0])
+            for j in range(1, self.num_branches):
+                y = y + (x[j] if i == j else row[j](x[j]))
+            out.append(q(F.relu(y)))
+        return out
+
+
+class HighResolutionNet(nn.Module):
+    def __init__(self, cfg, in_channels=3):
+        super().__init__()
+        self.out_encoder_channels = tuple(cfg['STAGE4']['NUM_CHANNELS'])
+        self.conv1 = nn.Conv2d(in_channels, cfg['STEM_WIDTH'], 3, 2, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cfg['STEM_WIDTH'])
+        self.conv2 = nn.Conv2d(cfg['STEM_WIDTH'], 64, 3, 2, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(64)
+        s1 = cfg['STAGE1']
+        block = _HR_BLOCKS[s1['BLOCK']]
+        self.layer1 = _hr_layer(block, 64, s1['NUM_CHANNELS'][0], s1['NUM_BLOCKS'][0])
+        pre = [block.expansion * s1['NUM_CHANNELS'][0]]
+        for idx in (2, 3, 4):
+            sc = cfg[f'STAGE{idx}']
+            block = _HR_BLOCKS[sc['BLOCK']]
+            cur = [c * block.expansion for c in sc['NUM_CHANNELS']]
+            trans = []
+            for i in range(len(cur)):
+                if i < len(pre):
+                    trans.append(_cb(pre[i], cur[i], 3, 1, 1, nn.ReLU()) if cur[i] != pre[i] else nn.Identity())
+                else:
+                    chain = []
+                    for j in range(i + 1 - len(pre)):
+                        cout = cur[i] if j == i - len(pre) else pre[-1]
+                        chain.append(_cb(pre[-1], cout, 3, 2, 1, nn.ReLU()))
+                    trans.append(nn.Sequential(*chain))
+            setattr(self, f'transition{idx - 1}', nn.ModuleList(trans))
+            mods, inch = [], cur
+            for _ in range(sc['NUM_MODULES']):
+                mods.append(HighResolutionModule(sc['NUM_BRANCHES'], block, sc['NUM_BLOCKS'], inch, sc['NUM_CHANNELS']))
+                inch = mods[-1].num_inchannels
+            setattr(self, f'stage{idx}', nn.Sequential(*mods))
+            pre = inch
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+
+    def forward(self, x):
+        x = q(F.relu(self.bn1(conv(self.conv1, q(x)))))
+        x = q(F.relu(self.bn2(conv(self.conv2, x))))
+        x = self.layer1(x)
+        xl = [t(x) for t in self.transition1]
+        for m in self.stage2:
+            xl = m(xl)
+        xl = [t(xl[-1]) if not isinstance(t, nn.Identity) else xl[i] for i, t in enumerate(self.transition2)]
+        for m in self.stage3:
+            xl = m(xl)
+        xl = [t(xl[-1]) if not isinstance(t, nn.Identity) else xl[i] for i, t in enumerate(self.transition3)]
+        for m in self.stage4:
+            xl = m(xl)
+        return xl
+
+    def forward_features(self, x):
+        return [x] + self.forward(x)
+
+
+def hrnet(name, in_channels=3):
+    return HighResolutionNet(HRNET_CFGS[name], in_channels)
+
+
+class HRNetSegmentationNeck(nn.Module):
+    """necks/segmentation/hrnet.py:16-42"""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.out_channels = sum(in_channels)
+        self.convbnact = ConvBnAct(self.out_channels, self.out_channels, 1)
+
+    def forward(self, features):
+        image, x0, x1, x2, x3 = features
+        size = x0.shape[2:]
+        up = [x0] + [q(F.interpolate(t, size=size, mode='bilinear', align_corners=False)) for t in (x1, x2, x3)]
+        return [image, self.convbnact(torch.cat(up, 1))]
+
+
+class HRNetClassificationNeck(nn.Module):
+    """necks/classification/hrnet.py:12-85, overwrite quirk included."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        hc = [32, 64, 128, 256]
+        self.out_channels = 2048
+
+        def layer(cin, planes):
+            ds = ConvBnAct(cin, planes * 4, 1, act=False) if cin != planes * 4 else None
+            return nn.Sequential(_NeckBottleneck(cin, planes, 1, ds))
+        self.incre_modules = nn.ModuleList([layer(c, hc[i]) for i, c in enumerate(in_channels)])
+        self.downsamp_modules = nn.ModuleList([ConvBnAct(hc[i] * 4, hc[i + 1] * 4, 3, padding=1, stride=2)
+                                               for i in range(len(in_channels) - 1)])
+        self.final_layer = ConvBnAct(hc[3] * 4, 2048, 1)
+
+    def forward(self, x):
+        y = self.incre_modules[0](x[0])
+        for i in range(len(self.downsamp_modules)):
+            y = self.downsamp_modules[i](y)
+            if i + 1 < len(x):
+                y = self.incre_modules[i + 1](x[i + 1])
+        return self.final_layer(y)
+
+
+class _NeckBottleneck(Bottleneck):
+    """timm Bottleneck whose shortcut is a ConvBnAct(act_layer=None) module (necks/classification/hrnet.py:60-68)."""
+
+    def forward(self, x):
+        shortcut = x
+        x = q(F.relu(self.bn1(conv(self.conv1, x))))
+        x = q(F.relu(self.bn2(conv(self.conv2, x))))
+        x = self.bn3(conv(self.conv3, x))
+        if self.downsample is not None:
+            shortcut = self.downsample(shortcut)
+        return q(F.relu(x + shortcut))
+
+
+class SegmentationHead(nn.Module):
+    """heads/segmentation/base.py:11-41"""
+
+    def __init__(self, in_channels, num_classes, do_interpolate=True):
+        super().__init__()
+        self.num_classes, self.do_interpolate = num_classes, do_interpolate
+        self.classifier = nn.Conv2d(in_channels, num_classes, 1)
+
+    def forward(self, x):
+        image, feats = x
+        logits = conv(self.classifier, feats)
+        if self.do_interpolate:
+            logits = q(F.interpolate(logits, size=image.shape[2:], mode='bilinear'))
+        return logits[:, 0] if self.num_classes == 1 else logits
+
+
+class SegmentationTask(nn.Module):
+    """tasks/segmentation.py:67-94"""
+
+    def __init__(self, backbone, neck, head):
+        super().__init__()
+        self.backbone, self.neck, self.head = backbone, neck, head
+
+    def forward_with_gt(self, batch):
+        pred = self.head(self.neck(self.backbone.forward_features(batch['image'])))
+        return {'prediction': pred, 'target': batch.get('target')}

@@ -1,0 +1,198 @@
+"""GPU parity of the HRNet / segmentation path against the CPU oracle.
+
+Element-wise passes (fuse, bilinear, pixel-wise CE) are compared with the torch ops the reference calls, on
+bf16-representable inputs: 1e-2 of the tensor maximum (one bf16 ulp of the stored result is 4e-3 relative).  Whole
+networks use the same bar as the ResNet tests: GPU error vs the fp32 oracle <= 1.5 x (oracle bf16-AMP error) + 5e-3.
+Shape contracts are the reference's own (tests/additional_tests/models/backbones/test_backbone.py:70-93,
+tests/additional_tests/models/necks/test_hrnet.py:15-26, .../heads/test_segmentation.py)."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize('c,h,shifts', [(18, 16, (0, 1, 2)), (64, 8, (0, 1)), (144, 8, (0, 0, 0, 0)), (36, 32, (0, 3))])
+def test_fuse_sum_matches_upsample_add_relu(c, h, shifts):
+    from torchok_b200 import kernels as K
+    torch.manual_seed(c + h)
+    terms = [_bf(torch.randn(2, c, h >> s, h >> s)) for s in shifts]
+    ref_in = [t.clone().requires_grad_(True) for t in terms]
+    y = sum(t if s == 0 else F.interpolate(t, scale_factor=2 ** s, mode='nearest') for t, s in zip(ref_in, shifts))
+    y = F.relu(y)
+    r = _bf(torch.randn_like(y))
+    (y * r).sum().backward()
+    gin = [t.cuda().requires_grad_(True) for t in terms]
+    out = K.fuse_sum(gin, relu=True)
+    assert tuple(out.shape) == tuple(y.shape)
+    (out.float() * r.cuda()).sum().backward()
+    assert rel_err(out, y) < 1e-2
+    for a, b in zip(gin, ref_in):
+        assert rel_err(a.grad, b.grad) < 1e-2
+
+
+@pytest.mark.parametrize('chans,sizes,out', [((18, 36, 72, 144), (16, 8, 4, 2), 16), ((16,), (8,), 32), ((10,), (16,), 64),
+                                             ((8, 24), (12, 5), 12)])
+def test_bilinear_cat_matches_interpolate(chans, sizes, out):
+    from torchok_b200 import kernels as K
+    torch.manual_seed(sum(chans))
+    xs = [_bf(torch.randn(2, c, s, s)) for c, s in zip(chans, sizes)]
+    ref_in = [x.clone().requires_grad_(True) for x in xs]
+    ups = [F.interpolate(x, size=(out, out), mode='bilinear', align_corners=False) for x in ref_in]
+    y = torch.cat(ups, 1)
+    r = _bf(torch.randn_like(y))
+    (y * r).sum().backward()
+    gin = [x.cuda().requires_grad_(True) for x in xs]
+    cat = K.bilinear_cat(gin, (out, out))
+    # the product concat pads every segment to a multiple of 8 channels: gather the logical channels back
+    segs, off = [], 0
+    for c in chans:
+        segs.append(cat[:, off:off + c])
+        off += K.ceil8(c)
+    got = torch.cat(segs, 1)
+    assert rel_err(got, y) < 1e-2
+    (got.float() * r.cuda()).sum().backward()
+    for a, b in zip(gin, ref_in):
+        assert rel_err(a.grad, b.grad) < 1e-2
+
+
+@pytest.mark.parametrize('n,c,h', [(2, 10, 16), (3, 21, 8), (1, 2, 32)])
+def test_pixelwise_cross_entropy(n, c, h):
+    import torchok_b200 as tb
+    torch.manual_seed(c)
+    x = _bf(torch.randn(n, c, h, h) * 3)
+    t = torch.randint(0, c, (n, h, h))
+    t[0, :2] = -100
+    xo, xm = x.clone().requires_grad_(True), x.cuda().requires_grad_(True)
+    lo = F.cross_entropy(xo, t)
+    lo.backward()
+    lm = tb.LOSSES.get('CrossEntropyLoss')()(xm, t.cuda())
+    lm.backward()
+    assert abs(float(lm.detach()) - float(lo.detach())) / abs(float(lo.detach())) < 2e-3
+    assert rel_err(xm.grad, xo.grad) < 1e-2
+
+
+def _pair(name):
+    import torchok_b200 as tb
+    from oracle import models as om
+    torch.manual_seed(0)
+    o = om.hrnet(name)
+    om.dedegenerate_(o, 0)
+    m = tb.BACKBONES.get(name)(pretrained=False)
+    m.load_state_dict(o.state_dict())
+    return o, m.cuda()
+
+
+def test_hrnet_w18_small_forward_features_and_backward():
+    """Reference shape contract (test_backbone.py:76-88) + numeric parity of every branch + parameter gradients."""
+    from oracle import models as om
+    o, m = _pair('hrnet_w18_small')
+    o16 = copy.deepcopy(o)
+    x = torch.randn(4, 3, 64, 64)
+    o.train(), o16.train(), m.train()
+    with torch.no_grad():
+        fo = o.forward_features(x)
+        with om.amp_bf16():
+            fa = o16.forward_features(x)
+    fm = m.forward_features(x.cuda())
+    assert [tuple(f.shape) for f in fm] == [(4, 3, 64, 64), (4, 16, 16, 16), (4, 32, 8, 8), (4, 64, 4, 4), (4, 128, 2, 2)]
+    for i, (a, b, c) in enumerate(zip(fm[1:], fo[1:], fa[1:])):
+        e, e_amp = rel_err(a, b), rel_err(c, b)
+        print(f'hrnet_w18_small branch {i}: gpu-vs-fp32 {e:.4f} | oracle-amp-vs-fp32 {e_amp:.4f}')
+        assert e < 1.5 * e_amp + 5e-3, (i, e, e_amp)
+    # backward through everything
+    grads = {}
+    rs = None
+    for mode in ('amp', 'fp32'):
+        o.zero_grad()
+        with om.amp_bf16(mode == 'amp'):
+            ys = o(x)
+            rs = [torch.randn_like(y) for y in ys] if rs is None else rs
+            sum((y * r).sum() for y, r in zip(ys, rs)).backward()
+        grads[mode] = {k: p.grad.clone() for k, p in o.named_parameters()}
+    ym = m(x.cuda())
+    sum((y.float() * r.cuda()).sum() for y, r in zip(ym, rs)).backward()
+    worst = worst_amp = 0.0
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        e = rel_l2(p.grad, grads['fp32'][k])
+        e_amp = rel_l2(grads['amp'][k], grads['fp32'][k])
+        worst, worst_amp = max(worst, e), max(worst_amp, e_amp)
+        assert e < 1.5 * e_amp + 2e-2, (k, e, e_amp)
+    print(f'hrnet_w18_small backward: worst rel_l2 gpu-vs-fp32 {worst:.4f} | oracle-amp-vs-fp32 {worst_amp:.4f}')
+    so, sm = o.state_dict(), m.state_dict()
+    for k in so:
+        if 'num_batches_tracked' in k:
+            assert int(sm[k]) >= 1, k
+
+
+def test_hrnet_w18_necks_shapes_and_parity():
+    """test_hrnet.py:15-26 of the reference: cls neck (2, 2048, 7, 7), seg neck (2, 270, 56, 56) for hrnet_w18 @224."""
+    import torchok_b200 as tb
+    from oracle import models as om
+    o, m = _pair('hrnet_w18')
+    torch.manual_seed(1)
+    on_s, on_c = om.HRNetSegmentationNeck(o.out_encoder_channels), om.HRNetClassificationNeck(o.out_encoder_channels)
+    om.dedegenerate_(on_s, 1), om.dedegenerate_(on_c, 2)
+    pn_s = tb.NECKS.get('HRNetSegmentationNeck')(in_channels=m.out_encoder_channels)
+    pn_c = tb.NECKS.get('HRNetClassificationNeck')(in_channels=m.out_encoder_channels)
+    pn_s.load_state_dict(on_s.state_dict()), pn_c.load_state_dict(on_c.state_dict())
+    pn_s.cuda(), pn_c.cuda()
+    x = torch.rand(2, 3, 224, 224)
+    for mod in (o, on_s, on_c, m, pn_s, pn_c):
+        mod.eval()
+    with torch.no_grad():
+        fo = o.forward_features(x)
+        fm = m.forward_features(x.cuda())
+        img, seg = pn_s(fm)
+        cls = pn_c(fm[1:])
+        seg_o, cls_o = on_s(fo)[1], on_c(fo[1:])
+    assert tuple(seg.shape) == (2, 270, 56, 56) and tuple(img.shape) == (2, 3, 224, 224)
+    assert tuple(cls.shape) == (2, 2048, 7, 7)
+    print('seg neck', rel_err(seg, seg_o), 'cls neck', rel_err(cls, cls_o))
+    assert rel_err(seg, seg_o) < 3e-2 and rel_err(cls, cls_o) < 3e-2
+
+
+def test_segmentation_task_training_step():
+    """SegmentationTask(hrnet_w18_small + HRNetSegmentationNeck + SegmentationHead) + CrossEntropyLoss: loss parity
+    with the oracle in its bf16 mode, logits shape (B, classes, H, W) as tests/.../heads/test_segmentation.py."""
+    import torchok_b200 as tb
+    from oracle import models as om
+    cfg = tb.load_config({
+        'task': {'name': 'SegmentationTask', 'params': {
+            'backbone_name': 'hrnet_w18_small', 'backbone_params': {'pretrained': False, 'in_channels': 3},
+            'neck_name': 'HRNetSegmentationNeck', 'head_name': 'SegmentationHead', 'head_params': {'num_classes': 10}}},
+        'joint_loss': {'losses': [{'name': 'CrossEntropyLoss', 'mapping': {'input': 'prediction', 'target': 'target'}}]},
+    })
+    task = tb.TASKS.get('SegmentationTask')(cfg, **cfg.task.params)
+    torch.manual_seed(5)
+    ob = om.hrnet('hrnet_w18_small')
+    oracle = om.SegmentationTask(ob, om.HRNetSegmentationNeck(ob.out_encoder_channels),
+                                 om.SegmentationHead(sum(ob.out_encoder_channels), 10))
+    om.dedegenerate_(oracle, 5)
+    task.load_state_dict(oracle.state_dict(), strict=True)
+    task.cuda().train()
+    oracle.train()
+    x = torch.randn(4, 3, 64, 64)
+    y = torch.randint(0, 10, (4, 64, 64))
+    with om.amp_bf16():
+        po = oracle.forward_with_gt({'image': x, 'target': y})['prediction']
+        lo = F.cross_entropy(po, y)
+        lo.backward()
+    out = task.forward_with_gt({'image': x.cuda(), 'target': y.cuda()})
+    assert tuple(out['prediction'].shape) == (4, 10, 64, 64)
+    step = task.training_step({'image': x.cuda(), 'target': y.cuda()})
+    step['loss'].backward()
+    e_logits = rel_err(out['prediction'], po)
+    e_loss = abs(float(step['loss'].detach()) - float(lo.detach())) / abs(float(lo.detach()))
+    g, go = task.head.classifier.weight.grad, oracle.head.classifier.weight.grad
+    print(f'seg task: logits {e_logits:.4f} loss {e_loss:.4f} head-grad l2 {rel_l2(g, go):.4f}')
+    assert e_logits < 5e-2 and e_loss < 2e-2 and rel_l2(g, go) < 5e-2

@@ -50,3 +50,19 @@ def test_amp_mode_rounds_storage_only():
             b = o(x)
     rel = ((a - b).abs().max() / a.abs().max()).item()
     assert 0 < rel < 5e-2
+
+
+def test_oracle_hrnet_shape_contracts():
+    """Reference shape tests: hrnet_w18_small @64 (test_backbone.py:76-88), hrnet_w18 necks @224 (test_hrnet.py:15-26),
+    segmentation head -> (B, classes, H, W)."""
+    o = om.hrnet('hrnet_w18_small').eval()
+    with torch.no_grad():
+        feats = o.forward_features(torch.randn(2, 3, 64, 64))
+    assert [tuple(f.shape) for f in feats] == [(2, 3, 64, 64), (2, 16, 16, 16), (2, 32, 8, 8), (2, 64, 4, 4), (2, 128, 2, 2)]
+    neck = om.HRNetSegmentationNeck(o.out_encoder_channels).eval()
+    head = om.SegmentationHead(neck.out_channels, 10).eval()
+    with torch.no_grad():
+        assert tuple(head(neck(feats)).shape) == (2, 10, 64, 64)
+    cls = om.HRNetClassificationNeck(o.out_encoder_channels).eval()
+    with torch.no_grad():
+        assert tuple(cls(feats[1:]).shape) == (2, 2048, 2, 2)

@@ -626,5 +626,140 @@ def contrastive_rows(emb1, emb2, R, margin):
     return ContrastiveFn.apply(emb1, emb2, R, margin)
 
 
+class SoftmaxXentNHWCFn(torch.autograd.Function):
+    """torch.nn.CrossEntropyLoss(reduction='mean', ignore_index) on (B, C, H, W) logits with (B, H, W) targets
+    (segmentation, torchok/losses/__init__.py:26): NHWC rows of C <= 64 classes, one thread per pixel."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        lg = to_nhwc(logits)
+        n, c, h, w = lg.shape
+        cp = nhwc_pitch(lg)
+        rows = n * h * w
+        target = target.long().contiguous()
+        if target.numel() != rows:
+            raise ValueError(f'CrossEntropyLoss: target shape {tuple(target.shape)} does not match logits {tuple(lg.shape)}')
+        acc = torch.zeros((2,), dtype=F32, device=lg.device)
+        lib().tok_softmax_xent_small(rows, c, cp, _p(lg), _p(target), _p(acc[0:1]), _p(acc[1:2]), None, None, 1.0,
+                                     None, ignore_index, _st())
+        inv = 1.0 / acc[1].clamp_min(1.0)
+        ctx.save_for_backward(lg, target, inv.reshape(1))
+        ctx.meta = (n, c, h, w, cp, ignore_index)
+        return acc[0] * inv
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, target, inv = ctx.saved_tensors
+        n, c, h, w, cp, ignore_index = ctx.meta
+        d = torch.empty((n, h, w, cp), dtype=BF16, device=lg.device)
+        g = g.to(F32).contiguous()
+        lib().tok_softmax_xent_small(n * h * w, c, cp, _p(lg), _p(target), None, None, _p(d), _p(inv), 1.0, _p(g),
+                                     ignore_index, _st())
+        d = d.permute(0, 3, 1, 2)
+        return (d if cp == c else d[:, :c]), None, None
+
+
 def softmax_xent_nhwc(logits, target, ignore_index=-100):
-    raise NotImplementedError('softmax_xent_nhwc kernel not built yet')
+    if logits.shape[1] > 64:
+        raise NotImplementedError('CrossEntropyLoss on 4-D logits supports up to 64 classes')
+    return SoftmaxXentNHWCFn.apply(logits, target, ignore_index)
+
+
+# ------------------------------------------------------------------------------------------------------ HRNet / seg
+class FuseSumFn(torch.autograd.Function):
+    """y = relu(sum_t nearest_upsample(term_t)) — the fuse step of timm's HighResolutionModule.forward
+    (torchok/models/backbones/hrnet.py:167-192).  terms[0] defines the output resolution; term t may be 2^s smaller."""
+
+    @staticmethod
+    def forward(ctx, relu, *terms):
+        import ctypes as C2
+        terms = [to_nhwc(t) for t in terms]
+        n, c, h, w = terms[0].shape
+        cp = nhwc_pitch(terms[0])
+        shifts = []
+        for t in terms:
+            if nhwc_pitch(t) != cp or t.shape[1] != c:
+                raise ValueError('fuse_sum: all terms must have the same channel count')
+            f = h // t.shape[2]
+            if f < 1 or f & (f - 1) or t.shape[2] * f != h or t.shape[3] * f != w:
+                raise ValueError(f'fuse_sum: term of size {tuple(t.shape)} is not a power-of-two reduction of {h}x{w}')
+            shifts.append(f.bit_length() - 1)
+        out = torch.empty((n, h, w, cp), dtype=BF16, device=terms[0].device)
+        bits = torch.empty((n * h * w * cp // 8,), dtype=torch.uint8, device=out.device) if relu else None
+        ptrs = (C2.c_void_p * len(terms))(*[t.data_ptr() for t in terms])
+        sh = (C2.c_int * len(terms))(*shifts)
+        lib().tok_fuse_sum_fwd(n, h, w, cp, len(terms), ptrs, sh, int(relu), _p(out), _p(bits), _st())
+        ctx.meta = (n, c, h, w, cp, shifts)
+        ctx.save_for_backward(bits) if relu else None
+        ctx.relu = relu
+        o = out.permute(0, 3, 1, 2)
+        return o if cp == c else o[:, :c]
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w, cp, shifts = ctx.meta
+        bits = ctx.saved_tensors[0] if ctx.relu else None
+        g = _dense_grad(g, cp)
+        grads = []
+        for i, s in enumerate(shifts):
+            if not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            d = torch.empty((n, h >> s, w >> s, cp), dtype=BF16, device=g.device)
+            lib().tok_fuse_sum_bwd(n, h, w, cp, s, _p(g), _p(bits), _p(d), _st())
+            d = d.permute(0, 3, 1, 2)
+            grads.append(d if cp == c else d[:, :c])
+        return (None,) + tuple(grads)
+
+
+def fuse_sum(terms, relu=True):
+    return FuseSumFn.apply(relu, *terms)
+
+
+class BilinearCatFn(torch.autograd.Function):
+    """cat([interpolate(x_k, size, 'bilinear', align_corners=False) for k], dim=1) in one padded NHWC buffer:
+    segment k occupies ceil8(C_k) channels (necks/segmentation/hrnet.py:35-40).  With a single input and the same
+    channel count it is plain F.interpolate (heads/segmentation/base.py:37)."""
+
+    @staticmethod
+    def forward(ctx, size, *xs):
+        xs = [to_nhwc(x) for x in xs]
+        n = xs[0].shape[0]
+        ho, wo = size
+        pitches = [nhwc_pitch(x) for x in xs]
+        total = sum(pitches)
+        out = torch.empty((n, ho, wo, total), dtype=BF16, device=xs[0].device)
+        off = 0
+        for x, cp in zip(xs, pitches):
+            lib().tok_bilinear_fwd(n, x.shape[2], x.shape[3], cp, ho, wo, _p(x), _p(out), total, off, _st())
+            off += cp
+        ctx.meta = (n, ho, wo, total, [(x.shape[1], x.shape[2], x.shape[3], cp) for x, cp in zip(xs, pitches)])
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        n, ho, wo, total, shapes = ctx.meta
+        g = _dense_grad(g, total)
+        grads, off = [], 0
+        for i, (c, h, w, cp) in enumerate(shapes):
+            if ctx.needs_input_grad[1 + i]:
+                d = torch.empty((n, h, w, cp), dtype=BF16, device=g.device)
+                lib().tok_bilinear_bwd(n, h, w, cp, ho, wo, _p(g), total, off, _p(d), _st())
+                d = d.permute(0, 3, 1, 2)
+                grads.append(d if cp == c else d[:, :c])
+            else:
+                grads.append(None)
+            off += cp
+        return (None,) + tuple(grads)
+
+
+def bilinear_cat(xs, size):
+    """Returns the (N, sum ceil8(C_k), H, W) padded concat; the consumer conv maps its input channels with
+    Conv2d.set_input_layout([C_k...])."""
+    return BilinearCatFn.apply(tuple(size), *xs)
+
+
+def bilinear_resize(x, size):
+    c = x.shape[1]
+    out = BilinearCatFn.apply(tuple(size), x)
+    return out if out.shape[1] == c else out[:, :c]

@@ -1,1 +1,2 @@
 from . import resnet  # noqa: F401
+from . import hrnet  # noqa: F401

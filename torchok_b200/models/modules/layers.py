@@ -44,6 +44,19 @@ class Conv2d(nn.Conv2d):
         self.cin_p, self.cout_p = K.ceil8(in_channels), K.ceil8(out_channels)
         self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
         self._descs = {}
+        self.tok_in_map = None  # optional LongTensor: padded position of every input channel (see set_input_layout)
+
+    def set_input_layout(self, segments):
+        """The input arrives as a concatenation of channel segments, each padded to a multiple of 8 (the HRNet
+        segmentation neck's torch.cat, necks/segmentation/hrnet.py:40): map logical input channels to padded slots."""
+        pos, off = [], 0
+        for c in segments:
+            pos.extend(range(off, off + c))
+            off += K.ceil8(c)
+        assert len(pos) == self.in_channels
+        self.tok_in_map = torch.tensor(pos, dtype=torch.long)
+        self.cin_p = off
+        self._descs = {}
 
     def desc(self, x):
         n, _, h, w = x.shape
@@ -57,7 +70,14 @@ class Conv2d(nn.Conv2d):
 
     @property
     def padded(self):
-        return self.cin_p != self.in_channels or self.cout_p != self.out_channels
+        return self.cin_p != self.in_channels or self.cout_p != self.out_channels or self.tok_in_map is not None
+
+    def _in_index(self, device):
+        if self.tok_in_map is None:
+            return slice(0, self.in_channels)
+        if self.tok_in_map.device != device:
+            self.tok_in_map = self.tok_in_map.to(device)
+        return self.tok_in_map
 
     def shadow(self):
         """bf16 [Kp][R][S][Cp] weights for the kernels."""
@@ -71,7 +91,7 @@ class Conv2d(nn.Conv2d):
         r, s = self.kernel_size
         full = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=BF16, device=w.device)
         tmp = K.cast_bf16(w.detach())
-        full[:self.out_channels, :, :, :self.in_channels] = tmp.permute(0, 2, 3, 1)
+        full[:self.out_channels, :, :, self._in_index(w.device)] = tmp.permute(0, 2, 3, 1)
         return full
 
     def wgrad_target(self):
@@ -85,7 +105,7 @@ class Conv2d(nn.Conv2d):
         tmp = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=F32, device=g.device)
 
         def finish():
-            g.add_(tmp[:self.out_channels, :, :, :self.in_channels].permute(0, 3, 1, 2))
+            g.add_(tmp[:self.out_channels, :, :, self._in_index(g.device)].permute(0, 3, 1, 2))
         return tmp, finish
 
     def forward(self, x):
@@ -107,16 +127,34 @@ class BatchNorm2d(nn.BatchNorm2d):
         self._pending_batches = 0
         self._register_state_dict_hook(_flush_batches)
 
-    def state(self):
+    def state(self, count_batch=True):
+        """BNState for the fused unit.  When the channel count is not a multiple of 8 (HRNet's 18 / 36-channel
+        branches) the kernels see zero-padded copies of weight / bias / running stats (pad lanes: gamma = beta = 0, so
+        they stay exactly zero); `commit()` copies the updated running statistics back."""
         if self._tok_acc.dtype != F32:
             self._tok_acc = self._tok_acc.float()
-        if self.cp != self.num_features:
-            raise NotImplementedError('BatchNorm2d with a channel count that is not a multiple of 8 goes through '
-                                      'PaddedBatchNorm state (see state_padded)')
-        if self.training:
+        if self.training and count_batch:
             self._pending_batches += 1
-        return K.BNState(self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
-                         self.training, self._tok_acc, self.cp)
+        if self.cp == self.num_features:
+            return K.BNState(self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+                             self.training, self._tok_acc, self.cp)
+        c, dev = self.num_features, self.weight.device
+        pad = torch.zeros((4, self.cp), dtype=F32, device=dev)
+        pad[3].fill_(1.0)
+        pad[0, :c] = self.weight.detach()
+        pad[1, :c] = self.bias.detach()
+        pad[2, :c] = self.running_mean
+        pad[3, :c] = self.running_var
+        self._tok_pad = pad
+        return K.BNState(pad[0], pad[1], pad[2], pad[3], self.eps, self.momentum, self.training, self._tok_acc,
+                         self.cp)
+
+    def commit(self):
+        """Copy running statistics updated on padded temporaries back into the real buffers."""
+        if self.cp != self.num_features and self.training and getattr(self, '_tok_pad', None) is not None:
+            c = self.num_features
+            self.running_mean.copy_(self._tok_pad[2, :c])
+            self.running_var.copy_(self._tok_pad[3, :c])
 
     def forward(self, x):
         raise NotImplementedError('torchok_b200.BatchNorm2d is executed fused with its producer conv '
@@ -139,15 +177,29 @@ def _bn_grads(bn):
 
 def _unit_fwd(x, conv, bn, relu, residual, keep):
     d, pq = conv.desc(x)
-    return K.unit_forward(x, d, pq, conv.shadow(), bn.state(), relu, residual, keep), d
+    res = K.unit_forward(x, d, pq, conv.shadow(), bn.state(), relu, residual, keep)
+    bn.commit()
+    return res, d
 
 
 def _unit_bwd(saved, d, conv, bn, dout, **kw):
     wbuf, finish = conv.wgrad_target()
     gw, gb = _bn_grads(bn)
-    st = K.BNState(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, bn.training,
-                   bn._tok_acc, bn.cp)
-    out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb, **kw)
+    padded = bn.cp != bn.num_features
+    if padded:
+        st = bn.state(count_batch=False)
+        tmp = torch.zeros((2, bn.cp), dtype=F32, device=dout.device)
+        out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf,
+                              dgamma=tmp[0] if gw is not None else None, dbeta=tmp[1] if gb is not None else None, **kw)
+        c = bn.num_features
+        if gw is not None:
+            gw.add_(tmp[0, :c])
+        if gb is not None:
+            gb.add_(tmp[1, :c])
+    else:
+        st = K.BNState(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, bn.training,
+                       bn._tok_acc, bn.cp)
+        out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb, **kw)
     if finish:
         finish()
     K.grad_ready(conv.weight)
@@ -176,7 +228,7 @@ class ConvBnActFn(torch.autograd.Function):
             ctx.mods = (conv, bn, d, residual is not None)
             ctx.has_bits, ctx.mode = saved[2] is not None, saved[4]
             ctx.save_for_backward(*[t for t in saved[:4] if t is not None])
-        return out
+        return out if conv.cout_p == conv.out_channels else out[:, :conv.out_channels]
 
     @staticmethod
     def backward(ctx, dout):
@@ -185,6 +237,10 @@ class ConvBnActFn(torch.autograd.Function):
         saved = (t[0], t[1], t[2] if ctx.has_bits else None, t[-1], ctx.mode)
         dout = K._dense_grad(dout, d.k)
         dx, dres = _unit_bwd(saved, d, conv, bn, dout, need_dx=ctx.needs_input_grad[0], want_dres=has_res)
+        if dx is not None and conv.cin_p != conv.in_channels and conv.tok_in_map is None:
+            dx = dx[:, :conv.in_channels]
+        if dres is not None and conv.cout_p != conv.out_channels:
+            dres = dres[:, :conv.out_channels]
         return (dx, dres, None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 6)
 
 
@@ -279,7 +335,9 @@ class ResidualBlockFn(torch.autograd.Function):
                 flat.extend(t for t in sv[:4] if t is not None)
             ctx.save_for_backward(*flat)
             ctx.layout, ctx.descs, ctx.block = layout, descs, block
-        return out
+            ctx.cin = x.shape[1]
+        cout = units[-1][0].out_channels
+        return out if out.shape[1] == cout else out[:, :cout]
 
     @staticmethod
     def backward(ctx, dout):
@@ -310,6 +368,8 @@ class ResidualBlockFn(torch.autograd.Function):
         dx, _ = _unit_bwd(saved_all[off], descs[off], conv, bn, dh, need_dx=need_dx, dx_addend=addend)
         if compact is not None and dx is not None:
             K.strided_add(dx, compact, descs[0].stride)
+        if dx is not None and dx.shape[1] != ctx.cin:
+            dx = dx[:, :ctx.cin]
         return (dx, None, None) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 

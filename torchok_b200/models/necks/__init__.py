@@ -1,0 +1,1 @@
+from . import hrnet  # noqa: F401
