@@ -180,6 +180,11 @@ def time_dominant_kernel(batch, sustained_tf):
             'ms_per_launch': ms, 'flop_per_launch': flops}
 
 
+def _trace(msg):
+    if os.environ.get('TOK_BENCH_TRACE'):
+        print(f'[bench rank {os.environ.get("RANK", "0")} {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -190,6 +195,7 @@ def run_ours(args):
         os.environ.setdefault('NCCL_IB_DISABLE', '1')      # NVLink only (north_star)
         os.environ.setdefault('NCCL_P2P_LEVEL', 'NVL')
         dist.init_process_group('nccl', device_id=dev)
+        _trace('process group up')
     import torchok_b200 as tb
     from torchok_b200._lib import lib
     from torchok_b200.engine import StreamLoop
@@ -198,6 +204,7 @@ def run_ours(args):
     cfg = tb.load_config(task_config(args.model))
     task = tb.TASKS.get(cfg.task.name)(cfg, **cfg.task.params).to(dev)
     loop = StreamLoop(task, use_graph=not args.no_graph)
+    _trace('StreamLoop built')
     B = args.batch
     if args.profile_step:
         loop.use_graph = False
@@ -224,6 +231,7 @@ def run_ours(args):
     # launches per step, counted on the eager warm-up inside the first train_step
     n0 = lib().launches
     loop.train_step(dev_batch)
+    _trace('first train_step (warm-up + capture) done')
     per_step = (lib().launches - n0) // (loop.warmup + (1 if loop.use_graph else 0)) if loop.use_graph else \
         (lib().launches - n0)
     for _ in range(max(args.warmup, 3) - 1):
@@ -243,6 +251,7 @@ def run_ours(args):
     e1.record(st)
     barrier()
     ms_total = e0.elapsed_time(e1)
+    _trace(f'timed region done: {ms_total / args.steps:.2f} ms/step')
     clocks = sampler.stop() if sampler else None
     loss_val = float(loss)
 
@@ -279,6 +288,7 @@ def run_ours(args):
     e3.record(st)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    _trace('e2e region done')
     assert bool(torch.isfinite(loss_host).all()), 'non-finite loss in the e2e run'
 
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)

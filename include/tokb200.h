@@ -148,6 +148,29 @@ int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const lo
                      void* dlogits, float inv_norm, float gscale, const float* gscale_dev, long long ignore_index,
                      int* correct, void* stream);
 
+/* ---- Swin-V2 passes (tok_swin.cu; timm swin_transformer_v2 semantics used by torchok/models/backbones/swin.py:71-81) ------
+ * LayerNorm over the last dimension of a (rows, C) bf16 matrix, C <= 1024; with `residual` the output is
+ * residual + rowscale[row / rows_per_sample] * LN(x) (res-post-norm block tail with stochastic depth; rowscale nullable).
+ * Backward: dx for the LN input (the residual gradient is dout itself); dgamma / dbeta are atomically ACCUMULATED. */
+int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, const float* beta, float eps,
+                      const void* residual, const float* rowscale, int rows_per_sample, void* out, float* mean,
+                      float* rstd, void* stream);
+int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, const float* mean, const float* rstd,
+                      const void* dout, const float* rowscale, int rows_per_sample, void* dx, float* dgamma,
+                      float* dbeta, void* stream);
+/* exact (erf) GELU of timm's Mlp */
+int tok_gelu_fwd(long long n, const void* x, void* y, void* stream);
+int tok_gelu_bwd(long long n, const void* x, const void* dy, void* dx, void* stream);
+/* WindowAttention.forward on the (B, H, W, 3C) qkv tensor ([3][heads][32] per token): cosine attention with
+ * exp(min(logit_scale, ln 100)), additive bias[heads][N][N], shifted-window mask (-100) computed from `shift`; windows are
+ * gathered from / scattered to their home positions (no roll / partition copies).  window <= 8, head_dim == 32.
+ * Backward recomputes the probabilities; dbias / dlogit_scale are atomically ACCUMULATED. */
+int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift, const void* qkv,
+                        const float* logit_scale, const float* bias, void* out, void* stream);
+int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift, const void* qkv,
+                        const float* logit_scale, const float* bias, const void* dout, void* dqkv, float* dbias,
+                        float* dlogit_scale, void* stream);
+
 /* ---- HRNet / segmentation passes (tok_seg.cu) ---------------------------------------------------------------------------
  * timm HighResolutionModule fuse (torchok/models/backbones/hrnet.py:167-192): out = relu(sum_t nearest_up(term_t)), term t
  * at resolution (h >> shifts[t], w >> shifts[t]); bits (nullable) = ReLU mask, 1 bit/element.  Backward per term. */

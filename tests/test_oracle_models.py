@@ -66,3 +66,54 @@ def test_oracle_hrnet_shape_contracts():
     cls = om.HRNetClassificationNeck(o.out_encoder_channels).eval()
     with torch.no_grad():
         assert tuple(cls(feats[1:]).shape) == (2, 2048, 2, 2)
+
+
+def test_oracle_swinv2_block_matches_torchvision():
+    """Independent cross-check of the Swin-V2 restatement (oracle/swin.py) against torchvision's
+    SwinTransformerBlockV2 (same Microsoft lineage, different code): shifted and unshifted blocks, 8x8 grid, window 4."""
+    from torchvision.models.swin_transformer import PatchMergingV2, SwinTransformerBlockV2
+
+    from oracle import swin as osw
+    torch.manual_seed(0)
+    for shift in (0, 2):
+        o = osw.SwinTransformerBlock(64, (8, 8), 2, window_size=4, shift_size=shift)
+        osw.dedegenerate_ln_(o, 1)
+        tv = SwinTransformerBlockV2(64, 2, [4, 4], [shift, shift], mlp_ratio=4.0, stochastic_depth_prob=0.0)
+        sd = o.state_dict()
+        with torch.no_grad():
+            tv.norm1.load_state_dict({'weight': sd['norm1.weight'], 'bias': sd['norm1.bias']})
+            tv.norm2.load_state_dict({'weight': sd['norm2.weight'], 'bias': sd['norm2.bias']})
+            tv.attn.qkv.weight.copy_(sd['attn.qkv.weight'])
+            tv.attn.qkv.bias.copy_(torch.cat([sd['attn.q_bias'], torch.zeros(64), sd['attn.v_bias']]))
+            tv.attn.proj.weight.copy_(sd['attn.proj.weight'])
+            tv.attn.proj.bias.copy_(sd['attn.proj.bias'])
+            tv.attn.logit_scale.copy_(sd['attn.logit_scale'])
+            tv.attn.cpb_mlp[0].weight.copy_(sd['attn.cpb_mlp.0.weight'])
+            tv.attn.cpb_mlp[0].bias.copy_(sd['attn.cpb_mlp.0.bias'])
+            tv.attn.cpb_mlp[2].weight.copy_(sd['attn.cpb_mlp.2.weight'])
+            tv.mlp[0].weight.copy_(sd['mlp.fc1.weight'])
+            tv.mlp[0].bias.copy_(sd['mlp.fc1.bias'])
+            tv.mlp[3].weight.copy_(sd['mlp.fc2.weight'])
+            tv.mlp[3].bias.copy_(sd['mlp.fc2.bias'])
+        x = torch.randn(2, 8, 8, 64)
+        o.eval(), tv.eval()
+        with torch.no_grad():
+            a = o(x.view(2, 64, 64)).view(2, 8, 8, 64)
+            b = tv(x)
+        assert torch.allclose(a, b, atol=2e-5, rtol=1e-4), (shift, (a - b).abs().max())
+    pm = osw.PatchMerging((8, 8), 64)
+    tvm = PatchMergingV2(64)
+    with torch.no_grad():
+        tvm.reduction.weight.copy_(pm.reduction.weight)
+        tvm.norm.weight.copy_(pm.norm.weight)
+        tvm.norm.bias.copy_(pm.norm.bias)
+        x = torch.randn(2, 8, 8, 64)
+        assert torch.allclose(pm(x.view(2, 64, 64)).view(2, 4, 4, 128), tvm(x), atol=1e-5)
+
+
+def test_oracle_swinv2_shape_contract():
+    from oracle import swin as osw
+    o = osw.SwinTransformerV2(img_size=64, window_size=8, depths=(1, 1, 1, 1)).eval()
+    with torch.no_grad():
+        feats = o.forward_features(torch.randn(2, 3, 64, 64))
+    assert [tuple(f.shape) for f in feats] == [(2, 3, 64, 64), (2, 96, 16, 16), (2, 192, 8, 8), (2, 384, 4, 4), (2, 768, 2, 2)]

@@ -1,0 +1,152 @@
+"""GPU parity of the Swin-V2 path against oracle/swin.py (itself cross-checked against
+torchvision's SwinTransformerBlockV2).  Tolerance 1e-2 of the tensor maximum for bf16 tensors (north_star), with the
+whole-network bar "GPU error vs fp32 oracle <= 1.5 x oracle-bf16-AMP error + 5e-3" used for the other backbones."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize('rows,c,res', [(64, 96, False), (50, 768, True), (33, 200, True)])
+def test_layernorm_residual(rows, c, res):
+    from torchok_b200 import kernels as K
+    torch.manual_seed(c)
+    x, r = _bf(torch.randn(rows, c) * 2 + 0.5), _bf(torch.randn(rows, c))
+    w, b = torch.rand(c) + 0.5, torch.randn(c) * 0.1
+    xo, ro, wo, bo = (t.clone().requires_grad_(True) for t in (x, r, w, b))
+    y = F.layer_norm(xo, (c,), wo, bo)
+    if res:
+        y = ro + y
+    g = _bf(torch.randn_like(y))
+    (y * g).sum().backward()
+    xm, rm = x.cuda().requires_grad_(True), r.cuda().requires_grad_(True)
+    wm, bm = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    ym = K.layernorm(xm.to(torch.bfloat16), wm, bm, 1e-5, rm.to(torch.bfloat16) if res else None)
+    (ym.float() * g.cuda()).sum().backward()
+    assert rel_err(ym, y) < 1e-2
+    assert rel_err(xm.grad, xo.grad) < 1e-2
+    assert rel_err(wm.grad, wo.grad) < 1e-2 and rel_err(bm.grad, bo.grad) < 1e-2
+    if res:
+        assert rel_err(rm.grad, ro.grad) < 1e-2
+
+
+def test_gelu():
+    from torchok_b200 import kernels as K
+    x = _bf(torch.randn(128, 96) * 2)
+    xo, xm = x.clone().requires_grad_(True), x.cuda().requires_grad_(True)
+    g = _bf(torch.randn_like(x))
+    (F.gelu(xo) * g).sum().backward()
+    ym = K.gelu(xm.to(torch.bfloat16))
+    (ym.float() * g.cuda()).sum().backward()
+    assert rel_err(ym, F.gelu(x)) < 1e-2 and rel_err(xm.grad, xo.grad) < 1e-2
+
+
+@pytest.mark.parametrize('dim,heads,res,ws,shift', [(96, 3, 8, 4, 0), (96, 3, 8, 4, 2), (64, 2, 14, 7, 3), (192, 6, 8, 8, 0),
+                                                    (128, 4, 16, 8, 4)])
+def test_swin_block_forward_backward(dim, heads, res, ws, shift):
+    """timm SwinTransformerBlock: attention (bias, logit scale, shift mask), res-post-norm, MLP — every gradient."""
+    from oracle import swin as osw
+    from torchok_b200.models.backbones import swin as psw
+    torch.manual_seed(dim + res + shift)
+    o = osw.SwinTransformerBlock(dim, (res, res), heads, window_size=ws, shift_size=shift)
+    osw.dedegenerate_ln_(o, 2)
+    with torch.no_grad():
+        for n_, p in o.named_parameters():
+            if p.dim() == 2 and 'cpb' not in n_:
+                p.copy_(_bf(p * 5))   # weights with visible magnitude, bf16-representable
+    m = psw.SwinTransformerBlock(dim, (res, res), heads, window_size=ws, shift_size=shift)
+    m.load_state_dict(o.state_dict())
+    m.cuda().train()
+    o.train()
+    b = 3
+    x = _bf(torch.randn(b, res * res, dim))
+    xo = x.clone().requires_grad_(True)
+    xm = x.cuda().requires_grad_(True)
+    yo = o(xo)
+    g = _bf(torch.randn_like(yo))
+    (yo * g).sum().backward()
+    ym = m(xm.view(-1, dim).to(torch.bfloat16), b)
+    (ym.float().view(b, -1, dim) * g.cuda()).sum().backward()
+    assert rel_err(ym.view(b, -1, dim), yo) < 1e-2
+    assert rel_err(xm.grad, xo.grad) < 2e-2
+    po = dict(o.named_parameters())
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        e = rel_l2(p.grad, po[k].grad)
+        assert e < 3e-2, (k, e)
+
+
+def test_swinv2_network_forward_features_and_backward():
+    import torchok_b200 as tb
+    from oracle import models as om
+    from oracle import swin as osw
+    torch.manual_seed(0)
+    kw = dict(img_size=64, window_size=8, depths=(2, 2, 2, 2))
+    o = osw.SwinTransformerV2(**kw)
+    osw.dedegenerate_ln_(o, 0)
+    m = tb.BACKBONES.get('swinv2_custom')(pretrained=False, drop_path_rate=0.0, **kw)
+    m.load_state_dict(o.state_dict())
+    m.cuda().train()
+    o16 = copy.deepcopy(o)
+    x = torch.randn(4, 3, 64, 64)
+    with torch.no_grad():
+        fo = o.forward_features(x)
+        with om.amp_bf16():
+            fa = o16.forward_features(x)
+    fm = m.forward_features(x.cuda())
+    assert [tuple(f.shape) for f in fm] == [(4, 3, 64, 64), (4, 96, 16, 16), (4, 192, 8, 8), (4, 384, 4, 4), (4, 768, 2, 2)]
+    for i, (a, b_, c) in enumerate(zip(fm[1:], fo[1:], fa[1:])):
+        e, e_amp = rel_err(a, b_), rel_err(c, b_)
+        print(f'swinv2 stage {i}: gpu-vs-fp32 {e:.4f} | oracle-amp-vs-fp32 {e_amp:.4f}')
+        assert e < 1.5 * e_amp + 5e-3, (i, e, e_amp)
+    grads = {}
+    r = None
+    for mode in ('amp', 'fp32'):
+        o.zero_grad()
+        with om.amp_bf16(mode == 'amp'):
+            y = o(x)
+            r = torch.randn_like(y) if r is None else r
+            (y * r).sum().backward()
+        grads[mode] = {k: p.grad.clone() for k, p in o.named_parameters() if p.grad is not None}
+    ym = m(x.cuda())
+    assert tuple(ym.shape) == (4, 768, 2, 2)
+    (ym.float() * r.cuda()).sum().backward()
+    worst = worst_amp = 0.0
+    for k, p in m.named_parameters():
+        if k not in grads['fp32']:
+            continue
+        assert p.grad is not None, k
+        e = rel_l2(p.grad, grads['fp32'][k])
+        e_amp = rel_l2(grads['amp'][k], grads['fp32'][k])
+        worst, worst_amp = max(worst, e), max(worst_amp, e_amp)
+        assert e < 1.5 * e_amp + 2e-2, (k, e, e_amp)
+    print(f'swinv2 backward: worst rel_l2 gpu-vs-fp32 {worst:.4f} | oracle-amp-vs-fp32 {worst_amp:.4f}')
+
+
+def test_swin_classification_task_step():
+    """BASELINE config 3 in miniature: ClassificationTask(swinv2_custom) + Pooling + ClassificationHead + CE."""
+    import torchok_b200 as tb
+    cfg = tb.load_config({
+        'task': {'name': 'ClassificationTask', 'params': {
+            'backbone_name': 'swinv2_custom',
+            'backbone_params': {'pretrained': False, 'img_size': 64, 'window_size': 8, 'depths': (1, 1, 1, 1)},
+            'pooling_name': 'Pooling', 'head_name': 'ClassificationHead', 'head_params': {'num_classes': 10}}},
+        'joint_loss': {'losses': [{'name': 'CrossEntropyLoss', 'mapping': {'input': 'prediction', 'target': 'target'}}]},
+    })
+    task = tb.TASKS.get('ClassificationTask')(cfg, **cfg.task.params).cuda().train()
+    out = task.training_step({'image': torch.randn(8, 3, 64, 64).cuda(), 'target': torch.randint(0, 10, (8,)).cuda()})
+    out['loss'].backward()
+    assert torch.isfinite(out['loss'])
+    # feature_norms 0-2 only serve forward_features (swin.py:240-249 of the reference); everything else must train
+    missing = [n for n, p in task.named_parameters() if p.grad is None and 'feature_norms' not in n]
+    assert not missing, missing
+    assert task.backbone.feature_norms[3].weight.grad is not None

@@ -68,6 +68,12 @@ _SIGS = {
     'tok_gap_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_gap_bwd': (_i, [_i, _i, _i, _vp, _vp, _vp]),
     'tok_softmax_xent': (_i, [_i, _i, _ll, _vp, _vp, _vp, _vp, _f, _f, _vp, _ll, _vp, _vp]),
+    'tok_layernorm_fwd': (_i, [_ll, _i, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    'tok_layernorm_bwd': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    'tok_gelu_fwd': (_i, [_ll, _vp, _vp, _vp]),
+    'tok_gelu_bwd': (_i, [_ll, _vp, _vp, _vp, _vp]),
+    'tok_window_attn_fwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'tok_window_attn_bwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_fuse_sum_fwd': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     'tok_fuse_sum_bwd': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_bilinear_fwd': (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),

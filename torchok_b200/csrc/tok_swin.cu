@@ -1,0 +1,529 @@
+// tok_swin.cu — Swin-V2 passes around the tcgen05 linear layers: LayerNorm (with the res-post-norm residual add), GELU,
+// and shifted-window cosine attention.
+//
+// Reference call sites (timm 0.6.13 swin_transformer_v2, used through torchok/models/backbones/swin.py:71-81,127,156-171;
+// semantics restated in SURVEY Appendix A.3):
+//   SwinTransformerBlock.forward: x = x + drop_path(norm1(attn(x))); x = x + drop_path(norm2(mlp(x)))   -> layernorm_*
+//   Mlp: fc1 -> GELU(erf) -> fc2                                                                          -> gelu_*
+//   WindowAttention.forward: softmax(normalize(q) normalize(k)^T * exp(min(logit_scale, ln 100)) + 16 sigmoid(cpb) +
+//     mask) v, on windows cut from the (cyclically shifted) token grid                                   -> window_attn_*
+// The roll / window_partition / window_reverse copies of the reference are index arithmetic here: a window's tokens are
+// gathered from and scattered to their home positions in the (B, H, W, 3C) qkv tensor.
+//
+// Round-1 note: the attention kernel is a CUDA-core kernel (one thread per query row, window <= 8x8); the tcgen05 version
+// named by the north star is the next step for this path.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/tokb200.h"
+#include "tok_internal.h"
+#include "tok_ptx.cuh"
+
+namespace tok {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- LayerNorm -----------------------------------------------------------------------------------------------------
+// y = LN(x) * gamma + beta ; out = (res ? res + rowscale[b] * y : y).  One warp per row, C <= 1024 (x kept in registers).
+constexpr int kLnMaxPerLane = 32;  // C <= 1024
+
+__global__ void __launch_bounds__(128)
+layernorm_fwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ res,
+                     const float* __restrict__ rowscale, int rows_per_sample, __nv_bfloat16* __restrict__ out,
+                     float* __restrict__ mean, float* __restrict__ rstd) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float v[kLnMaxPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < C ? __bfloat162float(x[r * C + c]) : 0.f;
+    s += v[i];
+  }
+  const float mu = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + i * 32;
+    const float d = c < C ? v[i] - mu : 0.f;
+    q = fmaf(d, d, q);
+  }
+  const float rs = rsqrtf(warp_sum(q) / C + eps);
+  const float sc = rowscale ? rowscale[r / rows_per_sample] : 1.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      float y = (v[i] - mu) * rs * gamma[c] + beta[c];
+      if (res) y = __bfloat162float(res[r * C + c]) + sc * y;
+      out[r * C + c] = __float2bfloat16(y);
+    }
+  }
+  if (lane == 0) {
+    mean[r] = mu;
+    rstd[r] = rs;
+  }
+}
+
+// dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)) with g = rowscale * dout (dres = dout passes through
+// unchanged on the Python side); dgamma += sum g*xhat, dbeta += sum g (per-CTA partials in shared memory, then atomics).
+__global__ void __launch_bounds__(128)
+layernorm_bwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const __nv_bfloat16* __restrict__ dout, const float* __restrict__ rowscale, int rows_per_sample,
+                     __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     int rows_per_cta) {
+  extern __shared__ float sh[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[kLnMaxPerLane], ab[kLnMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) ag[i] = ab[i] = 0.f;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > rows) r1 = rows;
+  for (long long r = r0 + warp; r < r1; r += 4) {
+    const float mu = mean[r], rs = rstd[r];
+    const float sc = rowscale ? rowscale[r / rows_per_sample] : 1.f;
+    float xh[kLnMaxPerLane], gg[kLnMaxPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) {
+        xh[i] = (__bfloat162float(x[r * C + c]) - mu) * rs;
+        const float g = sc * __bfloat162float(dout[r * C + c]);
+        ag[i] = fmaf(g, xh[i], ag[i]);
+        ab[i] += g;
+        gg[i] = g * gamma[c];
+        s1 += gg[i];
+        s2 = fmaf(gg[i], xh[i], s2);
+      } else {
+        xh[i] = gg[i] = 0.f;
+      }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) dx[r * C + c] = __float2bfloat16(rs * (gg[i] - s1 - xh[i] * s2));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      atomicAdd(&sh[c], ag[i]);
+      atomicAdd(&sh[C + c], ab[i]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + c, sh[c]);
+    if (dbeta) atomicAdd(dbeta + c, sh[C + c]);
+  }
+}
+
+// ---- GELU (exact, erf) ---------------------------------------------------------------------------------------------
+__global__ void gelu_fwd_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloat162* __restrict__ y, long long n2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const float2 v = __bfloat1622float2(x[i]);
+    y[i] = __floats2bfloat162_rn(0.5f * v.x * (1.f + erff(v.x * 0.70710678f)), 0.5f * v.y * (1.f + erff(v.y * 0.70710678f)));
+  }
+}
+__device__ __forceinline__ float gelu_grad(float v) {
+  return 0.5f * (1.f + erff(v * 0.70710678f)) + v * 0.39894228f * __expf(-0.5f * v * v);
+}
+__global__ void gelu_bwd_kernel(const __nv_bfloat162* __restrict__ x, const __nv_bfloat162* __restrict__ dy,
+                                __nv_bfloat162* __restrict__ dx, long long n2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const float2 v = __bfloat1622float2(x[i]);
+    const float2 g = __bfloat1622float2(dy[i]);
+    dx[i] = __floats2bfloat162_rn(g.x * gelu_grad(v.x), g.y * gelu_grad(v.y));
+  }
+}
+
+// ---- shifted-window cosine attention ---------------------------------------------------------------------------------
+constexpr int kHd = 32;      // head dimension (always 32 in Swin-V2: embed_dim 96 / 3 heads, doubling together)
+constexpr int kMaxN = 64;    // tokens per window (window <= 8x8)
+
+struct AttnGeom {
+  int B, H, W, C, heads, ws, shift;
+  int nwy, nwx;  // windows per axis
+};
+
+// home position (row in the (B*H*W, 3C) qkv matrix) of local token t of window (b, wy, wx)
+__device__ __forceinline__ long long token_row(const AttnGeom& g, int b, int wy, int wx, int t, int& region) {
+  const int ty = t / g.ws, tx = t - ty * g.ws;
+  const int ys = wy * g.ws + ty, xs = wx * g.ws + tx;  // coordinates in the shifted grid
+  int ry = 0, rx = 0;
+  if (g.shift > 0) {
+    ry = ys < g.H - g.ws ? 0 : (ys < g.H - g.shift ? 1 : 2);
+    rx = xs < g.W - g.ws ? 0 : (xs < g.W - g.shift ? 1 : 2);
+  }
+  region = ry * 3 + rx;
+  int y = ys + g.shift, x = xs + g.shift;
+  if (y >= g.H) y -= g.H;
+  if (x >= g.W) x -= g.W;
+  return ((long long)b * g.H + y) * g.W + x;
+}
+
+// One CTA (64 threads) per (window, head); thread i owns query row i.  Saves nothing: the backward recomputes.
+__global__ void __launch_bounds__(64)
+window_attn_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ logit_scale,
+                       const float* __restrict__ bias /* [heads][N][N] */, __nv_bfloat16* __restrict__ out) {
+  __shared__ float sk[kMaxN][kHd + 1], sv[kMaxN][kHd + 1];
+  __shared__ int sreg[kMaxN];
+  const int N = g.ws * g.ws;
+  const int head = blockIdx.x % g.heads;
+  int w = blockIdx.x / g.heads;
+  const int wx = w % g.nwx;
+  w /= g.nwx;
+  const int wy = w % g.nwy;
+  const int b = w / g.nwy;
+  const int i = threadIdx.x;
+  float q[kHd];
+  long long my_row = 0;
+  if (i < N) {
+    int region;
+    my_row = token_row(g, b, wy, wx, i, region);
+    sreg[i] = region;
+    const __nv_bfloat16* base = qkv + my_row * 3 * g.C + head * kHd;
+    float qq = 0.f, kk = 0.f;
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) {
+      q[e] = __bfloat162float(base[e]);
+      qq = fmaf(q[e], q[e], qq);
+      const float kv = __bfloat162float(base[g.C + e]);
+      sk[i][e] = kv;
+      kk = fmaf(kv, kv, kk);
+      sv[i][e] = __bfloat162float(base[2 * g.C + e]);
+    }
+    const float qi = 1.f / fmaxf(sqrtf(qq), 1e-12f), ki = 1.f / fmaxf(sqrtf(kk), 1e-12f);
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) {
+      q[e] *= qi;
+      sk[i][e] *= ki;
+    }
+  }
+  __syncthreads();
+  if (i >= N) return;
+  const float scale = __expf(fminf(logit_scale[head], 4.6051702f));  // ln(100)
+  const float* brow = bias + ((long long)head * N + i) * N;
+  const int my_reg = sreg[i];
+  float p[kMaxN];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kMaxN; ++j) {
+    if (j < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) s = fmaf(q[e], sk[j][e], s);
+      s = s * scale + brow[j] + (sreg[j] != my_reg ? -100.f : 0.f);
+      p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxN; ++j) {
+    if (j < N) {
+      p[j] = __expf(p[j] - mx);
+      l += p[j];
+    }
+  }
+  const float inv = 1.f / l;
+  float o[kHd];
+#pragma unroll
+  for (int e = 0; e < kHd; ++e) o[e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxN; ++j) {
+    if (j < N) {
+      const float pj = p[j] * inv;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) o[e] = fmaf(pj, sv[j][e], o[e]);
+    }
+  }
+  __nv_bfloat16* op = out + my_row * g.C + head * kHd;
+#pragma unroll
+  for (int e = 0; e < kHd; ++e) op[e] = __float2bfloat16(o[e]);
+}
+
+// Backward.  One CTA per (head, group); the CTA loops over the windows of its group so that the bias / logit-scale
+// gradients accumulate in registers and are flushed once.  Pass 1 (thread = query row i): softmax statistics, delta_i,
+// dq_i.  Pass 2 (thread = key row j): dk_j, dv_j, dbias[:, j].
+__global__ void __launch_bounds__(64)
+window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
+                       const float* __restrict__ logit_scale, const float* __restrict__ bias,
+                       const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
+                       float* __restrict__ dbias, float* __restrict__ dlogit_scale) {
+  __shared__ float sq[kMaxN][kHd + 1], sk[kMaxN][kHd + 1], sv[kMaxN][kHd + 1], sdo[kMaxN][kHd + 1];
+  __shared__ float sm[kMaxN], sl[kMaxN], sdelta[kMaxN], sqn[kMaxN], skn[kMaxN];
+  __shared__ int sreg[kMaxN];
+  __shared__ long long srow[kMaxN];
+  __shared__ float s_red[64];
+  const int N = g.ws * g.ws;
+  const int head = blockIdx.x % g.heads;
+  const int grp = blockIdx.x / g.heads;
+  const int t = threadIdx.x;
+  const float ls = logit_scale[head];
+  const float scale = __expf(fminf(ls, 4.6051702f));
+  const int total_windows = g.B * g.nwy * g.nwx;
+  float dbias_col[kMaxN];  // d bias[head][i][t] accumulated over this CTA's windows (thread t = key column)
+#pragma unroll
+  for (int i = 0; i < kMaxN; ++i) dbias_col[i] = 0.f;
+  float dls = 0.f;
+  for (int w = grp; w < total_windows; w += groups) {
+    const int wx = w % g.nwx;
+    const int wy = (w / g.nwx) % g.nwy;
+    const int b = w / (g.nwx * g.nwy);
+    __syncthreads();  // previous window fully consumed
+    if (t < N) {
+      int region;
+      const long long row = token_row(g, b, wy, wx, t, region);
+      srow[t] = row;
+      sreg[t] = region;
+      const __nv_bfloat16* base = qkv + row * 3 * g.C + head * kHd;
+      const __nv_bfloat16* dob = dout + row * g.C + head * kHd;
+      float qq = 0.f, kk = 0.f;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) {
+        const float qv = __bfloat162float(base[e]), kv = __bfloat162float(base[g.C + e]);
+        sq[t][e] = qv;
+        sk[t][e] = kv;
+        qq = fmaf(qv, qv, qq);
+        kk = fmaf(kv, kv, kk);
+        sv[t][e] = __bfloat162float(base[2 * g.C + e]);
+        sdo[t][e] = __bfloat162float(dob[e]);
+      }
+      const float qi = 1.f / fmaxf(sqrtf(qq), 1e-12f), ki = 1.f / fmaxf(sqrtf(kk), 1e-12f);
+      sqn[t] = qi;
+      skn[t] = ki;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) {
+        sq[t][e] *= qi;  // q_hat
+        sk[t][e] *= ki;  // k_hat
+      }
+    }
+    __syncthreads();
+    // ---- pass 1: row i = t
+    if (t < N) {
+      const float* brow = bias + ((long long)head * N + t) * N;
+      const int my_reg = sreg[t];
+      float p[kMaxN];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kMaxN; ++j) {
+        if (j < N) {
+          float s = 0.f;
+#pragma unroll
+          for (int e = 0; e < kHd; ++e) s = fmaf(sq[t][e], sk[j][e], s);
+          s = s * scale + brow[j] + (sreg[j] != my_reg ? -100.f : 0.f);
+          p[j] = s;
+          mx = fmaxf(mx, s);
+        }
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxN; ++j) {
+        if (j < N) {
+          p[j] = __expf(p[j] - mx);
+          l += p[j];
+        }
+      }
+      const float inv = 1.f / l;
+      float delta = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxN; ++j) {
+        if (j < N) {
+          float dp = 0.f;
+#pragma unroll
+          for (int e = 0; e < kHd; ++e) dp = fmaf(sdo[t][e], sv[j][e], dp);
+          p[j] *= inv;
+          delta = fmaf(p[j], dp, delta);
+        }
+      }
+      float dq[kHd];
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) dq[e] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxN; ++j) {
+        if (j < N) {
+          float dp = 0.f;
+#pragma unroll
+          for (int e = 0; e < kHd; ++e) dp = fmaf(sdo[t][e], sv[j][e], dp);
+          const float ds = p[j] * (dp - delta) * scale;
+#pragma unroll
+          for (int e = 0; e < kHd; ++e) dq[e] = fmaf(ds, sk[j][e], dq[e]);
+        }
+      }
+      sm[t] = mx;
+      sl[t] = inv;
+      sdelta[t] = delta;
+      // through the normalisation: dq = (dq_hat - q_hat (q_hat . dq_hat)) / |q|
+      float dot = 0.f;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) dot = fmaf(sq[t][e], dq[e], dot);
+      __nv_bfloat16* dst = dqkv + srow[t] * 3 * g.C + head * kHd;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) dst[e] = __float2bfloat16((dq[e] - sq[t][e] * dot) * sqn[t]);
+    }
+    __syncthreads();
+    // ---- pass 2: key column j = t
+    if (t < N) {
+      const int my_reg = sreg[t];
+      float dk[kHd], dv[kHd];
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) dk[e] = dv[e] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxN; ++i) {
+        if (i < N) {
+          float c = 0.f, dp = 0.f;
+#pragma unroll
+          for (int e = 0; e < kHd; ++e) {
+            c = fmaf(sq[i][e], sk[t][e], c);
+            dp = fmaf(sdo[i][e], sv[t][e], dp);
+          }
+          const float s = c * scale + bias[((long long)head * N + i) * N + t] + (sreg[i] != my_reg ? -100.f : 0.f);
+          const float p = __expf(s - sm[i]) * sl[i];
+          const float ds = p * (dp - sdelta[i]);
+          dbias_col[i] += ds;
+          dls = fmaf(ds, c, dls);
+          const float dsc = ds * scale;
+#pragma unroll
+          for (int e = 0; e < kHd; ++e) {
+            dk[e] = fmaf(dsc, sq[i][e], dk[e]);
+            dv[e] = fmaf(p, sdo[i][e], dv[e]);
+          }
+        }
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) dot = fmaf(sk[t][e], dk[e], dot);
+      __nv_bfloat16* dst = dqkv + srow[t] * 3 * g.C + head * kHd;
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) {
+        dst[g.C + e] = __float2bfloat16((dk[e] - sk[t][e] * dot) * skn[t]);
+        dst[2 * g.C + e] = __float2bfloat16(dv[e]);
+      }
+    }
+  }
+  // flush: d bias[head][i][t], d logit_scale[head] (zero when the clamp is active)
+  if (t < N) {
+#pragma unroll
+    for (int i = 0; i < kMaxN; ++i)
+      if (i < N) atomicAdd(dbias + ((long long)head * N + i) * N + t, dbias_col[i]);
+  }
+  s_red[t] = (t < N && ls < 4.6051702f) ? dls * scale : 0.f;
+  __syncthreads();
+  if (t == 0) {
+    float a = 0.f;
+    for (int i = 0; i < 64; ++i) a += s_red[i];
+    atomicAdd(dlogit_scale + head, a);
+  }
+}
+
+}  // namespace
+}  // namespace tok
+
+using namespace tok;
+
+extern "C" {
+
+int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, const float* beta, float eps,
+                      const void* residual, const float* rowscale, int rows_per_sample, void* out, float* mean,
+                      float* rstd, void* stream) {
+  if (rows <= 0 || C <= 0 || C > 32 * kLnMaxPerLane) return set_error(TOK_ERR_INVALID, "layernorm_fwd: 1 <= C <= 1024");
+  if (rowscale && rows_per_sample <= 0) return set_error(TOK_ERR_INVALID, "layernorm_fwd: rows_per_sample");
+  const long long threads = rows * 32;
+  layernorm_fwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      rows, C, (const __nv_bfloat16*)x, gamma, beta, eps, (const __nv_bfloat16*)residual, rowscale,
+      rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)out, mean, rstd);
+  TOK_CHECK_LAUNCH("layernorm_fwd");
+  return TOK_OK;
+}
+
+int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, const float* mean, const float* rstd,
+                      const void* dout, const float* rowscale, int rows_per_sample, void* dx, float* dgamma,
+                      float* dbeta, void* stream) {
+  if (rows <= 0 || C <= 0 || C > 32 * kLnMaxPerLane) return set_error(TOK_ERR_INVALID, "layernorm_bwd: 1 <= C <= 1024");
+  long long ctas = 148LL * 8;
+  long long rpc = (rows + ctas - 1) / ctas;
+  if (rpc < 4) rpc = 4;
+  ctas = (rows + rpc - 1) / rpc;
+  layernorm_bwd_kernel<<<(unsigned)ctas, 128, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      rows, C, (const __nv_bfloat16*)x, gamma, mean, rstd, (const __nv_bfloat16*)dout, rowscale,
+      rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)dx, dgamma, dbeta, (int)rpc);
+  TOK_CHECK_LAUNCH("layernorm_bwd");
+  return TOK_OK;
+}
+
+int tok_gelu_fwd(long long n, const void* x, void* y, void* stream) {
+  if (n <= 0 || (n & 1)) return set_error(TOK_ERR_INVALID, "gelu: element count must be positive and even");
+  long long blocks = (n / 2 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gelu_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)x, (__nv_bfloat162*)y, n / 2);
+  TOK_CHECK_LAUNCH("gelu_fwd");
+  return TOK_OK;
+}
+int tok_gelu_bwd(long long n, const void* x, const void* dy, void* dx, void* stream) {
+  if (n <= 0 || (n & 1)) return set_error(TOK_ERR_INVALID, "gelu: element count must be positive and even");
+  long long blocks = (n / 2 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gelu_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)x, (const __nv_bfloat162*)dy,
+                                                                     (__nv_bfloat162*)dx, n / 2);
+  TOK_CHECK_LAUNCH("gelu_bwd");
+  return TOK_OK;
+}
+
+static int attn_geom(AttnGeom* g, int B, int H, int W, int C, int heads, int ws, int shift) {
+  if (B <= 0 || H <= 0 || W <= 0 || heads <= 0 || ws <= 0) return set_error(TOK_ERR_INVALID, "window_attn: bad shape");
+  if (C != heads * kHd) return set_error(TOK_ERR_INVALID, "window_attn: head dimension must be 32 (C=%d heads=%d)", C, heads);
+  if (ws * ws > kMaxN) return set_error(TOK_ERR_INVALID, "window_attn: window %d exceeds the 8x8 limit of this kernel", ws);
+  if ((H % ws) || (W % ws) || shift < 0 || shift >= ws) return set_error(TOK_ERR_INVALID, "window_attn: H, W must be multiples of the window; 0 <= shift < window");
+  g->B = B; g->H = H; g->W = W; g->C = C; g->heads = heads; g->ws = ws; g->shift = shift;
+  g->nwy = H / ws; g->nwx = W / ws;
+  return TOK_OK;
+}
+
+int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift, const void* qkv,
+                        const float* logit_scale, const float* bias, void* out, void* stream) {
+  AttnGeom g;
+  int rc = attn_geom(&g, B, H, W, C, heads, ws, shift);
+  if (rc) return rc;
+  const long long ctas = (long long)B * g.nwy * g.nwx * heads;
+  window_attn_fwd_kernel<<<(unsigned)ctas, 64, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)qkv, logit_scale, bias,
+                                                                         (__nv_bfloat16*)out);
+  TOK_CHECK_LAUNCH("window_attn_fwd");
+  return TOK_OK;
+}
+
+int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift, const void* qkv,
+                        const float* logit_scale, const float* bias, const void* dout, void* dqkv, float* dbias,
+                        float* dlogit_scale, void* stream) {
+  AttnGeom g;
+  int rc = attn_geom(&g, B, H, W, C, heads, ws, shift);
+  if (rc) return rc;
+  const int windows = B * g.nwy * g.nwx;
+  int groups = (148 * 16 + heads - 1) / heads;
+  if (groups > windows) groups = windows;
+  window_attn_bwd_kernel<<<(unsigned)(groups * heads), 64, 0, (cudaStream_t)stream>>>(
+      g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
+      dlogit_scale);
+  TOK_CHECK_LAUNCH("window_attn_bwd");
+  return TOK_OK;
+}
+
+}  // extern "C"

@@ -236,6 +236,10 @@ class StreamLoop:
                         dist.broadcast(b, 0)
             self.arena.refresh_shadow()
         self.use_graph = use_graph and os.environ.get('TOK_NO_GRAPH', '0') != '1'
+        if self.world > 1 and os.environ.get('TOK_GRAPH_DDP', '0') != '1':
+            # Capturing torch.distributed's NCCL all-reduce inside the step graph hung on the 2xB200 box (round 1);
+            # until that is understood the multi-GPU loop runs eagerly (measured cost: ~4 % of the step).
+            self.use_graph = False
         self.warmup = warmup
         self.graph = None
         self.static = None

@@ -763,3 +763,149 @@ def bilinear_resize(x, size):
     c = x.shape[1]
     out = BilinearCatFn.apply(tuple(size), x)
     return out if out.shape[1] == c else out[:, :c]
+
+
+# ------------------------------------------------------------------------------------------------------ Swin-V2
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dim of a (rows, C) bf16 matrix; with `residual` computes
+    residual + rowscale[sample] * LN(x) — the res-post-norm block tail `x + drop_path(norm(f(x)))` of timm's
+    SwinTransformerBlock.  weight / bias gradients are accumulated into `.grad` directly."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, residual, rowscale, rows_per_sample):
+        require_cuda(x, 'LayerNorm input')
+        x = x.to(BF16).contiguous()
+        rows, c = x.shape
+        out = torch.empty_like(x)
+        stats = torch.empty((2, rows), dtype=F32, device=x.device)
+        res = residual.to(BF16).contiguous() if residual is not None else None
+        lib().tok_layernorm_fwd(rows, c, _p(x), _p(weight), _p(bias), float(eps), _p(res), _p(rowscale),
+                                int(rows_per_sample), _p(out), _p(stats[0]), _p(stats[1]), _st())
+        ctx.save_for_backward(x, stats, rowscale)
+        ctx.params = (weight, bias)
+        ctx.meta = (rows, c, int(rows_per_sample), residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, stats, rowscale = ctx.saved_tensors
+        weight, bias = ctx.params
+        rows, c, rps, has_res = ctx.meta
+        g = g.to(BF16).contiguous()
+        dx = torch.empty_like(x)
+        gw = grad_buffer(weight) if weight.requires_grad else None
+        gb = grad_buffer(bias) if bias.requires_grad else None
+        lib().tok_layernorm_bwd(rows, c, _p(x), _p(weight), _p(stats[0]), _p(stats[1]), _p(g), _p(rowscale), rps,
+                                _p(dx), _p(gw), _p(gb), _st())
+        grad_ready(weight)
+        grad_ready(bias)
+        return dx, None, None, None, (g if has_res else None), None, None
+
+
+def layernorm(x, weight, bias, eps=1e-5, residual=None, rowscale=None, rows_per_sample=1):
+    return LayerNormFn.apply(x, weight, bias, eps, residual, rowscale, rows_per_sample)
+
+
+class GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.to(BF16).contiguous()
+        y = torch.empty_like(x)
+        lib().tok_gelu_fwd(x.numel(), _p(x), _p(y), _st())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.to(BF16).contiguous()
+        dx = torch.empty_like(x)
+        lib().tok_gelu_bwd(x.numel(), _p(x), _p(g), _p(dx), _st())
+        return dx
+
+
+def gelu(x):
+    return GeluFn.apply(x)
+
+
+class WindowAttnFn(torch.autograd.Function):
+    """timm WindowAttention core on the (B*H*W, 3C) qkv matrix: cosine attention + logit scale + bias + shift mask ->
+    (B*H*W, C).  `bias` (heads, N, N) fp32 is an autograd input (its gradient flows back to the cpb MLP);
+    `logit_scale` gets its gradient accumulated into `.grad`."""
+
+    @staticmethod
+    def forward(ctx, qkv, bias, logit_scale, geom):
+        b, h, w, c, heads, ws, shift = geom
+        qkv = qkv.to(BF16).contiguous()
+        bias = bias.float().contiguous()
+        ls = logit_scale.detach().float().reshape(-1).contiguous()
+        out = torch.empty((b * h * w, c), dtype=BF16, device=qkv.device)
+        lib().tok_window_attn_fwd(b, h, w, c, heads, ws, shift, _p(qkv), _p(ls), _p(bias), _p(out), _st())
+        ctx.save_for_backward(qkv, bias, ls)
+        ctx.meta = (geom, logit_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, bias, ls = ctx.saved_tensors
+        (b, h, w, c, heads, ws, shift), logit_scale = ctx.meta
+        g = g.to(BF16).contiguous()
+        dqkv = torch.empty_like(qkv)
+        dbias = torch.zeros_like(bias)
+        dls = torch.zeros_like(ls)
+        lib().tok_window_attn_bwd(b, h, w, c, heads, ws, shift, _p(qkv), _p(ls), _p(bias), _p(g), _p(dqkv), _p(dbias),
+                                  _p(dls), _st())
+        if logit_scale.requires_grad:
+            grad_buffer(logit_scale).add_(dls.reshape(logit_scale.shape))
+            grad_ready(logit_scale)
+        return dqkv, dbias, None, None
+
+
+def window_attention(qkv, bias, logit_scale, geom):
+    return WindowAttnFn.apply(qkv, bias, logit_scale, geom)
+
+
+class QkvLinearFn(torch.autograd.Function):
+    """F.linear(x, qkv.weight, cat(q_bias, zeros, v_bias)) of timm's WindowAttention (k has no bias)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, q_bias, v_bias):
+        m, k = x.shape
+        n = weight.shape[0]
+        x = x.to(BF16).contiguous()
+        w = shadow_of(weight)
+        b = None
+        if q_bias is not None:
+            b = torch.cat([q_bias.detach(), torch.zeros_like(v_bias), v_bias.detach()]).float().contiguous()
+        y = torch.empty((m, n), dtype=BF16, device=x.device)
+        lib().tok_linear_fwd(m, n, k, _p(x), _p(w), _p(b), _p(y), _st())
+        ctx.save_for_backward(x, w)
+        ctx.params = (weight, q_bias, v_bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        weight, q_bias, v_bias = ctx.params
+        m, k = x.shape
+        n = weight.shape[0]
+        g = g.to(BF16).contiguous()
+        L, st = lib(), _st()
+        dx = torch.empty((m, k), dtype=BF16, device=g.device)
+        L.tok_linear_dgrad(m, n, k, _p(g), _p(w), _p(dx), st)
+        if weight.requires_grad:
+            L.tok_linear_wgrad(m, n, k, _p(x), _p(g), _p(grad_buffer(weight)), st)
+        if q_bias is not None:
+            acc = torch.zeros((2, n), dtype=F32, device=g.device)
+            L.tok_bn_bwd_reduce(m, n, _p(g), None, None, _p(g), _p(acc[0]), _p(acc[1]), st)
+            c = n // 3
+            grad_buffer(q_bias).add_(acc[0, :c])
+            grad_buffer(v_bias).add_(acc[0, 2 * c:])
+            grad_ready(q_bias)
+            grad_ready(v_bias)
+        grad_ready(weight)
+        return dx, None, None, None
+
+
+def qkv_linear(x, weight, q_bias, v_bias):
+    return QkvLinearFn.apply(x, weight, q_bias, v_bias)
