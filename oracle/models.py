@@ -540,3 +540,57 @@ class SegmentationTask(nn.Module):
     def forward_with_gt(self, batch):
         pred = self.head(self.neck(self.backbone.forward_features(batch['image'])))
         return {'prediction': pred, 'target': batch.get('target')}
+
+
+class FPN(nn.Module):
+    """mmdet 3.0.0 necks.FPN with torchok's reversed in_channels (necks/detection/fpn.py:61-117); ConvModule defaults
+    (no norm, no activation) => plain biased convs under `.conv`.  PARITY UNPINNED (mmdet not vendored, no upstream test)."""
+
+    class _CM(nn.Module):
+        def __init__(self, cin, cout, k, stride=1, padding=0):
+            super().__init__()
+            self.conv = nn.Conv2d(cin, cout, k, stride, padding)
+
+        def forward(self, x):
+            return conv(self.conv, x)
+
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, add_extra_convs=False,
+                 relu_before_extra_convs=False):
+        super().__init__()
+        self.in_channels = list(in_channels[::-1])
+        n = len(self.in_channels)
+        self.num_outs, self.start_level, self.relu_before_extra_convs = num_outs, start_level, relu_before_extra_convs
+        self.backbone_end_level = n if end_level in (-1, n - 1) else end_level + 1
+        self.add_extra_convs = 'on_input' if add_extra_convs is True else add_extra_convs
+        self.lateral_convs, self.fpn_convs = nn.ModuleList(), nn.ModuleList()
+        for i in range(start_level, self.backbone_end_level):
+            self.lateral_convs.append(FPN._CM(self.in_channels[i], out_channels, 1))
+            self.fpn_convs.append(FPN._CM(out_channels, out_channels, 3, padding=1))
+        extra = num_outs - self.backbone_end_level + start_level
+        if self.add_extra_convs and extra >= 1:
+            for i in range(extra):
+                cin = self.in_channels[self.backbone_end_level - 1] if (i == 0 and self.add_extra_convs == 'on_input') \
+                    else out_channels
+                self.fpn_convs.append(FPN._CM(cin, out_channels, 3, 2, 1))
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.normal_(m.bias, std=0.1)
+
+    def forward(self, inputs):
+        lat = [c(inputs[i + self.start_level]) for i, c in enumerate(self.lateral_convs)]
+        used = len(lat)
+        for i in range(used - 1, 0, -1):
+            lat[i - 1] = q(lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode='nearest'))
+        outs = [self.fpn_convs[i](lat[i]) for i in range(used)]
+        if self.num_outs > len(outs):
+            if not self.add_extra_convs:
+                for _ in range(self.num_outs - used):
+                    outs.append(F.max_pool2d(outs[-1], 1, stride=2))
+            else:
+                src = {'on_input': inputs[self.backbone_end_level - 1], 'on_lateral': lat[-1], 'on_output': outs[-1]}[
+                    self.add_extra_convs]
+                outs.append(self.fpn_convs[used](src))
+                for i in range(used + 1, self.num_outs):
+                    outs.append(self.fpn_convs[i](F.relu(outs[-1]) if self.relu_before_extra_convs else outs[-1]))
+        return tuple(outs)

@@ -196,3 +196,38 @@ def test_segmentation_task_training_step():
     g, go = task.head.classifier.weight.grad, oracle.head.classifier.weight.grad
     print(f'seg task: logits {e_logits:.4f} loss {e_loss:.4f} head-grad l2 {rel_l2(g, go):.4f}')
     assert e_logits < 5e-2 and e_loss < 2e-2 and rel_l2(g, go) < 5e-2
+
+
+@pytest.mark.parametrize('extra,num_outs,start', [(False, 5, 0), ('on_input', 5, 1), ('on_output', 4, 0)])
+def test_fpn_neck(extra, num_outs, start):
+    """FPN ("next" row N1 / a10): lateral 1x1 + nearest top-down add + 3x3, extra levels; forward and gradients."""
+    import torchok_b200 as tb
+    from oracle import models as om
+    torch.manual_seed(7)
+    chans_deepest_first = [512, 256, 128, 64]     # torchok reverses in_channels (fpn.py:62): pass deepest first
+    o = om.FPN(chans_deepest_first, 64, num_outs, start_level=start, add_extra_convs=extra, relu_before_extra_convs=bool(extra))
+    m = tb.DETECTION_NECKS.get('FPN')(in_channels=chans_deepest_first, out_channels=64, num_outs=num_outs,
+                                      start_level=start, add_extra_convs=extra, relu_before_extra_convs=bool(extra))
+    assert tb.NECKS.get('FPN') is tb.DETECTION_NECKS.get('FPN')
+    with torch.no_grad():
+        for p in o.parameters():
+            if p.dim() == 4:
+                p.copy_(_bf(p))
+    m.load_state_dict(o.state_dict())
+    m.cuda()
+    xs = [_bf(torch.randn(2, c, s, s)) for c, s in zip([64, 128, 256, 512], [32, 16, 8, 4])]
+    xo = [x.clone().requires_grad_(True) for x in xs]
+    xm = [x.cuda().requires_grad_(True) for x in xs]
+    yo = o(xo)
+    rs = [_bf(torch.randn_like(y)) for y in yo]
+    sum((y * r).sum() for y, r in zip(yo, rs)).backward()
+    ym = m(xm)
+    assert len(ym) == num_outs and [tuple(a.shape) for a in ym] == [tuple(b.shape) for b in yo]
+    sum((y.float() * r.cuda()).sum() for y, r in zip(ym, rs)).backward()
+    for a, b in zip(ym, yo):
+        assert rel_err(a, b) < 1e-2
+    for a, b in zip(xm[start:], xo[start:]):
+        assert rel_err(a.grad, b.grad) < 2e-2
+    po = dict(o.named_parameters())
+    for k, p in m.named_parameters():
+        assert rel_l2(p.grad, po[k].grad) < 2e-2, k

@@ -1,1 +1,2 @@
 from . import hrnet  # noqa: F401
+from . import fpn  # noqa: F401
