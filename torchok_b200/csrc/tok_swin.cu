@@ -32,8 +32,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- LayerNorm -----------------------------------------------------------------------------------------------------
 // y = LN(x) * gamma + beta ; out = (res ? res + rowscale[b] * y : y).  One warp per row, C <= 1024 (x kept in registers).
-constexpr int kLnMaxPerLane = 32;  // C <= 1024
+constexpr int kLnMaxPerLane = 32;  // C <= 1024; the kernels are instantiated for 4 / 8 / 16 / 32 elements per lane
 
+template <int PER_LANE>
 __global__ void __launch_bounds__(128)
 layernorm_fwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ res,
@@ -42,10 +43,10 @@ layernorm_fwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
   const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
-  float v[kLnMaxPerLane];
+  float v[PER_LANE];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < PER_LANE; ++i) {
     const int c = lane + i * 32;
     v[i] = c < C ? __bfloat162float(x[r * C + c]) : 0.f;
     s += v[i];
@@ -53,7 +54,7 @@ layernorm_fwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
   const float mu = warp_sum(s) / C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < PER_LANE; ++i) {
     const int c = lane + i * 32;
     const float d = c < C ? v[i] - mu : 0.f;
     q = fmaf(d, d, q);
@@ -61,7 +62,7 @@ layernorm_fwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
   const float rs = rsqrtf(warp_sum(q) / C + eps);
   const float sc = rowscale ? rowscale[r / rows_per_sample] : 1.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < PER_LANE; ++i) {
     const int c = lane + i * 32;
     if (c < C) {
       float y = (v[i] - mu) * rs * gamma[c] + beta[c];
@@ -77,6 +78,7 @@ layernorm_fwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
 
 // dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)) with g = rowscale * dout (dres = dout passes through
 // unchanged on the Python side); dgamma += sum g*xhat, dbeta += sum g (per-CTA partials in shared memory, then atomics).
+template <int PER_LANE>
 __global__ void __launch_bounds__(128)
 layernorm_bwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -87,19 +89,19 @@ layernorm_bwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ag[kLnMaxPerLane], ab[kLnMaxPerLane];
+  float ag[PER_LANE], ab[PER_LANE];
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) ag[i] = ab[i] = 0.f;
+  for (int i = 0; i < PER_LANE; ++i) ag[i] = ab[i] = 0.f;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta;
   if (r1 > rows) r1 = rows;
   for (long long r = r0 + warp; r < r1; r += 4) {
     const float mu = mean[r], rs = rstd[r];
     const float sc = rowscale ? rowscale[r / rows_per_sample] : 1.f;
-    float xh[kLnMaxPerLane], gg[kLnMaxPerLane];
+    float xh[PER_LANE], gg[PER_LANE];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < PER_LANE; ++i) {
       const int c = lane + i * 32;
       if (c < C) {
         xh[i] = (__bfloat162float(x[r * C + c]) - mu) * rs;
@@ -116,13 +118,13 @@ layernorm_bwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
     s1 = warp_sum(s1) / C;
     s2 = warp_sum(s2) / C;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < PER_LANE; ++i) {
       const int c = lane + i * 32;
       if (c < C) dx[r * C + c] = __float2bfloat16(rs * (gg[i] - s1 - xh[i] * s2));
     }
   }
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < PER_LANE; ++i) {
     const int c = lane + i * 32;
     if (c < C) {
       atomicAdd(&sh[c], ag[i]);
@@ -158,6 +160,30 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat162* __restrict__ x, const __nv
 // ---- shifted-window cosine attention ---------------------------------------------------------------------------------
 constexpr int kHd = 32;      // head dimension (always 32 in Swin-V2: embed_dim 96 / 3 heads, doubling together)
 constexpr int kMaxN = 64;    // tokens per window (window <= 8x8)
+constexpr int kPitch = kHd + 4;  // shared-memory row pitch in floats: 16-byte aligned rows for LDS.128 broadcasts
+
+__device__ __forceinline__ float dot32(const float (&a)[kHd], const float* __restrict__ row) {
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < kHd; e += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + e);
+    s = fmaf(a[e], v.x, s);
+    s = fmaf(a[e + 1], v.y, s);
+    s = fmaf(a[e + 2], v.z, s);
+    s = fmaf(a[e + 3], v.w, s);
+  }
+  return s;
+}
+__device__ __forceinline__ void axpy32(float (&acc)[kHd], float a, const float* __restrict__ row) {
+#pragma unroll
+  for (int e = 0; e < kHd; e += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + e);
+    acc[e] = fmaf(a, v.x, acc[e]);
+    acc[e + 1] = fmaf(a, v.y, acc[e + 1]);
+    acc[e + 2] = fmaf(a, v.z, acc[e + 2]);
+    acc[e + 3] = fmaf(a, v.w, acc[e + 3]);
+  }
+}
 
 struct AttnGeom {
   int B, H, W, C, heads, ws, shift;
@@ -184,7 +210,7 @@ __device__ __forceinline__ long long token_row(const AttnGeom& g, int b, int wy,
 __global__ void __launch_bounds__(64)
 window_attn_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ logit_scale,
                        const float* __restrict__ bias /* [heads][N][N] */, __nv_bfloat16* __restrict__ out) {
-  __shared__ float sk[kMaxN][kHd + 1], sv[kMaxN][kHd + 1];
+  __shared__ __align__(16) float sk[kMaxN][kPitch], sv[kMaxN][kPitch];
   __shared__ int sreg[kMaxN];
   const int N = g.ws * g.ws;
   const int head = blockIdx.x % g.heads;
@@ -228,9 +254,7 @@ window_attn_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const 
 #pragma unroll
   for (int j = 0; j < kMaxN; ++j) {
     if (j < N) {
-      float s = 0.f;
-#pragma unroll
-      for (int e = 0; e < kHd; ++e) s = fmaf(q[e], sk[j][e], s);
+      float s = dot32(q, sk[j]);
       s = s * scale + brow[j] + (sreg[j] != my_reg ? -100.f : 0.f);
       p[j] = s;
       mx = fmaxf(mx, s);
@@ -251,9 +275,7 @@ window_attn_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const 
 #pragma unroll
   for (int j = 0; j < kMaxN; ++j) {
     if (j < N) {
-      const float pj = p[j] * inv;
-#pragma unroll
-      for (int e = 0; e < kHd; ++e) o[e] = fmaf(pj, sv[j][e], o[e]);
+      axpy32(o, p[j] * inv, sv[j]);
     }
   }
   __nv_bfloat16* op = out + my_row * g.C + head * kHd;
@@ -262,18 +284,30 @@ window_attn_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const 
 }
 
 // Backward.  One CTA per (head, group); the CTA loops over the windows of its group so that the bias / logit-scale
-// gradients accumulate in registers and are flushed once.  Pass 1 (thread = query row i): softmax statistics, delta_i,
-// dq_i.  Pass 2 (thread = key row j): dk_j, dv_j, dbias[:, j].
+// gradients accumulate on chip and are flushed once.  Pass 1 (thread = query row i): softmax statistics, O_i,
+// delta_i = dO_i . O_i, dq_i.  Pass 2 (thread = key row j): dk_j, dv_j, dbias[:, j].  Row vectors live in registers,
+// the other operand is read from shared memory with 16-byte broadcasts.
+constexpr int kAttnBwdSmem = (4 * kMaxN * kPitch + kMaxN * kMaxN + 5 * kMaxN) * 4 + kMaxN * 4 + kMaxN * 8 + 64 * 4 + 64;
+
 __global__ void __launch_bounds__(64)
 window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
                        const float* __restrict__ logit_scale, const float* __restrict__ bias,
                        const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
                        float* __restrict__ dbias, float* __restrict__ dlogit_scale) {
-  __shared__ float sq[kMaxN][kHd + 1], sk[kMaxN][kHd + 1], sv[kMaxN][kHd + 1], sdo[kMaxN][kHd + 1];
-  __shared__ float sm[kMaxN], sl[kMaxN], sdelta[kMaxN], sqn[kMaxN], skn[kMaxN];
-  __shared__ int sreg[kMaxN];
-  __shared__ long long srow[kMaxN];
-  __shared__ float s_red[64];
+  extern __shared__ __align__(16) float dyn[];
+  float (*sq)[kPitch] = reinterpret_cast<float (*)[kPitch]>(dyn);
+  float (*sk)[kPitch] = sq + kMaxN;
+  float (*sv)[kPitch] = sk + kMaxN;
+  float (*sdo)[kPitch] = sv + kMaxN;
+  float (*sdb)[kMaxN] = reinterpret_cast<float (*)[kMaxN]>(sdo + kMaxN);  // dbias[i][j] of this CTA, owner = thread j
+  float* sm = reinterpret_cast<float*>(sdb + kMaxN);
+  float* sl = sm + kMaxN;
+  float* sdelta = sl + kMaxN;
+  float* sqn = sdelta + kMaxN;
+  float* skn = sqn + kMaxN;
+  float* s_red = skn + kMaxN;
+  int* sreg = reinterpret_cast<int*>(s_red + 64);
+  long long* srow = reinterpret_cast<long long*>(sreg + kMaxN);
   const int N = g.ws * g.ws;
   const int head = blockIdx.x % g.heads;
   const int grp = blockIdx.x / g.heads;
@@ -281,9 +315,7 @@ window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__
   const float ls = logit_scale[head];
   const float scale = __expf(fminf(ls, 4.6051702f));
   const int total_windows = g.B * g.nwy * g.nwx;
-  float dbias_col[kMaxN];  // d bias[head][i][t] accumulated over this CTA's windows (thread t = key column)
-#pragma unroll
-  for (int i = 0; i < kMaxN; ++i) dbias_col[i] = 0.f;
+  for (int i = 0; i < kMaxN; ++i) sdb[i][t] = 0.f;
   float dls = 0.f;
   for (int w = grp; w < total_windows; w += groups) {
     const int wx = w % g.nwx;
@@ -320,6 +352,12 @@ window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__
     __syncthreads();
     // ---- pass 1: row i = t
     if (t < N) {
+      float qr[kHd], dor[kHd];
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) {
+        qr[e] = sq[t][e];
+        dor[e] = sdo[t][e];
+      }
       const float* brow = bias + ((long long)head * N + t) * N;
       const int my_reg = sreg[t];
       float p[kMaxN];
@@ -327,46 +365,35 @@ window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__
 #pragma unroll
       for (int j = 0; j < kMaxN; ++j) {
         if (j < N) {
-          float s = 0.f;
-#pragma unroll
-          for (int e = 0; e < kHd; ++e) s = fmaf(sq[t][e], sk[j][e], s);
-          s = s * scale + brow[j] + (sreg[j] != my_reg ? -100.f : 0.f);
+          const float s = dot32(qr, sk[j]) * scale + brow[j] + (sreg[j] != my_reg ? -100.f : 0.f);
           p[j] = s;
           mx = fmaxf(mx, s);
         }
       }
       float l = 0.f;
+      float o[kHd];
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) o[e] = 0.f;
 #pragma unroll
       for (int j = 0; j < kMaxN; ++j) {
         if (j < N) {
           p[j] = __expf(p[j] - mx);
           l += p[j];
+          axpy32(o, p[j], sv[j]);
         }
       }
       const float inv = 1.f / l;
-      float delta = 0.f;
+      float delta = 0.f;  // sum_j P_ij dP_ij = dO_i . O_i
 #pragma unroll
-      for (int j = 0; j < kMaxN; ++j) {
-        if (j < N) {
-          float dp = 0.f;
-#pragma unroll
-          for (int e = 0; e < kHd; ++e) dp = fmaf(sdo[t][e], sv[j][e], dp);
-          p[j] *= inv;
-          delta = fmaf(p[j], dp, delta);
-        }
-      }
+      for (int e = 0; e < kHd; ++e) delta = fmaf(dor[e], o[e] * inv, delta);
       float dq[kHd];
 #pragma unroll
       for (int e = 0; e < kHd; ++e) dq[e] = 0.f;
 #pragma unroll
       for (int j = 0; j < kMaxN; ++j) {
         if (j < N) {
-          float dp = 0.f;
-#pragma unroll
-          for (int e = 0; e < kHd; ++e) dp = fmaf(sdo[t][e], sv[j][e], dp);
-          const float ds = p[j] * (dp - delta) * scale;
-#pragma unroll
-          for (int e = 0; e < kHd; ++e) dq[e] = fmaf(ds, sk[j][e], dq[e]);
+          const float dp = dot32(dor, sv[j]);
+          axpy32(dq, p[j] * inv * (dp - delta) * scale, sk[j]);
         }
       }
       sm[t] = mx;
@@ -375,56 +402,48 @@ window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__
       // through the normalisation: dq = (dq_hat - q_hat (q_hat . dq_hat)) / |q|
       float dot = 0.f;
 #pragma unroll
-      for (int e = 0; e < kHd; ++e) dot = fmaf(sq[t][e], dq[e], dot);
+      for (int e = 0; e < kHd; ++e) dot = fmaf(qr[e], dq[e], dot);
       __nv_bfloat16* dst = dqkv + srow[t] * 3 * g.C + head * kHd;
 #pragma unroll
-      for (int e = 0; e < kHd; ++e) dst[e] = __float2bfloat16((dq[e] - sq[t][e] * dot) * sqn[t]);
+      for (int e = 0; e < kHd; ++e) dst[e] = __float2bfloat16((dq[e] - qr[e] * dot) * sqn[t]);
     }
     __syncthreads();
     // ---- pass 2: key column j = t
     if (t < N) {
+      float kr[kHd], vr[kHd], dk[kHd], dv[kHd];
+#pragma unroll
+      for (int e = 0; e < kHd; ++e) {
+        kr[e] = sk[t][e];
+        vr[e] = sv[t][e];
+        dk[e] = dv[e] = 0.f;
+      }
       const int my_reg = sreg[t];
-      float dk[kHd], dv[kHd];
-#pragma unroll
-      for (int e = 0; e < kHd; ++e) dk[e] = dv[e] = 0.f;
-#pragma unroll
-      for (int i = 0; i < kMaxN; ++i) {
-        if (i < N) {
-          float c = 0.f, dp = 0.f;
-#pragma unroll
-          for (int e = 0; e < kHd; ++e) {
-            c = fmaf(sq[i][e], sk[t][e], c);
-            dp = fmaf(sdo[i][e], sv[t][e], dp);
-          }
-          const float s = c * scale + bias[((long long)head * N + i) * N + t] + (sreg[i] != my_reg ? -100.f : 0.f);
-          const float p = __expf(s - sm[i]) * sl[i];
-          const float ds = p * (dp - sdelta[i]);
-          dbias_col[i] += ds;
-          dls = fmaf(ds, c, dls);
-          const float dsc = ds * scale;
-#pragma unroll
-          for (int e = 0; e < kHd; ++e) {
-            dk[e] = fmaf(dsc, sq[i][e], dk[e]);
-            dv[e] = fmaf(p, sdo[i][e], dv[e]);
-          }
-        }
+#pragma unroll 2
+      for (int i = 0; i < N; ++i) {
+        const float c = dot32(kr, sq[i]);
+        const float dp = dot32(vr, sdo[i]);
+        const float s = c * scale + bias[((long long)head * N + i) * N + t] + (sreg[i] != my_reg ? -100.f : 0.f);
+        const float p = __expf(s - sm[i]) * sl[i];
+        const float ds = p * (dp - sdelta[i]);
+        sdb[i][t] += ds;
+        dls = fmaf(ds, c, dls);
+        axpy32(dk, ds * scale, sq[i]);
+        axpy32(dv, p, sdo[i]);
       }
       float dot = 0.f;
 #pragma unroll
-      for (int e = 0; e < kHd; ++e) dot = fmaf(sk[t][e], dk[e], dot);
+      for (int e = 0; e < kHd; ++e) dot = fmaf(kr[e], dk[e], dot);
       __nv_bfloat16* dst = dqkv + srow[t] * 3 * g.C + head * kHd;
 #pragma unroll
       for (int e = 0; e < kHd; ++e) {
-        dst[g.C + e] = __float2bfloat16((dk[e] - sk[t][e] * dot) * skn[t]);
+        dst[g.C + e] = __float2bfloat16((dk[e] - kr[e] * dot) * skn[t]);
         dst[2 * g.C + e] = __float2bfloat16(dv[e]);
       }
     }
   }
   // flush: d bias[head][i][t], d logit_scale[head] (zero when the clamp is active)
   if (t < N) {
-#pragma unroll
-    for (int i = 0; i < kMaxN; ++i)
-      if (i < N) atomicAdd(dbias + ((long long)head * N + i) * N + t, dbias_col[i]);
+    for (int i = 0; i < N; ++i) atomicAdd(dbias + ((long long)head * N + i) * N + t, sdb[i][t]);
   }
   s_red[t] = (t < N && ls < 4.6051702f) ? dls * scale : 0.f;
   __syncthreads();
@@ -448,9 +467,16 @@ int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, 
   if (rows <= 0 || C <= 0 || C > 32 * kLnMaxPerLane) return set_error(TOK_ERR_INVALID, "layernorm_fwd: 1 <= C <= 1024");
   if (rowscale && rows_per_sample <= 0) return set_error(TOK_ERR_INVALID, "layernorm_fwd: rows_per_sample");
   const long long threads = rows * 32;
-  layernorm_fwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      rows, C, (const __nv_bfloat16*)x, gamma, beta, eps, (const __nv_bfloat16*)residual, rowscale,
-      rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)out, mean, rstd);
+  const unsigned grid = (unsigned)((threads + 127) / 128);
+#define TOK_LN_FWD(P)                                                                                              \
+  layernorm_fwd_kernel<P><<<grid, 128, 0, (cudaStream_t)stream>>>(                                                  \
+      rows, C, (const __nv_bfloat16*)x, gamma, beta, eps, (const __nv_bfloat16*)residual, rowscale,                \
+      rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)out, mean, rstd)
+  if (C <= 128) TOK_LN_FWD(4);
+  else if (C <= 256) TOK_LN_FWD(8);
+  else if (C <= 512) TOK_LN_FWD(16);
+  else TOK_LN_FWD(32);
+#undef TOK_LN_FWD
   TOK_CHECK_LAUNCH("layernorm_fwd");
   return TOK_OK;
 }
@@ -463,9 +489,15 @@ int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, 
   long long rpc = (rows + ctas - 1) / ctas;
   if (rpc < 4) rpc = 4;
   ctas = (rows + rpc - 1) / rpc;
-  layernorm_bwd_kernel<<<(unsigned)ctas, 128, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      rows, C, (const __nv_bfloat16*)x, gamma, mean, rstd, (const __nv_bfloat16*)dout, rowscale,
-      rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)dx, dgamma, dbeta, (int)rpc);
+#define TOK_LN_BWD(P)                                                                                              \
+  layernorm_bwd_kernel<P><<<(unsigned)ctas, 128, 2 * C * sizeof(float), (cudaStream_t)stream>>>(                    \
+      rows, C, (const __nv_bfloat16*)x, gamma, mean, rstd, (const __nv_bfloat16*)dout, rowscale,                   \
+      rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)dx, dgamma, dbeta, (int)rpc)
+  if (C <= 128) TOK_LN_BWD(4);
+  else if (C <= 256) TOK_LN_BWD(8);
+  else if (C <= 512) TOK_LN_BWD(16);
+  else TOK_LN_BWD(32);
+#undef TOK_LN_BWD
   TOK_CHECK_LAUNCH("layernorm_bwd");
   return TOK_OK;
 }
@@ -519,7 +551,13 @@ int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift
   const int windows = B * g.nwy * g.nwx;
   int groups = (148 * 16 + heads - 1) / heads;
   if (groups > windows) groups = windows;
-  window_attn_bwd_kernel<<<(unsigned)(groups * heads), 64, 0, (cudaStream_t)stream>>>(
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem);
+    if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_bwd: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  window_attn_bwd_kernel<<<(unsigned)(groups * heads), 64, kAttnBwdSmem, (cudaStream_t)stream>>>(
       g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
       dlogit_scale);
   TOK_CHECK_LAUNCH("window_attn_bwd");
