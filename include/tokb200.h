@@ -127,6 +127,19 @@ int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2
                       const void* bits, const float* scale, const float* shift, const float* coef_a,
                       const float* coef_c1, const float* coef_c0, void* dy, void* dres, void* stream);
 
+/* Fused ResNet stem tail (resnet.py:488-490,510): BN -> ReLU -> maxpool 3x3 stride 2 pad 1 in one pass over the conv
+ * output y (act is written only when non-NULL: the act1 feature of forward_features), and its backward with the pooled
+ * gradient gathered on the fly (dact nullable = gradient of the act1 feature): pass 1 reduces sum_g / sum_gy, pass 2
+ * writes dy = a*g + c1*y + c0.  argmax: one byte per pooled element (window slot of the first maximum). */
+int tok_stem_bn_relu_pool_fwd(int n, int h, int w, int c, const void* y, const float* scale, const float* shift,
+                              void* act, void* pooled, void* argmax, void* stream);
+int tok_stem_bwd_reduce(int n, int h, int w, int c, const void* dpooled, const void* argmax, const void* dact,
+                        const void* y, const float* scale, const float* shift, float* sum_g, float* sum_gy,
+                        void* stream);
+int tok_stem_bwd_apply(int n, int h, int w, int c, const void* dpooled, const void* argmax, const void* dact,
+                       const void* y, const float* scale, const float* shift, const float* coef_a,
+                       const float* coef_c1, const float* coef_c0, void* dy, void* stream);
+
 /* dst[n, p*stride, q*stride, :] += src_compact[n, p, q, :] (NHWC bf16, P = (h-1)/stride+1): merges the compact data
  * gradient of a strided 1x1 downsample conv (timm downsample_conv, resnet.py:14) into the block-input gradient. */
 int tok_strided_add(int n, int h, int w, int c, int stride, const void* src_compact, void* dst, void* stream);

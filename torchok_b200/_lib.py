@@ -62,6 +62,9 @@ _SIGS = {
     'tok_bn_apply_bits': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_reduce2': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_apply2': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_stem_bn_relu_pool_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_stem_bwd_reduce': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_stem_bwd_apply': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_strided_add': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_maxpool_fwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_maxpool_bwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -14,6 +14,7 @@
 // the forward pass, 8 channels per byte in vector order).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/tokb200.h"
@@ -290,6 +291,163 @@ strided_add_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused ResNet stem
+// conv7x7 output y -> BN -> ReLU -> maxpool 3x3/2 pad 1 in ONE pass (torchok/models/backbones/resnet.py:488-490,510,
+// 542-545): reads y once, writes the pooled tensor + argmax slots (and `act` only when the caller needs the act1
+// feature); the backward below gathers the pooled gradient on the fly, so neither the 112x112 activation nor its
+// gradient ever makes a round trip through HBM.
+__global__ void __launch_bounds__(256)
+stem_bn_relu_pool_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
+                             const float* __restrict__ shift, uint4* __restrict__ act, uint4* __restrict__ pooled,
+                             uint2* __restrict__ arg, long long total, int H, int W, int P, int Q, int cvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    long long t = i / cvec;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const long long n = t / P;
+    float sc[8], sf[8], best[8];
+    uint32_t bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + cv * 8 + j);
+      sf[j] = __ldg(shift + cv * 8 + j);
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = p * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int w = q * 2 - 1 + c;
+        if (w < 0 || w >= W) continue;
+        const long long o = ((n * H + h) * W + w) * cvec + cv;
+        float f[8];
+        unpack8(__ldg(y + o), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaxf(fmaf(f[j], sc[j], sf[j]), 0.f);
+          f[j] = __bfloat162float(__float2bfloat16(f[j]));  // the value torch's pool would see (bf16 activation)
+          if (f[j] > best[j]) {
+            best[j] = f[j];
+            bi[j] = r * 3 + c;
+          }
+        }
+        if (act != nullptr && r >= 1 && c >= 1) act[o] = pack8(f);  // rows 2p, 2p+1 / cols 2q, 2q+1: unique owner
+      }
+    }
+    pooled[i] = pack8(best);
+    arg[i] = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24),
+                        bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
+  }
+}
+
+// gradient reaching y's ReLU output at (n, h, w, cv): sum over the <= 4 pooling windows that contain the pixel of
+// dpooled * [argmax slot == this pixel]  (+ the direct gradient of the act1 feature when it was used).
+// Branch-free: window A = (h >> 1) always contains the row (tap 1 or 2), window B = A + 1 contains it (tap 0) iff h is
+// odd; same along w.  All eight loads are issued before any use.
+__device__ __forceinline__ void stem_pool_grad(float (&g)[8], const uint4* __restrict__ dpooled,
+                                               const uint2* __restrict__ arg, const uint4* __restrict__ dact,
+                                               long long n, int h, int w, int cv, int H, int W, int P, int Q, int cvec) {
+  const int pA = h >> 1, qA = w >> 1;
+  const int rA = h - (pA * 2 - 1), cA = w - (qA * 2 - 1);
+  const bool hB = (h & 1) && (pA + 1 < P), wB = (w & 1) && (qA + 1 < Q);
+  const int pB = hB ? pA + 1 : pA, qB = wB ? qA + 1 : qA;
+  const long long base = n * P;
+  const long long o00 = ((base + pA) * Q + qA) * cvec + cv, o01 = ((base + pA) * Q + qB) * cvec + cv;
+  const long long o10 = ((base + pB) * Q + qA) * cvec + cv, o11 = ((base + pB) * Q + qB) * cvec + cv;
+  const uint2 a00 = __ldg(arg + o00), a01 = __ldg(arg + o01), a10 = __ldg(arg + o10), a11 = __ldg(arg + o11);
+  const uint4 d00 = __ldg(dpooled + o00), d01 = __ldg(dpooled + o01), d10 = __ldg(dpooled + o10),
+              d11 = __ldg(dpooled + o11);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (dact != nullptr) unpack8(ldg_stream(dact + ((n * H + h) * W + w) * cvec + cv), g);
+  const uint32_t s00 = rA * 3 + cA, s01 = rA * 3 + 0, s10 = 0 * 3 + cA, s11 = 0;
+  auto add = [&](const uint2& a, const uint4& dv, uint32_t slot, bool on) {
+    float d[8];
+    unpack8(dv, d);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (on && ((a.x >> (8 * j)) & 0xFF) == slot) g[j] += d[j];
+      if (on && ((a.y >> (8 * j)) & 0xFF) == slot) g[4 + j] += d[4 + j];
+    }
+  };
+  add(a00, d00, s00, true);
+  add(a01, d01, s01, wB);
+  add(a10, d10, s10, hB);
+  add(a11, d11, s11, hB && wB);
+}
+
+// mode 0: sum_g / sum_gy reduction; mode 1: dy = a*g + c1*y + c0
+template <int MODE>
+__global__ void __launch_bounds__(256)
+stem_bwd_kernel(const uint4* __restrict__ dpooled, const uint2* __restrict__ arg, const uint4* __restrict__ dact,
+                const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                float* __restrict__ sum_g, float* __restrict__ sum_gy, const float* __restrict__ coef_a,
+                const float* __restrict__ coef_c1, const float* __restrict__ coef_c0, uint4* __restrict__ dy,
+                long long rows, int H, int W, int P, int Q, int cvec, int cvec_b, int rows_per_cta) {
+  __shared__ float part[MODE == 0 ? 256 * 16 : 1];
+  const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
+  float a1[8], a2[8], sc[8], sf[8], ca[8], c1[8], c0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  if (m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + m.cv * 8 + j);
+      sf[j] = __ldg(shift + m.cv * 8 + j);
+      if (MODE == 1) {
+        ca[j] = __ldg(coef_a + m.cv * 8 + j);
+        c1[j] = __ldg(coef_c1 + m.cv * 8 + j);
+        c0[j] = __ldg(coef_c0 + m.cv * 8 + j);
+      }
+    }
+    for (long long r = m.r0 + m.rl; r < m.r1; r += m.rlanes) {
+      const int w = (int)(r % W);
+      const long long t = r / W;
+      const int h = (int)(t % H);
+      const long long n = t / H;
+      float g[8], yy[8];
+      unpack8(ldg_stream(y + r * cvec + m.cv), yy);
+      stem_pool_grad(g, dpooled, arg, dact, n, h, w, m.cv, H, W, P, Q, cvec);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = fmaf(yy[j], sc[j], sf[j]) > 0.f ? g[j] : 0.f;
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a1[j] += g[j];
+          a2[j] = fmaf(g[j], yy[j], a2[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yy[j] = fmaf(ca[j], g[j], fmaf(c1[j], yy[j], c0[j]));
+        dy[r * cvec + m.cv] = pack8(yy);
+      }
+    }
+  }
+  if (MODE == 0) {
+    float* mine = part + threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mine[j] = a1[j];
+      mine[8 + j] = a2[j];
+    }
+    __syncthreads();
+    const int rlanes = 256 / cvec_b;
+    for (int o = threadIdx.x; o < cvec_b * 16; o += 256) {
+      float t = 0.f;
+      for (int rl = 0; rl < rlanes; ++rl) t += part[rl * cvec_b * 16 + o];
+      const int cl = o >> 4, k = o & 15;
+      const int c = (blockIdx.y * cvec_b + cl) * 8 + (k & 7);
+      if (c < cvec * 8) atomicAdd((k < 8 ? sum_g : sum_gy) + c, t);
+    }
+  }
+}
+
 struct Grid2 {
   dim3 grid;
   int cvec, cvec_b, rows_per_cta;
@@ -340,6 +498,48 @@ int tok_strided_add(int n, int h, int w, int c, int stride, const void* src_comp
   strided_add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src_compact, (uint4*)dst, total,
                                                                        P, Q, c / 8, h, w, stride);
   TOK_CHECK_LAUNCH("strided_add");
+  return TOK_OK;
+}
+
+int tok_stem_bn_relu_pool_fwd(int n, int h, int w, int c, const void* y, const float* scale, const float* shift,
+                              void* act, void* pooled, void* argmax, void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8)) return set_error(TOK_ERR_INVALID, "stem_bn_relu_pool_fwd: bad shape");
+  const int P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
+  if (act && ((h & 1) || (w & 1))) return set_error(TOK_ERR_INVALID, "stem_bn_relu_pool_fwd: act output needs even H, W");
+  const long long total = (long long)n * P * Q * (c / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stem_bn_relu_pool_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)y, scale, shift, (uint4*)act, (uint4*)pooled, (uint2*)argmax, total, h, w, P, Q, c / 8);
+  TOK_CHECK_LAUNCH("stem_bn_relu_pool_fwd");
+  return TOK_OK;
+}
+
+int tok_stem_bwd_reduce(int n, int h, int w, int c, const void* dpooled, const void* argmax, const void* dact,
+                        const void* y, const float* scale, const float* shift, float* sum_g, float* sum_gy,
+                        void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8)) return set_error(TOK_ERR_INVALID, "stem_bwd_reduce: bad shape");
+  const int P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
+  const long long rows = (long long)n * h * w;
+  const Grid2 g = plan(rows, c, 6);
+  stem_bwd_kernel<0><<<g.grid, 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, sum_g, sum_gy,
+      nullptr, nullptr, nullptr, nullptr, rows, h, w, P, Q, g.cvec, g.cvec_b, g.rows_per_cta);
+  TOK_CHECK_LAUNCH("stem_bwd_reduce");
+  return TOK_OK;
+}
+
+int tok_stem_bwd_apply(int n, int h, int w, int c, const void* dpooled, const void* argmax, const void* dact,
+                       const void* y, const float* scale, const float* shift, const float* coef_a,
+                       const float* coef_c1, const float* coef_c0, void* dy, void* stream) {
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8)) return set_error(TOK_ERR_INVALID, "stem_bwd_apply: bad shape");
+  const int P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
+  const long long rows = (long long)n * h * w;
+  const Grid2 g = plan(rows, c, 6);
+  stem_bwd_kernel<1><<<g.grid, 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, nullptr, nullptr,
+      coef_a, coef_c1, coef_c0, (uint4*)dy, rows, h, w, P, Q, g.cvec, g.cvec_b, g.rows_per_cta);
+  TOK_CHECK_LAUNCH("stem_bwd_apply");
   return TOK_OK;
 }
 

@@ -136,8 +136,12 @@ class ResNet(BaseBackbone):
                 if hasattr(m, 'zero_init_last'):
                     m.zero_init_last()
 
-    def _forward_collect(self, x):
-        act1, x = stem(x, self.conv1, self.bn1, (3, 2, 1))
+    def forward(self, x):
+        # only the last stage is needed: the stem does not materialise the act1 feature
+        return self._forward_collect(x, need_act=False)[-1]
+
+    def _forward_collect(self, x, need_act=True):
+        act1, x = stem(x, self.conv1, self.bn1, (3, 2, 1), need_act=need_act)
         feats = [act1]
         for name in ('layer1', 'layer2', 'layer3', 'layer4'):
             x = getattr(self, name)(x)

@@ -382,10 +382,12 @@ def residual_block(x, block):
 # ------------------------------------------------------------------------------------------------------ ResNet stem
 class StemFn(torch.autograd.Function):
     """conv 7x7 s2 p3 (Cin <= 4) -> BN -> ReLU -> maxpool 3x3 s2 p1 (torchok/models/backbones/resnet.py:488-490,510,
-    542-545).  Returns (act1, pooled); the image is consumed straight from its NCHW fp32/bf16 layout."""
+    542-545).  Returns (act1 or None, pooled); the image is consumed straight from its NCHW fp32/bf16 layout.  With the
+    standard 3/2/1 pool the BN-apply, ReLU and pooling run as ONE pass over the conv output (and the backward gathers
+    the pooled gradient on the fly), so the 112x112 activation only exists in HBM when the caller asks for it."""
 
     @staticmethod
-    def forward(ctx, image, conv, bn, pool, keep, *params):
+    def forward(ctx, image, conv, bn, pool, keep, need_act, *params):
         K.require_cuda(image, 'image')
         ctx.set_materialize_grads(False)  # `act` is usually unused: do not build (and convert) a zero gradient for it
         L = lib()
@@ -419,19 +421,33 @@ class StemFn(torch.autograd.Function):
             L.tok_stem_conv_fprop(n, h, w, k, K._p(xs2d), K._p(wp), K._p(y), None, None, st)
             L.tok_bn_finalize_eval(k, K._p(bs.running_mean), K._p(bs.running_var), K._p(bs.weight), K._p(bs.bias),
                                    bs.eps, K._p(small[0]), K._p(small[1]), st)
-        act = torch.empty_like(y) if keep else y
-        L.tok_bn_apply(rows, k, K._p(y), K._p(small[0]), K._p(small[1]), None, 1, K._p(act), st)
-        act = act.permute(0, 3, 1, 2)
         pk, ps, pp = pool
-        pooled, arg = K.maxpool_fwd(act, pk, ps, pp)
+        fused = (pk, ps, pp) == (3, 2, 1) and P % 2 == 0 and Q % 2 == 0
+        act = None
+        if fused:
+            PP, QQ = (P + 2 - 3) // 2 + 1, (Q + 2 - 3) // 2 + 1
+            if need_act:
+                act = torch.empty_like(y)
+            pooled_raw = torch.empty((n, PP, QQ, k), dtype=BF16, device=dev)
+            arg = torch.empty((n, PP, QQ, k), dtype=torch.uint8, device=dev)
+            L.tok_stem_bn_relu_pool_fwd(n, P, Q, k, K._p(y), K._p(small[0]), K._p(small[1]), K._p(act),
+                                        K._p(pooled_raw), K._p(arg), st)
+            pooled = pooled_raw.permute(0, 3, 1, 2)
+            if act is not None:
+                act = act.permute(0, 3, 1, 2)
+        else:
+            act = torch.empty_like(y) if keep else y
+            L.tok_bn_apply(rows, k, K._p(y), K._p(small[0]), K._p(small[1]), None, 1, K._p(act), st)
+            act = act.permute(0, 3, 1, 2)
+            pooled, arg = K.maxpool_fwd(act, pk, ps, pp)
         if keep:
             ctx.save_for_backward(xs2d, y, small, arg)
-            ctx.meta = (conv, bn, pool, (n, c, h, w), (P, Q))
+            ctx.meta = (conv, bn, pool, (n, c, h, w), (P, Q), fused)
         return act, pooled
 
     @staticmethod
     def backward(ctx, d_act, d_pooled):
-        conv, bn, (pk, ps, pp), (n, c, h, w), (P, Q) = ctx.meta
+        conv, bn, (pk, ps, pp), (n, c, h, w), (P, Q), fused = ctx.meta
         xs2d, y, small, arg = ctx.saved_tensors
         L = lib()
         st = K._st()
@@ -440,23 +456,35 @@ class StemFn(torch.autograd.Function):
         rows = n * P * Q
         if d_pooled is None and d_act is None:
             return (None,) * len(ctx.needs_input_grad)
-        if d_pooled is not None:
-            dout = K.maxpool_bwd(K._dense_grad(d_pooled, k), arg, (n, k, P, Q), k, pk, ps, pp)
-            dout2 = K._dense_grad(d_act, k) if d_act is not None else None
-        else:
-            dout, dout2 = K._dense_grad(d_act, k), None
         acc = bn._tok_acc
         gw, gb = _bn_grads(bn)
         coefs = torch.empty((3, k), dtype=F32, device=dev)
-        # ReLU mask rebuilt from y and the forward's scale/shift (MASK_Y): `act` is not kept for the backward
-        L.tok_bn_bwd_reduce2(rows, k, K._p(dout), K._p(dout2), K._p(y), K.MASK_Y, None, K._p(small[0]),
-                             K._p(small[1]), K._p(acc[2]), K._p(acc[3]), st)
-        L.tok_bn_bwd_finalize(k, float(rows), K._p(acc[2]), K._p(acc[3]), K._p(small[2]), K._p(small[3]),
-                              K._p(bn.weight), K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(gw), K._p(gb), 1,
-                              st)
         dy = torch.empty_like(y)
-        L.tok_bn_bwd_apply2(rows, k, K._p(dout), K._p(dout2), K._p(y), K.MASK_Y, None, K._p(small[0]),
-                            K._p(small[1]), K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(dy), None, st)
+        if fused and d_pooled is not None:
+            dp = K._dense_grad(d_pooled, k)
+            da = K._dense_grad(d_act, k) if d_act is not None else None
+            L.tok_stem_bwd_reduce(n, P, Q, k, K._p(dp), K._p(arg), K._p(da), K._p(y), K._p(small[0]), K._p(small[1]),
+                                  K._p(acc[2]), K._p(acc[3]), st)
+            L.tok_bn_bwd_finalize(k, float(rows), K._p(acc[2]), K._p(acc[3]), K._p(small[2]), K._p(small[3]),
+                                  K._p(bn.weight), K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(gw), K._p(gb),
+                                  1, st)
+            L.tok_stem_bwd_apply(n, P, Q, k, K._p(dp), K._p(arg), K._p(da), K._p(y), K._p(small[0]), K._p(small[1]),
+                                 K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(dy), st)
+        else:
+            if d_pooled is not None:
+                PP, QQ = arg.shape[1], arg.shape[2]
+                dout = K.maxpool_bwd(K._dense_grad(d_pooled, k), arg, (n, k, P, Q), k, pk, ps, pp)
+                dout2 = K._dense_grad(d_act, k) if d_act is not None else None
+            else:
+                dout, dout2 = K._dense_grad(d_act, k), None
+            # ReLU mask rebuilt from y and the forward's scale/shift (MASK_Y): `act` is not kept for the backward
+            L.tok_bn_bwd_reduce2(rows, k, K._p(dout), K._p(dout2), K._p(y), K.MASK_Y, None, K._p(small[0]),
+                                 K._p(small[1]), K._p(acc[2]), K._p(acc[3]), st)
+            L.tok_bn_bwd_finalize(k, float(rows), K._p(acc[2]), K._p(acc[3]), K._p(small[2]), K._p(small[3]),
+                                  K._p(bn.weight), K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(gw), K._p(gb),
+                                  1, st)
+            L.tok_bn_bwd_apply2(rows, k, K._p(dout), K._p(dout2), K._p(y), K.MASK_Y, None, K._p(small[0]),
+                                K._p(small[1]), K._p(coefs[0]), K._p(coefs[1]), K._p(coefs[2]), K._p(dy), None, st)
         if conv.weight.requires_grad:
             dwp = torch.zeros((k, 256), dtype=F32, device=dev)
             L.tok_stem_conv_wgrad(n, h, w, k, K._p(xs2d), K._p(dy), K._p(dwp), st)
@@ -468,10 +496,10 @@ class StemFn(torch.autograd.Function):
         return (None,) * len(ctx.needs_input_grad)
 
 
-def stem(image, conv, bn, pool=(3, 2, 1)):
+def stem(image, conv, bn, pool=(3, 2, 1), need_act=True):
     params = _params(conv, bn)
     keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    return StemFn.apply(image, conv, bn, pool, keep, *params)
+    return StemFn.apply(image, conv, bn, pool, keep, need_act, *params)
 
 
 # ------------------------------------------------------------------------------------------------------ small modules
