@@ -192,6 +192,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('TOK_GRAPH_DDP', '0') == '1':    # experimental: NCCL all-reduce captured in the step graph
+            os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')
+            os.environ.setdefault('NCCL_ASYNC_ERROR_HANDLING', '0')
         os.environ.setdefault('NCCL_IB_DISABLE', '1')      # NVLink only (north_star)
         os.environ.setdefault('NCCL_P2P_LEVEL', 'NVL')
         dist.init_process_group('nccl', device_id=dev)
@@ -335,7 +338,13 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroy_process_group() was seen to block after graph-captured collectives,
+        # and a benchmark process has nothing left to clean up.  All ranks meet at a barrier first.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():

@@ -237,8 +237,10 @@ class StreamLoop:
             self.arena.refresh_shadow()
         self.use_graph = use_graph and os.environ.get('TOK_NO_GRAPH', '0') != '1'
         if self.world > 1 and os.environ.get('TOK_GRAPH_DDP', '0') != '1':
-            # Capturing torch.distributed's NCCL all-reduce inside the step graph hung on the 2xB200 box (round 1);
-            # until that is understood the multi-GPU loop runs eagerly (measured cost: ~4 % of the step).
+            # Graph capture of the NCCL all-reduce works on 2xB200 with capture_error_mode='thread_local' and
+            # TORCH_NCCL_ASYNC_ERROR_HANDLING=0 (21.6 ms/step vs 22.5 eager) but is opt-in (TOK_GRAPH_DDP=1) until it
+            # has been validated at 4 and 8 ranks: with the default 'global' mode the capture hung, and a hang costs a
+            # whole scaling run where the eager loop costs ~4 %.
             self.use_graph = False
         self.warmup = warmup
         self.graph = None
@@ -292,7 +294,9 @@ class StreamLoop:
             torch.cuda.synchronize()
             self._restore(snap)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.stream):
+            # with NCCL in the step, other threads (the process-group watchdog) touch the CUDA API during capture
+            mode = 'thread_local' if self.world > 1 else 'global'
+            with torch.cuda.graph(g, stream=self.stream, capture_error_mode=mode):
                 out = self._eager_step(static)
                 self.loss = out['loss'].detach()
             self.graph = g
