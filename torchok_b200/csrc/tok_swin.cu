@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/tokb200.h"
 #include "tok_internal.h"
@@ -283,6 +284,210 @@ window_attn_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const 
   for (int e = 0; e < kHd; ++e) op[e] = __float2bfloat16(o[e]);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// tcgen05 forward: QK^T -> scale + bias + mask -> softmax -> PV in ONE kernel, accumulators in TMEM.
+// A CTA (128 threads, thread = row) owns one head and walks pairs of windows.  The two windows of a pair are stacked
+// along M (rows 0-63 / 64-127, 49 or 64 valid tokens each):
+//   S[128 x 128] = Qhat[128 x 32] . Khat[128 x 32]^T      one UMMA chain (2 x K16); only the two diagonal 64 x 64 blocks
+//                                                          are meaningful (query and key of the same window)
+//   softmax per row in registers straight from TMEM (tcgen05.ld), P written to shared memory as bf16
+//   O[128 x 64]  = [P_A; 0] . V_A + [0; P_B] . V_B         two K64 blocks: block-diagonal P against the per-window V
+// Operand tiles are written by the threads themselves in the 128B-swizzled K-major / MN-major layouts the UMMA
+// descriptors expect (the same layouts TMA produces for the conv kernels); rows are 128 bytes of which 64 carry data.
+constexpr int kTcThreads = 128;
+constexpr int kTcSmem = 16384 * 2 + 8192 * 2 + 16384 * 2 + kMaxN * kMaxN * 4 + 128 * 4 + 2 * 8 + 16 + 1024;
+
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+__global__ void __launch_bounds__(kTcThreads)
+window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
+                          const float* __restrict__ logit_scale, const float* __restrict__ bias,
+                          __nv_bfloat16* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                 // [128][128 B]  K-major A of S
+  uint8_t* sK = sQ + 16384;           // [128][128 B]  K-major B of S
+  uint8_t* sV = sK + 16384;           // 2 x [64 keys][128 B]  MN-major B of O (cols 32..63 stay zero)
+  uint8_t* sP = sV + 16384;           // 2 x [128][128 B]  K-major A of O (block-diagonal halves)
+  float* sbias = reinterpret_cast<float*>(sP + 32768);  // [N][N] of this head
+  int* sreg = reinterpret_cast<int*>(sbias + kMaxN * kMaxN);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sreg + 128);  // [0] S ready, [1] O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+  const int N = g.ws * g.ws;
+  const int head = blockIdx.x % g.heads;
+  const int grp = blockIdx.x / g.heads;
+  const int r = threadIdx.x;
+  const int warp = r >> 5;
+  const int prob = r >> 6;        // which window of the pair
+  const int t = r & 63;           // token inside the window
+  const bool tok_ok = t < N;
+  const float scale = __expf(fminf(logit_scale[head], 4.6051702f));
+  const int total_windows = g.B * g.nwy * g.nwx;
+  const int total_pairs = (total_windows + 1) / 2;
+
+  // one-time: zero every operand tile (pad rows / pad columns are never written again), barriers, TMEM, bias table
+  for (int i = r; i < (16384 * 2 + 16384 + 32768) / 16; i += kTcThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = r; i < N * N; i += kTcThreads) sbias[i] = bias[(long long)head * N * N + i];
+  if (r == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = *tmem_slot;        // S: columns [0, 128)
+  const uint32_t tmem_o = tmem_s + 128;      // O: columns [128, 192)
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+  const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+
+  uint32_t phase = 0;
+  for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
+    // ---- gather this row's token, normalise q / k, write the operand rows
+    const int w = pair * 2 + prob;
+    const bool valid = tok_ok && w < total_windows;
+    long long my_row = 0;
+    int region = 0;
+    uint4 qraw[4], kraw[4], vraw[4];
+    if (valid) {
+      const int wx = w % g.nwx, wy = (w / g.nwx) % g.nwy, b = w / (g.nwx * g.nwy);
+      my_row = token_row(g, b, wy, wx, t, region);
+      const uint4* base = reinterpret_cast<const uint4*>(qkv + my_row * 3 * g.C + head * kHd);
+      const int cstep = g.C / 8;  // uint4 per C bf16
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        qraw[c] = __ldg(base + c);
+        kraw[c] = __ldg(base + cstep + c);
+        vraw[c] = __ldg(base + 2 * cstep + c);
+      }
+      float qq = 0.f, kk = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t qw[4] = {qraw[c].x, qraw[c].y, qraw[c].z, qraw[c].w};
+        const uint32_t kw[4] = {kraw[c].x, kraw[c].y, kraw[c].z, kraw[c].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          qq = fmaf(bf16_lo(qw[e]), bf16_lo(qw[e]), fmaf(bf16_hi(qw[e]), bf16_hi(qw[e]), qq));
+          kk = fmaf(bf16_lo(kw[e]), bf16_lo(kw[e]), fmaf(bf16_hi(kw[e]), bf16_hi(kw[e]), kk));
+        }
+      }
+      const float qi = 1.f / fmaxf(sqrtf(qq), 1e-12f), ki = 1.f / fmaxf(sqrtf(kk), 1e-12f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t qw[4] = {qraw[c].x, qraw[c].y, qraw[c].z, qraw[c].w};
+        const uint32_t kw[4] = {kraw[c].x, kraw[c].y, kraw[c].z, kraw[c].w};
+        uint32_t qo[4], ko[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          qo[e] = pack_bf16x2(bf16_lo(qw[e]) * qi, bf16_hi(qw[e]) * qi);
+          ko[e] = pack_bf16x2(bf16_lo(kw[e]) * ki, bf16_hi(kw[e]) * ki);
+        }
+        sts128(aQ + sw128_off(r, c), make_uint4(qo[0], qo[1], qo[2], qo[3]));
+        sts128(aK + sw128_off(r, c), make_uint4(ko[0], ko[1], ko[2], ko[3]));
+        sts128(aV + prob * 8192 + sw128_off(t, c), vraw[c]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        sts128(aQ + sw128_off(r, c), make_uint4(0, 0, 0, 0));
+        sts128(aK + sw128_off(r, c), make_uint4(0, 0, 0, 0));
+        sts128(aV + prob * 8192 + sw128_off(t, c), make_uint4(0, 0, 0, 0));
+      }
+    }
+    sreg[r] = region;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- S = Qhat . Khat^T
+    if (r == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
+                  idesc_s, k);
+      umma_commit(&bar[0]);
+    }
+    mbar_wait(&bar[0], phase);
+    tc_fence_after();
+    // ---- softmax of this row over its own window's keys
+    float p[kMaxN];
+    {
+      uint32_t raw[32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + prob * 64 + half * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = half * 32 + j;
+          float sc = -INFINITY;
+          if (key < N && valid)
+            sc = __uint_as_float(raw[j]) * scale + sbias[t * N + key] + (sreg[prob * 64 + key] != region ? -100.f : 0.f);
+          p[key] = sc;
+          mx = fmaxf(mx, sc);
+        }
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxN; ++j) {
+        p[j] = (j < N && valid) ? __expf(p[j] - mx) : 0.f;
+        l += p[j];
+      }
+      const float inv = valid ? 1.f / l : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o4[e] = pack_bf16x2(p[c * 8 + 2 * e] * inv, p[c * 8 + 2 * e + 1] * inv);
+        sts128(aP + prob * 16384 + sw128_off(r, c), make_uint4(o4[0], o4[1], o4[2], o4[3]));
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- O = [P_A; 0] . V_A + [0; P_B] . V_B
+    if (r == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_o, make_smem_desc_sw128(aP + kb * 16384 + k * 32, 16, 1024),
+                    make_smem_desc_sw128(aV + kb * 8192 + k * 2048, 8192, 1024), idesc_o, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&bar[1]);
+    }
+    mbar_wait(&bar[1], phase);
+    tc_fence_after();
+    {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(tmem_o + lane_addr, raw);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* op = reinterpret_cast<uint4*>(out + my_row * g.C + head * kHd);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          op[c] = make_uint4(pack_bf16x2(__uint_as_float(raw[c * 8]), __uint_as_float(raw[c * 8 + 1])),
+                             pack_bf16x2(__uint_as_float(raw[c * 8 + 2]), __uint_as_float(raw[c * 8 + 3])),
+                             pack_bf16x2(__uint_as_float(raw[c * 8 + 4]), __uint_as_float(raw[c * 8 + 5])),
+                             pack_bf16x2(__uint_as_float(raw[c * 8 + 6]), __uint_as_float(raw[c * 8 + 7])));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM and the operand tiles are free for the next pair
+    tc_fence_after();
+  }
+  if (warp == 0) tmem_dealloc(tmem_s, 256);
+}
+
 // Backward.  One CTA per (head, group); the CTA loops over the windows of its group so that the bias / logit-scale
 // gradients accumulate on chip and are flushed once.  Pass 1 (thread = query row i): softmax statistics, O_i,
 // delta_i = dO_i . O_i, dq_i.  Pass 2 (thread = key row j): dk_j, dv_j, dbias[:, j].  Row vectors live in registers,
@@ -535,6 +740,22 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
   AttnGeom g;
   int rc = attn_geom(&g, B, H, W, C, heads, ws, shift);
   if (rc) return rc;
+  static const bool use_cuda_cores = getenv("TOK_ATTN_CUDA_CORES") != nullptr;  // bring-up aid: the round-1 fp32 kernel
+  if (!use_cuda_cores && (C % 8) == 0) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(window_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+      if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_fwd: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    const int pairs = (B * g.nwy * g.nwx + 1) / 2;
+    int groups = (148 * 2 + heads - 1) / heads;
+    if (groups > pairs) groups = pairs;
+    window_attn_fwd_tc_kernel<<<(unsigned)(groups * heads), kTcThreads, kTcSmem, (cudaStream_t)stream>>>(
+        g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out);
+    TOK_CHECK_LAUNCH("window_attn_fwd_tc");
+    return TOK_OK;
+  }
   const long long ctas = (long long)B * g.nwy * g.nwx * heads;
   window_attn_fwd_kernel<<<(unsigned)ctas, 64, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)qkv, logit_scale, bias,
                                                                          (__nv_bfloat16*)out);
