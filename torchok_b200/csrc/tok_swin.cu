@@ -10,8 +10,8 @@
 // The roll / window_partition / window_reverse copies of the reference are index arithmetic here: a window's tokens are
 // gathered from and scattered to their home positions in the (B, H, W, 3C) qkv tensor.
 //
-// Round-1 note: the attention kernel is a CUDA-core kernel (one thread per query row, window <= 8x8); the tcgen05 version
-// named by the north star is the next step for this path.
+// Forward attention runs on tcgen05 (window_attn_fwd_tc_kernel: two windows stacked into one 128-row UMMA tile, S and O
+// in TMEM); the backward and the TOK_ATTN_CUDA_CORES=1 forward are CUDA-core kernels (one thread per row, window <= 8x8).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>

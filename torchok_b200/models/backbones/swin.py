@@ -11,7 +11,8 @@ LayerNorm.  Parameter names follow timm (`layers.0.blocks.1.attn.cpb_mlp.0.weigh
 Execution: tokens live as one (B*H*W, C) bf16 matrix (= the NHWC grid).  Linear layers run on the tcgen05 GEMM
 (tok_linear_*), LayerNorm + residual (+ stochastic depth scale) is one pass (tok_layernorm_*), GELU one pass, and the
 whole attention core of a block — normalise q/k, logits, bias, shift mask, softmax, PV, with the cyclic shift and the
-window partition folded into its addressing — is one kernel (tok_window_attn_*; round 1: CUDA cores, window <= 8).
+window partition folded into its addressing — is one kernel (tok_window_attn_*: forward on tcgen05 with S and O in
+TMEM, backward on CUDA cores; window <= 8).
 The 169 x 2 -> 512 -> heads cpb MLP that produces the bias table is evaluated with torch ops (a few kFLOP).
 """
 import math
