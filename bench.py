@@ -176,7 +176,11 @@ def time_dominant_kernel(batch, sustained_tf):
     flops = 2.0 * n * p * q * k * 9 * c
     ach = flops / (ms * 1e-3) / 1e12
     return {'bound': 'tensor', 'achieved': ach, 'peak': sustained_tf, 'unit': 'TFLOP/s', 'frac': ach / sustained_tf,
-            'traffic': None, 'kernel': 'conv_fwd_kernel<128,3,false> fprop 3x3 256->256 @14x14',
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from profiles/r1_roofline_kernel_full.md
+            # (ncu --set full, scripts/roofline_kernel.py): 26.94 MB read + 0.11 MB written — the 25.7 MB output tile
+            # stream stays in the 126 MB L2; algorithmic bytes are 25.7 (x) + 25.7 (y) + 1.2 (w) MB.
+            'traffic': 27.05e6 if n == 256 else None, 'traffic_unit': 'B',
+            'kernel': 'conv_fwd_persist_kernel<256,3,0,1,0> fprop 3x3 256->256 @14x14',
             'ms_per_launch': ms, 'flop_per_launch': flops}
 
 
