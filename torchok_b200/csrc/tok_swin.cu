@@ -659,6 +659,301 @@ window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// tcgen05 backward: all five contractions of the attention backward on the tensor cores, in ONE kernel.
+// A CTA (512 threads) owns one head and walks pairs of windows stacked along M exactly like the forward kernel.
+// Thread (r, h): r = stacked token row 0..127 (= TMEM lane), h = warp >> 2 = which quarter of the row's 64 key columns
+// it owns in the softmax phase / which tensor it gathers (q, k, v, dO) / which gradient it finishes (dq, dk, dv).
+//   round 1   S  [128 x 128] = Qhat . Khat^T          dP [128 x 128] = dO . V^T              (K = 32, K-major operands)
+//   registers P = softmax(S * scale + bias + mask), delta = sum_j P dP, dS = P o (dP - delta); the four threads of a
+//             row merge their (max, sum, sum P~ dP) partials through shared memory once (online-softmax merge);
+//             dbias and dlogit_scale accumulate in registers across all windows of the CTA
+//   round 2   dV [128 x 32] = P^T . dO    dKhat = dS^T . Qhat   (A = the bf16 P / dS tiles read MN-major, K = 128 rows)
+//             dQhat [128 x 32] = dS . Khat                      (A K-major block-diagonal halves, as P . V in forward)
+//   epilogue  through the cosine normalisation: dq = scale * (dQhat - qhat (qhat . dQhat)) / |q|, same for k.
+// The next pair's rows are prefetched into registers while round 2 runs.
+constexpr int kBwThreads = 512;
+constexpr int kBwTiles = 8 * 16384;  // sQ sK sV sDO, sP[2], sDS[2]
+constexpr int kBwSmem = kBwTiles + kMaxN * kMaxN * 4 + 128 * 4 * 16 + 128 * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(kBwThreads, 1)
+window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
+                          const float* __restrict__ logit_scale, const float* __restrict__ bias,
+                          const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
+                          float* __restrict__ dbias, float* __restrict__ dlogit_scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t aQ = smem_u32(smem), aK = aQ + 16384, aV = aK + 16384, aDO = aV + 16384;
+  const uint32_t aP = aDO + 16384, aDS = aP + 32768;
+  const uint32_t aBias = aDS + 32768;                 // float [N][N]
+  const uint32_t aX = aBias + kMaxN * kMaxN * 4;      // float4 [128 rows][4 quarters]: (max, sum, sum p~ dP, -)
+  const uint32_t aReg = aX + 128 * 4 * 16;            // int [128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (aReg - aQ) + 128 * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+  const int N = g.ws * g.ws;
+  const int head = blockIdx.x % g.heads;
+  const int grp = blockIdx.x / g.heads;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int h = warp >> 2;                      // column quarter / role
+  const int r = (warp & 3) * 32 + (tid & 31);   // stacked row = TMEM lane
+  const int prob = r >> 6;
+  const int t = r & 63;
+  const float ls = logit_scale[head];
+  const float scale = __expf(fminf(ls, 4.6051702f));
+  const int total_windows = g.B * g.nwy * g.nwx;
+  const int total_pairs = (total_windows + 1) / 2;
+
+  for (int i = tid; i < kBwTiles / 16; i += kBwThreads) sts128(aQ + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < N * N; i += kBwThreads) sts_f32(aBias + i * 4, bias[(long long)head * N * N + i]);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;  // S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_mm = make_idesc_bf16(128, 64, true, true);
+  constexpr uint32_t idesc_km = make_idesc_bf16(128, 64, false, true);
+  const uint32_t my_tile = aQ + h * 16384;  // tile this thread fills in the gather (q, k, v, dO by role)
+
+  float db[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) db[j] = 0.f;
+  float dls = 0.f;
+
+  // ---- rows of a pair: token position, validity, mask region; raw 64 bytes of this role's tensor
+  uint4 raw[4];
+  long long nrow = 0;
+  int nregion = 0;
+  bool nvalid = false;
+  auto fetch = [&](int pair) {
+    const int w = pair * 2 + prob;
+    nvalid = t < N && pair < total_pairs && w < total_windows;
+    nrow = 0;
+    nregion = 0;
+    if (nvalid) {
+      const int wx = w % g.nwx, wy = (w / g.nwx) % g.nwy, b = w / (g.nwx * g.nwy);
+      nrow = token_row(g, b, wy, wx, t, nregion);
+      const uint4* src = h < 3 ? reinterpret_cast<const uint4*>(qkv + nrow * 3 * g.C + h * g.C + head * kHd)
+                               : reinterpret_cast<const uint4*>(dout + nrow * g.C + head * kHd);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) raw[c] = __ldg(src + c);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) raw[c] = make_uint4(0, 0, 0, 0);
+    }
+  };
+  fetch(grp);
+
+  uint32_t phase = 0;
+  for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
+    const long long row = nrow;
+    const int region = nregion;
+    const bool valid = nvalid;
+    float inv_norm = 0.f;  // 1 / |q| or 1 / |k| (roles 0, 1)
+    // ---- stage this role's operand row (q and k normalised)
+    if (h < 2) {
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t wv[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ss = fmaf(bf16_lo(wv[e]), bf16_lo(wv[e]), fmaf(bf16_hi(wv[e]), bf16_hi(wv[e]), ss));
+      }
+      inv_norm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t wv[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(bf16_lo(wv[e]) * inv_norm, bf16_hi(wv[e]) * inv_norm);
+        sts128(my_tile + sw128_off(r, c), make_uint4(o[0], o[1], o[2], o[3]));
+      }
+      if (h == 0) sts_f32(aReg + r * 4, __int_as_float(region));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sts128(my_tile + sw128_off(r, c), raw[c]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- round 1: S = Qhat Khat^T, dP = dO V^T
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        umma_bf16(tmem, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
+                  idesc_kk, k);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        umma_bf16(tmem + 128, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024),
+                  idesc_kk, k);
+      umma_commit(&bar[0]);
+    }
+    mbar_wait(&bar[0], phase);
+    tc_fence_after();
+    // ---- softmax statistics of this quarter-row, merged across the four quarters
+    uint32_t sraw[16], graw[16];
+    tmem_ld_32x32b_x16(tmem + lane_addr + prob * 64 + h * 16, sraw);
+    tmem_ld_32x32b_x16(tmem + 128 + lane_addr + prob * 64 + h * 16, graw);
+    tmem_ld_wait();
+    float e[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int key = h * 16 + j;
+      float sc = -INFINITY;
+      if (valid && key < N) {
+        const int kreg = __float_as_int(lds_f32(aReg + (prob * 64 + key) * 4));
+        sc = fmaf(__uint_as_float(sraw[j]), scale, lds_f32(aBias + (t * N + key) * 4)) + (kreg != region ? -100.f : 0.f);
+      }
+      e[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    float lsum = 0.f, dsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      e[j] = mx > -INFINITY ? __expf(e[j] - mx) : 0.f;   // exp(-inf) = 0 for the padded / foreign keys
+      lsum += e[j];
+      dsum = fmaf(e[j], __uint_as_float(graw[j]), dsum);
+    }
+    sts128(aX + (r * 4 + h) * 16, make_uint4(__float_as_uint(mx), __float_as_uint(lsum), __float_as_uint(dsum), 0u));
+    __syncthreads();
+    float factor = 0.f, delta = 0.f;
+    {
+      uint4 x[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) x[q4] = lds128(aX + (r * 4 + q4) * 16);
+      float m = -INFINITY;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) m = fmaxf(m, __uint_as_float(x[q4].x));
+      float l = 0.f, d = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float mq = __uint_as_float(x[q4].x);
+        const float f = mq > -INFINITY ? __expf(mq - m) : 0.f;
+        l = fmaf(__uint_as_float(x[q4].y), f, l);
+        d = fmaf(__uint_as_float(x[q4].z), f, d);
+      }
+      if (valid && l > 0.f) {
+        const float inv = 1.f / l;
+        delta = d * inv;
+        factor = mx > -INFINITY ? __expf(mx - m) * inv : 0.f;
+      }
+    }
+    // ---- P and dS of this quarter-row: bf16 tiles for round 2, dbias / dlogit_scale partials in registers
+    {
+      uint32_t pp[8], dd[8];
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float p0 = e[j] * factor, p1 = e[j + 1] * factor;
+        const float d0 = p0 * (__uint_as_float(graw[j]) - delta), d1 = p1 * (__uint_as_float(graw[j + 1]) - delta);
+        db[j] += d0;
+        db[j + 1] += d1;
+        dls = fmaf(d0, __uint_as_float(sraw[j]), fmaf(d1, __uint_as_float(sraw[j + 1]), dls));
+        pp[j >> 1] = pack_bf16x2(p0, p1);
+        dd[j >> 1] = pack_bf16x2(d0, d1);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        sts128(aP + prob * 16384 + sw128_off(r, 2 * h + c), make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]));
+        sts128(aDS + prob * 16384 + sw128_off(r, 2 * h + c), make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]));
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- round 2
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // dV = P^T dO: K = the 128 stacked query rows
+        umma_bf16(tmem + 384, make_smem_desc_sw128(aP + k * 2048, 16384, 1024),
+                  make_smem_desc_sw128(aDO + k * 2048, 8192, 1024), idesc_mm, k);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // dKhat = dS^T Qhat
+        umma_bf16(tmem + 320, make_smem_desc_sw128(aDS + k * 2048, 16384, 1024),
+                  make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), idesc_mm, k);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)   // dQhat = dS Khat, block-diagonal halves
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + 256, make_smem_desc_sw128(aDS + kb * 16384 + k * 32, 16, 1024),
+                    make_smem_desc_sw128(aK + kb * 8192 + k * 2048, 8192, 1024), idesc_km, (kb | k) != 0 ? 1u : 0u);
+      umma_commit(&bar[1]);
+    }
+    fetch(pair + groups);   // the next pair's rows travel while round 2 runs
+    mbar_wait(&bar[1], phase);
+    tc_fence_after();
+    if (h < 3) {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(tmem + 256 + h * 64 + lane_addr, acc);
+      tmem_ld_wait();
+      if (valid) {
+        float mul = 1.f;
+        if (h < 2) {
+          // through x_hat = x / |x|:  dx = (dx_hat - x_hat (x_hat . dx_hat)) / |x|, with the logit scale folded in
+          uint4 hat[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) hat[c] = lds128(my_tile + sw128_off(r, c));
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t wv[4] = {hat[c].x, hat[c].y, hat[c].z, hat[c].w};
+#pragma unroll
+            for (int q2 = 0; q2 < 4; ++q2)
+              dot = fmaf(bf16_lo(wv[q2]), __uint_as_float(acc[c * 8 + 2 * q2]),
+                         fmaf(bf16_hi(wv[q2]), __uint_as_float(acc[c * 8 + 2 * q2 + 1]), dot));
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t wv[4] = {hat[c].x, hat[c].y, hat[c].z, hat[c].w};
+#pragma unroll
+            for (int q2 = 0; q2 < 4; ++q2) {
+              acc[c * 8 + 2 * q2] = __float_as_uint(fmaf(-bf16_lo(wv[q2]), dot, __uint_as_float(acc[c * 8 + 2 * q2])));
+              acc[c * 8 + 2 * q2 + 1] = __float_as_uint(fmaf(-bf16_hi(wv[q2]), dot, __uint_as_float(acc[c * 8 + 2 * q2 + 1])));
+            }
+          }
+          mul = scale * inv_norm;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(dqkv + row * 3 * g.C + h * g.C + head * kHd);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_uint4(pack_bf16x2(__uint_as_float(acc[c * 8]) * mul, __uint_as_float(acc[c * 8 + 1]) * mul),
+                              pack_bf16x2(__uint_as_float(acc[c * 8 + 2]) * mul, __uint_as_float(acc[c * 8 + 3]) * mul),
+                              pack_bf16x2(__uint_as_float(acc[c * 8 + 4]) * mul, __uint_as_float(acc[c * 8 + 5]) * mul),
+                              pack_bf16x2(__uint_as_float(acc[c * 8 + 6]) * mul, __uint_as_float(acc[c * 8 + 7]) * mul));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM and every operand tile are free for the next pair
+    tc_fence_after();
+  }
+  // ---- flush the on-chip accumulators: d bias[head][t][key], d logit_scale[head] (zero while the clamp is active)
+  if (t < N) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int key = h * 16 + j;
+      if (key < N) atomicAdd(dbias + ((long long)head * N + t) * N + key, db[j]);
+    }
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) dls += __shfl_xor_sync(0xffffffffu, dls, s);
+  if ((tid & 31) == 0 && ls < 4.6051702f) atomicAdd(dlogit_scale + head, dls * scale);
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 }  // namespace tok
 
@@ -749,7 +1044,8 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
       configured = true;
     }
     const int pairs = (B * g.nwy * g.nwx + 1) / 2;
-    int groups = (148 * 2 + heads - 1) / heads;
+    int groups = (148 * 2) / heads;   // two CTAs per SM (shared memory); one more CTA would be a second wave
+    if (groups < 1) groups = 1;
     if (groups > pairs) groups = pairs;
     window_attn_fwd_tc_kernel<<<(unsigned)(groups * heads), kTcThreads, kTcSmem, (cudaStream_t)stream>>>(
         g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out);
@@ -770,6 +1066,24 @@ int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift
   int rc = attn_geom(&g, B, H, W, C, heads, ws, shift);
   if (rc) return rc;
   const int windows = B * g.nwy * g.nwx;
+  const char* cc = getenv("TOK_ATTN_BWD_CUDA_CORES");  // bring-up aid: the round-1 fp32 kernel (read per call)
+  if (!(cc && cc[0] == '1') && (C % 8) == 0) {
+    static bool configured_tc = false;
+    if (!configured_tc) {
+      cudaError_t e = cudaFuncSetAttribute(window_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmem);
+      if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_bwd_tc: %s", cudaGetErrorString(e));
+      configured_tc = true;
+    }
+    const int pairs = (windows + 1) / 2;
+    int groups = 148 / heads;   // one CTA per SM (shared memory), never a second wave
+    if (groups < 1) groups = 1;
+    if (groups > pairs) groups = pairs;
+    window_attn_bwd_tc_kernel<<<(unsigned)(groups * heads), kBwThreads, kBwSmem, (cudaStream_t)stream>>>(
+        g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
+        dlogit_scale);
+    TOK_CHECK_LAUNCH("window_attn_bwd_tc");
+    return TOK_OK;
+  }
   int groups = (148 * 16 + heads - 1) / heads;
   if (groups > windows) groups = windows;
   static bool configured = false;
