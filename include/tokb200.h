@@ -164,25 +164,32 @@ int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const lo
 /* ---- Swin-V2 passes (tok_swin.cu; timm swin_transformer_v2 semantics used by torchok/models/backbones/swin.py:71-81) ------
  * LayerNorm over the last dimension of a (rows, C) bf16 matrix, C <= 1024; with `residual` the output is
  * residual + rowscale[row / rows_per_sample] * LN(x) (res-post-norm block tail with stochastic depth; rowscale nullable).
- * Backward: dx for the LN input (the residual gradient is dout itself); dgamma / dbeta are atomically ACCUMULATED. */
+ * Backward: dx for the LN input (the residual gradient is dout itself); dgamma / dbeta are atomically ACCUMULATED.
+ * `dxsum` (nullable, C floats, ACCUMULATED): column sums of dx = the bias gradient of the torch.nn.Linear whose output
+ * this LayerNorm consumed (timm Mlp.fc2 / WindowAttention.proj), saving that layer's own pass over dx; only for widths
+ * with tok_layernorm_has_dxsum(C) == 1 (C = 8 * {1,2,3,4} * {4,8,16,32}, i.e. every Swin width). */
 int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, const float* beta, float eps,
                       const void* residual, const float* rowscale, int rows_per_sample, void* out, float* mean,
                       float* rstd, void* stream);
 int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, const float* mean, const float* rstd,
                       const void* dout, const float* rowscale, int rows_per_sample, void* dx, float* dgamma,
-                      float* dbeta, void* stream);
-/* exact (erf) GELU of timm's Mlp */
+                      float* dbeta, float* dxsum, void* stream);
+int tok_layernorm_has_dxsum(int C);
+/* exact (erf) GELU of timm's Mlp (Mlp.act between fc1 and fc2).  Backward over an (n / C, C) matrix; `dbias` (nullable,
+ * C floats, ACCUMULATED, needs C % 128 == 0) receives the column sums of dx = the bias gradient of Mlp.fc1. */
 int tok_gelu_fwd(long long n, const void* x, void* y, void* stream);
-int tok_gelu_bwd(long long n, const void* x, const void* dy, void* dx, void* stream);
+int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, float* dbias, void* stream);
 /* WindowAttention.forward on the (B, H, W, 3C) qkv tensor ([3][heads][32] per token): cosine attention with
  * exp(min(logit_scale, ln 100)), additive bias[heads][N][N], shifted-window mask (-100) computed from `shift`; windows are
  * gathered from / scattered to their home positions (no roll / partition copies).  window <= 8, head_dim == 32.
- * Backward recomputes the probabilities; dbias / dlogit_scale are atomically ACCUMULATED. */
+ * Backward (tcgen05: S, dP, dV, dK, dQ as UMMA chains, P / dS kept on chip) recomputes the probabilities; dbias /
+ * dlogit_scale are atomically ACCUMULATED.  `dqkv_colsum` (nullable, 3C floats, ACCUMULATED; the k third is left
+ * untouched): column sums of dq and dv = the q_bias / v_bias gradients of timm's WindowAttention.qkv. */
 int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift, const void* qkv,
                         const float* logit_scale, const float* bias, void* out, void* stream);
 int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift, const void* qkv,
                         const float* logit_scale, const float* bias, const void* dout, void* dqkv, float* dbias,
-                        float* dlogit_scale, void* stream);
+                        float* dlogit_scale, float* dqkv_colsum, void* stream);
 
 /* ---- HRNet / segmentation passes (tok_seg.cu) ---------------------------------------------------------------------------
  * timm HighResolutionModule fuse (torchok/models/backbones/hrnet.py:167-192): out = relu(sum_t nearest_up(term_t)), term t

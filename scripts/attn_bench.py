@@ -40,7 +40,7 @@ def bwd(mode):
     dls = torch.zeros_like(ls)
     os.environ['TOK_ATTN_BWD_CUDA_CORES'] = '1' if mode else '0'
     L.tok_window_attn_bwd(B, H, H, C, heads, ws, shift, _p(qkv), _p(ls), _p(bias), _p(g), _p(dqkv), _p(dbias), _p(dls),
-                          _st())
+                          None, _st())
     return dqkv, dbias, dls
 
 

@@ -39,15 +39,42 @@ def test_layernorm_residual(rows, c, res):
         assert rel_err(rm.grad, ro.grad) < 1e-2
 
 
-def test_gelu():
+@pytest.mark.parametrize('rows,c', [(128, 96), (100, 256), (37, 384)])
+def test_gelu(rows, c):
+    """exact-erf GELU; for C % 128 == 0 the backward also returns the column sums of dx (Mlp.fc1's bias gradient)."""
     from torchok_b200 import kernels as K
-    x = _bf(torch.randn(128, 96) * 2)
+    torch.manual_seed(c)
+    x = _bf(torch.randn(rows, c) * 2)
     xo, xm = x.clone().requires_grad_(True), x.cuda().requires_grad_(True)
     g = _bf(torch.randn_like(x))
     (F.gelu(xo) * g).sum().backward()
-    ym = K.gelu(xm.to(torch.bfloat16))
+    fused = K.gelu_fuses_colsum(c)
+    bias = torch.zeros(c, device='cuda', requires_grad=True)
+    ym = K.gelu(xm.to(torch.bfloat16), bias if fused else None)
     (ym.float() * g.cuda()).sum().backward()
     assert rel_err(ym, F.gelu(x)) < 1e-2 and rel_err(xm.grad, xo.grad) < 1e-2
+    if fused:
+        assert rel_err(bias.grad, xo.grad.sum(0)) < 1e-2
+
+
+@pytest.mark.parametrize('rows,c', [(70, 96), (33, 384), (9, 1024)])
+def test_layernorm_colsum(rows, c):
+    """LayerNorm backward also accumulates the column sums of dx into the bias of the linear layer feeding it."""
+    from torchok_b200 import kernels as K
+    assert K.layernorm_fuses_colsum(c)
+    torch.manual_seed(rows)
+    x = _bf(torch.randn(rows, c) * 3 - 1)
+    w, b = torch.rand(c) + 0.5, torch.randn(c) * 0.1
+    xo = x.clone().requires_grad_(True)
+    g = _bf(torch.randn(rows, c))
+    (F.layer_norm(xo, (c,), w, b) * g).sum().backward()
+    xm = x.cuda().requires_grad_(True)
+    wm, bm = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    lin_bias = torch.zeros(c, device='cuda', requires_grad=True)
+    ym = K.layernorm(xm.to(torch.bfloat16), wm, bm, 1e-5, colsum_param=lin_bias)
+    (ym.float() * g.cuda()).sum().backward()
+    assert rel_err(xm.grad, xo.grad) < 1e-2
+    assert rel_err(lin_bias.grad, xo.grad.sum(0)) < 1e-2
 
 
 @pytest.mark.parametrize('dim,heads,res,ws,shift', [(96, 3, 8, 4, 0), (96, 3, 8, 4, 2), (64, 2, 14, 7, 3), (192, 6, 8, 8, 0),

@@ -72,11 +72,12 @@ _SIGS = {
     'tok_gap_bwd': (_i, [_i, _i, _i, _vp, _vp, _vp]),
     'tok_softmax_xent': (_i, [_i, _i, _ll, _vp, _vp, _vp, _vp, _f, _f, _vp, _ll, _vp, _vp]),
     'tok_layernorm_fwd': (_i, [_ll, _i, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    'tok_layernorm_bwd': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    'tok_layernorm_bwd': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    'tok_layernorm_has_dxsum': (_i, [_i]),
     'tok_gelu_fwd': (_i, [_ll, _vp, _vp, _vp]),
-    'tok_gelu_bwd': (_i, [_ll, _vp, _vp, _vp, _vp]),
+    'tok_gelu_bwd': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp]),
     'tok_window_attn_fwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    'tok_window_attn_bwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_window_attn_bwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_fuse_sum_fwd': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     'tok_fuse_sum_bwd': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_bilinear_fwd': (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
@@ -99,7 +100,7 @@ _SIGS = {
     'tok_adam_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
 }
-_RAW = {'tok_debug_conv_profile', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+_RAW = {'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}
 
 

@@ -139,15 +139,216 @@ layernorm_bwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
   }
 }
 
+// Vector path for C = 8 * CH * G (every Swin width: 96 * 2^k = 8 * 3 * G): a row is owned by G lanes, each holding CH
+// 16-byte chunks (chunk index = lane_in_group + i * G, so a group reads consecutive 16-byte pieces); a warp works on
+// 32 / G rows at once and walks the matrix with a grid stride.  Same arithmetic as the scalar kernels above.
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+template <int G, int CH>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ res,
+                         const float* __restrict__ rowscale, int rows_per_sample, __nv_bfloat16* __restrict__ out,
+                         float* __restrict__ mean, float* __restrict__ rstd) {
+  constexpr int C = 8 * CH * G;
+  constexpr int RPW = 32 / G;  // rows per warp pass
+  const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
+  const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp_id * RPW + sub; r < rows; r += warps * RPW) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + r * C);
+    float v[CH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      unpack8(__ldg(xr + l + i * G), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+    const float mu = group_sum<G>(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mu;
+        q = fmaf(d, d, q);
+      }
+    const float rs = rsqrtf(group_sum<G>(q) * (1.f / C) + eps);
+    const float sc = rowscale ? rowscale[r / rows_per_sample] : 1.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c0 = (l + i * G) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = fmaf((v[i][e] - mu) * rs, gm[e], bt[e]);
+      if (res) {
+        float rr[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(res + r * C) + l + i * G), rr);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = fmaf(sc, y[e], rr[e]);
+      }
+      reinterpret_cast<uint4*>(out + r * C)[l + i * G] = pack8(y);
+    }
+    if (l == 0) {
+      mean[r] = mu;
+      rstd[r] = rs;
+    }
+  }
+}
+
+// Backward, vector path.  Per-thread column partials (dgamma, dbeta and, when asked, the column sums of dx = the bias
+// gradient of the linear layer that produced x) stay in registers over the whole grid-stride walk.
+template <int G, int CH>
+__global__ void __launch_bounds__(128, CH >= 3 ? 3 : 4)
+layernorm_bwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const __nv_bfloat16* __restrict__ dout, const float* __restrict__ rowscale, int rows_per_sample,
+                         __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         float* __restrict__ dxsum) {
+  constexpr int C = 8 * CH * G;
+  constexpr int RPW = 32 / G;
+  extern __shared__ float sh[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
+  const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  // the row stays in registers as the packed bf16 it arrived in (x, dout: 8 words per chunk); gamma comes from L1
+  float ag[CH][8], ab[CH][8], ax[CH][8];
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ag[i][e] = ab[i][e] = ax[i][e] = 0.f;
+  for (long long r = warp_id * RPW + sub; r < rows; r += warps * RPW) {
+    uint4 xr[CH], gr[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      xr[i] = __ldg(reinterpret_cast<const uint4*>(x + r * C) + l + i * G);
+      gr[i] = __ldg(reinterpret_cast<const uint4*>(dout + r * C) + l + i * G);
+    }
+    const float mu = mean[r], rs = rstd[r];
+    const float sc = rowscale ? rowscale[r / rows_per_sample] : 1.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c0 = (l + i * G) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float xv[8], gv[8];
+      unpack8(xr[i], xv);
+      unpack8(gr[i], gv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xv[e] - mu) * rs;
+        const float g = sc * gv[e];
+        ag[i][e] = fmaf(g, xh, ag[i][e]);
+        ab[i][e] += g;
+        const float gg = g * gm[e];
+        s1 += gg;
+        s2 = fmaf(gg, xh, s2);
+      }
+    }
+    s1 = group_sum<G>(s1) * (1.f / C);
+    s2 = group_sum<G>(s2) * (1.f / C);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c0 = (l + i * G) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float xv[8], gv[8], d[8];
+      unpack8(xr[i], xv);
+      unpack8(gr[i], gv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xv[e] - mu) * rs;
+        d[e] = rs * (sc * gv[e] * gm[e] - s1 - xh * s2);
+        ax[i][e] += d[e];
+      }
+      reinterpret_cast<uint4*>(dx + r * C)[l + i * G] = pack8(d);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (l + i * G) * 8 + e;
+      atomicAdd(&sh[c], ag[i][e]);
+      atomicAdd(&sh[C + c], ab[i][e]);
+      if (dxsum) atomicAdd(&sh[2 * C + c], ax[i][e]);
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + c, sh[c]);
+    if (dbeta) atomicAdd(dbeta + c, sh[C + c]);
+    if (dxsum) atomicAdd(dxsum + c, sh[2 * C + c]);
+  }
+}
+
+// (G, CH) with C == 8 * CH * G, G in {4, 8, 16, 32}, CH in {3, 4, 2, 1}; false if the width has no vector path
+inline bool ln_vec_shape(int C, int* G, int* CH) {
+  if (C % 8) return false;
+  const int chunks = C / 8;
+  const int chs[4] = {3, 4, 2, 1};
+  for (int i = 0; i < 4; ++i) {
+    if (chunks % chs[i]) continue;
+    const int g = chunks / chs[i];
+    if (g == 4 || g == 8 || g == 16 || g == 32) {
+      *G = g;
+      *CH = chs[i];
+      return true;
+    }
+  }
+  return false;
+}
+
 // ---- GELU (exact, erf) ---------------------------------------------------------------------------------------------
+// erf through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution): one reciprocal, one exp2 and
+// five FMAs instead of the ~30-instruction erff, which made these passes compute-bound.  exp(-v^2/2) is shared
+// between erf(v / sqrt 2) and the Gaussian density of the derivative.
+__device__ __forceinline__ void gelu_parts(float v, float& cdf, float& pdf) {
+  const float a = fabsf(v) * 0.70710678f;
+  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.f));
+  const float ex = __expf(-a * a);  // = exp(-v^2 / 2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.f - poly * t * ex;
+  cdf = 0.5f * (1.f + copysignf(erf_abs, v));
+  pdf = 0.39894228f * ex;
+}
+__device__ __forceinline__ float gelu_value(float v) {
+  float cdf, pdf;
+  gelu_parts(v, cdf, pdf);
+  return v * cdf;
+}
+__device__ __forceinline__ float gelu_grad(float v) {
+  float cdf, pdf;
+  gelu_parts(v, cdf, pdf);
+  return fmaf(v, pdf, cdf);
+}
 __global__ void gelu_fwd_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloat162* __restrict__ y, long long n2) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const float2 v = __bfloat1622float2(x[i]);
-    y[i] = __floats2bfloat162_rn(0.5f * v.x * (1.f + erff(v.x * 0.70710678f)), 0.5f * v.y * (1.f + erff(v.y * 0.70710678f)));
+    y[i] = __floats2bfloat162_rn(gelu_value(v.x), gelu_value(v.y));
   }
-}
-__device__ __forceinline__ float gelu_grad(float v) {
-  return 0.5f * (1.f + erff(v * 0.70710678f)) + v * 0.39894228f * __expf(-0.5f * v * v);
 }
 __global__ void gelu_bwd_kernel(const __nv_bfloat162* __restrict__ x, const __nv_bfloat162* __restrict__ dy,
                                 __nv_bfloat162* __restrict__ dx, long long n2) {
@@ -155,6 +356,52 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat162* __restrict__ x, const __nv
     const float2 v = __bfloat1622float2(x[i]);
     const float2 g = __bfloat1622float2(dy[i]);
     dx[i] = __floats2bfloat162_rn(g.x * gelu_grad(v.x), g.y * gelu_grad(v.y));
+  }
+}
+// 16-byte version (n % 8 == 0)
+__global__ void __launch_bounds__(256)
+gelu_fwd_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    unpack8(__ldg(x + i), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = gelu_value(v[e]);
+    y[i] = pack8(v);
+  }
+}
+// Backward over a (rows, C) matrix, C % 128 == 0: CTA = 16 chunk-columns x 16 row lanes; a thread keeps its 8 columns
+// for every row it visits, so the column sums of dx (the bias gradient of the linear layer that produced x) are
+// register partials, merged through shared memory once per CTA.
+__global__ void __launch_bounds__(256)
+gelu_bwd_vec_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                    __nv_bfloat16* __restrict__ dx, float* __restrict__ dbias) {
+  __shared__ float sh[16][129];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * 128 + tx * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (long long r = blockIdx.y * 16LL + ty; r < rows; r += gridDim.y * 16LL) {
+    float v[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = g[e] * gelu_grad(v[e]);
+      acc[e] += v[e];
+    }
+    *reinterpret_cast<uint4*>(dx + r * C + c0) = pack8(v);
+  }
+  if (dbias) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sh[ty][tx * 8 + e] = acc[e];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t += sh[j][threadIdx.x];
+      atomicAdd(dbias + blockIdx.x * 128 + threadIdx.x, t);
+    }
   }
 }
 
@@ -675,13 +922,13 @@ window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__
 // The next pair's rows are prefetched into registers while round 2 runs.
 constexpr int kBwThreads = 512;
 constexpr int kBwTiles = 8 * 16384;  // sQ sK sV sDO, sP[2], sDS[2]
-constexpr int kBwSmem = kBwTiles + kMaxN * kMaxN * 4 + 128 * 4 * 16 + 128 * 4 + 64 + 1024;
+constexpr int kBwSmem = kBwTiles + kMaxN * kMaxN * 4 + 128 * 4 * 16 + 128 * 4 + 64 + 32 * 256 * 4 + 1024;
 
 __global__ void __launch_bounds__(kBwThreads, 1)
 window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
                           const float* __restrict__ logit_scale, const float* __restrict__ bias,
                           const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
-                          float* __restrict__ dbias, float* __restrict__ dlogit_scale) {
+                          float* __restrict__ dbias, float* __restrict__ dlogit_scale, float* __restrict__ dcolsum) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t aQ = smem_u32(smem), aK = aQ + 16384, aV = aK + 16384, aDO = aV + 16384;
@@ -691,6 +938,9 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   const uint32_t aReg = aX + 128 * 4 * 16;            // int [128]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (aReg - aQ) + 128 * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  // column sums of dq / dv over every token this CTA sees (= the q_bias / v_bias gradients): float [32][256],
+  // slot = (dv ? 128 : 0) + row, owned by one thread each
+  const uint32_t aCol = aReg + 128 * 4 + 64;
 
   const int N = g.ws * g.ws;
   const int head = blockIdx.x % g.heads;
@@ -707,6 +957,7 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   const int total_pairs = (total_windows + 1) / 2;
 
   for (int i = tid; i < kBwTiles / 16; i += kBwThreads) sts128(aQ + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < 32 * 256 / 4; i += kBwThreads) sts128(aCol + i * 16, make_uint4(0, 0, 0, 0));
   for (int i = tid; i < N * N; i += kBwThreads) sts_f32(aBias + i * 4, bias[(long long)head * N * N + i]);
   if (tid == 0) {
     mbar_init(&bar[0], 1);
@@ -927,6 +1178,12 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
           }
           mul = scale * inv_norm;
         }
+        if (dcolsum != nullptr && h != 1) {
+          const uint32_t slot = aCol + ((h >> 1) * 128 + r) * 4;
+#pragma unroll
+          for (int e2 = 0; e2 < 32; ++e2)
+            sts_f32(slot + e2 * 1024, lds_f32(slot + e2 * 1024) + __uint_as_float(acc[e2]) * mul);
+        }
         uint4* dst = reinterpret_cast<uint4*>(dqkv + row * 3 * g.C + h * g.C + head * kHd);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -951,6 +1208,12 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
 #pragma unroll
   for (int s = 16; s >= 1; s >>= 1) dls += __shfl_xor_sync(0xffffffffu, dls, s);
   if ((tid & 31) == 0 && ls < 4.6051702f) atomicAdd(dlogit_scale + head, dls * scale);
+  if (dcolsum != nullptr && tid < 64) {   // the last loop iteration ended with a __syncthreads
+    const int part = tid >> 5, e2 = tid & 31;   // part 0: dq columns, part 1: dv columns
+    float tsum = 0.f;
+    for (int i = 0; i < 128; ++i) tsum += lds_f32(aCol + (e2 * 256 + part * 128 + ((i + e2) & 127)) * 4);
+    atomicAdd(dcolsum + part * 2 * g.C + head * kHd + e2, tsum);
+  }
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -966,6 +1229,31 @@ int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, 
                       float* rstd, void* stream) {
   if (rows <= 0 || C <= 0 || C > 32 * kLnMaxPerLane) return set_error(TOK_ERR_INVALID, "layernorm_fwd: 1 <= C <= 1024");
   if (rowscale && rows_per_sample <= 0) return set_error(TOK_ERR_INVALID, "layernorm_fwd: rows_per_sample");
+  int G, CH;
+  if (ln_vec_shape(C, &G, &CH)) {
+    const long long rows_per_cta = 8LL * (32 / G);
+    long long ctas = (rows + rows_per_cta - 1) / rows_per_cta;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+#define TOK_LN_FWD_V(GG, CC)                                                                                      \
+  layernorm_fwd_vec_kernel<GG, CC><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(                               \
+      rows, (const __nv_bfloat16*)x, gamma, beta, eps, (const __nv_bfloat16*)residual, rowscale,                   \
+      rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)out, mean, rstd)
+#define TOK_LN_FWD_G(CC)                                                                                          \
+  do {                                                                                                             \
+    if (G == 4) TOK_LN_FWD_V(4, CC);                                                                               \
+    else if (G == 8) TOK_LN_FWD_V(8, CC);                                                                          \
+    else if (G == 16) TOK_LN_FWD_V(16, CC);                                                                        \
+    else TOK_LN_FWD_V(32, CC);                                                                                     \
+  } while (0)
+    if (CH == 3) TOK_LN_FWD_G(3);
+    else if (CH == 4) TOK_LN_FWD_G(4);
+    else if (CH == 2) TOK_LN_FWD_G(2);
+    else TOK_LN_FWD_G(1);
+#undef TOK_LN_FWD_G
+#undef TOK_LN_FWD_V
+    TOK_CHECK_LAUNCH("layernorm_fwd_vec");
+    return TOK_OK;
+  }
   const long long threads = rows * 32;
   const unsigned grid = (unsigned)((threads + 127) / 128);
 #define TOK_LN_FWD(P)                                                                                              \
@@ -981,10 +1269,42 @@ int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, 
   return TOK_OK;
 }
 
+int tok_layernorm_has_dxsum(int C) {
+  int G, CH;
+  return ln_vec_shape(C, &G, &CH) ? 1 : 0;
+}
+
 int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, const float* mean, const float* rstd,
                       const void* dout, const float* rowscale, int rows_per_sample, void* dx, float* dgamma,
-                      float* dbeta, void* stream) {
+                      float* dbeta, float* dxsum, void* stream) {
   if (rows <= 0 || C <= 0 || C > 32 * kLnMaxPerLane) return set_error(TOK_ERR_INVALID, "layernorm_bwd: 1 <= C <= 1024");
+  int G, CH;
+  if (ln_vec_shape(C, &G, &CH)) {
+    const long long rows_per_pass = 4LL * (32 / G);
+    long long ctas = (rows + rows_per_pass - 1) / rows_per_pass;
+    const int resident = CH >= 3 ? 3 : 4;
+    if (ctas > 148 * resident * 2) ctas = 148 * resident * 2;
+#define TOK_LN_BWD_V(GG, CC)                                                                                      \
+  layernorm_bwd_vec_kernel<GG, CC><<<(unsigned)ctas, 128, 3 * C * sizeof(float), (cudaStream_t)stream>>>(           \
+      rows, (const __nv_bfloat16*)x, gamma, mean, rstd, (const __nv_bfloat16*)dout, rowscale,                      \
+      rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum)
+#define TOK_LN_BWD_G(CC)                                                                                          \
+  do {                                                                                                             \
+    if (G == 4) TOK_LN_BWD_V(4, CC);                                                                               \
+    else if (G == 8) TOK_LN_BWD_V(8, CC);                                                                          \
+    else if (G == 16) TOK_LN_BWD_V(16, CC);                                                                        \
+    else TOK_LN_BWD_V(32, CC);                                                                                     \
+  } while (0)
+    if (CH == 3) TOK_LN_BWD_G(3);
+    else if (CH == 4) TOK_LN_BWD_G(4);
+    else if (CH == 2) TOK_LN_BWD_G(2);
+    else TOK_LN_BWD_G(1);
+#undef TOK_LN_BWD_G
+#undef TOK_LN_BWD_V
+    TOK_CHECK_LAUNCH("layernorm_bwd_vec");
+    return TOK_OK;
+  }
+  if (dxsum) return set_error(TOK_ERR_INVALID, "layernorm_bwd: dxsum needs a vector-path width (tok_layernorm_has_dxsum)");
   long long ctas = 148LL * 8;
   long long rpc = (rows + ctas - 1) / ctas;
   if (rpc < 4) rpc = 4;
@@ -1004,14 +1324,32 @@ int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, 
 
 int tok_gelu_fwd(long long n, const void* x, void* y, void* stream) {
   if (n <= 0 || (n & 1)) return set_error(TOK_ERR_INVALID, "gelu: element count must be positive and even");
+  if ((n & 7) == 0) {
+    long long blocks = (n / 8 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gelu_fwd_vec_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, n / 8);
+    TOK_CHECK_LAUNCH("gelu_fwd_vec");
+    return TOK_OK;
+  }
   long long blocks = (n / 2 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   gelu_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)x, (__nv_bfloat162*)y, n / 2);
   TOK_CHECK_LAUNCH("gelu_fwd");
   return TOK_OK;
 }
-int tok_gelu_bwd(long long n, const void* x, const void* dy, void* dx, void* stream) {
+int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, float* dbias, void* stream) {
   if (n <= 0 || (n & 1)) return set_error(TOK_ERR_INVALID, "gelu: element count must be positive and even");
+  if (C > 0 && (C % 128) == 0 && (n % C) == 0) {
+    const long long rows = n / C;
+    const int gx = C / 128;
+    long long gy = (148 * 8 + gx - 1) / gx;
+    if (gy > (rows + 15) / 16) gy = (rows + 15) / 16;
+    gelu_bwd_vec_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(
+        rows, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, dbias);
+    TOK_CHECK_LAUNCH("gelu_bwd_vec");
+    return TOK_OK;
+  }
+  if (dbias) return set_error(TOK_ERR_INVALID, "gelu_bwd: the fused bias gradient needs C %% 128 == 0 (C=%d)", C);
   long long blocks = (n / 2 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   gelu_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)x, (const __nv_bfloat162*)dy,
@@ -1061,7 +1399,7 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
 
 int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift, const void* qkv,
                         const float* logit_scale, const float* bias, const void* dout, void* dqkv, float* dbias,
-                        float* dlogit_scale, void* stream) {
+                        float* dlogit_scale, float* dqkv_colsum, void* stream) {
   AttnGeom g;
   int rc = attn_geom(&g, B, H, W, C, heads, ws, shift);
   if (rc) return rc;
@@ -1080,10 +1418,11 @@ int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift
     if (groups > pairs) groups = pairs;
     window_attn_bwd_tc_kernel<<<(unsigned)(groups * heads), kBwThreads, kBwSmem, (cudaStream_t)stream>>>(
         g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
-        dlogit_scale);
+        dlogit_scale, dqkv_colsum);
     TOK_CHECK_LAUNCH("window_attn_bwd_tc");
     return TOK_OK;
   }
+  if (dqkv_colsum) return set_error(TOK_ERR_INVALID, "window_attn_bwd: dqkv_colsum is only produced by the tcgen05 kernel");
   int groups = (148 * 16 + heads - 1) / heads;
   if (groups > windows) groups = windows;
   static bool configured = false;

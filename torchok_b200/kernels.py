@@ -12,6 +12,8 @@ views `[:, :C]` of a Cp-channel buffer whose pad lanes are zero).  The reference
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from ._lib import lib, tokConvDesc
@@ -384,10 +386,11 @@ class LinearFn(torch.autograd.Function):
     fp32 master (bf16 shadow used), bias fp32.  N is padded to a multiple of 8 inside; K must be one."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, bias_grad_external=False):
         require_cuda(x, 'linear input')
         m, k = x.shape
         n = weight.shape[0]
+        ctx.bias_grad_external = bool(bias_grad_external)
         if k % 8:
             raise ValueError(f'linear: in_features must be a multiple of 8 (got {k})')
         np_ = ceil8(n)
@@ -432,14 +435,14 @@ class LinearFn(torch.autograd.Function):
                 tmp = torch.zeros((np_, k), dtype=F32, device=g.device)
                 L.tok_linear_wgrad(m, np_, k, _p(x), _p(g), _p(tmp), st)
                 gw += tmp[:n]
-        if bias is not None and bias.requires_grad:
+        if bias is not None and bias.requires_grad and not ctx.bias_grad_external:
             acc = torch.zeros((2, np_), dtype=F32, device=g.device)
             L.tok_bn_bwd_reduce(m, np_, _p(g), None, None, _p(g), _p(acc[0]), _p(acc[1]), st)
             grad_buffer(bias).add_(acc[0, :n])
         grad_ready(weight)
         if bias is not None:
-            grad_ready(bias)
-        return dx, None, None
+            grad_ready(bias)   # with bias_grad_external the consumer's backward (which ran first) has filled it
+        return dx, None, None, None
 
 
 def padded_linear_shadow(weight):
@@ -452,8 +455,10 @@ def padded_linear_shadow(weight):
     return w
 
 
-def linear(x, weight, bias=None):
-    return LinearFn.apply(x, weight, bias)
+def linear(x, weight, bias=None, bias_grad_external=False):
+    """`bias_grad_external`: the op consuming this output (layernorm / gelu with `colsum_param=bias`) accumulates the
+    bias gradient as the column sums of its own input gradient, so this layer skips its pass over dy."""
+    return LinearFn.apply(x, weight, bias, bias_grad_external)
 
 
 # ------------------------------------------------------------------------------------------------------ loss
@@ -772,8 +777,9 @@ class LayerNormFn(torch.autograd.Function):
     SwinTransformerBlock.  weight / bias gradients are accumulated into `.grad` directly."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, residual, rowscale, rows_per_sample):
+    def forward(ctx, x, weight, bias, eps, residual, rowscale, rows_per_sample, colsum_param=None):
         require_cuda(x, 'LayerNorm input')
+        ctx.colsum_param = colsum_param
         x = x.to(BF16).contiguous()
         rows, c = x.shape
         out = torch.empty_like(x)
@@ -795,24 +801,37 @@ class LayerNormFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         gw = grad_buffer(weight) if weight.requires_grad else None
         gb = grad_buffer(bias) if bias.requires_grad else None
+        cp = ctx.colsum_param
+        gx = grad_buffer(cp) if cp is not None and cp.requires_grad else None
         lib().tok_layernorm_bwd(rows, c, _p(x), _p(weight), _p(stats[0]), _p(stats[1]), _p(g), _p(rowscale), rps,
-                                _p(dx), _p(gw), _p(gb), _st())
+                                _p(dx), _p(gw), _p(gb), _p(gx), _st())
         grad_ready(weight)
         grad_ready(bias)
-        return dx, None, None, None, (g if has_res else None), None, None
+        return dx, None, None, None, (g if has_res else None), None, None, None
 
 
-def layernorm(x, weight, bias, eps=1e-5, residual=None, rowscale=None, rows_per_sample=1):
-    return LayerNormFn.apply(x, weight, bias, eps, residual, rowscale, rows_per_sample)
+def layernorm(x, weight, bias, eps=1e-5, residual=None, rowscale=None, rows_per_sample=1, colsum_param=None):
+    """`colsum_param`: fp32 (C,) bias of the linear layer that produced `x`; its gradient (column sums of dx) is
+    accumulated by the LayerNorm backward (only if `layernorm_fuses_colsum(C)`)."""
+    return LayerNormFn.apply(x, weight, bias, eps, residual, rowscale, rows_per_sample, colsum_param)
+
+
+def layernorm_fuses_colsum(c):
+    return bool(lib().tok_layernorm_has_dxsum(int(c)))
+
+
+def gelu_fuses_colsum(c):
+    return c % 128 == 0
 
 
 class GeluFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, colsum_param=None):
         x = x.to(BF16).contiguous()
         y = torch.empty_like(x)
         lib().tok_gelu_fwd(x.numel(), _p(x), _p(y), _st())
         ctx.save_for_backward(x)
+        ctx.colsum_param = colsum_param
         return y
 
     @staticmethod
@@ -820,12 +839,15 @@ class GeluFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         g = g.to(BF16).contiguous()
         dx = torch.empty_like(x)
-        lib().tok_gelu_bwd(x.numel(), _p(x), _p(g), _p(dx), _st())
-        return dx
+        cp = ctx.colsum_param
+        gx = grad_buffer(cp) if cp is not None and cp.requires_grad else None
+        lib().tok_gelu_bwd(x.numel(), x.shape[-1], _p(x), _p(g), _p(dx), _p(gx), _st())
+        return dx, None
 
 
-def gelu(x):
-    return GeluFn.apply(x)
+def gelu(x, colsum_param=None):
+    """`colsum_param`: bias of the linear layer that produced `x` (timm Mlp.fc1); see `layernorm`."""
+    return GeluFn.apply(x, colsum_param)
 
 
 class WindowAttnFn(torch.autograd.Function):
@@ -834,8 +856,9 @@ class WindowAttnFn(torch.autograd.Function):
     `logit_scale` gets its gradient accumulated into `.grad`."""
 
     @staticmethod
-    def forward(ctx, qkv, bias, logit_scale, geom):
+    def forward(ctx, qkv, bias, logit_scale, geom, qv_bias=None):
         b, h, w, c, heads, ws, shift = geom
+        ctx.qv_bias = qv_bias
         qkv = qkv.to(BF16).contiguous()
         bias = bias.float().contiguous()
         ls = logit_scale.detach().float().reshape(-1).contiguous()
@@ -853,25 +876,36 @@ class WindowAttnFn(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         dbias = torch.zeros_like(bias)
         dls = torch.zeros_like(ls)
+        col = torch.zeros(3 * c, dtype=F32, device=qkv.device) if ctx.qv_bias is not None else None
         lib().tok_window_attn_bwd(b, h, w, c, heads, ws, shift, _p(qkv), _p(ls), _p(bias), _p(g), _p(dqkv), _p(dbias),
-                                  _p(dls), _st())
+                                  _p(dls), _p(col), _st())
         if logit_scale.requires_grad:
             grad_buffer(logit_scale).add_(dls.reshape(logit_scale.shape))
             grad_ready(logit_scale)
-        return dqkv, dbias, None, None
+        if col is not None:   # q_bias / v_bias gradients = column sums of dq / dv, accumulated by the kernel
+            q_bias, v_bias = ctx.qv_bias
+            grad_buffer(q_bias).add_(col[:c])
+            grad_buffer(v_bias).add_(col[2 * c:])
+        return dqkv, dbias, None, None, None
 
 
-def window_attention(qkv, bias, logit_scale, geom):
-    return WindowAttnFn.apply(qkv, bias, logit_scale, geom)
+def attn_fuses_qv_bias_grad():
+    return os.environ.get('TOK_ATTN_BWD_CUDA_CORES') != '1'
+
+
+def window_attention(qkv, bias, logit_scale, geom, qv_bias=None):
+    """`qv_bias=(q_bias, v_bias)`: their gradients are produced by the attention backward (see `linear`)."""
+    return WindowAttnFn.apply(qkv, bias, logit_scale, geom, qv_bias)
 
 
 class QkvLinearFn(torch.autograd.Function):
     """F.linear(x, qkv.weight, cat(q_bias, zeros, v_bias)) of timm's WindowAttention (k has no bias)."""
 
     @staticmethod
-    def forward(ctx, x, weight, q_bias, v_bias):
+    def forward(ctx, x, weight, q_bias, v_bias, bias_grad_external=False):
         m, k = x.shape
         n = weight.shape[0]
+        ctx.bias_grad_external = bool(bias_grad_external)
         x = x.to(BF16).contiguous()
         w = shadow_of(weight)
         b = None
@@ -896,16 +930,17 @@ class QkvLinearFn(torch.autograd.Function):
         if weight.requires_grad:
             L.tok_linear_wgrad(m, n, k, _p(x), _p(g), _p(grad_buffer(weight)), st)
         if q_bias is not None:
-            acc = torch.zeros((2, n), dtype=F32, device=g.device)
-            L.tok_bn_bwd_reduce(m, n, _p(g), None, None, _p(g), _p(acc[0]), _p(acc[1]), st)
-            c = n // 3
-            grad_buffer(q_bias).add_(acc[0, :c])
-            grad_buffer(v_bias).add_(acc[0, 2 * c:])
+            if not ctx.bias_grad_external:
+                acc = torch.zeros((2, n), dtype=F32, device=g.device)
+                L.tok_bn_bwd_reduce(m, n, _p(g), None, None, _p(g), _p(acc[0]), _p(acc[1]), st)
+                c = n // 3
+                grad_buffer(q_bias).add_(acc[0, :c])
+                grad_buffer(v_bias).add_(acc[0, 2 * c:])
             grad_ready(q_bias)
             grad_ready(v_bias)
         grad_ready(weight)
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
-def qkv_linear(x, weight, q_bias, v_bias):
-    return QkvLinearFn.apply(x, weight, q_bias, v_bias)
+def qkv_linear(x, weight, q_bias, v_bias, bias_grad_external=False):
+    return QkvLinearFn.apply(x, weight, q_bias, v_bias, bias_grad_external)

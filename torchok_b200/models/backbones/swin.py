@@ -34,13 +34,13 @@ def to_2tuple(v):
 class Linear(nn.Linear):
     """nn.Linear parameters executed by tok_linear_* on (rows, in_features) bf16 matrices."""
 
-    def forward(self, x):
-        return K.linear(x, self.weight, self.bias)
+    def forward(self, x, bias_grad_external=False):
+        return K.linear(x, self.weight, self.bias, bias_grad_external)
 
 
 class LayerNorm(nn.LayerNorm):
-    def forward(self, x, residual=None, rowscale=None, rows_per_sample=1):
-        return K.layernorm(x, self.weight, self.bias, self.eps, residual, rowscale, rows_per_sample)
+    def forward(self, x, residual=None, rowscale=None, rows_per_sample=1, colsum_param=None):
+        return K.layernorm(x, self.weight, self.bias, self.eps, residual, rowscale, rows_per_sample, colsum_param)
 
 
 class Mlp(nn.Module):
@@ -50,8 +50,12 @@ class Mlp(nn.Module):
         self.act = nn.GELU()
         self.fc2 = Linear(hidden_features, in_features)
 
-    def forward(self, x):
-        return self.fc2(K.gelu(self.fc1(x)))
+    def forward(self, x, fc2_bias_external=False):
+        # the bias gradients of fc1 / fc2 are the column sums of the GELU / LayerNorm input gradients: those backward
+        # kernels accumulate them on the way instead of a separate pass over dy per linear layer
+        ext1 = self.fc1.bias is not None and K.gelu_fuses_colsum(self.fc1.out_features)
+        h = K.gelu(self.fc1(x, ext1), self.fc1.bias if ext1 else None)
+        return self.fc2(h, fc2_bias_external)
 
 
 class WindowAttention(nn.Module):
@@ -94,10 +98,12 @@ class WindowAttention(nn.Module):
         t = t[self.relative_position_index.view(-1)].view(n, n, -1).permute(2, 0, 1).contiguous()
         return 16 * torch.sigmoid(t)
 
-    def forward(self, x, geom):
-        qkv = K.qkv_linear(x, self.qkv.weight, self.q_bias, self.v_bias)
-        out = K.window_attention(qkv, self.bias_table(), self.logit_scale, geom)
-        return self.proj(out)
+    def forward(self, x, geom, proj_bias_external=False):
+        ext = self.q_bias is not None and K.attn_fuses_qv_bias_grad()
+        qkv = K.qkv_linear(x, self.qkv.weight, self.q_bias, self.v_bias, ext)
+        out = K.window_attention(qkv, self.bias_table(), self.logit_scale, geom,
+                                 (self.q_bias, self.v_bias) if ext else None)
+        return self.proj(out, proj_bias_external)
 
 
 class SwinTransformerBlock(nn.Module):
@@ -143,8 +149,11 @@ class SwinTransformerBlock(nn.Module):
         h, w = self.input_resolution
         geom = (batch, h, w, self.dim, self.num_heads, self.window_size[0], self.shift_size[0])
         rps = h * w
-        x = self.norm1(self.attn(x, geom), residual=x, rowscale=self._rowscale(batch, x.device), rows_per_sample=rps)
-        x = self.norm2(self.mlp(x), residual=x, rowscale=self._rowscale(batch, x.device), rows_per_sample=rps)
+        ext = K.layernorm_fuses_colsum(self.dim)   # proj / fc2 bias gradients come out of the LayerNorm backward
+        x = self.norm1(self.attn(x, geom, ext), residual=x, rowscale=self._rowscale(batch, x.device), rows_per_sample=rps,
+                       colsum_param=self.attn.proj.bias if ext else None)
+        x = self.norm2(self.mlp(x, ext), residual=x, rowscale=self._rowscale(batch, x.device), rows_per_sample=rps,
+                       colsum_param=self.mlp.fc2.bias if ext else None)
         return x
 
 
