@@ -65,6 +65,20 @@ def _step_bench(cfg, batch, size, classes, seg=False, steps=10):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return 0.0, float(loop.loss)
+    if os.environ.get('TOK_EXTRA_TORCHPROF'):  # attribute the non-tok helper kernels (aten copies / fills / adds) to shapes
+        from torch.profiler import ProfilerActivity, profile
+        loop.use_graph = False
+        for _ in range(2):
+            loop.train_step(b)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
+            loop.train_step(b)
+            torch.cuda.synchronize()
+        print(prof.key_averages(group_by_input_shape=True).table(sort_by='device_time_total', row_limit=45,
+                                                                 max_name_column_width=48, max_shapes_column_width=60))
+        print(prof.key_averages(group_by_stack_n=4).table(sort_by='device_time_total', row_limit=30,
+                                                          max_name_column_width=40, max_src_column_width=90))
+        return 0.0, float(loop.loss)
     ms = timed(lambda: loop.train_step(b), warm=3, iters=steps)
     return ms, float(loop.loss)
 

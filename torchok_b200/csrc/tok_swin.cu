@@ -167,7 +167,11 @@ layernorm_fwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
   const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
   const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp_id * RPW + sub; r < rows; r += warps * RPW) {
+  // the trip count is warp-uniform (the group shuffles need every lane); rows past the end are computed on row
+  // `rows - 1` and not stored
+  for (long long base = warp_id * RPW; base < rows; base += warps * RPW) {
+    const bool live = base + sub < rows;
+    const long long r = live ? base + sub : rows - 1;
     const uint4* xr = reinterpret_cast<const uint4*>(x + r * C);
     float v[CH][8];
     float s = 0.f;
@@ -204,9 +208,9 @@ layernorm_fwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = fmaf(sc, y[e], rr[e]);
       }
-      reinterpret_cast<uint4*>(out + r * C)[l + i * G] = pack8(y);
+      if (live) reinterpret_cast<uint4*>(out + r * C)[l + i * G] = pack8(y);
     }
-    if (l == 0) {
+    if (l == 0 && live) {
       mean[r] = mu;
       rstd[r] = rs;
     }
@@ -236,12 +240,14 @@ layernorm_bwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
   for (int i = 0; i < CH; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) ag[i][e] = ab[i][e] = ax[i][e] = 0.f;
-  for (long long r = warp_id * RPW + sub; r < rows; r += warps * RPW) {
+  for (long long base = warp_id * RPW; base < rows; base += warps * RPW) {   // warp-uniform trip count (shuffles)
+    const bool live = base + sub < rows;
+    const long long r = live ? base + sub : rows - 1;
     uint4 xr[CH], gr[CH];
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       xr[i] = __ldg(reinterpret_cast<const uint4*>(x + r * C) + l + i * G);
-      gr[i] = __ldg(reinterpret_cast<const uint4*>(dout + r * C) + l + i * G);
+      gr[i] = live ? __ldg(reinterpret_cast<const uint4*>(dout + r * C) + l + i * G) : make_uint4(0, 0, 0, 0);
     }
     const float mu = mean[r], rs = rstd[r];
     const float sc = rowscale ? rowscale[r / rows_per_sample] : 1.f;
@@ -281,7 +287,7 @@ layernorm_bwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
         d[e] = rs * (sc * gv[e] * gm[e] - s1 - xh * s2);
         ax[i][e] += d[e];
       }
-      reinterpret_cast<uint4*>(dx + r * C)[l + i * G] = pack8(d);
+      if (live) reinterpret_cast<uint4*>(dx + r * C)[l + i * G] = pack8(d);
     }
   }
 #pragma unroll
@@ -361,7 +367,22 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat162* __restrict__ x, const __nv
 // 16-byte version (n % 8 == 0)
 __global__ void __launch_bounds__(256)
 gelu_fwd_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long n8) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n8; i += 4 * stride) {   // four independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(x + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      unpack8(u[k], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = gelu_value(v[e]);
+      y[i + k * stride] = pack8(v);
+    }
+  }
+  for (; i < n8; i += stride) {
     float v[8];
     unpack8(__ldg(x + i), v);
 #pragma unroll
@@ -381,7 +402,32 @@ gelu_bwd_vec_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, 
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (long long r = blockIdx.y * 16LL + ty; r < rows; r += gridDim.y * 16LL) {
+  const long long rstep = gridDim.y * 16LL;
+  long long r = blockIdx.y * 16LL + ty;
+  for (; r + rstep < rows; r += 2 * rstep) {   // two rows (four 16-byte loads) in flight per thread
+    const uint4 xa = __ldg(reinterpret_cast<const uint4*>(x + r * C + c0));
+    const uint4 ga = __ldg(reinterpret_cast<const uint4*>(dy + r * C + c0));
+    const uint4 xb = __ldg(reinterpret_cast<const uint4*>(x + (r + rstep) * C + c0));
+    const uint4 gb = __ldg(reinterpret_cast<const uint4*>(dy + (r + rstep) * C + c0));
+    float v[8], g[8];
+    unpack8(xa, v);
+    unpack8(ga, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = g[e] * gelu_grad(v[e]);
+      acc[e] += v[e];
+    }
+    *reinterpret_cast<uint4*>(dx + r * C + c0) = pack8(v);
+    unpack8(xb, v);
+    unpack8(gb, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = g[e] * gelu_grad(v[e]);
+      acc[e] += v[e];
+    }
+    *reinterpret_cast<uint4*>(dx + (r + rstep) * C + c0) = pack8(v);
+  }
+  for (; r < rows; r += rstep) {
     float v[8], g[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), v);
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), g);
