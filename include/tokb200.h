@@ -72,6 +72,9 @@ int tok_conv_wgrad(const tokConvDesc* d, const void* x, const void* dy, float* d
 int tok_linear_fwd(int m, int n, int k, const void* x, const void* w, const float* bias, void* y, void* stream);
 /* dx[m,k] = sum_n dy[m,n] * w[n,k] */
 int tok_linear_dgrad(int m, int n, int k, const void* dy, const void* w, void* dx, void* stream);
+/* dx[m,k] = sum_n dy[m,n] * w[n,k] + addend[m,k]: the residual-branch gradient of a transformer block
+ * (x + f(x), timm SwinTransformerBlock) joins the branch gradient in the GEMM epilogue instead of a separate add pass. */
+int tok_linear_dgrad_add(int m, int n, int k, const void* dy, const void* w, const void* addend, void* dx, void* stream);
 /* dw[n,k] += sum_m dy[m,n] * x[m,k]  (fp32, atomically accumulated) */
 int tok_linear_wgrad(int m, int n, int k, const void* x, const void* dy, float* dw, void* stream);
 
@@ -175,6 +178,10 @@ int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, 
                       const void* dout, const float* rowscale, int rows_per_sample, void* dx, float* dgamma,
                       float* dbeta, float* dxsum, void* stream);
 int tok_layernorm_has_dxsum(int C);
+/* timm PatchMerging gather on a (B, H, W, C) bf16 tensor: dst[b,i,j,q*C+c] = src[b, 2i+(q&1), 2j+(q>>1), c] (q = 0..3, the
+ * order of torch.cat([x[:,0::2,0::2], x[:,1::2,0::2], x[:,0::2,1::2], x[:,1::2,1::2]], -1)); inverse != 0 scatters back
+ * (the backward).  H, W even, C % 8 == 0. */
+int tok_patch_merge(int B, int H, int W, int C, const void* src, void* dst, int inverse, void* stream);
 /* exact (erf) GELU of timm's Mlp (Mlp.act between fc1 and fc2).  Backward over an (n / C, C) matrix; `dbias` (nullable,
  * C floats, ACCUMULATED, needs C % 128 == 0) receives the column sums of dx = the bias gradient of Mlp.fc1. */
 int tok_gelu_fwd(long long n, const void* x, void* y, void* stream);

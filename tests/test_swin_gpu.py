@@ -77,6 +77,23 @@ def test_layernorm_colsum(rows, c):
     assert rel_err(lin_bias.grad, xo.grad.sum(0)) < 1e-2
 
 
+def test_patch_merge_is_the_reference_cat():
+    """timm PatchMerging gather: bit-exact against torch.cat of the four strided slices, forward and backward."""
+    from torchok_b200 import kernels as K
+    b, h, w, c = 3, 8, 6, 24
+    x = _bf(torch.randn(b, h, w, c))
+    xo = x.clone().requires_grad_(True)
+    ref = torch.cat([xo[:, 0::2, 0::2, :], xo[:, 1::2, 0::2, :], xo[:, 0::2, 1::2, :], xo[:, 1::2, 1::2, :]], -1)
+    ref = ref.reshape(-1, 4 * c)
+    g = _bf(torch.randn_like(ref))
+    (ref * g).sum().backward()
+    xm = x.cuda().to(torch.bfloat16).view(-1, c).requires_grad_(True)
+    out = K.patch_merge(xm, b, h, w)
+    (out.float() * g.cuda()).sum().backward()
+    assert torch.equal(out.float().cpu(), ref.detach())
+    assert torch.equal(xm.grad.float().cpu().view(b, h, w, c), xo.grad)
+
+
 @pytest.mark.parametrize('dim,heads,res,ws,shift', [(96, 3, 8, 4, 0), (96, 3, 8, 4, 2), (64, 2, 14, 7, 3), (192, 6, 8, 8, 0),
                                                     (128, 4, 16, 8, 4)])
 def test_swin_block_forward_backward(dim, heads, res, ws, shift):

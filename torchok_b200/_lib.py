@@ -46,6 +46,8 @@ _SIGS = {
     'tok_conv_wgrad': (_i, [_pd, _vp, _vp, _vp, _vp]),
     'tok_linear_fwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'tok_linear_dgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    'tok_linear_dgrad_add': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'tok_patch_merge': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
     'tok_linear_wgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_stem_geometry': (None, [_i, _i, _pi, _pi, _pi, _pi]),
     'tok_stem_pack_input': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),

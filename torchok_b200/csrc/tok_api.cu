@@ -483,6 +483,16 @@ int tok_linear_dgrad(int m, int n, int k, const void* dy, const void* w, void* d
   return run_fwd(dy, 1, 1, m, n, flat_src(), m, w, n, k, true, k, 0, p, static_cast<cudaStream_t>(stream));
 }
 
+int tok_linear_dgrad_add(int m, int n, int k, const void* dy, const void* w, const void* addend, void* dx, void* stream) {
+  if (m <= 0 || n <= 0 || k <= 0 || (n % 8) || (k % 8)) return set_error(TOK_ERR_INVALID, "linear: n and k must be positive multiples of 8");
+  ConvFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = static_cast<__nv_bfloat16*>(dx);
+  p.ldo = k;
+  p.addend = static_cast<const __nv_bfloat16*>(addend);
+  return run_fwd(dy, 1, 1, m, n, flat_src(), m, w, n, k, true, k, 0, p, static_cast<cudaStream_t>(stream));
+}
+
 int tok_linear_wgrad(int m, int n, int k, const void* x, const void* dy, float* dw, void* stream) {
   if (m <= 0 || n <= 0 || k <= 0 || (n % 8) || (k % 8)) return set_error(TOK_ERR_INVALID, "linear: n and k must be positive multiples of 8");
   return run_wgrad(x, 1, 1, m, k, flat_src(), dy, m, n, dw, static_cast<cudaStream_t>(stream));

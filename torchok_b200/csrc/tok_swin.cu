@@ -451,6 +451,31 @@ gelu_bwd_vec_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, 
   }
 }
 
+// ---- PatchMerging gather -----------------------------------------------------------------------------------------
+// timm PatchMerging (used by torchok/models/backbones/swin.py:71-81 through BasicLayer.downsample):
+//   cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)  on a (B, H, W, C) tensor.
+// A pure permutation in 16-byte pieces: out[b, i, j, q*C + c] = x[b, 2i + (q & 1), 2j + (q >> 1), c]; the backward is
+// the same walk with source and destination swapped (the reference pays 8 strided slices, a cat and, in backward,
+// 8 zero-fills + 8 strided copies + 3 accumulations for it).
+__global__ void __launch_bounds__(256)
+patch_merge_kernel(int B, int H, int W, int C8, const uint4* __restrict__ src, uint4* __restrict__ dst, int inverse) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long long total = (long long)B * H2 * W2 * 4 * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long t = i / C8;
+    const int q = (int)(t & 3);
+    t >>= 2;
+    const int j = (int)(t % W2);
+    t /= W2;
+    const int ii = (int)(t % H2);
+    const long long b = t / H2;
+    const long long xi = ((b * H + 2 * ii + (q & 1)) * W + 2 * j + (q >> 1)) * C8 + c;
+    if (inverse) dst[xi] = __ldg(src + i);
+    else dst[i] = __ldg(src + xi);
+  }
+}
+
 // ---- shifted-window cosine attention ---------------------------------------------------------------------------------
 constexpr int kHd = 32;      // head dimension (always 32 in Swin-V2: embed_dim 96 / 3 heads, doubling together)
 constexpr int kMaxN = 64;    // tokens per window (window <= 8x8)
@@ -1268,6 +1293,25 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
 
 using namespace tok;
 
+// grid = SMs x resident CTAs per SM: a grid-stride kernel launched with a few more CTAs than fit runs a second,
+// mostly empty wave (1184 CTAs on 888 slots cost the GELU passes a third of their bandwidth)
+template <typename Kern>
+static int full_wave_ctas(Kern kernel, int threads, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+  return 148 * n;
+}
+template <int G, int CH>
+static long long ln_fwd_ctas() {
+  static const int n = full_wave_ctas(layernorm_fwd_vec_kernel<G, CH>, 256, 0);
+  return n;
+}
+template <int G, int CH>
+static long long ln_bwd_ctas() {
+  static const int n = full_wave_ctas(layernorm_bwd_vec_kernel<G, CH>, 128, 3 * 8 * CH * G * sizeof(float));
+  return n;
+}
+
 extern "C" {
 
 int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, const float* beta, float eps,
@@ -1278,10 +1322,10 @@ int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, 
   int G, CH;
   if (ln_vec_shape(C, &G, &CH)) {
     const long long rows_per_cta = 8LL * (32 / G);
-    long long ctas = (rows + rows_per_cta - 1) / rows_per_cta;
-    if (ctas > 148 * 8) ctas = 148 * 8;
+    const long long want = (rows + rows_per_cta - 1) / rows_per_cta;
 #define TOK_LN_FWD_V(GG, CC)                                                                                      \
-  layernorm_fwd_vec_kernel<GG, CC><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(                               \
+  layernorm_fwd_vec_kernel<GG, CC><<<(unsigned)(want < ln_fwd_ctas<GG, CC>() ? want : ln_fwd_ctas<GG, CC>()), 256, 0,    \
+                                     (cudaStream_t)stream>>>(                                                      \
       rows, (const __nv_bfloat16*)x, gamma, beta, eps, (const __nv_bfloat16*)residual, rowscale,                   \
       rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)out, mean, rstd)
 #define TOK_LN_FWD_G(CC)                                                                                          \
@@ -1327,11 +1371,10 @@ int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, 
   int G, CH;
   if (ln_vec_shape(C, &G, &CH)) {
     const long long rows_per_pass = 4LL * (32 / G);
-    long long ctas = (rows + rows_per_pass - 1) / rows_per_pass;
-    const int resident = CH >= 3 ? 3 : 4;
-    if (ctas > 148 * resident * 2) ctas = 148 * resident * 2;
+    const long long want = (rows + rows_per_pass - 1) / rows_per_pass;
 #define TOK_LN_BWD_V(GG, CC)                                                                                      \
-  layernorm_bwd_vec_kernel<GG, CC><<<(unsigned)ctas, 128, 3 * C * sizeof(float), (cudaStream_t)stream>>>(           \
+  layernorm_bwd_vec_kernel<GG, CC><<<(unsigned)(want < ln_bwd_ctas<GG, CC>() ? want : ln_bwd_ctas<GG, CC>()), 128,       \
+                                     3 * C * sizeof(float), (cudaStream_t)stream>>>(                               \
       rows, (const __nv_bfloat16*)x, gamma, mean, rstd, (const __nv_bfloat16*)dout, rowscale,                      \
       rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum)
 #define TOK_LN_BWD_G(CC)                                                                                          \
@@ -1372,7 +1415,8 @@ int tok_gelu_fwd(long long n, const void* x, void* y, void* stream) {
   if (n <= 0 || (n & 1)) return set_error(TOK_ERR_INVALID, "gelu: element count must be positive and even");
   if ((n & 7) == 0) {
     long long blocks = (n / 8 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    static const int wave = full_wave_ctas(gelu_fwd_vec_kernel, 256, 0);
+    if (blocks > wave) blocks = wave;
     gelu_fwd_vec_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, n / 8);
     TOK_CHECK_LAUNCH("gelu_fwd_vec");
     return TOK_OK;
@@ -1388,7 +1432,9 @@ int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, fl
   if (C > 0 && (C % 128) == 0 && (n % C) == 0) {
     const long long rows = n / C;
     const int gx = C / 128;
-    long long gy = (148 * 8 + gx - 1) / gx;
+    static const int wave = full_wave_ctas(gelu_bwd_vec_kernel, 256, 0);
+    long long gy = wave / gx;   // never more CTAs than one resident wave
+    if (gy < 1) gy = 1;
     if (gy > (rows + 15) / 16) gy = (rows + 15) / 16;
     gelu_bwd_vec_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(
         rows, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, dbias);
@@ -1401,6 +1447,18 @@ int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, fl
   gelu_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)x, (const __nv_bfloat162*)dy,
                                                                      (__nv_bfloat162*)dx, n / 2);
   TOK_CHECK_LAUNCH("gelu_bwd");
+  return TOK_OK;
+}
+
+int tok_patch_merge(int B, int H, int W, int C, const void* src, void* dst, int inverse, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || C <= 0 || (C % 8))
+    return set_error(TOK_ERR_INVALID, "patch_merge: even H, W and C %% 8 == 0 required (H=%d W=%d C=%d)", H, W, C);
+  const long long total = (long long)B * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  static const int wave = full_wave_ctas(patch_merge_kernel, 256, 0);
+  if (blocks > wave) blocks = wave;
+  patch_merge_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, H, W, C / 8, (const uint4*)src, (uint4*)dst, inverse);
+  TOK_CHECK_LAUNCH("patch_merge");
   return TOK_OK;
 }
 

@@ -381,16 +381,42 @@ class GlobalPoolFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------------ linear
+class ResidualLink:
+    """Side channel for the gradient of the skip connection of a residual block `x + f(x)`.
+
+    Autograd would sum the two gradients of `x` (skip path, branch path) with a separate elementwise pass.  Instead
+    the block's tail (LayerNormFn with `res_link`) parks the skip gradient here and returns no gradient for its
+    residual input, and the first linear layer of the branch (`linear(..., res_link=...)`, whose backward always runs
+    after the tail's) adds it in the epilogue of its dgrad GEMM."""
+    __slots__ = ('g',)
+
+    def __init__(self):
+        self.g = None
+
+    def take(self):
+        g, self.g = self.g, None
+        return g
+
+
+def _dgrad_with_link(L, link, m, n, k, g, w, dx, st):
+    add = link.take() if link is not None else None
+    if add is not None:
+        L.tok_linear_dgrad_add(m, n, k, _p(g), _p(w), _p(add), _p(dx), st)
+    else:
+        L.tok_linear_dgrad(m, n, k, _p(g), _p(w), _p(dx), st)
+
+
 class LinearFn(torch.autograd.Function):
     """torch.nn.Linear (torchok/models/heads/representation/linear_head.py:25-31).  x (M, K) bf16, weight (N, K)
     fp32 master (bf16 shadow used), bias fp32.  N is padded to a multiple of 8 inside; K must be one."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, bias_grad_external=False):
+    def forward(ctx, x, weight, bias, bias_grad_external=False, res_link=None):
         require_cuda(x, 'linear input')
         m, k = x.shape
         n = weight.shape[0]
         ctx.bias_grad_external = bool(bias_grad_external)
+        ctx.res_link = res_link
         if k % 8:
             raise ValueError(f'linear: in_features must be a multiple of 8 (got {k})')
         np_ = ceil8(n)
@@ -426,7 +452,7 @@ class LinearFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((m, k), dtype=BF16, device=g.device)
-            L.tok_linear_dgrad(m, np_, k, _p(g), _p(w), _p(dx), st)
+            _dgrad_with_link(L, ctx.res_link, m, np_, k, g, w, dx, st)
         if weight.requires_grad:
             gw = grad_buffer(weight)
             if np_ == n:
@@ -442,7 +468,7 @@ class LinearFn(torch.autograd.Function):
         grad_ready(weight)
         if bias is not None:
             grad_ready(bias)   # with bias_grad_external the consumer's backward (which ran first) has filled it
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
 def padded_linear_shadow(weight):
@@ -455,10 +481,11 @@ def padded_linear_shadow(weight):
     return w
 
 
-def linear(x, weight, bias=None, bias_grad_external=False):
+def linear(x, weight, bias=None, bias_grad_external=False, res_link=None):
     """`bias_grad_external`: the op consuming this output (layernorm / gelu with `colsum_param=bias`) accumulates the
-    bias gradient as the column sums of its own input gradient, so this layer skips its pass over dy."""
-    return LinearFn.apply(x, weight, bias, bias_grad_external)
+    bias gradient as the column sums of its own input gradient, so this layer skips its pass over dy.
+    `res_link`: see ResidualLink."""
+    return LinearFn.apply(x, weight, bias, bias_grad_external, res_link)
 
 
 # ------------------------------------------------------------------------------------------------------ loss
@@ -777,9 +804,10 @@ class LayerNormFn(torch.autograd.Function):
     SwinTransformerBlock.  weight / bias gradients are accumulated into `.grad` directly."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, residual, rowscale, rows_per_sample, colsum_param=None):
+    def forward(ctx, x, weight, bias, eps, residual, rowscale, rows_per_sample, colsum_param=None, res_link=None):
         require_cuda(x, 'LayerNorm input')
         ctx.colsum_param = colsum_param
+        ctx.res_link = res_link if residual is not None else None
         x = x.to(BF16).contiguous()
         rows, c = x.shape
         out = torch.empty_like(x)
@@ -807,13 +835,17 @@ class LayerNormFn(torch.autograd.Function):
                                 _p(dx), _p(gw), _p(gb), _p(gx), _st())
         grad_ready(weight)
         grad_ready(bias)
-        return dx, None, None, None, (g if has_res else None), None, None, None
+        gres = g if has_res else None
+        if ctx.res_link is not None:   # the branch's first linear layer adds the skip gradient in its dgrad epilogue
+            ctx.res_link.g, gres = g, None
+        return dx, None, None, None, gres, None, None, None, None
 
 
-def layernorm(x, weight, bias, eps=1e-5, residual=None, rowscale=None, rows_per_sample=1, colsum_param=None):
+def layernorm(x, weight, bias, eps=1e-5, residual=None, rowscale=None, rows_per_sample=1, colsum_param=None,
+              res_link=None):
     """`colsum_param`: fp32 (C,) bias of the linear layer that produced `x`; its gradient (column sums of dx) is
     accumulated by the LayerNorm backward (only if `layernorm_fuses_colsum(C)`)."""
-    return LayerNormFn.apply(x, weight, bias, eps, residual, rowscale, rows_per_sample, colsum_param)
+    return LayerNormFn.apply(x, weight, bias, eps, residual, rowscale, rows_per_sample, colsum_param, res_link)
 
 
 def layernorm_fuses_colsum(c):
@@ -902,10 +934,11 @@ class QkvLinearFn(torch.autograd.Function):
     """F.linear(x, qkv.weight, cat(q_bias, zeros, v_bias)) of timm's WindowAttention (k has no bias)."""
 
     @staticmethod
-    def forward(ctx, x, weight, q_bias, v_bias, bias_grad_external=False):
+    def forward(ctx, x, weight, q_bias, v_bias, bias_grad_external=False, res_link=None):
         m, k = x.shape
         n = weight.shape[0]
         ctx.bias_grad_external = bool(bias_grad_external)
+        ctx.res_link = res_link
         x = x.to(BF16).contiguous()
         w = shadow_of(weight)
         b = None
@@ -926,7 +959,7 @@ class QkvLinearFn(torch.autograd.Function):
         g = g.to(BF16).contiguous()
         L, st = lib(), _st()
         dx = torch.empty((m, k), dtype=BF16, device=g.device)
-        L.tok_linear_dgrad(m, n, k, _p(g), _p(w), _p(dx), st)
+        _dgrad_with_link(L, ctx.res_link, m, n, k, g, w, dx, st)
         if weight.requires_grad:
             L.tok_linear_wgrad(m, n, k, _p(x), _p(g), _p(grad_buffer(weight)), st)
         if q_bias is not None:
@@ -939,8 +972,33 @@ class QkvLinearFn(torch.autograd.Function):
             grad_ready(q_bias)
             grad_ready(v_bias)
         grad_ready(weight)
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
-def qkv_linear(x, weight, q_bias, v_bias, bias_grad_external=False):
-    return QkvLinearFn.apply(x, weight, q_bias, v_bias, bias_grad_external)
+def qkv_linear(x, weight, q_bias, v_bias, bias_grad_external=False, res_link=None):
+    return QkvLinearFn.apply(x, weight, q_bias, v_bias, bias_grad_external, res_link)
+
+
+class PatchMergeFn(torch.autograd.Function):
+    """The gather of timm's PatchMerging: (B*H*W, C) tokens -> (B*H/2*W/2, 4C); a permutation in both directions."""
+
+    @staticmethod
+    def forward(ctx, x, b, h, w):
+        x = x.to(BF16).contiguous()
+        c = x.shape[-1]
+        out = torch.empty((b * (h // 2) * (w // 2), 4 * c), dtype=BF16, device=x.device)
+        lib().tok_patch_merge(b, h, w, c, _p(x), _p(out), 0, _st())
+        ctx.geom = (b, h, w, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        b, h, w, c = ctx.geom
+        g = g.to(BF16).contiguous()
+        dx = torch.empty((b * h * w, c), dtype=BF16, device=g.device)
+        lib().tok_patch_merge(b, h, w, c, _p(g), _p(dx), 1, _st())
+        return dx, None, None, None
+
+
+def patch_merge(x, b, h, w):
+    return PatchMergeFn.apply(x, b, h, w)

@@ -34,13 +34,14 @@ def to_2tuple(v):
 class Linear(nn.Linear):
     """nn.Linear parameters executed by tok_linear_* on (rows, in_features) bf16 matrices."""
 
-    def forward(self, x, bias_grad_external=False):
-        return K.linear(x, self.weight, self.bias, bias_grad_external)
+    def forward(self, x, bias_grad_external=False, res_link=None):
+        return K.linear(x, self.weight, self.bias, bias_grad_external, res_link)
 
 
 class LayerNorm(nn.LayerNorm):
-    def forward(self, x, residual=None, rowscale=None, rows_per_sample=1, colsum_param=None):
-        return K.layernorm(x, self.weight, self.bias, self.eps, residual, rowscale, rows_per_sample, colsum_param)
+    def forward(self, x, residual=None, rowscale=None, rows_per_sample=1, colsum_param=None, res_link=None):
+        return K.layernorm(x, self.weight, self.bias, self.eps, residual, rowscale, rows_per_sample, colsum_param,
+                           res_link)
 
 
 class Mlp(nn.Module):
@@ -50,11 +51,11 @@ class Mlp(nn.Module):
         self.act = nn.GELU()
         self.fc2 = Linear(hidden_features, in_features)
 
-    def forward(self, x, fc2_bias_external=False):
+    def forward(self, x, fc2_bias_external=False, res_link=None):
         # the bias gradients of fc1 / fc2 are the column sums of the GELU / LayerNorm input gradients: those backward
         # kernels accumulate them on the way instead of a separate pass over dy per linear layer
         ext1 = self.fc1.bias is not None and K.gelu_fuses_colsum(self.fc1.out_features)
-        h = K.gelu(self.fc1(x, ext1), self.fc1.bias if ext1 else None)
+        h = K.gelu(self.fc1(x, ext1, res_link), self.fc1.bias if ext1 else None)
         return self.fc2(h, fc2_bias_external)
 
 
@@ -98,9 +99,9 @@ class WindowAttention(nn.Module):
         t = t[self.relative_position_index.view(-1)].view(n, n, -1).permute(2, 0, 1).contiguous()
         return 16 * torch.sigmoid(t)
 
-    def forward(self, x, geom, proj_bias_external=False):
+    def forward(self, x, geom, proj_bias_external=False, res_link=None):
         ext = self.q_bias is not None and K.attn_fuses_qv_bias_grad()
-        qkv = K.qkv_linear(x, self.qkv.weight, self.q_bias, self.v_bias, ext)
+        qkv = K.qkv_linear(x, self.qkv.weight, self.q_bias, self.v_bias, ext, res_link)
         out = K.window_attention(qkv, self.bias_table(), self.logit_scale, geom,
                                  (self.q_bias, self.v_bias) if ext else None)
         return self.proj(out, proj_bias_external)
@@ -150,10 +151,14 @@ class SwinTransformerBlock(nn.Module):
         geom = (batch, h, w, self.dim, self.num_heads, self.window_size[0], self.shift_size[0])
         rps = h * w
         ext = K.layernorm_fuses_colsum(self.dim)   # proj / fc2 bias gradients come out of the LayerNorm backward
-        x = self.norm1(self.attn(x, geom, ext), residual=x, rowscale=self._rowscale(batch, x.device), rows_per_sample=rps,
-                       colsum_param=self.attn.proj.bias if ext else None)
-        x = self.norm2(self.mlp(x, ext), residual=x, rowscale=self._rowscale(batch, x.device), rows_per_sample=rps,
-                       colsum_param=self.mlp.fc2.bias if ext else None)
+        # skip-connection gradients join the branch gradients inside the qkv / fc1 dgrad GEMMs (K.ResidualLink); only
+        # when x itself needs a gradient, otherwise the branch's dgrad (and with it the link) would never run
+        link1 = K.ResidualLink() if x.requires_grad else None
+        x = self.norm1(self.attn(x, geom, ext, link1), residual=x, rowscale=self._rowscale(batch, x.device),
+                       rows_per_sample=rps, colsum_param=self.attn.proj.bias if ext else None, res_link=link1)
+        link2 = K.ResidualLink() if x.requires_grad else None
+        x = self.norm2(self.mlp(x, ext, link2), residual=x, rowscale=self._rowscale(batch, x.device), rows_per_sample=rps,
+                       colsum_param=self.mlp.fc2.bias if ext else None, res_link=link2)
         return x
 
 
@@ -166,9 +171,7 @@ class PatchMerging(nn.Module):
 
     def forward(self, x, batch):
         h, w = self.input_resolution
-        x = x.view(batch, h, w, self.dim)
-        x = torch.cat([x[:, 0::2, 0::2, :], x[:, 1::2, 0::2, :], x[:, 0::2, 1::2, :], x[:, 1::2, 1::2, :]], -1)
-        x = x.reshape(-1, 4 * self.dim)
+        x = K.patch_merge(x.reshape(-1, self.dim), batch, h, w)   # the 2x2 gather of timm's PatchMerging, one kernel
         return self.norm(K.linear(x, self.reduction.weight, None))
 
 
