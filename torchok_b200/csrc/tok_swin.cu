@@ -697,26 +697,37 @@ window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
         }
       }
       const float qi = 1.f / fmaxf(sqrtf(qq), 1e-12f), ki = 1.f / fmaxf(sqrtf(kk), 1e-12f);
+      // Split-bf16 cosine: q_hat = q_hi + q_lo, k_hat = k_hi + k_lo (bf16 each); S = q_hi.k_hi + q_lo.k_hi + q_hi.k_lo
+      // keeps the logits at ~2^-16 relative error although the logit scale multiplies them by up to 100.  The low
+      // halves ride in the 64 padding bytes of the operand rows: sQ = [q_hi | q_lo], sK = [k_hi | k_hi],
+      // sV = [v | k_lo] (P.V then also produces 32 unused output columns).
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t qw[4] = {qraw[c].x, qraw[c].y, qraw[c].z, qraw[c].w};
         const uint32_t kw[4] = {kraw[c].x, kraw[c].y, kraw[c].z, kraw[c].w};
-        uint32_t qo[4], ko[4];
+        uint32_t qo[4], ko[4], ql[4], kl[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          qo[e] = pack_bf16x2(bf16_lo(qw[e]) * qi, bf16_hi(qw[e]) * qi);
-          ko[e] = pack_bf16x2(bf16_lo(kw[e]) * ki, bf16_hi(kw[e]) * ki);
+          const float q0 = bf16_lo(qw[e]) * qi, q1 = bf16_hi(qw[e]) * qi;
+          const float k0 = bf16_lo(kw[e]) * ki, k1 = bf16_hi(kw[e]) * ki;
+          qo[e] = pack_bf16x2(q0, q1);
+          ko[e] = pack_bf16x2(k0, k1);
+          ql[e] = pack_bf16x2(q0 - bf16_lo(qo[e]), q1 - bf16_hi(qo[e]));
+          kl[e] = pack_bf16x2(k0 - bf16_lo(ko[e]), k1 - bf16_hi(ko[e]));
         }
         sts128(aQ + sw128_off(r, c), make_uint4(qo[0], qo[1], qo[2], qo[3]));
+        sts128(aQ + sw128_off(r, c + 4), make_uint4(ql[0], ql[1], ql[2], ql[3]));
         sts128(aK + sw128_off(r, c), make_uint4(ko[0], ko[1], ko[2], ko[3]));
-        sts128(aV + prob * 8192 + sw128_off(t, c), vraw[c]);
+        sts128(aK + sw128_off(r, c + 4), make_uint4(ko[0], ko[1], ko[2], ko[3]));
+        sts128(aV + sw128_off(r, c), vraw[c]);
+        sts128(aV + sw128_off(r, c + 4), make_uint4(kl[0], kl[1], kl[2], kl[3]));
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 8; ++c) {
         sts128(aQ + sw128_off(r, c), make_uint4(0, 0, 0, 0));
         sts128(aK + sw128_off(r, c), make_uint4(0, 0, 0, 0));
-        sts128(aV + prob * 8192 + sw128_off(t, c), make_uint4(0, 0, 0, 0));
+        sts128(aV + sw128_off(r, c), make_uint4(0, 0, 0, 0));
       }
     }
     sreg[r] = region;
@@ -727,9 +738,13 @@ window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
     if (r == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
+      for (int k = 0; k < 4; ++k)   // [q_hi | q_lo] . [k_hi | k_hi]
         umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
                   idesc_s, k);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)   // q_hi . k_lo (k_lo lives in the second half of the V rows)
+        umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aV + (k + 2) * 32, 16, 1024),
+                  idesc_s, 1u);
       umma_commit(&bar[0]);
     }
     mbar_wait(&bar[0], phase);
@@ -1094,13 +1109,24 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
         for (int e = 0; e < 4; ++e) ss = fmaf(bf16_lo(wv[e]), bf16_lo(wv[e]), fmaf(bf16_hi(wv[e]), bf16_hi(wv[e]), ss));
       }
       inv_norm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      // split-bf16 operands exactly as in the forward kernel: sQ = [q_hi | q_lo], sK = [k_hi | k_hi], sV = [v | k_lo]
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t wv[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
-        uint32_t o[4];
+        uint32_t o[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(bf16_lo(wv[e]) * inv_norm, bf16_hi(wv[e]) * inv_norm);
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = bf16_lo(wv[e]) * inv_norm, x1 = bf16_hi(wv[e]) * inv_norm;
+          o[e] = pack_bf16x2(x0, x1);
+          lo[e] = pack_bf16x2(x0 - bf16_lo(o[e]), x1 - bf16_hi(o[e]));
+        }
         sts128(my_tile + sw128_off(r, c), make_uint4(o[0], o[1], o[2], o[3]));
+        if (h == 0) {
+          sts128(aQ + sw128_off(r, c + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+        } else {
+          sts128(aK + sw128_off(r, c + 4), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(aV + sw128_off(r, c + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+        }
       }
       if (h == 0) sts_f32(aReg + r * 4, __int_as_float(region));
     } else {
@@ -1114,9 +1140,13 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
+      for (int k = 0; k < 4; ++k)   // [q_hi | q_lo] . [k_hi | k_hi]
         umma_bf16(tmem, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
                   idesc_kk, k);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)   // q_hi . k_lo
+        umma_bf16(tmem, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aV + (k + 2) * 32, 16, 1024),
+                  idesc_kk, 1u);
 #pragma unroll
       for (int k = 0; k < 2; ++k)
         umma_bf16(tmem + 128, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024),
