@@ -126,9 +126,9 @@ def test_swin_block_forward_backward(dim, heads, res, ws, shift):
     for k, p in m.named_parameters():
         assert p.grad is not None, k
         e = rel_l2(p.grad, po[k].grad)
-        # logit_scale: `heads` numbers, each a sum over every (query, key) pair of dS * cos — the bf16 rounding of the
-        # normalised tensor-core operands (|q_hat| = 1 +- 2^-9) does not average out as it does elsewhere
-        assert e < (5e-2 if k.endswith('logit_scale') else 3e-2), (k, e)
+        # (logit_scale is a sum over every (query, key) pair of dS * cos; it only meets this bar because the kernels
+        # form the cosine from split-bf16 operands — plain bf16 q_hat / k_hat left it at 3-5e-2)
+        assert e < 3e-2, (k, e)
 
 
 def test_swinv2_network_forward_features_and_backward():

@@ -666,18 +666,20 @@ window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
   const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
 
-  uint32_t phase = 0;
-  for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
-    // ---- gather this row's token, normalise q / k, write the operand rows
+  // rows of a pair: the next pair's q / k / v travel while the current one is in the tensor cores and the softmax
+  uint4 qraw[4], kraw[4], vraw[4];
+  long long nrow = 0;
+  int nregion = 0;
+  bool nvalid = false;
+  auto fetch = [&](int pair) {
     const int w = pair * 2 + prob;
-    const bool valid = tok_ok && w < total_windows;
-    long long my_row = 0;
-    int region = 0;
-    uint4 qraw[4], kraw[4], vraw[4];
-    if (valid) {
+    nvalid = tok_ok && pair < total_pairs && w < total_windows;
+    nrow = 0;
+    nregion = 0;
+    if (nvalid) {
       const int wx = w % g.nwx, wy = (w / g.nwx) % g.nwy, b = w / (g.nwx * g.nwy);
-      my_row = token_row(g, b, wy, wx, t, region);
-      const uint4* base = reinterpret_cast<const uint4*>(qkv + my_row * 3 * g.C + head * kHd);
+      nrow = token_row(g, b, wy, wx, t, nregion);
+      const uint4* base = reinterpret_cast<const uint4*>(qkv + nrow * 3 * g.C + head * kHd);
       const int cstep = g.C / 8;  // uint4 per C bf16
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -685,6 +687,17 @@ window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
         kraw[c] = __ldg(base + cstep + c);
         vraw[c] = __ldg(base + 2 * cstep + c);
       }
+    }
+  };
+  fetch(grp);
+
+  uint32_t phase = 0;
+  for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
+    // ---- this row's token: normalise q / k, write the operand rows
+    const bool valid = nvalid;
+    const long long my_row = nrow;
+    const int region = nregion;
+    if (valid) {
       float qq = 0.f, kk = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -747,6 +760,7 @@ window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
                   idesc_s, 1u);
       umma_commit(&bar[0]);
     }
+    fetch(pair + groups);
     mbar_wait(&bar[0], phase);
     tc_fence_after();
     // ---- softmax of this row over its own window's keys
