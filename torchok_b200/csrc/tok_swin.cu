@@ -835,6 +835,219 @@ window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   if (warp == 0) tmem_dealloc(tmem_s, 256);
 }
 
+// Forward, second layout: the same UMMA chains, but TWO threads per row (256 threads, warps 0-3 own key columns 0-31 of
+// the row's window, warps 4-7 columns 32-63) and two CTAs per SM, so sixteen warps hide each other's latencies where
+// the one-thread-per-row kernel above was issue-bound (2300 instructions per row and iteration on 8 warps per SM).
+// The two halves of a row merge their (max, sum) once through shared memory (online-softmax merge).  Gather roles:
+// half 0 stages q (hi | lo) and v, half 1 stages k (hi | hi, lo into the v rows); O columns are split 16 / 16.
+constexpr int kTc2Threads = 256;
+constexpr int kTc2Smem = 3 * 16384 + 32768 + kMaxN * kMaxN * 4 + 128 * 2 * 8 + 128 * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(kTc2Threads, 2)
+window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
+                           const float* __restrict__ logit_scale, const float* __restrict__ bias,
+                           __nv_bfloat16* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t aQ = smem_u32(smem), aK = aQ + 16384, aV = aK + 16384, aP = aV + 16384;
+  const uint32_t aBias = aP + 32768;               // float [N][N]
+  const uint32_t aX = aBias + kMaxN * kMaxN * 4;   // float2 [128 rows][2 halves]: (max, sum)
+  const uint32_t aReg = aX + 128 * 2 * 8;          // int [128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (aReg - aQ) + 128 * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+  const int N = g.ws * g.ws;
+  const int head = blockIdx.x % g.heads;
+  const int grp = blockIdx.x / g.heads;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int h = warp >> 2;                      // column half / gather role
+  const int r = (warp & 3) * 32 + (tid & 31);   // stacked row = TMEM lane
+  const int prob = r >> 6;
+  const int t = r & 63;
+  const float scale = __expf(fminf(logit_scale[head], 4.6051702f));
+  const int total_windows = g.B * g.nwy * g.nwx;
+  const int total_pairs = (total_windows + 1) / 2;
+
+  for (int i = tid; i < (3 * 16384 + 32768) / 16; i += kTc2Threads) sts128(aQ + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < N * N; i += kTc2Threads) sts_f32(aBias + i * 4, bias[(long long)head * N * N + i]);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = *tmem_slot;      // S: columns [0, 128)
+  const uint32_t tmem_o = tmem_s + 128;    // O: columns [128, 192)
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+
+  uint32_t phase = 0;
+  for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
+    const int w = pair * 2 + prob;
+    const bool valid = t < N && w < total_windows;
+    long long my_row = 0;
+    int region = 0;
+    if (valid) {
+      const int wx = w % g.nwx, wy = (w / g.nwx) % g.nwy, b = w / (g.nwx * g.nwy);
+      my_row = token_row(g, b, wy, wx, t, region);
+      const uint4* base = reinterpret_cast<const uint4*>(qkv + my_row * 3 * g.C + head * kHd);
+      const int cstep = g.C / 8;
+      uint4 xr[4], vr[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        xr[c] = __ldg(base + h * cstep + c);            // q (half 0) or k (half 1)
+        if (h == 0) vr[c] = __ldg(base + 2 * cstep + c);
+      }
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t wv[4] = {xr[c].x, xr[c].y, xr[c].z, xr[c].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ss = fmaf(bf16_lo(wv[e]), bf16_lo(wv[e]), fmaf(bf16_hi(wv[e]), bf16_hi(wv[e]), ss));
+      }
+      const float inv_norm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      // split-bf16 cosine operands (see window_attn_fwd_tc_kernel): sQ = [q_hi | q_lo], sK = [k_hi | k_hi], sV = [v | k_lo]
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t wv[4] = {xr[c].x, xr[c].y, xr[c].z, xr[c].w};
+        uint32_t o[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x0 = bf16_lo(wv[e]) * inv_norm, x1 = bf16_hi(wv[e]) * inv_norm;
+          o[e] = pack_bf16x2(x0, x1);
+          lo[e] = pack_bf16x2(x0 - bf16_lo(o[e]), x1 - bf16_hi(o[e]));
+        }
+        if (h == 0) {
+          sts128(aQ + sw128_off(r, c), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(aQ + sw128_off(r, c + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          sts128(aV + sw128_off(r, c), vr[c]);
+        } else {
+          sts128(aK + sw128_off(r, c), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(aK + sw128_off(r, c + 4), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(aV + sw128_off(r, c + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (h == 0) {
+          sts128(aQ + sw128_off(r, c), make_uint4(0, 0, 0, 0));
+          sts128(aQ + sw128_off(r, c + 4), make_uint4(0, 0, 0, 0));
+          sts128(aV + sw128_off(r, c), make_uint4(0, 0, 0, 0));
+        } else {
+          sts128(aK + sw128_off(r, c), make_uint4(0, 0, 0, 0));
+          sts128(aK + sw128_off(r, c + 4), make_uint4(0, 0, 0, 0));
+          sts128(aV + sw128_off(r, c + 4), make_uint4(0, 0, 0, 0));
+        }
+      }
+    }
+    if (h == 0) sts_f32(aReg + r * 4, __int_as_float(region));
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
+                  idesc_s, k);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aV + (k + 2) * 32, 16, 1024),
+                  idesc_s, 1u);
+      umma_commit(&bar[0]);
+    }
+    mbar_wait(&bar[0], phase);
+    tc_fence_after();
+    // ---- softmax of this half-row, merged with the other half
+    float e[32];
+    float mx = -INFINITY;
+    {
+      uint32_t sraw[32];
+      tmem_ld_32x32b_x32(tmem_s + lane_addr + prob * 64 + h * 32, sraw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int key = h * 32 + j;
+        float sc = -INFINITY;
+        if (valid && key < N) {
+          const int kreg = __float_as_int(lds_f32(aReg + (prob * 64 + key) * 4));
+          sc = fmaf(__uint_as_float(sraw[j]), scale, lds_f32(aBias + (t * N + key) * 4)) + (kreg != region ? -100.f : 0.f);
+        }
+        e[j] = sc;
+        mx = fmaxf(mx, sc);
+      }
+    }
+    float lsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      e[j] = mx > -INFINITY ? __expf(e[j] - mx) : 0.f;
+      lsum += e[j];
+    }
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(aX + (r * 2 + h) * 8), "f"(mx), "f"(lsum) : "memory");
+    __syncthreads();
+    float factor = 0.f;
+    {
+      float m0, l0, m1, l1;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m0), "=f"(l0), "=f"(m1), "=f"(l1) : "r"(aX + r * 16));
+      const float m = fmaxf(m0, m1);
+      const float f0 = m0 > -INFINITY ? __expf(m0 - m) : 0.f, f1 = m1 > -INFINITY ? __expf(m1 - m) : 0.f;
+      const float l = l0 * f0 + l1 * f1;
+      if (valid && l > 0.f) factor = (h == 0 ? f0 : f1) / l;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o4[4];
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) o4[q2] = pack_bf16x2(e[c * 8 + 2 * q2] * factor, e[c * 8 + 2 * q2 + 1] * factor);
+      sts128(aP + prob * 16384 + sw128_off(r, 4 * h + c), make_uint4(o4[0], o4[1], o4[2], o4[3]));
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- O = [P_A; 0] . V_A + [0; P_B] . V_B
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_o, make_smem_desc_sw128(aP + kb * 16384 + k * 32, 16, 1024),
+                    make_smem_desc_sw128(aV + kb * 8192 + k * 2048, 8192, 1024), idesc_o, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&bar[1]);
+    }
+    mbar_wait(&bar[1], phase);
+    tc_fence_after();
+    {
+      uint32_t acc[16];
+      tmem_ld_32x32b_x16(tmem_o + lane_addr + h * 16, acc);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* op = reinterpret_cast<uint4*>(out + my_row * g.C + head * kHd + h * 16);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          op[c] = make_uint4(pack_bf16x2(__uint_as_float(acc[c * 8]), __uint_as_float(acc[c * 8 + 1])),
+                             pack_bf16x2(__uint_as_float(acc[c * 8 + 2]), __uint_as_float(acc[c * 8 + 3])),
+                             pack_bf16x2(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5])),
+                             pack_bf16x2(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7])));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM and the operand tiles are free for the next pair
+    tc_fence_after();
+  }
+  if (warp == 0) tmem_dealloc(tmem_s, 256);
+}
+
 // Backward.  One CTA per (head, group); the CTA loops over the windows of its group so that the bias / logit-scale
 // gradients accumulate on chip and are flushed once.  Pass 1 (thread = query row i): softmax statistics, O_i,
 // delta_i = dO_i . O_i, dq_i.  Pass 2 (thread = key row j): dk_j, dv_j, dbias[:, j].  Row vectors live in registers,
@@ -1522,6 +1735,23 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
   int rc = attn_geom(&g, B, H, W, C, heads, ws, shift);
   if (rc) return rc;
   static const bool use_cuda_cores = getenv("TOK_ATTN_CUDA_CORES") != nullptr;  // bring-up aid: the round-1 fp32 kernel
+  static const bool use_v1 = getenv("TOK_ATTN_FWD_V1") != nullptr;   // the one-thread-per-row tcgen05 kernel
+  if (!use_cuda_cores && !use_v1 && (C % 8) == 0) {
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e = cudaFuncSetAttribute(window_attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem);
+      if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_fwd: %s", cudaGetErrorString(e));
+      configured2 = true;
+    }
+    const int pairs = (B * g.nwy * g.nwx + 1) / 2;
+    int groups = (148 * 2) / heads;   // two CTAs per SM (shared memory, registers); one more CTA would be a second wave
+    if (groups < 1) groups = 1;
+    if (groups > pairs) groups = pairs;
+    window_attn_fwd_tc2_kernel<<<(unsigned)(groups * heads), kTc2Threads, kTc2Smem, (cudaStream_t)stream>>>(
+        g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out);
+    TOK_CHECK_LAUNCH("window_attn_fwd_tc2");
+    return TOK_OK;
+  }
   if (!use_cuda_cores && (C % 8) == 0) {
     static bool configured = false;
     if (!configured) {
