@@ -178,6 +178,16 @@ int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, 
                       const void* dout, const float* rowscale, int rows_per_sample, void* dx, float* dgamma,
                       float* dbeta, float* dxsum, void* stream);
 int tok_layernorm_has_dxsum(int C);
+/* timm PatchEmbed.proj = Conv2d(3, E, kernel 4, stride 4) followed by flatten(2).transpose(1, 2)
+ * (torchok/models/backbones/swin.py:156-171 constructs it): `image` is the (B, 3, H, W) fp32 NCHW batch exactly as the
+ * task hands it over, `tokens` the (B * H/4 * W/4, E) bf16 matrix.  `weight` / `dweight` are fp32 (E, 3, 4, 4) tensors
+ * addressed through `wstride` = their four element strides (the masters live in channels_last memory).  Backward
+ * ACCUMULATES dweight / dbias (no image gradient: the image is the network input).  E % 32 == 0, E <= 256. */
+int tok_patch_embed_supported(int Cin, int patch, int H, int W, int E);
+int tok_patch_embed_fwd(int B, int H, int W, int E, const float* image, const float* weight, const float* bias,
+                        const int* wstride, void* tokens, void* stream);
+int tok_patch_embed_bwd(int B, int H, int W, int E, const float* image, const void* dtokens, const int* wstride,
+                        float* dweight, float* dbias, void* stream);
 /* timm PatchMerging gather on a (B, H, W, C) bf16 tensor: dst[b,i,j,q*C+c] = src[b, 2i+(q&1), 2j+(q>>1), c] (q = 0..3, the
  * order of torch.cat([x[:,0::2,0::2], x[:,1::2,0::2], x[:,0::2,1::2], x[:,1::2,1::2]], -1)); inverse != 0 scatters back
  * (the backward).  H, W even, C % 8 == 0. */

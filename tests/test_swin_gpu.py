@@ -77,6 +77,29 @@ def test_layernorm_colsum(rows, c):
     assert rel_err(lin_bias.grad, xo.grad.sum(0)) < 1e-2
 
 
+@pytest.mark.parametrize('b,hw,e', [(3, 32, 96), (2, 224, 96), (2, 64, 128)])
+def test_patch_embed(b, hw, e):
+    """timm PatchEmbed.proj (Conv2d(3, E, 4, 4) on the NCHW image) + flatten/transpose; weights in channels_last memory
+    as the parameter arena keeps them."""
+    from torchok_b200 import kernels as K
+    assert K.patch_embed_supported(3, 4, hw, hw, e)
+    torch.manual_seed(e + hw)
+    x = torch.randn(b, 3, hw, hw)
+    w = torch.randn(e, 3, 4, 4) * 0.2
+    bias = torch.randn(e) * 0.1
+    wo, bo = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = F.conv2d(x, wo, bo, stride=4).flatten(2).transpose(1, 2).reshape(-1, e)
+    g = _bf(torch.randn_like(ref))
+    (ref * g).sum().backward()
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        wm = w.cuda().contiguous(memory_format=fmt).requires_grad_(True)
+        bm = bias.cuda().requires_grad_(True)
+        out = K.patch_embed(x.cuda(), wm, bm)
+        (out.float() * g.cuda()).sum().backward()
+        assert rel_err(out, ref) < 1e-2
+        assert rel_err(wm.grad, wo.grad) < 1e-3 and rel_err(bm.grad, bo.grad) < 1e-3
+
+
 def test_patch_merge_is_the_reference_cat():
     """timm PatchMerging gather: bit-exact against torch.cat of the four strided slices, forward and backward."""
     from torchok_b200 import kernels as K

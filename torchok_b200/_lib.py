@@ -47,6 +47,9 @@ _SIGS = {
     'tok_linear_fwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'tok_linear_dgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_linear_dgrad_add': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'tok_patch_embed_supported': (_i, [_i, _i, _i, _i, _i]),
+    'tok_patch_embed_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_patch_embed_bwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_patch_merge': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
     'tok_linear_wgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_stem_geometry': (None, [_i, _i, _pi, _pi, _pi, _pi]),
@@ -102,7 +105,7 @@ _SIGS = {
     'tok_adam_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
 }
-_RAW = {'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+_RAW = {'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}
 
 

@@ -535,9 +535,23 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
         if (p.bias != nullptr) {
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+            // 8 x LDG.128 instead of 32 scalar loads per thread and chunk (the linear layers of the Swin blocks spent
+            // as many instructions fetching the bias as converting the tile)
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              v[4 * j] += b4.x;
+              v[4 * j + 1] += b4.y;
+              v[4 * j + 2] += b4.z;
+              v[4 * j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
         }
         // 128B-swizzled staging: 64-column blocks of [128 rows][128 B]; 16-byte chunk index XOR (row & 7)
         const int blk_off = (c >> 1) * (kBlockM * 128) + row * 128;

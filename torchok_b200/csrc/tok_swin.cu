@@ -451,6 +451,102 @@ gelu_bwd_vec_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, 
   }
 }
 
+// ---- patch embedding ----------------------------------------------------------------------------------------------
+// timm PatchEmbed (torchok/models/backbones/swin.py:156-171 builds it): Conv2d(3, E, kernel 4, stride 4) on the NCHW fp32
+// image, flatten(2).transpose(1, 2).  K = 3 * 4 * 4 = 48 is too thin for the tensor-core conv (it ran at 578 us plus an
+// 870 us NCHW->NHWC pass for 0.07 GFLOP/img); here one CTA takes one row of patches: the 12 image rows it needs are read
+// coalesced straight from NCHW into a [tokens][48] shared-memory patch matrix, thread (o, half) keeps row o of the
+// weight matrix in registers and walks half of the tokens with broadcast 16-byte shared loads.  fp32 math, bf16 out.
+constexpr int kPeK = 48;       // in_chans * patch * patch
+constexpr int kPePitch = 52;   // floats per patch row in shared memory (16-byte aligned, conflict-free 16-byte stores)
+
+__device__ __forceinline__ void pe_load_patches(const float* __restrict__ img, int b, int i, int H, int W, int TW,
+                                                float* __restrict__ sp) {
+  // image rows (c, 4i + dy), c < 3, dy < 4: W floats each, one float4 = the 4 dx of one (c, dy, token)
+  const int per_row = W / 4;
+  for (int idx = threadIdx.x; idx < 12 * per_row; idx += blockDim.x) {
+    const int rowi = idx / per_row, j = idx - rowi * per_row;
+    const int c = rowi >> 2, dy = rowi & 3;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(img + (((long long)b * 3 + c) * H + 4 * i + dy) * W) + j);
+    *reinterpret_cast<float4*>(sp + j * kPePitch + c * 16 + dy * 4) = v;
+  }
+}
+
+__global__ void __launch_bounds__(512)
+patch_embed_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                       int H, int W, int E, int sO, int sC, int sH, int sW, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) float sp[];
+  const int TH = H / 4, TW = W / 4;
+  const int b = blockIdx.x / TH, i = blockIdx.x - b * TH;
+  const int o = threadIdx.x % E, half = threadIdx.x / E;
+  float wr[kPeK];
+#pragma unroll
+  for (int k = 0; k < kPeK; ++k) wr[k] = __ldg(w + (long long)o * sO + (k >> 4) * sC + ((k >> 2) & 3) * sH + (k & 3) * sW);
+  const float bo = bias ? __ldg(bias + o) : 0.f;
+  pe_load_patches(img, b, i, H, W, TW, sp);
+  __syncthreads();
+  const int t0 = half * ((TW + 1) / 2), t1 = min(TW, t0 + (TW + 1) / 2);
+  for (int tk = t0; tk < t1; ++tk) {
+    float acc = bo;
+#pragma unroll
+    for (int k4 = 0; k4 < kPeK / 4; ++k4) {
+      const float4 pv = *reinterpret_cast<const float4*>(sp + tk * kPePitch + k4 * 4);
+      acc = fmaf(wr[k4 * 4], pv.x, acc);
+      acc = fmaf(wr[k4 * 4 + 1], pv.y, acc);
+      acc = fmaf(wr[k4 * 4 + 2], pv.z, acc);
+      acc = fmaf(wr[k4 * 4 + 3], pv.w, acc);
+    }
+    out[(((long long)b * TH + i) * TW + tk) * E + o] = __float2bfloat16(acc);
+  }
+}
+
+// dW[o][k] += sum_tokens dy[token][o] * patch[token][k], dbias[o] += sum dy: thread (o, half) accumulates its 48 + 1
+// values in registers over every patch row its CTA visits; halves merge in shared memory, CTAs with atomics.
+__global__ void __launch_bounds__(512)
+patch_embed_bwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int E,
+                       int sO, int sC, int sH, int sW, float* __restrict__ dw, float* __restrict__ dbias) {
+  extern __shared__ __align__(16) float sp[];
+  const int TH = H / 4, TW = W / 4;
+  const int o = threadIdx.x % E, half = threadIdx.x / E;
+  float acc[kPeK];
+#pragma unroll
+  for (int k = 0; k < kPeK; ++k) acc[k] = 0.f;
+  float accb = 0.f;
+  const int t0 = half * ((TW + 1) / 2), t1 = min(TW, t0 + (TW + 1) / 2);
+  for (int rowi = blockIdx.x; rowi < B * TH; rowi += gridDim.x) {
+    const int b = rowi / TH, i = rowi - b * TH;
+    __syncthreads();   // the previous row's patches are consumed
+    pe_load_patches(img, b, i, H, W, TW, sp);
+    __syncthreads();
+    for (int tk = t0; tk < t1; ++tk) {
+      const float g = __bfloat162float(dy[((long long)rowi * TW + tk) * E + o]);
+      accb += g;
+#pragma unroll
+      for (int k4 = 0; k4 < kPeK / 4; ++k4) {
+        const float4 pv = *reinterpret_cast<const float4*>(sp + tk * kPePitch + k4 * 4);
+        acc[k4 * 4] = fmaf(g, pv.x, acc[k4 * 4]);
+        acc[k4 * 4 + 1] = fmaf(g, pv.y, acc[k4 * 4 + 1]);
+        acc[k4 * 4 + 2] = fmaf(g, pv.z, acc[k4 * 4 + 2]);
+        acc[k4 * 4 + 3] = fmaf(g, pv.w, acc[k4 * 4 + 3]);
+      }
+    }
+  }
+  // merge the two halves through shared memory (reusing the patch buffer: E * 49 floats <= TW * 52 is checked by the host)
+  __syncthreads();
+  if (half == 1) {
+#pragma unroll
+    for (int k = 0; k < kPeK; ++k) sp[k * E + o] = acc[k];
+    sp[kPeK * E + o] = accb;
+  }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int k = 0; k < kPeK; ++k)
+      atomicAdd(dw + (long long)o * sO + (k >> 4) * sC + ((k >> 2) & 3) * sH + (k & 3) * sW, acc[k] + sp[k * E + o]);
+    if (dbias) atomicAdd(dbias + o, accb + sp[kPeK * E + o]);
+  }
+}
+
 // ---- PatchMerging gather -----------------------------------------------------------------------------------------
 // timm PatchMerging (used by torchok/models/backbones/swin.py:71-81 through BasicLayer.downsample):
 //   cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)  on a (B, H, W, C) tensor.
@@ -889,23 +985,36 @@ window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restri
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
 
-  uint32_t phase = 0;
-  for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
+  // the next pair's rows are fetched while P . V and the output store of the current pair run (registers are free then)
+  uint4 xr[4], vr[4];
+  long long nrow = 0;
+  int nregion = 0;
+  bool nvalid = false;
+  auto fetch = [&](int pair) {
     const int w = pair * 2 + prob;
-    const bool valid = t < N && w < total_windows;
-    long long my_row = 0;
-    int region = 0;
-    if (valid) {
+    nvalid = t < N && pair < total_pairs && w < total_windows;
+    nrow = 0;
+    nregion = 0;
+    if (nvalid) {
       const int wx = w % g.nwx, wy = (w / g.nwx) % g.nwy, b = w / (g.nwx * g.nwy);
-      my_row = token_row(g, b, wy, wx, t, region);
-      const uint4* base = reinterpret_cast<const uint4*>(qkv + my_row * 3 * g.C + head * kHd);
+      nrow = token_row(g, b, wy, wx, t, nregion);
+      const uint4* base = reinterpret_cast<const uint4*>(qkv + nrow * 3 * g.C + head * kHd);
       const int cstep = g.C / 8;
-      uint4 xr[4], vr[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         xr[c] = __ldg(base + h * cstep + c);            // q (half 0) or k (half 1)
         if (h == 0) vr[c] = __ldg(base + 2 * cstep + c);
       }
+    }
+  };
+  fetch(grp);
+
+  uint32_t phase = 0;
+  for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
+    const bool valid = nvalid;
+    const long long my_row = nrow;
+    const int region = nregion;
+    if (valid) {
       float ss = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -1025,6 +1134,7 @@ window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restri
       }
       umma_commit(&bar[1]);
     }
+    fetch(pair + groups);
     mbar_wait(&bar[1], phase);
     tc_fence_after();
     {
@@ -1704,6 +1814,51 @@ int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, fl
   gelu_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)x, (const __nv_bfloat162*)dy,
                                                                      (__nv_bfloat162*)dx, n / 2);
   TOK_CHECK_LAUNCH("gelu_bwd");
+  return TOK_OK;
+}
+
+int tok_patch_embed_supported(int Cin, int patch, int H, int W, int E) {
+  if (Cin != 3 || patch != 4 || H <= 0 || W <= 0 || (H % 4) || (W % 4)) return 0;
+  if (E < 32 || (E % 32) || 2 * E > 512) return 0;
+  const int TW = W / 4;
+  if (TW * kPePitch < E * (kPeK + 1) || TW * kPePitch * 4 > 160 * 1024) return 0;   // the backward reuses the patch buffer
+  return 1;
+}
+
+int tok_patch_embed_fwd(int B, int H, int W, int E, const float* image, const float* weight, const float* bias,
+                        const int* wstride, void* tokens, void* stream) {
+  if (B <= 0 || !tok_patch_embed_supported(3, 4, H, W, E))
+    return set_error(TOK_ERR_INVALID, "patch_embed: unsupported shape (tok_patch_embed_supported)");
+  const int smem = (W / 4) * kPePitch * 4;
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(patch_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(patch_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "patch_embed: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  patch_embed_fwd_kernel<<<(unsigned)(B * (H / 4)), 2 * E, smem, (cudaStream_t)stream>>>(
+      image, weight, bias, H, W, E, wstride[0], wstride[1], wstride[2], wstride[3], (__nv_bfloat16*)tokens);
+  TOK_CHECK_LAUNCH("patch_embed_fwd");
+  return TOK_OK;
+}
+
+int tok_patch_embed_bwd(int B, int H, int W, int E, const float* image, const void* dtokens, const int* wstride,
+                        float* dweight, float* dbias, void* stream) {
+  if (B <= 0 || !tok_patch_embed_supported(3, 4, H, W, E))
+    return set_error(TOK_ERR_INVALID, "patch_embed: unsupported shape (tok_patch_embed_supported)");
+  const int smem = (W / 4) * kPePitch * 4;
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(patch_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "patch_embed: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  long long ctas = (long long)B * (H / 4);
+  if (ctas > 148 * 2) ctas = 148 * 2;
+  patch_embed_bwd_kernel<<<(unsigned)ctas, 2 * E, smem, (cudaStream_t)stream>>>(
+      image, (const __nv_bfloat16*)dtokens, B, H, W, E, wstride[0], wstride[1], wstride[2], wstride[3], dweight, dbias);
+  TOK_CHECK_LAUNCH("patch_embed_bwd");
   return TOK_OK;
 }
 

@@ -1002,3 +1002,49 @@ class PatchMergeFn(torch.autograd.Function):
 
 def patch_merge(x, b, h, w):
     return PatchMergeFn.apply(x, b, h, w)
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """timm PatchEmbed.proj (Conv2d(3, E, 4, stride 4)) + flatten(2).transpose(1, 2) on the NCHW image: (B*H/4*W/4, E)
+    bf16 tokens.  Reads the fp32 NCHW batch directly (no layout pass); weight / bias gradients are accumulated into
+    `.grad`; the image gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        require_cuda(x, 'image')
+        b, c, h, w = x.shape
+        e = weight.shape[0]
+        x = x.detach().float().contiguous()
+        wst = (C.c_int * 4)(*weight.stride())
+        out = torch.empty((b * (h // 4) * (w // 4), e), dtype=BF16, device=x.device)
+        lib().tok_patch_embed_fwd(b, h, w, e, _p(x), _p(weight), _p(bias), wst, _p(out), _st())
+        ctx.save_for_backward(x)
+        ctx.params = (weight, bias)
+        ctx.geom = (b, h, w, e)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        weight, bias = ctx.params
+        b, h, w, e = ctx.geom
+        g = g.to(BF16).contiguous()
+        gw = grad_buffer(weight)
+        if gw.stride() != weight.stride():
+            raise RuntimeError('patch_embed: gradient buffer and weight must share their memory layout')
+        gb = grad_buffer(bias) if bias is not None and bias.requires_grad else None
+        wst = (C.c_int * 4)(*weight.stride())
+        lib().tok_patch_embed_bwd(b, h, w, e, _p(x), _p(g), wst, _p(gw), _p(gb), _st())
+        grad_ready(weight)
+        if bias is not None:
+            grad_ready(bias)
+        return None, None, None
+
+
+def patch_embed_supported(cin, patch, h, w, e):
+    return bool(lib().tok_patch_embed_supported(int(cin), int(patch), int(h), int(w), int(e)))
+
+
+def patch_embed(x, weight, bias):
+    # weight / bias are passed as non-differentiable handles: their gradients go straight into the arena buffers
+    return PatchEmbedFn.apply(x, weight, bias)

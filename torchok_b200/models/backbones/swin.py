@@ -216,8 +216,12 @@ class PatchEmbed(nn.Module):
         b, c, h, w = x.shape
         if (h, w) != self.img_size:
             raise AssertionError(f"Input image size ({h}*{w}) doesn't match model ({self.img_size[0]}*{self.img_size[1]}).")
-        y = ConvFn.apply(x, self.proj, False, self.proj.weight, self.proj.bias)   # (B, C, H/4, W/4), NHWC memory
-        tokens = y.permute(0, 2, 3, 1).reshape(-1, y.shape[1])
+        ph, pw = self.patch_size
+        if ph == pw and self.proj.bias is not None and K.patch_embed_supported(c, ph, h, w, self.proj.out_channels):
+            tokens = K.patch_embed(x, self.proj.weight, self.proj.bias)   # direct kernel on the NCHW fp32 image
+        else:
+            y = ConvFn.apply(x, self.proj, False, self.proj.weight, self.proj.bias)   # (B, C, H/4, W/4), NHWC memory
+            tokens = y.permute(0, 2, 3, 1).reshape(-1, y.shape[1])
         return self.norm(tokens) if not isinstance(self.norm, nn.Identity) else tokens
 
 
