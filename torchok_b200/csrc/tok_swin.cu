@@ -531,7 +531,7 @@ patch_embed_bwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __res
       }
     }
   }
-  // merge the two halves through shared memory (reusing the patch buffer: E * 49 floats <= TW * 52 is checked by the host)
+  // merge the two halves through shared memory (the buffer is sized for max(patch rows, 49 * E) floats by the host)
   __syncthreads();
   if (half == 1) {
 #pragma unroll
@@ -1817,11 +1817,16 @@ int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, fl
   return TOK_OK;
 }
 
+// patch rows of one CTA, or (backward) the [49][E] merge buffer of the two token halves, whichever is larger
+static int pe_smem_bytes(int W, int E) {
+  const int a = (W / 4) * kPePitch, b = E * (kPeK + 1);
+  return (a > b ? a : b) * 4;
+}
+
 int tok_patch_embed_supported(int Cin, int patch, int H, int W, int E) {
   if (Cin != 3 || patch != 4 || H <= 0 || W <= 0 || (H % 4) || (W % 4)) return 0;
   if (E < 32 || (E % 32) || 2 * E > 512) return 0;
-  const int TW = W / 4;
-  if (TW * kPePitch < E * (kPeK + 1) || TW * kPePitch * 4 > 160 * 1024) return 0;   // the backward reuses the patch buffer
+  if (pe_smem_bytes(W, E) > 160 * 1024) return 0;
   return 1;
 }
 
@@ -1829,7 +1834,7 @@ int tok_patch_embed_fwd(int B, int H, int W, int E, const float* image, const fl
                         const int* wstride, void* tokens, void* stream) {
   if (B <= 0 || !tok_patch_embed_supported(3, 4, H, W, E))
     return set_error(TOK_ERR_INVALID, "patch_embed: unsupported shape (tok_patch_embed_supported)");
-  const int smem = (W / 4) * kPePitch * 4;
+  const int smem = pe_smem_bytes(W, E);
   static int configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(patch_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1847,7 +1852,7 @@ int tok_patch_embed_bwd(int B, int H, int W, int E, const float* image, const vo
                         float* dweight, float* dbias, void* stream) {
   if (B <= 0 || !tok_patch_embed_supported(3, 4, H, W, E))
     return set_error(TOK_ERR_INVALID, "patch_embed: unsupported shape (tok_patch_embed_supported)");
-  const int smem = (W / 4) * kPePitch * 4;
+  const int smem = pe_smem_bytes(W, E);
   static int configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(patch_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
