@@ -474,39 +474,45 @@ __device__ __forceinline__ void pe_load_patches(const float* __restrict__ img, i
 
 __global__ void __launch_bounds__(512)
 patch_embed_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
-                       int H, int W, int E, int sO, int sC, int sH, int sW, __nv_bfloat16* __restrict__ out) {
+                       int B, int H, int W, int E, int sO, int sC, int sH, int sW, __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) float sp[];
   const int TH = H / 4, TW = W / 4;
-  const int b = blockIdx.x / TH, i = blockIdx.x - b * TH;
   const int o = threadIdx.x % E, half = threadIdx.x / E;
+  // persistent CTA: the weight row is fetched once (it was 48 uncoalesced loads per thread and patch row otherwise)
   float wr[kPeK];
 #pragma unroll
   for (int k = 0; k < kPeK; ++k) wr[k] = __ldg(w + (long long)o * sO + (k >> 4) * sC + ((k >> 2) & 3) * sH + (k & 3) * sW);
   const float bo = bias ? __ldg(bias + o) : 0.f;
-  pe_load_patches(img, b, i, H, W, TW, sp);
-  __syncthreads();
   const int t0 = half * ((TW + 1) / 2), t1 = min(TW, t0 + (TW + 1) / 2);
-  for (int tk = t0; tk < t1; ++tk) {
-    float acc = bo;
+  for (int rowi = blockIdx.x; rowi < B * TH; rowi += gridDim.x) {
+    const int b = rowi / TH, i = rowi - b * TH;
+    __syncthreads();   // the previous row's patches are consumed
+    pe_load_patches(img, b, i, H, W, TW, sp);
+    __syncthreads();
+    for (int tk = t0; tk < t1; ++tk) {
+      float acc = bo;
 #pragma unroll
-    for (int k4 = 0; k4 < kPeK / 4; ++k4) {
-      const float4 pv = *reinterpret_cast<const float4*>(sp + tk * kPePitch + k4 * 4);
-      acc = fmaf(wr[k4 * 4], pv.x, acc);
-      acc = fmaf(wr[k4 * 4 + 1], pv.y, acc);
-      acc = fmaf(wr[k4 * 4 + 2], pv.z, acc);
-      acc = fmaf(wr[k4 * 4 + 3], pv.w, acc);
+      for (int k4 = 0; k4 < kPeK / 4; ++k4) {
+        const float4 pv = *reinterpret_cast<const float4*>(sp + tk * kPePitch + k4 * 4);
+        acc = fmaf(wr[k4 * 4], pv.x, acc);
+        acc = fmaf(wr[k4 * 4 + 1], pv.y, acc);
+        acc = fmaf(wr[k4 * 4 + 2], pv.z, acc);
+        acc = fmaf(wr[k4 * 4 + 3], pv.w, acc);
+      }
+      out[((long long)rowi * TW + tk) * E + o] = __float2bfloat16(acc);
     }
-    out[(((long long)b * TH + i) * TW + tk) * E + o] = __float2bfloat16(acc);
   }
 }
 
 // dW[o][k] += sum_tokens dy[token][o] * patch[token][k], dbias[o] += sum dy: thread (o, half) accumulates its 48 + 1
-// values in registers over every patch row its CTA visits; halves merge in shared memory, CTAs with atomics.
+// values in registers over every patch row its CTA visits (the row of dy is staged in shared memory next to the
+// patches, so no thread waits on a global load inside the token loop); halves merge in shared memory, CTAs with atomics.
 __global__ void __launch_bounds__(512)
 patch_embed_bwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int E,
                        int sO, int sC, int sH, int sW, float* __restrict__ dw, float* __restrict__ dbias) {
   extern __shared__ __align__(16) float sp[];
   const int TH = H / 4, TW = W / 4;
+  __nv_bfloat16* sg = reinterpret_cast<__nv_bfloat16*>(sp + TW * kPePitch);   // [TW][E]
   const int o = threadIdx.x % E, half = threadIdx.x / E;
   float acc[kPeK];
 #pragma unroll
@@ -517,9 +523,13 @@ patch_embed_bwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __res
     const int b = rowi / TH, i = rowi - b * TH;
     __syncthreads();   // the previous row's patches are consumed
     pe_load_patches(img, b, i, H, W, TW, sp);
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(dy + (long long)rowi * TW * E);
+      for (int idx = threadIdx.x; idx < TW * E / 8; idx += blockDim.x) reinterpret_cast<uint4*>(sg)[idx] = __ldg(src + idx);
+    }
     __syncthreads();
     for (int tk = t0; tk < t1; ++tk) {
-      const float g = __bfloat162float(dy[((long long)rowi * TW + tk) * E + o]);
+      const float g = __bfloat162float(sg[tk * E + o]);
       accb += g;
 #pragma unroll
       for (int k4 = 0; k4 < kPeK / 4; ++k4) {
@@ -531,7 +541,7 @@ patch_embed_bwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __res
       }
     }
   }
-  // merge the two halves through shared memory (the buffer is sized for max(patch rows, 49 * E) floats by the host)
+  // merge the two halves through shared memory (the buffer is sized for max(patch rows + dy row, 49 * E floats))
   __syncthreads();
   if (half == 1) {
 #pragma unroll
@@ -1817,10 +1827,10 @@ int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, fl
   return TOK_OK;
 }
 
-// patch rows of one CTA, or (backward) the [49][E] merge buffer of the two token halves, whichever is larger
+// patch rows (+ the bf16 dy row in the backward) of one CTA, or the backward's [49][E] merge buffer, whichever is larger
 static int pe_smem_bytes(int W, int E) {
-  const int a = (W / 4) * kPePitch, b = E * (kPeK + 1);
-  return (a > b ? a : b) * 4;
+  const int a = (W / 4) * kPePitch * 4 + (W / 4) * E * 2, b = E * (kPeK + 1) * 4;
+  return a > b ? a : b;
 }
 
 int tok_patch_embed_supported(int Cin, int patch, int H, int W, int E) {
@@ -1842,8 +1852,10 @@ int tok_patch_embed_fwd(int B, int H, int W, int E, const float* image, const fl
     if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "patch_embed: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  patch_embed_fwd_kernel<<<(unsigned)(B * (H / 4)), 2 * E, smem, (cudaStream_t)stream>>>(
-      image, weight, bias, H, W, E, wstride[0], wstride[1], wstride[2], wstride[3], (__nv_bfloat16*)tokens);
+  long long ctas = (long long)B * (H / 4);
+  if (ctas > 148 * 3) ctas = 148 * 3;
+  patch_embed_fwd_kernel<<<(unsigned)ctas, 2 * E, smem, (cudaStream_t)stream>>>(
+      image, weight, bias, B, H, W, E, wstride[0], wstride[1], wstride[2], wstride[3], (__nv_bfloat16*)tokens);
   TOK_CHECK_LAUNCH("patch_embed_fwd");
   return TOK_OK;
 }
@@ -1860,7 +1872,7 @@ int tok_patch_embed_bwd(int B, int H, int W, int E, const float* image, const vo
     configured = smem;
   }
   long long ctas = (long long)B * (H / 4);
-  if (ctas > 148 * 2) ctas = 148 * 2;
+  if (ctas > 148 * 3) ctas = 148 * 3;
   patch_embed_bwd_kernel<<<(unsigned)ctas, 2 * E, smem, (cudaStream_t)stream>>>(
       image, (const __nv_bfloat16*)dtokens, B, H, W, E, wstride[0], wstride[1], wstride[2], wstride[3], dweight, dbias);
   TOK_CHECK_LAUNCH("patch_embed_bwd");
