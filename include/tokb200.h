@@ -56,6 +56,14 @@ void tok_conv_out_hw(const tokConvDesc* d, int* p, int* q);
  * to them (caller zero-fills): these are the BatchNorm batch statistics (torch.nn.BatchNorm2d training mode). */
 int tok_conv_fprop(const tokConvDesc* d, const void* x, const void* w, void* y, float* sum, float* sqsum,
                    const void* addend, const float* bias, int relu, void* stream);
+/* tok_conv_fprop (with statistics) + tok_bn_finalize_train in ONE launch — the Conv2d -> BatchNorm2d(training) pair of
+ * torchok/models/modules/bricks/convbnact.py:48-53: the last CTA of the persistent grid to finish (ticket in *counter, a
+ * zero-initialised 32-bit word owned by the BatchNorm layer, handed back zeroed) computes scale / shift / save_mean /
+ * save_invstd, updates the running statistics (torch.nn.BatchNorm2d semantics) and zeroes sum / sqsum. */
+int tok_conv_fprop_bn(const tokConvDesc* d, const void* x, const void* w, void* y, float* sum, float* sqsum,
+                      const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                      float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
+                      unsigned* counter, void* stream);
 
 /* dx = conv_transpose(dy, w).  `addend` (nullable, NHWC like dx, may alias dx) is added before the store.
  * `ws` is scratch of tok_conv_dgrad_workspace_bytes(d) bytes (needed for strided RxS>1 filters). */
@@ -126,6 +134,14 @@ int tok_bn_apply_bits(long long rows, int C, const void* y, const float* scale, 
 int tok_bn_bwd_reduce2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
                        const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
                        void* stream);
+/* tok_bn_bwd_reduce2 + tok_bn_bwd_finalize in one launch: the last CTA to finish (ticket in *counter, a zero-initialised
+ * 32-bit word owned by the BatchNorm layer, handed back zeroed) computes coef_a / coef_c1 / coef_c0 and the gamma / beta
+ * gradients from the completed sums and zeroes the accumulators. */
+int tok_bn_bwd_reduce2_finalize(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
+                                const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
+                                const float* save_mean, const float* save_invstd, const float* gamma, float* coef_a,
+                                float* coef_c1, float* coef_c0, float* dgamma, float* dbeta, int accumulate,
+                                unsigned* counter, void* stream);
 int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
                       const void* bits, const float* scale, const float* shift, const float* coef_a,
                       const float* coef_c1, const float* coef_c0, void* dy, void* dres, void* stream);

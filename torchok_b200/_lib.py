@@ -41,6 +41,7 @@ _SIGS = {
     'tok_debug_conv_profile': (_i, [_vp, _i]),
     'tok_conv_out_hw': (None, [_pd, _pi, _pi]),
     'tok_conv_fprop': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'tok_conv_fprop_bn': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_conv_dgrad_workspace_bytes': (_sz, [_pd]),
     'tok_conv_dgrad': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_conv_wgrad': (_i, [_pd, _vp, _vp, _vp, _vp]),
@@ -66,6 +67,8 @@ _SIGS = {
     'tok_bn_bwd_apply': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_apply_bits': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_reduce2': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_bn_bwd_reduce2_finalize': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _vp, _i, _vp, _vp]),
     'tok_bn_bwd_apply2': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_stem_bn_relu_pool_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_stem_bwd_reduce': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -323,8 +323,8 @@ void tok_conv_out_hw(const tokConvDesc* d, int* p, int* q) {
   *q = (d->w + 2 * d->pad - d->dil * (d->s - 1) - 1) / d->stride + 1;
 }
 
-int tok_conv_fprop(const tokConvDesc* d, const void* x, const void* w, void* y, float* sum, float* sqsum,
-                   const void* addend, const float* bias, int relu, void* stream) {
+static int conv_fprop_impl(const tokConvDesc* d, const void* x, const void* w, void* y, float* sum, float* sqsum,
+                           const void* addend, const float* bias, int relu, const FwdFin* fin, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   int P, Q;
@@ -342,8 +342,48 @@ int tok_conv_fprop(const tokConvDesc* d, const void* x, const void* w, void* y, 
   p.bias = bias;
   p.relu = relu;
   const long long M = (long long)d->n * P * Q;
+  if (fin) {
+    p.fin = *fin;
+    p.fin.count = (float)M;
+  }
   return run_fwd(x, d->n, d->h, d->w, d->c, src, M, w, d->k, (long long)d->r * d->s * d->c, false, d->k, 0, p,
                  static_cast<cudaStream_t>(stream));
+}
+
+int tok_conv_fprop(const tokConvDesc* d, const void* x, const void* w, void* y, float* sum, float* sqsum,
+                   const void* addend, const float* bias, int relu, void* stream) {
+  return conv_fprop_impl(d, x, w, y, sum, sqsum, addend, bias, relu, nullptr, stream);
+}
+
+int tok_conv_fprop_bn(const tokConvDesc* d, const void* x, const void* w, void* y, float* sum, float* sqsum,
+                      const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                      float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
+                      unsigned* counter, void* stream) {
+  if (!sum || !sqsum || !scale || !shift || !save_mean || !save_invstd || !counter)
+    return set_error(TOK_ERR_INVALID, "conv_fprop_bn: accumulators, outputs and the ticket counter are required");
+  static const bool v1 = getenv("TOK_CONV_V1") != nullptr;
+  if (v1) {   // the one-tile-per-CTA bring-up kernel has no fused finalize
+    int rc = conv_fprop_impl(d, x, w, y, sum, sqsum, nullptr, nullptr, 0, nullptr, stream);
+    if (rc) return rc;
+    int P, Q;
+    tok_conv_out_hw(d, &P, &Q);
+    return tok_bn_finalize_train(d->k, (double)d->n * P * Q, sum, sqsum, gamma, beta, eps, momentum, running_mean,
+                                 running_var, scale, shift, save_mean, save_invstd, stream);
+  }
+  FwdFin fin;
+  fin.counter = counter;
+  fin.count = 0.f;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.scale = scale;
+  fin.shift = shift;
+  fin.save_mean = save_mean;
+  fin.save_invstd = save_invstd;
+  return conv_fprop_impl(d, x, w, y, sum, sqsum, nullptr, nullptr, 0, &fin, stream);
 }
 
 size_t tok_conv_dgrad_workspace_bytes(const tokConvDesc* d) {

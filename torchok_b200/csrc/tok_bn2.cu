@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/tokb200.h"
 #include "tok_internal.h"
@@ -129,13 +130,32 @@ bn_apply_bits_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res,
 }
 
 // ------------------------------------------------------------------------------------------------ backward pass 1
+// Optional fused finalize: the LAST CTA to finish (ticket counter in global memory, handed back zeroed) turns the
+// per-channel sums into the coefficients of pass 2 and the gamma / beta gradients, so the 4-microsecond single-CTA
+// bn_bwd_finalize launch (and its launch gap) between the two passes disappears: 53 launches per ResNet-50 step.
+struct BwdFin {
+  unsigned* counter;   // nullptr: no fused finalize
+  float count;
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  float* coef_a;
+  float* coef_c1;
+  float* coef_c0;
+  float* dgamma;
+  float* dbeta;
+  int accumulate;
+  int C;
+};
+
 template <int MASK, bool HAS2>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2, const uint4* __restrict__ y,
                       const uint8_t* __restrict__ bits, const float* __restrict__ scale,
                       const float* __restrict__ shift, float* __restrict__ sum_g, float* __restrict__ sum_gy,
-                      long long rows, int cvec, int cvec_b, int rows_per_cta) {
+                      long long rows, int cvec, int cvec_b, int rows_per_cta, const BwdFin fin) {
   __shared__ float part[256 * 16];
+  __shared__ int s_last;
   const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
   float a1[8], a2[8];
 #pragma unroll
@@ -204,6 +224,33 @@ bn_bwd_reduce2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ 
     const int cl = o >> 4, k = o & 15;
     const int c = (blockIdx.y * cvec_b + cl) * 8 + (k & 7);
     if (c < cvec * 8) atomicAdd((k < 8 ? sum_g : sum_gy) + c, t);
+  }
+  if (fin.counter != nullptr) {
+    __threadfence();   // this CTA's contributions are ordered before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int c = threadIdx.x; c < fin.C; c += 256) {
+        const float sg = __ldcg(sum_g + c);
+        const float mu = fin.mean[c];
+        const float is = fin.invstd[c];
+        const float sgx = is * (__ldcg(sum_gy + c) - mu * sg);
+        sum_g[c] = 0.f;   // consumed: handed back zeroed (see bn_bwd_finalize_kernel)
+        sum_gy[c] = 0.f;
+        const float g = fin.gamma ? fin.gamma[c] : 1.f;
+        const float a = g * is;
+        const float k1 = sg / fin.count;
+        const float k2 = sgx / fin.count;
+        fin.coef_a[c] = a;
+        fin.coef_c1[c] = -a * k2 * is;
+        fin.coef_c0[c] = -a * k1 + a * k2 * is * mu;
+        if (fin.dgamma) fin.dgamma[c] = fin.accumulate ? fin.dgamma[c] + sgx : sgx;
+        if (fin.dbeta) fin.dbeta[c] = fin.accumulate ? fin.dbeta[c] + sg : sg;
+      }
+      if (threadIdx.x == 0) *fin.counter = 0u;
+    }
   }
 }
 
@@ -550,9 +597,9 @@ int tok_stem_bwd_apply(int n, int h, int w, int c, const void* dpooled, const vo
     else { KERNEL(MASK_BITS, __VA_ARGS__); }                                                  \
   } while (0)
 
-int tok_bn_bwd_reduce2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
-                       const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
-                       void* stream) {
+static int launch_bwd_reduce2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
+                              const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
+                              const BwdFin& fin, void* stream) {
   if (C <= 0 || (C % 8)) return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: C must be a positive multiple of 8 (got %d)", C);
   if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: no rows");
   if (mask_mode < 0 || mask_mode > 2 || (mask_mode == MASK_BITS && !bits) || (mask_mode == MASK_Y && (!scale || !shift)))
@@ -562,12 +609,43 @@ int tok_bn_bwd_reduce2(long long rows, int C, const void* dout, const void* dout
 #define K_REDUCE(M, H2)                                                                                        \
   bn_bwd_reduce2_kernel<M, H2><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y, \
                                                        (const uint8_t*)bits, scale, shift, sum_g, sum_gy, rows, \
-                                                       g.cvec, g.cvec_b, g.rows_per_cta)
+                                                       g.cvec, g.cvec_b, g.rows_per_cta, fin)
   if (dout2) TOK_BN2_DISPATCH_MASK(K_REDUCE, true);
   else TOK_BN2_DISPATCH_MASK(K_REDUCE, false);
 #undef K_REDUCE
   TOK_CHECK_LAUNCH("bn_bwd_reduce2");
   return TOK_OK;
+}
+
+int tok_bn_bwd_reduce2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
+                       const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
+                       void* stream) {
+  BwdFin fin;
+  memset(&fin, 0, sizeof(fin));
+  return launch_bwd_reduce2(rows, C, dout, dout2, y, mask_mode, bits, scale, shift, sum_g, sum_gy, fin, stream);
+}
+
+int tok_bn_bwd_reduce2_finalize(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
+                                const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
+                                const float* save_mean, const float* save_invstd, const float* gamma, float* coef_a,
+                                float* coef_c1, float* coef_c0, float* dgamma, float* dbeta, int accumulate,
+                                unsigned* counter, void* stream) {
+  if (!counter || !save_mean || !save_invstd || !coef_a || !coef_c1 || !coef_c0)
+    return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2_finalize: counter, saved statistics and coefficient outputs are required");
+  BwdFin fin;
+  fin.counter = counter;
+  fin.count = (float)rows;
+  fin.mean = save_mean;
+  fin.invstd = save_invstd;
+  fin.gamma = gamma;
+  fin.coef_a = coef_a;
+  fin.coef_c1 = coef_c1;
+  fin.coef_c0 = coef_c0;
+  fin.dgamma = dgamma;
+  fin.dbeta = dbeta;
+  fin.accumulate = accumulate;
+  fin.C = C;
+  return launch_bwd_reduce2(rows, C, dout, dout2, y, mask_mode, bits, scale, shift, sum_g, sum_gy, fin, stream);
 }
 
 int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,

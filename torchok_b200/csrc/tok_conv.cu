@@ -662,6 +662,37 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #undef TOK_PROF
     if (leader) tma_store_wait_all();
     if (want_stats && prev_n0 >= 0) flush_stats(prev_n0);
+    if (want_stats && p.fin.counter != nullptr) {
+      // last CTA standing finalizes the BatchNorm statistics (every CTA takes a ticket, also one that had no tile)
+      __threadfence();   // this thread's column-sum atomics are ordered before the ticket
+      epi_bar();         // ... for every epilogue thread of the CTA; s_stat is free again
+      if (leader) sts_f32(s_stat_s, __int_as_float(atomicAdd(p.fin.counter, 1u) == gridDim.x - 1 ? 1 : 0));
+      epi_bar();
+      if (__float_as_int(lds_f32(s_stat_s)) != 0) {
+        __threadfence();
+        const FwdFin& f = p.fin;
+        for (int c = threadIdx.x - 64; c < p.N; c += 32 * kEpiWarps) {
+          const float mean = __ldcg(p.col_sum + c) / f.count;
+          float var = __ldcg(p.col_sqsum + c) / f.count - mean * mean;
+          var = fmaxf(var, 0.f);
+          p.col_sum[c] = 0.f;   // consumed: handed back zeroed for the next step
+          p.col_sqsum[c] = 0.f;
+          const float invstd = rsqrtf(var + f.eps);
+          const float g = f.gamma ? f.gamma[c] : 1.f;
+          const float b = f.beta ? f.beta[c] : 0.f;
+          f.scale[c] = g * invstd;
+          f.shift[c] = b - mean * g * invstd;
+          f.save_mean[c] = mean;
+          f.save_invstd[c] = invstd;
+          if (f.running_mean) {
+            const float unbiased = f.count > 1.f ? var * f.count / (f.count - 1.f) : var;
+            f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+            f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unbiased;
+          }
+        }
+        if (leader) *p.fin.counter = 0u;
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) {

@@ -17,6 +17,22 @@ struct PixelSrc {
   int R, S;     // filter taps
 };
 
+// BatchNorm "finalize" fused into the conv launch: the last CTA of the grid to finish (ticket in *counter, a zeroed 32-bit
+// word owned by the BatchNorm layer and handed back zeroed) turns the completed column sums into the per-channel affine
+// and the running statistics, exactly as bn_finalize_train_kernel does, and zeroes the accumulators.
+struct FwdFin {
+  unsigned* counter;   // nullptr: no fused finalize
+  float count, eps, momentum;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* scale;
+  float* shift;
+  float* save_mean;
+  float* save_invstd;
+};
+
 // Forward / data-gradient implicit GEMM:  out[m, n] = sum_{tap, c} A_tap[m, c] * Wmat[n, wtap*Cin + c]
 struct ConvFwdParams {
   int M;        // GEMM rows = N_img * P * Q
@@ -38,6 +54,7 @@ struct ConvFwdParams {
   int mn_lbo, mn_sbo, mn_kadv;
   // bring-up aid (TOK_CONV_PROFILE=1): per-CTA cycle counts of the epilogue phases, 8 slots per CTA
   long long* prof;
+  FwdFin fin;   // persistent kernel only
 };
 
 // Weight-gradient implicit GEMM:  dW[co, tap*Cin + ci] += sum_{pix in split} dy[pix, co] * x_tap[pix, ci]

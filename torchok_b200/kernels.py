@@ -229,10 +229,15 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
     st = _st()
     if bn.training:
         acc = bn.acc
-        L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), None, None, 0, st)
-        L.tok_bn_finalize_train(kp, float(rows), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias), bn.eps,
-                                bn.momentum, _p(bn.running_mean), _p(bn.running_var), _p(small[0]), _p(small[1]),
-                                _p(small[2]), _p(small[3]), st)
+        if acc.shape[0] > 4:   # conv + statistics + finalize in one launch (acc[4]: the layer's ticket counters)
+            L.tok_conv_fprop_bn(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias),
+                                bn.eps, bn.momentum, _p(bn.running_mean), _p(bn.running_var), _p(small[0]),
+                                _p(small[1]), _p(small[2]), _p(small[3]), _p(acc[4]), st)
+        else:
+            L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), None, None, 0, st)
+            L.tok_bn_finalize_train(kp, float(rows), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias), bn.eps,
+                                    bn.momentum, _p(bn.running_mean), _p(bn.running_var), _p(small[0]), _p(small[1]),
+                                    _p(small[2]), _p(small[3]), st)
     else:
         L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), None, None, None, None, 0, st)
         L.tok_bn_finalize_eval(kp, _p(bn.running_mean), _p(bn.running_var), _p(bn.weight), _p(bn.bias), bn.eps,
@@ -265,10 +270,15 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
     if not bn.training:
         raise NotImplementedError('backward through eval-mode BatchNorm is not implemented yet')
     coefs = torch.empty((3, kp), dtype=F32, device=dev)
-    L.tok_bn_bwd_reduce2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
-                         _p(acc[2]), _p(acc[3]), st)
-    L.tok_bn_bwd_finalize(kp, float(rows), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
-                          _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, st)
+    if acc.shape[0] > 4:   # reduce + finalize in one launch (acc[4] holds the ticket counters of this layer)
+        L.tok_bn_bwd_reduce2_finalize(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
+                                      _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight), _p(coefs[0]),
+                                      _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, acc[4].data_ptr() + 4, st)
+    else:
+        L.tok_bn_bwd_reduce2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
+                             _p(acc[2]), _p(acc[3]), st)
+        L.tok_bn_bwd_finalize(kp, float(rows), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
+                              _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, st)
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
     L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),

@@ -122,8 +122,9 @@ class BatchNorm2d(nn.BatchNorm2d):
         if not (affine and track_running_stats) or momentum is None:
             raise NotImplementedError('torchok_b200.BatchNorm2d: affine=True, track_running_stats=True, momentum set')
         self.cp = K.ceil8(num_features)
-        # fwd sum / sqsum, bwd sum_g / sum_gy: zero between uses (the finalize kernels hand them back zeroed)
-        self.register_buffer('_tok_acc', torch.zeros(4, self.cp), persistent=False)
+        # fwd sum / sqsum, bwd sum_g / sum_gy: zero between uses (the finalize kernels hand them back zeroed); row 4
+        # holds the 32-bit ticket counters of the fused reduce+finalize launches (word 0 forward, word 1 backward)
+        self.register_buffer('_tok_acc', torch.zeros(5, self.cp), persistent=False)
         self._pending_batches = 0
         self._register_state_dict_hook(_flush_batches)
 
