@@ -212,6 +212,14 @@ class BNState:
 MASK_NONE, MASK_Y, MASK_BITS = 0, 1, 2
 
 
+# Fused BatchNorm finalize (last-CTA ticket).  A/B on one B200, ResNet-50 bs256 graph replay (profiles/r1_resnet50_step.md
+# section 8): forward fusion 21.64-21.68 ms vs 21.25-21.42 ms unfused (the fence + ticket + finalize tail of the
+# persistent conv kernel costs more than the 4 us single-CTA launch it replaces), backward fusion neutral (21.39) and
+# 53 launches fewer for the eager multi-GPU loop.  Hence: forward off, backward on.
+_FUSE_FWD_FIN = os.environ.get('TOK_BN_FUSE_FWD', '0') == '1'
+_FUSE_BWD_FIN = os.environ.get('TOK_BN_FUSE_BWD', '1') == '1'
+
+
 def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
     """conv -> BatchNorm (batch stats in training) -> (+residual) -> (ReLU).
 
@@ -229,7 +237,7 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
     st = _st()
     if bn.training:
         acc = bn.acc
-        if acc.shape[0] > 4:   # conv + statistics + finalize in one launch (acc[4]: the layer's ticket counters)
+        if acc.shape[0] > 4 and _FUSE_FWD_FIN:   # conv + statistics + finalize in one launch (acc[4]: ticket counters)
             L.tok_conv_fprop_bn(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias),
                                 bn.eps, bn.momentum, _p(bn.running_mean), _p(bn.running_var), _p(small[0]),
                                 _p(small[1]), _p(small[2]), _p(small[3]), _p(acc[4]), st)
@@ -270,7 +278,7 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
     if not bn.training:
         raise NotImplementedError('backward through eval-mode BatchNorm is not implemented yet')
     coefs = torch.empty((3, kp), dtype=F32, device=dev)
-    if acc.shape[0] > 4:   # reduce + finalize in one launch (acc[4] holds the ticket counters of this layer)
+    if acc.shape[0] > 4 and _FUSE_BWD_FIN:   # reduce + finalize in one launch (acc[4]: the layer's ticket counters)
         L.tok_bn_bwd_reduce2_finalize(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                                       _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight), _p(coefs[0]),
                                       _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, acc[4].data_ptr() + 4, st)
