@@ -69,6 +69,48 @@ def test_conv_bn_act_unit(cin, cout, k, stride, pad, hw, n, relu):
         assert e < 1e-2, (k_, e)
 
 
+@pytest.mark.parametrize('frozen_affine', [False, True])
+def test_conv_bn_act_unit_eval_mode_backward(frozen_affine):
+    """BatchNorm in eval mode inside a training graph (torchok/callbacks/freeze_unfreeze.py freezes BatchNorm statistics
+    while fine-tuning): the running statistics are constants, dx / dw (and dgamma / dbeta unless frozen) still flow."""
+    from oracle import models as om
+    from torchok_b200.models.modules.bricks import ConvBnAct
+    torch.manual_seed(11)
+    cin, cout, hw, n = 64, 128, 12, 4
+    o = om.ConvBnAct(cin, cout, 3, padding=1, stride=1, act=True)
+    om.dedegenerate_(o, 5)
+    with torch.no_grad():
+        o.conv.weight.copy_(_bf16(o.conv.weight))
+    m = ConvBnAct(cin, cout, 3, padding=1, stride=1, act_layer=torch.nn.ReLU)
+    m.load_state_dict(o.state_dict())
+    m.cuda()
+    for net in (o, m):
+        net.bn.eval()
+        if frozen_affine:
+            net.bn.weight.requires_grad_(False)
+            net.bn.bias.requires_grad_(False)
+    x = _bf16(torch.randn(n, cin, hw, hw))
+    xo = x.clone().requires_grad_(True)
+    xm = x.cuda().requires_grad_(True)
+    with om.amp_bf16():
+        yo = o(xo)
+        r = _bf16(torch.randn_like(yo))
+        (yo * r).sum().backward()
+    rm0 = m.bn.running_mean.clone()
+    ym = m(xm)
+    assert rel_err(ym, yo) < 1e-2
+    (ym.float() * r.cuda()).sum().backward()
+    assert torch.equal(m.bn.running_mean, rm0)   # eval mode: statistics untouched
+    errs = dict(dx=rel_err(xm.grad, xo.grad), dw=rel_err(m.conv.weight.grad, o.conv.weight.grad))
+    if frozen_affine:
+        assert m.bn.weight.grad is None and m.bn.bias.grad is None
+    else:
+        errs.update(dgamma=rel_err(m.bn.weight.grad, o.bn.weight.grad), dbeta=rel_err(m.bn.bias.grad, o.bn.bias.grad))
+    print(errs)
+    for k_, e in errs.items():
+        assert e < 1e-2, (k_, e)
+
+
 @pytest.mark.parametrize('kind,inpl,planes,stride,hw,n', [
     ('basic', 64, 64, 1, 14, 4), ('basic', 64, 128, 2, 16, 4), ('bottleneck', 256, 64, 1, 14, 4),
     ('bottleneck', 256, 128, 2, 16, 4), ('bottleneck', 64, 64, 1, 12, 2)])

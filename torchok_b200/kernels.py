@@ -275,9 +275,27 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
     dev = y.device
     st = _st()
     acc = bn.acc
-    if not bn.training:
-        raise NotImplementedError('backward through eval-mode BatchNorm is not implemented yet')
     coefs = torch.empty((3, kp), dtype=F32, device=dev)
+    if not bn.training:
+        # Frozen statistics (torchok/callbacks/freeze_unfreeze.py puts BatchNorm into eval mode while the layers around
+        # it train): out = y * scale + shift with constants, so dy = scale * g; gamma / beta still receive
+        # dgamma = sum g * (y - running_mean) * invstd, dbeta = sum g when they are trainable.
+        if dgamma is not None or dbeta is not None:
+            L.tok_bn_bwd_reduce2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
+                                 _p(acc[2]), _p(acc[3]), st)
+            invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+            if dgamma is not None:
+                dgamma += (acc[3] - bn.running_mean.float() * acc[2]) * invstd
+            if dbeta is not None:
+                dbeta += acc[2]
+            acc[2:4].zero_()
+        coefs[0].copy_(small[0])
+        coefs[1:].zero_()
+        dy = torch.empty_like(y)
+        dres = torch.empty_like(y) if want_dres else None
+        L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
+                            _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
+        return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev)
     if acc.shape[0] > 4 and _FUSE_BWD_FIN:   # reduce + finalize in one launch (acc[4]: the layer's ticket counters)
         L.tok_bn_bwd_reduce2_finalize(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                                       _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight), _p(coefs[0]),
@@ -291,6 +309,11 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
     dres = torch.empty_like(y) if want_dres else None
     L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                         _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
+    return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev)
+
+
+def _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev):
+    """Data and weight gradients of the conv once dy (the gradient at the conv output) is known."""
     dx = None
     if need_dx and compact_dx:
         # strided 1x1 conv: the data gradient lives on the (p*stride, q*stride) sub-lattice only; return it compact
