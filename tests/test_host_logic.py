@@ -154,3 +154,71 @@ def test_library_exports_every_declared_symbol():
         assert dll.tok_device_ok() < 0
         dll.tok_last_error.restype = ctypes.c_char_p
         assert dll.tok_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ N > 1 gradient path
+def _bucket_worker(rank, world, port, ret):
+    """The data-parallel gradient path of engine.ParamArena / BucketAllReduce on CPU tensors: bucket plan, readiness
+    counting in backward order, one all-reduce (sum) per bucket, leftovers reduced by finish()."""
+    import torch.distributed as dist
+    from torchok_b200 import engine
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    numels = [9408, 64, 64, 36864, 64, 64, 147456, 513, 1000, 7]
+    arena = engine.ParamArena.__new__(engine.ParamArena)       # the bookkeeping half only: no CUDA arenas on this box
+    arena.buckets = engine.plan_buckets(numels, bucket_mb=0.05)
+    arena.begin_step()
+    total = arena.buckets[-1][1]
+    gen = torch.Generator().manual_seed(100 + rank)
+    arena.grad = torch.randn(total, generator=gen)
+    mine = arena.grad.clone()
+    launched = []
+
+    class GlooReducer:
+        def launch(self, b):
+            begin, end, _ = arena.buckets[b]
+            launched.append(b)
+            dist.all_reduce(arena.grad[begin:end], op=dist.ReduceOp.SUM)
+
+        def join(self):
+            pass
+    arena.reducer = GlooReducer()
+    owner = {i: b for b, (_, _, m) in enumerate(arena.buckets) for i in m}
+    for i in reversed(range(len(numels))):      # backward produces gradients last layer first
+        if i == 3:
+            continue                            # a parameter whose backward never announces itself
+        arena.ready(owner[i])
+    arena.finish()
+    other = torch.randn(total, generator=torch.Generator().manual_seed(100 + (1 - rank)))
+    ret[rank] = dict(ok=bool(torch.allclose(arena.grad, mine + other)), launched=launched, buckets=arena.buckets)
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_gloo_world2():
+    import torch.multiprocessing as mp
+    from torchok_b200 import engine
+    numels = [9408, 64, 64, 36864, 64, 64, 147456, 513, 1000, 7]
+    buckets = engine.plan_buckets(numels, bucket_mb=0.05)
+    # the plan tiles the arena: contiguous, aligned, every parameter in exactly one bucket, in order
+    assert buckets[0][0] == 0 and all(a[1] == b[0] for a, b in zip(buckets, buckets[1:]))
+    assert [i for _, _, m in buckets for i in m] == list(range(len(numels)))
+    assert buckets[-1][1] == sum((n + 63) // 64 * 64 for n in numels)
+    assert all(e - b >= int(0.05 * (1 << 20) / 4) for b, e, _ in buckets[:-1])   # 0.05 MiB of fp32 before a bucket closes
+    assert len(buckets) > 2
+    ctx = mp.get_context('spawn')
+    ret = ctx.Manager().dict()
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for r in range(2):
+        assert ret[r]['ok']                                        # every element is the sum over both ranks
+        assert sorted(ret[r]['launched']) == list(range(len(buckets)))   # each bucket reduced exactly once
+    assert ret[0]['launched'] == ret[1]['launched']                # same collective order on both ranks
+    # buckets complete from the end of the arena backwards; the one with the silent parameter is left to finish()
+    silent = [b for b, (_, _, m) in enumerate(buckets) if 3 in m][0]
+    assert ret[0]['launched'][-1] == silent

@@ -36,6 +36,23 @@ def _round_up(n, a):
     return (n + a - 1) // a * a
 
 
+def plan_buckets(numels, bucket_mb=32.0, align=_ALIGN):
+    """Cut the flat gradient arena into all-reduce buckets: contiguous slices that start and end at parameter boundaries
+    (every parameter occupies `round_up(numel, align)` elements), closed as soon as they reach `bucket_mb` MiB of fp32.
+    Returns [(begin, end, [parameter indices])]; the slices tile [0, total) without gaps or overlap.  Pure host logic
+    (covered by the gloo world-size-2 test on CPU)."""
+    limit = max(1, int(bucket_mb * (1 << 20) / 4))
+    buckets, begin, members, off = [], 0, [], 0
+    for i, n in enumerate(numels):
+        end = off + _round_up(n, align)
+        members.append(i)
+        if end - begin >= limit or i == len(numels) - 1:
+            buckets.append((begin, end, members))
+            begin, members = end, []
+        off = end
+    return buckets
+
+
 class ParamArena:
     def __init__(self, module, bucket_mb=32.0):
         params, seen = [], set()
@@ -68,15 +85,7 @@ class ParamArena:
             p._tok_shadow = torch.as_strided(self.shadow, shape, stride, off)
         self.refresh_shadow()
         # gradient buckets: contiguous arena slices, cut at parameter boundaries
-        limit = max(1, int(bucket_mb * (1 << 20) / 4))
-        self.buckets = []  # (begin, end, [param indices])
-        begin, members = 0, []
-        for i, (p, off) in enumerate(zip(params, offs)):
-            end = off + _round_up(p.numel(), _ALIGN)
-            members.append(i)
-            if end - begin >= limit or i == len(params) - 1:
-                self.buckets.append((begin, end, members))
-                begin, members = end, []
+        self.buckets = plan_buckets([p.numel() for p in params], bucket_mb)
         for b, (_, _, members) in enumerate(self.buckets):
             for i in members:
                 params[i]._tok_bucket = (self, b)
