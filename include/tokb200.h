@@ -306,6 +306,18 @@ int tok_sgd_step_dev(long long n, float* param, float* grad, float* momentum_buf
 int tok_adam_step_dev(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                       const float* lr_dev, int* step_dev, float beta1, float beta2, float eps, float weight_decay,
                       int decoupled, float grad_scale, int zero_grad, void* stream);
+/* The same steps with `paramwise_cfg` (torchok/constructor/constructor.py:162-251: bias_lr_mult, bias_decay_mult,
+ * norm_decay_mult, dwconv_decay_mult, custom_keys): the reference builds one torch.optim param group per parameter; here
+ * the flat kernel looks up lr / weight-decay MULTIPLIERS in a sorted per-parameter segment table (seg_begin[k] = first
+ * arena element of segment k, seg_begin[0] = 0; device arrays; n_segs = 0 disables the lookup). */
+int tok_sgd_step_dev_groups(long long n, float* param, float* grad, float* momentum_buf, void* shadow_bf16,
+                            const float* lr_dev, int* step_dev, float momentum, float weight_decay, float dampening,
+                            int nesterov, float grad_scale, int zero_grad, const int* seg_begin,
+                            const float* seg_lr_mult, const float* seg_wd_mult, int n_segs, void* stream);
+int tok_adam_step_dev_groups(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                             void* shadow_bf16, const float* lr_dev, int* step_dev, float beta1, float beta2, float eps,
+                             float weight_decay, int decoupled, float grad_scale, int zero_grad, const int* seg_begin,
+                             const float* seg_lr_mult, const float* seg_wd_mult, int n_segs, void* stream);
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream);
 
 #ifdef __cplusplus

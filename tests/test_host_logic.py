@@ -222,3 +222,22 @@ def test_gradient_buckets_gloo_world2():
     # buckets complete from the end of the arena backwards; the one with the silent parameter is left to finish()
     silent = [b for b, (_, _, m) in enumerate(buckets) if 3 in m][0]
     assert ret[0]['launched'][-1] == silent
+
+
+# ------------------------------------------------------------------------------------------------ paramwise_cfg
+def test_paramwise_cfg_rules():
+    """The rules of Constructor.add_params (torchok/constructor/constructor.py:162-251): custom_keys beat everything
+    (longest key first), bias_lr_mult skips norm biases, decay precedence norm > depth-wise conv > bias."""
+    import torch.nn as nn
+    from torchok_b200.constructor.paramwise import paramwise_multipliers
+    m = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.Conv2d(8, 8, 3, groups=8), nn.Linear(8, 4))
+    m[3].bias.requires_grad_(False)
+    cfg = dict(bias_lr_mult=2., bias_decay_mult=0., norm_decay_mult=0.5, dwconv_decay_mult=0.25,
+               custom_keys={'0': dict(lr_mult=7.), '3.weight': dict(lr_mult=0.1), '3.w': dict(decay_mult=9.)})
+    got = {n: paramwise_multipliers(m, cfg)[p] for n, p in m.named_parameters()}
+    assert got == {'0.weight': (7., 1.), '0.bias': (7., 1.),      # custom key: other rules skipped (no bias_lr_mult)
+                   '1.weight': (1., 0.5), '1.bias': (1., 0.5),    # norm: no bias_lr_mult, norm decay
+                   '2.weight': (1., 0.25), '2.bias': (2., 0.25),  # depth-wise conv decay wins over bias decay
+                   '3.weight': (0.1, 1.),                         # the longer key '3.weight' wins over '3.w'
+                   '3.bias': (1., 1.)}                            # frozen: defaults
+    assert all(v == (1., 1.) for v in paramwise_multipliers(m, None).values())

@@ -106,6 +106,9 @@ _SIGS = {
     'tok_adam_step': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _i, _f, _vp]),
     'tok_sgd_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _i, _vp]),
     'tok_adam_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),
+    'tok_sgd_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _i, _vp]),
+    'tok_adam_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _i,
+                                      _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
 }
 _RAW = {'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',

@@ -677,19 +677,47 @@ __device__ __forceinline__ float sgd_one(float w, float g, float* buf, const Sgd
   }
   return w - a.lr * d;
 }
+// paramwise_cfg (torchok/constructor/constructor.py:162-251): per-parameter lr / weight-decay multipliers, looked up by
+// the element offset in a sorted segment table (one segment per parameter of the arena); n == 0 means "all ones".
+struct ParamSegs {
+  const int* begin;
+  const float* lr_mult;
+  const float* wd_mult;
+  int n;
+};
+__device__ __forceinline__ void seg_lookup(const ParamSegs& s, long long elem, float& lr_mult, float& wd_mult) {
+  lr_mult = wd_mult = 1.f;
+  if (s.n == 0) return;
+  int lo = 0, hi = s.n - 1;   // largest k with begin[k] <= elem
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(s.begin + mid) <= elem) lo = mid;
+    else hi = mid - 1;
+  }
+  lr_mult = __ldg(s.lr_mult + lo);
+  wd_mult = __ldg(s.wd_mult + lo);
+}
+
 __global__ void __launch_bounds__(256)
 sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf,
                     __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
                     const int* __restrict__ step_dev, float mu, float wd, float damp, int nesterov, float gscale,
-                    int zero_grad) {
+                    int zero_grad, const ParamSegs segs) {
   SgdArgs a;
   a.lr = __ldg(lr_dev);
+  const float lr0 = a.lr;
   a.first = __ldg(step_dev) <= 1;
   a.mu = mu; a.wd = wd; a.damp = damp; a.gscale = gscale; a.nesterov = nesterov; a.zero_grad = zero_grad;
   const bool aligned = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)buf | ((uintptr_t)shadow << 1)) & 15) == 0;
   const long long n4 = aligned ? (n >> 2) : 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    if (segs.n) {   // parameters start on 64-element boundaries, so a float4 never straddles two segments
+      float lm, wm;
+      seg_lookup(segs, i << 2, lm, wm);
+      a.lr = lr0 * lm;
+      a.wd = wd * wm;
+    }
     float4 w = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -704,6 +732,12 @@ sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restr
     if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
   }
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (segs.n) {
+      float lm, wm;
+      seg_lookup(segs, i, lm, wm);
+      a.lr = lr0 * lm;
+      a.wd = wd * wm;
+    }
     float b = (mu != 0.f && !a.first) ? buf[i] : 0.f;
     const float w = sgd_one(p[i], g[i], &b, a);
     if (mu != 0.f) buf[i] = b;
@@ -732,9 +766,10 @@ __global__ void __launch_bounds__(256)
 adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                      __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
                      const int* __restrict__ step_dev, float b1, float b2, float eps, float wd, int decoupled,
-                     float gscale, int zero_grad) {
+                     float gscale, int zero_grad, const ParamSegs segs) {
   AdamArgs a;
   a.lr = __ldg(lr_dev);
+  const float lr0 = a.lr;
   const float t = (float)__ldg(step_dev);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   a.step = a.lr / bc1;
@@ -744,6 +779,13 @@ adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __rest
   const long long n4 = aligned ? (n >> 2) : 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    if (segs.n) {
+      float lm, wm;
+      seg_lookup(segs, i << 2, lm, wm);
+      a.lr = lr0 * lm;
+      a.step = a.lr / bc1;
+      a.wd = wd * wm;
+    }
     float4 w = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -759,6 +801,13 @@ adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __rest
     if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
   }
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (segs.n) {
+      float lm, wm;
+      seg_lookup(segs, i, lm, wm);
+      a.lr = lr0 * lm;
+      a.step = a.lr / bc1;
+      a.wd = wd * wm;
+    }
     float mi = m[i], vi = v[i];
     const float w = adam_one(p[i], g[i], &mi, &vi, a);
     m[i] = mi;
@@ -1009,30 +1058,62 @@ int tok_adam_step(long long n, float* param, const float* grad, float* exp_avg, 
   return TOK_OK;
 }
 
-int tok_sgd_step_dev(long long n, float* param, float* grad, float* momentum_buf, void* shadow_bf16,
-                     const float* lr_dev, int* step_dev, float momentum, float weight_decay, float dampening,
-                     int nesterov, float grad_scale, int zero_grad, void* stream) {
+static int check_segs(ParamSegs* s, const int* begin, const float* lr_mult, const float* wd_mult, int n, const char* who) {
+  s->begin = begin;
+  s->lr_mult = lr_mult;
+  s->wd_mult = wd_mult;
+  s->n = n;
+  if (n < 0 || (n > 0 && (!begin || !lr_mult || !wd_mult)))
+    return set_error(TOK_ERR_INVALID, "%s: a segment table needs begin / lr_mult / wd_mult arrays", who);
+  return TOK_OK;
+}
+
+int tok_sgd_step_dev_groups(long long n, float* param, float* grad, float* momentum_buf, void* shadow_bf16,
+                            const float* lr_dev, int* step_dev, float momentum, float weight_decay, float dampening,
+                            int nesterov, float grad_scale, int zero_grad, const int* seg_begin,
+                            const float* seg_lr_mult, const float* seg_wd_mult, int n_segs, void* stream) {
   if (n <= 0) return TOK_OK;
   if (!lr_dev || !step_dev) return set_error(TOK_ERR_INVALID, "sgd_step_dev: lr_dev and step_dev are required");
+  ParamSegs segs;
+  int rc = check_segs(&segs, seg_begin, seg_lr_mult, seg_wd_mult, n_segs, "sgd_step_dev_groups");
+  if (rc) return rc;
   step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
   sgd_step_dev_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
       param, grad, momentum_buf, (__nv_bfloat16*)shadow_bf16, n, lr_dev, step_dev, momentum, weight_decay, dampening,
-      nesterov, grad_scale, zero_grad);
+      nesterov, grad_scale, zero_grad, segs);
   TOK_CHECK_LAUNCH("sgd_step_dev");
+  return TOK_OK;
+}
+
+int tok_sgd_step_dev(long long n, float* param, float* grad, float* momentum_buf, void* shadow_bf16,
+                     const float* lr_dev, int* step_dev, float momentum, float weight_decay, float dampening,
+                     int nesterov, float grad_scale, int zero_grad, void* stream) {
+  return tok_sgd_step_dev_groups(n, param, grad, momentum_buf, shadow_bf16, lr_dev, step_dev, momentum, weight_decay,
+                                 dampening, nesterov, grad_scale, zero_grad, nullptr, nullptr, nullptr, 0, stream);
+}
+
+int tok_adam_step_dev_groups(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
+                             void* shadow_bf16, const float* lr_dev, int* step_dev, float beta1, float beta2, float eps,
+                             float weight_decay, int decoupled, float grad_scale, int zero_grad, const int* seg_begin,
+                             const float* seg_lr_mult, const float* seg_wd_mult, int n_segs, void* stream) {
+  if (n <= 0) return TOK_OK;
+  if (!lr_dev || !step_dev) return set_error(TOK_ERR_INVALID, "adam_step_dev: lr_dev and step_dev are required");
+  ParamSegs segs;
+  int rc = check_segs(&segs, seg_begin, seg_lr_mult, seg_wd_mult, n_segs, "adam_step_dev_groups");
+  if (rc) return rc;
+  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  adam_step_dev_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr_dev, step_dev, beta1, beta2, eps,
+      weight_decay, decoupled, grad_scale, zero_grad, segs);
+  TOK_CHECK_LAUNCH("adam_step_dev");
   return TOK_OK;
 }
 
 int tok_adam_step_dev(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                       const float* lr_dev, int* step_dev, float beta1, float beta2, float eps, float weight_decay,
                       int decoupled, float grad_scale, int zero_grad, void* stream) {
-  if (n <= 0) return TOK_OK;
-  if (!lr_dev || !step_dev) return set_error(TOK_ERR_INVALID, "adam_step_dev: lr_dev and step_dev are required");
-  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
-  adam_step_dev_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
-      param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr_dev, step_dev, beta1, beta2, eps,
-      weight_decay, decoupled, grad_scale, zero_grad);
-  TOK_CHECK_LAUNCH("adam_step_dev");
-  return TOK_OK;
+  return tok_adam_step_dev_groups(n, param, grad, exp_avg, exp_avg_sq, shadow_bf16, lr_dev, step_dev, beta1, beta2, eps,
+                                  weight_decay, decoupled, grad_scale, zero_grad, nullptr, nullptr, nullptr, 0, stream);
 }
 
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream) {

@@ -152,6 +152,25 @@ class _ArenaOptimizer:
         self._lr = float(lr)
         self.grad_scale = 1.0
 
+    def set_param_multipliers(self, mults):
+        """`mults`: {parameter: (lr_mult, decay_mult)} from constructor.paramwise.paramwise_multipliers.  Builds the
+        per-parameter segment table the step kernels look multipliers up in (one segment per arena parameter)."""
+        a = self.arena
+        lr_m = [float(mults.get(p, (1., 1.))[0]) for p in a.params]
+        wd_m = [float(mults.get(p, (1., 1.))[1]) for p in a.params]
+        if all(v == 1. for v in lr_m) and all(v == 1. for v in wd_m):
+            self.segs = None
+            return
+        dev = a.master.device
+        self.segs = (torch.tensor(a.offsets, dtype=torch.int32, device=dev),
+                     torch.tensor(lr_m, dtype=F32, device=dev), torch.tensor(wd_m, dtype=F32, device=dev))
+
+    def _seg_args(self):
+        if getattr(self, 'segs', None) is None:
+            return None, None, None, 0
+        b, l, w = self.segs
+        return K._p(b), K._p(l), K._p(w), int(b.numel())
+
     @property
     def lr(self):
         return self._lr
@@ -180,9 +199,9 @@ class ArenaSGD(_ArenaOptimizer):
 
     def step(self):
         a = self.arena
-        lib().tok_sgd_step_dev(a.numel, K._p(a.master), K._p(a.grad), K._p(self.buf), K._p(a.shadow),
-                               K._p(self.lr_dev), K._p(self.step_dev), self.momentum, self.weight_decay,
-                               self.dampening, int(self.nesterov), self.grad_scale, 1, K._st())
+        lib().tok_sgd_step_dev_groups(a.numel, K._p(a.master), K._p(a.grad), K._p(self.buf), K._p(a.shadow),
+                                      K._p(self.lr_dev), K._p(self.step_dev), self.momentum, self.weight_decay,
+                                      self.dampening, int(self.nesterov), self.grad_scale, 1, *self._seg_args(), K._st())
 
 
 class ArenaAdam(_ArenaOptimizer):
@@ -196,21 +215,31 @@ class ArenaAdam(_ArenaOptimizer):
 
     def step(self):
         a = self.arena
-        lib().tok_adam_step_dev(a.numel, K._p(a.master), K._p(a.grad), K._p(self.exp_avg), K._p(self.exp_avg_sq),
-                                K._p(a.shadow), K._p(self.lr_dev), K._p(self.step_dev), self.betas[0], self.betas[1],
-                                self.eps, self.weight_decay, int(self.decoupled), self.grad_scale, 1, K._st())
+        lib().tok_adam_step_dev_groups(a.numel, K._p(a.master), K._p(a.grad), K._p(self.exp_avg),
+                                       K._p(self.exp_avg_sq), K._p(a.shadow), K._p(self.lr_dev), K._p(self.step_dev),
+                                       self.betas[0], self.betas[1], self.eps, self.weight_decay, int(self.decoupled),
+                                       self.grad_scale, 1, *self._seg_args(), K._st())
 
 
-def build_optimizer(arena, name, params):
+def build_optimizer(arena, name, params, module=None, paramwise_cfg=None):
+    """`paramwise_cfg` (optimization[i].optimizer.paramwise_cfg, torchok/constructor/constructor.py:145-156) needs the
+    `module` whose tree the rules are evaluated on (the task)."""
     params = dict(params or {})
     if name == 'SGD':
-        return ArenaSGD(arena, **params)
-    if name == 'Adam':
-        return ArenaAdam(arena, decoupled=False, **params)
-    if name == 'AdamW':
+        opt = ArenaSGD(arena, **params)
+    elif name == 'Adam':
+        opt = ArenaAdam(arena, decoupled=False, **params)
+    elif name == 'AdamW':
         params.setdefault('weight_decay', 1e-2)
-        return ArenaAdam(arena, decoupled=True, **params)
-    raise NotImplementedError(f'optimizer {name}: the arena step kernels cover SGD, Adam and AdamW')
+        opt = ArenaAdam(arena, decoupled=True, **params)
+    else:
+        raise NotImplementedError(f'optimizer {name}: the arena step kernels cover SGD, Adam and AdamW')
+    if paramwise_cfg:
+        if module is None:
+            raise ValueError('paramwise_cfg needs the module tree it is evaluated on')
+        from .constructor.paramwise import paramwise_multipliers
+        opt.set_param_multipliers(paramwise_multipliers(module, dict(paramwise_cfg)))
+    return opt
 
 
 class StreamLoop:
@@ -233,7 +262,8 @@ class StreamLoop:
                 raise ValueError('StreamLoop needs an optimizer (argument or hparams.optimization[0].optimizer)')
             optimizer = opt_cfg['optimizer']
         self.arena = ParamArena(task, bucket_mb=bucket_mb)
-        self.optimizer = build_optimizer(self.arena, optimizer['name'], optimizer.get('params'))
+        self.optimizer = build_optimizer(self.arena, optimizer['name'], optimizer.get('params'), task,
+                                         optimizer.get('paramwise_cfg'))
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if self.world > 1:
             BucketAllReduce(self.arena)
