@@ -243,6 +243,17 @@ int tok_bilinear_bwd(int n, int hi, int wi, int c, int ho, int wo, const void* d
 int tok_softmax_xent_small(long long rows, int C, int ld, const void* logits, const long long* target,
                            float* loss_sum, float* count, void* dlogits, const float* inv_count_dev, float gscale,
                            const float* gscale_dev, long long ignore_index, void* stream);
+/* DiceLoss(mode='multiclass', from_logits=True) of torchok/losses/segmentation/dice.py:85-188 on (rows, C <= 64) bf16
+ * logits (NHWC rows of pitch ld) with int64 targets: tok_dice_stats ACCUMULATES per class [3][64] = (sum p_c [t = c],
+ * sum p_c, count_c) with p = softmax; tok_dice_finalize turns them into the scalar loss (mean over classes, classes
+ * without a true pixel masked, optional -log) and the per-class coefficients coef[2][64] = (a_c, b_c) of
+ * d loss / d p_c(pixel) = a_c [t = c] + b_c; tok_dice_bwd writes dlogits = gscale * p o (dp - sum_k p_k dp_k). */
+int tok_dice_stats(long long rows, int C, int ld, const void* logits, const long long* target, float* stats,
+                   void* stream);
+int tok_dice_finalize(int C, const float* stats, float smooth, float eps, int log_loss, float* loss, float* coef,
+                      void* stream);
+int tok_dice_bwd(long long rows, int C, int ld, const void* logits, const long long* target, const float* coef,
+                 const float* gscale_dev, void* dlogits, void* stream);
 
 /* ---- embedding heads and the pairwise loss (tok_heads.cu) ------------------------------------------------------------
  * F.normalize (LinearHead(normalize=True), linear_head.py:33-35; ArcFaceHead, arcface_head.py:125-126):

@@ -306,6 +306,21 @@ class ContrastiveLoss(nn.Module):
         raise ValueError(f'Unknown reduction type: {self.reduction}')
 
 
+def dice_loss_multiclass(logits, target, smooth=0.0, eps=1e-7, log_loss=False):
+    """torchok/losses/segmentation/dice.py:85-188, DiceLoss(mode='multiclass', from_logits=True).forward with
+    soft_dice_score (dice.py:23-56): log_softmax(dim=1).exp(), one-hot targets, per-class sums over (batch, pixels),
+    score = (2 I + smooth) / (clamp_min(card, eps) + smooth), classes without a true pixel masked, mean over classes."""
+    bs, nc = logits.shape[:2]
+    p = logits.log_softmax(dim=1).exp().view(bs, nc, -1)
+    t = F.one_hot(target.view(bs, -1), nc).permute(0, 2, 1).type_as(p)
+    inter = (p * t).sum(dim=(0, 2))
+    card = (p + t).sum(dim=(0, 2))
+    score = (2.0 * inter + smooth) / (card.clamp_min(eps) + smooth)
+    loss = -torch.log(score.clamp_min(eps)) if log_loss else 1 - score
+    loss = loss * (t.sum(dim=(0, 2)) > 0).to(loss.dtype)
+    return loss.mean()
+
+
 def calc_relevance_matrix(y, num_classes):
     """pairwise_task.py:87-107: one-hot -> y y^T > 0."""
     if y.ndim == 1:

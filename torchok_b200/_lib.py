@@ -91,6 +91,9 @@ _SIGS = {
     'tok_bilinear_fwd': (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     'tok_bilinear_bwd': (_i, [_i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     'tok_softmax_xent_small': (_i, [_ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _ll, _vp]),
+    'tok_dice_stats': (_i, [_ll, _i, _i, _vp, _vp, _vp, _vp]),
+    'tok_dice_finalize': (_i, [_i, _vp, _f, _f, _i, _vp, _vp, _vp]),
+    'tok_dice_bwd': (_i, [_ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_rownorm_fwd': (_i, [_i, _i, _vp, _i, _f, _vp, _i, _vp, _vp]),
     'tok_rownorm_bwd': (_i, [_i, _i, _vp, _i, _vp, _f, _vp, _i, _i, _vp, _i, _i, _vp]),
     'tok_arcface_margin_fwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _ll, _f, _f, _i, _vp, _vp]),

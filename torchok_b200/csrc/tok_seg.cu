@@ -241,6 +241,126 @@ xent_small_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __r
   }
 }
 
+
+// ---- Dice loss (multiclass, from logits) ------------------------------------------------------------------------------
+// torchok/losses/segmentation/dice.py:85-188 (DiceLoss, mode='multiclass', from_logits=True) with soft_dice_score
+// (dice.py:23-56) over dims (0, 2): per class c
+//   I_c = sum p_c [t = c],  card_c = sum p_c + sum [t = c],  score_c = (2 I_c + smooth) / (max(card_c, eps) + smooth)
+//   loss = mean_c [count_c > 0] (1 - score_c)      (or -log(max(score_c, eps)) with log_loss)
+// where p = softmax(logits) per pixel.  Pass 1 (one thread per pixel, C <= 64) accumulates I, sum p, count; a
+// one-warp finalize turns them into the scalar loss and the per-class coefficients a_c, b_c of
+// dloss/dp_c(pixel) = a_c [t = c] + b_c; pass 2 recomputes the softmax and writes dlogits = p o (dp - sum_k p_k dp_k).
+__global__ void __launch_bounds__(256)
+dice_stats_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ target,
+                  float* __restrict__ stats /* [3][64]: I, sum p, count */, long long rows, int C, int ld) {
+  __shared__ float sh[3][64];
+  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) (&sh[0][0])[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // warp-uniform trip count: every lane takes part in the shuffles, rows past the end contribute zeros
+  for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x - lane); base < rows; base += stride) {
+    const long long r = base + lane;
+    const bool live = r < rows;
+    const __nv_bfloat16* lp = logits + (live ? r : 0) * ld;
+    const long long t = live ? target[r] : -1;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, __bfloat162float(lp[c]));
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += __expf(__bfloat162float(lp[c]) - mx);
+    const float inv = live ? 1.f / se : 0.f;
+    for (int c = 0; c < C; ++c) {
+      float pc = __expf(__bfloat162float(lp[c]) - mx) * inv;
+      float ic = t == c ? pc : 0.f;
+      const unsigned hit = __ballot_sync(0xffffffffu, t == c);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        pc += __shfl_xor_sync(0xffffffffu, pc, o);
+        ic += __shfl_xor_sync(0xffffffffu, ic, o);
+      }
+      if (lane == 0) {
+        atomicAdd(&sh[0][c], ic);
+        atomicAdd(&sh[1][c], pc);
+        atomicAdd(&sh[2][c], (float)__popc(hit));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) {
+    const float v = (&sh[0][0])[i];
+    if (v != 0.f) atomicAdd(stats + i, v);
+  }
+}
+
+__global__ void dice_finalize_kernel(const float* __restrict__ stats, int C, float smooth, float eps, int log_loss,
+                                     float* __restrict__ loss, float* __restrict__ coef /* [2][64]: a, b */) {
+  const int c = threadIdx.x;  // 64 threads
+  float l = 0.f;
+  if (c < C) {
+    const float I = stats[c], card = stats[64 + c] + stats[128 + c], cnt = stats[128 + c];
+    const float D = fmaxf(card, eps) + smooth;
+    const float num = 2.f * I + smooth;
+    const float score = num / D;
+    const float mask = cnt > 0.f ? 1.f / C : 0.f;   // 1/C of the mean folded in
+    float dscore = -1.f;                              // d loss_c / d score_c
+    if (log_loss) {
+      l = -logf(fmaxf(score, eps));
+      dscore = score > eps ? -1.f / score : 0.f;
+    } else {
+      l = 1.f - score;
+    }
+    l *= mask;
+    coef[c] = mask * dscore * 2.f / D;                                       // a_c: through I_c
+    coef[64 + c] = card > eps ? -mask * dscore * num / (D * D) : 0.f;        // b_c: through card_c (clamp_min)
+  } else {
+    coef[c] = 0.f;
+    coef[64 + c] = 0.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  __shared__ float part[2];
+  if ((c & 31) == 0) part[c >> 5] = l;
+  __syncthreads();
+  if (c == 0) *loss = part[0] + part[1];
+}
+
+__global__ void __launch_bounds__(256)
+dice_bwd_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ target,
+                const float* __restrict__ coef, const float* __restrict__ gscale_dev,
+                __nv_bfloat16* __restrict__ dlogits, long long rows, int C, int ld) {
+  __shared__ float sa[64], sb[64];
+  if (threadIdx.x < 64) {
+    sa[threadIdx.x] = coef[threadIdx.x];
+    sb[threadIdx.x] = coef[64 + threadIdx.x];
+  }
+  __syncthreads();
+  const float gs = gscale_dev ? __ldg(gscale_dev) : 1.f;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const __nv_bfloat16* lp = logits + r * ld;
+    const long long t = target[r];
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, __bfloat162float(lp[c]));
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += __expf(__bfloat162float(lp[c]) - mx);
+    const float inv = 1.f / se;
+    float dot = 0.f;   // sum_k p_k dp_k
+    for (int c = 0; c < C; ++c) {
+      const float pc = __expf(__bfloat162float(lp[c]) - mx) * inv;
+      dot = fmaf(pc, (t == c ? sa[c] : 0.f) + sb[c], dot);
+    }
+    __nv_bfloat16* dp = dlogits + r * ld;
+    for (int c = 0; c < ld; ++c) {
+      float g = 0.f;
+      if (c < C) {
+        const float pc = __expf(__bfloat162float(lp[c]) - mx) * inv;
+        g = pc * ((t == c ? sa[c] : 0.f) + sb[c] - dot) * gs;
+      }
+      dp[c] = __float2bfloat16(g);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace tok
 
@@ -313,6 +433,31 @@ int tok_softmax_xent_small(long long rows, int C, int ld, const void* logits, co
       (const __nv_bfloat16*)logits, target, loss_sum, count, (__nv_bfloat16*)dlogits, rows, C, ld, inv_count_dev,
       gscale, gscale_dev, ignore_index);
   TOK_CHECK_LAUNCH("softmax_xent_small");
+  return TOK_OK;
+}
+
+int tok_dice_stats(long long rows, int C, int ld, const void* logits, const long long* target, float* stats,
+                   void* stream) {
+  if (rows <= 0 || C <= 0 || C > 64 || ld < C || !stats) return set_error(TOK_ERR_INVALID, "dice_stats: 1 <= C <= 64, ld >= C");
+  dice_stats_kernel<<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, stats, rows, C, ld);
+  TOK_CHECK_LAUNCH("dice_stats");
+  return TOK_OK;
+}
+
+int tok_dice_finalize(int C, const float* stats, float smooth, float eps, int log_loss, float* loss, float* coef,
+                      void* stream) {
+  if (C <= 0 || C > 64 || !stats || !loss || !coef) return set_error(TOK_ERR_INVALID, "dice_finalize: 1 <= C <= 64");
+  dice_finalize_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(stats, C, smooth, eps, log_loss, loss, coef);
+  TOK_CHECK_LAUNCH("dice_finalize");
+  return TOK_OK;
+}
+
+int tok_dice_bwd(long long rows, int C, int ld, const void* logits, const long long* target, const float* coef,
+                 const float* gscale_dev, void* dlogits, void* stream) {
+  if (rows <= 0 || C <= 0 || C > 64 || ld < C || !coef || !dlogits) return set_error(TOK_ERR_INVALID, "dice_bwd: 1 <= C <= 64, ld >= C");
+  dice_bwd_kernel<<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, coef, gscale_dev,
+                                                                  (__nv_bfloat16*)dlogits, rows, C, ld);
+  TOK_CHECK_LAUNCH("dice_bwd");
   return TOK_OK;
 }
 

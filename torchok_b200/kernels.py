@@ -732,6 +732,45 @@ class SoftmaxXentNHWCFn(torch.autograd.Function):
         return (d if cp == c else d[:, :c]), None, None
 
 
+class DiceMulticlassFn(torch.autograd.Function):
+    """DiceLoss(mode='multiclass', from_logits=True) (torchok/losses/segmentation/dice.py:85-188) on (B, C, H, W) logits
+    with (B, H, W) int64 targets: statistics pass, one-warp finalize (loss + per-class coefficients), gradient pass."""
+
+    @staticmethod
+    def forward(ctx, logits, target, smooth, eps, log_loss):
+        lg = to_nhwc(logits)
+        n, c, h, w = lg.shape
+        cp = nhwc_pitch(lg)
+        rows = n * h * w
+        target = target.long().contiguous()
+        if target.numel() != rows:
+            raise ValueError(f"Shapes of input {tuple(lg.shape)} and target {tuple(target.shape)} tensors don't match!")
+        stats = torch.zeros((3, 64), dtype=F32, device=lg.device)
+        out = torch.empty((1 + 2 * 64,), dtype=F32, device=lg.device)   # loss, then coef[2][64]
+        L, st = lib(), _st()
+        L.tok_dice_stats(rows, c, cp, _p(lg), _p(target), _p(stats), st)
+        L.tok_dice_finalize(c, _p(stats), float(smooth), float(eps), int(bool(log_loss)), _p(out[0:1]), _p(out[1:]), st)
+        ctx.save_for_backward(lg, target, out)
+        ctx.meta = (n, c, h, w, cp)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, target, out = ctx.saved_tensors
+        n, c, h, w, cp = ctx.meta
+        d = torch.empty((n, h, w, cp), dtype=BF16, device=lg.device)
+        g = g.to(F32).reshape(1).contiguous()
+        lib().tok_dice_bwd(n * h * w, c, cp, _p(lg), _p(target), _p(out[1:]), _p(g), _p(d), _st())
+        d = d.permute(0, 3, 1, 2)
+        return (d if cp == c else d[:, :c]), None, None, None, None
+
+
+def dice_multiclass(logits, target, smooth=0.0, eps=1e-7, log_loss=False):
+    if logits.dim() != 4 or logits.shape[1] > 64:
+        raise NotImplementedError('DiceLoss: (B, C, H, W) logits with up to 64 classes')
+    return DiceMulticlassFn.apply(logits, target, smooth, eps, log_loss)
+
+
 def softmax_xent_nhwc(logits, target, ignore_index=-100):
     if logits.shape[1] > 64:
         raise NotImplementedError('CrossEntropyLoss on 4-D logits supports up to 64 classes')
