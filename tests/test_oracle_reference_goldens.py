@@ -114,3 +114,38 @@ def test_dice_loss(case):
     val.backward()
     close(val, case['loss'])
     close(x.grad, case['grad'])
+
+
+# ------------------------------------------------------------------ host logic pinned by the reference's own code
+@pytest.mark.parametrize('case', G['JointLoss'], ids=lambda c: f"{c['weights']}-{c['normalize']}")
+def test_joint_loss_matches_reference(case):
+    """torchok_b200.losses.JointLoss (host logic, shipped) vs the reference's losses/base.py executed by path."""
+    from torchok_b200.losses.base import JointLoss
+    j = JointLoss([torch.nn.MSELoss(), torch.nn.L1Loss()],
+                  [{'input': 'pred_a', 'target': 'gt'}, {'input': 'pred_b', 'target': 'gt'}],
+                  tags=['mse', 'l1'], weights=list(case['weights']), normalize_weights=case['normalize'])
+    total, tagged = j(**case['inputs'])
+    close(total, case['total'])
+    assert set(tagged) == set(case['tagged'])
+    for k, v in case['tagged'].items():
+        close(tagged[k], v)
+
+
+@pytest.mark.parametrize('case', G['paramwise_cfg'], ids=lambda c: ','.join(sorted(c['cfg'])))
+def test_paramwise_cfg_matches_reference(case):
+    """constructor/paramwise.py vs the param groups built by the reference's Constructor.add_params
+    (constructor/constructor.py:162-251) on the same module tree."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        '_mk_goldens', os.path.join(os.path.dirname(__file__), 'golden', 'make_reference_goldens.py'))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    from torchok_b200.constructor.paramwise import paramwise_multipliers
+    module = mk.build_from_spec(case['spec'])
+    for name in case['frozen']:
+        dict(module.named_parameters())[name].requires_grad_(False)
+    mult = paramwise_multipliers(module, case['cfg'])
+    got = {n: mult[p] for n, p in module.named_parameters()}
+    assert set(got) == set(case['multipliers'])
+    for n, (lr, wd) in case['multipliers'].items():
+        assert got[n] == pytest.approx((lr, wd), rel=1e-12, abs=1e-12), (n, got[n], (lr, wd))
