@@ -188,6 +188,39 @@ class _ArenaOptimizer:
     def zero_grad(self, set_to_none=False):
         self.arena.zero_grad()
 
+    # -- checkpointing: state is stored per parameter NAME so that it survives a different arena layout -------------
+    _STATE_BUFFERS = ('buf', 'exp_avg', 'exp_avg_sq')
+
+    def state_dict(self, module):
+        """{'step', 'lr', 'state': {buffer: {parameter name: tensor}}} for the parameters of `module` in the arena."""
+        a = self.arena
+        names = {id(p): n for n, p in module.named_parameters()}
+        state = {}
+        for key in self._STATE_BUFFERS:
+            flat = getattr(self, key, None)
+            if flat is None:
+                continue
+            state[key] = {names[id(p)]: flat[off:off + p.numel()].detach().cpu().clone()
+                          for p, off in zip(a.params, a.offsets) if id(p) in names}
+        return {'step': int(self.step_dev.item()), 'lr': self._lr, 'state': state}
+
+    def load_state_dict(self, state, module):
+        a = self.arena
+        names = {id(p): n for n, p in module.named_parameters()}
+        for key, per_name in state.get('state', {}).items():
+            flat = getattr(self, key, None)
+            if flat is None:
+                continue
+            for p, off in zip(a.params, a.offsets):
+                src = per_name.get(names.get(id(p)))
+                if src is not None:
+                    if src.numel() != p.numel():
+                        raise ValueError(f'optimizer state {key} of {names[id(p)]}: {src.numel()} values for a '
+                                         f'parameter of {p.numel()}')
+                    flat[off:off + p.numel()].copy_(src.reshape(-1))
+        self.step_dev.fill_(int(state.get('step', 0)))
+        self.lr = state.get('lr', self._lr)
+
 
 class ArenaSGD(_ArenaOptimizer):
     """torch.optim.SGD (registered in torchok/optim/optimizers/__init__.py:9-19) over the flat arena."""
@@ -312,7 +345,9 @@ class StreamLoop:
 
     def train_step(self, batch):
         self.task.train()
-        if not self.use_graph:
+        odd_shape = self.static is not None and any(
+            torch.is_tensor(batch.get(k)) and batch[k].shape != v.shape for k, v in self.static.items())
+        if not self.use_graph or odd_shape:   # e.g. the short last batch of an epoch: run it outside the graph
             dev_batch = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v)
                          for k, v in batch.items()}
             out = self._eager_step(dev_batch)
@@ -337,7 +372,8 @@ class StreamLoop:
             mode = 'thread_local' if self.world > 1 else 'global'
             with torch.cuda.graph(g, stream=self.stream, capture_error_mode=mode):
                 out = self._eager_step(static)
-                self.loss = out['loss'].detach()
+                self._graph_loss = out['loss'].detach()
+                self._graph_output = getattr(self.task, 'last_output', None)   # static forward outputs (metrics)
             self.graph = g
             self._restore(snap)
             del snap
@@ -345,8 +381,18 @@ class StreamLoop:
         self.graph.replay()
         self.steps += 1
         for m in self._bns:
-            m._pending_batches += 1
+            if m.track_running_stats:
+                m._pending_batches += 1
+        self.loss = self._graph_loss
+        if self._graph_output is not None:
+            self.task.last_output = self._graph_output
         return self.loss
+
+    def reset_graph(self):
+        """Drop the captured step; the next `train_step` warms up and captures again.  Needed whenever what a step
+        launches changes: the frozen set (callbacks.FreezeUnfreeze), the multiplier table, the batch shape."""
+        self.graph = None
+        self.static = None
 
     def _state_tensors(self):
         opt = self.optimizer

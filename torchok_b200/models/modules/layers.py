@@ -134,10 +134,14 @@ class BatchNorm2d(nn.BatchNorm2d):
         they stay exactly zero); `commit()` copies the updated running statistics back."""
         if self._tok_acc.dtype != F32:
             self._tok_acc = self._tok_acc.float()
-        if self.training and count_batch:
+        # `track_running_stats` switched off after construction (FreezeUnfreeze's `bn_track_running_stats: false`,
+        # torchok/callbacks/freeze_unfreeze.py:113-117): torch then normalises with batch statistics in training mode
+        # and leaves the running buffers alone — a momentum of zero in the fused finalize step does exactly that.
+        momentum = self.momentum if self.track_running_stats else 0.0
+        if self.training and count_batch and self.track_running_stats:
             self._pending_batches += 1
         if self.cp == self.num_features:
-            return K.BNState(self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+            return K.BNState(self.weight, self.bias, self.running_mean, self.running_var, self.eps, momentum,
                              self.training, self._tok_acc, self.cp)
         c, dev = self.num_features, self.weight.device
         pad = torch.zeros((4, self.cp), dtype=F32, device=dev)
@@ -147,7 +151,7 @@ class BatchNorm2d(nn.BatchNorm2d):
         pad[2, :c] = self.running_mean
         pad[3, :c] = self.running_var
         self._tok_pad = pad
-        return K.BNState(pad[0], pad[1], pad[2], pad[3], self.eps, self.momentum, self.training, self._tok_acc,
+        return K.BNState(pad[0], pad[1], pad[2], pad[3], self.eps, momentum, self.training, self._tok_acc,
                          self.cp)
 
     def commit(self):

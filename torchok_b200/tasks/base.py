@@ -62,6 +62,9 @@ class BaseTask(nn.Module, ABC):
         """torchok/tasks/base.py:125-133 minus logging/metrics (done by the loop on device-side accumulators)."""
         output = self.forward_with_gt(batch)
         total_loss, tagged = self.losses(**output)
+        # what `metrics_manager.update(Phase.TRAIN, **output)` reads (base.py:130); under graph replay these are the
+        # graph's static output tensors, refreshed by every replay
+        self.last_output = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in output.items()}
         out = {'loss': total_loss}
         out.update(tagged)
         return out
