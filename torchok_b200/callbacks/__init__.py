@@ -251,6 +251,24 @@ class EarlyStopping(Callback):
         self.best, self.wait = state.get('best'), state.get('wait', 0)
 
 
+@CALLBACKS.register_class
+class CheckpointONNX(ModelCheckpoint):
+    """torchok/callbacks/checkpoint_onnx.py:13-83 writes an .onnx file next to each kept checkpoint.  The modules here
+    execute hand-written kernels through a C ABI, which torch.onnx cannot trace, so this keeps the ModelCheckpoint
+    behaviour (the .ckpt files load into the reference's torch.nn modules: same state-dict keys) and says once that
+    the ONNX file is not produced."""
+
+    def __init__(self, *args, onnx_params=None, remove_head=False, export_to_onnx=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.onnx_params, self.remove_head = onnx_params or {}, remove_head
+
+    def setup(self, runner):
+        super().setup(runner)
+        import warnings
+        warnings.warn('CheckpointONNX: ONNX export is not available for the sm_100a kernel modules; '
+                      'checkpoints (.ckpt) are written as with ModelCheckpoint')
+
+
 def _accepted(name):
     cls = type(name, (Callback,), {'__init__': lambda self, *a, **k: None,
                                    '__doc__': f'{name}: accepted for config compatibility; no effect in the stream loop.'})
@@ -258,6 +276,6 @@ def _accepted(name):
 
 
 for _n in ('FinalizeLogger', 'TQDMProgressBar', 'RichProgressBar', 'ModelSummary', 'RichModelSummary',
-           'LearningRateMonitor', 'DeviceStatsMonitor', 'Timer', 'CheckpointONNX'):
+           'LearningRateMonitor', 'DeviceStatsMonitor', 'Timer'):
     CALLBACKS.register_class(_accepted(_n))
 del _n

@@ -66,6 +66,27 @@ class Compose:
 
 
 @TRANSFORMS.register_class
+class OneOf:
+    """albumentations.OneOf: with probability `p` apply exactly one of `transforms`, drawn with weights equal to the
+    members' own `p` (normalised)."""
+
+    def __init__(self, transforms, p=0.5, **unused):
+        self.transforms, self.p = list(transforms), p
+        w = np.array([getattr(t, 'p', 1.0) for t in self.transforms], dtype=np.float64)
+        self.weights = w / w.sum() if w.sum() > 0 else np.full(len(w), 1.0 / max(len(w), 1))
+
+    def __call__(self, **sample):
+        if self.transforms and np.random.random() < self.p:
+            t = self.transforms[int(np.random.choice(len(self.transforms), p=self.weights))]
+            saved, t.p = getattr(t, 'p', 1.0), 1.0       # the chosen member is applied unconditionally
+            try:
+                sample = t(**sample)
+            finally:
+                t.p = saved
+        return sample
+
+
+@TRANSFORMS.register_class
 class Resize(_Transform):
     def __init__(self, height, width, interpolation=1, always_apply=False, p=1.0):
         super().__init__(always_apply, p)
