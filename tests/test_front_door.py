@@ -390,8 +390,12 @@ class _CpuLoop:
             p.grad = None
         out = self.task.training_step(batch)
         out['loss'].backward()
+        import torch.distributed as dist
         with torch.no_grad():
             for p in self.task.parameters():
+                if p.grad is not None and dist.is_available() and dist.is_initialized():
+                    dist.all_reduce(p.grad)                          # what engine.BucketAllReduce does per bucket
+                    p.grad /= dist.get_world_size()
                 if p.grad is not None:
                     m = (self.optimizer.mults or {}).get(p, (1.0, 1.0))[0]
                     p -= self.optimizer.lr * m * p.grad
@@ -623,3 +627,70 @@ def test_transforms_and_cifar_reader(tmp_path):
     img = np.arange(16, dtype=np.uint8).reshape(4, 4, 1)
     out = t(image=img, mask=img[..., 0])
     assert out['image'][..., 0].tolist() == [[6, 5], [10, 9]] and out['mask'].tolist() == [[6, 5], [10, 9]]
+
+
+# ------------------------------------------------------------------------------------------------ world size 2 (gloo)
+class MetricMemoryBlock(Metric):
+    """test_metric_manager_ddp.py:43-53: a list state gathered over ranks at compute time."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.add_state('memory_list', default=[], dist_reduce_fx=None)
+
+    def update(self, state):
+        self.memory_list.append(state)
+
+    def compute(self):
+        return torch.tensor(torch.cat(self.synced_states()['memory_list']).shape[0])
+
+
+def _ddp_worker(rank, world, port, tmp, ret):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    if 'MetricMemoryBlock' not in tb.METRICS:
+        tb.METRICS.register_class(MetricMemoryBlock)
+    # (1) the reference's DDP metric case: 50 samples x 5 epochs sharded over the ranks
+    mm = MetricsManager([dict(name='Accuracy', mapping=dict(preds='predict', target='target'), phases=['TRAIN'],
+                              params=dict(task='multiclass', num_classes=10)),
+                         dict(name='MetricMemoryBlock', mapping=dict(state='predict'), phases=['TRAIN'])])
+    for _ in range(5):
+        for i in range(rank * 4, 50, 4 * world):            # DistributedSampler-like interleaving of batches of 4
+            mm.update(Phase.TRAIN, predict=torch.tensor(PREDICTS[i:i + 4]), target=torch.tensor(LABELS[i:i + 4]))
+    out = {k: float(v) for k, v in mm.on_epoch_end(Phase.TRAIN).items()}
+    # (2) the Runner under two ranks: sharded TRAIN data, gradients averaged by the stand-in loop, metrics / losses
+    # combined over ranks, files written by rank 0 only
+    cfg = _runner_cfg(tmp, trainer={'max_epochs': 2})
+    r = Runner(cfg, loop_factory=_CpuLoop)
+    logs = r.fit()
+    ret[rank] = dict(metrics=out, logs={k: float(v) for k, v in logs.items()}, steps=r.global_step,
+                     weight=r.task.head.weight.detach().clone(), wrote=os.path.exists(os.path.join(tmp, 'run', 'metrics.csv')))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_front_door_world_size_two_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    ret = ctx.Manager().dict()
+    port = 29300 + os.getpid() % 500
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, str(tmp_path), ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    a, b = ret[0], ret[1]
+    # test_metric_manager_ddp.py:15-24,100-108: Accuracy 0.18, memory block = all samples of all epochs
+    for r in (a, b):
+        assert r['metrics']['train/Accuracy'] == pytest.approx(0.18, abs=1e-7)
+        assert r['metrics']['train/MetricMemoryBlock'] == len(LABELS) * 5
+    # 40 samples / (2 ranks x batch 8) = 3 steps per rank and epoch (DistributedSampler pads 20 -> 3 batches of 8,8,4)
+    assert a['steps'] == b['steps'] == 6
+    assert torch.equal(a['weight'], b['weight'])                       # replicas stay in step
+    for k in ('train/loss', 'train/Accuracy', 'valid/loss', 'valid/Accuracy'):
+        assert a['logs'][k] == pytest.approx(b['logs'][k], rel=1e-6), k
+    assert a['wrote'] and b['wrote']                                   # same tmp dir: the file exists, written once
+    rows = open(os.path.join(str(tmp_path), 'run', 'metrics.csv')).read().strip().splitlines()
+    assert len(rows) == len(set(rows))                                 # no duplicated rows from a second writer
