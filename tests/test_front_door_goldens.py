@@ -1,0 +1,78 @@
+"""Front-door host logic replayed against vectors produced by the REFERENCE's own files
+(tests/golden/make_front_door_goldens.py executes torchok/constructor/load.py, torchok/metrics/metrics_manager.py and
+torchok/callbacks/freeze_unfreeze.py by path under stubbed framework imports; fixture
+tests/golden/front_door_goldens.pt)."""
+import importlib.util
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+import torchok_b200 as tb
+from torchok_b200.callbacks import FreezeUnfreeze
+from torchok_b200.constructor.load import load_checkpoint
+from torchok_b200.metrics.metrics_manager import MetricsManager
+
+HERE = os.path.join(os.path.dirname(__file__), 'golden')
+G = torch.load(os.path.join(HERE, 'front_door_goldens.pt'), weights_only=False)
+_spec = importlib.util.spec_from_file_location('_mk_front_door', os.path.join(HERE, 'make_front_door_goldens.py'))
+mk = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mk)            # helpers only: nothing under /root/reference is touched at import time
+
+for _cls in (mk.MockSum, mk.MockDict):
+    if _cls.__name__ not in tb.METRICS:
+        tb.METRICS.register_class(_cls)
+
+
+@pytest.mark.parametrize('case', G['MetricsManager'], ids=lambda c: '+'.join(p['name'] for p in c['spec']))
+def test_metrics_manager_matches_reference(case):
+    mgr = MetricsManager(case['spec'])
+    for phase, idx in case['updates']:
+        mgr.update(phase, idx, emb=torch.zeros(1), y=torch.zeros(1))
+    for phase, want in case['logs'].items():
+        got = {k: int(v) for k, v in mgr.on_epoch_end(phase).items()}
+        assert got == want, phase
+    assert {k: int(v) for k, v in mgr.on_epoch_end('VALID').items()} == case['valid_after_reset']
+
+
+@pytest.mark.parametrize('case', G['load_checkpoint'], ids=lambda c: f"{sorted(c['overrides'])}-{c['exclude_keys']}")
+def test_load_checkpoint_matches_reference(case, tmp_path):
+    task = mk.tree_from_spec(case['spec'])
+    task.load_state_dict(case['initial'])
+    torch.save({'state_dict': case['base']}, tmp_path / 'base.ckpt')
+    paths = {}
+    for name, state in case['overrides'].items():
+        torch.save(state, tmp_path / f'{name}.pth')
+        paths[name] = str(tmp_path / f'{name}.pth')
+    load_checkpoint(task, str(tmp_path / 'base.ckpt'), paths or None, case['exclude_keys'] or None)
+    got = task.state_dict()
+    assert set(got) == set(case['loaded'])
+    for k, v in case['loaded'].items():
+        assert torch.equal(got[k], v), k
+
+
+@pytest.mark.parametrize('case', G['FreezeUnfreeze'], ids=lambda c: str([r['module_name'] for r in c['rules']]))
+def test_freeze_unfreeze_matches_reference(case):
+    """Epoch-by-epoch `requires_grad` of every parameter and `track_running_stats` of every BatchNorm: the
+    reference's freeze_before_training, then finetune_function(epoch) for epochs 0..3."""
+    task = mk.tree_from_spec(case['spec'])
+    cb = FreezeUnfreeze(case['rules'], top_down_freeze_order=case['top_down'])
+
+    class R:                                    # the two things the hooks touch on a runner
+        current_epoch = 0
+        changes = 0
+
+        def frozen_set_changed(self):
+            self.changes += 1
+    r = R()
+    r.task = task
+    cb.setup(r)
+    assert mk.flags(task) == case['history'][0]
+    for epoch in range(4):
+        r.current_epoch = epoch
+        cb.on_train_epoch_start(r)
+        assert mk.flags(task) == case['history'][epoch + 1], epoch
+    distinct = sum(a != b for a, b in zip(case['history'], case['history'][1:]))
+    assert r.changes == 1 + distinct            # the step graph is recaptured exactly when the flags change
+    assert case['n_groups'] == 1                # thawing adds no optimizer group in the reference either (all present)
