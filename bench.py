@@ -313,7 +313,7 @@ def run_ours(args):
         step_tf = FLOP_PER_IMG * B / (ms_step * 1e-3) / 1e12
         h2d = host_img[0].numel() * host_img[0].element_size() + host_tgt[0].numel() * host_tgt[0].element_size()
         cpu = None
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:     # the CPU baseline is an N=1 leg (rank 0 only; the other ranks would idle)
             cores = os.cpu_count()
             torch.set_num_threads(cores)
             ips, ms = cpu_reference(args.cpu_batch, 3, 1)
