@@ -559,7 +559,8 @@ class SegmentationTask(nn.Module):
 
 class FPN(nn.Module):
     """mmdet 3.0.0 necks.FPN with torchok's reversed in_channels (necks/detection/fpn.py:61-117); ConvModule defaults
-    (no norm, no activation) => plain biased convs under `.conv`.  PARITY UNPINNED (mmdet not vendored, no upstream test)."""
+    (no norm, no activation) => plain biased convs under `.conv`.  Parity unpinned by reference goldens (mmdet not
+    vendored, no upstream test); cross-checked against torchvision.ops.FeaturePyramidNetwork in tests/test_oracle_models.py."""
 
     class _CM(nn.Module):
         def __init__(self, cin, cout, k, stride=1, padding=0):

@@ -117,3 +117,42 @@ def test_oracle_swinv2_shape_contract():
     with torch.no_grad():
         feats = o.forward_features(torch.randn(2, 3, 64, 64))
     assert [tuple(f.shape) for f in feats] == [(2, 3, 64, 64), (2, 96, 16, 16), (2, 192, 8, 8), (2, 384, 4, 4), (2, 768, 2, 2)]
+
+
+@pytest.mark.parametrize('extra', ['maxpool', 'p6p7'])
+def test_oracle_fpn_matches_torchvision_fpn(extra):
+    """mmdet 3.0.0's FPN (what torchok/models/necks/detection/fpn.py:61-117 wraps) is not in this image; torchvision's
+    FeaturePyramidNetwork is an independent implementation of the same pyramid: 1x1 laterals, nearest top-down add,
+    3x3 output convs, and either a stride-2 max-pool level (mmdet: add_extra_convs=False) or P6/P7 convs on C5 with a
+    ReLU in between (mmdet: add_extra_convs='on_input', relu_before_extra_convs=True).  Same weights => same outputs
+    and input gradients."""
+    from collections import OrderedDict
+
+    from torchvision.ops import FeaturePyramidNetwork
+    from torchvision.ops.feature_pyramid_network import LastLevelMaxPool, LastLevelP6P7
+    torch.manual_seed(11)
+    chans, out_c = [24, 40, 64], 16
+    blocks = LastLevelMaxPool() if extra == 'maxpool' else LastLevelP6P7(chans[-1], out_c)
+    tv = FeaturePyramidNetwork(chans, out_c, extra_blocks=blocks)
+    kw = dict(num_outs=4) if extra == 'maxpool' else \
+        dict(num_outs=5, add_extra_convs='on_input', relu_before_extra_convs=True)
+    fpn = om.FPN(chans[::-1], out_c, **kw)               # torchok hands the channels over reversed (fpn.py:66)
+    with torch.no_grad():
+        for i in range(3):
+            fpn.lateral_convs[i].conv.load_state_dict(tv.inner_blocks[i][0].state_dict())
+            fpn.fpn_convs[i].conv.load_state_dict(tv.layer_blocks[i][0].state_dict())
+        if extra == 'p6p7':
+            fpn.fpn_convs[3].conv.load_state_dict(tv.extra_blocks.p6.state_dict())
+            fpn.fpn_convs[4].conv.load_state_dict(tv.extra_blocks.p7.state_dict())
+    feats = [torch.randn(2, c, s, s) for c, s in zip(chans, (20, 10, 5))]
+    a = [f.clone().requires_grad_(True) for f in feats]
+    b = [f.clone().requires_grad_(True) for f in feats]
+    want = list(tv(OrderedDict((str(i), f) for i, f in enumerate(a))).values())
+    got = list(fpn(b))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and torch.allclose(g, w, rtol=1e-5, atol=1e-6), float((g - w).abs().max())
+    sum((w * w).sum() for w in want).backward()
+    sum((g * g).sum() for g in got).backward()
+    for x, y in zip(a, b):
+        assert torch.allclose(x.grad, y.grad, rtol=1e-4, atol=1e-5)
