@@ -156,3 +156,59 @@ def test_oracle_fpn_matches_torchvision_fpn(extra):
     sum((g * g).sum() for g in got).backward()
     for x, y in zip(a, b):
         assert torch.allclose(x.grad, y.grad, rtol=1e-4, atol=1e-5)
+
+
+def _copy_swin_block(o, tv, dim):
+    sd = o.state_dict()
+    with torch.no_grad():
+        tv.norm1.load_state_dict({'weight': sd['norm1.weight'], 'bias': sd['norm1.bias']})
+        tv.norm2.load_state_dict({'weight': sd['norm2.weight'], 'bias': sd['norm2.bias']})
+        tv.attn.qkv.weight.copy_(sd['attn.qkv.weight'])
+        tv.attn.qkv.bias.copy_(torch.cat([sd['attn.q_bias'], torch.zeros(dim), sd['attn.v_bias']]))
+        tv.attn.proj.load_state_dict({'weight': sd['attn.proj.weight'], 'bias': sd['attn.proj.bias']})
+        tv.attn.logit_scale.copy_(sd['attn.logit_scale'])
+        tv.attn.cpb_mlp[0].load_state_dict({'weight': sd['attn.cpb_mlp.0.weight'], 'bias': sd['attn.cpb_mlp.0.bias']})
+        tv.attn.cpb_mlp[2].weight.copy_(sd['attn.cpb_mlp.2.weight'])
+        tv.mlp[0].load_state_dict({'weight': sd['mlp.fc1.weight'], 'bias': sd['mlp.fc1.bias']})
+        tv.mlp[3].load_state_dict({'weight': sd['mlp.fc2.weight'], 'bias': sd['mlp.fc2.bias']})
+
+
+def test_oracle_swinv2_network_matches_torchvision():
+    """The WIRING of the Swin-V2 restatement (patch embedding -> stages of alternately shifted blocks -> PatchMerging
+    between stages -> final LayerNorm -> B x C x H x W, torchok/models/backbones/swin.py:204-256 over timm 0.6.13) against
+    torchvision's independent SwinTransformer(block=SwinTransformerBlockV2, downsample_layer=PatchMergingV2): same
+    weights, 128x128 input, window 4 (every stage grid >= the window, where timm shrinks the window and torchvision
+    pads instead), outputs and the input gradient."""
+    from functools import partial
+
+    from torchvision.models.swin_transformer import PatchMergingV2, SwinTransformer, SwinTransformerBlockV2
+
+    from oracle import swin as osw
+    torch.manual_seed(5)
+    depths, heads, dim = (2, 2, 2, 2), (1, 2, 4, 8), 32
+    o = osw.SwinTransformerV2(img_size=128, embed_dim=dim, depths=depths, num_heads=heads, window_size=4)
+    osw.dedegenerate_ln_(o, 3)
+    tv = SwinTransformer(patch_size=[4, 4], embed_dim=dim, depths=list(depths), num_heads=list(heads), window_size=[4, 4],
+                         stochastic_depth_prob=0.0, num_classes=3, block=SwinTransformerBlockV2,
+                         downsample_layer=PatchMergingV2, norm_layer=partial(torch.nn.LayerNorm, eps=1e-5))
+    with torch.no_grad():
+        tv.features[0][0].load_state_dict(o.patch_embed.proj.state_dict())
+        tv.features[0][2].load_state_dict(o.patch_embed.norm.state_dict())
+        for i, layer in enumerate(o.layers):
+            for j, blk in enumerate(layer.blocks):
+                _copy_swin_block(blk, tv.features[1 + 2 * i][j], dim * 2 ** i)
+            if layer.downsample is not None:
+                tv.features[2 + 2 * i].reduction.weight.copy_(layer.downsample.reduction.weight)
+                tv.features[2 + 2 * i].norm.load_state_dict(layer.downsample.norm.state_dict())
+        tv.norm.load_state_dict(o.feature_norms[-1].state_dict())
+    o.eval(), tv.eval()
+    x = torch.randn(2, 3, 128, 128)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    a = o(xa)
+    b = tv.permute(tv.norm(tv.features(xb)))
+    assert a.shape == b.shape == (2, dim * 8, 4, 4)
+    assert torch.allclose(a, b, atol=5e-5, rtol=1e-4), float((a - b).abs().max())
+    r = torch.randn_like(a)
+    (a * r).sum().backward()
+    (b * r).sum().backward()
+    assert torch.allclose(xa.grad, xb.grad, atol=5e-5, rtol=1e-3), float((xa.grad - xb.grad).abs().max())
