@@ -103,6 +103,40 @@ UPDATES = [('TRAIN', 0), ('TRAIN', 0), ('VALID', 0), ('VALID', 2), ('VALID', 2),
            ('PREDICT', 0)]
 
 
+REGISTRY_NAMES = [('resnet18', 'resnet'), ('resnet50', 'resnet'), ('resnet101', 'resnet'), ('resnet9', 'resnet'),
+                  ('hrnet_w18', 'hrnet'), ('hrnet_w18_small_v2', 'hrnet'), ('swinv2_tiny_window8_256', 'swin'),
+                  ('Resnet_B', 'resnet')]
+REGISTRY_QUERIES = [dict(), dict(filter='resnet*'), dict(filter='*net*', exclude_filters='hr*'),
+                    dict(filter=['hrnet*', 'swin*']), dict(module='resnet'), dict(filter='*18*', module='hrnet'),
+                    dict(filter='nothing*'), dict(exclude_filters=['*small*', 'resnet1*']), dict(module='missing')]
+
+
+def registry_scenario(registry_cls):
+    """Everything a caller can observe from a Registry: listing under filters, lookups, error types and texts."""
+    reg = registry_cls('backbones')
+    for name, module in REGISTRY_NAMES:
+        mod = sys.modules.setdefault(f'fake_pkg.{module}', types.ModuleType(f'fake_pkg.{module}'))
+        fn = types.FunctionType((lambda: None).__code__, {}, name)
+        fn.__module__ = mod.__name__
+        assert reg.register_class(fn) is fn
+    res = {'lists': [reg.list_models(**q) for q in REGISTRY_QUERIES],
+           'contains': ['resnet18' in reg, 'nope' in reg], 'repr': repr(reg),
+           'object_to_module': dict(reg.object_to_module),
+           'exported': sorted(sys.modules['fake_pkg.hrnet'].__all__)}
+    errors = []
+    for action in (lambda: reg.get('nope'), lambda: reg['nope2'], lambda: reg.register_class(42),
+                   lambda: reg.register_class(reg.get('resnet18'))):
+        try:
+            action()
+            errors.append(None)
+        except Exception as e:  # noqa: BLE001
+            errors.append((type(e).__name__, str(e)))
+    res['errors'] = errors
+    for module in {m for _, m in REGISTRY_NAMES}:
+        del sys.modules[f'fake_pkg.{module}']
+    return res
+
+
 def main():
     install_stub_tree()
     out = {}
@@ -217,6 +251,18 @@ def main():
         cases.append(dict(spec=TASK_SPEC, rules=case['rules'], top_down=case['top_down'], history=history,
                           n_groups=len(opt.param_groups)))
     out['FreezeUnfreeze'] = cases
+
+    # ---- registry.py (the plug-in boundary itself) ---------------------------------------------------------------
+    import re
+    for name in ('timm', 'timm.models'):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    treg = types.ModuleType('timm.models.registry')      # timm 0.6.13 models/registry.py `_natural_key`
+    treg._natural_key = lambda s: [int(t) if t.isdigit() else t for t in re.split(r'(\d+)', s.lower())]
+    sys.modules['timm.models.registry'] = treg
+    rg = load('torchok.constructor.registry')
+    out['Registry'] = registry_scenario(rg.Registry)
 
     torch.save(out, OUT)
     print(f'wrote {OUT}: ' + ', '.join(f'{k} x{len(v)}' for k, v in out.items()))

@@ -76,3 +76,13 @@ def test_freeze_unfreeze_matches_reference(case):
     distinct = sum(a != b for a, b in zip(case['history'], case['history'][1:]))
     assert r.changes == 1 + distinct            # the step graph is recaptured exactly when the flags change
     assert case['n_groups'] == 1                # thawing adds no optimizer group in the reference either (all present)
+
+
+def test_registry_matches_reference():
+    """The same scenario through torchok/constructor/registry.py (executed by path; timm's `_natural_key` stubbed with
+    its one-line definition) and through torchok_b200.constructor.Registry: listings under every filter form, `in`,
+    repr, module bookkeeping, `__all__` export, and the type + text of all four errors."""
+    from torchok_b200.constructor.registry import Registry
+    got = mk.registry_scenario(Registry)
+    want = G['Registry']
+    assert got == want
