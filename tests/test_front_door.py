@@ -400,6 +400,7 @@ class _CpuLoop:
                     m = (self.optimizer.mults or {}).get(p, (1.0, 1.0))[0]
                     p -= self.optimizer.lr * m * p.grad
         self.optimizer.steps += 1
+        self.tagged = {k: v.detach() for k, v in out.items() if k != 'loss'}
         return out['loss'].detach()
 
 
@@ -434,7 +435,8 @@ def test_runner_epochs_logging_checkpoints_freeze_and_resume(tmp_path):
     w0 = r.task.backbone[0].weight.detach().clone()
     logs = r.fit()
     assert r.current_epoch == 3 and r.global_step == 15
-    assert {'train/loss', 'train/ce', 'valid/loss', 'valid/ce', 'train/Accuracy', 'valid/Accuracy'} <= set(logs) | {'train/ce'}
+    assert {'train/loss', 'train/ce', 'valid/loss', 'valid/ce', 'train/Accuracy', 'valid/Accuracy'} <= set(logs)
+    assert logs['train/ce'] == pytest.approx(logs['train/loss'], rel=1e-6)       # one loss, weight normalised to 1
     assert 0.0 <= logs['valid/Accuracy'] <= 1.0
     # ExponentialLR per epoch: 0.1 -> 0.0125 after three epochs
     assert r.loop.optimizer.lr == pytest.approx(0.1 * 0.5 ** 3)

@@ -318,6 +318,7 @@ class StreamLoop:
         self.graph = None
         self.static = None
         self.loss = None
+        self.tagged = {}      # tagged JointLoss values of the last step (device scalars), logged as train/<tag>
         self.outputs = None
         self.steps = 0
         self.stream = torch.cuda.Stream()
@@ -353,6 +354,7 @@ class StreamLoop:
             out = self._eager_step(dev_batch)
             self.steps += 1
             self.loss = out['loss'].detach()
+            self.tagged = {k: v.detach() for k, v in out.items() if k != 'loss' and torch.is_tensor(v)}
             return self.loss
         cur = torch.cuda.current_stream()
         if self.graph is None:
@@ -373,6 +375,7 @@ class StreamLoop:
             with torch.cuda.graph(g, stream=self.stream, capture_error_mode=mode):
                 out = self._eager_step(static)
                 self._graph_loss = out['loss'].detach()
+                self._graph_tagged = {k: v.detach() for k, v in out.items() if k != 'loss' and torch.is_tensor(v)}
                 self._graph_output = getattr(self.task, 'last_output', None)   # static forward outputs (metrics)
             self.graph = g
             self._restore(snap)
@@ -384,6 +387,7 @@ class StreamLoop:
             if m.track_running_stats:
                 m._pending_batches += 1
         self.loss = self._graph_loss
+        self.tagged = self._graph_tagged
         if self._graph_output is not None:
             self.task.last_output = self._graph_output
         return self.loss

@@ -274,12 +274,14 @@ class Runner:
             if hasattr(train_loader.sampler, 'set_epoch'):
                 train_loader.sampler.set_epoch(self.current_epoch)
             n = _limit(len(train_loader), tr.get('limit_train_batches'))
-            loss_sum, steps = None, 0
+            loss_sum, steps, tag_sums = None, 0, {}
             for i, batch in enumerate(train_loader):
                 if i >= n:
                     break
                 loss = self.loop.train_step(batch)                          # device scalar, no sync
                 loss_sum = loss.float().clone() if loss_sum is None else loss_sum + loss
+                for tag, value in getattr(self.loop, 'tagged', {}).items():       # train/<tag>, tasks/base.py:163-173
+                    tag_sums[tag] = value.float().clone() if tag not in tag_sums else tag_sums[tag] + value
                 steps += 1
                 self.global_step += 1
                 if train_metrics:
@@ -292,6 +294,7 @@ class Runner:
                     self.should_stop = True
                     break
             logs = {'train/loss': self._mean_over_ranks(loss_sum / max(steps, 1))} if steps else {}
+            logs.update({f'train/{t}': self._mean_over_ranks(v / max(steps, 1)) for t, v in tag_sums.items()})
             logs.update(self.metrics_manager.on_epoch_end(Phase.TRAIN))
             logs['step'] = float(self.current_epoch)
             self._log(logs)
