@@ -18,7 +18,12 @@ $(LIB): $(OBJS)
 tests/gpu/tok_selftest: tests/gpu/tok_selftest.cu $(LIB) include/tokb200.h
 	$(NVCC) $(ARCH) -O2 -std=c++17 -o $@ $< -Ltorchok_b200 -ltokb200 -Xlinker -rpath -Xlinker '$$ORIGIN/../../torchok_b200' -cudart static
 
-clean:
-	rm -f $(OBJS) $(CSRC)/*.log $(LIB) tests/gpu/tok_selftest
+# bring-up probe of the cta_group::2 UMMA path (stand-alone; not part of `all`)
+probe: tests/gpu/gemm2cta_probe
+tests/gpu/gemm2cta_probe: tests/gpu/gemm2cta_probe.cu $(CSRC)/tok_ptx.cuh
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -I $(CSRC) -o $@ $< -lcuda
 
-.PHONY: all clean
+clean:
+	rm -f $(OBJS) $(CSRC)/*.log $(LIB) tests/gpu/tok_selftest tests/gpu/gemm2cta_probe
+
+.PHONY: all clean probe
