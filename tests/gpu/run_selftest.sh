@@ -10,6 +10,16 @@ for g in gemm conv dgrad; do
   echo "exit=$?" >> gpurun_out/selftest_${g}_bn256.log
   tail -n 3 gpurun_out/selftest_${g}_bn256.log
 done
+# CTA-pair (cta_group::2) conv kernel, opt-in: first the mechanism probe, then the pair shapes with and without it
+echo "===== gemm2cta_probe"
+timeout 60 tests/gpu/gemm2cta_probe > gpurun_out/gemm2cta_probe.log 2>&1; echo "exit=$?" >> gpurun_out/gemm2cta_probe.log
+tail -n 3 gpurun_out/gemm2cta_probe.log
+echo "===== group pair (baseline 128x256 tiles)"
+TOK_CONV_BN=256 timeout 120 tests/gpu/tok_selftest pair > gpurun_out/selftest_pair_base.log 2>&1
+echo "exit=$?" >> gpurun_out/selftest_pair_base.log; tail -n 12 gpurun_out/selftest_pair_base.log
+echo "===== group pair (TOK_CONV_2CTA=1)"
+TOK_CONV_2CTA=1 TOK_CONV_BN=256 timeout 120 tests/gpu/tok_selftest pair > gpurun_out/selftest_pair_2cta.log 2>&1
+echo "exit=$?" >> gpurun_out/selftest_pair_2cta.log; tail -n 12 gpurun_out/selftest_pair_2cta.log
 for g in ${@:-gemm conv dgrad wgrad stem elem perf}; do
   echo "===== group $g"
   timeout 120 tests/gpu/tok_selftest $g > gpurun_out/selftest_$g.log 2>&1

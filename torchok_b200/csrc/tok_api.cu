@@ -16,6 +16,9 @@ cudaError_t launch_conv_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                     const CUtensorMap& tmD, const ConvFwdParams& p, int bn, bool b_mn,
                                     cudaStream_t st);
+// tok_conv2.cu: CTA-pair (cta_group::2) variant of the 128x256 persistent kernel, opt-in through TOK_CONV_2CTA=1
+cudaError_t launch_conv_fwd_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                 const CUtensorMap& tmD, const ConvFwdParams& p, bool b_mn, cudaStream_t st);
 cudaError_t launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const ConvWgradParams& p, int bn,
                               int splits, cudaStream_t st);
 void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
@@ -150,7 +153,11 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
   CUtensorMap tmB;
   static const bool v1 = getenv("TOK_CONV_V1") != nullptr;  // bring-up aid: the one-tile-per-CTA kernel
   const int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N, (long long)src.R * src.S * ac);
-  int rc = make_tmap_2d(&tmB, wmat, w_rows, w_cols, w_cols, b_mn ? 64 : bn);
+  // Opt-in CTA-pair kernel (unverified on hardware as a conv; the default path is untouched unless the variable is
+  // set): a 256x256 tile per pair of SMs, each CTA fetches half of the weight tile, hence the 128-row boxes.
+  static const bool pair_env = getenv("TOK_CONV_2CTA") != nullptr;
+  const bool pair = pair_env && !v1 && bn == 256 && !p.scatter && (M % 256) == 0 && (N % 256) == 0;
+  int rc = make_tmap_2d(&tmB, wmat, w_rows, w_cols, w_cols, b_mn ? 64 : (pair ? 128 : bn));
   if (rc) return rc;
   p.M = (int)M;
   p.N = N;
@@ -181,7 +188,8 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
         if (rc) return rc;
       }
     }
-    e = launch_conv_fwd_persist(tmA, tmB, tmC, tmD, p, bn, b_mn, st);
+    e = pair ? launch_conv_fwd_pair(tmA, tmB, tmC, tmD, p, b_mn, st)
+             : launch_conv_fwd_persist(tmA, tmB, tmC, tmD, p, bn, b_mn, st);
   }
   if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv_fwd launch: %s", cudaGetErrorString(e));
   return TOK_OK;
