@@ -1,6 +1,8 @@
 """Plain-torch CPU restatement of the reference's model path.  TEST INFRASTRUCTURE (see oracle/__init__.py).
 
-PARITY UNPINNED by reference goldens (shape-only tests upstream); cross-checked against torchvision.
+Pinning: see oracle/__init__.py — the torch-only reference files (ConvBnAct, heads, seg neck/head, losses) are PINNED by
+reference-executed goldens; the timm / mmdet networks are PARITY UNPINNED by reference goldens (shape-only tests
+upstream) and cross-checked against torchvision's independent ResNet / FPN.
 
 Follows:
   ResNet ............ torchok/models/backbones/resnet.py:408-563 (+ make_blocks :363-405) with timm 0.6.13

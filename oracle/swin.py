@@ -1,8 +1,8 @@
 """Plain-torch CPU restatement of Swin Transformer V2.  TEST INFRASTRUCTURE (see oracle/__init__.py).
 
 PARITY UNPINNED by reference goldens (upstream tests are shape-only: test_backbone.py:161-182); the block arithmetic
-is cross-checked against torchvision's independent SwinTransformerBlockV2 / PatchMergingV2 in
-tests/test_oracle_models.py.
+and the whole network are cross-checked against torchvision's independent SwinTransformerBlockV2 / PatchMergingV2 /
+SwinTransformer (V2) in tests/test_oracle_models.py (outputs and input gradient, copied weights).
 
 Follows torchok/models/backbones/swin.py:71-275 (BasicLayer returning (downsampled, pre-downsample), feature_norms,
 BCHW outputs) and timm 0.6.13 swin_transformer_v2: PatchEmbed conv4x4 s4 + LN; res-post-norm
