@@ -696,3 +696,78 @@ def test_front_door_world_size_two_gloo(tmp_path):
     assert a['wrote'] and b['wrote']                                   # same tmp dir: the file exists, written once
     rows = open(os.path.join(str(tmp_path), 'run', 'metrics.csv')).read().strip().splitlines()
     assert len(rows) == len(set(rows))                                 # no duplicated rows from a second writer
+
+
+def test_file_backed_example_datasets(tmp_path):
+    """ImageClassificationDataset / SOP / SweetPepper (what classification_imagenet.yaml, pairwise_sop.yaml and
+    segmentation_sweet_pepper.yaml name) on small generated image files: annotation formats, target conventions,
+    dtypes, missing-folder error."""
+    import cv2
+    import numpy as np
+    from torchok_b200.data import create_dataset
+    rng = np.random.RandomState(1)
+    tf = [{'name': 'Resize', 'params': {'height': 8, 'width': 8}}, {'name': 'Normalize'}, {'name': 'ToTensorV2'}]
+
+    def write(path, shape):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        img = rng.randint(0, 256, shape, dtype=np.uint8)
+        assert cv2.imwrite(path, img)
+        return img
+    # --- csv classification (multiclass + multilabel)
+    root = tmp_path / 'cls'
+    imgs = [write(str(root / f'im{i}.png'), (10, 12, 3)) for i in range(3)]
+    (root / 'ann.csv').write_text('image_path,label\nim0.png,2\nim1.png,0\nim2.png,1\n')
+    ds = create_dataset({'name': 'ImageClassificationDataset', 'transform': tf,
+                         'params': {'data_folder': str(root), 'annotation_path': 'ann.csv', 'num_classes': 3,
+                                    'input_dtype': 'float16'}})
+    s = ds[0]
+    assert len(ds) == 3 and s['image'].shape == (3, 8, 8) and s['image'].dtype == torch.float16
+    assert s['target'].dtype == torch.long and int(s['target']) == 2 and s['index'] == 0
+    raw = ds.get_raw(1)['image']
+    assert raw.shape == (10, 12, 3) and np.array_equal(raw, imgs[1][..., ::-1])     # stored BGR by cv2, returned RGB
+    (root / 'multi.csv').write_text('image_path,label\nim0.png,0 2\nim1.png,1\n')
+    ml = create_dataset({'name': 'ImageClassificationDataset', 'transform': tf,
+                         'params': {'data_folder': str(root), 'annotation_path': 'multi.csv', 'num_classes': 3,
+                                    'multilabel': True, 'target_dtype': 'float32'}})
+    assert ml[0]['target'].tolist() == [1.0, 0.0, 1.0]
+    with pytest.raises(ValueError, match='more than num_classes'):
+        create_dataset({'name': 'ImageClassificationDataset', 'transform': tf,
+                        'params': {'data_folder': str(root), 'annotation_path': 'ann.csv', 'num_classes': 2}})
+    with pytest.raises(ValueError, match='annotation_path'):
+        create_dataset({'name': 'ImageClassificationDataset', 'transform': tf, 'params': {'data_folder': str(root)}})
+    # --- SOP: space-separated txt, zero-based targets per split
+    sop = tmp_path / 'Stanford_Online_Products'
+    write(str(sop / 'bicycle_final' / 'a.JPG'), (9, 9, 3))
+    write(str(sop / 'chair_final' / 'b.JPG'), (9, 9))                                # gray file -> RGB
+    (sop / 'Ebay_train.txt').write_text('image_id class_id super_class_id path\n1 1 1 bicycle_final/a.JPG\n2 7 2 chair_final/b.JPG\n')
+    (sop / 'Ebay_test.txt').write_text('image_id class_id super_class_id path\n3 11319 1 bicycle_final/a.JPG\n4 11325 2 chair_final/b.JPG\n')
+    tr = create_dataset({'name': 'SOP', 'transform': tf, 'params': {'train': True, 'download': True, 'data_folder': str(tmp_path)}})
+    te = create_dataset({'name': 'SOP', 'transform': tf, 'params': {'train': False, 'download': False, 'data_folder': str(tmp_path)}})
+    assert [int(tr[i]['target']) for i in range(2)] == [0, 6] and [int(te[i]['target']) for i in range(2)] == [0, 6]
+    assert tr[1]['image'].shape == (3, 8, 8)
+    with pytest.raises(RuntimeError, match='Dataset not found or corrupted'):
+        create_dataset({'name': 'SOP', 'transform': tf, 'params': {'train': True, 'download': True,
+                                                                 'data_folder': str(tmp_path / 'nowhere')}})
+    # --- SweetPepper: image + mask files, mask resized with nearest neighbour, int64 target
+    sp = tmp_path / 'sweet_pepper'
+    write(str(sp / 'img' / '0.png'), (16, 16, 3))
+    mask = (rng.randint(0, 3, (16, 16))).astype(np.uint8)
+    os.makedirs(str(sp / 'msk'), exist_ok=True)
+    assert cv2.imwrite(str(sp / 'msk' / '0.png'), mask)
+    for name in ('train.csv', 'valid.csv'):
+        (sp / name).write_text('image_path,mask\nimg/0.png,msk/0.png\n')
+    seg = create_dataset({'name': 'SweetPepper', 'transform': tf,
+                          'params': {'train': True, 'download': True, 'data_folder': str(tmp_path)}})
+    s = seg[0]
+    assert s['image'].shape == (3, 8, 8) and s['target'].shape == (8, 8) and s['target'].dtype == torch.int64
+    assert set(s['target'].unique().tolist()) <= {0, 1, 2} and 'mask' not in s
+    want = cv2.resize(mask, (8, 8), interpolation=0)
+    assert torch.equal(s['target'], torch.from_numpy(want).long())
+    # --- FancyPCA keeps shape / dtype, changes colours, leaves masks alone
+    from torchok_b200.data import FancyPCA
+    np.random.seed(0)
+    img = rng.randint(0, 256, (12, 12, 3), dtype=np.uint8)
+    out = FancyPCA(alpha=0.5, p=1.0)(image=img, mask=mask)
+    assert out['image'].shape == img.shape and out['image'].dtype == np.uint8 and not np.array_equal(out['image'], img)
+    assert np.array_equal(out['mask'], mask)
+    assert 'ModelCheckpointWithOnnx' in tb.CALLBACKS

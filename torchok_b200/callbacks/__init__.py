@@ -269,6 +269,13 @@ class CheckpointONNX(ModelCheckpoint):
                       'checkpoints (.ckpt) are written as with ModelCheckpoint')
 
 
+@CALLBACKS.register_class
+class ModelCheckpointWithOnnx(CheckpointONNX):
+    """Name used by examples/configs/segmentation_sweet_pepper.yaml:145 and representation_arcface_sop.yaml:161 (the
+    reference itself registers only `CheckpointONNX`, so those two files fail there with a KeyError); same behaviour
+    as CheckpointONNX here."""
+
+
 def _accepted(name):
     cls = type(name, (Callback,), {'__init__': lambda self, *a, **k: None,
                                    '__doc__': f'{name}: accepted for config compatibility; no effect in the stream loop.'})

@@ -10,6 +10,8 @@ load and run unchanged on an offline box:
 * DATASETS `CIFAR10` / `CIFAR100` reading the standard python pickles from `data_folder` (sample dict of
   torchok/data/datasets/examples/cifar.py:139-163: 'image' CHW tensor of `input_dtype`, 'target', 'index').  There is
   no network here: `download: true` with the files absent raises the reference's RuntimeError text plus a hint;
+* DATASETS `ImageClassificationDataset`, `ImageSegmentationDataset`, `SOP`, `SweetPepper` (bottom of this file) with
+  the reference's annotation formats and sample dicts; TRANSFORMS `OneOf`, `FancyPCA`;
 * `SyntheticImages`: seeded random images / targets of a given shape, for smoke runs and benchmarks;
 * `create_dataloaders(data_cfg, phase)` = Constructor.create_dataloaders (torchok/constructor/constructor.py:268-312).
 """
@@ -347,3 +349,201 @@ def create_dataloaders(data_cfg, phase, distributed_sampler=True):
         params.setdefault('pin_memory', True)
         loaders.append(DataLoader(dataset, collate_fn=getattr(dataset, 'collate_fn', None), sampler=sampler, **params))
     return loaders
+
+
+# ------------------------------------------------------------------------------------- file-backed example datasets
+# What the other hot-path example configs name (classification_imagenet.yaml, pairwise_sop.yaml,
+# segmentation_sweet_pepper.yaml).  Same constructor arguments, annotation formats and sample dicts as the reference;
+# archives are never downloaded (no network): a missing folder raises the reference's RuntimeError text.
+def _read_image(path, image_format='rgb', reader_library='opencv', rgba_layout_color=0):
+    """torchok/data/datasets/base.py:67-92 for the formats the example datasets hold (8-bit gray / RGB / RGBA files)."""
+    if cv2 is None:
+        raise ImportError('reading image files needs opencv (cv2)')
+    img = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise ValueError(f'{path} image does not exist')
+    if img.dtype != np.uint8:
+        img = (img // 256).astype('uint8')
+    if img.ndim == 3 and img.shape[2] == 4:
+        img = cv2.cvtColor(img, cv2.COLOR_BGRA2RGBA)
+        alpha = img[..., 3:4] / 255
+        img = np.clip(img[..., :3] * alpha + rgba_layout_color * (1 - alpha), 0, 255).astype('uint8')
+    elif img.ndim == 3:
+        img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    if image_format == 'rgb':
+        return cv2.cvtColor(img, cv2.COLOR_GRAY2RGB) if img.ndim == 2 else img
+    if image_format == 'bgr':
+        return cv2.cvtColor(img, cv2.COLOR_GRAY2BGR) if img.ndim == 2 else cv2.cvtColor(img, cv2.COLOR_RGB2BGR)
+    if image_format == 'gray':
+        return (img if img.ndim == 2 else cv2.cvtColor(img, cv2.COLOR_RGB2GRAY))[..., None]
+    raise ValueError(f'Unsupported image format `{image_format}`')
+
+
+def _read_table(folder, annotation_path, dtype=None, **kw):
+    import pandas as pd
+    path = os.path.join(str(folder), annotation_path)
+    if annotation_path.endswith('.csv') or annotation_path.endswith('.txt'):
+        return pd.read_csv(path, dtype=dtype, **kw)
+    if annotation_path.endswith('.pkl'):
+        return pd.read_pickle(path)
+    raise ValueError('Detection dataset error. Annotation path is not in `csv` or `pkl` format')
+
+
+@DATASETS.register_class
+class ImageClassificationDataset(ImageDataset):
+    """csv / pkl of (image_path, label) rows: torchok/data/datasets/classification/classification.py:38-209."""
+
+    def __init__(self, data_folder, transform, augment=None, annotation_path=None, num_classes=None,
+                 input_column='image_path', input_dtype='float32', target_column='label', target_dtype='long',
+                 reader_library='opencv', image_format='rgb', rgba_layout_color=0, test_mode=False, multilabel=False,
+                 lazy_init=False, csv_path=None):
+        annotation_path = annotation_path if annotation_path is not None else csv_path
+        if annotation_path is None:
+            raise ValueError('`annotation_path` must be specified.')
+        super().__init__(transform, augment, input_dtype, reader_library, image_format, rgba_layout_color, test_mode)
+        if num_classes is None and multilabel:
+            raise ValueError('``num_classes`` must be specified when ``multilabel`` is `True`')
+        self.data_folder, self.num_classes, self.multilabel, self.lazy_init = str(data_folder), num_classes, multilabel, lazy_init
+        self.input_column, self.target_column, self.target_dtype = input_column, target_column, target_dtype
+        self.df = _read_table(data_folder, annotation_path,
+                              dtype={input_column: 'str', target_column: 'str' if multilabel else 'int'})
+        if not lazy_init and not test_mode:
+            self.df[target_column] = self.df[target_column].apply(self.process_function)
+
+    def process_function(self, target):
+        import re
+        if self.multilabel:
+            labels = list(map(int, re.findall(r'\d+', target)))
+            if max(labels) >= self.num_classes:
+                raise ValueError(f'Target column contains label: {max(labels)}, '
+                                 f'it\'s more than num_classes = {self.num_classes}')
+            multihot = np.zeros((self.num_classes,), dtype=bool)
+            multihot[labels] = True
+            return multihot
+        if self.num_classes is not None and target >= self.num_classes:
+            raise ValueError(f'Target column contains label: {target}, it\'s more than num_classes = {self.num_classes}')
+        return target
+
+    def get_raw(self, idx):
+        record = self.df.iloc[idx]
+        sample = {'image': _read_image(os.path.join(self.data_folder, record[self.input_column]), self.image_format,
+                                       self.reader_library, self.rgba_layout_color), 'index': idx}
+        if not self.test_mode:
+            target = record[self.target_column]
+            sample['target'] = self.process_function(target) if self.lazy_init else target
+        return self._apply(self.augment, sample)
+
+    def __getitem__(self, idx):
+        sample = super().__getitem__(idx)
+        if not self.test_mode:
+            sample['target'] = torch.tensor(sample['target']).type(getattr(torch, self.target_dtype))
+        return sample
+
+    def __len__(self):
+        return len(self.df)
+
+
+@DATASETS.register_class
+class ImageSegmentationDataset(ImageDataset):
+    """csv / pkl of (image_path, mask_path) rows: torchok/data/datasets/segmentation/image_segmentation.py:14-125."""
+
+    def __init__(self, data_folder, annotation_path, transform, augment=None, input_column='image_path',
+                 input_dtype='float32', target_column='mask_path', target_dtype='int64', reader_library='opencv',
+                 image_format='rgb', rgba_layout_color=0, test_mode=False):
+        super().__init__(transform, augment, input_dtype, reader_library, image_format, rgba_layout_color, test_mode)
+        self.data_folder, self.input_column, self.target_column = str(data_folder), input_column, target_column
+        self.target_dtype = target_dtype
+        self.df = _read_table(data_folder, annotation_path, dtype={input_column: 'str', target_column: 'str'})
+
+    def get_raw(self, idx):
+        record = self.df.iloc[idx]
+        sample = {'image': _read_image(os.path.join(self.data_folder, record[self.input_column]), self.image_format,
+                                       self.reader_library, self.rgba_layout_color), 'index': idx}
+        if not self.test_mode:
+            mask_path = os.path.join(self.data_folder, record[self.target_column])
+            mask = cv2.imread(str(mask_path), 0)
+            if mask is None:
+                raise ValueError(f'{mask_path} was not read correctly!')
+            sample['mask'] = mask
+        return self._apply(self.augment, sample)
+
+    def __getitem__(self, idx):
+        sample = super().__getitem__(idx)
+        if not self.test_mode:
+            sample['target'] = torch.as_tensor(sample.pop('mask')).type(getattr(torch, self.target_dtype))
+        return sample
+
+    def __len__(self):
+        return len(self.df)
+
+
+@DATASETS.register_class
+class SweetPepper(ImageSegmentationDataset):
+    """torchok/data/datasets/examples/sweet_pepper.py:12-91: `<data_folder>/sweet_pepper/{train,valid}.csv`."""
+    base_folder, train_csv, valid_csv = 'sweet_pepper', 'train.csv', 'valid.csv'
+
+    def __init__(self, train, download, data_folder, transform, augment=None, input_dtype='float32',
+                 target_dtype='int64', reader_library='opencv', image_format='rgb', rgba_layout_color=0,
+                 test_mode=False):
+        path = os.path.join(str(data_folder), self.base_folder)
+        if not os.path.isdir(path):
+            raise RuntimeError('Dataset not found or corrupted. You can use download=True to download it'
+                               f' [torchok_b200: no network on this box; expected {path}]')
+        super().__init__(path, self.train_csv if train else self.valid_csv, transform, augment, input_dtype=input_dtype,
+                         target_column='mask', target_dtype=target_dtype, reader_library=reader_library,
+                         image_format=image_format, rgba_layout_color=rgba_layout_color, test_mode=test_mode)
+
+
+@DATASETS.register_class
+class SOP(ImageDataset):
+    """Stanford Online Products, torchok/data/datasets/examples/sop.py:15-136: `Ebay_{train,test}.txt` (space separated,
+    columns class_id / path); targets are zero-based per split (train: class_id - 1, test: class_id - 11319)."""
+    base_folder, train_txt, test_txt = 'Stanford_Online_Products', 'Ebay_train.txt', 'Ebay_test.txt'
+
+    def __init__(self, train, download, data_folder, transform, augment=None, input_dtype='float32',
+                 reader_library='opencv', image_format='rgb', rgba_layout_color=0, test_mode=False):
+        super().__init__(transform, augment, input_dtype, reader_library, image_format, rgba_layout_color, test_mode)
+        self.path, self.train = os.path.join(str(data_folder), self.base_folder), train
+        if not os.path.isdir(self.path):
+            raise RuntimeError('Dataset not found or corrupted. You can use download=True to download it'
+                               f' [torchok_b200: no network on this box; expected {self.path}]')
+        self.csv = _read_table(self.path, self.train_txt if train else self.test_txt, sep=' ')
+        self.target_column, self.path_column = 'class_id', 'path'
+
+    def get_raw(self, idx):
+        record = self.csv.iloc[idx]
+        sample = {'image': _read_image(os.path.join(self.path, record[self.path_column]), self.image_format,
+                                       self.reader_library, self.rgba_layout_color), 'index': idx}
+        if not self.test_mode:
+            sample['target'] = record[self.target_column] - (1 if self.train else 11319)
+        return self._apply(self.augment, sample)
+
+    def __len__(self):
+        return len(self.csv)
+
+
+@TRANSFORMS.register_class
+class FancyPCA(_Transform):
+    """albumentations.FancyPCA (Krizhevsky et al. colour augmentation): add alpha_k * lambda_k * p_k summed over the
+    principal components of the image's own RGB covariance, alpha_k ~ N(0, alpha)."""
+
+    def __init__(self, alpha=0.1, always_apply=False, p=0.5):
+        super().__init__(always_apply, p)
+        self.alpha = alpha
+
+    def params(self, sample):
+        return {'a': np.random.normal(0.0, self.alpha, 3)}
+
+    def image(self, img, a=None):
+        if img.ndim != 3 or img.shape[2] != 3 or a is None:
+            return img
+        x = img.astype(np.float64).reshape(-1, 3) / 255.0
+        x = x - x.mean(0)
+        vals, vecs = np.linalg.eigh(np.cov(x, rowvar=False))
+        order = vals.argsort()[::-1]
+        vals, vecs = vals[order], vecs[:, order]
+        shift = (vecs @ (a * vals).reshape(3, 1)).reshape(1, 1, 3) * 255.0
+        return np.clip(img.astype(np.float64) + shift, 0, 255).astype(np.uint8)
+
+    def mask(self, m, **params):
+        return m
