@@ -771,3 +771,37 @@ def test_file_backed_example_datasets(tmp_path):
     assert out['image'].shape == img.shape and out['image'].dtype == np.uint8 and not np.array_equal(out['image'], img)
     assert np.array_equal(out['mask'], mask)
     assert 'ModelCheckpointWithOnnx' in tb.CALLBACKS
+
+
+REF_CONFIGS = '/root/reference/examples/configs'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONFIGS), reason='the reference checkout only exists in the build container')
+@pytest.mark.parametrize('name,task_cls', [('classification_cifar10', 'ClassificationTask'),
+                                           ('classification_cifar10_multi_validation', 'ClassificationTask'),
+                                           ('classification_imagenet', 'ClassificationTask'),
+                                           ('pairwise_sop', 'PairwiseLearnTask'),
+                                           ('segmentation_sweet_pepper', 'SegmentationTask')])
+def test_reference_example_configs_drop_in(name, task_cls, monkeypatch):
+    """The reference's own example YAMLs, unchanged: the file loads (anchors, ${oc.env:…}, ${now:…}), every name
+    resolves in the registry its position implies, the task assembles from `task.params`, and the metrics / callbacks /
+    scheduler blocks construct.  (Datasets are not instantiated: their files are not on this box.)"""
+    import importlib.util
+    monkeypatch.setenv('HOME', '/root')
+    spec = importlib.util.spec_from_file_location(
+        '_cov', os.path.join(os.path.dirname(__file__), '..', 'scripts', 'config_coverage.py'))
+    cov = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cov)
+    cfg = tb.load_config(os.path.join(REF_CONFIGS, name + '.yaml'))
+    missing = [(reg, n) for reg, n in cov.names_of(cfg) if n is not None and n not in getattr(tb, reg)]
+    assert not missing, missing
+    task = tb.TASKS.get(cfg.task.name)(cfg, **cfg.task.params)
+    assert type(task).__name__ == task_cls and sum(p.numel() for p in task.parameters()) > 1e6
+    MetricsManager(cfg.get('metrics') or [])
+    for c in cfg.get('callbacks') or []:
+        tb.CALLBACKS.get(c['name'])(**dict(c.get('params') or {}))
+    for o in cfg.optimization:
+        assert o.optimizer.name in tb.OPTIMIZERS
+        if o.get('scheduler'):
+            params = dict(o.scheduler.get('params') or {})
+            LrDriver(_FakeOpt(o.optimizer.params.lr), o.scheduler.name, params, o.scheduler.get('pl_params'))
