@@ -36,7 +36,10 @@ class PairwiseLearnTask(ClassificationTask):
 
     def calc_relevance_matrix(self, y):
         if y.ndim == 1:
-            if bool(((y < 0) | (y >= self.num_classes)).any()):
+            # the range check reads a device flag back (as F.one_hot does in the reference): not possible while the
+            # step is being captured into a CUDA graph — the eager warm-up steps before the capture have run it
+            capturing = y.is_cuda and torch.cuda.is_current_stream_capturing()
+            if not capturing and bool(((y < 0) | (y >= self.num_classes)).any()):
                 raise RuntimeError('calc_relevance_matrix: label outside [0, num_classes)')
             return (y[:, None] == y[None, :]).float()
         y = y.float()
