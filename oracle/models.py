@@ -612,3 +612,100 @@ class FPN(nn.Module):
                 for i in range(used + 1, self.num_outs):
                     outs.append(self.fpn_convs[i](F.relu(outs[-1]) if self.relu_before_extra_convs else outs[-1]))
         return tuple(outs)
+
+
+# ------------------------------------------------------------------------------------------- N4: OCR head, UNet neck
+# Restated ahead of the CUDA path (no kernels yet): pinned against the reference's own files executed by
+# path (tests/golden/make_reference_goldens.py), so that the kernels have a checked target when they are written.
+class OCRSegmentationHead(nn.Module):
+    """torchok/models/heads/segmentation/ocr.py:133-192 with SpatialGather_Module (:24-46), ObjectAttentionBlock
+    (:49-102) at scale 1 and SpatialOCR (:105-130).  State-dict keys follow the reference's module names."""
+
+    class _Attention(nn.Module):
+        def __init__(self, cin, key):
+            super().__init__()
+            self.key_channels = key
+            two = lambda a, b: nn.Sequential(ConvBnAct(a, b, 1), ConvBnAct(b, b, 1))  # noqa: E731
+            self.f_pixel, self.f_object, self.f_down = two(cin, key), two(cin, key), two(cin, key)
+            self.f_up = ConvBnAct(key, cin, 1)
+
+        def forward(self, x, proxy):
+            b, _, h, w = x.shape
+            query = self.f_pixel(x).view(b, self.key_channels, -1).permute(0, 2, 1)
+            key = self.f_object(proxy).view(b, self.key_channels, -1)
+            value = self.f_down(proxy).view(b, self.key_channels, -1).permute(0, 2, 1)
+            sim = q(F.softmax(q((self.key_channels ** -.5) * torch.matmul(query, key)), dim=-1))
+            ctx = q(torch.matmul(sim, value)).permute(0, 2, 1).contiguous().view(b, self.key_channels, h, w)
+            return self.f_up(ctx)
+
+    class _SpatialOCR(nn.Module):
+        def __init__(self, cin, key, cout, dropout):
+            super().__init__()
+            self.object_context_block = OCRSegmentationHead._Attention(cin, key)
+            self.conv_bn_dropout = nn.Sequential(ConvBnAct(2 * cin, cout, 1), nn.Dropout2d(dropout))
+
+        def forward(self, feats, proxy):
+            return self.conv_bn_dropout(torch.cat([self.object_context_block(feats, proxy), feats], 1))
+
+    def __init__(self, in_channels, num_classes, do_interpolate=True, ocr_mid_channels=128, ocr_key_channels=64):
+        super().__init__()
+        self.num_classes, self.do_interpolate = num_classes, do_interpolate
+        self.conv3x3_ocr = ConvBnAct(in_channels, ocr_mid_channels, 3, padding=1)
+        self.ocr_distri_head = OCRSegmentationHead._SpatialOCR(ocr_mid_channels, ocr_key_channels, ocr_mid_channels, 0.05)
+        self.last_reduction = ConvBnAct(ocr_mid_channels, ocr_mid_channels // 16, 1)
+        self.aux_head = nn.Sequential(ConvBnAct(in_channels, in_channels, 1), nn.Conv2d(in_channels, num_classes, 1))
+        self.classifier = nn.Conv2d(ocr_mid_channels // 16, num_classes, 1)
+
+    def forward(self, x):
+        image, feats = x
+        out_aux = conv(self.aux_head[1], self.aux_head[0](feats))
+        feats = self.conv3x3_ocr(feats)
+        b, k = out_aux.shape[:2]
+        probs = q(F.softmax(out_aux.view(b, k, -1), dim=2))                         # soft object regions, scale 1
+        context = q(torch.matmul(probs, feats.view(b, feats.size(1), -1).permute(0, 2, 1)))
+        context = context.permute(0, 2, 1).unsqueeze(3)                             # b x c x k x 1
+        out = conv(self.classifier, self.last_reduction(self.ocr_distri_head(feats, context)))
+        if self.do_interpolate:
+            out = q(F.interpolate(out, size=image.shape[2:], mode='bilinear', align_corners=False))
+            out_aux = q(F.interpolate(out_aux, size=image.shape[2:], mode='bilinear', align_corners=False))
+        if self.num_classes == 1:
+            out, out_aux = out[:, 0], out_aux[:, 0]
+        return (out, out_aux) if self.training else out
+
+
+class UnetNeck(nn.Module):
+    """torchok/models/necks/segmentation/unet.py:77-131 (use_attention=False): optional centre block, then decoder
+    blocks `nearest x2 -> cat(skip) -> ConvBnAct 3x3 -> ConvBnAct 3x3`, deepest feature first."""
+
+    class _Block(nn.Module):
+        def __init__(self, cin, skip, cout, use_batchnorm):
+            super().__init__()
+            self.conv1 = ConvBnAct(cin + skip, cout, 3, padding=1, use_batchnorm=use_batchnorm)
+            self.conv2 = ConvBnAct(cout, cout, 3, padding=1, use_batchnorm=use_batchnorm)
+
+        def forward(self, x, skip=None):
+            x = F.interpolate(x, scale_factor=2, mode='nearest')
+            if skip is not None:
+                if skip.size(2) != x.size(2):
+                    skip = F.interpolate(skip, size=x.shape[2:], mode='nearest')
+                x = torch.cat([x, skip], dim=1)
+            return self.conv2(self.conv1(x))
+
+    def __init__(self, in_channels, decoder_channels=(512, 256, 128, 64, 64), use_batchnorm=True, center=True):
+        super().__init__()
+        enc = list(in_channels)[::-1]
+        ins = [enc[0]] + list(decoder_channels[:-1])
+        skips = enc[1:] + [0] * (len(decoder_channels) - len(enc) + 1)
+        self.out_channels = decoder_channels[-1]
+        self.center = nn.Sequential(ConvBnAct(enc[0], enc[0], 3, padding=1, use_batchnorm=use_batchnorm),
+                                    ConvBnAct(enc[0], enc[0], 3, padding=1, use_batchnorm=use_batchnorm)) \
+            if center else nn.Identity()
+        self.blocks = nn.ModuleList(UnetNeck._Block(i, s, o, use_batchnorm)
+                                    for i, s, o in zip(ins, skips, decoder_channels))
+
+    def forward(self, features):
+        head, *skips, image = features[::-1]
+        x = self.center(head)
+        for i, blk in enumerate(self.blocks):
+            x = blk(x, skips[i] if i < len(skips) else None)
+        return [image, x]
