@@ -27,6 +27,28 @@ def running(m):
     return {k: v.detach().clone() for k, v in m.state_dict().items() if 'running_' in k}
 
 
+def seeded_state(module, seed):
+    """A full state dict that both the generator and the replaying test can rebuild from `seed` alone: conv / linear
+    weights ~ N(0, 1/sqrt(fan_in)) rounded to bf16, BatchNorm gamma ~ U(.5, 1.5), beta / running_mean ~ N(0, .1),
+    running_var ~ U(.5, 1.5), in state-dict key order."""
+    gen = torch.Generator().manual_seed(seed)
+    state = {}
+    for k, v in module.state_dict().items():
+        if k.endswith('num_batches_tracked'):
+            state[k] = v.clone()
+        elif k.endswith('running_var'):
+            state[k] = torch.rand(v.shape, generator=gen) + 0.5
+        elif k.endswith('running_mean'):
+            state[k] = torch.randn(v.shape, generator=gen) * 0.1
+        elif v.dim() > 1:
+            state[k] = bf(torch.randn(v.shape, generator=gen) / (v[0].numel() ** 0.5))
+        elif k.endswith('weight'):
+            state[k] = torch.rand(v.shape, generator=gen) + 0.5
+        else:
+            state[k] = torch.randn(v.shape, generator=gen) * 0.1
+    return state
+
+
 def main():
     install_stub_tree()
     pkg = types.ModuleType('torchok.models.modules.blocks')
@@ -89,6 +111,38 @@ def main():
                           feats=[f.detach() for f in feats], r=r, y=y.detach(), dfeats=[f.grad.clone() for f in feats[1:]],
                           grads=grads, state_after=running(m)))
     out['UnetNeck'] = cases
+    # ---- HRNetClassificationNeck (necks/classification/hrnet.py:12-85).  The file imports timm's Bottleneck; timm is not
+    # installed, so torchvision's independent Bottleneck (same constructor order, same v1.5 arithmetic, same state-dict
+    # keys) stands in for it — everything else (layer construction, the S7 overwrite quirk in forward) is the
+    # reference's code.  The 3.9 M parameters are not stored: both sides build them with `seeded_state`.
+    import torchvision
+    for name in ('timm', 'timm.models'):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+        sys.modules[name] = mod
+    tres = types.ModuleType('timm.models.resnet')
+    tres.Bottleneck = torchvision.models.resnet.Bottleneck
+    sys.modules['timm.models.resnet'] = tres
+    for name in ('torchok.models.necks.classification',):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+        sys.modules[name] = mod
+    hn = load('torchok.models.necks.classification.hrnet')
+    cases = []
+    for chans, sizes, train in [((18, 36, 72, 144), (8, 4, 2, 1), False), ((18, 36, 72, 144), (8, 4, 2, 1), True)]:
+        m = hn.HRNetClassificationNeck(list(chans))
+        m.load_state_dict(seeded_state(m, 77))
+        m.train(train)
+        feats = [bf(torch.randn(3, c, s, s, generator=g)).requires_grad_(True) for c, s in zip(chans, sizes)]
+        y = m(feats)
+        r = bf(torch.randn(y.shape, generator=g))
+        (y * r).sum().backward()
+        cases.append(dict(chans=chans, train=train, seed=77, feats=[f.detach() for f in feats], r=r, y=y.detach(),
+                          dfeats=[None if f.grad is None else f.grad.clone() for f in feats],
+                          grad_norms={n: float(p.grad.norm()) for n, p in m.named_parameters() if p.grad is not None},
+                          state_after=running(m) if train else {}))
+    out['HRNetClassificationNeck'] = cases
+
     torch.save(out, OUT)
     print(f'wrote {OUT}: ' + ', '.join(f'{k} x{len(v)}' for k, v in out.items()))
 

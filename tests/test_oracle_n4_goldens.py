@@ -62,3 +62,33 @@ def test_unet_neck(case):
     for f, d in zip(feats[1:], case['dfeats']):
         close(f.grad, d, atol=5e-5)
     check_params(m, case)
+
+
+@pytest.mark.parametrize('case', G['HRNetClassificationNeck'], ids=lambda c: f"train{int(c['train'])}")
+def test_hrnet_classification_neck(case):
+    """necks/classification/hrnet.py:12-85 executed by path with torchvision's independent Bottleneck standing in for
+    timm's (same constructor order, arithmetic and state-dict keys): layer construction, key names, the S7 overwrite
+    quirk (only the last branch reaches the output, so only its input receives a gradient), running statistics."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('_mk_n4', os.path.join(os.path.dirname(__file__), 'golden', 'make_n4_goldens.py'))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    m = om.HRNetClassificationNeck(list(case['chans']))
+    m.load_state_dict(mk.seeded_state(m, case['seed']))          # same keys and shapes as the reference's module
+    m.train(case['train'])
+    feats = [f.clone().requires_grad_(True) for f in case['feats']]
+    y = m(feats)
+    close(y, case['y'], rtol=1e-4, atol=1e-4)
+    (y * case['r']).sum().backward()
+    for f, d in zip(feats, case['dfeats']):
+        if d is None:
+            assert f.grad is None or float(f.grad.abs().max()) == 0.0
+        else:
+            close(f.grad, d, rtol=1e-4, atol=1e-4)
+    norms = {n: float(p.grad.norm()) for n, p in m.named_parameters() if p.grad is not None}
+    assert set(norms) == set(case['grad_norms'])
+    for n, v in case['grad_norms'].items():
+        assert norms[n] == pytest.approx(v, rel=2e-3, abs=1e-5), n
+    now = m.state_dict()
+    for k, v in case['state_after'].items():
+        close(now[k], v, rtol=1e-4, atol=1e-5)
