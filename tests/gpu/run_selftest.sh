@@ -20,6 +20,9 @@ echo "exit=$?" >> gpurun_out/selftest_pair_base.log; tail -n 12 gpurun_out/selft
 echo "===== group pair (TOK_CONV_2CTA=1)"
 TOK_CONV_2CTA=1 TOK_CONV_BN=256 timeout 120 tests/gpu/tok_selftest pair > gpurun_out/selftest_pair_2cta.log 2>&1
 echo "exit=$?" >> gpurun_out/selftest_pair_2cta.log; tail -n 12 gpurun_out/selftest_pair_2cta.log
+echo "===== perf A/B: 128x256 tiles vs CTA-pair 256x256 tiles (only shapes with M % 256 == 0, N % 256 == 0 differ)"
+TOK_CONV_BN=256 timeout 120 tests/gpu/tok_selftest perf > gpurun_out/selftest_perf_bn256.log 2>&1; tail -n 14 gpurun_out/selftest_perf_bn256.log
+TOK_CONV_2CTA=1 TOK_CONV_BN=256 timeout 120 tests/gpu/tok_selftest perf > gpurun_out/selftest_perf_2cta.log 2>&1; tail -n 14 gpurun_out/selftest_perf_2cta.log
 for g in ${@:-gemm conv dgrad wgrad stem elem perf}; do
   echo "===== group $g"
   timeout 120 tests/gpu/tok_selftest $g > gpurun_out/selftest_$g.log 2>&1
