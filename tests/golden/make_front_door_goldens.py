@@ -152,6 +152,10 @@ def main():
         def get(self, name):
             return {'MockSum': MockSum, 'MockDict': MockDict}[name]
     sys.modules['torchok.constructor'].METRICS = Table()
+    import dataclasses
+    out['config_structure'] = {name: [f.name for f in dataclasses.fields(obj)] for name, obj in vars(cs).items()
+                               if dataclasses.is_dataclass(obj)}
+    out['phases'] = [p.name for p in cs.Phase]
     mmod = load('torchok.metrics.metrics_manager')
     cases = []
     for spec in MANAGER_CASES:

@@ -86,3 +86,41 @@ def test_registry_matches_reference():
     got = mk.registry_scenario(Registry)
     want = G['Registry']
     assert got == want
+
+
+def test_config_schema_matches_reference_dataclasses(tmp_path):
+    """constructor/config.py::SCHEMA (what `validate_schema` enforces on YAML files) against the field names of the
+    reference's dataclasses (torchok/constructor/config_structure.py executed as is), and the error behaviour hydra's
+    structured merge has for unknown keys (tests/base_tests/constructor/test_config_structure_load.py:58-59: the
+    `bag` key under joint_loss raises KeyError)."""
+    from torchok_b200.constructor.config import PHASES, SCHEMA, load_config, validate_schema
+    ref = G['config_structure']
+    assert set(SCHEMA) == set(ref)
+    for cls, fields in ref.items():
+        assert list(SCHEMA[cls]) == fields or set(SCHEMA[cls]) == set(fields), cls
+    assert list(PHASES) == G['phases']
+    good = {'task': {'name': 'ClassificationTask', 'params': {'anything': {'goes': 1}}},
+            'joint_loss': {'losses': [{'name': 'CrossEntropyLoss', 'mapping': {'input': 'prediction'}}]},
+            'data': {'TRAIN': [{'dataset': {'name': 'X', 'params': {}, 'transform': []}, 'dataloader': {'whatever': 1}}]},
+            'trainer': {'max_epochs': 1}, 'hydra': {'run': {'dir': 'x'}}}
+    validate_schema(good)
+    for path, key, cls in [(('joint_loss',), 'bag', 'JointLossParams'), ((), 'log_dir', 'ConfigParams'),
+                           (('trainer',), 'gpus', 'TrainerParams'), (('task',), 'input_size', 'TaskParams'),
+                           (('joint_loss', 'losses', 0), 'wieght', 'LossParams')]:
+        import copy
+        bad = copy.deepcopy(good)
+        node = bad
+        for part in path:
+            node = node[part]
+        node[key] = 1
+        with pytest.raises(KeyError, match=f"Key '{key}' not in '{cls}'"):
+            validate_schema(bad)
+    with pytest.raises(KeyError, match='expected one of'):
+        validate_schema({'data': {'TRIAN': []}})
+    # files are validated, dicts built in code are not (unless asked to)
+    (tmp_path / 'bad.yaml').write_text('task: {name: X}\njoint_loss: {bag: big_bag, losses: []}\n')
+    with pytest.raises(KeyError, match="Key 'bag' not in 'JointLossParams'"):
+        load_config(str(tmp_path / 'bad.yaml'))
+    assert load_config({'task': {'name': 'X'}, 'joint_loss': {'bag': 1, 'losses': []}}).joint_loss.bag == 1
+    with pytest.raises(KeyError):
+        load_config({'task': {'name': 'X'}, 'bag': 1}, strict=True)

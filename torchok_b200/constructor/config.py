@@ -110,7 +110,76 @@ def apply_overrides(raw, overrides):
     return raw
 
 
-def load_config(path_or_dict, overrides=None):
+# Field names of the reference's structured schema (torchok/constructor/config_structure.py:14-196).  hydra merges every
+# config into `OmegaConf.structured(ConfigParams)` (torchok/__main__.py:27-31), so a key the schema does not know is an
+# error there (`ConfigKeyError`, a KeyError: "Key 'bag' not in 'JointLossParams'"); `validate_schema` reproduces that.
+# `Dict` / `Any` typed fields (params, mapping, dataloader, paramwise_cfg, ...) are free-form.  The table is compared
+# with the reference's dataclasses in tests/test_front_door_goldens.py.
+SCHEMA = {
+    'ConfigParams': {'task': 'TaskParams', 'data': 'data', 'trainer': 'TrainerParams', 'optimization': ['OptimizationParams'],
+                     'joint_loss': 'JointLossParams', 'logger': 'LoggerParams', 'metrics': ['MetricParams'],
+                     'callbacks': ['CallbacksParams'], 'resume_path': None, 'seed_params': 'SeedParams'},
+    'TaskParams': {'name': None, 'compute_loss_on_valid': None, 'params': None, 'load_checkpoint': 'LoadCheckpointParams'},
+    'LoadCheckpointParams': {'base_ckpt_path': None, 'overridden_name2ckpt_path': None, 'exclude_keys': None, 'strict': None},
+    'JointLossParams': {'losses': ['LossParams'], 'normalize_weights': None},
+    'LossParams': {'name': None, 'mapping': None, 'params': None, 'tag': None, 'weight': None},
+    'OptimizationParams': {'optimizer': 'OptmizerParams', 'scheduler': 'SchedulerParams'},
+    'OptmizerParams': {'name': None, 'params': None, 'paramwise_cfg': None},
+    'SchedulerParams': {'name': None, 'params': None, 'pl_params': 'SchedulerPLParams'},
+    'SchedulerPLParams': {'interval': None, 'frequency': None, 'monitor': None, 'strict': None, 'name': None},
+    'DataParams': {'dataset': 'DatasetParams', 'dataloader': None, 'sampler': 'SamplerParams'},
+    'DatasetParams': {'name': None, 'params': None, 'transform': ['AugmentationParams'], 'augment': ['AugmentationParams']},
+    'AugmentationParams': {'name': None, 'params': None},
+    'SamplerParams': {'name': None, 'params': None},
+    'MetricParams': {'name': None, 'mapping': None, 'params': None, 'phases': None, 'val_dataloader_idxs': None,
+                     'test_dataloader_idxs': None, 'tag': None},
+    'CallbacksParams': {'name': None, 'params': None},
+    'SeedParams': {'seed': None, 'workers': None},
+    'LoggerParams': {'name': None, 'log_dir': None, 'experiment_name': None, 'timestamp': None, 'params': None},
+    'TrainerParams': {k: None for k in (
+        'accelerator', 'strategy', 'devices', 'num_nodes', 'precision', 'fast_dev_run', 'max_epochs', 'min_epochs',
+        'max_steps', 'min_steps', 'max_time', 'limit_train_batches', 'limit_val_batches', 'limit_test_batches',
+        'limit_predict_batches', 'overfit_batches', 'val_check_interval', 'check_val_every_n_epoch',
+        'num_sanity_val_steps', 'log_every_n_steps', 'enable_checkpointing', 'enable_progress_bar',
+        'enable_model_summary', 'accumulate_grad_batches', 'gradient_clip_val', 'gradient_clip_algorithm',
+        'deterministic', 'benchmark', 'inference_mode', 'use_distributed_sampler', 'profiler', 'detect_anomaly',
+        'barebones', 'sync_batchnorm', 'reload_dataloaders_every_n_epochs')},
+}
+PHASES = ('TRAIN', 'VALID', 'TEST', 'PREDICT')
+_HYDRA_KEYS = ('hydra', 'defaults', 'mode')      # consumed by hydra / __main__ before the schema merge
+
+
+def validate_schema(raw):
+    """Raise KeyError for keys the reference's structured config would reject."""
+    def check(node, cls):
+        if node is None:
+            return
+        if cls == 'data':
+            for phase, entries in node.items():
+                if phase not in PHASES:
+                    raise KeyError(f"Invalid value '{phase}', expected one of [{', '.join(PHASES)}]")
+                for entry in entries or []:
+                    check(entry, 'DataParams')
+            return
+        if not isinstance(node, dict):
+            raise TypeError(f'{cls}: expected a mapping, got {type(node).__name__}')
+        fields = SCHEMA[cls]
+        for key, value in node.items():
+            if cls == 'ConfigParams' and key in _HYDRA_KEYS:
+                continue
+            if key not in fields:
+                raise KeyError(f"Key '{key}' not in '{cls}'")
+            sub = fields[key]
+            if isinstance(sub, list):
+                for item in value or []:
+                    check(item, sub[0])
+            elif sub is not None:
+                check(value, sub)
+    check(raw, 'ConfigParams')
+
+
+def load_config(path_or_dict, overrides=None, strict=None):
+    """`strict` (default: True for files, False for dicts built in code) applies `validate_schema`."""
     if isinstance(path_or_dict, (str, os.PathLike)):
         with open(path_or_dict) as f:
             raw = yaml.safe_load(f)
@@ -118,6 +187,8 @@ def load_config(path_or_dict, overrides=None):
         raw = Config.wrap(path_or_dict).to_dict()
     raw = apply_overrides(raw, overrides)
     raw = _resolve(raw, raw, datetime.now())
+    if strict if strict is not None else isinstance(path_or_dict, (str, os.PathLike)):
+        validate_schema(raw)
     for k, v in _TOP_DEFAULTS.items():
         raw.setdefault(k, v)
     if isinstance(raw.get('task'), dict):
