@@ -496,6 +496,9 @@ def test_runner_limits_max_steps_test_and_predict(tmp_path):
     bad['data']['VALID'][0]['dataloader']['drop_last'] = True
     with pytest.raises(ValueError, match='drop_last'):
         Runner(bad, loop_factory=_CpuLoop).fit()
+    for key, value in (('accumulate_grad_batches', 4), ('gradient_clip_val', 1.0), ('sync_batchnorm', True)):
+        with pytest.raises(NotImplementedError, match=key):
+            Runner(_runner_cfg(tmp_path / key, trainer={'max_epochs': 1, key: value}), loop_factory=_CpuLoop)
     two = _runner_cfg(tmp_path / 'two')
     two['optimization'] = two['optimization'] * 2
     with pytest.raises(NotImplementedError):

@@ -12,7 +12,9 @@ with the host-side pieces Lightning provided restated around it: `task.load_chec
 (model + optimizer + scheduler + callbacks + epoch), per-epoch validation with `MetricsManager`, lr schedulers
 (optim.LrDriver), callbacks (callbacks.FreezeUnfreeze / ModelCheckpoint / EarlyStopping), CSV (+ TensorBoard when the
 config names it) logging, `limit_*_batches`, `max_epochs` / `max_steps`, `check_val_every_n_epoch`,
-`num_sanity_val_steps` (ignored), `log_every_n_steps`.  Trainer keys about devices / precision / strategy are accepted:
+`num_sanity_val_steps` (ignored), `log_every_n_steps`.  `accumulate_grad_batches`, `gradient_clip_val`, `sync_batchnorm`
+and `overfit_batches` raise NotImplementedError when set to a non-neutral value.  Trainer keys about devices /
+precision / strategy are accepted:
 the device is `cuda:LOCAL_RANK`, compute is bf16 with fp32 masters, and data parallelism follows torch.distributed's
 environment (one process per GPU, launched by torchrun) — not the trainer block.
 
@@ -107,6 +109,13 @@ class Runner:
         self.cfg = config if isinstance(config, Config) and not overrides else load_config(config, overrides)
         cfg = self.cfg
         self.trainer = Config.wrap(dict(cfg.get('trainer') or {}))
+        # trainer keys that would change the arithmetic of a step are refused rather than silently ignored
+        for key, neutral in (('accumulate_grad_batches', (None, 1)), ('gradient_clip_val', (None, 0, 0.0)),
+                             ('sync_batchnorm', (None, False)), ('overfit_batches', (None, 0, 0.0))):
+            if self.trainer.get(key) not in neutral:
+                raise NotImplementedError(f'trainer.{key}={self.trainer.get(key)!r}: not built in the stream loop '
+                                          f'(one optimizer step per batch, unclipped gradients, per-GPU BatchNorm '
+                                          f'statistics)')
         seed_everything(**dict(cfg.get('seed_params') or {}))
         self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
