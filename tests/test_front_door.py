@@ -505,6 +505,24 @@ def test_runner_limits_max_steps_test_and_predict(tmp_path):
         Runner(two, loop_factory=_CpuLoop).fit()
 
 
+def test_runner_two_validation_loaders(tmp_path):
+    """classification_cifar10_multi_validation.yaml layout: two VALID loaders, one metric per loader
+    (`val_dataloader_idxs`), Lightning's `/dataloader_idx_i` suffix on the per-loader losses."""
+    cfg = _runner_cfg(tmp_path, trainer={'max_epochs': 1})
+    cfg['callbacks'] = []
+    cfg['data']['VALID'] = cfg['data']['VALID'] + [dict(cfg['data']['VALID'][0])]
+    acc = dict(cfg['metrics'][0], phases=['VALID'])
+    cfg['metrics'] = [dict(acc, val_dataloader_idxs=[0]), dict(acc, tag='acc_second', val_dataloader_idxs=[1]),
+                      dict(acc, tag='acc_both', val_dataloader_idxs=[0, 1])]
+    logs = Runner(cfg, loop_factory=_CpuLoop).fit()
+    for key in ('valid/loss/dataloader_idx_0', 'valid/loss/dataloader_idx_1', 'valid/Accuracy', 'valid/acc_second',
+                'valid/acc_both_dataloader_0', 'valid/acc_both_dataloader_1'):
+        assert key in logs, (key, sorted(logs))
+    assert 'valid/loss' not in logs
+    assert logs['valid/Accuracy'] == logs['valid/acc_second'] == logs['valid/acc_both_dataloader_1']   # same data twice
+    assert logs['valid/loss/dataloader_idx_0'] == pytest.approx(logs['valid/loss/dataloader_idx_1'])
+
+
 def test_model_checkpoint_top_k(tmp_path):
     class R:
         output_dir, current_epoch, global_step, has_validation = str(tmp_path), 0, 0, True

@@ -221,9 +221,10 @@ class Runner:
     def _evaluate(self, phase, loaders, limit):
         """validation_step / test_step over every loader: metrics + (VALID only) mean loss; tasks/base.py:135-161."""
         self.task.eval()
-        sums, count = {}, 0
+        logs = {}
         with torch.no_grad():
             for dl_idx, loader in enumerate(loaders):
+                sums, count = {}, 0
                 n = _limit(len(loader), limit)
                 for i, batch in enumerate(loader):
                     if i >= n:
@@ -237,7 +238,10 @@ class Runner:
                     else:
                         output = self.task.forward_with_gt(batch)
                     self.metrics_manager.update(phase, dl_idx, **output)
-        logs = {f'{phase.value}/{k}': self._mean_over_ranks(v / max(count, 1)) for k, v in sums.items()}
+                # with several loaders Lightning suffixes every logged key with its dataloader index
+                suffix = f'/dataloader_idx_{dl_idx}' if len(loaders) > 1 else ''
+                for k, v in sums.items():
+                    logs[f'{phase.value}/{k}{suffix}'] = self._mean_over_ranks(v / max(count, 1))
         logs.update(self.metrics_manager.on_epoch_end(phase))
         return logs
 
