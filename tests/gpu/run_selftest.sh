@@ -23,6 +23,10 @@ echo "exit=$?" >> gpurun_out/selftest_pair_2cta.log; tail -n 12 gpurun_out/selft
 echo "===== perf A/B: 128x256 tiles vs CTA-pair 256x256 tiles (only shapes with M % 256 == 0, N % 256 == 0 differ)"
 TOK_CONV_BN=256 timeout 120 tests/gpu/tok_selftest perf > gpurun_out/selftest_perf_bn256.log 2>&1; tail -n 14 gpurun_out/selftest_perf_bn256.log
 TOK_CONV_2CTA=1 TOK_CONV_BN=256 timeout 120 tests/gpu/tok_selftest perf > gpurun_out/selftest_perf_2cta.log 2>&1; tail -n 14 gpurun_out/selftest_perf_2cta.log
+echo "===== retrieval search: CTA-pair kernel (TOK_TOPK_2CTA=1) parity (bit-exact neighbour indices) and A/B at N = 262144"
+TOK_TOPK_2CTA=1 timeout 300 python -m pytest tests/test_retrieval_meter.py -m gpu -q -x > gpurun_out/retrieval_pair_tests.log 2>&1; tail -n 3 gpurun_out/retrieval_pair_tests.log
+timeout 120 python scripts/bench_extra.py retrieval 262144 512 1 > gpurun_out/retrieval_ab_base.log 2>&1; tail -n 1 gpurun_out/retrieval_ab_base.log
+TOK_TOPK_2CTA=1 timeout 120 python scripts/bench_extra.py retrieval 262144 512 1 > gpurun_out/retrieval_ab_pair.log 2>&1; tail -n 1 gpurun_out/retrieval_ab_pair.log
 for g in ${@:-gemm conv dgrad wgrad stem elem perf}; do
   echo "===== group $g"
   timeout 120 tests/gpu/tok_selftest $g > gpurun_out/selftest_$g.log 2>&1

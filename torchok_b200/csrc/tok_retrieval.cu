@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/tokb200.h"
 #include "tok_internal.h"
@@ -274,6 +275,10 @@ cudaError_t launch_topk(const CUtensorMap& tmQ, const CUtensorMap& tmG, int nq, 
 }
 
 }  // namespace
+
+// tok_retrieval2.cu: CTA-pair (cta_group::2) variant, opt-in through TOK_TOPK_2CTA=1 (not yet run on hardware)
+cudaError_t launch_topk_pair(int kp, const CUtensorMap& tmQ, const CUtensorMap& tmG, int nq, int ng, int d,
+                             const float* g_sqnorm, float* cand_score, int* cand_idx, cudaStream_t st);
 }  // namespace tok
 
 using namespace tok;
@@ -305,7 +310,9 @@ int tok_topk_candidates(int nq, int ng, int d, int kp, const void* q_bf16, const
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (kp == 8) e = launch_topk<8>(tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
+  static const bool pair = getenv("TOK_TOPK_2CTA") != nullptr;
+  if (pair) e = launch_topk_pair(kp, tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
+  else if (kp == 8) e = launch_topk<8>(tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
   else if (kp == 16) e = launch_topk<16>(tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
   else e = launch_topk<32>(tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
   if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "topk_candidates launch: %s", cudaGetErrorString(e));
