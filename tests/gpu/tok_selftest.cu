@@ -684,6 +684,9 @@ int main(int argc, char** argv) {
     test_dgrad(Conv{148, 16, 16, 256, 64, 1, 1, 1, 0, 1}, true);    // MN-major B with 128x256 tiles + addend
     test_dgrad(Conv{37, 16, 16, 256, 64, 3, 3, 1, 1, 1}, false);
   }
+  if (grp == "pair1") {   // the smallest pair-kernel case alone (a few seconds including the CPU reference)
+    test_fprop(Conv{4, 16, 16, 256, 256, 3, 3, 1, 1, 1}, false);
+  }
   if (grp == "pair") {
     // shapes that satisfy the CTA-pair kernel's preconditions (M % 256 == 0, N % 256 == 0, 128x256 tile chosen);
     // run with TOK_CONV_2CTA=1 TOK_CONV_BN=256 to route them through tok_conv2.cu, without to get the baseline
