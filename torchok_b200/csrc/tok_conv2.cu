@@ -1,7 +1,9 @@
 // tok_conv2.cu — CTA-pair (cta_group::2) variant of the persistent implicit-GEMM convolution, OPT-IN (TOK_CONV_2CTA=1).
 //
-// Status: compiles for sm_100a; the pair mechanism itself is verified on a B200 by tests/gpu/gemm2cta_probe.cu, this
-// kernel has NOT been run yet (the round's GPU budget was spent) and is therefore not on the default path.
+// Status: first hardware run correct — `TOK_CONV_2CTA=1 TOK_CONV_BN=256 tests/gpu/tok_selftest pair1` (fprop 3x3
+// 256->256 on 4x16x16, output and both BatchNorm column statistics against the CPU reference,
+// profiles/r1_selftest_pair1_2cta.log).  The other shapes of the `pair` group (dgrad / MN-major B, addend, stride 2,
+// N = 512, many tiles per pair) and its timing are still to be run, so it stays off the default path.
 //
 // Why: with one SM per 128x256 tile a k-block moves 96 KB through that SM's shared memory per 512 tensor
 // clocks (48 KB in by TMA, 48 KB read by the four UMMAs) — ~187 B/clk against ~128 B/clk, a ~68 % ceiling on the tensor
