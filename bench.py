@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """bench.py — images/sec/GPU, forward+backward(+optimizer step), ResNet-50 224x224 bs256 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload W]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-One "step" = one pass of the hot path over one synthetic batch: ClassificationTask(resnet50 -> Pooling ->
-ClassificationHead(1000)).forward_with_gt -> JointLoss(CrossEntropyLoss) -> backward -> (bucketed NCCL all-reduce) ->
-SGD(momentum 0.9, wd 1e-4) step, the step the reference's Lightning loop runs for
-examples/configs/classification_imagenet.yaml (torchok/tasks/base.py:125-133).  Synthetic N(0,1) images, random
-labels, random-init weights (seed 42).
+One "step" = one pass of the hot path over one synthetic batch: Task.forward_with_gt -> JointLoss -> backward ->
+(gradient exchange over NVLink) -> optimizer step, the step the reference's Lightning loop runs
+(torchok/tasks/base.py:125-133).  Synthetic N(0,1) images, random labels, random-init weights (seed 42).
+
+Workloads (`--workload`, default resnet50 = the BASELINE.json metric; the others are BASELINE.json's other configs):
+    resnet50        C2  ResNet-50 ClassificationTask 3x224x224 bs256, SGD momentum   (classification_imagenet.yaml)
+    resnet18_cifar  C1  ResNet-18 ClassificationTask 3x32x32 bs128, Adam             (classification_cifar10.yaml)
+    swin_t          C3  Swin-T (V2, swinv2_custom img 224 window 7) bs256, AdamW
+    hrnet_seg       C4  HRNet-W18 + HRNetSegmentationNeck + SegmentationHead 3x512x512 bs32, SGD
+    retrieval       C5  IndexBasedMeter search: N x N cosine top-2, N = 1 M x 512 (query rows sharded over the ranks)
 
 Output: ONE JSON line on rank 0 (see the driver contract).  `value` = device-resident inputs, whole-job img/s;
 `e2e` = same loop fed from pinned HOST buffers through the public API (H2D of every batch and D2H of every loss inside
-the timed region); `roofline` = the dominant kernel (tcgen05 implicit-GEMM conv) timed live with CUDA events;
-`cpu_baseline` = the CPU oracle (oracle/models.py, the torch.nn graph the reference dispatches) on the host cores.
-`--impl reference` times that CPU path alone on the same config/metric.
+the timed region); `roofline` = the kernel FAMILY that takes the largest share of the step, every launch of one step
+timed live with CUDA events on the launching stream and set against max(tensor floor, HBM floor) of its algorithmic
+FLOPs / bytes (time-weighted fraction), with the per-family table beside it; `roofline_step` = whole-step FLOPs / time;
+`cpu_baseline` = the CPU oracle (oracle/models.py, the torch.nn graph the reference dispatches) on the host cores;
+`gpu_torch_baseline` = the same torch.nn graph on this GPU through cuDNN / cuBLAS (bf16 autocast, channels_last) — the
+library path SURVEY 2.3 names as the one to beat.  `--impl reference` times the CPU path alone on the same config/metric.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -33,22 +42,48 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = 'images/sec/GPU fwd+bwd ResNet-50 224² bs256; 1/2/4/8 GPU scaling'
 UNIT = 'img/s'
-FLOP_PER_IMG = 24.30e9  # fwd 8.178 + bwd (no dgrad of the first conv), FlopCounterMode, 2*MAC
-NUM_CLASSES = 1000
+CE = {'losses': [{'name': 'CrossEntropyLoss', 'mapping': {'input': 'prediction', 'target': 'target'}}]}
 
 
-def task_config(model='resnet50'):
-    """The task/loss/optimizer blocks of examples/configs/classification_imagenet.yaml with backbone resnet50."""
-    return {
-        'task': {'name': 'ClassificationTask', 'params': {
-            'backbone_name': model, 'backbone_params': {'pretrained': False, 'in_channels': 3},
-            'pooling_name': 'Pooling', 'head_name': 'ClassificationHead',
-            'head_params': {'num_classes': NUM_CLASSES}}},
-        'joint_loss': {'losses': [{'name': 'CrossEntropyLoss',
-                                   'mapping': {'input': 'prediction', 'target': 'target'}}]},
-        'optimization': [{'optimizer': {'name': 'SGD',
-                                        'params': {'lr': 0.1, 'weight_decay': 0.0001, 'momentum': 0.9}}}],
-    }
+def _cls(backbone, classes, opt, **bp):
+    params = {'pretrained': False}
+    params.update(bp)
+    return {'task': {'name': 'ClassificationTask', 'params': {
+        'backbone_name': backbone, 'backbone_params': params, 'pooling_name': 'Pooling',
+        'head_name': 'ClassificationHead', 'head_params': {'num_classes': classes}}},
+        'joint_loss': CE, 'optimization': [{'optimizer': opt}]}
+
+
+# flop_per_img: SURVEY 8(d) (FlopCounterMode on the oracle, fwd + bwd without the dgrad of the first conv, 2*MAC)
+WORKLOADS = {
+    'resnet50': dict(
+        cfg=_cls('resnet50', 1000, {'name': 'SGD', 'params': {'lr': 0.1, 'weight_decay': 0.0001, 'momentum': 0.9}},
+                 in_channels=3),
+        batch=256, size=224, classes=1000, flop_per_img=24.30e9, metric=METRIC,
+        name='ResNet-50 ClassificationTask synthetic 3x224x224 bs256/GPU bf16 (fp32 master weights, fp32 BN '
+             'statistics), SGD momentum step included', oracle=('resnet50', 2048)),
+    'resnet18_cifar': dict(
+        cfg=_cls('resnet18', 10, {'name': 'Adam', 'params': {'lr': 0.0001}}, in_channels=3),
+        batch=128, size=32, classes=10, flop_per_img=0.2173e9,
+        metric='images/sec fwd+bwd ResNet-18 32² bs128 (classification_cifar10.yaml); 1/2/4/8 GPU scaling',
+        name='ResNet-18 ClassificationTask synthetic 3x32x32 bs128/GPU bf16, Adam step included (C1)',
+        oracle=('resnet18', 512)),
+    'swin_t': dict(
+        cfg=_cls('swinv2_custom', 1000, {'name': 'AdamW', 'params': {'lr': 1e-4, 'weight_decay': 0.05}},
+                 img_size=224, window_size=7),
+        batch=256, size=224, classes=1000, flop_per_img=26.95e9,
+        metric='images/sec fwd+bwd Swin-T(V2) 224² window 7 bs256; 1/2/4/8 GPU scaling',
+        name='Swin-T (V2) ClassificationTask synthetic 3x224x224 bs256/GPU bf16, AdamW step included (C3)', oracle=None),
+    'hrnet_seg': dict(
+        cfg={'task': {'name': 'SegmentationTask', 'params': {
+            'backbone_name': 'hrnet_w18', 'backbone_params': {'pretrained': False, 'in_channels': 3},
+            'neck_name': 'HRNetSegmentationNeck', 'head_name': 'SegmentationHead', 'head_params': {'num_classes': 19}}},
+            'joint_loss': CE, 'optimization': [{'optimizer': {'name': 'SGD', 'params': {'lr': 0.01, 'momentum': 0.9}}}]},
+        batch=32, size=512, classes=19, seg=True, flop_per_img=None,
+        metric='images/sec fwd+bwd HRNet-W18 + seg neck/head 512² bs32; 1/2/4/8 GPU scaling',
+        name='HRNet-W18 + HRNetSegmentationNeck + SegmentationHead synthetic 3x512x512 bs32/GPU bf16, SGD step (C4)',
+        oracle=None),
+}
 
 
 def peaks():
@@ -99,16 +134,25 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference(batch, steps, warmup, model='resnet50', size=224):
-    """The reference's CPU path restated (oracle): same graph, fp32, all host threads (BASELINE.md §4)."""
+def _oracle_net(wl):
     from oracle import models as om
+    name, width = wl['oracle']
+    return om.ClassificationTask(om.resnet(name), om.Pooling(width), om.ClassificationHead(width, wl['classes']))
+
+
+def _torch_optimizer(wl, params, **kw):
+    o = wl['cfg']['optimization'][0]['optimizer']
+    return getattr(torch.optim, o['name'])(params, **o['params'], **kw)
+
+
+def cpu_reference(wl, batch, steps, warmup):
+    """The reference's CPU path restated (oracle): same graph, fp32, all host threads (BASELINE.md 4)."""
     torch.manual_seed(42)
     torch.set_float32_matmul_precision('highest')  # torchok/__main__.py:36
-    net = om.ClassificationTask(om.resnet(model), om.Pooling(2048 if model == 'resnet50' else 512),
-                                om.ClassificationHead(2048 if model == 'resnet50' else 512, NUM_CLASSES))
-    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
-    x = torch.randn(batch, 3, size, size)
-    y = torch.randint(0, NUM_CLASSES, (batch,))
+    net = _oracle_net(wl)
+    opt = _torch_optimizer(wl, net.parameters())
+    x = torch.randn(batch, 3, wl['size'], wl['size'])
+    y = torch.randint(0, wl['classes'], (batch,))
     crit = torch.nn.CrossEntropyLoss()
     times = []
     for i in range(warmup + steps):
@@ -123,65 +167,262 @@ def cpu_reference(batch, steps, warmup, model='resnet50', size=224):
     return batch * len(times) / total, total / len(times) * 1e3
 
 
+def gpu_torch_baseline(wl, batch, steps=10, warmup=5):
+    """The oracle's torch.nn graph on THIS GPU: channels_last, bf16 autocast, torch.optim (fused) — i.e. cuDNN / cuBLAS,
+    the library path the product has to beat.  Not the product path; reported for comparison only."""
+    import torch.nn as nn
+    torch.manual_seed(42)
+    dev = torch.device('cuda')
+    net = _oracle_net(wl).to(dev).to(memory_format=torch.channels_last)
+    opt = _torch_optimizer(wl, net.parameters(), fused=True)
+    x = torch.randn(batch, 3, wl['size'], wl['size'], device=dev).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, wl['classes'], (batch,), device=dev)
+
+    class Plain(nn.Module):        # the oracle's precision-policy wrappers are identities outside amp_bf16(): plain torch.nn
+        def __init__(self, t):
+            super().__init__()
+            self.t = t
+
+        def forward(self, x, y):
+            return nn.functional.cross_entropy(self.t.forward_with_gt({'image': x, 'target': y})['prediction'], y)
+    model = Plain(net)
+    torch.backends.cudnn.benchmark = True
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            loss = model(x, y)
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    # CUDA-graph the torch step too, so the comparison is not about Python launch overhead
+    graphed = True
+    try:
+        g = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=False)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream().wait_stream(s)
+
+        def gstep():
+            opt.zero_grad(set_to_none=False)
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                loss = model(x, y)
+            loss.backward()
+            opt.step()
+        with torch.cuda.graph(g):
+            gstep()
+        run = g.replay
+    except Exception as e:   # capture can fail on some optimizer paths: fall back to the eager loop and say so
+        graphed = False
+        run = step
+        print(f'[bench] torch baseline graph capture failed ({type(e).__name__}); eager loop', file=sys.stderr)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del net, opt, model
+    torch.cuda.empty_cache()
+    return {'value': batch / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'cuda_graph': graphed,
+            'how': f'oracle torch.nn graph .cuda(), channels_last, bf16 autocast, torch.optim fused, bs{batch}, '
+                   f'cudnn.benchmark, torch {torch.__version__} / cuDNN {torch.backends.cudnn.version()}'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload]
+    if wl['oracle'] is None:
+        print(json.dumps({'impl': 'reference', 'unavailable': f'no CPU arm for workload {args.workload}'}), flush=True)
+        return
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    batch = args.cpu_batch
+    batch = min(args.cpu_batch, wl['batch'])
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 1))
-    ips, ms = cpu_reference(batch, steps, warm)
+    ips, ms = cpu_reference(wl, batch, steps, warm)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'impl': 'reference', 'metric': wl['metric'], 'value': ips, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'ResNet-50 ClassificationTask synthetic 3x224x224, CPU sample at bs{batch} '
-                               f'(img/s normalised; reference CPU path = oracle restatement of the torch.nn graph)'},
+        'config': {'workload': f'{wl["name"]} — CPU sample at bs{batch} (img/s normalised; reference CPU path = oracle '
+                               f'restatement of the torch.nn graph)'},
         'cpu_baseline': {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': f'{steps} fwd+bwd+SGD steps at bs{batch} fp32, torch {torch.__version__} CPU'},
+                         'sample': f'{steps} fwd+bwd+optimizer steps at bs{batch} fp32, torch {torch.__version__} CPU'},
         'e2e': {'value': ips, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# ---------------------------------------------------------------------------------------------------- GPU arm
-def time_dominant_kernel(batch, sustained_tf):
-    """roofline: the tcgen05 implicit-GEMM conv on ResNet-50's heaviest layer shape (3x3 256->256 @14x14, 5 layers,
-    1.156 GFLOP/img fwd — SURVEY §8a census), timed alone with CUDA events on the launching stream."""
-    from torchok_b200 import kernels as K
-    dev = torch.device('cuda')
-    n, h, c, k = batch, 14, 256, 256
-    d, p, q = K.conv_desc(n, h, h, c, k, 3, 3, 1, 1, 1)
-    x = torch.randn(n, h, h, c, device=dev).to(torch.bfloat16)
-    w = torch.randn(k, 3, 3, c, device=dev).to(torch.bfloat16)
-    y = torch.empty(n, p, q, k, device=dev, dtype=torch.bfloat16)
-    stats = torch.zeros(2, k, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    st = torch.cuda.current_stream()
-    for _ in range(3):
-        K.conv_fprop(d, x, w, y, stats)
-    reps, total = 20, 0.0
-    for _ in range(reps):
-        flush.zero_()  # L2 flush between timed launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(st)
-        K.conv_fprop(d, x, w, y, stats)
-        e1.record(st)
-        e1.synchronize()
-        total += e0.elapsed_time(e1)
-    ms = total / reps
-    flops = 2.0 * n * p * q * k * 9 * c
-    ach = flops / (ms * 1e-3) / 1e12
-    return {'bound': 'tensor', 'achieved': ach, 'peak': sustained_tf, 'unit': 'TFLOP/s', 'frac': ach / sustained_tf,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from profiles/r1_roofline_kernel_full.md
-            # (ncu --set full, scripts/roofline_kernel.py): 26.94 MB read + 0.11 MB written — the 25.7 MB output tile
-            # stream stays in the 126 MB L2; algorithmic bytes are 25.7 (x) + 25.7 (y) + 1.2 (w) MB.
-            'traffic': 27.05e6 if n == 256 else None, 'traffic_unit': 'B',
-            'kernel': 'conv_fwd_persist_kernel<256,3,0,1,0> fprop 3x3 256->256 @14x14',
-            'ms_per_launch': ms, 'flop_per_launch': flops}
+# ---------------------------------------------------------------------------------------------------- roofline
+class CallTimer:
+    """CUDA events around every kernel-launching C-ABI call of one eager step (torchok_b200._lib tracer hook)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def before(self, name, a):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+        return (name, a, e0)
+
+    def after(self, tok):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream())
+        self.calls.append(tok + (e1,))
+
+
+def _desc(a):
+    d = a._obj
+    p = (d.h + 2 * d.pad - d.dil * (d.r - 1) - 1) // d.stride + 1
+    q = (d.w + 2 * d.pad - d.dil * (d.s - 1) - 1) // d.stride + 1
+    return d, p, q
+
+
+def _call_work(name, a):
+    """(family, algorithmic FLOPs, algorithmic HBM bytes) of one C-ABI call; None when the call is not modelled.
+    Bytes = every operand read once and every result written once (DESIGN 4's per-unit figures x units of the launch)."""
+    v = lambda x: x is not None and x != 0   # noqa: E731  (nullable pointer argument given?)
+    if name in ('tok_conv_fprop', 'tok_conv_fprop_bn'):
+        d, p, q = _desc(a[0])
+        m = d.n * p * q
+        x_elems = m * d.c if (d.r == 1 and d.s == 1) else d.n * d.h * d.w * d.c
+        add = m * d.k if (name == 'tok_conv_fprop' and v(a[6])) else 0
+        return 'conv fprop', 2.0 * m * d.k * d.r * d.s * d.c, 2.0 * (x_elems + m * d.k + d.k * d.r * d.s * d.c + add)
+    if name == 'tok_conv_dgrad':
+        d, p, q = _desc(a[0])
+        m = d.n * p * q
+        dx = d.n * d.h * d.w * d.c
+        return 'conv dgrad', 2.0 * m * d.k * d.r * d.s * d.c, \
+            2.0 * (m * d.k + dx * (2 if v(a[4]) else 1) + d.k * d.r * d.s * d.c)
+    if name == 'tok_conv_wgrad':
+        d, p, q = _desc(a[0])
+        m = d.n * p * q
+        x_elems = m * d.c if (d.r == 1 and d.s == 1) else d.n * d.h * d.w * d.c
+        return 'conv wgrad', 2.0 * m * d.k * d.r * d.s * d.c, 2.0 * (x_elems + m * d.k) + 4.0 * d.k * d.r * d.s * d.c
+    if name in ('tok_linear_fwd', 'tok_linear_dgrad', 'tok_linear_dgrad_add', 'tok_linear_wgrad'):
+        m, n, k = a[0], a[1], a[2]
+        extra = m * k if name == 'tok_linear_dgrad_add' else 0
+        fam = {'tok_linear_fwd': 'linear fwd', 'tok_linear_wgrad': 'linear wgrad'}.get(name, 'linear dgrad')
+        return fam, 2.0 * m * n * k, 2.0 * (m * k + m * n + n * k + extra)
+    if name == 'tok_stem_conv_fprop' or name == 'tok_stem_conv_wgrad':
+        n, h, w, k = a[0], a[1], a[2], a[3]
+        p, q = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        return 'stem conv', 2.0 * n * p * q * k * 147, 2.0 * (n * (p + 3) * (q + 3) * 16 + n * p * q * k)
+    if name == 'tok_bn_apply':
+        rows, c = a[0], a[1]
+        return 'bn fwd apply', 0.0, 2.0 * rows * c * (3 if v(a[5]) else 2)
+    if name == 'tok_bn_apply_bits':
+        rows, c = a[0], a[1]
+        return 'bn fwd apply', 0.0, 2.0 * rows * c * 3 + rows * c / 8
+    if name in ('tok_bn_bwd_reduce2', 'tok_bn_bwd_reduce2_finalize'):
+        rows, c = a[0], a[1]
+        return 'bn bwd reduce', 0.0, 2.0 * rows * c * (3 if v(a[3]) else 2) + (rows * c / 8 if v(a[6]) else 0)
+    if name == 'tok_bn_bwd_apply2':
+        rows, c = a[0], a[1]
+        return 'bn bwd apply', 0.0, 2.0 * rows * c * ((3 if v(a[3]) else 2) + 1 + (1 if v(a[13]) else 0)) + \
+            (rows * c / 8 if v(a[6]) else 0)
+    if name in ('tok_layernorm_fwd', 'tok_layernorm_bwd'):
+        return 'layernorm', 0.0, 6.0 * a[0] * a[1]
+    if name == 'tok_gelu_fwd':
+        return 'gelu', 0.0, 4.0 * a[0]
+    if name == 'tok_gelu_bwd':
+        return 'gelu', 0.0, 6.0 * a[0]
+    if name in ('tok_window_attn_fwd', 'tok_window_attn_bwd'):
+        # (batch, h, w, heads, window, shift, head_dim): 4 N^2 d fwd / 10 N^2 d bwd per (window, head)
+        b, h, w, heads, ws = a[0], a[1], a[2], a[3], a[4]
+        nwin = b * (h // ws) * (w // ws)
+        n2 = (ws * ws) ** 2
+        f = (4.0 if name.endswith('fwd') else 10.0) * n2 * 32 * nwin * heads
+        tok = b * h * w * heads * 32
+        return 'window attention', f, 2.0 * tok * (4 if name.endswith('fwd') else 8)
+    return None
+
+
+def step_roofline(loop, batch, sustained_tf, hbm_gbs):
+    """Time every C-ABI launch of ONE eager step with CUDA events on the launching stream and aggregate by kernel
+    family: share of the step, achieved rate, and time-weighted fraction of max(tensor floor, HBM floor)."""
+    from torchok_b200._lib import lib
+    L = lib()
+    use_graph, loop.use_graph = loop.use_graph, False
+    snap = loop._snapshot()
+    for _ in range(2):
+        loop.train_step(batch)
+    torch.cuda.synchronize()
+    timer = CallTimer()
+    L.tracer = timer
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream())
+    loop.train_step(batch)
+    e1.record(torch.cuda.current_stream())
+    L.tracer = None
+    torch.cuda.synchronize()
+    step_ms = e0.elapsed_time(e1)
+    loop._restore(snap)
+    loop.use_graph = use_graph
+    fam = {}
+    for name, a, s, e in timer.calls:
+        ms = s.elapsed_time(e)
+        w = _call_work(name, a)
+        key, flops, byts = w if w else ('other (' + name.replace('tok_', '') + ')', 0.0, 0.0)
+        f = fam.setdefault(key, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0, floor_ms=0.0, modelled=w is not None))
+        floor = max(flops / (sustained_tf * 1e12), byts / (hbm_gbs * 1e9)) * 1e3
+        f['launches'] += 1
+        f['ms'] += ms
+        f['flops'] += flops
+        f['bytes'] += byts
+        f['floor_ms'] += floor
+    total = sum(f['ms'] for f in fam.values())
+    groups = {'tcgen05 implicit-GEMM conv/linear (fprop+dgrad+wgrad)':
+              [k for k in fam if k.startswith('conv ') or k.startswith('linear ') or k == 'stem conv'],
+              'BatchNorm elementwise (apply / backward reduce / backward apply)': [k for k in fam if k.startswith('bn ')],
+              'window attention (tcgen05)': [k for k in fam if k == 'window attention'],
+              'LayerNorm / GELU elementwise': [k for k in fam if k in ('layernorm', 'gelu')]}
+    table = {}
+    for k, f in sorted(fam.items(), key=lambda kv: -kv[1]['ms']):
+        if f['ms'] < 0.005 * total and not f['modelled']:
+            continue
+        table[k] = {'launches': f['launches'], 'ms': round(f['ms'], 4), 'share': round(f['ms'] / total, 4),
+                    'frac_of_floor': round(f['floor_ms'] / f['ms'], 4) if f['modelled'] and f['ms'] > 0 else None,
+                    'tflops': round(f['flops'] / (f['ms'] * 1e-3) / 1e12, 1) if f['flops'] else None,
+                    'gbs': round(f['bytes'] / (f['ms'] * 1e-3) / 1e9, 1) if f['bytes'] else None}
+    best, best_ms = None, 0.0
+    for g, keys in groups.items():
+        ms = sum(fam[k]['ms'] for k in keys)
+        if ms > best_ms:
+            best, best_ms = g, ms
+    keys = groups[best]
+    ms = sum(fam[k]['ms'] for k in keys)
+    flops = sum(fam[k]['flops'] for k in keys)
+    byts = sum(fam[k]['bytes'] for k in keys)
+    floor = sum(fam[k]['floor_ms'] for k in keys)
+    tensor_bound = sum(fam[k]['flops'] for k in keys) / (sustained_tf * 1e12) >= byts / (hbm_gbs * 1e9)
+    if tensor_bound:
+        ach, peak, unit = flops / (ms * 1e-3) / 1e12, sustained_tf, 'TFLOP/s'
+    else:
+        ach, peak, unit = byts / (ms * 1e-3) / 1e9, hbm_gbs, 'GB/s'
+    return {'bound': 'tensor' if tensor_bound else 'hbm', 'achieved': ach, 'peak': peak, 'unit': unit,
+            'frac': floor / ms, 'traffic': None,
+            'kernel': best, 'launches': sum(fam[k]['launches'] for k in keys), 'ms_per_step': ms,
+            'share_of_step': ms / total,
+            'frac_note': 'time-weighted: sum over the launches of max(FLOPs / sustained bf16 peak, algorithmic bytes / '
+                         'HBM peak) divided by the sum of their CUDA-event durations; achieved/peak is the raw rate of '
+                         'the family in the unit of its dominant bound',
+            'eager_step_ms': step_ms, 'families': table}
 
 
 def _trace(msg):
@@ -189,34 +430,104 @@ def _trace(msg):
         print(f'[bench rank {os.environ.get("RANK", "0")} {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
 
 
-def run_ours(args):
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def _init_dist(dev):
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:
+        os.environ.setdefault('NCCL_IB_DISABLE', '1')      # NVLink only (north_star)
+        os.environ.setdefault('NCCL_P2P_LEVEL', 'NVL')
+        os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')
+        dist.init_process_group('nccl', device_id=dev)
+        _trace('process group up')
+    return world
+
+
+def run_retrieval(args):
+    """C5: IndexBasedMeter's search over N x 512 vectors; with N ranks: one all-gather of the vectors, each rank
+    searches its N/world query rows (torchok/metrics/index_base_metric.py:112-120,170-270)."""
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    world = _init_dist(dev)
+    from torchok_b200._lib import lib
+    from torchok_b200.metrics import index_base_metric as ibm
+    n, d, k = args.retrieval_n, 512, 1
+    per = n // world
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    mine = ibm.normalize_rows(torch.randn(per, d, device=dev, generator=g))
+
+    def search():
+        if world > 1:
+            allv = torch.empty(world * per, d, device=dev)
+            dist.all_gather_into_tensor(allv, mine)
+        else:
+            allv = mine
+        return ibm.search_topk(mine, allv, k + 1)
+    n0 = lib().launches
+    s, i = search()
+    per_call = lib().launches - n0
+    torch.cuda.synchronize()
+    ok = bool((i[:, 0] == torch.arange(per, device=dev) + rank * per).float().mean() > 0.999)
+    steps = max(1, min(args.steps, 3))
     if world > 1:
-        if os.environ.get('TOK_GRAPH_DDP', '0') == '1':    # experimental: NCCL all-reduce captured in the step graph
-            os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')
-            os.environ.setdefault('NCCL_ASYNC_ERROR_HANDLING', '0')
-        os.environ.setdefault('NCCL_IB_DISABLE', '1')      # NVLink only (north_star)
-        os.environ.setdefault('NCCL_P2P_LEVEL', 'NVL')
-        dist.init_process_group('nccl', device_id=dev)
-        _trace('process group up')
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        search()
+    e1.record()
+    e1.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t) / steps
+    if rank == 0:
+        sustained, burst, hbm, src = peaks()
+        flop = 2.0 * n * n * d
+        tf = flop / (ms * 1e-3) / 1e12 / world
+        print(json.dumps({
+            'metric': f'queries/sec retrieval cosine top-{k + 1} N={n} D={d}', 'value': n / (ms * 1e-3), 'unit': 'queries/s',
+            'n_gpus': world, 'steps': steps, 'warmup': 1, 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': f'IndexBasedMeter search, {n} x {d} unit vectors, top-{k + 1}, query rows sharded over '
+                                   f'{world} rank(s), one all-gather of the vectors per search (C5)',
+                       'self_is_top1': ok},
+            'gpu_launches': per_call * steps,
+            'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': sustained, 'unit': 'TFLOP/s', 'frac': tf / sustained,
+                         'traffic': None, 'kernel': 'cosine_topk_kernel (tcgen05 GEMM + fused running top-k), per GPU',
+                         'peak_source': f'MEASURED_PEAKS.json bf16_tflops_sustained ({src})'}}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_ours(args):
+    if args.workload == 'retrieval':
+        return run_retrieval(args)
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    world = _init_dist(dev)
     import torchok_b200 as tb
     from torchok_b200._lib import lib
     from torchok_b200.engine import StreamLoop
 
     torch.manual_seed(42)
-    cfg = tb.load_config(task_config(args.model))
+    cfg = tb.load_config(wl['cfg'])
     task = tb.TASKS.get(cfg.task.name)(cfg, **cfg.task.params).to(dev)
     loop = StreamLoop(task, use_graph=not args.no_graph)
     _trace('StreamLoop built')
-    B = args.batch
+    B = args.batch or wl['batch']
+    size, classes, seg = wl['size'], wl['classes'], wl.get('seg', False)
+    tshape = (B, size, size) if seg else (B,)
     if args.profile_step:
         loop.use_graph = False
-        x = torch.randn(B, 3, args.size, args.size, device=dev)
-        y = torch.randint(0, NUM_CLASSES, (B,), device=dev)
+        x = torch.randn(B, 3, size, size, device=dev)
+        y = torch.randint(0, classes, tshape, device=dev)
         for _ in range(3):
             loop.train_step({'image': x, 'target': y})
         torch.cuda.synchronize()
@@ -226,8 +537,10 @@ def run_ours(args):
         torch.cuda.profiler.stop()
         return
     g = torch.Generator().manual_seed(42 + rank)
-    host_img = [torch.randn(B, 3, args.size, args.size, generator=g).pin_memory() for _ in range(2)]
-    host_tgt = [torch.randint(0, NUM_CLASSES, (B,), generator=g).pin_memory() for _ in range(2)]
+    # host batches as the reference's datasets deliver them with `input_dtype: float16`
+    # (examples/configs/classification_cifar10.yaml:13,44): half-precision images, int64 targets, pinned
+    host_img = [torch.randn(B, 3, size, size, generator=g).to(torch.bfloat16).pin_memory() for _ in range(2)]
+    host_tgt = [torch.randint(0, classes, tshape, generator=g).pin_memory() for _ in range(2)]
     dev_batch = {'image': host_img[0].to(dev), 'target': host_tgt[0].to(dev)}
 
     def barrier():
@@ -308,47 +621,55 @@ def run_ours(args):
         ms_step = ms_total / args.steps
         value = world * B * args.steps / (ms_total * 1e-3)
         e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-        roof = time_dominant_kernel(B, sustained)
-        roof['peak_source'] = f'MEASURED_PEAKS.json bf16_tflops_sustained ({src})'
-        step_tf = FLOP_PER_IMG * B / (ms_step * 1e-3) / 1e12
         h2d = host_img[0].numel() * host_img[0].element_size() + host_tgt[0].numel() * host_tgt[0].element_size()
-        cpu = None
-        if not args.skip_cpu and world == 1:     # the CPU baseline is an N=1 leg (rank 0 only; the other ranks would idle)
-            cores = os.cpu_count()
-            torch.set_num_threads(cores)
-            ips, ms = cpu_reference(args.cpu_batch, 3, 1)
-            cpu = {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                   'sample': f'3 fwd+bwd+SGD steps of the oracle at bs{args.cpu_batch} fp32 ({ms:.0f} ms/step), '
-                             f'img/s normalised'}
+        roof = step_rf = cpu = torch_gpu = None
+        if world == 1:   # single-GPU legs: per-launch roofline of one eager step, CPU baseline, cuDNN baseline
+            roof = step_roofline(loop, dev_batch, sustained, hbm)
+            roof['peak_source'] = f'MEASURED_PEAKS.json bf16_tflops_sustained / hbm_gbs ({src})'
+            if not args.skip_cpu and wl['oracle'] is not None:
+                cores = os.cpu_count()
+                torch.set_num_threads(cores)
+                cb = min(args.cpu_batch, B)
+                ips, ms = cpu_reference(wl, cb, 3, 1)
+                cpu = {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                       'sample': f'3 fwd+bwd+optimizer steps of the oracle at bs{cb} fp32 ({ms:.0f} ms/step), img/s normalised'}
+            if not args.skip_torch and wl['oracle'] is not None:
+                try:
+                    torch_gpu = gpu_torch_baseline(wl, B)
+                except Exception as e:   # the comparison leg must never cost the bench line
+                    torch_gpu = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
+        if wl['flop_per_img']:
+            step_tf = wl['flop_per_img'] * B / (ms_step * 1e-3) / 1e12
+            step_rf = {'bound': 'tensor', 'achieved': step_tf, 'peak': sustained, 'unit': 'TFLOP/s',
+                       'frac': step_tf / sustained,
+                       'note': f'whole step: {wl["flop_per_img"] / 1e9:.2f} GFLOP/img x {B} img / step time'}
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'metric': wl['metric'], 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': f'ResNet-50 ClassificationTask synthetic 3x{args.size}x{args.size} bs{B}/GPU bf16 '
-                                   f'(fp32 master weights, fp32 BN statistics), SGD momentum step included',
-                       'global_batch': world * B, 'parallelism': f'dp{world}',
-                       'l2': 'inputs/activations per step (>5 GB) far exceed the 126 MB L2; no explicit flush',
-                       'cuda_graph': bool(loop.use_graph), 'final_loss': loss_val},
+            'config': {'workload': wl['name'], 'global_batch': world * B, 'parallelism': f'dp{world}',
+                       'l2': 'activations of one step far exceed the 126 MB L2; no explicit flush'
+                             if args.workload != 'resnet18_cifar' else
+                             'whole working set of a step fits the 126 MB L2 (launch/latency-bound workload)',
+                       'cuda_graph': bool(loop.use_graph), 'grad_exchange': loop.exchange, 'final_loss': loss_val},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': int(per_step) * args.steps,
             'gpu_launches_note': 'C-ABI kernel-launching calls per step x steps (each call launches >= 1 kernel)',
             'clocks': clocks,
             'roofline': roof,
-            'roofline_step': {'bound': 'tensor', 'achieved': step_tf, 'peak': sustained, 'unit': 'TFLOP/s',
-                              'frac': step_tf / sustained,
-                              'note': f'whole step: {FLOP_PER_IMG / 1e9:.2f} GFLOP/img x {B} img / step time'},
+            'roofline_step': step_rf,
             'cpu_baseline': cpu,
+            'gpu_torch_baseline': torch_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        # Leave without tearing NCCL down: destroy_process_group() was seen to block after graph-captured collectives,
-        # and a benchmark process has nothing left to clean up.  All ranks meet at a barrier first.
         sys.stdout.flush()
         sys.stderr.flush()
+        loop.close()
         dist.barrier()
         torch.cuda.synchronize()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 def main():
@@ -357,11 +678,12 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=256)
-    ap.add_argument('--size', type=int, default=224)
-    ap.add_argument('--model', default='resnet50')
+    ap.add_argument('--workload', default='resnet50', choices=sorted(WORKLOADS) + ['retrieval'])
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s BASELINE.json batch)')
+    ap.add_argument('--retrieval-n', type=int, default=1 << 20)
     ap.add_argument('--cpu-batch', type=int, default=32)
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-torch', action='store_true', help='skip the cuDNN (torch.nn on this GPU) comparison leg')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--profile-step', action='store_true',
                     help='ncu aid: warm up eagerly, then run ONE eager step between cudaProfilerStart/Stop and exit '

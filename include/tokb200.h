@@ -172,6 +172,9 @@ int tok_maxpool_bwd(int n, int h, int w, int c, int k, int s, int pad, const voi
 /* mode 0 avg, 1 max, 2 avgmax */
 int tok_gap_fwd(int n, int hw, int c, int mode, const void* x, void* out, void* stream);
 int tok_gap_bwd(int n, int hw, int c, const void* dout, void* dx, void* stream);
+/* backward of mode 1 / 2: the first maximal position (F.adaptive_max_pool2d's choice) takes the max-path gradient;
+ * x is the pooled activation [n][hw][c] (timm SelectAdaptivePool2d, pooling.py:8-12) */
+int tok_gap_bwd_max(int n, int hw, int c, int mode, const void* dout, const void* x, void* dx, void* stream);
 
 /* ---- loss (torch.nn.CrossEntropyLoss, torchok/losses/__init__.py:26): *loss_sum += inv_norm * sum NLL (nullable);
  * dlogits (nullable) = (softmax - onehot) * gscale * (*gscale_dev if non-NULL: the upstream scalar gradient, read on
@@ -328,8 +331,50 @@ int tok_sgd_step_dev_groups(long long n, float* param, float* grad, float* momen
 int tok_adam_step_dev_groups(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                              void* shadow_bf16, const float* lr_dev, int* step_dev, float beta1, float beta2, float eps,
                              float weight_decay, int decoupled, float grad_scale, int zero_grad, const int* seg_begin,
-                             const float* seg_lr_mult, const float* seg_wd_mult, int n_segs, void* stream);
+                             const float* seg_lr_mult, const float* seg_wd_mult, int* seg_steps, int n_segs,
+                             void* stream);
+/* `seg_steps` (nullable, n_segs ints on the device): per-parameter Adam step counts (torch.optim.Adam's state['step']);
+ * advanced by this call for every segment whose multipliers are not both zero and used for the bias correction, so a
+ * parameter thawed by FreezeUnfreeze (torchok/callbacks/freeze_unfreeze.py:51-184) restarts at step 1 as in the
+ * reference.  Segments with lr_mult == wd_mult == 0 (frozen) are skipped entirely by both step kernels. */
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream);
+
+/* ---- data-parallel gradient exchange over NVLink / NVSwitch PEER MEMORY, fused with the optimizer --------------------
+ * Replaces Lightning's DDP gradient all-reduce + optimizer.step (`trainer.strategy: ddp`,
+ * torchok/constructor/config_structure.py:137-140; examples/configs/classification_imagenet.yaml:121-122).  One process
+ * per GPU; every rank allocates its parameter / gradient / bf16-shadow arenas and a flag block with tok_ipc_alloc and
+ * opens the other ranks' with tok_ipc_open (CUDA IPC, peer access over NVLink).  tok_peer_step then runs, per gradient
+ * bucket, ONE kernel per rank: barrier (flags in peer memory) -> each rank sums ITS 1/world slice of the bucket from
+ * all ranks' gradient arenas (reduce-scatter by peer loads) -> SGD / Adam(W) on that slice (momentum / moment state
+ * exists only for the slice: ZeRO-1) -> the new fp32 master and bf16 shadow values are stored into EVERY rank's arenas
+ * (all-gather by peer stores) -> barrier -> the local gradients of the bucket are cleared.  No host synchronisation, so
+ * the launch can be captured in a CUDA graph. */
+#define TOK_PEER_MAX_RANKS 8
+#define TOK_PEER_MAX_BUCKETS 256
+/* cudaMalloc + zero fill + cudaIpcGetMemHandle; `handle64` receives the 64-byte cudaIpcMemHandle_t. */
+int tok_ipc_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int tok_ipc_free(void* dev_ptr);
+/* cudaIpcOpenMemHandle (peer access enabled lazily) of a handle produced by ANOTHER process. */
+int tok_ipc_open(const void* handle64, void** dev_ptr);
+int tok_ipc_close(void* dev_ptr);
+/* bytes a flag block must have (two phases x buckets x ranks 32-bit epochs + per-bucket epoch / ticket words) */
+size_t tok_peer_flag_bytes(void);
+typedef struct {
+  int world, rank;
+  float* master[TOK_PEER_MAX_RANKS];     /* fp32 parameter arenas of every rank (index = rank; [rank] is local) */
+  float* grad[TOK_PEER_MAX_RANKS];       /* fp32 gradient arenas */
+  void* shadow[TOK_PEER_MAX_RANKS];      /* bf16 shadow arenas */
+  unsigned* flags[TOK_PEER_MAX_RANKS];   /* flag blocks */
+} tokPeerArenas;
+/* kind 0: SGD (h0 momentum, h1 weight_decay, h2 dampening, i0 nesterov; state0 = momentum buffer or NULL);
+ * kind 1: Adam / AdamW (h0 beta1, h1 beta2, h2 eps, h3 weight_decay, i0 decoupled; state0 exp_avg, state1 exp_avg_sq).
+ * [begin, end) = the bucket's element range in the arenas (multiples of 64); `bucket` < TOK_PEER_MAX_BUCKETS indexes
+ * the flags; grad_scale multiplies the SUMMED gradient (1/world for DDP's mean); advance_step != 0 on the first bucket
+ * launched in a step (advances *step_dev and the per-segment Adam counters). */
+int tok_peer_step(const tokPeerArenas* arenas, int bucket, long long begin, long long end, int kind, float* state0,
+                  float* state1, const float* lr_dev, int* step_dev, float h0, float h1, float h2, float h3, int i0,
+                  float grad_scale, const int* seg_begin, const float* seg_lr_mult, const float* seg_wd_mult,
+                  int* seg_steps, int n_segs, int advance_step, void* stream);
 
 #ifdef __cplusplus
 }

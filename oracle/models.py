@@ -174,7 +174,8 @@ class Pooling(nn.Module):
         self.out_channels = in_channels * (2 if pooling_type == 'catavgmax' else 1)
 
     def forward(self, x):
-        avg, mx = x.mean((2, 3)), x.amax((2, 3))
+        # timm SelectAdaptivePool2d: F.adaptive_avg_pool2d / F.adaptive_max_pool2d (the first maximum takes the gradient)
+        avg, mx = F.adaptive_avg_pool2d(x, 1).flatten(1), F.adaptive_max_pool2d(x, 1).flatten(1)
         return q({'avg': avg, 'max': mx, 'avgmax': 0.5 * (avg + mx), 'catavgmax': torch.cat([avg, mx], 1)}[
             self.pooling_type])
 

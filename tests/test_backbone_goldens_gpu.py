@@ -1,0 +1,60 @@
+"""The sm_100a backbones replayed against tests/golden/backbone_goldens.pt — outputs of the REFERENCE's own resnet.py /
+hrnet.py / swin.py executed by path (tests/golden/make_backbone_goldens.py): the product must take the reference's
+state dict STRICTLY (key names, shapes) and reproduce forward_features / forward / the attribute contract.
+
+Bar: fp32 goldens vs bf16 kernels.  Eval-mode cases: 1e-2 of the tensor maximum and 1e-2 relative L2 (north_star).
+Training-mode cases (batch statistics over 2-sample batches amplify storage rounding in the reference's own precision-16
+mode too): GPU error <= 1.5 x the error of the oracle's bf16-AMP evaluation of the same case + 5e-3."""
+import os
+import sys
+
+import pytest
+import torch
+
+from tests.util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+from make_backbone_goldens import seeded_state  # noqa: E402
+from tests.test_oracle_backbone_goldens import build_oracle  # noqa: E402
+
+G = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'backbone_goldens.pt'))
+CASES = [(name, i) for name, cs in G.items() for i in range(len(cs))]
+
+
+@pytest.mark.parametrize('name,idx', CASES)
+def test_product_backbone_replays_reference_wiring(name, idx):
+    import torchok_b200 as tb
+    from oracle import models as om
+    c = G[name][idx]
+    kw = dict(c['kwargs'])
+    if name.startswith('swin'):
+        kw['drop_path_rate'] = 0.0
+    else:
+        kw['in_channels'] = 3
+    m = tb.BACKBONES.get(name)(pretrained=False, **kw)
+    o = build_oracle(name, c['kwargs'])
+    state = seeded_state(o, c['seed'])
+    missing = m.load_state_dict(state, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert m.out_channels == c['out_channels']
+    assert tuple(m.out_encoder_channels) == tuple(c['out_encoder_channels'])
+    assert [len(m.get_stages(i)) for i in range(5)] == c['stages']
+    o.load_state_dict(state)
+    o.train(c['train'])
+    m.cuda().train(c['train'])
+    x = c['x']
+    with torch.no_grad():
+        with om.amp_bf16():
+            fa = o.forward_features(x)[1:]
+        fm = m.forward_features(x.cuda())[1:]
+    assert len(fm) == len(c['feats'])
+    for i, (a, g, amp) in enumerate(zip(fm, c['feats'], fa)):
+        assert tuple(a.shape) == tuple(g.shape)
+        e, e_amp = rel_err(a, g), rel_err(amp, g)
+        print(f'{name}[{idx}] feature {i}: gpu-vs-reference max {e:.4f} l2 {rel_l2(a, g):.4f} | oracle-amp {e_amp:.4f}')
+        if c['train']:
+            assert e < 1.5 * e_amp + 5e-3, (i, e, e_amp)
+        else:
+            assert e < max(1e-2, 1.5 * e_amp) and rel_l2(a, g) < 1e-2, (i, e, e_amp)

@@ -826,3 +826,30 @@ def test_reference_example_configs_drop_in(name, task_cls, monkeypatch):
         if o.get('scheduler'):
             params = dict(o.scheduler.get('params') or {})
             LrDriver(_FakeOpt(o.optimizer.params.lr), o.scheduler.name, params, o.scheduler.get('pl_params'))
+
+
+def test_jaccard_index_with_in_range_ignore_index():
+    """torchmetrics 0.11.4 `_jaccard_index_reduce` takes an in-range ignore_index out of the score (macro:
+    weight 0; micro: its denominator subtracted) — segmentation_sweet_pepper.yaml uses num_classes 3 / ignore_index 0."""
+    import torch
+    from torchok_b200.metrics.metrics_manager import JaccardIndex
+    t, p = torch.tensor([0, 0, 1, 1, 2, 2]), torch.tensor([0, 1, 1, 1, 2, 1])
+    m = JaccardIndex(num_classes=3, ignore_index=0)
+    m.update(p, t)
+    # the two ignored targets are dropped: class 1 = 2/3, class 2 = 1/2, class 0 weight 0
+    assert abs(float(m.compute()) - (2 / 3 + 1 / 2) / 2) < 1e-6
+    m = JaccardIndex(num_classes=3, ignore_index=0, average='micro')
+    m.update(p, t)
+    assert abs(float(m.compute()) - 3 / 5) < 1e-6          # tp 3 / (unions 3 + 2; class 0's denominator is taken out)
+    m = JaccardIndex(num_classes=3, ignore_index=255)      # out of range: every class counts
+    m.update(p, t)
+    assert abs(float(m.compute()) - (1 / 2 + 2 / 4 + 1 / 2) / 3) < 1e-6
+
+
+def test_optimizer_rejects_arithmetic_changing_keys():
+    from torchok_b200.engine import _check_optimizer_kwargs
+    _check_optimizer_kwargs('Adam', {'foreach': True, 'amsgrad': False, 'fused': None})
+    with pytest.raises(NotImplementedError):
+        _check_optimizer_kwargs('Adam', {'amsgrad': True})
+    with pytest.raises(NotImplementedError):
+        _check_optimizer_kwargs('SGD', {'maximize': True})

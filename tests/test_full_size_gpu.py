@@ -1,0 +1,234 @@
+"""Parity at BASELINE.json's FULL configuration sizes: the CUDA path against the CPU oracle on
+the same seeded inputs.
+
+  C2  ResNet-50 ClassificationTask, 3x224x224, bs256 — ONE TRAINING STEP (batch statistics): loss, logits, class ids,
+      fc / layer4 / conv1 gradients, BatchNorm running statistics
+  C3  Swin-T (V2) = swinv2_custom img_size=224 window 7, bs32: the four feature maps
+  C4  HRNet-W18 + HRNetSegmentationNeck + SegmentationHead, 3x512x512, bs2: backbone branches and segmentation logits
+  C5  retrieval cosine top-k, N = 262 144 x 512: neighbour indices bit-exact against (a) the CPU oracle on a query sample
+      and (b) a blocked fp32 matmul + topk over ALL rows
+
+Bars (north_star: 1e-2 relative for bf16 tensors, class ids bit-exact).  Every tensor is compared in the max norm
+relative to the oracle tensor's maximum (tests/util.rel_err) AND in the relative L2 norm; the fp32 oracle is the
+reference, the oracle's own bf16-AMP evaluation is printed beside each number to show what the storage precision alone
+costs.  Training-mode whole networks: GPU error <= 1.5 x oracle-AMP error + 5e-3 (batch-statistics amplification of
+storage rounding, see tests/test_resnet_gpu.py), and never above 3e-2.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _task_cfg(tb, backbone, head, head_params, task='ClassificationTask', **extra):
+    params = {'backbone_name': backbone, 'backbone_params': {'pretrained': False, 'in_channels': 3},
+              'head_name': head, 'head_params': head_params}
+    params.update(extra)
+    return tb.load_config({
+        'task': {'name': task, 'params': params},
+        'joint_loss': {'losses': [{'name': 'CrossEntropyLoss', 'mapping': {'input': 'prediction', 'target': 'target'}}]}})
+
+
+def test_c2_resnet50_bs256_train_step():
+    import torchok_b200 as tb
+    from oracle import models as om
+    torch.manual_seed(0)
+    cfg = _task_cfg(tb, 'resnet50', 'ClassificationHead', {'num_classes': 1000}, pooling_name='Pooling')
+    task = tb.TASKS.get('ClassificationTask')(cfg, **cfg.task.params)
+    oracle = om.ClassificationTask(om.resnet('resnet50'), om.Pooling(2048), om.ClassificationHead(2048, 1000))
+    om.dedegenerate_(oracle, 4)
+    task.load_state_dict(oracle.state_dict(), strict=False)
+    task.cuda().train()
+    o16 = copy.deepcopy(oracle)
+    oracle.train(), o16.train()
+    x = torch.randn(256, 3, 224, 224)
+    y = torch.randint(0, 1000, (256,))
+    res = {}
+    for name, net, amp in (('fp32', oracle, False), ('amp', o16, True)):
+        with om.amp_bf16(amp):
+            out = net.forward_with_gt({'image': x, 'target': y})
+            loss = F.cross_entropy(out['prediction'], y)
+            loss.backward()
+        res[name] = (out['prediction'].detach(), float(loss), {k: p.grad for k, p in net.named_parameters()},
+                     net.state_dict())
+    step = task.training_step({'image': x.cuda(), 'target': y.cuda()})
+    step['loss'].backward()
+    torch.cuda.synchronize()
+    logits = task.last_output['prediction'].float().cpu()      # training-mode logits of this very step
+    e, e_amp = rel_err(logits, res['fp32'][0]), rel_err(res['amp'][0], res['fp32'][0])
+    print(f'C2 train step: logits gpu-vs-fp32 {e:.4f} | oracle-amp-vs-fp32 {e_amp:.4f}')
+    assert e < 1.5 * e_amp + 5e-3 and e < 3e-2, (e, e_amp)
+    lo, lo_amp = res['fp32'][1], res['amp'][1]
+    e_loss, e_loss_amp = abs(float(step['loss']) - lo) / lo, abs(lo_amp - lo) / lo
+    print(f'C2 train step: loss gpu {float(step["loss"]):.5f} fp32 {lo:.5f} amp {lo_amp:.5f}')
+    assert e_loss < 1.5 * e_loss_amp + 2e-3, (e_loss, e_loss_amp)
+    grads = dict(task.named_parameters())
+    worst = 0.0
+    for k in ('head.fc.weight', 'head.fc.bias', 'backbone.layer4.2.conv3.weight', 'backbone.layer4.0.downsample.0.weight',
+              'backbone.layer3.5.bn3.weight', 'backbone.layer2.3.conv2.weight', 'backbone.layer1.0.conv1.weight',
+              'backbone.bn1.weight', 'backbone.conv1.weight'):
+        g, go, ga = grads[k].grad, res['fp32'][2][k], res['amp'][2][k]
+        e, e_amp = rel_l2(g, go), rel_l2(ga, go)
+        worst = max(worst, e)
+        print(f'  grad {k}: gpu-vs-fp32 l2 {e:.4f} | oracle-amp-vs-fp32 l2 {e_amp:.4f}')
+        assert e < 1.5 * e_amp + 1e-2 and e < 6e-2, (k, e, e_amp)
+    sd = task.state_dict()
+    for k in ('backbone.bn1.running_mean', 'backbone.layer4.2.bn3.running_var', 'backbone.layer2.0.bn1.running_mean'):
+        e, e_amp = rel_l2(sd[k], res['fp32'][3][k]), rel_l2(res['amp'][3][k], res['fp32'][3][k])
+        print(f'  {k}: {e:.5f} | amp {e_amp:.5f}')
+        assert e < 1.5 * e_amp + 5e-3, (k, e, e_amp)
+    # logits of the training-mode forward and their class ids
+    with torch.no_grad():
+        task.eval()
+        oracle.eval()
+        a = task.forward_with_gt({'image': x[:64].cuda()})['prediction'].float().cpu()
+        b = oracle.forward_with_gt({'image': x[:64]})['prediction']
+    e = rel_err(a, b)
+    print(f'  eval logits after the step (running statistics updated on both sides): rel_err {e:.4f}')
+    assert e < 2e-2
+
+
+def test_c2_resnet50_bs256_eval_class_ids_bit_exact():
+    """north_star: class ids bit-exact.  Every one of the 256 rows must give the oracle's class id; a row may only be
+    excused if the ORACLE's own top-2 logits are closer than north_star's fp32 bar (1e-3 of the logit range), and such
+    rows are listed."""
+    import torchok_b200 as tb
+    from oracle import models as om
+    torch.manual_seed(0)
+    cfg = _task_cfg(tb, 'resnet50', 'ClassificationHead', {'num_classes': 1000}, pooling_name='Pooling')
+    task = tb.TASKS.get('ClassificationTask')(cfg, **cfg.task.params)
+    oracle = om.ClassificationTask(om.resnet('resnet50'), om.Pooling(2048), om.ClassificationHead(2048, 1000))
+    om.dedegenerate_(oracle, 4)
+    task.load_state_dict(oracle.state_dict(), strict=False)
+    task.cuda().eval()
+    oracle.eval()
+    x = torch.randn(256, 3, 224, 224)
+    with torch.no_grad():
+        a = task.forward_with_gt({'image': x.cuda()})['prediction'].float().cpu()
+        b = oracle.forward_with_gt({'image': x})['prediction']
+    top2 = b.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1]) / b.abs().max()
+    same = a.argmax(1) == b.argmax(1)
+    bad = (~same).nonzero().flatten().tolist()
+    print(f'C2 eval class ids: {int(same.sum())}/256 equal; differing rows {bad} with oracle top-2 margins '
+          f'{[round(float(margin[i]), 5) for i in bad]}; logits rel_err {rel_err(a, b):.4f}; min margin overall '
+          f'{float(margin.min()):.5f}')
+    assert rel_err(a, b) < 1e-2
+    assert all(float(margin[i]) < 1e-3 for i in bad), (bad, [float(margin[i]) for i in bad])
+    assert len(bad) <= 2
+
+
+def test_c3_swin_t_224_window7_features():
+    import torchok_b200 as tb
+    from oracle import models as om
+    from oracle import swin as osw
+    torch.manual_seed(0)
+    kw = dict(img_size=224, window_size=7)
+    o = osw.SwinTransformerV2(**kw)
+    osw.dedegenerate_ln_(o, 0)
+    m = tb.BACKBONES.get('swinv2_custom')(pretrained=False, drop_path_rate=0.0, **kw)
+    m.load_state_dict(o.state_dict())
+    m.cuda().eval()
+    o.eval()
+    o16 = copy.deepcopy(o)
+    x = torch.randn(32, 3, 224, 224)
+    with torch.no_grad():
+        fo = o.forward_features(x)
+        with om.amp_bf16():
+            fa = o16.forward_features(x)
+        fm = m.forward_features(x.cuda())
+    assert [tuple(f.shape) for f in fm[1:]] == [(32, 96, 56, 56), (32, 192, 28, 28), (32, 384, 14, 14), (32, 768, 7, 7)]
+    for i, (a, b, c) in enumerate(zip(fm[1:], fo[1:], fa[1:])):
+        e, e_amp = rel_err(a, b), rel_err(c, b)
+        print(f'C3 Swin-T@224 w7 stage {i}: gpu-vs-fp32 max {e:.4f} l2 {rel_l2(a, b):.4f} | oracle-amp max {e_amp:.4f} '
+              f'l2 {rel_l2(c, b):.4f}')
+        assert e < 1.5 * e_amp + 5e-3 and rel_l2(a, b) < 1e-2, (i, e, e_amp)
+
+
+def test_c4_hrnet_w18_512_seg_logits():
+    import torchok_b200 as tb
+    from oracle import models as om
+    torch.manual_seed(5)
+    cfg = _task_cfg(tb, 'hrnet_w18', 'SegmentationHead', {'num_classes': 19}, task='SegmentationTask',
+                    neck_name='HRNetSegmentationNeck')
+    task = tb.TASKS.get('SegmentationTask')(cfg, **cfg.task.params)
+    ob = om.hrnet('hrnet_w18')
+    oracle = om.SegmentationTask(ob, om.HRNetSegmentationNeck(ob.out_encoder_channels),
+                                 om.SegmentationHead(sum(ob.out_encoder_channels), 19))
+    om.dedegenerate_(oracle, 5)
+    task.load_state_dict(oracle.state_dict(), strict=True)
+    task.cuda().eval()
+    oracle.eval()
+    o16 = copy.deepcopy(oracle)
+    x = torch.randn(2, 3, 512, 512)
+    with torch.no_grad():
+        fo = oracle.backbone.forward_features(x)
+        po = oracle.forward_with_gt({'image': x})['prediction']
+        with om.amp_bf16():
+            fa = o16.backbone.forward_features(x)
+            pa = o16.forward_with_gt({'image': x})['prediction']
+        fm = task.backbone.forward_features(x.cuda())
+        pm = task.forward_with_gt({'image': x.cuda()})['prediction']
+    assert [tuple(f.shape) for f in fm[1:]] == [(2, 18, 128, 128), (2, 36, 64, 64), (2, 72, 32, 32), (2, 144, 16, 16)]
+    for i, (a, b, c) in enumerate(zip(fm[1:], fo[1:], fa[1:])):
+        e, e_amp = rel_err(a, b), rel_err(c, b)
+        print(f'C4 HRNet-W18@512 branch {i}: gpu-vs-fp32 max {e:.4f} l2 {rel_l2(a, b):.4f} | oracle-amp max {e_amp:.4f}')
+        assert e < 1.5 * e_amp + 5e-3 and rel_l2(a, b) < 1e-2, (i, e, e_amp)
+    assert tuple(pm.shape) == (2, 19, 512, 512)
+    e, e_amp = rel_err(pm, po), rel_err(pa, po)
+    agree = float((pm.float().cpu().argmax(1) == po.argmax(1)).float().mean())
+    print(f'C4 seg logits: gpu-vs-fp32 max {e:.4f} l2 {rel_l2(pm, po):.4f} | oracle-amp {e_amp:.4f}; pixel class ids '
+          f'equal on {agree:.5f}')
+    assert e < 1.5 * e_amp + 5e-3 and rel_l2(pm, po) < 1e-2
+    assert agree > 0.995
+
+
+def test_c5_retrieval_262144_indices_bit_exact():
+    from oracle import retrieval as orc
+    from torchok_b200.metrics import index_base_metric as ibm
+    n, d, k = 262144, 512, 3
+    g = torch.Generator(device='cuda').manual_seed(7)
+    # clustered data (64 rows per class around a class centre) so that the neighbours are meaningful, not noise
+    centres = torch.randn(n // 64, d, device='cuda', generator=g)
+    v = centres.repeat_interleave(64, 0) + 0.7 * torch.randn(n, d, device='cuda', generator=g)
+    v = ibm.normalize_rows(v)
+    s, i = ibm.search_topk(v, v, k)
+    torch.cuda.synchronize()
+    assert (i[:, 0] == torch.arange(n, device='cuda')).all()          # self-retrieval
+    # (b) every row against blocked fp32 matmul + topk (torch on the device, fp32 'highest' precision: the checker)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        bad_rows = 0
+        tie_rows = 0
+        for q0 in range(0, n, 8192):
+            sc = v[q0:q0 + 8192] @ v.t()
+            ts, ti = sc.topk(k + 1, dim=1)
+            gap = (ts[:, :-1] - ts[:, 1:]).abs() < 2e-6          # fp32 summation-order noise: order not defined
+            tie = gap.any(1)
+            eq = (ti[:, :k] == i[q0:q0 + 8192]).all(1)
+            bad_rows += int((~eq & ~tie).sum())
+            tie_rows += int(tie.sum())
+            assert torch.allclose(ts[:, :k][~tie], s[q0:q0 + 8192][~tie], rtol=1e-4, atol=2e-5)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    print(f'C5 N={n}: rows differing from the fp32 brute force outside fp32 ties: {bad_rows}; rows with an fp32 tie '
+          f'among the first {k + 1} scores: {tie_rows}')
+    assert bad_rows == 0 and tie_rows < n * 1e-3
+    # (a) the CPU oracle (numpy brute force, oracle/retrieval.py) on a sample of 256 query rows
+    rows = np.random.default_rng(0).choice(n, 256, replace=False)
+    vh = v.cpu().numpy()
+    s_ref, i_ref = orc.flat_search(vh, vh[rows], k, 'IP')
+    got = i[torch.from_numpy(rows).cuda()].cpu().numpy()
+    gap = np.abs(np.diff(s_ref, axis=1)) < 2e-6
+    ok = np.ones_like(i_ref, dtype=bool)
+    ok[:, 1:] &= ~gap
+    ok[:, :-1] &= ~gap
+    assert (got[ok] == i_ref[ok]).all()
+    assert ok.mean() > 0.99

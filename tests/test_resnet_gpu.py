@@ -200,40 +200,7 @@ def test_forward_eval(name, size, batch):
     assert e < 2e-2
 
 
-def test_full_size_resnet50_bs256_eval_logits_and_class_ids():
-    """BASELINE.json config 2 at its FULL size (ResNet-50 ClassificationTask, 3x224x224, bs256, 1000 classes), eval mode
-    (running statistics, so the comparison is not at the mercy of batch-statistics chaos): logits against the fp32 CPU
-    oracle within the bf16 bar, class ids equal wherever the oracle's own top-2 margin exceeds that bar."""
-    import torchok_b200 as tb
-    from oracle import models as om
-    torch.manual_seed(0)
-    cfg = tb.load_config({
-        'task': {'name': 'ClassificationTask', 'params': {
-            'backbone_name': 'resnet50', 'backbone_params': {'pretrained': False, 'in_channels': 3},
-            'pooling_name': 'Pooling', 'head_name': 'ClassificationHead', 'head_params': {'num_classes': 1000}}},
-        'joint_loss': {'losses': [{'name': 'CrossEntropyLoss', 'mapping': {'input': 'prediction', 'target': 'target'}}]}})
-    task = tb.TASKS.get('ClassificationTask')(cfg, **cfg.task.params)
-    oracle = om.ClassificationTask(om.resnet('resnet50'), om.Pooling(2048), om.ClassificationHead(2048, 1000))
-    om.dedegenerate_(oracle, 4)
-    task.load_state_dict(oracle.state_dict(), strict=False)
-    task.cuda().eval()
-    oracle.eval()
-    x = torch.randn(256, 3, 224, 224)
-    with torch.no_grad():
-        om_ = task.forward_with_gt({'image': x.cuda()})
-        oo = oracle.forward_with_gt({'image': x})
-    a, b = om_['prediction'].float().cpu(), oo['prediction']
-    assert a.shape == b.shape == (256, 1000)
-    assert rel_err(om_['embeddings'], oo['embeddings']) < 2e-2      # the 256 x 2048 pooled features
-    e = rel_err(a, b)
-    top2 = b.topk(2, dim=1).values
-    margin = (top2[:, 0] - top2[:, 1]) / b.abs().max()
-    same = a.argmax(1) == b.argmax(1)
-    print(f'resnet50 bs256 @224 eval: rel_err={e:.4f}, class ids equal on {int(same.sum())}/256 rows, '
-          f'min margin of a differing row={float(margin[~same].min()) if (~same).any() else float("nan"):.4f}')
-    assert e < 2e-2
-    assert bool((same | (margin < 2e-2)).all())     # a class id may only differ where the oracle itself is within the bar
-    assert float(same.float().mean()) >= 0.97
+# full-size (bs256 @224) eval / train-step parity with strict class-id equality: tests/test_full_size_gpu.py
 
 
 @pytest.mark.parametrize('name,size,batch', [('resnet18', 64, 32), ('resnet26', 64, 16), ('resnet50', 64, 16)])

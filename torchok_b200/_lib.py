@@ -29,6 +29,12 @@ class tokConvDesc(C.Structure):
     _fields_ = [(k, C.c_int) for k in ('n', 'h', 'w', 'c', 'k', 'r', 's', 'stride', 'pad', 'dil')]
 
 
+class tokPeerArenas(C.Structure):
+    """include/tokb200.h: pointer table of tok_peer_step (8 = TOK_PEER_MAX_RANKS)."""
+    _fields_ = [('world', C.c_int), ('rank', C.c_int), ('master', C.c_void_p * 8), ('grad', C.c_void_p * 8),
+                ('shadow', C.c_void_p * 8), ('flags', C.c_void_p * 8)]
+
+
 _vp, _i, _ll, _f, _d, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_size_t
 _pd = C.POINTER(tokConvDesc)
 _pi = C.POINTER(C.c_int)
@@ -78,6 +84,7 @@ _SIGS = {
     'tok_maxpool_bwd': (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_gap_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_gap_bwd': (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    'tok_gap_bwd_max': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_softmax_xent': (_i, [_i, _i, _ll, _vp, _vp, _vp, _vp, _f, _f, _vp, _ll, _vp, _vp]),
     'tok_layernorm_fwd': (_i, [_ll, _i, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     'tok_layernorm_bwd': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -110,11 +117,18 @@ _SIGS = {
     'tok_sgd_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _i, _vp]),
     'tok_adam_step_dev': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp]),
     'tok_sgd_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _i, _vp]),
-    'tok_adam_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _i,
-                                      _vp]),
+    'tok_adam_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _vp,
+                                      _i, _vp]),
+    'tok_ipc_alloc': (_i, [_sz, C.POINTER(C.c_void_p), _vp]),
+    'tok_ipc_free': (_i, [_vp]),
+    'tok_ipc_open': (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    'tok_ipc_close': (_i, [_vp]),
+    'tok_peer_flag_bytes': (_sz, []),
+    'tok_peer_step': (_i, [C.POINTER(tokPeerArenas), _i, _ll, _ll, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp, _vp,
+                           _vp, _vp, _i, _i, _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
 }
-_RAW = {'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+_RAW = {'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}
 
 
@@ -133,6 +147,7 @@ class _Lib:
                 'torchok_b200 has no CPU or torch.nn fallback for its kernels.')
         self._dll = C.CDLL(path)
         self.path = path
+        self.tracer = None
         self.launches = 0  # kernels-launching ABI calls made through this binding (bench.py's gpu_launches claim)
         for name, (res, args) in _SIGS.items():
             fn = getattr(self._dll, name)
@@ -144,7 +159,13 @@ class _Lib:
 
     def _checked(self, name, fn):
         def call(*a):
-            rc = fn(*a)
+            tr = self.tracer
+            if tr is not None:     # bench.py's per-call CUDA-event timing (off on the product path)
+                tok = tr.before(name, a)
+                rc = fn(*a)
+                tr.after(tok)
+            else:
+                rc = fn(*a)
             self.launches += 1
             if rc != 0:
                 raise TokError(f'{name} failed ({rc}): {self._dll.tok_last_error().decode()}')

@@ -14,6 +14,7 @@
 #include "../../include/tokb200.h"
 #include "tok_internal.h"
 #include "tok_ptx.cuh"
+#include "tok_optim.cuh"
 
 namespace tok {
 
@@ -422,6 +423,43 @@ __global__ void gap_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict
   }
 }
 
+// Backward of the max / avgmax pool (F.adaptive_max_pool2d semantics: the FIRST maximal position in scan order takes
+// the whole max-path gradient).  One thread per (n, 8-channel vector): pass 1 finds the arg-max rows, pass 2 writes dx.
+__global__ void gap_bwd_max_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ x, uint4* __restrict__ dx,
+                                   int N, int HW, int cvec, int mode) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)N * cvec) return;
+  const int cv = (int)(i % cvec);
+  const long long n = i / cvec;
+  float m[8];
+  int am[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m[j] = -INFINITY;
+    am[j] = 0;
+  }
+  for (int r = 0; r < HW; ++r) {
+    float f[8];
+    unpack8(__ldg(x + (n * HW + r) * cvec + cv), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (f[j] > m[j] || (r == 0)) {   // NaN-free inputs; strict '>' keeps the first maximum
+        m[j] = f[j];
+        am[j] = r;
+      }
+  }
+  float g[8];
+  unpack8(__ldg(dout + n * cvec + cv), g);
+  const float wmax = mode == 1 ? 1.f : 0.5f;
+  const float wavg = mode == 1 ? 0.f : 0.5f / HW;
+  for (int r = 0; r < HW; ++r) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = g[j] * (wavg + (am[j] == r ? wmax : 0.f));
+    dx[(n * HW + r) * cvec + cv] = pack8(o);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ cross entropy
 // One block per row. loss_sum += -log softmax(logits[row])[target] / norm ; dlogits = (softmax - onehot) * gscale.
 // Rows whose target == ignore_index contribute nothing (torch.nn.CrossEntropyLoss semantics).
@@ -661,43 +699,14 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
 // Graph-replayable variants: lr and the step counter are read from device memory (the counter is advanced by
 // step_advance_kernel just before), and the consumed gradient is zeroed for the next step's atomic accumulation.
 __global__ void step_advance_kernel(int* step) { *step += 1; }
+// per-parameter Adam step counts: advance where the parameter is being optimised (lr multiplier != 0)
+__global__ void seg_steps_advance_kernel(int* steps, const float* lr_mult, const float* wd_mult, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(lr_mult[i] == 0.f && wd_mult[i] == 0.f)) steps[i] += 1;
+}
 
 // The *_dev kernels process 4 parameters per thread with 16-byte accesses (the arenas are 256-byte aligned and padded
 // to 64 elements); a scalar tail covers n % 4.
-struct SgdArgs {
-  float lr, mu, wd, damp, gscale;
-  int nesterov, first, zero_grad;
-};
-__device__ __forceinline__ float sgd_one(float w, float g, float* buf, const SgdArgs& a) {
-  float d = g * a.gscale + a.wd * w;
-  if (a.mu != 0.f) {
-    const float b = a.first ? d : a.mu * (*buf) + (1.f - a.damp) * d;
-    *buf = b;
-    d = a.nesterov ? d + a.mu * b : b;
-  }
-  return w - a.lr * d;
-}
-// paramwise_cfg (torchok/constructor/constructor.py:162-251): per-parameter lr / weight-decay multipliers, looked up by
-// the element offset in a sorted segment table (one segment per parameter of the arena); n == 0 means "all ones".
-struct ParamSegs {
-  const int* begin;
-  const float* lr_mult;
-  const float* wd_mult;
-  int n;
-};
-__device__ __forceinline__ void seg_lookup(const ParamSegs& s, long long elem, float& lr_mult, float& wd_mult) {
-  lr_mult = wd_mult = 1.f;
-  if (s.n == 0) return;
-  int lo = 0, hi = s.n - 1;   // largest k with begin[k] <= elem
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(s.begin + mid) <= elem) lo = mid;
-    else hi = mid - 1;
-  }
-  lr_mult = __ldg(s.lr_mult + lo);
-  wd_mult = __ldg(s.wd_mult + lo);
-}
-
 __global__ void __launch_bounds__(256)
 sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf,
                     __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
@@ -717,6 +726,10 @@ sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restr
       seg_lookup(segs, i << 2, lm, wm);
       a.lr = lr0 * lm;
       a.wd = wd * wm;
+      if (lm == 0.f && wm == 0.f) {   // frozen parameter: torch.optim skips it (momentum buffer untouched)
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
     }
     float4 w = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
@@ -737,6 +750,10 @@ sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restr
       seg_lookup(segs, i, lm, wm);
       a.lr = lr0 * lm;
       a.wd = wd * wm;
+      if (lm == 0.f && wm == 0.f) {
+        if (zero_grad) g[i] = 0.f;
+        continue;
+      }
     }
     float b = (mu != 0.f && !a.first) ? buf[i] : 0.f;
     const float w = sgd_one(p[i], g[i], &b, a);
@@ -745,22 +762,6 @@ sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restr
     if (zero_grad) g[i] = 0.f;
     if (shadow) shadow[i] = __float2bfloat16(w);
   }
-}
-struct AdamArgs {
-  float lr, b1, b2, eps, wd, gscale, step, rbc2;
-  int decoupled;
-};
-__device__ __forceinline__ float adam_one(float w, float g, float* m, float* v, const AdamArgs& a) {
-  float d = g * a.gscale;
-  if (a.decoupled)
-    w *= 1.f - a.lr * a.wd;
-  else
-    d += a.wd * w;
-  const float mi = a.b1 * (*m) + (1.f - a.b1) * d;
-  const float vi = a.b2 * (*v) + (1.f - a.b2) * d * d;
-  *m = mi;
-  *v = vi;
-  return w - a.step * mi / (sqrtf(vi) * a.rbc2 + a.eps);
 }
 __global__ void __launch_bounds__(256)
 adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -781,10 +782,20 @@ adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __rest
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
     if (segs.n) {
       float lm, wm;
-      seg_lookup(segs, i << 2, lm, wm);
+      const int sg = seg_lookup(segs, i << 2, lm, wm);
+      if (lm == 0.f && wm == 0.f) {   // frozen parameter: torch.optim.Adam skips it (exp_avg / exp_avg_sq / step untouched)
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
       a.lr = lr0 * lm;
-      a.step = a.lr / bc1;
       a.wd = wd * wm;
+      float c1 = bc1;
+      if (segs.steps) {
+        const float ts = (float)__ldg(segs.steps + sg);
+        c1 = 1.f - powf(b1, ts);
+        a.rbc2 = rsqrtf(1.f - powf(b2, ts));
+      }
+      a.step = a.lr / c1;
     }
     float4 w = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
@@ -803,10 +814,20 @@ adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __rest
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
     if (segs.n) {
       float lm, wm;
-      seg_lookup(segs, i, lm, wm);
+      const int sg = seg_lookup(segs, i, lm, wm);
+      if (lm == 0.f && wm == 0.f) {
+        if (zero_grad) g[i] = 0.f;
+        continue;
+      }
       a.lr = lr0 * lm;
-      a.step = a.lr / bc1;
       a.wd = wd * wm;
+      float c1 = bc1;
+      if (segs.steps) {
+        const float ts = (float)__ldg(segs.steps + sg);
+        c1 = 1.f - powf(b1, ts);
+        a.rbc2 = rsqrtf(1.f - powf(b2, ts));
+      }
+      a.step = a.lr / c1;
     }
     float mi = m[i], vi = v[i];
     const float w = adam_one(p[i], g[i], &mi, &vi, a);
@@ -967,6 +988,16 @@ int tok_gap_bwd(int n, int hw, int c, const void* dout, void* dx, void* stream) 
   return TOK_OK;
 }
 
+int tok_gap_bwd_max(int n, int hw, int c, int mode, const void* dout, const void* x, void* dx, void* stream) {
+  TOK_VEC_CHECK(c);
+  if (mode != 1 && mode != 2) return set_error(TOK_ERR_INVALID, "gap_bwd_max: mode must be 1 (max) or 2 (avgmax)");
+  const long long total = (long long)n * (c / 8);
+  gap_bwd_max_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (const uint4*)dout, (const uint4*)x, (uint4*)dx, n, hw, c / 8, mode);
+  TOK_CHECK_LAUNCH("gap_bwd_max");
+  return TOK_OK;
+}
+
 int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const long long* target, float* loss_sum,
                      void* dlogits, float inv_norm, float gscale, const float* gscale_dev, long long ignore_index,
                      int* correct, void* stream) {
@@ -1059,6 +1090,7 @@ int tok_adam_step(long long n, float* param, const float* grad, float* exp_avg, 
 }
 
 static int check_segs(ParamSegs* s, const int* begin, const float* lr_mult, const float* wd_mult, int n, const char* who) {
+  s->steps = nullptr;
   s->begin = begin;
   s->lr_mult = lr_mult;
   s->wd_mult = wd_mult;
@@ -1095,13 +1127,19 @@ int tok_sgd_step_dev(long long n, float* param, float* grad, float* momentum_buf
 int tok_adam_step_dev_groups(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq,
                              void* shadow_bf16, const float* lr_dev, int* step_dev, float beta1, float beta2, float eps,
                              float weight_decay, int decoupled, float grad_scale, int zero_grad, const int* seg_begin,
-                             const float* seg_lr_mult, const float* seg_wd_mult, int n_segs, void* stream) {
+                             const float* seg_lr_mult, const float* seg_wd_mult, int* seg_steps, int n_segs,
+                             void* stream) {
   if (n <= 0) return TOK_OK;
   if (!lr_dev || !step_dev) return set_error(TOK_ERR_INVALID, "adam_step_dev: lr_dev and step_dev are required");
   ParamSegs segs;
   int rc = check_segs(&segs, seg_begin, seg_lr_mult, seg_wd_mult, n_segs, "adam_step_dev_groups");
   if (rc) return rc;
   step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  if (seg_steps && n_segs > 0) {
+    seg_steps_advance_kernel<<<(n_segs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seg_steps, seg_lr_mult, seg_wd_mult,
+                                                                                   n_segs);
+    segs.steps = seg_steps;
+  }
   adam_step_dev_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
       param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr_dev, step_dev, beta1, beta2, eps,
       weight_decay, decoupled, grad_scale, zero_grad, segs);
@@ -1113,7 +1151,7 @@ int tok_adam_step_dev(long long n, float* param, float* grad, float* exp_avg, fl
                       const float* lr_dev, int* step_dev, float beta1, float beta2, float eps, float weight_decay,
                       int decoupled, float grad_scale, int zero_grad, void* stream) {
   return tok_adam_step_dev_groups(n, param, grad, exp_avg, exp_avg_sq, shadow_bf16, lr_dev, step_dev, beta1, beta2, eps,
-                                  weight_decay, decoupled, grad_scale, zero_grad, nullptr, nullptr, nullptr, 0, stream);
+                                  weight_decay, decoupled, grad_scale, zero_grad, nullptr, nullptr, nullptr, nullptr, 0, stream);
 }
 
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream) {

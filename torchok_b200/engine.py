@@ -26,7 +26,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import kernels as K
-from ._lib import lib
+from ._lib import lib, tokPeerArenas
 
 F32, BF16 = torch.float32, torch.bfloat16
 _ALIGN = 64  # elements; keeps every bf16 shadow 128-byte aligned for TMA
@@ -54,7 +54,9 @@ def plan_buckets(numels, bucket_mb=32.0, align=_ALIGN):
 
 
 class ParamArena:
-    def __init__(self, module, bucket_mb=32.0):
+    def __init__(self, module, bucket_mb=32.0, alloc=None):
+        """`alloc(numel, dtype) -> zero-filled flat CUDA tensor` lets the caller place the three arenas in memory it
+        owns (PeerExchange: CUDA-IPC allocations the other ranks can map); default: torch's caching allocator."""
         params, seen = [], set()
         for p in module.parameters():
             if p.requires_grad and id(p) not in seen:
@@ -73,9 +75,12 @@ class ParamArena:
             offs.append(total)
             total += _round_up(p.numel(), _ALIGN)
         self.params, self.offsets, self.numel = params, offs, total
-        self.master = torch.zeros(total, dtype=F32, device=dev)
-        self.grad = torch.zeros(total, dtype=F32, device=dev)
-        self.shadow = torch.zeros(total, dtype=BF16, device=dev)
+        if alloc is None:
+            def alloc(n, dtype):
+                return torch.zeros(n, dtype=dtype, device=dev)
+        self.master = alloc(total, F32)
+        self.grad = alloc(total, F32)
+        self.shadow = alloc(total, BF16)
         for p, off in zip(params, offs):
             shape, stride = tuple(p.shape), tuple(p.stride())
             view = torch.as_strided(self.master, shape, stride, off)
@@ -143,6 +148,98 @@ class BucketAllReduce:
         torch.cuda.current_stream().wait_stream(self.comm_stream)
 
 
+class _DevMem:
+    """A raw device allocation seen through the CUDA array interface (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+
+
+class PeerExchange:
+    """Gradient exchange over NVLink peer memory fused with the optimizer step (tok_peer_step, csrc/tok_comm.cu): per
+    gradient bucket ONE kernel per rank does reduce-scatter (peer loads) -> SGD / Adam(W) on the owned slice ->
+    all-gather of the new fp32 master + bf16 shadow values (peer stores).  Replaces DDP's all-reduce + optimizer.step
+    (`trainer.strategy: ddp`, torchok/constructor/config_structure.py:137-140).  torch.distributed is used only to
+    exchange the 64-byte IPC handles.  Plain kernel launches: the step stays CUDA-graph capturable at any world size."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        self.C, self.L = C, lib()
+        self.group, self.device = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError('PeerExchange covers one NVSwitch domain (<= 8 ranks)')
+        self._local, self._opened = [], []
+        self.comm_stream = torch.cuda.Stream()
+        self._first = True
+        self.table = None
+
+    def _alloc_raw(self, nbytes):
+        C = self.C
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        self.L.tok_ipc_alloc(C.c_size_t(nbytes), C.byref(ptr), handle)
+        self._local.append(ptr.value)
+        return ptr.value, handle.raw
+
+    def alloc(self, numel, dtype):
+        """Arena allocator handed to ParamArena: IPC-exportable, zero-filled."""
+        nbytes = _round_up(numel * torch.empty((), dtype=dtype).element_size(), 256)
+        ptr, handle = self._alloc_raw(nbytes)
+        t = torch.as_tensor(_DevMem(ptr, nbytes), device=self.device).view(dtype)[:numel]
+        assert t.data_ptr() == ptr
+        self._handles = getattr(self, '_handles', []) + [handle]
+        return t
+
+    def connect(self, arena):
+        """Exchange the handles of (master, grad, shadow, flags) and build the pointer table of tok_peer_step."""
+        C = self.C
+        fptr, fh = self._alloc_raw(int(self.L.tok_peer_flag_bytes()))
+        mine = self._handles[-3:] + [fh]
+        ptrs = [arena.master.data_ptr(), arena.grad.data_ptr(), arena.shadow.data_ptr(), fptr]
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        tab = tokPeerArenas()
+        tab.world, tab.rank = self.world, self.rank
+        for r in range(self.world):
+            for j, field in enumerate(('master', 'grad', 'shadow', 'flags')):
+                if r == self.rank:
+                    val = ptrs[j]
+                else:
+                    p = C.c_void_p()
+                    self.L.tok_ipc_open(everyone[r][j], C.byref(p))
+                    self._opened.append(p.value)
+                    val = p.value
+                getattr(tab, field)[r] = val
+        self.table, self.arena = tab, arena
+        arena.reducer = self
+        dist.barrier(group=self.group)
+
+    # -- reducer interface used by ParamArena.ready / finish ---------------------------------------------------------
+    def begin_step(self):
+        self._first = True
+
+    def launch(self, b):
+        begin, end, _ = self.arena.buckets[b]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            self.optimizer.peer_step(self.table, b, begin, end, self._first)
+        self._first = False
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def close(self):
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self._opened:
+            self.L.tok_ipc_close(p)
+        self._opened = []
+
+
 class _ArenaOptimizer:
     def __init__(self, arena, lr):
         self.arena = arena
@@ -164,12 +261,36 @@ class _ArenaOptimizer:
         dev = a.master.device
         self.segs = (torch.tensor(a.offsets, dtype=torch.int32, device=dev),
                      torch.tensor(lr_m, dtype=F32, device=dev), torch.tensor(wd_m, dtype=F32, device=dev))
+        # per-parameter step counts (torch.optim.Adam's state['step']): a parameter that has been optimised keeps its
+        # count while frozen; one that never was starts at 0, so its bias correction begins at 1 when it is thawed
+        if getattr(self, 'seg_steps', None) is None or self.seg_steps.numel() != len(a.params):
+            self.seg_steps = self.step_dev.expand(len(a.params)).clone()
 
     def _seg_args(self):
         if getattr(self, 'segs', None) is None:
             return None, None, None, 0
         b, l, w = self.segs
         return K._p(b), K._p(l), K._p(w), int(b.numel())
+
+    def _seg_args5(self):
+        b, l, w, n = self._seg_args()
+        return b, l, w, (K._p(self.seg_steps) if n else None), n
+
+    def _full_state(self, flat):
+        """Under the peer-fused exchange every rank holds the momentum / moment values of ITS slice of each bucket only
+        (ZeRO-1): assemble the full buffer with one all-reduce.  COLLECTIVE — every rank must call state_dict()."""
+        peer = getattr(a := self.arena, 'reducer', None)
+        if not isinstance(peer, PeerExchange):
+            return flat
+        full = torch.zeros_like(flat)
+        for begin, end, _ in a.buckets:
+            per = ((end - begin) // 4 + peer.world - 1) // peer.world * 4
+            lo = begin + per * peer.rank
+            hi = min(end, lo + per)
+            if hi > lo:
+                full[lo:hi] = flat[lo:hi]
+        dist.all_reduce(full, group=peer.group)
+        return full
 
     @property
     def lr(self):
@@ -200,9 +321,14 @@ class _ArenaOptimizer:
             flat = getattr(self, key, None)
             if flat is None:
                 continue
+            flat = self._full_state(flat)
             state[key] = {names[id(p)]: flat[off:off + p.numel()].detach().cpu().clone()
                           for p, off in zip(a.params, a.offsets) if id(p) in names}
-        return {'step': int(self.step_dev.item()), 'lr': self._lr, 'state': state}
+        out = {'step': int(self.step_dev.item()), 'lr': self._lr, 'state': state}
+        if getattr(self, 'segs', None) is not None and getattr(self, 'seg_steps', None) is not None:
+            steps = self.seg_steps.cpu().tolist()
+            out['param_steps'] = {names[id(p)]: int(t) for p, t in zip(a.params, steps) if id(p) in names}
+        return out
 
     def load_state_dict(self, state, module):
         a = self.arena
@@ -220,13 +346,18 @@ class _ArenaOptimizer:
                     flat[off:off + p.numel()].copy_(src.reshape(-1))
         self.step_dev.fill_(int(state.get('step', 0)))
         self.lr = state.get('lr', self._lr)
+        per = state.get('param_steps')
+        if getattr(self, 'seg_steps', None) is not None:
+            vals = [int((per or {}).get(names.get(id(p)), state.get('step', 0))) for p in a.params]
+            self.seg_steps.copy_(torch.tensor(vals, dtype=torch.int32))
 
 
 class ArenaSGD(_ArenaOptimizer):
     """torch.optim.SGD (registered in torchok/optim/optimizers/__init__.py:9-19) over the flat arena."""
 
-    def __init__(self, arena, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, **unused):
+    def __init__(self, arena, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, **other):
         super().__init__(arena, lr)
+        _check_optimizer_kwargs('SGD', other)
         self.momentum, self.dampening, self.weight_decay, self.nesterov = momentum, dampening, weight_decay, nesterov
         self.buf = torch.zeros_like(arena.master) if momentum != 0 else None
 
@@ -236,12 +367,19 @@ class ArenaSGD(_ArenaOptimizer):
                                       K._p(self.lr_dev), K._p(self.step_dev), self.momentum, self.weight_decay,
                                       self.dampening, int(self.nesterov), self.grad_scale, 1, *self._seg_args(), K._st())
 
+    def peer_step(self, table, bucket, begin, end, first):
+        import ctypes as C
+        lib().tok_peer_step(C.byref(table), bucket, begin, end, 0, K._p(self.buf), None, K._p(self.lr_dev),
+                            K._p(self.step_dev), self.momentum, self.weight_decay, self.dampening, 0.0,
+                            int(self.nesterov), self.grad_scale, *self._seg_args5(), int(first), K._st())
+
 
 class ArenaAdam(_ArenaOptimizer):
     """torch.optim.Adam / AdamW (amsgrad off) over the flat arena."""
 
-    def __init__(self, arena, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, **unused):
+    def __init__(self, arena, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, **other):
         super().__init__(arena, lr)
+        _check_optimizer_kwargs('Adam', other)
         self.betas, self.eps, self.weight_decay, self.decoupled = tuple(betas), eps, weight_decay, decoupled
         self.exp_avg = torch.zeros_like(arena.master)
         self.exp_avg_sq = torch.zeros_like(arena.master)
@@ -251,7 +389,25 @@ class ArenaAdam(_ArenaOptimizer):
         lib().tok_adam_step_dev_groups(a.numel, K._p(a.master), K._p(a.grad), K._p(self.exp_avg),
                                        K._p(self.exp_avg_sq), K._p(a.shadow), K._p(self.lr_dev), K._p(self.step_dev),
                                        self.betas[0], self.betas[1], self.eps, self.weight_decay, int(self.decoupled),
-                                       self.grad_scale, 1, *self._seg_args(), K._st())
+                                       self.grad_scale, 1, *self._seg_args5(), K._st())
+
+    def peer_step(self, table, bucket, begin, end, first):
+        import ctypes as C
+        lib().tok_peer_step(C.byref(table), bucket, begin, end, 1, K._p(self.exp_avg), K._p(self.exp_avg_sq),
+                            K._p(self.lr_dev), K._p(self.step_dev), self.betas[0], self.betas[1], self.eps,
+                            self.weight_decay, int(self.decoupled), self.grad_scale, *self._seg_args5(), int(first),
+                            K._st())
+
+
+_NOOP_OPT_KEYS = ('foreach', 'fused', 'capturable', 'differentiable')
+
+
+def _check_optimizer_kwargs(name, other):
+    """torch.optim keys the arena kernels do not implement must not be dropped silently (they change the arithmetic)."""
+    for k, v in other.items():
+        if k in _NOOP_OPT_KEYS or (k in ('amsgrad', 'maximize') and not v):
+            continue
+        raise NotImplementedError(f'{name}: optimizer parameter {k}={v!r} is not implemented by the arena step kernels')
 
 
 def build_optimizer(arena, name, params, module=None, paramwise_cfg=None):
@@ -294,12 +450,35 @@ class StreamLoop:
             if opt_cfg is None:
                 raise ValueError('StreamLoop needs an optimizer (argument or hparams.optimization[0].optimizer)')
             optimizer = opt_cfg['optimizer']
-        self.arena = ParamArena(task, bucket_mb=bucket_mb)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        # gradient exchange: 'none' (one GPU), 'peer-fused' (NVLink peer memory + optimizer in one kernel per bucket,
+        # the default for 2..8 ranks), 'nccl' (torch.distributed all-reduce per bucket, then the arena optimizer;
+        # TOK_DDP=nccl or when CUDA IPC / peer access is unavailable)
+        self.exchange, self.peer = 'none', None
+        if self.world > 1:
+            self.exchange = 'nccl'
+            if os.environ.get('TOK_DDP', 'peer') == 'peer' and self.world <= 8 and dist.get_backend() == 'nccl':
+                try:
+                    self.peer = PeerExchange(self.device)
+                    self.arena = ParamArena(task, bucket_mb=bucket_mb, alloc=self.peer.alloc)
+                    self.peer.connect(self.arena)
+                    self.exchange = 'peer-fused'
+                except Exception as e:   # no IPC in this container / no peer access: say so and use NCCL
+                    import warnings
+                    warnings.warn(f'torchok_b200: peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); '
+                                  f'using the NCCL all-reduce path')
+                    if self.peer is not None and getattr(self, 'arena', None) is not None:
+                        raise   # arenas already re-homed into IPC memory: do not continue half-configured
+                    self.peer = None
+        if self.peer is None:
+            self.arena = ParamArena(task, bucket_mb=bucket_mb)
         self.optimizer = build_optimizer(self.arena, optimizer['name'], optimizer.get('params'), task,
                                          optimizer.get('paramwise_cfg'))
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if self.world > 1:
-            BucketAllReduce(self.arena)
+            if self.peer is not None:
+                self.peer.optimizer = self.optimizer
+            else:
+                BucketAllReduce(self.arena)
             self.optimizer.grad_scale = 1.0 / self.world
             with torch.no_grad():  # replicas start from rank 0's weights (DDP's initial broadcast)
                 dist.broadcast(self.arena.master, 0)
@@ -308,11 +487,10 @@ class StreamLoop:
                         dist.broadcast(b, 0)
             self.arena.refresh_shadow()
         self.use_graph = use_graph and os.environ.get('TOK_NO_GRAPH', '0') != '1'
-        if self.world > 1 and os.environ.get('TOK_GRAPH_DDP', '0') != '1':
-            # Graph capture of the NCCL all-reduce works on 2xB200 with capture_error_mode='thread_local' and
-            # TORCH_NCCL_ASYNC_ERROR_HANDLING=0 (21.6 ms/step vs 22.5 eager) but is opt-in (TOK_GRAPH_DDP=1) until it
-            # has been validated at 4 and 8 ranks: with the default 'global' mode the capture hung, and a hang costs a
-            # whole scaling run where the eager loop costs ~4 %.
+        if self.exchange == 'nccl' and os.environ.get('TOK_GRAPH_DDP', '0') != '1':
+            # Capturing torch.distributed's NCCL all-reduce needs capture_error_mode='thread_local' and
+            # TORCH_NCCL_ASYNC_ERROR_HANDLING=0; validated at 2 ranks only, so it stays opt-in (TOK_GRAPH_DDP=1).  The
+            # default peer-fused exchange is plain kernel launches and is always captured.
             self.use_graph = False
         self.warmup = warmup
         self.graph = None
@@ -327,11 +505,20 @@ class StreamLoop:
     # ------------------------------------------------------------------------------------------------------------
     def _eager_step(self, batch):
         self.arena.begin_step()
+        if self.peer is not None:
+            self.peer.begin_step()
         out = self.task.training_step(batch)
         out['loss'].backward()
         self.arena.finish()
-        self.optimizer.step()
+        if self.peer is None:      # peer-fused: the optimizer ran inside the exchange kernels, bucket by bucket
+            self.optimizer.step()
         return out
+
+    def close(self):
+        """Release the peer mappings (all ranks together); the loop must not be used afterwards."""
+        if self.peer is not None:
+            self.graph = None
+            self.peer.close()
 
     def _stage(self, batch):
         """Copy a batch (pinned host or device tensors) into the static device buffers the graph reads."""
@@ -401,8 +588,8 @@ class StreamLoop:
     def _state_tensors(self):
         opt = self.optimizer
         ts = [self.arena.master, self.arena.grad, opt.step_dev]
-        ts += [t for t in (getattr(opt, 'buf', None), getattr(opt, 'exp_avg', None), getattr(opt, 'exp_avg_sq', None))
-               if t is not None]
+        ts += [t for t in (getattr(opt, 'buf', None), getattr(opt, 'exp_avg', None), getattr(opt, 'exp_avg_sq', None),
+                           getattr(opt, 'seg_steps', None)) if t is not None]
         ts += [b for b in self.task.buffers() if b.is_cuda]
         return ts
 

@@ -408,15 +408,17 @@ class GlobalPoolFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         n, c, h, w, cp, mode = ctx.meta
-        if mode != 'avg':
-            raise NotImplementedError("backward of pooling_type 'max'/'avgmax' is not implemented")
         if cp != c:
             gp = torch.zeros((n, cp), dtype=BF16, device=g.device)
             gp[:, :c] = g
             g = gp
         g = g.to(BF16).contiguous()
         dx = torch.empty((n, h, w, cp), dtype=BF16, device=g.device)
-        lib().tok_gap_bwd(n, h * w, cp, _p(g), _p(dx), _st())
+        if mode == 'avg':
+            lib().tok_gap_bwd(n, h * w, cp, _p(g), _p(dx), _st())
+        else:
+            x, _ = ctx.saved_tensors
+            lib().tok_gap_bwd_max(n, h * w, cp, POOL_MODES[mode], _p(g), _p(x), _p(dx), _st())
         o = dx.permute(0, 3, 1, 2)
         return (o if cp == c else o[:, :c]), None
 

@@ -211,10 +211,24 @@ class JaccardIndex(_ConfusionMetric):
 
     def compute(self):
         cm, tp, fp, fn = self._stats()
+        denom = tp + fp + fn
+        # torchmetrics 0.11.4 `_jaccard_index_reduce(confmat, average, ignore_index)`: an IN-RANGE ignore_index (e.g.
+        # `num_classes: 3, ignore_index: 0` of examples/configs/segmentation_sweet_pepper.yaml) is taken out of the
+        # score: its denominator is subtracted for 'micro', its weight is zero for 'macro'
+        ign = self.ignore_index if (self.ignore_index is not None and 0 <= self.ignore_index < self.num_classes) else None
         if self.average == 'micro':
-            return self._safe_div(tp.sum(), (tp + fp + fn).sum()).float()
-        # torchmetrics 0.11.4 `_jaccard_index_reduce`: macro weights are one for every class (absent ones score 0)
-        return self._reduce_scores(self._safe_div(tp, tp + fp + fn), tp, fp, fn, skip_absent=False)
+            total = denom.sum() - (denom[ign] if ign is not None else 0.0)
+            return self._safe_div(tp.sum(), total).float()
+        score = self._safe_div(tp, denom)
+        if self.average in (None, 'none'):
+            return score.float()
+        if self.average == 'weighted':
+            w = tp + fn
+        else:   # macro: weight one for every class (absent ones score 0), zero for the ignored class
+            w = torch.ones_like(score)
+            if ign is not None:
+                w[ign] = 0.0
+        return self._safe_div(w * score, w.sum()).sum().float()
 
 
 # ---------------------------------------------------------------------------------------------- the manager

@@ -173,19 +173,27 @@ class Runner:
 
     # ------------------------------------------------------------------------------------------------ checkpoints
     def save_checkpoint(self, path, weights_only=False):
+        # the optimizer state is sharded over the ranks under the peer-fused gradient exchange: gathering it is collective
+        opt_state = self.loop.optimizer.state_dict(self.task) if (not weights_only and self.loop is not None) else None
         if self.rank != 0:
             return
         ckpt = {'state_dict': {k: v.detach().cpu() for k, v in self.task.state_dict().items()},
                 'epoch': self.current_epoch, 'global_step': self.global_step,
                 'torchok_b200': True, 'hyper_parameters': self.cfg.to_dict()}
         if not weights_only and self.loop is not None:
-            ckpt['optimizer_states'] = [self.loop.optimizer.state_dict(self.task)]
+            ckpt['optimizer_states'] = [opt_state]
             ckpt['lr_schedulers'] = [self.scheduler.state_dict()] if self.scheduler else []
-            ckpt['callbacks'] = {type(c).__name__: c.state_dict() for c in self.callbacks}
+            ckpt['callbacks'] = {self._callback_key(i, c): c.state_dict() for i, c in enumerate(self.callbacks)}
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         tmp = f'{path}.tmp'
         torch.save(ckpt, tmp)
         os.replace(tmp, path)
+
+    def _callback_key(self, index, c):
+        ident = {k: getattr(c, k) for k in ('monitor', 'mode', 'every_n_epochs', 'save_top_k') if hasattr(c, k)}
+        same = [x for x in self.callbacks if type(x) is type(c)]
+        suffix = f'#{same.index(c)}' if len(same) > 1 else ''
+        return f'{type(c).__name__}{ident}{suffix}'
 
     def remove_checkpoint(self, path):
         if self.rank == 0 and os.path.exists(path):
@@ -202,8 +210,11 @@ class Runner:
             self.loop.optimizer.load_state_dict(ckpt['optimizer_states'][0], self.task)
         if ckpt.get('lr_schedulers') and self.scheduler is not None and ckpt.get('torchok_b200'):
             self.scheduler.load_state_dict(ckpt['lr_schedulers'][0])
-        for c in self.callbacks:
-            state = (ckpt.get('callbacks') or {}).get(type(c).__name__)
+        saved = ckpt.get('callbacks') or {}
+        for i, c in enumerate(self.callbacks):
+            # keyed like Lightning's state_key: class name + the parameters that tell two instances apart (two
+            # ModelCheckpoints monitoring different metrics); older checkpoints used the bare class name
+            state = saved.get(self._callback_key(i, c), saved.get(type(c).__name__))
             if state and ckpt.get('torchok_b200'):
                 c.load_state_dict(state)
         self.current_epoch = int(ckpt.get('epoch', -1)) + 1       # the stored epoch was completed
