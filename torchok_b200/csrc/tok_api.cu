@@ -127,16 +127,28 @@ static int pick_bn(int n) { return n <= 64 ? 64 : 128; }
 
 // Persistent kernel: a 128x256 tile halves the L2->SM operand traffic per FLOP (the 128x128 tile is L2-bandwidth
 // bound at ~1/3 of the tensor peak); it is chosen when it does not cost wave-quantisation efficiency on 148 SMs.
-static int pick_bn_persist(long long M, int N, long long k_total) {
+static int pick_bn_persist(long long M, int N, long long k_total, bool gather_a) {
   if (N <= 64) return 64;
   const int forced = getenv("TOK_CONV_BN") ? atoi(getenv("TOK_CONV_BN")) : 0;
   if (forced == 128 || (forced == 256 && N > 128)) return forced;
   if (N <= 128) return 128;
   // Short reductions are bound by the epilogue / HBM, not by the tensor pipe: the 128x128 tile double-buffers its
-  // staging (and addend) tiles so stores drain behind the next tile, which the 128x256 tile has no room for.
+  // staging (and addend) tiles so stores drain behind the next tile, which the 128x256 tile has no room for.  Exception:
+  // a strided (im2col-gathered) A operand is expensive to fetch, and the wider tile fetches it half as often
+  // (measured r2, 1x1 s2 256->512 @56: 91 us vs 109 us).
   static const long long small_k = getenv("TOK_CONV_SMALLK") ? atoll(getenv("TOK_CONV_SMALLK")) : 512;
-  if (k_total <= small_k) return 128;
+  if (k_total < small_k && !gather_a) return 128;
+  // Waves of the persistent grid x relative tile time.  A 128x256 tile moves 1.5x the operand bytes of a 128x128 tile for
+  // 2x the MACs and measures ~1.25x its time on the long reductions (r2 selftest: 3x3 512->512 @7, 196 tiles in 2 waves
+  // = 69 us against 392 tiles in 3 waves = 95 us).
   const long long m_tiles = (M + 127) / 128;
+  auto cost = [&](int bn) {
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long long waves = (tiles + 147) / 148;
+    return (double)waves * (bn == 256 ? 1.25 : 1.0);
+  };
+  if (N % 256 == 0) return cost(256) <= cost(128) ? 256 : 128;
+  // ragged N: the padded half tile of the wide configuration is pure waste — keep the r1 efficiency rule
   auto eff = [&](int bn) {
     const long long tiles = m_tiles * ((N + bn - 1) / bn);
     const long long waves = (tiles + 147) / 148;
@@ -152,7 +164,7 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
                       cudaStream_t st) {
   CUtensorMap tmB;
   static const bool v1 = getenv("TOK_CONV_V1") != nullptr;  // bring-up aid: the one-tile-per-CTA kernel
-  const int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N, (long long)src.R * src.S * ac);
+  const int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N, (long long)src.R * src.S * ac, src.im2col && src.R * src.S == 1);
   // Opt-in CTA-pair kernel (unverified on hardware as a conv; the default path is untouched unless the variable is
   // set): a 256x256 tile per pair of SMs, each CTA fetches half of the weight tile, hence the 128-row boxes.
   static const bool pair_env = getenv("TOK_CONV_2CTA") != nullptr;

@@ -72,6 +72,33 @@ __device__ __forceinline__ Map make_map(long long rows, int cvec, int cvec_b, in
   return m;
 }
 
+// Second half of the CTA reduction of the backward sums: part[thread][16] (8 x sum g, 8 x sum g*y per 8-channel vector)
+// -> one thread per (channel vector, group of four values) adds the row lanes up and issues ONE 16-byte vector
+// reduction.  r1 used one scalar atomicAdd per value and ~570 CTAs per channel: with up to 4096 scalar atomics per CTA
+// on the same addresses the L2 atomic units serialised them into a 13-40 us tail per launch (profiles/r2: 55 us for
+// a 2048 x 7x7 tail whose traffic needs 16 us); now a channel is shared by at most ~37-148 CTAs (plan(): 16 vectors per
+// column block) and every request carries four values.
+__device__ __forceinline__ void cta_reduce_red4(const float* part, int cvec, int cvec_b, float* sum_g, float* sum_gy) {
+  const int rlanes = 256 / cvec_b;
+  for (int o = threadIdx.x; o < cvec_b * 4; o += 256) {
+    const int cl = o >> 2, k0 = (o & 3) * 4;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int rl = 0; rl < rlanes; ++rl) {
+      const float* q = part + (rl * cvec_b + cl) * 16 + k0;
+      t0 += q[0];
+      t1 += q[1];
+      t2 += q[2];
+      t3 += q[3];
+    }
+    const int cv = blockIdx.y * cvec_b + cl;
+    if (cv < cvec) {
+      float* dst = (k0 < 8 ? sum_g : sum_gy) + cv * 8 + (k0 & 7);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t0), "f"(t1), "f"(t2), "f"(t3)
+                   : "memory");
+    }
+  }
+}
+
 template <int MASK>
 __device__ __forceinline__ void apply_mask(float (&g)[8], const float (&yy)[8], const float (&sc)[8],
                                            const float (&sf)[8], uint32_t bits) {
@@ -217,14 +244,7 @@ bn_bwd_reduce2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ 
     mine[8 + j] = a2[j];
   }
   __syncthreads();
-  const int rlanes = 256 / cvec_b;
-  for (int o = threadIdx.x; o < cvec_b * 16; o += 256) {
-    float t = 0.f;
-    for (int rl = 0; rl < rlanes; ++rl) t += part[rl * cvec_b * 16 + o];
-    const int cl = o >> 4, k = o & 15;
-    const int c = (blockIdx.y * cvec_b + cl) * 8 + (k & 7);
-    if (c < cvec * 8) atomicAdd((k < 8 ? sum_g : sum_gy) + c, t);
-  }
+  cta_reduce_red4(part, cvec, cvec_b, sum_g, sum_gy);
   if (fin.counter != nullptr) {
     __threadfence();   // this CTA's contributions are ordered before its ticket
     __syncthreads();
@@ -484,14 +504,7 @@ stem_bwd_kernel(const uint4* __restrict__ dpooled, const uint2* __restrict__ arg
       mine[8 + j] = a2[j];
     }
     __syncthreads();
-    const int rlanes = 256 / cvec_b;
-    for (int o = threadIdx.x; o < cvec_b * 16; o += 256) {
-      float t = 0.f;
-      for (int rl = 0; rl < rlanes; ++rl) t += part[rl * cvec_b * 16 + o];
-      const int cl = o >> 4, k = o & 15;
-      const int c = (blockIdx.y * cvec_b + cl) * 8 + (k & 7);
-      if (c < cvec * 8) atomicAdd((k < 8 ? sum_g : sum_gy) + c, t);
-    }
+    cta_reduce_red4(part, cvec, cvec_b, sum_g, sum_gy);
   }
 }
 
@@ -499,10 +512,10 @@ struct Grid2 {
   dim3 grid;
   int cvec, cvec_b, rows_per_cta;
 };
-Grid2 plan(long long rows, int C, int ctas_per_sm) {
+Grid2 plan(long long rows, int C, int ctas_per_sm, int max_cvec_b = 256) {
   Grid2 g;
   g.cvec = C / 8;
-  g.cvec_b = g.cvec < 256 ? g.cvec : 256;
+  g.cvec_b = g.cvec < max_cvec_b ? g.cvec : max_cvec_b;
   const int gy = (g.cvec + g.cvec_b - 1) / g.cvec_b;
   const int rlanes = 256 / g.cvec_b;
   long long ctas = 148LL * ctas_per_sm / gy;
@@ -604,7 +617,7 @@ static int launch_bwd_reduce2(long long rows, int C, const void* dout, const voi
   if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: no rows");
   if (mask_mode < 0 || mask_mode > 2 || (mask_mode == MASK_BITS && !bits) || (mask_mode == MASK_Y && (!scale || !shift)))
     return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: mask_mode %d needs its operands", mask_mode);
-  const Grid2 g = plan(rows, C, 4);
+  const Grid2 g = plan(rows, C, 4, 16);
   cudaStream_t st = (cudaStream_t)stream;
 #define K_REDUCE(M, H2)                                                                                        \
   bn_bwd_reduce2_kernel<M, H2><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y, \

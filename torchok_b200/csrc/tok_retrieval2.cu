@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "tok_pair.cuh"
+#include "tok_topk.cuh"
 
 namespace tok {
 namespace {
@@ -137,31 +138,17 @@ cosine_topk_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const int buf = t & 1;
       mbar_wait(&tmem_full_bar[buf], (t >> 1) & 1);
       tc_fence_after();
+      // two 32-column TMEM loads in flight per wait; each chunk is folded by a max tree + one compare (tok_topk.cuh)
 #pragma unroll 1
-      for (int c = 0; c < kGPair / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + buf * kGPair + c * 32, r);
+      for (int c = 0; c < kGPair / 32; c += 2) {
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + buf * kGPair + c * 32;
+        tmem_ld_32x32b_x32(taddr, r0);
+        tmem_ld_32x32b_x32(taddr + 32, r1);
         tmem_ld_wait();
         const int col0 = t * kGPair + c * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          float s = __uint_as_float(r[j]);
-          if (g_sqnorm != nullptr) s = 2.f * s - (col < ng ? __ldg(g_sqnorm + col) : 0.f);  // L2: rank by -(|g|^2 - 2qg)
-          if (col < ng && s > val[KP - 1]) {
-#pragma unroll
-            for (int u = KP - 1; u >= 1; --u) {
-              const bool above = s > val[u - 1];
-              const bool here = !above && s > val[u];
-              val[u] = above ? val[u - 1] : (here ? s : val[u]);
-              id[u] = above ? id[u - 1] : (here ? col : id[u]);
-            }
-            if (s > val[0]) {
-              val[0] = s;
-              id[0] = col;
-            }
-          }
-        }
+        if (col0 < ng) topk_fold_chunk<KP>(val, id, r0, col0, ng, g_sqnorm);
+        if (col0 + 32 < ng) topk_fold_chunk<KP>(val, id, r1, col0 + 32, ng, g_sqnorm);
       }
       tc_fence_before();
       __syncwarp();

@@ -440,7 +440,7 @@ class StreamLoop:
     With torch.distributed initialised (NCCL), gradients are averaged over ranks bucket by bucket.
     """
 
-    def __init__(self, task, optimizer=None, use_graph=True, bucket_mb=32.0, warmup=3):
+    def __init__(self, task, optimizer=None, use_graph=True, bucket_mb=32.0, warmup=3, distributed=True):
         self.task = task
         self.device = next(task.parameters()).device
         K.require_cuda(next(task.parameters()), 'task')
@@ -450,7 +450,7 @@ class StreamLoop:
             if opt_cfg is None:
                 raise ValueError('StreamLoop needs an optimizer (argument or hparams.optimization[0].optimizer)')
             optimizer = opt_cfg['optimizer']
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size() if distributed and dist.is_available() and dist.is_initialized() else 1
         # gradient exchange: 'none' (one GPU), 'peer-fused' (NVLink peer memory + optimizer in one kernel per bucket,
         # the default for 2..8 ranks), 'nccl' (torch.distributed all-reduce per bucket, then the arena optimizer;
         # TOK_DDP=nccl or when CUDA IPC / peer access is unavailable)
