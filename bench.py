@@ -344,7 +344,7 @@ def _call_work(name, a):
         return 'gelu', 0.0, 6.0 * a[0]
     if name in ('tok_window_attn_fwd', 'tok_window_attn_bwd'):
         # (batch, h, w, heads, window, shift, head_dim): 4 N^2 d fwd / 10 N^2 d bwd per (window, head)
-        b, h, w, heads, ws = a[0], a[1], a[2], a[3], a[4]
+        b, h, w, heads, ws = a[0], a[1], a[2], a[4], a[5]      # (B, H, W, C, heads, window, shift, ...)
         nwin = b * (h // ws) * (w // ws)
         n2 = (ws * ws) ** 2
         f = (4.0 if name.endswith('fwd') else 10.0) * n2 * 32 * nwin * heads
@@ -437,6 +437,7 @@ def _init_dist(dev):
         os.environ.setdefault('NCCL_IB_DISABLE', '1')      # NVLink only (north_star)
         os.environ.setdefault('NCCL_P2P_LEVEL', 'NVL')
         os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')
+        os.environ['NCCL_DEBUG'] = os.environ.get('TOK_NCCL_DEBUG', 'NONE')   # NCCL prints its version banner to STDOUT at VERSION and above
         dist.init_process_group('nccl', device_id=dev)
         _trace('process group up')
     return world

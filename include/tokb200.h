@@ -339,6 +339,33 @@ int tok_adam_step_dev_groups(long long n, float* param, float* grad, float* exp_
  * reference.  Segments with lr_mult == wd_mult == 0 (frozen) are skipped entirely by both step kernels. */
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream);
 
+/* ---- object-context head and U-Net decoder glue ----------------------------------------------------
+ * nearest-neighbour resize written into a channel slice of a padded NHWC concat buffer: F.interpolate(mode='nearest') +
+ * torch.cat of DecoderBlock.forward (torchok/models/necks/segmentation/unet.py:40-58); same argument meaning as
+ * tok_bilinear_fwd / _bwd. */
+int tok_nearest_fwd(int n, int hi, int wi, int c, int ho, int wo, const void* src, void* dst, int dst_c,
+                    int dst_c_offset, void* stream);
+int tok_nearest_bwd(int n, int hi, int wi, int c, int ho, int wo, const void* dout, int dout_c, int dout_c_offset,
+                    void* dsrc, void* stream);
+/* out[n, :, c] = x[n, :, c] * scale[n][c]: nn.Dropout2d (ocr.py:126) with the mask drawn by the caller. */
+int tok_channel_scale(int n, long long hw, int c, const void* x, const float* scale, void* out, void* stream);
+/* SpatialGather_Module.forward (torchok/models/heads/segmentation/ocr.py:37-46): p = softmax over the hw positions of
+ * every class map (logits [b][hw][kp] bf16, k <= kp classes); ctx[b][k][c] = sum_hw p * feats[b][hw][c].
+ * stats [b][k][2] fp32 (max, sum of exp) is kept for the backward; ctx_f32 [b][k][c] is fp32 scratch. */
+int tok_spatial_gather_fwd(int b, int hw, int c, int k, int kp, const void* feats, const void* logits, float* stats,
+                           float* ctx_f32, void* ctx, void* stream);
+int tok_spatial_gather_bwd(int b, int hw, int c, int k, int kp, const void* feats, const void* logits,
+                           const float* stats, const void* ctx, const void* dctx, void* dfeats, void* dlogits,
+                           void* stream);
+/* ObjectAttentionBlock.forward at scale 1 (ocr.py:77-101): out[b][hw][:] = softmax_k(scale * q[b][hw] . key[b][k]) .
+ * value[b][k][:]; q / out [b][hw][kc], key / value [b][k][kc], all bf16.  The backward returns dq and, through fp32
+ * scratch, dkey / dvalue. */
+int tok_object_attn_fwd(int b, int hw, int kc, int k, float scale, const void* q, const void* key, const void* value,
+                        void* out, void* stream);
+int tok_object_attn_bwd(int b, int hw, int kc, int k, float scale, const void* q, const void* key, const void* value,
+                        const void* dout, void* dq, float* dkey_f32, float* dvalue_f32, void* dkey, void* dvalue,
+                        void* stream);
+
 /* ---- data-parallel gradient exchange over NVLink / NVSwitch PEER MEMORY, fused with the optimizer --------------------
  * Replaces Lightning's DDP gradient all-reduce + optimizer.step (`trainer.strategy: ddp`,
  * torchok/constructor/config_structure.py:137-140; examples/configs/classification_imagenet.yaml:121-122).  One process

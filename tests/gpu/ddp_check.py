@@ -43,9 +43,9 @@ def check_step(mode):
     import torchok_b200 as tb
     from torchok_b200.engine import StreamLoop
     opt = {'name': 'SGD', 'params': {'lr': 0.1, 'momentum': 0.9, 'weight_decay': 1e-4}}
-    per = 16
+    per = 32
     g = torch.Generator().manual_seed(123)
-    x = torch.randn(world * per, 3, 32, 32, generator=g).to(torch.bfloat16).float()
+    x = torch.randn(world * per, 3, 64, 64, generator=g).to(torch.bfloat16).float()
     y = torch.randint(0, 10, (world * per,), generator=g)
     shard = lambda r: {'image': x[r * per:(r + 1) * per].to(dev), 'target': y[r * per:(r + 1) * per].to(dev)}  # noqa: E731
 
@@ -65,6 +65,15 @@ def check_step(mode):
         torch.cuda.synchronize()
         grads.append(ref.arena.grad.clone())
     gmean = sum(grads) / world
+    # noise floor of the comparison: the same shard twice on this GPU (BatchNorm statistics and weight gradients are
+    # accumulated with fp32 atomics, so two runs differ by summation order and the occasional bf16 rounding it flips)
+    for b, s in zip(ref_task.buffers(), state0):
+        b.copy_(s)
+    ref.arena.zero_grad()
+    ref.arena.begin_step()
+    ref_task.training_step(shard(world - 1))['loss'].backward()
+    torch.cuda.synchronize()
+    noise = float((ref.arena.grad - grads[-1]).norm() / grads[-1].norm())
     d = gmean + 1e-4 * w0
     expected1 = w0 - 0.1 * d                                  # first step: momentum buffer = d
     # the N-rank loop
@@ -89,7 +98,8 @@ def check_step(mode):
     grads_cleared = float(loop.arena.grad.abs().max()) == 0.0
     print(f'[rank {rank}] {mode}: loss {float(loss):.4f} update vs expectation: max {err:.3e}, l2 {upd:.3e} '
           f'replicas identical: {same} shadow == bf16(master): {shadow_ok} grads cleared: {grads_cleared}', flush=True)
-    assert err < 5e-2 and upd < 1e-2, (err, upd)
+    print(f'[rank {rank}] run-to-run noise of one shard gradient (l2): {noise:.3e}', flush=True)
+    assert upd < max(1e-2, 4 * noise) and err < max(5e-2, 20 * noise), (err, upd, noise)
     assert same and shadow_ok and grads_cleared
     # graph replay at world size > 1 (peer path: plain kernel launches): three more steps stay finite and identical
     if mode == 'peer':

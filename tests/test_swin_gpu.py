@@ -118,7 +118,11 @@ def test_patch_merge_is_the_reference_cat():
 
 
 @pytest.mark.parametrize('dim,heads,res,ws,shift', [(96, 3, 8, 4, 0), (96, 3, 8, 4, 2), (64, 2, 14, 7, 3), (192, 6, 8, 8, 0),
-                                                    (128, 4, 16, 8, 4)])
+                                                    (128, 4, 16, 8, 4),
+                                                    # windows above 8x8 (large-window kernels): 12 / 16 / 24, with and
+                                                    # without the cyclic shift
+                                                    (96, 3, 24, 12, 6), (96, 3, 16, 16, 0), (64, 2, 32, 16, 8),
+                                                    (64, 2, 24, 24, 0), (32, 1, 48, 24, 12)])
 def test_swin_block_forward_backward(dim, heads, res, ws, shift):
     """timm SwinTransformerBlock: attention (bias, logit scale, shift mask), res-post-norm, MLP — every gradient."""
     from oracle import swin as osw
@@ -219,3 +223,34 @@ def test_swin_classification_task_step():
     missing = [n for n, p in task.named_parameters() if p.grad is None and 'feature_norms' not in n]
     assert not missing, missing
     assert task.backbone.feature_norms[3].weight.grad is not None
+
+
+def test_swinv2_tiny_window16_256_is_the_references_own_test_model():
+    """tests/additional_tests/models/backbones/test_backbone.py:161-182 of the reference builds
+    `swinv2_tiny_window16_256` at 256 x 256 and checks the output / feature shapes; here additionally parity of the four
+    feature maps with the oracle (windows of 16 x 16 = 256 tokens in stages 1-2, 16 and 8 in stages 3-4)."""
+    import torchok_b200 as tb
+    from oracle import models as om
+    from oracle import swin as osw
+    torch.manual_seed(0)
+    o = osw.SwinTransformerV2(img_size=256, window_size=16)
+    osw.dedegenerate_ln_(o, 0)
+    m = tb.BACKBONES.get('swinv2_tiny_window16_256')(pretrained=False, drop_path_rate=0.0)
+    m.load_state_dict(o.state_dict())
+    m.cuda().eval()
+    o.eval()
+    o16 = copy.deepcopy(o)
+    x = torch.randn(2, 3, 256, 256)
+    with torch.no_grad():
+        fo = o.forward_features(x)
+        with om.amp_bf16():
+            fa = o16.forward_features(x)
+        fm = m.forward_features(x.cuda())
+        last = m(x.cuda())
+    assert tuple(last.shape) == (2, 768, 8, 8)
+    assert [tuple(f.shape) for f in fm] == [(2, 3, 256, 256), (2, 96, 64, 64), (2, 192, 32, 32), (2, 384, 16, 16),
+                                            (2, 768, 8, 8)]
+    for i, (a, b_, c) in enumerate(zip(fm[1:], fo[1:], fa[1:])):
+        e, e_amp = rel_err(a, b_), rel_err(c, b_)
+        print(f'swinv2_tiny_window16_256 stage {i}: gpu-vs-fp32 {e:.4f} | oracle-amp-vs-fp32 {e_amp:.4f}')
+        assert e < 1.5 * e_amp + 5e-3, (i, e, e_amp)

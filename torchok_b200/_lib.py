@@ -119,6 +119,13 @@ _SIGS = {
     'tok_sgd_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _i, _vp]),
     'tok_adam_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _vp,
                                       _i, _vp]),
+    'tok_nearest_fwd': (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    'tok_nearest_bwd': (_i, [_i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    'tok_channel_scale': (_i, [_i, _ll, _i, _vp, _vp, _vp, _vp]),
+    'tok_spatial_gather_fwd': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_spatial_gather_bwd': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_object_attn_fwd': (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    'tok_object_attn_bwd': (_i, [_i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_ipc_alloc': (_i, [_sz, C.POINTER(C.c_void_p), _vp]),
     'tok_ipc_free': (_i, [_vp]),
     'tok_ipc_open': (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),

@@ -617,12 +617,21 @@ static int launch_bwd_reduce2(long long rows, int C, const void* dout, const voi
   if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: no rows");
   if (mask_mode < 0 || mask_mode > 2 || (mask_mode == MASK_BITS && !bits) || (mask_mode == MASK_Y && (!scale || !shift)))
     return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2: mask_mode %d needs its operands", mask_mode);
-  const Grid2 g = plan(rows, C, 4, 16);
   cudaStream_t st = (cudaStream_t)stream;
+  // The grid is ONE wave of the CTAs that are really resident (occupancy API, per instantiation).  ncu r2: planned for 4
+  // CTAs per SM while 77 registers admit 3, the 523-CTA grid ran as 1.18 waves and its 79-CTA tail nearly doubled the
+  // kernel time (35 us for 103 MB).
 #define K_REDUCE(M, H2)                                                                                        \
-  bn_bwd_reduce2_kernel<M, H2><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y, \
-                                                       (const uint8_t*)bits, scale, shift, sum_g, sum_gy, rows, \
-                                                       g.cvec, g.cvec_b, g.rows_per_cta, fin)
+  {                                                                                                            \
+    static int occ = 0;                                                                                        \
+    if (occ == 0 &&                                                                                            \
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_reduce2_kernel<M, H2>, 256, 0) != cudaSuccess || occ < 1)) \
+      occ = 2;                                                                                                 \
+    const Grid2 g = plan(rows, C, occ, 16);                                                                    \
+    bn_bwd_reduce2_kernel<M, H2><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y, \
+                                                         (const uint8_t*)bits, scale, shift, sum_g, sum_gy, rows, \
+                                                         g.cvec, g.cvec_b, g.rows_per_cta, fin);                \
+  }
   if (dout2) TOK_BN2_DISPATCH_MASK(K_REDUCE, true);
   else TOK_BN2_DISPATCH_MASK(K_REDUCE, false);
 #undef K_REDUCE

@@ -103,7 +103,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else {
           tma_load_2d(&tmA, &full_bar[stage], sa, kc, m0);
         }
-        const int wtap = p.flip_taps ? (taps - 1 - tap) : tap;
+        const int wtap = p.use_tapmap ? p.tapmap[tap] : (p.flip_taps ? (taps - 1 - tap) : tap);
         if (!B_MN) {
           // weight matrix seen as [N rows][taps*Cin] : K-major B tile
           tma_load_2d(&tmB, &full_bar[stage], sb, wtap * p.Cin + kc, n0);
@@ -149,8 +149,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int rem = m - img * pq;
       const int pp = rem / p.sc_Q;
       const int qq = rem - pp * p.sc_Q;
-      out_row = (static_cast<long long>(img) * p.sc_H + static_cast<long long>(pp) * p.sc_sh) * p.sc_W +
-                static_cast<long long>(qq) * p.sc_sw;
+      out_row = (static_cast<long long>(img) * p.sc_H + static_cast<long long>(pp) * p.sc_sh + p.sc_oh) * p.sc_W +
+                static_cast<long long>(qq) * p.sc_sw + p.sc_ow;
     }
     const bool want_stats = p.col_sum != nullptr;
     mbar_wait(tmem_full_bar, 0);
@@ -359,7 +359,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           } else {
             tma_load_2d(&tmA, &full_bar[stage], sa, kc, m0);
           }
-          const int wtap = p.flip_taps ? (taps - 1 - tap) : tap;
+          const int wtap = p.use_tapmap ? p.tapmap[tap] : (p.flip_taps ? (taps - 1 - tap) : tap);
           if (!B_MN) {
             tma_load_2d(&tmB, &full_bar[stage], sb, wtap * p.Cin + kc, n0);
           } else {
@@ -493,8 +493,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int rem = m - img * pq;
         const int pp = rem / p.sc_Q;
         const int qq = rem - pp * p.sc_Q;
-        out_row = (static_cast<long long>(img) * p.sc_H + static_cast<long long>(pp) * p.sc_sh) * p.sc_W +
-                  static_cast<long long>(qq) * p.sc_sw;
+        out_row = (static_cast<long long>(img) * p.sc_H + static_cast<long long>(pp) * p.sc_sh + p.sc_oh) * p.sc_W +
+                  static_cast<long long>(qq) * p.sc_sw + p.sc_ow;
       }
       mbar_wait(&tmem_full_bar[buf], (li >> 1) & 1);
       tc_fence_after();

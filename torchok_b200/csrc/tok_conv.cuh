@@ -48,8 +48,11 @@ struct ConvFwdParams {
   float* col_sqsum;           // optional per-column sum of squares
   const float* bias;          // optional per-column bias added before rounding
   int relu;                   // optional ReLU before rounding
-  // optional row scatter: GEMM row (n,p,q) is written to row (n*sc_H + p*sc_sh)*sc_W + q*sc_sw
-  int scatter, sc_P, sc_Q, sc_H, sc_W, sc_sh, sc_sw;
+  // optional row scatter: GEMM row (n,p,q) is written to row (n*sc_H + p*sc_sh + sc_oh)*sc_W + q*sc_sw + sc_ow
+  int scatter, sc_P, sc_Q, sc_H, sc_W, sc_sh, sc_sw, sc_oh, sc_ow;
+  // optional explicit filter-tap table (strided dgrad by output parity class): weight tap of local tap i
+  int use_tapmap;
+  signed char tapmap[16];
   // MN-major operand descriptor geometry (bytes): chunk distance, 8-row group distance, advance per 16-row MMA step.
   int mn_lbo, mn_sbo, mn_kadv;
   // bring-up aid (TOK_CONV_PROFILE=1): per-CTA cycle counts of the epilogue phases, 8 slots per CTA

@@ -154,7 +154,7 @@ conv_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           } else {
             tma_load_2d_2cta(&tmA, full_lead, smem_u32(sa), kc, m0);
           }
-          const int wtap = p.flip_taps ? (taps - 1 - tap) : tap;
+          const int wtap = p.use_tapmap ? p.tapmap[tap] : (p.flip_taps ? (taps - 1 - tap) : tap);
           if (!B_MN) {
             tma_load_2d_2cta(&tmB, full_lead, smem_u32(sb), wtap * p.Cin + kc, n0 + rank * (BN / 2));
           } else {

@@ -297,8 +297,10 @@ int tok_topk_candidates(int nq, int ng, int d, int kp, const void* q_bf16, const
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  static const bool pair = getenv("TOK_TOPK_2CTA") != nullptr;
-  if (pair) e = launch_topk_pair(kp, tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
+  // CTA-pair kernel (tok_retrieval2.cu): 256 query rows per pair, each SM streams HALF of every gallery tile.  Default since
+  // r2 (bit-exact neighbour tests green, 842 vs 736 TFLOP/s at N = 262144); TOK_TOPK_2CTA=0 selects the 1-SM kernel.
+  static const bool pair = !(getenv("TOK_TOPK_2CTA") && atoi(getenv("TOK_TOPK_2CTA")) == 0);
+  if (pair && nq >= 256) e = launch_topk_pair(kp, tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
   else if (kp == 8) e = launch_topk<8>(tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
   else if (kp == 16) e = launch_topk<16>(tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);
   else e = launch_topk<32>(tmQ, tmG, nq, ng, d, g_sqnorm, cand_score, cand_idx, st);

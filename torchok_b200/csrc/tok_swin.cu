@@ -713,6 +713,251 @@ window_attn_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Windows LARGER than 8x8 (N = 144 / 256 / 576 tokens: swinv2_*_window12_192, *_window16_256, *_window12to16/24_*,
+// torchok/models/backbones/swin.py:293-402; the reference's own backbone test uses swinv2_tiny_window16_256).  One CTA of
+// 256 threads per (window, head); K-hat and V (forward) of the whole window live in shared memory as fp32, a thread owns a
+// query row and folds the keys with an online softmax, so nothing of size N x N is ever stored.  The backward makes three
+// sweeps (row statistics + output, query gradients, key / value gradients) with the resident pair of operands swapped
+// between the second and the third.  CUDA cores: this path exists for coverage of the registered large-window variants;
+// the tcgen05 kernels above serve windows up to 8x8 (all of Swin-T/S/B at 224 / 256 with window 7 / 8).
+constexpr int kBigMaxN = 576;
+constexpr int kBigThreads = 256;
+constexpr int kBigSmem = (2 * kBigMaxN * kPitch + 4 * kBigMaxN) * 4 + kBigMaxN * 4 + 32 * 4 + 64;
+
+__device__ __forceinline__ void load_row32(const __nv_bfloat16* p, float (&v)[kHd]) {
+#pragma unroll
+  for (int e = 0; e < kHd; e += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + e);
+    v[e] = bf16_lo(u.x); v[e + 1] = bf16_hi(u.x);
+    v[e + 2] = bf16_lo(u.y); v[e + 3] = bf16_hi(u.y);
+    v[e + 4] = bf16_lo(u.z); v[e + 5] = bf16_hi(u.z);
+    v[e + 6] = bf16_lo(u.w); v[e + 7] = bf16_hi(u.w);
+  }
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16* p, const float (&v)[kHd]) {
+#pragma unroll
+  for (int e = 0; e < kHd; e += 8)
+    *reinterpret_cast<uint4*>(p + e) = make_uint4(pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
+                                                  pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]));
+}
+__device__ __forceinline__ float normalize32(float (&v)[kHd]) {   // v <- v / max(|v|, eps); returns 1 / max(|v|, eps)
+  float ss = 0.f;
+#pragma unroll
+  for (int e = 0; e < kHd; ++e) ss = fmaf(v[e], v[e], ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+  for (int e = 0; e < kHd; ++e) v[e] *= inv;
+  return inv;
+}
+
+__global__ void __launch_bounds__(kBigThreads)
+window_attn_big_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ logit_scale,
+                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) float dyn[];
+  const int N = g.ws * g.ws;
+  float (*sk)[kPitch] = reinterpret_cast<float (*)[kPitch]>(dyn);
+  float (*sv)[kPitch] = sk + N;
+  int* sreg = reinterpret_cast<int*>(sv + N);
+  const int head = blockIdx.x % g.heads;
+  int w = blockIdx.x / g.heads;
+  const int wx = w % g.nwx;
+  w /= g.nwx;
+  const int wy = w % g.nwy;
+  const int b = w / g.nwy;
+  for (int t = threadIdx.x; t < N; t += kBigThreads) {
+    int region;
+    const long long row = token_row(g, b, wy, wx, t, region);
+    sreg[t] = region;
+    const __nv_bfloat16* base = qkv + row * 3 * g.C + head * kHd;
+    float kv[kHd], vv[kHd];
+    load_row32(base + g.C, kv);
+    load_row32(base + 2 * g.C, vv);
+    normalize32(kv);
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) {
+      sk[t][e] = kv[e];
+      sv[t][e] = vv[e];
+    }
+  }
+  __syncthreads();
+  const float scale = __expf(fminf(logit_scale[head], 4.6051702f));  // ln(100)
+  for (int i = threadIdx.x; i < N; i += kBigThreads) {
+    int region;
+    const long long row = token_row(g, b, wy, wx, i, region);
+    float q[kHd];
+    load_row32(qkv + row * 3 * g.C + head * kHd, q);
+    normalize32(q);
+    const float* brow = bias + ((long long)head * N + i) * N;
+    float mx = -INFINITY, l = 0.f, o[kHd];
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) o[e] = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float sc = dot32(q, sk[j]) * scale + __ldg(brow + j) + (sreg[j] != region ? -100.f : 0.f);
+      if (sc > mx) {   // rescale the running sums to the new maximum
+        const float c = __expf(mx - sc);
+        l *= c;
+#pragma unroll
+        for (int e = 0; e < kHd; ++e) o[e] *= c;
+        mx = sc;
+      }
+      const float pr = __expf(sc - mx);
+      l += pr;
+      axpy32(o, pr, sv[j]);
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) o[e] *= inv;
+    store_row32(out + row * g.C + head * kHd, o);
+  }
+}
+
+__global__ void __launch_bounds__(kBigThreads)
+window_attn_big_bwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ logit_scale,
+                           const float* __restrict__ bias, const __nv_bfloat16* __restrict__ dout,
+                           __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
+                           float* __restrict__ dlogit_scale) {
+  extern __shared__ __align__(16) float dyn[];
+  const int N = g.ws * g.ws;
+  float (*sa)[kPitch] = reinterpret_cast<float (*)[kPitch]>(dyn);   // sweep 1-2: K-hat     sweep 3: Q-hat
+  float (*sb)[kPitch] = sa + N;                                      // sweep 1-2: V         sweep 3: dO
+  float* smx = reinterpret_cast<float*>(sb + N);
+  float* sl = smx + N;
+  float* sdelta = sl + N;
+  float* sqn = sdelta + N;         // unused tail kept for alignment of the ints below
+  int* sreg = reinterpret_cast<int*>(sqn + N);
+  float* s_red = reinterpret_cast<float*>(sreg + N);
+  const int head = blockIdx.x % g.heads;
+  int w = blockIdx.x / g.heads;
+  const int wx = w % g.nwx;
+  w /= g.nwx;
+  const int wy = w % g.nwy;
+  const int b = w / g.nwy;
+  const float raw_ls = logit_scale[head];
+  const float scale = __expf(fminf(raw_ls, 4.6051702f));
+  for (int t = threadIdx.x; t < N; t += kBigThreads) {
+    int region;
+    const long long row = token_row(g, b, wy, wx, t, region);
+    sreg[t] = region;
+    const __nv_bfloat16* base = qkv + row * 3 * g.C + head * kHd;
+    float kv[kHd], vv[kHd];
+    load_row32(base + g.C, kv);
+    load_row32(base + 2 * g.C, vv);
+    normalize32(kv);
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) {
+      sa[t][e] = kv[e];
+      sb[t][e] = vv[e];
+    }
+  }
+  __syncthreads();
+  float dls = 0.f;   // sum over this thread's rows of ds * cos
+  // ---- sweeps 1 + 2: thread = query row
+  for (int i = threadIdx.x; i < N; i += kBigThreads) {
+    int region;
+    const long long row = token_row(g, b, wy, wx, i, region);
+    float q[kHd], go[kHd];
+    load_row32(qkv + row * 3 * g.C + head * kHd, q);
+    const float qinv = normalize32(q);
+    load_row32(dout + row * g.C + head * kHd, go);
+    const float* brow = bias + ((long long)head * N + i) * N;
+    float mx = -INFINITY, l = 0.f, o[kHd];
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) o[e] = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float sc = dot32(q, sa[j]) * scale + __ldg(brow + j) + (sreg[j] != region ? -100.f : 0.f);
+      if (sc > mx) {
+        const float c = __expf(mx - sc);
+        l *= c;
+#pragma unroll
+        for (int e = 0; e < kHd; ++e) o[e] *= c;
+        mx = sc;
+      }
+      const float pr = __expf(sc - mx);
+      l += pr;
+      axpy32(o, pr, sb[j]);
+    }
+    const float linv = 1.f / l;
+    float delta = 0.f;   // sum_j p_ij dp_ij = dO_i . O_i
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) delta = fmaf(go[e], o[e] * linv, delta);
+    smx[i] = mx;
+    sl[i] = linv;
+    sdelta[i] = delta;
+    float dq[kHd];
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) dq[e] = 0.f;
+    float* db = dbias + ((long long)head * N + i) * N;
+    for (int j = 0; j < N; ++j) {
+      const float cs = dot32(q, sa[j]);
+      const float sc = cs * scale + __ldg(brow + j) + (sreg[j] != region ? -100.f : 0.f);
+      const float pr = __expf(sc - mx) * linv;
+      const float ds = pr * (dot32(go, sb[j]) - delta);
+      atomicAdd(db + j, ds);
+      dls = fmaf(ds, cs, dls);
+      axpy32(dq, ds * scale, sa[j]);
+    }
+    // through q-hat = q / |q|
+    float qd = 0.f;
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) qd = fmaf(q[e], dq[e], qd);
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) dq[e] = (dq[e] - q[e] * qd) * qinv;
+    store_row32(dqkv + row * 3 * g.C + head * kHd, dq);
+  }
+  // logit_scale gradient of this (window, head)
+  dls = warp_sum(dls);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dls;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < kBigThreads / 32; ++k) t += s_red[k];
+    if (raw_ls < 4.6051702f) atomicAdd(dlogit_scale + head, t * scale);
+  }
+  // ---- sweep 3: thread = key row; resident operands become Q-hat and dO
+  for (int t = threadIdx.x; t < N; t += kBigThreads) {
+    int region;
+    const long long row = token_row(g, b, wy, wx, t, region);
+    float q[kHd], go[kHd];
+    load_row32(qkv + row * 3 * g.C + head * kHd, q);
+    normalize32(q);
+    load_row32(dout + row * g.C + head * kHd, go);
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) {
+      sa[t][e] = q[e];
+      sb[t][e] = go[e];
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += kBigThreads) {
+    int region;
+    const long long row = token_row(g, b, wy, wx, j, region);
+    const __nv_bfloat16* base = qkv + row * 3 * g.C + head * kHd;
+    float k[kHd], v[kHd];
+    load_row32(base + g.C, k);
+    const float kinv = normalize32(k);
+    load_row32(base + 2 * g.C, v);
+    float dk[kHd], dv[kHd];
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) dk[e] = dv[e] = 0.f;
+    const float* bcol = bias + (long long)head * N * N + j;
+    for (int i = 0; i < N; ++i) {
+      const float sc = dot32(k, sa[i]) * scale + __ldg(bcol + (long long)i * N) + (sreg[i] != region ? -100.f : 0.f);
+      const float pr = __expf(sc - smx[i]) * sl[i];
+      const float ds = pr * (dot32(v, sb[i]) - sdelta[i]);
+      axpy32(dk, ds * scale, sa[i]);
+      axpy32(dv, pr, sb[i]);
+    }
+    float kd = 0.f;
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) kd = fmaf(k[e], dk[e], kd);
+#pragma unroll
+    for (int e = 0; e < kHd; ++e) dk[e] = (dk[e] - k[e] * kd) * kinv;
+    store_row32(dqkv + row * 3 * g.C + g.C + head * kHd, dk);
+    store_row32(dqkv + row * 3 * g.C + 2 * g.C + head * kHd, dv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // tcgen05 forward: QK^T -> scale + bias + mask -> softmax -> PV in ONE kernel, accumulators in TMEM.
 // A CTA (128 threads, thread = row) owns one head and walks pairs of windows.  The two windows of a pair are stacked
 // along M (rows 0-63 / 64-127, 49 or 64 valid tokens each):
@@ -1898,7 +2143,7 @@ int tok_patch_merge(int B, int H, int W, int C, const void* src, void* dst, int 
 static int attn_geom(AttnGeom* g, int B, int H, int W, int C, int heads, int ws, int shift) {
   if (B <= 0 || H <= 0 || W <= 0 || heads <= 0 || ws <= 0) return set_error(TOK_ERR_INVALID, "window_attn: bad shape");
   if (C != heads * kHd) return set_error(TOK_ERR_INVALID, "window_attn: head dimension must be 32 (C=%d heads=%d)", C, heads);
-  if (ws * ws > kMaxN) return set_error(TOK_ERR_INVALID, "window_attn: window %d exceeds the 8x8 limit of this kernel", ws);
+  if (ws * ws > kBigMaxN) return set_error(TOK_ERR_INVALID, "window_attn: window %d exceeds the 24x24 limit", ws);
   if ((H % ws) || (W % ws) || shift < 0 || shift >= ws) return set_error(TOK_ERR_INVALID, "window_attn: H, W must be multiples of the window; 0 <= shift < window");
   g->B = B; g->H = H; g->W = W; g->C = C; g->heads = heads; g->ws = ws; g->shift = shift;
   g->nwy = H / ws; g->nwx = W / ws;
@@ -1910,6 +2155,21 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
   AttnGeom g;
   int rc = attn_geom(&g, B, H, W, C, heads, ws, shift);
   if (rc) return rc;
+  if (ws * ws > kMaxN) {   // windows 12 / 16 / 24: the large-window CUDA-core kernel
+    if (C % 8) return set_error(TOK_ERR_INVALID, "window_attn: C must be a multiple of 8");
+    const int smem = (2 * ws * ws * kPitch) * 4 + ws * ws * 4 + 64;
+    static int configured_big = 0;
+    if (configured_big < smem) {
+      cudaError_t e = cudaFuncSetAttribute(window_attn_big_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigSmem);
+      if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_fwd(big): %s", cudaGetErrorString(e));
+      configured_big = kBigSmem;
+    }
+    const long long ctas = (long long)B * g.nwy * g.nwx * heads;
+    window_attn_big_fwd_kernel<<<(unsigned)ctas, kBigThreads, smem, (cudaStream_t)stream>>>(
+        g, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out);
+    TOK_CHECK_LAUNCH("window_attn_big_fwd");
+    return TOK_OK;
+  }
   static const bool use_cuda_cores = getenv("TOK_ATTN_CUDA_CORES") != nullptr;  // bring-up aid: the round-1 fp32 kernel
   static const bool use_v1 = getenv("TOK_ATTN_FWD_V1") != nullptr;   // the one-thread-per-row tcgen05 kernel
   if (!use_cuda_cores && !use_v1 && (C % 8) == 0) {
@@ -1958,6 +2218,23 @@ int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift
   int rc = attn_geom(&g, B, H, W, C, heads, ws, shift);
   if (rc) return rc;
   const int windows = B * g.nwy * g.nwx;
+  if (ws * ws > kMaxN) {   // windows 12 / 16 / 24
+    if (C % 8) return set_error(TOK_ERR_INVALID, "window_attn: C must be a multiple of 8");
+    if (dqkv_colsum) return set_error(TOK_ERR_INVALID, "window_attn_bwd: dqkv_colsum is not produced for windows > 8x8");
+    const int n = ws * ws;
+    const int smem = (2 * n * kPitch + 4 * n) * 4 + n * 4 + 32 * 4 + 64;
+    static bool configured_big = false;
+    if (!configured_big) {
+      cudaError_t e = cudaFuncSetAttribute(window_attn_big_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBigSmem);
+      if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_bwd(big): %s", cudaGetErrorString(e));
+      configured_big = true;
+    }
+    window_attn_big_bwd_kernel<<<(unsigned)((long long)windows * heads), kBigThreads, smem, (cudaStream_t)stream>>>(
+        g, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
+        dlogit_scale);
+    TOK_CHECK_LAUNCH("window_attn_big_bwd");
+    return TOK_OK;
+  }
   const char* cc = getenv("TOK_ATTN_BWD_CUDA_CORES");  // bring-up aid: the round-1 fp32 kernel (read per call)
   if (!(cc && cc[0] == '1') && (C % 8) == 0) {
     static bool configured_tc = false;

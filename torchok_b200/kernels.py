@@ -837,40 +837,176 @@ class BilinearCatFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, size, *xs):
-        xs = [to_nhwc(x) for x in xs]
-        n = xs[0].shape[0]
-        ho, wo = size
-        pitches = [nhwc_pitch(x) for x in xs]
-        total = sum(pitches)
-        out = torch.empty((n, ho, wo, total), dtype=BF16, device=xs[0].device)
-        off = 0
-        for x, cp in zip(xs, pitches):
-            lib().tok_bilinear_fwd(n, x.shape[2], x.shape[3], cp, ho, wo, _p(x), _p(out), total, off, _st())
-            off += cp
-        ctx.meta = (n, ho, wo, total, [(x.shape[1], x.shape[2], x.shape[3], cp) for x, cp in zip(xs, pitches)])
-        return out.permute(0, 3, 1, 2)
+        return _resize_cat_fwd('bilinear', ctx, size, xs)
 
     @staticmethod
     def backward(ctx, g):
-        n, ho, wo, total, shapes = ctx.meta
-        g = _dense_grad(g, total)
-        grads, off = [], 0
-        for i, (c, h, w, cp) in enumerate(shapes):
-            if ctx.needs_input_grad[1 + i]:
-                d = torch.empty((n, h, w, cp), dtype=BF16, device=g.device)
-                lib().tok_bilinear_bwd(n, h, w, cp, ho, wo, _p(g), total, off, _p(d), _st())
-                d = d.permute(0, 3, 1, 2)
-                grads.append(d if cp == c else d[:, :c])
-            else:
-                grads.append(None)
-            off += cp
-        return (None,) + tuple(grads)
+        return _resize_cat_bwd('bilinear', ctx, g)
+
+
+def _resize_cat_fwd(mode, ctx, size, xs):
+    xs = [to_nhwc(x) for x in xs]
+    n = xs[0].shape[0]
+    ho, wo = size
+    pitches = [nhwc_pitch(x) for x in xs]
+    total = sum(pitches)
+    out = torch.empty((n, ho, wo, total), dtype=BF16, device=xs[0].device)
+    off = 0
+    fwd = lib().tok_bilinear_fwd if mode == 'bilinear' else lib().tok_nearest_fwd
+    for x, cp in zip(xs, pitches):
+        fwd(n, x.shape[2], x.shape[3], cp, ho, wo, _p(x), _p(out), total, off, _st())
+        off += cp
+    ctx.meta = (n, ho, wo, total, [(x.shape[1], x.shape[2], x.shape[3], cp) for x, cp in zip(xs, pitches)])
+    return out.permute(0, 3, 1, 2)
+
+def _resize_cat_bwd(mode, ctx, g):
+    n, ho, wo, total, shapes = ctx.meta
+    g = _dense_grad(g, total)
+    grads, off = [], 0
+    bwd = lib().tok_bilinear_bwd if mode == 'bilinear' else lib().tok_nearest_bwd
+    for i, (c, h, w, cp) in enumerate(shapes):
+        if ctx.needs_input_grad[1 + i]:
+            d = torch.empty((n, h, w, cp), dtype=BF16, device=g.device)
+            bwd(n, h, w, cp, ho, wo, _p(g), total, off, _p(d), _st())
+            d = d.permute(0, 3, 1, 2)
+            grads.append(d if cp == c else d[:, :c])
+        else:
+            grads.append(None)
+        off += cp
+    return (None,) + tuple(grads)
 
 
 def bilinear_cat(xs, size):
     """Returns the (N, sum ceil8(C_k), H, W) padded concat; the consumer conv maps its input channels with
     Conv2d.set_input_layout([C_k...])."""
     return BilinearCatFn.apply(tuple(size), *xs)
+
+
+class NearestCatFn(torch.autograd.Function):
+    """cat([interpolate(x_k, size, 'nearest') for k], dim=1): the upsample + skip concat of the U-Net decoder blocks
+    (torchok/models/necks/segmentation/unet.py:48-56), one pass per input straight into the padded concat buffer."""
+
+    @staticmethod
+    def forward(ctx, size, *xs):
+        return _resize_cat_fwd('nearest', ctx, size, xs)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _resize_cat_bwd('nearest', ctx, g)
+
+
+def nearest_cat(xs, size):
+    return NearestCatFn.apply(tuple(size), *xs)
+
+
+class SpatialGatherFn(torch.autograd.Function):
+    """SpatialGather_Module.forward (torchok/models/heads/segmentation/ocr.py:37-46): soft object regions.
+    feats (B, C, H, W), class logits (B, K, H, W) -> context (B, C, K, 1)."""
+
+    @staticmethod
+    def forward(ctx, feats, logits):
+        feats, logits = to_nhwc(feats), to_nhwc(logits)
+        b, c, h, w = feats.shape
+        k, kp = logits.shape[1], nhwc_pitch(logits)
+        if nhwc_pitch(feats) != c:
+            raise NotImplementedError('spatial gather: feature channels must be a multiple of 8')
+        dev = feats.device
+        stats = torch.empty((b, k, 2), dtype=F32, device=dev)
+        scratch = torch.empty((b, k, c), dtype=F32, device=dev)
+        out = torch.empty((b, k, 1, c), dtype=BF16, device=dev)
+        lib().tok_spatial_gather_fwd(b, h * w, c, k, kp, _p(feats), _p(logits), _p(stats), _p(scratch), _p(out), _st())
+        ctx.save_for_backward(feats, logits, stats, out)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, logits, stats, out = ctx.saved_tensors
+        b, c, h, w = feats.shape
+        k, kp = logits.shape[1], nhwc_pitch(logits)
+        g = _dense_grad(g, c)
+        dfeats = torch.empty((b, h, w, c), dtype=BF16, device=g.device)
+        dlogits = torch.empty((b, h, w, kp), dtype=BF16, device=g.device)
+        lib().tok_spatial_gather_bwd(b, h * w, c, k, kp, _p(feats), _p(logits), _p(stats), _p(out), _p(g), _p(dfeats),
+                                     _p(dlogits), _st())
+        dl = dlogits.permute(0, 3, 1, 2)
+        return dfeats.permute(0, 3, 1, 2), (dl if kp == k else dl[:, :k])
+
+
+def spatial_gather(feats, logits):
+    return SpatialGatherFn.apply(feats, logits)
+
+
+class ObjectAttnFn(torch.autograd.Function):
+    """ObjectAttentionBlock.forward's attention (ocr.py:84-95): query (B, Kc, H, W), key / value (B, Kc, K, 1)
+    -> context (B, Kc, H, W) = softmax_k(Kc^-.5 q.key) . value."""
+
+    @staticmethod
+    def forward(ctx, q, key, value, scale):
+        q, key, value = to_nhwc(q), to_nhwc(key), to_nhwc(value)
+        b, kc, h, w = q.shape
+        k = key.shape[2]
+        if kc % 8 or nhwc_pitch(key) != kc or nhwc_pitch(value) != kc:
+            raise NotImplementedError('object attention: key_channels must be a multiple of 8')
+        out = torch.empty((b, h, w, kc), dtype=BF16, device=q.device)
+        lib().tok_object_attn_fwd(b, h * w, kc, k, float(scale), _p(q), _p(key), _p(value), _p(out), _st())
+        ctx.save_for_backward(q, key, value)
+        ctx.scale = float(scale)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        q, key, value = ctx.saved_tensors
+        b, kc, h, w = q.shape
+        k = key.shape[2]
+        g = _dense_grad(g, kc)
+        dev = g.device
+        dq = torch.empty((b, h, w, kc), dtype=BF16, device=dev)
+        dk32, dv32 = torch.empty((b, k, kc), dtype=F32, device=dev), torch.empty((b, k, kc), dtype=F32, device=dev)
+        dk, dv = torch.empty((b, k, 1, kc), dtype=BF16, device=dev), torch.empty((b, k, 1, kc), dtype=BF16, device=dev)
+        lib().tok_object_attn_bwd(b, h * w, kc, k, ctx.scale, _p(q), _p(key), _p(value), _p(g), _p(dq), _p(dk32),
+                                  _p(dv32), _p(dk), _p(dv), _st())
+        return dq.permute(0, 3, 1, 2), dk.permute(0, 3, 1, 2), dv.permute(0, 3, 1, 2), None
+
+
+def object_attention(q, key, value, scale):
+    return ObjectAttnFn.apply(q, key, value, scale)
+
+
+class ChannelScaleFn(torch.autograd.Function):
+    """x * scale[n, c] (nn.Dropout2d with the caller's mask, ocr.py:126)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = to_nhwc(x)
+        n, c, h, w = x.shape
+        cp = nhwc_pitch(x)
+        s = torch.zeros((n, cp), dtype=F32, device=x.device)
+        s[:, :c] = scale
+        out = torch.empty((n, h, w, cp), dtype=BF16, device=x.device)
+        lib().tok_channel_scale(n, h * w, cp, _p(x), _p(s), _p(out), _st())
+        ctx.save_for_backward(s)
+        ctx.c = c
+        o = out.permute(0, 3, 1, 2)
+        return o if cp == c else o[:, :c]
+
+    @staticmethod
+    def backward(ctx, g):
+        (s,) = ctx.saved_tensors
+        n, cp = s.shape
+        g = _dense_grad(g, cp)
+        _, c, h, w = g.shape
+        out = torch.empty((n, h, w, cp), dtype=BF16, device=g.device)
+        lib().tok_channel_scale(n, h * w, cp, _p(g), _p(s), _p(out), _st())
+        o = out.permute(0, 3, 1, 2)
+        return (o if cp == ctx.c else o[:, :ctx.c]), None
+
+
+def dropout2d(x, p, training):
+    """nn.Dropout2d: whole channels of a sample are zeroed with probability p and the rest scaled by 1 / (1 - p)."""
+    if not training or p == 0.0:
+        return x
+    keep = (torch.rand((x.shape[0], x.shape[1]), device=x.device) >= p).float() / (1.0 - p)
+    return ChannelScaleFn.apply(x, keep)
 
 
 def bilinear_resize(x, size):

@@ -100,7 +100,10 @@ class WindowAttention(nn.Module):
         return 16 * torch.sigmoid(t)
 
     def forward(self, x, geom, proj_bias_external=False, res_link=None):
-        ext = self.q_bias is not None and K.attn_fuses_qv_bias_grad()
+        # q/v bias gradients ride in the tcgen05 attention backward (windows up to 8x8); the large-window kernel leaves
+        # them to the qkv linear layer
+        ext = (self.q_bias is not None and K.attn_fuses_qv_bias_grad()
+               and self.window_size[0] * self.window_size[1] <= 64)
         qkv = K.qkv_linear(x, self.qkv.weight, self.q_bias, self.v_bias, ext, res_link)
         out = K.window_attention(qkv, self.bias_table(), self.logit_scale, geom,
                                  (self.q_bias, self.v_bias) if ext else None)
@@ -347,7 +350,8 @@ def _register(name, **fixed):
     return BACKBONES.register_class(factory)
 
 
-# swin.py:285-405 of the reference (window16/12/24 variants construct but their attention exceeds the 8x8 kernel limit)
+# swin.py:285-405 of the reference (windows up to 8x8: tcgen05 attention kernels; window 12 / 16 / 24 variants: the
+# large-window CUDA-core attention kernels, csrc/tok_swin.cu::window_attn_big_*)
 _register('swinv2_custom')
 _T, _S, _B = dict(embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24)), \
     dict(embed_dim=96, depths=(2, 2, 18, 2), num_heads=(3, 6, 12, 24)), \

@@ -272,7 +272,7 @@ class ConvFn(torch.autograd.Function):
         y = torch.empty((d.n, p, q, d.k), dtype=BF16, device=x.device)
         K.conv_fprop(d, x, w, y, bias=b, relu=relu)
         ctx.conv, ctx.d, ctx.relu = conv, d, relu
-        ctx.save_for_backward(x, y if relu else None)
+        ctx.save_for_backward(x, y if relu else None)   # y: post-ReLU output (its sign pattern is the mask)
         out = y.permute(0, 3, 1, 2)
         return out if conv.cout_p == conv.out_channels else out[:, :conv.out_channels]
 
@@ -280,9 +280,17 @@ class ConvFn(torch.autograd.Function):
     def backward(ctx, dout):
         conv, d = ctx.conv, ctx.d
         x, y = ctx.saved_tensors
-        if ctx.relu:
-            raise NotImplementedError('backward of conv+ReLU without BatchNorm')
         dy = K._dense_grad(dout, d.k)
+        if ctx.relu:
+            # conv -> ReLU without normalisation (ConvBnAct(use_batchnorm=False), unet.py:37-38): dy = dout * (y > 0) through
+            # the BatchNorm backward-apply kernel with identity coefficients (mask rebuilt from y: scale 1, shift 0)
+            rows = dy.numel() // d.k
+            one = torch.ones(d.k, dtype=F32, device=dy.device)
+            zero = torch.zeros(d.k, dtype=F32, device=dy.device)
+            masked = torch.empty_like(dy)
+            lib().tok_bn_bwd_apply2(rows, d.k, K._p(dy), None, K._p(y), K.MASK_Y, None, K._p(one), K._p(zero), K._p(one),
+                                    K._p(zero), K._p(zero), K._p(masked), None, K._st())
+            dy = masked
         dx = None
         if ctx.needs_input_grad[0]:
             dxb = torch.empty((d.n, d.h, d.w, d.c), dtype=BF16, device=dy.device)
