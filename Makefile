@@ -9,7 +9,7 @@ LIB       := torchok_b200/libtokb200.so
 
 all: $(LIB) tests/gpu/tok_selftest
 
-%.o: %.cu $(CSRC)/tok_topk.cuh $(CSRC)/tok_optim.cuh $(CSRC)/tok_ptx.cuh $(CSRC)/tok_pair.cuh $(CSRC)/tok_conv.cuh $(CSRC)/tok_internal.h include/tokb200.h
+%.o: %.cu $(CSRC)/tok_bnfin.cuh $(CSRC)/tok_topk.cuh $(CSRC)/tok_optim.cuh $(CSRC)/tok_ptx.cuh $(CSRC)/tok_pair.cuh $(CSRC)/tok_conv.cuh $(CSRC)/tok_internal.h include/tokb200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
 
 $(LIB): $(OBJS)

@@ -375,9 +375,19 @@ def step_roofline(loop, batch, sustained_tf, hbm_gbs):
     loop._restore(snap)
     loop.use_graph = use_graph
     fam = {}
+    dump = open(os.environ['TOK_BENCH_CALLS'], 'w') if os.environ.get('TOK_BENCH_CALLS') else None
     for name, a, s, e in timer.calls:
         ms = s.elapsed_time(e)
         w = _call_work(name, a)
+        if dump is not None:    # per-launch table for profiles/: call, shape, measured us, max(tensor, HBM) floor us
+            shape = ''
+            if name.startswith('tok_conv_'):
+                d_, p_, q_ = _desc(a[0])
+                shape = f'n{d_.n} {d_.c}x{d_.h}x{d_.w}->{d_.k}x{p_}x{q_} k{d_.r} s{d_.stride}'
+            elif w is not None and len(a) > 2 and isinstance(a[0], int) and isinstance(a[1], int):
+                shape = f'{a[0]}x{a[1]}' + (f'x{a[2]}' if isinstance(a[2], int) else '')
+            fl = max(w[1] / (sustained_tf * 1e12), w[2] / (hbm_gbs * 1e9)) * 1e6 if w else 0.0
+            dump.write(f'{name},{shape},{ms * 1e3:.1f},{fl:.1f},{(w[1] if w else 0):.3e},{(w[2] if w else 0):.3e}\n')
         key, flops, byts = w if w else ('other (' + name.replace('tok_', '') + ')', 0.0, 0.0)
         f = fam.setdefault(key, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0, floor_ms=0.0, modelled=w is not None))
         floor = max(flops / (sustained_tf * 1e12), byts / (hbm_gbs * 1e9)) * 1e3
@@ -386,6 +396,8 @@ def step_roofline(loop, batch, sustained_tf, hbm_gbs):
         f['flops'] += flops
         f['bytes'] += byts
         f['floor_ms'] += floor
+    if dump is not None:
+        dump.close()
     total = sum(f['ms'] for f in fam.values())
     groups = {'tcgen05 implicit-GEMM conv/linear (fprop+dgrad+wgrad)':
               [k for k in fam if k.startswith('conv ') or k.startswith('linear ') or k == 'stem conv'],

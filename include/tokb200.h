@@ -125,6 +125,20 @@ int tok_bn_bwd_apply(long long rows, int C, const void* dout, const void* dout2,
                      const float* coef_a, const float* coef_c1, const float* coef_c0, void* dy, void* dres,
                      void* stream);
 
+/* tok_bn_finalize_train fused INTO the apply pass (the BatchNorm2d(training) + ReLU (+ residual) tail of ConvBnAct,
+ * torchok/models/modules/bricks/convbnact.py:48-53): every CTA derives scale / shift from the completed column sums, CTA 0
+ * also stores them (+ saved mean / invstd) and updates the running statistics, the last CTA through the ticket (*counter,
+ * a zeroed 32-bit word owned by the layer, handed back zeroed) clears the sums.  One launch less per BatchNorm layer.
+ * tok_bn_apply_train needs C / 8 to divide its grid stride: ask tok_bn_apply_train_supported first. */
+int tok_bn_apply_train_supported(long long rows, int C);
+int tok_bn_apply_train(long long rows, int C, const void* y, float* sum, float* sqsum, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                       float* scale, float* shift, float* save_mean, float* save_invstd, unsigned* counter,
+                       const void* residual, int relu, void* out, void* stream);
+int tok_bn_apply_bits_train(long long rows, int C, const void* y, float* sum, float* sqsum, const float* gamma,
+                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                            float* scale, float* shift, float* save_mean, float* save_invstd, unsigned* counter,
+                            const void* residual, void* out, void* bits, void* stream);
 /* Second-generation passes (tok_bn2.cu): the backward no longer re-reads the activation to rebuild the ReLU mask.
  * mask_mode 0: no activation; 1: plain conv->BN->ReLU unit, mask = (y*scale + shift > 0) recomputed from the forward's
  * scale/shift; 2: residual tail, mask = bits (1 bit per element, one byte per 8-channel vector, written by
@@ -338,6 +352,16 @@ int tok_adam_step_dev_groups(long long n, float* param, float* grad, float* exp_
  * parameter thawed by FreezeUnfreeze (torchok/callbacks/freeze_unfreeze.py:51-184) restarts at step 1 as in the
  * reference.  Segments with lr_mult == wd_mult == 0 (frozen) are skipped entirely by both step kernels. */
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream);
+
+/* ---- Swin-V2 continuous position bias (timm WindowAttention.cpb_mlp + relative_position_index gather + 16 * sigmoid,
+ *      used through torchok/models/backbones/swin.py:71-81): coords [(2ws-1)^2][2], w1 [512][2], b1 [512], w2 [heads][512]
+ *      -> hidden [(2ws-1)^2][512], table [(2ws-1)^2][heads] (kept for the backward), bias [heads][ws^2][ws^2].  The backward
+ *      ACCUMULATES dw1 / db1 / dw2 (fp32) from dbias; dtable is scratch. */
+int tok_cpb_bias_fwd(int ws, int heads, int hidden_dim, const float* coords, const float* w1, const float* b1,
+                     const float* w2, float* hidden, float* table, float* bias, void* stream);
+int tok_cpb_bias_bwd(int ws, int heads, int hidden_dim, const float* coords, const float* w2, const float* hidden,
+                     const float* table, const float* dbias, float* dtable, float* dw1, float* db1, float* dw2,
+                     void* stream);
 
 /* ---- object-context head and U-Net decoder glue ----------------------------------------------------
  * nearest-neighbour resize written into a channel slice of a padded NHWC concat buffer: F.interpolate(mode='nearest') +

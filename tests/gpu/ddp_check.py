@@ -123,6 +123,55 @@ def check_step(mode):
     loop.close()
 
 
+def check_exchange(mode):
+    """The exchange + optimizer arithmetic alone, on KNOWN gradients (no backward pass, hence no bf16 / atomics noise):
+    rank r's gradient arena is filled from a generator seeded with r, every rank can rebuild all of them, and two SGD
+    steps (momentum, weight decay) must reproduce torch's update rule applied to the rank-ordered mean to fp32 round-off."""
+    os.environ['TOK_DDP'] = mode
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    import torchok_b200 as tb
+    from torchok_b200.engine import StreamLoop
+    lr, mu, wd = 0.1, 0.9, 1e-4
+    task = build_task(tb).to(dev)
+    loop = StreamLoop(task, optimizer={'name': 'SGD', 'params': {'lr': lr, 'momentum': mu, 'weight_decay': wd}},
+                      use_graph=False, bucket_mb=4.0)
+    a = loop.arena
+    w = a.master.clone()
+    buf = None
+    for step in range(2):
+        gs = []
+        for r in range(world):
+            g = torch.Generator(device=dev).manual_seed(1000 * step + r)
+            gs.append(torch.randn(a.numel, device=dev, generator=g))
+        a.grad.copy_(gs[rank])
+        a.begin_step()
+        if loop.peer is not None:
+            loop.peer.begin_step()
+        a.finish()                       # every bucket: exchange (+ fused optimizer on the peer path)
+        if loop.peer is None:
+            loop.optimizer.step()
+        torch.cuda.synchronize()
+        gsum = gs[0].clone()
+        for r in range(1, world):        # rank order, like the kernel
+            gsum += gs[r]
+        d = gsum * (1.0 / world) + wd * w
+        buf = d.clone() if step == 0 else mu * buf + d
+        w = w - lr * buf
+        err = float((a.master - w).abs().max() / w.abs().max())
+        # padding elements between parameters are not parameters: compare parameter slices only
+        worst = 0.0
+        for p_, off in zip(a.params, a.offsets):
+            n = p_.numel()
+            worst = max(worst, float((a.master[off:off + n] - w[off:off + n]).abs().max()))
+        print(f'[rank {rank}] {mode} exchange step {step}: max |w - expected| = {worst:.3e} (whole arena rel {err:.3e}), '
+              f'grads cleared: {float(a.grad.abs().max()) == 0.0}', flush=True)
+        assert worst < 2e-6, worst
+        assert float(a.grad.abs().max()) == 0.0
+        assert torch.equal(a.shadow, a.master.to(torch.bfloat16))
+    loop.close()
+
+
 def check_retrieval():
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device('cuda', torch.cuda.current_device())
@@ -151,6 +200,8 @@ if __name__ == '__main__':
     what = sys.argv[1]
     if what == 'step':
         check_step(sys.argv[2] if len(sys.argv) > 2 else 'peer')
+    elif what == 'exchange':
+        check_exchange(sys.argv[2] if len(sys.argv) > 2 else 'peer')
     else:
         check_retrieval()
     dist.barrier()

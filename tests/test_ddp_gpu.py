@@ -32,5 +32,13 @@ def test_nccl_bucket_allreduce_step_equals_single_rank_large_batch_step():
     _run(['step', 'nccl'], 29612)
 
 
+def test_peer_fused_exchange_and_sgd_are_exact_on_known_gradients():
+    _run(['exchange', 'peer'], 29614)
+
+
+def test_nccl_exchange_and_sgd_are_exact_on_known_gradients():
+    _run(['exchange', 'nccl'], 29615)
+
+
 def test_sharded_retrieval_equals_single_gpu_search():
     _run(['retrieval'], 29613)

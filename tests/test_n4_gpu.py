@@ -113,7 +113,9 @@ def _check_params(m, o, case):
     assert set(grads) == set(case['grads'])
     for n, g in case['grads'].items():
         if float(g.norm()) > 1e-6:
-            _compare(f'grad {n}', grads[n], ogr[n], g, l2=True, slack=2e-2)
+            # gradients with a handful of elements (the 2-channel BatchNorm of last_reduction at mid = 32) are sums over a
+            # ReLU mask that a single flipped pixel moves by percents: wider absolute slack for them
+            _compare(f'grad {n}', grads[n], ogr[n], g, l2=True, slack=2e-2 if g.numel() > 8 else 1e-1)
     now, onow = m.state_dict(), o.state_dict()
     for k, v in case['state_after'].items():
         _compare(k, now[k], onow[k], v)

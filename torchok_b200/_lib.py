@@ -68,6 +68,9 @@ _SIGS = {
     'tok_bn_finalize_train': (_i, [_i, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_finalize_eval': (_i, [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     'tok_bn_apply': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    'tok_bn_apply_train_supported': (_i, [_ll, _i]),
+    'tok_bn_apply_train': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    'tok_bn_apply_bits_train': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_reduce': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_finalize': (_i, [_i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'tok_bn_bwd_apply': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -119,6 +122,8 @@ _SIGS = {
     'tok_sgd_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _i, _vp]),
     'tok_adam_step_dev_groups': (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _i, _vp, _vp, _vp, _vp,
                                       _i, _vp]),
+    'tok_cpb_bias_fwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_cpb_bias_bwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_nearest_fwd': (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     'tok_nearest_bwd': (_i, [_i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     'tok_channel_scale': (_i, [_i, _ll, _i, _vp, _vp, _vp, _vp]),
@@ -135,7 +140,7 @@ _SIGS = {
                            _vp, _vp, _i, _i, _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
 }
-_RAW = {'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+_RAW = {'tok_bn_apply_train_supported', 'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}
 
 

@@ -16,11 +16,13 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/tokb200.h"
 #include "tok_internal.h"
 #include "tok_ptx.cuh"
+#include "tok_bnfin.cuh"
 
 namespace tok {
 
@@ -116,14 +118,21 @@ __device__ __forceinline__ void apply_mask(float (&g)[8], const float (&yy)[8], 
 __global__ void __launch_bounds__(256)
 bn_apply_bits_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res, uint4* __restrict__ out,
                      uint8_t* __restrict__ bits, const float* __restrict__ scale, const float* __restrict__ shift,
-                     long long rows, int cvec, int cvec_b, int rows_per_cta) {
+                     long long rows, int cvec, int cvec_b, int rows_per_cta, const ApplyFin fin) {
+  __shared__ int s_flag;
   const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
-  if (!m.active) return;
   float sc[8], sf[8];
+  if (fin.counter != nullptr) {
+    if (m.cv < cvec) applyfin_coefs(fin, m.cv * 8, sc, sf);
+    applyfin_publish(fin, blockIdx.x == 0 && blockIdx.y == 0, gridDim.x * gridDim.y, &s_flag);
+  }
+  if (!m.active) return;
+  if (fin.counter == nullptr) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = __ldg(scale + m.cv * 8 + j);
-    sf[j] = __ldg(shift + m.cv * 8 + j);
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + m.cv * 8 + j);
+      sf[j] = __ldg(shift + m.cv * 8 + j);
+    }
   }
   const long long step = (long long)m.rlanes * kUnroll;
   for (long long r = m.r0 + m.rl; r < m.r1; r += step) {
@@ -508,6 +517,113 @@ stem_bwd_kernel(const uint4* __restrict__ dpooled, const uint2* __restrict__ arg
   }
 }
 
+// Second version of the stem backward: a thread owns the 2x2 block of conv-output pixels {2p, 2p+1} x {2q, 2q+1} of one
+// 8-channel vector.  The four pooling windows {p, p+1} x {q, q+1} are exactly the windows that can have picked one of
+// those pixels, so 4 argmax words + 4 pooled gradients + 4 y vectors serve 32 outputs (v1: 9 loads and two 64-bit
+// div/mod chains PER PIXEL; 437 + 463 us for the 205 M element tensor whose traffic needs ~90 + ~130 us).
+// Requires even H and W (the fused 3/2/1 pooling path) and cvec | 256.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+stem_bwd2_kernel(const uint4* __restrict__ dpooled, const uint2* __restrict__ arg, const uint4* __restrict__ dact,
+                 const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                 float* __restrict__ sum_g, float* __restrict__ sum_gy, const float* __restrict__ coef_a,
+                 const float* __restrict__ coef_c1, const float* __restrict__ coef_c0, uint4* __restrict__ dy, int total,
+                 int H, int W, int P, int Q, int cvec) {
+  __shared__ float part[MODE == 0 ? 256 * 16 : 1];
+  const int cv = threadIdx.x % cvec;   // constant per thread: 256 and the grid stride are multiples of cvec
+  float a1[8], a2[8], sc[8], sf[8], ca[8], c1[8], c0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a1[j] = a2[j] = 0.f;
+    sc[j] = __ldg(scale + cv * 8 + j);
+    sf[j] = __ldg(shift + cv * 8 + j);
+    if (MODE == 1) {
+      ca[j] = __ldg(coef_a + cv * 8 + j);
+      c1[j] = __ldg(coef_c1 + cv * 8 + j);
+      c0[j] = __ldg(coef_c0 + cv * 8 + j);
+    }
+  }
+  const int H2 = H >> 1, W2 = W >> 1;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    int t = i / cvec;
+    const int qA = t % W2;
+    t /= W2;
+    const int pA = t % H2;
+    const int n = t / H2;
+    const bool hB = pA + 1 < P, wB = qA + 1 < Q;
+    const int pB = hB ? pA + 1 : pA, qB = wB ? qA + 1 : qA;
+    const long long wbase = (long long)n * P;
+    const long long o00 = ((wbase + pA) * Q + qA) * cvec + cv, o01 = ((wbase + pA) * Q + qB) * cvec + cv;
+    const long long o10 = ((wbase + pB) * Q + qA) * cvec + cv, o11 = ((wbase + pB) * Q + qB) * cvec + cv;
+    const long long y00 = (((long long)n * H + 2 * pA) * W + 2 * qA) * cvec + cv;
+    const long long yo[4] = {y00, y00 + cvec, y00 + (long long)W * cvec, y00 + (long long)W * cvec + cvec};
+    const uint2 a00 = __ldg(arg + o00), a01 = __ldg(arg + o01), a10 = __ldg(arg + o10), a11 = __ldg(arg + o11);
+    const uint4 d00 = __ldg(dpooled + o00), d01 = __ldg(dpooled + o01), d10 = __ldg(dpooled + o10),
+                d11 = __ldg(dpooled + o11);
+    uint4 vy[4], va[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      vy[k] = ldg_stream(y + yo[k]);
+      if (dact != nullptr) va[k] = ldg_stream(dact + yo[k]);
+    }
+    float p00[8], p01[8], p10[8], p11[8];
+    unpack8(d00, p00);
+    unpack8(d01, p01);
+    unpack8(d10, p10);
+    unpack8(d11, p11);
+    // pooling slot (3 * r + c) of pixel k = (dh, dw) inside each window that contains it
+    //   window (pA, qA): r = 1 + dh, c = 1 + dw        window (pA, qB): r = 1 + dh, c = 0   (odd w only)
+    //   window (pB, qA): r = 0, c = 1 + dw (odd h only)  window (pB, qB): slot 0             (odd h and odd w)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int dh = k >> 1, dw = k & 1;
+      float g[8], yy[8];
+      unpack8(vy[k], yy);
+      if (dact != nullptr) unpack8(va[k], g);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+      }
+      const uint32_t s00 = (1 + dh) * 3 + (1 + dw), s01 = (1 + dh) * 3, s10 = 1 + dw, s11 = 0;
+      const bool on01 = dw == 1 && wB, on10 = dh == 1 && hB, on11 = on01 && on10;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t w00 = ((j < 4 ? a00.x : a00.y) >> (8 * (j & 3))) & 0xFF;
+        const uint32_t w01 = ((j < 4 ? a01.x : a01.y) >> (8 * (j & 3))) & 0xFF;
+        const uint32_t w10 = ((j < 4 ? a10.x : a10.y) >> (8 * (j & 3))) & 0xFF;
+        const uint32_t w11 = ((j < 4 ? a11.x : a11.y) >> (8 * (j & 3))) & 0xFF;
+        float v = g[j];
+        v += (w00 == s00) ? p00[j] : 0.f;
+        v += (on01 && w01 == s01) ? p01[j] : 0.f;
+        v += (on10 && w10 == s10) ? p10[j] : 0.f;
+        v += (on11 && w11 == s11) ? p11[j] : 0.f;
+        g[j] = fmaf(yy[j], sc[j], sf[j]) > 0.f ? v : 0.f;
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a1[j] += g[j];
+          a2[j] = fmaf(g[j], yy[j], a2[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yy[j] = fmaf(ca[j], g[j], fmaf(c1[j], yy[j], c0[j]));
+        dy[yo[k]] = pack8(yy);
+      }
+    }
+  }
+  if (MODE == 0) {
+    float* mine = part + threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mine[j] = a1[j];
+      mine[8 + j] = a2[j];
+    }
+    __syncthreads();
+    cta_reduce_red4(part, cvec, cvec, sum_g, sum_gy);   // blockIdx.y == 0: column block 0 covers all cvec vectors
+  }
+}
+
 struct Grid2 {
   dim3 grid;
   int cvec, cvec_b, rows_per_cta;
@@ -536,16 +652,48 @@ using namespace tok;
 
 extern "C" {
 
-int tok_bn_apply_bits(long long rows, int C, const void* y, const float* scale, const float* shift,
-                      const void* residual, void* out, void* bits, void* stream) {
+static int launch_apply_bits(long long rows, int C, const void* y, const float* scale, const float* shift,
+                             const void* residual, void* out, void* bits, const ApplyFin& fin, void* stream) {
   if (C <= 0 || (C % 8)) return set_error(TOK_ERR_INVALID, "bn_apply_bits: C must be a positive multiple of 8 (got %d)", C);
   if (rows <= 0 || !residual || !bits) return set_error(TOK_ERR_INVALID, "bn_apply_bits: rows, residual and bits are required");
   const Grid2 g = plan(rows, C, 6);
   bn_apply_bits_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)y, (const uint4*)residual, (uint4*)out,
                                                                 (uint8_t*)bits, scale, shift, rows, g.cvec, g.cvec_b,
-                                                                g.rows_per_cta);
+                                                                g.rows_per_cta, fin);
   TOK_CHECK_LAUNCH("bn_apply_bits");
   return TOK_OK;
+}
+
+int tok_bn_apply_bits(long long rows, int C, const void* y, const float* scale, const float* shift,
+                      const void* residual, void* out, void* bits, void* stream) {
+  ApplyFin fin;
+  memset(&fin, 0, sizeof(fin));
+  return launch_apply_bits(rows, C, y, scale, shift, residual, out, bits, fin, stream);
+}
+
+int tok_bn_apply_bits_train(long long rows, int C, const void* y, float* sum, float* sqsum, const float* gamma,
+                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                            float* scale, float* shift, float* save_mean, float* save_invstd, unsigned* counter,
+                            const void* residual, void* out, void* bits, void* stream) {
+  if (!sum || !sqsum || !scale || !shift || !save_mean || !save_invstd || !counter)
+    return set_error(TOK_ERR_INVALID, "bn_apply_bits_train: accumulators, outputs and the ticket counter are required");
+  ApplyFin fin;
+  fin.counter = counter;
+  fin.sum = sum;
+  fin.sqsum = sqsum;
+  fin.count = (float)rows;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.scale = scale;
+  fin.shift = shift;
+  fin.save_mean = save_mean;
+  fin.save_invstd = save_invstd;
+  fin.C = C;
+  return launch_apply_bits(rows, C, y, scale, shift, residual, out, bits, fin, stream);
 }
 
 int tok_strided_add(int n, int h, int w, int c, int stride, const void* src_compact, void* dst, void* stream) {
@@ -581,6 +729,19 @@ int tok_stem_bwd_reduce(int n, int h, int w, int c, const void* dpooled, const v
   if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8)) return set_error(TOK_ERR_INVALID, "stem_bwd_reduce: bad shape");
   const int P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
   const long long rows = (long long)n * h * w;
+  if (!(h & 1) && !(w & 1) && 256 % (c / 8) == 0 && !getenv("TOK_STEM_BWD_V1")) {
+    const int total = n * (h / 2) * (w / 2) * (c / 8);
+    static int occ = 0;
+    if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_bwd2_kernel<0>, 256, 0) != cudaSuccess || occ < 1))
+      occ = 2;
+    int grid = 148 * occ;
+    if (grid > (total + 255) / 256) grid = (total + 255) / 256;
+    stem_bwd2_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, sum_g, sum_gy,
+        nullptr, nullptr, nullptr, nullptr, total, h, w, P, Q, c / 8);
+    TOK_CHECK_LAUNCH("stem_bwd_reduce");
+    return TOK_OK;
+  }
   const Grid2 g = plan(rows, c, 6);
   stem_bwd_kernel<0><<<g.grid, 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, sum_g, sum_gy,
@@ -595,6 +756,19 @@ int tok_stem_bwd_apply(int n, int h, int w, int c, const void* dpooled, const vo
   if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8)) return set_error(TOK_ERR_INVALID, "stem_bwd_apply: bad shape");
   const int P = (h + 2 - 3) / 2 + 1, Q = (w + 2 - 3) / 2 + 1;
   const long long rows = (long long)n * h * w;
+  if (!(h & 1) && !(w & 1) && 256 % (c / 8) == 0 && !getenv("TOK_STEM_BWD_V1")) {
+    const int total = n * (h / 2) * (w / 2) * (c / 8);
+    static int occ = 0;
+    if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_bwd2_kernel<1>, 256, 0) != cudaSuccess || occ < 1))
+      occ = 2;
+    int grid = 148 * occ * 2;
+    if (grid > (total + 255) / 256) grid = (total + 255) / 256;
+    stem_bwd2_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, nullptr, nullptr,
+        coef_a, coef_c1, coef_c0, (uint4*)dy, total, h, w, P, Q, c / 8);
+    TOK_CHECK_LAUNCH("stem_bwd_apply");
+    return TOK_OK;
+  }
   const Grid2 g = plan(rows, c, 6);
   stem_bwd_kernel<1><<<g.grid, 256, 0, (cudaStream_t)stream>>>(
       (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, nullptr, nullptr,

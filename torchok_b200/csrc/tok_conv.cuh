@@ -33,6 +33,26 @@ struct FwdFin {
   float* save_invstd;
 };
 
+// BatchNorm training-mode "finalize" fused into the APPLY pass (tok_bn_apply_train / tok_bn_apply_bits_train): every thread
+// derives scale / shift of its 8 channels from the completed column sums, CTA 0 also writes them (with the saved mean /
+// invstd for the backward) and updates the running statistics, and the last CTA to have read the sums (ticket) zeroes
+// them for the next step.  Replaces the single-CTA bn_finalize_train launch between the conv and the apply pass.
+struct ApplyFin {
+  unsigned* counter;   // nullptr: scale / shift are read from memory (eval mode, or the separate finalize launch)
+  float* sum;
+  float* sqsum;
+  float count, eps, momentum;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* scale;
+  float* shift;
+  float* save_mean;
+  float* save_invstd;
+  int C;
+};
+
 // Forward / data-gradient implicit GEMM:  out[m, n] = sum_{tap, c} A_tap[m, c] * Wmat[n, wtap*Cin + c]
 struct ConvFwdParams {
   int M;        // GEMM rows = N_img * P * Q

@@ -10,11 +10,13 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/tokb200.h"
 #include "tok_internal.h"
 #include "tok_ptx.cuh"
 #include "tok_optim.cuh"
+#include "tok_bnfin.cuh"
 
 namespace tok {
 
@@ -111,13 +113,18 @@ __global__ void bn_finalize_eval_kernel(const float* __restrict__ running_mean, 
 template <bool HAS_RES, bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res,
                                                        uint4* __restrict__ out, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, long long total, int cvec) {
+                                                       const float* __restrict__ shift, long long total, int cvec,
+                                                       const ApplyFin fin) {
+  __shared__ int s_flag;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const bool invariant = (stride % cvec) == 0;
+  const bool invariant = (stride % cvec) == 0;   // the host guarantees it when fin.counter != nullptr
   float sc[8], sf[8];
   int cv = (int)(i % cvec);
-  if (invariant) {
+  if (fin.counter != nullptr) {
+    applyfin_coefs(fin, cv * 8, sc, sf);
+    applyfin_publish(fin, blockIdx.x == 0, gridDim.x, &s_flag);
+  } else if (invariant) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sc[j] = __ldg(scale + cv * 8 + j);
@@ -873,27 +880,67 @@ int tok_bn_finalize_eval(int C, const float* running_mean, const float* running_
   return TOK_OK;
 }
 
-int tok_bn_apply(long long rows, int C, const void* y, const float* scale, const float* shift, const void* residual,
-                 int relu, void* out, void* stream) {
+static int launch_bn_apply(long long rows, int C, const void* y, const float* scale, const float* shift,
+                           const void* residual, int relu, void* out, const ApplyFin& fin, void* stream) {
   TOK_VEC_CHECK(C);
   if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_apply: no rows");
   const int cvec = C / 8;
   const long long total = rows * cvec;
   const int grid = elem_grid(total, 256 * 2);
+  if (fin.counter != nullptr && ((long long)grid * 256) % cvec != 0)
+    return set_error(TOK_ERR_INVALID, "bn_apply_train: C / 8 = %d does not divide the grid stride", cvec);
   cudaStream_t st = (cudaStream_t)stream;
   const uint4* yp = (const uint4*)y;
   const uint4* rp = (const uint4*)residual;
   uint4* op = (uint4*)out;
   if (residual && relu)
-    bn_apply_kernel<true, true><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec);
+    bn_apply_kernel<true, true><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec, fin);
   else if (residual)
-    bn_apply_kernel<true, false><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec);
+    bn_apply_kernel<true, false><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec, fin);
   else if (relu)
-    bn_apply_kernel<false, true><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec);
+    bn_apply_kernel<false, true><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec, fin);
   else
-    bn_apply_kernel<false, false><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec);
+    bn_apply_kernel<false, false><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec, fin);
   TOK_CHECK_LAUNCH("bn_apply");
   return TOK_OK;
+}
+
+int tok_bn_apply(long long rows, int C, const void* y, const float* scale, const float* shift, const void* residual,
+                 int relu, void* out, void* stream) {
+  ApplyFin fin;
+  memset(&fin, 0, sizeof(fin));
+  return launch_bn_apply(rows, C, y, scale, shift, residual, relu, out, fin, stream);
+}
+
+int tok_bn_apply_train_supported(long long rows, int C) {
+  if (C <= 0 || (C % 8) || rows <= 0) return 0;
+  const int cvec = C / 8;
+  return ((long long)elem_grid(rows * cvec, 256 * 2) * 256) % cvec == 0 ? 1 : 0;
+}
+
+int tok_bn_apply_train(long long rows, int C, const void* y, float* sum, float* sqsum, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                       float* scale, float* shift, float* save_mean, float* save_invstd, unsigned* counter,
+                       const void* residual, int relu, void* out, void* stream) {
+  if (!sum || !sqsum || !scale || !shift || !save_mean || !save_invstd || !counter)
+    return set_error(TOK_ERR_INVALID, "bn_apply_train: accumulators, outputs and the ticket counter are required");
+  ApplyFin fin;
+  fin.counter = counter;
+  fin.sum = sum;
+  fin.sqsum = sqsum;
+  fin.count = (float)rows;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.scale = scale;
+  fin.shift = shift;
+  fin.save_mean = save_mean;
+  fin.save_invstd = save_invstd;
+  fin.C = C;
+  return launch_bn_apply(rows, C, y, scale, shift, residual, relu, out, fin, stream);
 }
 
 int tok_bn_bwd_reduce(long long rows, int C, const void* dout, const void* dout2, const void* out, const void* y,

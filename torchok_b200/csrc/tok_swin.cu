@@ -1938,6 +1938,135 @@ static long long ln_bwd_ctas() {
   return n;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Swin-V2 continuous position bias (timm WindowAttention: cpb_mlp = Linear(2, 512) -> ReLU -> Linear(512, heads, no bias) on
+// the log-spaced relative coordinate table, gathered by relative_position_index, 16 * sigmoid): one small kernel chain
+// instead of torch's sgemm + index + sort + reduce launches (r1: ~3 % of the Swin-T step).
+//   T = (2 ws - 1)^2 table entries, N = ws^2 tokens, e(i, j) = (yi - yj + ws - 1) * (2 ws - 1) + (xi - xj + ws - 1)
+namespace tok {
+namespace {
+constexpr int kCpbHidden = 512;
+
+// hidden[e][k] = relu(w1[k] . coords[e] + b1[k]);  t[e][h] = w2[h] . hidden[e].  One CTA (128 threads) per entry.
+__global__ void __launch_bounds__(128)
+cpb_table_kernel(const float* __restrict__ coords, const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ w2, float* __restrict__ hidden, float* __restrict__ table, int heads) {
+  __shared__ float sh[kCpbHidden];
+  __shared__ float red[4];
+  const int e = blockIdx.x;
+  const float c0 = coords[2 * e], c1 = coords[2 * e + 1];
+  for (int k = threadIdx.x; k < kCpbHidden; k += 128) {
+    const float v = fmaxf(fmaf(w1[2 * k], c0, fmaf(w1[2 * k + 1], c1, b1[k])), 0.f);
+    sh[k] = v;
+    hidden[(long long)e * kCpbHidden + k] = v;
+  }
+  __syncthreads();
+  for (int h = 0; h < heads; ++h) {
+    float t = 0.f;
+    for (int k = threadIdx.x; k < kCpbHidden; k += 128) t = fmaf(w2[(long long)h * kCpbHidden + k], sh[k], t);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) table[(long long)e * heads + h] = red[0] + red[1] + red[2] + red[3];
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ int cpb_entry(int i, int j, int ws) {
+  const int yi = i / ws, xi = i - yi * ws, yj = j / ws, xj = j - yj * ws;
+  return (yi - yj + ws - 1) * (2 * ws - 1) + (xi - xj + ws - 1);
+}
+
+// bias[h][i][j] = 16 * sigmoid(table[e(i, j)][h])
+__global__ void __launch_bounds__(256)
+cpb_gather_kernel(const float* __restrict__ table, float* __restrict__ bias, int heads, int ws) {
+  const int N = ws * ws;
+  const long long total = (long long)heads * N * N;
+  for (long long o = blockIdx.x * 256LL + threadIdx.x; o < total; o += gridDim.x * 256LL) {
+    const int j = (int)(o % N);
+    const int i = (int)((o / N) % N);
+    const int h = (int)(o / ((long long)N * N));
+    const float t = table[(long long)cpb_entry(i, j, ws) * heads + h];
+    bias[o] = 16.f / (1.f + __expf(-t));
+  }
+}
+
+// dtable[e][h] = 16 s (1 - s) * sum over the (i, j) with e(i, j) = e of dbias[h][i][j].  One CTA per entry.
+__global__ void __launch_bounds__(128)
+cpb_scatter_kernel(const float* __restrict__ dbias, const float* __restrict__ table, float* __restrict__ dtable,
+                   int heads, int ws) {
+  __shared__ float red[4];
+  const int N = ws * ws;
+  const int e = blockIdx.x;
+  const int dy = e / (2 * ws - 1) - (ws - 1), dx = e % (2 * ws - 1) - (ws - 1);
+  // token j = (yj, xj) pairs with i = (yj + dy, xj + dx) when that is inside the window
+  const int y0 = max(0, -dy), y1 = min(ws, ws - dy), x0 = max(0, -dx), x1 = min(ws, ws - dx);
+  const int ny = y1 - y0, nx = x1 - x0, cnt = ny > 0 && nx > 0 ? ny * nx : 0;
+  for (int h = 0; h < heads; ++h) {
+    float acc = 0.f;
+    for (int t = threadIdx.x; t < cnt; t += 128) {
+      const int yj = y0 + t / nx, xj = x0 + t % nx;
+      const int j = yj * ws + xj, i = (yj + dy) * ws + (xj + dx);
+      acc += dbias[((long long)h * N + i) * N + j];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float s = 1.f / (1.f + __expf(-table[(long long)e * heads + h]));
+      dtable[(long long)e * heads + h] = 16.f * s * (1.f - s) * (red[0] + red[1] + red[2] + red[3]);
+    }
+    __syncthreads();
+  }
+}
+
+// MLP backward.  One CTA (128 threads) per hidden unit k:
+//   dw2[h][k] = sum_e dt[e][h] hidden[e][k];  dhid[e] = [hidden > 0] sum_h dt[e][h] w2[h][k]
+//   dw1[k][0..1] = sum_e dhid[e] coords[e];   db1[k] = sum_e dhid[e]
+__global__ void __launch_bounds__(128)
+cpb_mlp_bwd_kernel(const float* __restrict__ dtable, const float* __restrict__ hidden, const float* __restrict__ coords,
+                   const float* __restrict__ w2, float* __restrict__ dw1, float* __restrict__ db1,
+                   float* __restrict__ dw2, int T, int heads) {
+  __shared__ float red[4][4];
+  const int k = blockIdx.x;
+  float a0 = 0.f, a1 = 0.f, ab = 0.f;
+  for (int e = threadIdx.x; e < T; e += 128) {
+    const float hv = hidden[(long long)e * kCpbHidden + k];
+    if (hv > 0.f) {
+      float d = 0.f;
+      for (int h = 0; h < heads; ++h) d = fmaf(dtable[(long long)e * heads + h], w2[(long long)h * kCpbHidden + k], d);
+      a0 = fmaf(d, coords[2 * e], a0);
+      a1 = fmaf(d, coords[2 * e + 1], a1);
+      ab += d;
+    }
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  ab = warp_sum(ab);
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5][0] = a0;
+    red[threadIdx.x >> 5][1] = a1;
+    red[threadIdx.x >> 5][2] = ab;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dw1[2 * k] += red[0][0] + red[1][0] + red[2][0] + red[3][0];
+    dw1[2 * k + 1] += red[0][1] + red[1][1] + red[2][1] + red[3][1];
+    db1[k] += red[0][2] + red[1][2] + red[2][2] + red[3][2];
+  }
+  for (int h = 0; h < heads; ++h) {
+    float t = 0.f;
+    for (int e = threadIdx.x; e < T; e += 128) t = fmaf(dtable[(long long)e * heads + h], hidden[(long long)e * kCpbHidden + k], t);
+    t = warp_sum(t);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][3] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) dw2[(long long)h * kCpbHidden + k] += red[0][3] + red[1][3] + red[2][3] + red[3][3];
+  }
+}
+}  // namespace
+}  // namespace tok
+
 extern "C" {
 
 int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, const float* beta, float eps,
@@ -2266,6 +2395,34 @@ int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift
       g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
       dlogit_scale);
   TOK_CHECK_LAUNCH("window_attn_bwd");
+  return TOK_OK;
+}
+
+int tok_cpb_bias_fwd(int ws, int heads, int hidden_dim, const float* coords, const float* w1, const float* b1,
+                     const float* w2, float* hidden, float* table, float* bias, void* stream) {
+  if (ws <= 0 || heads <= 0 || hidden_dim != kCpbHidden)
+    return set_error(TOK_ERR_INVALID, "cpb_bias: the cpb MLP of timm's WindowAttention has 512 hidden units");
+  const int T = (2 * ws - 1) * (2 * ws - 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  cpb_table_kernel<<<T, 128, 0, st>>>(coords, w1, b1, w2, hidden, table, heads);
+  const long long total = (long long)heads * ws * ws * ws * ws;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cpb_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(table, bias, heads, ws);
+  TOK_CHECK_LAUNCH("cpb_bias_fwd");
+  return TOK_OK;
+}
+
+int tok_cpb_bias_bwd(int ws, int heads, int hidden_dim, const float* coords, const float* w2, const float* hidden,
+                     const float* table, const float* dbias, float* dtable, float* dw1, float* db1, float* dw2,
+                     void* stream) {
+  if (ws <= 0 || heads <= 0 || hidden_dim != kCpbHidden)
+    return set_error(TOK_ERR_INVALID, "cpb_bias: the cpb MLP of timm's WindowAttention has 512 hidden units");
+  const int T = (2 * ws - 1) * (2 * ws - 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  cpb_scatter_kernel<<<T, 128, 0, st>>>(dbias, table, dtable, heads, ws);
+  cpb_mlp_bwd_kernel<<<kCpbHidden, 128, 0, st>>>(dtable, hidden, coords, w2, dw1, db1, dw2, T, heads);
+  TOK_CHECK_LAUNCH("cpb_bias_bwd");
   return TOK_OK;
 }
 

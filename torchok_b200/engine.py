@@ -113,10 +113,12 @@ class ParamArena:
         self._pending[b] -= 1
         if self._pending[b] == 0 and self.reducer is not None and not self._launched[b]:
             self._launched[b] = True
+            K.join_side()          # weight gradients launched on the side stream belong to this bucket
             self.reducer.launch(b)
 
     def finish(self):
         """Reduce whatever has not been reduced yet (parameters whose backward did not announce itself)."""
+        K.join_side()
         if self.reducer is not None:
             for b in range(len(self.buckets)):
                 if not self._launched[b]:

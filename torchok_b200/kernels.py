@@ -175,6 +175,53 @@ def grad_buffer(param):
     return param.grad
 
 
+# ------------------------------------------------------------------------------------------------------ side stream
+# Weight gradients have no consumer inside the backward pass (only the gradient exchange / optimizer read them), so they
+# are launched on a side stream forked off the main one: in the captured step graph they become parallel branches that
+# run next to the HBM-bound BatchNorm / LayerNorm passes of the following units instead of in line with them.
+_WGRAD_ASYNC = os.environ.get('TOK_WGRAD_STREAM', '1') == '1'
+_side_streams, _side_state = {}, {'pending': False, 'keep': [], 'queued': False}
+
+
+def side_stream():
+    dev = torch.cuda.current_device()
+    s = _side_streams.get(dev)
+    if s is None:
+        s = _side_streams[dev] = torch.cuda.Stream()
+    return s
+
+
+def join_side():
+    """The current stream waits for everything launched on the side stream; operands kept alive for it are released."""
+    if _side_state['pending']:
+        torch.cuda.current_stream().wait_stream(side_stream())
+        _side_state['pending'] = False
+    _side_state['keep'].clear()
+    _side_state['queued'] = False
+
+
+def wgrad_async(operands, launch):
+    """Run `launch(stream_ptr)` (one weight-gradient kernel) on the side stream, ordered after the work enqueued on the
+    current stream so far.  `operands` stay referenced until the join, so the caching allocator cannot hand their
+    memory to a later main-stream allocation while the side stream still reads it.  The join happens when a gradient
+    bucket is handed to the exchange, in ParamArena.finish(), and — for plain autograd use — in a callback at the end of
+    the backward pass."""
+    if not _WGRAD_ASYNC:
+        launch(_st())
+        return
+    cur, side = torch.cuda.current_stream(), side_stream()
+    side.wait_stream(cur)
+    _side_state['keep'].extend(operands)
+    launch(side.cuda_stream)
+    _side_state['pending'] = True
+    if not _side_state['queued']:
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(join_side)
+            _side_state['queued'] = True
+        except RuntimeError:      # not inside a backward pass (direct call): order the streams now
+            join_side()
+
+
 # ------------------------------------------------------------------------------------------------------ conv
 def conv_desc(n, h, w, c, k, r, s, stride, pad, dil):
     d = tokConvDesc(n, h, w, c, k, r, s, stride, pad, dil)
@@ -218,6 +265,11 @@ MASK_NONE, MASK_Y, MASK_BITS = 0, 1, 2
 # 53 launches fewer for the eager multi-GPU loop.  Hence: forward off, backward on.
 _FUSE_FWD_FIN = os.environ.get('TOK_BN_FUSE_FWD', '0') == '1'
 _FUSE_BWD_FIN = os.environ.get('TOK_BN_FUSE_BWD', '1') == '1'
+# r2 experiment (opt-in, TOK_BN_FUSE_APPLY=1): the forward finalize inside the APPLY pass (every CTA derives scale / shift
+# from the sums; a ticket only to zero them).  Correct (the GPU suite passes with it) but SLOWER: 22.19 vs 20.25 ms per
+# ResNet-50 step — the apply grids have ~2 400 CTAs and their tickets serialise on one L2 address (~20 ns each), which
+# costs more than the 53 single-CTA finalize launches it removes.  Kept off.
+_FUSE_APPLY_FIN = os.environ.get('TOK_BN_FUSE_APPLY', '0') == '1'
 
 
 def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
@@ -235,7 +287,14 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
     small = torch.empty((4, kp), dtype=F32, device=dev)  # scale, shift, save_mean, save_invstd
     rows = n * p * q
     st = _st()
-    if bn.training:
+    fused_apply = False
+    if bn.training and bn.acc.shape[0] > 4 and _FUSE_APPLY_FIN and not _FUSE_FWD_FIN and \
+            (keep and relu and residual is not None or L.tok_bn_apply_train_supported(rows, kp)):
+        # conv (+ statistics), then ONE pass that finalizes the statistics and applies them (acc[4] word 2: its ticket)
+        acc = bn.acc
+        L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), None, None, 0, st)
+        fused_apply = True
+    elif bn.training:
         acc = bn.acc
         if acc.shape[0] > 4 and _FUSE_FWD_FIN:   # conv + statistics + finalize in one launch (acc[4]: ticket counters)
             L.tok_conv_fprop_bn(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias),
@@ -252,20 +311,30 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
                                _p(small[0]), _p(small[1]), st)
     out = torch.empty_like(y) if keep else y
     bits, mode = None, MASK_NONE
+    fin_args = ()
+    if fused_apply:
+        fin_args = (_p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias), bn.eps, bn.momentum, _p(bn.running_mean),
+                    _p(bn.running_var), _p(small[0]), _p(small[1]), _p(small[2]), _p(small[3]), acc[4].data_ptr() + 8)
     if keep and relu and residual is not None:
         bits = torch.empty((rows * kp // 8,), dtype=torch.uint8, device=dev)
         mode = MASK_BITS
-        L.tok_bn_apply_bits(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), _p(out), _p(bits), st)
+        if fused_apply:
+            L.tok_bn_apply_bits_train(rows, kp, _p(y), *fin_args, _p(residual), _p(out), _p(bits), st)
+        else:
+            L.tok_bn_apply_bits(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), _p(out), _p(bits), st)
     else:
         if relu:
             mode = MASK_Y
-        L.tok_bn_apply(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), int(relu), _p(out), st)
+        if fused_apply:
+            L.tok_bn_apply_train(rows, kp, _p(y), *fin_args, _p(residual), int(relu), _p(out), st)
+        else:
+            L.tok_bn_apply(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), int(relu), _p(out), st)
     saved = (x, y, bits, small, mode) if keep else None
     return out.permute(0, 3, 1, 2), saved
 
 
 def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=None, want_dres=False,
-                  wgrad_into=None, dgamma=None, dbeta=None, compact_dx=False):
+                  wgrad_into=None, dgamma=None, dbeta=None, compact_dx=False, wgrad_direct=False):
     """Backward of `unit_forward`.  Returns (dx or None, dres or None).  Parameter gradients are ACCUMULATED into
     wgrad_into / dgamma / dbeta (fp32, may be None for frozen parameters)."""
     L = lib()
@@ -295,7 +364,8 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
         dres = torch.empty_like(y) if want_dres else None
         L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                             _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
-        return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev)
+        return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
+                                   wgrad_direct)
     if acc.shape[0] > 4 and _FUSE_BWD_FIN:   # reduce + finalize in one launch (acc[4]: the layer's ticket counters)
         L.tok_bn_bwd_reduce2_finalize(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                                       _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight), _p(coefs[0]),
@@ -309,10 +379,12 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
     dres = torch.empty_like(y) if want_dres else None
     L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                         _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
-    return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev)
+    return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
+                               wgrad_direct)
 
 
-def _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev):
+def _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
+                        wgrad_direct=False):
     """Data and weight gradients of the conv once dy (the gradient at the conv output) is known."""
     dx = None
     if need_dx and compact_dx:
@@ -326,7 +398,10 @@ def _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_add
         conv_dgrad(d, dy, w, dx, dx_addend)
         dx = dx.permute(0, 3, 1, 2)
     if wgrad_into is not None:
-        L.tok_conv_wgrad(C.byref(d), _p(x), _p(dy), _p(wgrad_into), st)
+        if wgrad_direct:
+            wgrad_async((x, dy, wgrad_into), lambda s: L.tok_conv_wgrad(C.byref(d), _p(x), _p(dy), _p(wgrad_into), s))
+        else:   # a padded temporary that torch ops merge on the main stream right after: stay in line
+            L.tok_conv_wgrad(C.byref(d), _p(x), _p(dy), _p(wgrad_into), st)
     return dx, (dres.permute(0, 3, 1, 2) if dres is not None else None)
 
 
@@ -499,7 +574,7 @@ class LinearFn(torch.autograd.Function):
         if weight.requires_grad:
             gw = grad_buffer(weight)
             if np_ == n:
-                L.tok_linear_wgrad(m, np_, k, _p(x), _p(g), _p(gw), st)
+                wgrad_async((x, g, gw), lambda s: L.tok_linear_wgrad(m, np_, k, _p(x), _p(g), _p(gw), s))
             else:
                 tmp = torch.zeros((np_, k), dtype=F32, device=g.device)
                 L.tok_linear_wgrad(m, np_, k, _p(x), _p(g), _p(tmp), st)
@@ -1146,6 +1221,46 @@ def attn_fuses_qv_bias_grad():
 def window_attention(qkv, bias, logit_scale, geom, qv_bias=None):
     """`qv_bias=(q_bias, v_bias)`: their gradients are produced by the attention backward (see `linear`)."""
     return WindowAttnFn.apply(qkv, bias, logit_scale, geom, qv_bias)
+
+
+class CpbBiasFn(torch.autograd.Function):
+    """timm WindowAttention's bias table: 16 * sigmoid(cpb_mlp(relative_coords_table))[relative_position_index] ->
+    (heads, N, N) fp32.  Parameters: cpb_mlp.0.weight (512, 2), cpb_mlp.0.bias (512), cpb_mlp.2.weight (heads, 512);
+    their gradients are accumulated into `.grad` by the backward kernels."""
+
+    @staticmethod
+    def forward(ctx, coords, w1, b1, w2, ws):
+        heads, hid = w2.shape
+        t = (2 * ws - 1) ** 2
+        n = ws * ws
+        dev = w1.device
+        c = coords.reshape(t, 2).float().contiguous()
+        w1c, b1c, w2c = w1.detach().float().contiguous(), b1.detach().float().contiguous(), w2.detach().float().contiguous()
+        hidden = torch.empty((t, hid), dtype=F32, device=dev)
+        table = torch.empty((t, heads), dtype=F32, device=dev)
+        bias = torch.empty((heads, n, n), dtype=F32, device=dev)
+        lib().tok_cpb_bias_fwd(ws, heads, hid, _p(c), _p(w1c), _p(b1c), _p(w2c), _p(hidden), _p(table), _p(bias), _st())
+        ctx.save_for_backward(c, w2c, hidden, table)
+        ctx.params = (w1, b1, w2)
+        ctx.ws = ws
+        return bias
+
+    @staticmethod
+    def backward(ctx, g):
+        c, w2c, hidden, table = ctx.saved_tensors
+        w1, b1, w2 = ctx.params
+        heads, hid = w2c.shape
+        g = g.float().contiguous()
+        dtable = torch.empty_like(table)
+        lib().tok_cpb_bias_bwd(ctx.ws, heads, hid, _p(c), _p(w2c), _p(hidden), _p(table), _p(g), _p(dtable),
+                               _p(grad_buffer(w1)), _p(grad_buffer(b1)), _p(grad_buffer(w2)), _st())
+        for prm in (w1, b1, w2):
+            grad_ready(prm)
+        return None, None, None, None, None
+
+
+def cpb_bias(coords, w1, b1, w2, ws):
+    return CpbBiasFn.apply(coords, w1, b1, w2, ws)
 
 
 class QkvLinearFn(torch.autograd.Function):

@@ -13,7 +13,8 @@ Execution: tokens live as one (B*H*W, C) bf16 matrix (= the NHWC grid).  Linear 
 whole attention core of a block — normalise q/k, logits, bias, shift mask, softmax, PV, with the cyclic shift and the
 window partition folded into its addressing — is one kernel (tok_window_attn_*: forward on tcgen05 with S and O in
 TMEM, backward on CUDA cores; window <= 8).
-The 169 x 2 -> 512 -> heads cpb MLP that produces the bias table is evaluated with torch ops (a few kFLOP).
+The (2 ws - 1)^2 x 2 -> 512 -> heads cpb MLP, the relative-position gather and the 16 * sigmoid that produce the bias table
+are one small kernel chain (tok_cpb_bias_*), forward and backward.
 """
 import math
 
@@ -94,8 +95,14 @@ class WindowAttention(nn.Module):
         self.proj = Linear(dim, dim)
 
     def bias_table(self):
+        # cpb MLP + relative_position_index gather + 16 * sigmoid as one kernel chain (tok_cpb_bias_*); the gradients of
+        # the three cpb parameters are accumulated by its backward
+        mlp = self.cpb_mlp
+        w1, b1, w2 = mlp[0].weight, mlp[0].bias, mlp[2].weight
+        if w1.is_cuda and w1.is_contiguous() and w2.is_contiguous() and w2.shape[1] == 512:
+            return K.cpb_bias(self.relative_coords_table, w1, b1, w2, self.window_size[0])
         n = self.window_size[0] * self.window_size[1]
-        t = self.cpb_mlp(self.relative_coords_table).view(-1, self.num_heads)
+        t = mlp(self.relative_coords_table).view(-1, self.num_heads)
         t = t[self.relative_position_index.view(-1)].view(n, n, -1).permute(2, 0, 1).contiguous()
         return 16 * torch.sigmoid(t)
 

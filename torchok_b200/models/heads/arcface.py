@@ -52,6 +52,11 @@ class ArcFaceHead(BaseModel):
         nn.init.xavier_uniform_(self.weight)
 
     def _update_margin(self):
+        if self.dynamic_margin and self.step.is_cuda and torch.cuda.is_current_stream_capturing():
+            # the schedule is host arithmetic on a device counter: captured, the margin would be frozen into the graph
+            # while `step` kept advancing on every replay
+            raise NotImplementedError('ArcFaceHead(dynamic_margin=True) cannot run inside a captured step: build the '
+                                      'loop with StreamLoop(use_graph=False) (or TOK_NO_GRAPH=1)')
         if self.dynamic_margin and int(self.step) <= self.num_warmup_steps:
             frac = int(self.step) / self.num_warmup_steps
             self.margin = self.min_margin + frac * (self.max_margin - self.min_margin)

@@ -204,7 +204,8 @@ def _unit_bwd(saved, d, conv, bn, dout, **kw):
     else:
         st = K.BNState(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, bn.training,
                        bn._tok_acc, bn.cp)
-        out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb, **kw)
+        out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb,
+                              wgrad_direct=finish is None, **kw)
     if finish:
         finish()
     K.grad_ready(conv.weight)
@@ -284,7 +285,7 @@ class ConvFn(torch.autograd.Function):
         if ctx.relu:
             # conv -> ReLU without normalisation (ConvBnAct(use_batchnorm=False), unet.py:37-38): dy = dout * (y > 0) through
             # the BatchNorm backward-apply kernel with identity coefficients (mask rebuilt from y: scale 1, shift 0)
-            rows = dy.numel() // d.k
+            rows = dy.shape[0] * dy.shape[2] * dy.shape[3]   # pixels (dy may be a [:, :C] view of a padded buffer)
             one = torch.ones(d.k, dtype=F32, device=dy.device)
             zero = torch.zeros(d.k, dtype=F32, device=dy.device)
             masked = torch.empty_like(dy)
@@ -304,7 +305,7 @@ class ConvFn(torch.autograd.Function):
             if finish:
                 finish()
         if conv.bias is not None and conv.bias.requires_grad:
-            rows = dy.numel() // d.k
+            rows = dy.shape[0] * dy.shape[2] * dy.shape[3]   # pixels (dy may be a [:, :C] view of a padded buffer)
             acc = torch.zeros((2, d.k), dtype=F32, device=dy.device)
             lib().tok_bn_bwd_reduce(rows, d.k, K._p(dy), None, None, K._p(dy), K._p(acc[0]), K._p(acc[1]), K._st())
             K.grad_buffer(conv.bias).add_(acc[0, :conv.out_channels])
