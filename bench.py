@@ -358,6 +358,8 @@ def step_roofline(loop, batch, sustained_tf, hbm_gbs):
     family: share of the step, achieved rate, and time-weighted fraction of max(tensor floor, HBM floor)."""
     from torchok_b200._lib import lib
     L = lib()
+    from torchok_b200 import kernels as K
+    wgrad_async, K._WGRAD_ASYNC = K._WGRAD_ASYNC, False    # events on the launching stream: keep every launch in line
     use_graph, loop.use_graph = loop.use_graph, False
     snap = loop._snapshot()
     for _ in range(2):
@@ -374,6 +376,7 @@ def step_roofline(loop, batch, sustained_tf, hbm_gbs):
     step_ms = e0.elapsed_time(e1)
     loop._restore(snap)
     loop.use_graph = use_graph
+    K._WGRAD_ASYNC = wgrad_async
     fam = {}
     dump = open(os.environ['TOK_BENCH_CALLS'], 'w') if os.environ.get('TOK_BENCH_CALLS') else None
     for name, a, s, e in timer.calls:

@@ -254,7 +254,11 @@ constexpr int kPersistThreads = 64 + 32 * kEpiWarps;  // 320
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS>
+// BRES > 0: the WEIGHT SLAB of the current n-tile (all k-blocks, BRES bytes at most) stays resident in shared memory
+// while the CTA walks the m-tiles of that n-tile; the ring then carries the pixel operand only.  ncu r2
+// (profiles/r2_conv3x3_c64_kernel.md): the short-reduction layers are bound by what an SM can ingest (~27-40 B/clk), and
+// re-fetching the 8-32 KB weight tile with every k-block was a third to a half of it.
+template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS, int BRES>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
@@ -262,14 +266,15 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   static_assert(CBUFS == 1 || CBUFS == 2, "staging buffers");
   static_assert(ABUFS == 0 || ABUFS == 2, "addend buffers");
   constexpr int kBTile = BN * kBlockK * 2;
-  constexpr int kStage = kATile + kBTile;
+  constexpr int kStage = kATile + (BRES > 0 ? 0 : kBTile);
   constexpr int kCTile = kBlockM * BN * 2;
   constexpr int kBlocks = BN / 64;              // 64-column staging blocks per tile
   constexpr int kChunks = BN / 32;              // 32-column TMEM chunks per tile
   constexpr int kChunksPerWarp = kChunks / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_c = smem + STAGES * kStage;
+  uint8_t* smem_w = smem + STAGES * kStage;     // resident weight slab (BRES bytes)
+  uint8_t* smem_c = smem_w + BRES;
   uint8_t* smem_d = smem_c + CBUFS * kCTile;    // prefetched addend tiles (ABUFS of them)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_d + ABUFS * kCTile);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -277,7 +282,9 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint64_t* addend_full_bar = tmem_empty_bar + 2; // [2]
   uint64_t* addend_empty_bar = addend_full_bar + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(addend_empty_bar + 2);
+  uint64_t* wres_full_bar = addend_empty_bar + 2; // [1] slab landed
+  uint64_t* wres_empty_bar = wres_full_bar + 1;   // [1] every UMMA of the slab's n-tile has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_empty_bar + 1);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);  // [sum | sqsum][BN], one owner lane per slot
 
   const int warp = threadIdx.x >> 5;
@@ -305,6 +312,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       mbar_init(&addend_full_bar[i], 1);
       mbar_init(&addend_empty_bar[i], kEpiWarps);
     }
+    mbar_init(wres_full_bar, 1);
+    mbar_init(wres_empty_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -323,6 +332,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     if (elect_one()) {
       uint32_t it = 0;
       int li = 0;
+      int wres_n0 = -1;
+      uint32_t wres_gen = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
         const int n0 = (t / m_tiles) * BN;
         const int m0 = (t % m_tiles) * kBlockM;
@@ -342,6 +353,30 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
         int w0 = 0, h0 = 0, img = 0;
         if (p.a.im2col) pixel_coords(p.a, m0, w0, h0, img);
+        if (BRES > 0 && n0 != wres_n0) {
+          // new n-tile: the MMA warp commits wres_empty after the last tile of the old one.  (A parity wait on the
+          // accumulator barrier of tile li-1 is NOT enough: with one k-block per tile the producer runs several tiles
+          // ahead and the parity aliases — found by scripts/check_big_conv.py.)
+          if (wres_n0 >= 0) {
+            mbar_wait(wres_empty_bar, wres_gen & 1);
+            ++wres_gen;
+          }
+          mbar_arrive_expect_tx(wres_full_bar, static_cast<uint32_t>(num_kb) * kBTile);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const int tap = kb / cin_chunks;
+            const int kc = (kb - tap * cin_chunks) * kBlockK;
+            const int wtap = p.use_tapmap ? p.tapmap[tap] : (p.flip_taps ? (taps - 1 - tap) : tap);
+            uint8_t* sb = smem_w + kb * kBTile;
+            if (!B_MN) {
+              tma_load_2d(&tmB, wres_full_bar, sb, wtap * p.Cin + kc, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(&tmB, wres_full_bar, sb + j * 8192, wtap * p.N + n0 + j * 64, kc);
+            }
+          }
+          wres_n0 = n0;
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int stage = it % STAGES;
           const uint32_t phase = (it / STAGES) & 1;
@@ -359,13 +394,15 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           } else {
             tma_load_2d(&tmA, &full_bar[stage], sa, kc, m0);
           }
-          const int wtap = p.use_tapmap ? p.tapmap[tap] : (p.flip_taps ? (taps - 1 - tap) : tap);
-          if (!B_MN) {
-            tma_load_2d(&tmB, &full_bar[stage], sb, wtap * p.Cin + kc, n0);
-          } else {
+          if (BRES == 0) {
+            const int wtap = p.use_tapmap ? p.tapmap[tap] : (p.flip_taps ? (taps - 1 - tap) : tap);
+            if (!B_MN) {
+              tma_load_2d(&tmB, &full_bar[stage], sb, wtap * p.Cin + kc, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, wtap * p.N + n0 + j * 64, kc);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, wtap * p.N + n0 + j * 64, kc);
+            }
           }
         }
       }
@@ -375,10 +412,21 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, false, B_MN);
       uint32_t it = 0;
       int li = 0;
+      int wres_n0 = -1;
+      uint32_t wres_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
         const int buf = li & 1;
         mbar_wait(&tmem_empty_bar[buf], ((li >> 1) & 1) ^ 1);
         tc_fence_after();
+        if (BRES > 0) {
+          const int n0 = (t / m_tiles) * BN;
+          if (n0 != wres_n0) {     // the producer reloads the slab exactly at these tiles
+            mbar_wait(wres_full_bar, wres_phase);
+            tc_fence_after();
+            wres_phase ^= 1;
+            wres_n0 = n0;
+          }
+        }
         const uint32_t acc = tmem_base + buf * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int stage = it % STAGES;
@@ -386,7 +434,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * kStage);
-          const uint32_t b_addr = a_addr + kATile;
+          const uint32_t b_addr = BRES > 0 ? smem_u32(smem_w + kb * kBTile) : a_addr + kATile;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
@@ -397,6 +445,10 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           umma_commit(&empty_bar[stage]);
         }
         umma_commit(&tmem_full_bar[buf]);
+        if (BRES > 0) {   // last tile of this CTA in the n-tile: hand the slab back once these UMMAs have retired
+          const int tn = t + gridDim.x;
+          if (tn < total_tiles && (tn / m_tiles) * BN != wres_n0) umma_commit(wres_empty_bar);
+        }
       }
     }
   } else {
@@ -856,10 +908,10 @@ constexpr int conv_smem_bytes() {
   return STAGES * (kATile + BN * kBlockK * 2) + (2 * STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
 }
 
-template <int BN, int STAGES, int CBUFS, int ABUFS>
+template <int BN, int STAGES, int CBUFS, int ABUFS, int BRES>
 constexpr int conv_persist_smem_bytes() {
-  return STAGES * (kATile + BN * kBlockK * 2) + (CBUFS + ABUFS) * kBlockM * BN * 2 + (2 * STAGES + 8) * 8 + 16 +
-         2 * BN * 4 + 1024;
+  return STAGES * (kATile + (BRES > 0 ? 0 : BN * kBlockK * 2)) + BRES + (CBUFS + ABUFS) * kBlockM * BN * 2 +
+         (2 * STAGES + 10) * 8 + 16 + 2 * BN * 4 + 1024;
 }
 
 int num_sms() {
@@ -873,14 +925,14 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS>
+template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS, int BRES = 0>
 static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                     const CUtensorMap& tmD, const ConvFwdParams& p, cudaStream_t st) {
-  constexpr int smem = conv_persist_smem_bytes<BN, STAGES, CBUFS, ABUFS>();
+  constexpr int smem = conv_persist_smem_bytes<BN, STAGES, CBUFS, ABUFS, BRES>();
   static_assert(smem <= 232448, "persistent conv kernel exceeds the 227 KB shared-memory limit");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS>,
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS, BRES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -889,7 +941,8 @@ static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& t
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS><<<grid, kPersistThreads, smem, st>>>(tmA, tmB, tmC, tmD, p);
+  conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS, BRES><<<grid, kPersistThreads, smem, st>>>(tmA, tmB, tmC,
+                                                                                                    tmD, p);
   return cudaGetLastError();
 }
 
@@ -901,10 +954,20 @@ cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& t
                                     const CUtensorMap& tmD, const ConvFwdParams& p, int bn, bool b_mn,
                                     cudaStream_t st) {
   const bool add = p.addend != nullptr && !p.scatter;
+  // weight slab of one n-tile (all taps x channel blocks): resident when it fits next to the ring (TOK_CONV_BRES=0: off)
+  static const bool bres_on = !(getenv("TOK_CONV_BRES") && atoi(getenv("TOK_CONV_BRES")) == 0);
+  const long long num_kb = (long long)p.a.R * p.a.S * ((p.Cin + kBlockK - 1) / kBlockK);
+  const long long slab = num_kb * bn * kBlockK * 2;
+  const long long m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  // the slab load is a pipeline bubble once per n-tile and CTA: worth it when a CTA then re-uses it for >= 8 m-tiles
+  const bool reuse = m_tiles >= 8LL * num_sms();
   if (bn == 64) {
     if (add)
       return b_mn ? launch_persist_t<64, 6, true, 2, 2>(tmA, tmB, tmC, tmD, p, st)
                   : launch_persist_t<64, 6, false, 2, 2>(tmA, tmB, tmC, tmD, p, st);
+    if (bres_on && reuse && slab <= 73728)
+      return b_mn ? launch_persist_t<64, 6, true, 2, 0, 73728>(tmA, tmB, tmC, tmD, p, st)
+                  : launch_persist_t<64, 6, false, 2, 0, 73728>(tmA, tmB, tmC, tmD, p, st);
     return b_mn ? launch_persist_t<64, 6, true, 2, 0>(tmA, tmB, tmC, tmD, p, st)
                 : launch_persist_t<64, 6, false, 2, 0>(tmA, tmB, tmC, tmD, p, st);
   }
@@ -912,6 +975,12 @@ cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& t
     if (add)
       return b_mn ? launch_persist_t<128, 3, true, 2, 2>(tmA, tmB, tmC, tmD, p, st)
                   : launch_persist_t<128, 3, false, 2, 2>(tmA, tmB, tmC, tmD, p, st);
+    // measured r2 (profiles/r2_resnet50_step.md): no gain for the 128-wide tile (1x1 64->256: 133 vs 129 us), -10 % for the
+    // 64-wide 3x3 (180 -> 161 us); so the 128-wide variant needs TOK_CONV_BRES=2
+    static const bool bres128 = getenv("TOK_CONV_BRES") && atoi(getenv("TOK_CONV_BRES")) == 2;
+    if (bres128 && reuse && slab <= 65536)
+      return b_mn ? launch_persist_t<128, 5, true, 2, 0, 65536>(tmA, tmB, tmC, tmD, p, st)
+                  : launch_persist_t<128, 5, false, 2, 0, 65536>(tmA, tmB, tmC, tmD, p, st);
     return b_mn ? launch_persist_t<128, 4, true, 2, 0>(tmA, tmB, tmC, tmD, p, st)
                 : launch_persist_t<128, 4, false, 2, 0>(tmA, tmB, tmC, tmD, p, st);
   }
