@@ -6,7 +6,8 @@
  * torch dispatch it replaces.  The Python host (torchok_b200/_lib.py) binds these with ctypes.
  *
  * Conventions
- *   - every pointer is a DEVICE pointer owned by the caller; nothing here allocates, frees or synchronises;
+ *   - every pointer is a DEVICE pointer owned by the caller; nothing here allocates, frees or synchronises (the one
+ *     exception: tok_ipc_alloc / tok_ipc_open own the peer-mapped arenas of the multi-GPU gradient exchange);
  *   - activations are NHWC bf16 ("pixel-major"), conv weights are [Cout][R][S][Cin] bf16 (= a torch OIHW tensor in
  *     channels_last memory format), weight gradients are fp32 in the same layout;
  *   - `stream` is a cudaStream_t passed as void*;
