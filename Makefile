@@ -3,7 +3,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v
 CSRC      := torchok_b200/csrc
-SRCS      := $(CSRC)/tok_conv.cu $(CSRC)/tok_conv2.cu $(CSRC)/tok_api.cu $(CSRC)/tok_elem.cu $(CSRC)/tok_bn2.cu $(CSRC)/tok_retrieval.cu $(CSRC)/tok_retrieval2.cu $(CSRC)/tok_heads.cu $(CSRC)/tok_seg.cu $(CSRC)/tok_swin.cu $(CSRC)/tok_comm.cu $(CSRC)/tok_ocr.cu
+SRCS      := $(CSRC)/tok_conv.cu $(CSRC)/tok_conv2.cu $(CSRC)/tok_conv3.cu $(CSRC)/tok_api.cu $(CSRC)/tok_elem.cu $(CSRC)/tok_bn2.cu $(CSRC)/tok_retrieval.cu $(CSRC)/tok_retrieval2.cu $(CSRC)/tok_heads.cu $(CSRC)/tok_seg.cu $(CSRC)/tok_swin.cu $(CSRC)/tok_comm.cu $(CSRC)/tok_ocr.cu
 OBJS      := $(SRCS:.cu=.o)
 LIB       := torchok_b200/libtokb200.so
 

@@ -21,6 +21,11 @@ cudaError_t launch_conv_fwd_pair(const CUtensorMap& tmA, const CUtensorMap& tmB,
                                  const CUtensorMap& tmD, const ConvFwdParams& p, bool b_mn, cudaStream_t st);
 cudaError_t launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const ConvWgradParams& p, int bn,
                               int splits, cudaStream_t st);
+// tok_conv3.cu: halo formulation of the 3x3 / stride 1 / pad 1 convolution for Cin <= 128
+bool conv3x3_halo_eligible(int n_img, int H, int W, int Cin, int N);
+int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, const void* w, int wK, int wC,
+                        int transposed, void* out, const void* addend, float* col_sum, float* col_sqsum,
+                        cudaStream_t st);
 void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
                         int sh, int sw, cudaStream_t st);
 
@@ -362,6 +367,10 @@ static int conv_fprop_impl(const tokConvDesc* d, const void* x, const void* w, v
   p.bias = bias;
   p.relu = relu;
   const long long M = (long long)d->n * P * Q;
+  if (d->r == 3 && d->s == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && !addend && !bias && !relu && !fin &&
+      !getenv("TOK_CONV_V1") && conv3x3_halo_eligible(d->n, d->h, d->w, d->c, d->k))
+    return launch_conv3x3_halo(x, d->n, d->h, d->w, d->c, d->k, w, d->k, d->c, 0, y, nullptr, sum, sqsum,
+                               static_cast<cudaStream_t>(stream));
   if (fin) {
     p.fin = *fin;
     p.fin.count = (float)M;
@@ -485,6 +494,9 @@ int tok_conv_dgrad(const tokConvDesc* d, const void* dy, const void* w, void* dx
     }
     return run_fwd(dy, d->n, P, Q, d->k, src, (long long)d->n * P * Q, w, d->k, wcols, true, d->c, 0, p, st);
   }
+  if (d->r == 3 && d->s == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && !getenv("TOK_CONV_V1") &&
+      conv3x3_halo_eligible(d->n, d->h, d->w, d->k, d->c))
+    return launch_conv3x3_halo(dy, d->n, d->h, d->w, d->k, d->c, w, d->k, d->c, 1, dx, addend, nullptr, nullptr, st);
   // RxS filter: stride-1 correlation of (zero-dilated) dy with the flipped filter.
   const int pad_h = (d->r - 1) * d->dil - d->pad;
   const int pad_w = (d->s - 1) * d->dil - d->pad;
