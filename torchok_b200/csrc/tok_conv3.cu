@@ -55,6 +55,7 @@ struct HaloParams {
   int patch_stride;      // bytes between ring slots (1024-aligned)
   int slab_bytes;
   int tmem_cols;
+  int dbg;               // bring-up aid (TOK_HALO_DBG): bit 0 = tap shifts rounded to 8 rows (WRONG results, timing only)
   const __nv_bfloat16* w;
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
@@ -245,7 +246,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const HaloParams p)
       uint32_t a_tap[9], b_tap[9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        a_tap[tap] = static_cast<uint32_t>(((tap / 3) * Wp + (tap % 3)) * kRowB) >> 4;
+        a_tap[tap] = static_cast<uint32_t>((((tap / 3) * Wp + (tap % 3)) & ((p.dbg & 1) ? ~7 : ~0)) * kRowB) >> 4;
         b_tap[tap] = static_cast<uint32_t>(tap * p.KBLK * tile_bytes) >> 4;
       }
       uint32_t it = 0;
@@ -554,6 +555,7 @@ int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, 
   p.TR = pl.TR; p.MT = pl.MT; p.BN = pl.BN; p.BNC = pl.BNC; p.n_tiles = pl.n_tiles; p.KBLK = pl.KBLK; p.NBUF = pl.NBUF;
   p.SBUF = pl.SBUF; p.stages = pl.stages; p.patch_bytes = pl.patch_bytes; p.patch_stride = pl.patch_stride;
   p.slab_bytes = pl.slab_bytes; p.tmem_cols = pl.tmem_cols;
+  p.dbg = getenv("TOK_HALO_DBG") ? atoi(getenv("TOK_HALO_DBG")) : 0;
   p.w = static_cast<const __nv_bfloat16*>(w);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.addend = static_cast<const __nv_bfloat16*>(addend);
