@@ -58,16 +58,20 @@ for (n, c, h, w_, k) in shapes:
         dxa = torch.full((n, h, w_, c), float('nan'), device=dev, dtype=torch.bfloat16)
         K.conv_dgrad(d, dy, wk, dxa, add)
         torch.cuda.synchronize()
+        dw = torch.zeros(k, 3, 3, c, device=dev)
+        K.conv_wgrad(d, xn, dy, dw)
+        dw_keep = dw.clone()
+        t_w = timed(lambda: K.conv_wgrad(d, xn, dy, dw))
         t_f = timed(lambda: K.conv_fprop(d, xn, wk, y, stats))
         t_d = timed(lambda: K.conv_dgrad(d, dy, wk, dx))
         stats.zero_()
         K.conv_fprop(d, xn, wk, y, stats)
-        res[halo] = (y, stats.clone(), dx, dxa, t_f, t_d)
+        res[halo] = (y, stats.clone(), dx, dxa, t_f, t_d, dw_keep, t_w)
     ref = F.conv2d(x.float(), w.float(), padding=1).permute(0, 2, 3, 1)
     refd = torch.nn.grad.conv2d_input((n, c, h, w_), w.float(), dy.permute(0, 3, 1, 2).float(),
                                       padding=1).permute(0, 2, 3, 1)
-    y, stats, dx, dxa, t_f, t_d = res['1']
-    y0, stats0, dx0, dxa0, t_f0, t_d0 = res['0']
+    y, stats, dx, dxa, t_f, t_d, dw, t_w = res['1']
+    y0, stats0, dx0, dxa0, t_f0, t_d0, dw0, t_w0 = res['0']
     e_f = float((y.float() - ref).abs().max() / ref.abs().max())
     e_d = float((dx.float() - refd).abs().max() / refd.abs().max())
     e_a = float((dxa.float() - (refd + add.float())).abs().max() / (refd + add.float()).abs().max())
@@ -75,12 +79,15 @@ for (n, c, h, w_, k) in shapes:
     ysq = (y.float() ** 2).sum((0, 1, 2))
     e_s = float((stats[0] - ysum).abs().max() / (ysum.abs().max() + 1e-6))
     e_q = float((stats[1] - ysq).abs().max() / ysq.abs().max())
+    refw = torch.nn.grad.conv2d_weight(x.float(), (k, c, 3, 3), dy.permute(0, 3, 1, 2).float(), padding=1).permute(0, 2, 3, 1)
+    e_w = float((dw - refw).abs().max() / refw.abs().max())
+    e_w0 = float((dw0 - refw).abs().max() / refw.abs().max())
     same_f = float((y.float() - y0.float()).abs().max())
     same_d = float((dx.float() - dx0.float()).abs().max())
-    good = e_f < 1e-2 and e_d < 1e-2 and e_a < 1e-2 and e_s < 1e-3 and e_q < 1e-3
+    good = e_f < 1e-2 and e_d < 1e-2 and e_a < 1e-2 and e_s < 1e-3 and e_q < 1e-3 and e_w < 2e-3
     ok &= good
     print(f'{"PASS" if good else "FAIL"} n{n} {c}x{h}x{w_}->{k}: fprop {e_f:.1e} dgrad {e_d:.1e} dgrad+add {e_a:.1e} '
-          f'sum {e_s:.1e} sq {e_q:.1e} | vs generic: fprop {same_f:.1e} dgrad {same_d:.1e} | us halo {t_f:.1f}/{t_d:.1f} '
-          f'generic {t_f0:.1f}/{t_d0:.1f}', flush=True)
+          f'sum {e_s:.1e} sq {e_q:.1e} wgrad {e_w:.1e} (generic {e_w0:.1e}) | vs generic: fprop {same_f:.1e} dgrad {same_d:.1e} | us halo {t_f:.1f}/{t_d:.1f} '
+          f'generic {t_f0:.1f}/{t_d0:.1f} | wgrad us {t_w:.1f} vs {t_w0:.1f}', flush=True)
 print('HALO CONV CHECK', 'OK' if ok else 'FAILED')
 sys.exit(0 if ok else 1)

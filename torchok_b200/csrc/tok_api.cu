@@ -26,6 +26,9 @@ bool conv3x3_halo_eligible(int n_img, int H, int W, int Cin, int N);
 int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, const void* w, int wK, int wC,
                         int transposed, void* out, const void* addend, float* col_sum, float* col_sqsum,
                         cudaStream_t st);
+bool conv3x3_wgrad_halo_eligible(int n_img, int H, int W, int Cin, int Cout);
+int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, int W, int Cin, int Cout, float* dw,
+                              cudaStream_t st);
 void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
                         int sh, int sw, cudaStream_t st);
 
@@ -572,6 +575,9 @@ int tok_conv_wgrad(const tokConvDesc* d, const void* x, const void* dy, float* d
   if (rc) return rc;
   int P, Q;
   tok_conv_out_hw(d, &P, &Q);
+  if (d->r == 3 && d->s == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && !getenv("TOK_CONV_V1") &&
+      conv3x3_wgrad_halo_eligible(d->n, d->h, d->w, d->c, d->k))
+    return launch_conv3x3_wgrad_halo(x, dy, d->n, d->h, d->w, d->c, d->k, dw, static_cast<cudaStream_t>(stream));
   PixelSrc src = conv_src(d, P, Q);
   return run_wgrad(x, d->n, d->h, d->w, d->c, src, dy, (long long)d->n * P * Q, d->k, dw,
                    static_cast<cudaStream_t>(stream));

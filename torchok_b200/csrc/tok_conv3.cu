@@ -417,6 +417,147 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const HaloParams p)
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient by the same trick:  dW[co][r][s][ci] += sum over pixels dy[pix][co] * x[pix + (r-1, s-1)][ci].
+// A tile stages the dy rows of TR image rows IN THE PADDED RASTER (box of W + 2 columns: the two columns past the
+// image edge are TMA zero fill, so the padding positions contribute nothing) and the x patch of TR + 2 rows.  Both are
+// MN-major UMMA operands with the pixel index as the reduction dimension: A = dy tile (M = 64 output channels),
+// B = the x patch read r*(W+2)+s rows further down (N = input channels).  One fp32 accumulator per filter tap lives in
+// TMEM for the whole kernel (9 x N columns) and is flushed once per CTA with 16-byte vector reductions.
+// The generic kernel (tok_conv.cu) walks the pixels once per tap and per 128x64 tile: 294 us for HRNet's 18 -> 18 @128.
+// M = 64 accumulator rows sit in TMEM lanes (row / 16) * 32 + row % 16 (tests/gpu/halo_probe.cu, probe 2).
+struct HaloWgradParams {
+  int n_img, H, W;
+  int Cin, Cout;         // pitches of x / dy (multiples of 8)
+  int N;                 // UMMA N = Cin rounded up to 16
+  int TR;                // image rows per tile
+  int ksteps;            // 16-pixel reduction steps per tile = ceil(TR * (W + 2) / 16)
+  int dy_bytes, x_bytes; // TMA box bytes
+  int dy_stride, x_stride;   // shared-memory bytes reserved per stage for each operand (zero-initialised guard rows included)
+  int stages;
+  int tmem_cols;
+  float* dw;             // [Cout][9][Cin] fp32, accumulated
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                          const HaloWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = p.dy_stride + p.x_stride;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + 4;
+  uint64_t* done_bar = empty_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Wp = p.W + 2;
+  const int row_blocks = (p.H + p.TR - 1) / p.TR;
+  const int tiles = p.n_img * row_blocks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  // guard rows (past the TMA boxes) are read by the last reduction steps: they must be zero (dy) / finite (x)
+  {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint32_t base = smem_u32(smem);
+    for (int i = threadIdx.x; i < p.stages * stage_bytes / 16; i += 192) sts128(base + i * 16, z);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int img = t / row_blocks;
+        const int h0 = (t - img * row_blocks) * p.TR;
+        const int stage = it % p.stages;
+        mbar_wait(&empty_bar[stage], ((it / p.stages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], p.dy_bytes + p.x_bytes);
+        const uint32_t sdy = smem_u32(smem + stage * stage_bytes);
+        tma_load_tile_4d(&tmDY, &full_bar[stage], sdy, 0, 0, h0, img);
+        tma_load_tile_4d(&tmX, &full_bar[stage], sdy + p.dy_stride, 0, -1, h0 - 1, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(64, p.N, true, true);
+      // high descriptor word: SBO 1024 B, version 1, SWIZZLE_128B; low word: address >> 4 | LBO (8192 B, unused) << 16
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t kLbo = (8192u >> 4) << 16;
+      uint32_t tap_rows[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) tap_rows[tap] = static_cast<uint32_t>((tap / 3) * Wp + (tap % 3)) * 8u;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int stage = it % p.stages;
+        mbar_wait(&full_bar[stage], (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sdy = smem_u32(smem + stage * stage_bytes);
+        const uint32_t a_lo0 = ((sdy >> 4) & 0x3FFFu) | kLbo;
+        const uint32_t b_lo0 = (((sdy + p.dy_stride) >> 4) & 0x3FFFu) | kLbo;
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const uint32_t acc_flag = (it | ks) != 0 ? 1u : 0u;
+          const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (a_lo0 + ks * 128);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (b_lo0 + tap_rows[tap] + ks * 128);
+            umma_bf16(tmem_base + tap * p.N, adesc, bdesc, idesc, acc_flag);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // ---- flush: warp q reads TMEM lanes q*32 .. q*32+15 = output channels q*16 .. q*16+15
+    const int q = warp & 3;
+    const int co = q * 16 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    if (blockIdx.x < tiles) {
+      for (int tap = 0; tap < 9; ++tap) {
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tap * p.N + c0, r);
+          tmem_ld_wait();
+          if (lane < 16 && co < p.Cout) {
+            float* dst = p.dw + (static_cast<long long>(co) * 9 + tap) * p.Cin + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (c0 + j < p.Cin)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "r"(r[j]), "r"(r[j + 1]),
+                             "r"(r[j + 2]), "r"(r[j + 3])
+                             : "memory");
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -591,6 +732,103 @@ int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, 
   if (e0 != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv3x3 halo: %s", cudaGetErrorString(e0));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv3x3 halo launch: %s", cudaGetErrorString(e));
+  return TOK_OK;
+}
+
+// ---- weight gradient
+struct HaloWgradPlan {
+  bool ok;
+  int N, TR, ksteps, dy_bytes, x_bytes, dy_stride, x_stride, stages, tmem_cols, smem;
+};
+
+static HaloWgradPlan halo_wgrad_plan(int n_img, int H, int W, int Cin, int Cout) {
+  HaloWgradPlan best;
+  memset(&best, 0, sizeof(best));
+  const int N = (Cin + 15) / 16 * 16;
+  if (W + 2 > 256 || Cout > 64 || Cout < 8 || Cin < 8 || 9 * N > 512) return best;
+  const int Wp = W + 2;
+  double best_cost = 1e30;
+  static const int forced_tr = getenv("TOK_HALO_WGRAD_TR") ? atoi(getenv("TOK_HALO_WGRAD_TR")) : 0;
+  for (int TR = 1; TR <= 16 && TR <= H; ++TR) {
+    if (forced_tr && TR != forced_tr) continue;
+    const int ksteps = (TR * Wp + 15) / 16;
+    const int drows = ksteps * 16;
+    const int xrows = drows + 2 * Wp + 2;
+    const int dy_stride = (drows * 128 + 1023) / 1024 * 1024;
+    const int x_stride = (xrows * 128 + 1023) / 1024 * 1024;
+    int stages = (kHaloSmemLimit - 256) / (dy_stride + x_stride);
+    if (stages > 4) stages = 4;
+    if (stages < 2) break;
+    // per tile: reduction steps x 9 taps (shared-memory operand bound), amortised over the valid pixels; a tile count
+    // that does not fill the last wave costs a whole tile
+    const long long tiles = (long long)n_img * ((H + TR - 1) / TR);
+    const long long waves = (tiles + num_sms() - 1) / num_sms();
+    const double cost = (double)waves * (ksteps * 9.0 + 40.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best.ok = true;
+      best.N = N; best.TR = TR; best.ksteps = ksteps; best.dy_bytes = TR * Wp * 128; best.x_bytes = (TR + 2) * Wp * 128;
+      best.dy_stride = dy_stride; best.x_stride = x_stride; best.stages = stages;
+      best.tmem_cols = pow2_at_least(9 * N);
+      best.smem = stages * (dy_stride + x_stride) + 256 + 1024;
+    }
+  }
+  return best;
+}
+
+bool conv3x3_wgrad_halo_eligible(int n_img, int H, int W, int Cin, int Cout) {
+  const char* e = getenv("TOK_CONV_HALO");
+  if (e && atoi(e) == 0) return false;
+  return halo_wgrad_plan(n_img, H, W, Cin, Cout).ok;
+}
+
+static int make_halo_tmap(CUtensorMap* tm, const void* base, int n_img, int H, int W, int C, int box_w, int box_h) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return set_error(TOK_ERR_NODRIVER, "cuTensorMapEncodeTiled unavailable");
+  if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(TOK_ERR_INVALID, "conv3x3 halo: operand not 16-byte aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(TOK_ERR_CUDA, "conv3x3 halo: cuTensorMapEncodeTiled failed (%d) C=%d W=%d H=%d N=%d box=%d,%d", (int)r,
+                     C, W, H, n_img, box_w, box_h);
+  return TOK_OK;
+}
+
+// x: [n_img][H][W][Cin], dy: [n_img][H][W][Cout] bf16; dw: [Cout][3][3][Cin] fp32, accumulated.
+int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, int W, int Cin, int Cout, float* dw,
+                              cudaStream_t st) {
+  const HaloWgradPlan pl = halo_wgrad_plan(n_img, H, W, Cin, Cout);
+  if (!pl.ok) return set_error(TOK_ERR_INVALID, "conv3x3 halo wgrad: unsupported shape");
+  CUtensorMap tmDY, tmX;
+  int rc = make_halo_tmap(&tmDY, dy, n_img, H, W, Cout, W + 2, pl.TR);
+  if (rc) return rc;
+  rc = make_halo_tmap(&tmX, x, n_img, H, W, Cin, W + 2, pl.TR + 2);
+  if (rc) return rc;
+  static const bool debug = getenv("TOK_HALO_DEBUG") != nullptr;
+  if (debug)
+    fprintf(stderr, "halo wgrad n%d %dx%dx%d->%d: N %d TR %d ksteps %d stages %d smem %d tmem %d\n", n_img, Cin, H, W, Cout,
+            pl.N, pl.TR, pl.ksteps, pl.stages, pl.smem, pl.tmem_cols);
+  HaloWgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = n_img; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.N = pl.N; p.TR = pl.TR; p.ksteps = pl.ksteps;
+  p.dy_bytes = pl.dy_bytes; p.x_bytes = pl.x_bytes; p.dy_stride = pl.dy_stride; p.x_stride = pl.x_stride;
+  p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.dw = dw;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv3x3 halo wgrad: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long tiles = (long long)n_img * ((H + pl.TR - 1) / pl.TR);
+  const int grid = tiles < num_sms() ? (int)tiles : num_sms();
+  conv3x3_wgrad_halo_kernel<<<grid, 192, pl.smem, st>>>(tmDY, tmX, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv3x3 halo wgrad launch: %s", cudaGetErrorString(e));
   return TOK_OK;
 }
 
