@@ -47,7 +47,16 @@ typedef struct {
   int k;               /* output channels */
   int r, s;            /* filter */
   int stride, pad, dil;
+  /* Optional (0 = k / c): dimensions of the WEIGHT tensor [wk][r][s][wc] when they differ from the activation pitches
+   * k / c — a channel count that is not a multiple of 8 (HRNet's 18 / 36-channel branches,
+   * torchok/models/backbones/hrnet.py:140-192) keeps its weights and weight gradient unpadded; activations still carry
+   * the pitch rounded up to 8 with zero pad lanes.  Supported where tok_conv_halo_caps() says so. */
+  int wk, wc;
 } tokConvDesc;
+
+/* Bit mask of the operations of this convolution that run on the halo 3x3 kernels (tok_conv3.cu) and therefore accept
+ * unpadded weights (wk / wc): 1 = fprop, 2 = dgrad, 4 = wgrad. */
+int tok_conv_halo_caps(const tokConvDesc* d);
 
 /* Output spatial size of a convolution (same arithmetic as torch.nn.Conv2d). */
 void tok_conv_out_hw(const tokConvDesc* d, int* p, int* q);
@@ -110,6 +119,15 @@ int tok_bn_finalize_train(int C, double count, float* sum, float* sqsum, const f
                           float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
 int tok_bn_finalize_eval(int C, const float* running_mean, const float* running_var, const float* gamma,
                          const float* beta, float eps, float* scale, float* shift, void* stream);
+/* The same with gamma / beta / running statistics that hold only c_valid <= C entries: channels c_valid .. C-1 are the
+ * pad lanes of a channel count that is not a multiple of 8 (nn.BatchNorm2d(18) of HRNet); they get scale = shift = 0
+ * and the parameter buffers are never touched past c_valid. */
+int tok_bn_finalize_train_cv(int C, int c_valid, double count, float* sum, float* sqsum, const float* gamma,
+                             const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                             float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+int tok_bn_finalize_eval_cv(int C, int c_valid, const float* running_mean, const float* running_var,
+                            const float* gamma, const float* beta, float eps, float* scale, float* shift,
+                            void* stream);
 /* out = act(y*scale + shift (+residual)) over a [rows][C] bf16 matrix */
 int tok_bn_apply(long long rows, int C, const void* y, const float* scale, const float* shift, const void* residual,
                  int relu, void* out, void* stream);
@@ -121,6 +139,9 @@ int tok_bn_bwd_reduce(long long rows, int C, const void* dout, const void* dout2
 int tok_bn_bwd_finalize(int C, double count, float* sum_g, float* sum_gy, const float* save_mean,
                         const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1, float* coef_c0,
                         float* dgamma, float* dbeta, int accumulate, void* stream);
+int tok_bn_bwd_finalize_cv(int C, int c_valid, double count, float* sum_g, float* sum_gy, const float* save_mean,
+                           const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1,
+                           float* coef_c0, float* dgamma, float* dbeta, int accumulate, void* stream);
 /* dy = coef_a*g + coef_c1*y + coef_c0 ; dres (nullable) receives g */
 int tok_bn_bwd_apply(long long rows, int C, const void* dout, const void* dout2, const void* out, const void* y,
                      const float* coef_a, const float* coef_c1, const float* coef_c0, void* dy, void* dres,
@@ -157,6 +178,11 @@ int tok_bn_bwd_reduce2_finalize(long long rows, int C, const void* dout, const v
                                 const float* save_mean, const float* save_invstd, const float* gamma, float* coef_a,
                                 float* coef_c1, float* coef_c0, float* dgamma, float* dbeta, int accumulate,
                                 unsigned* counter, void* stream);
+int tok_bn_bwd_reduce2_finalize_cv(long long rows, int C, int c_valid, const void* dout, const void* dout2, const void* y,
+                                   int mask_mode, const void* bits, const float* scale, const float* shift, float* sum_g,
+                                   float* sum_gy, const float* save_mean, const float* save_invstd, const float* gamma,
+                                   float* coef_a, float* coef_c1, float* coef_c0, float* dgamma, float* dbeta,
+                                   int accumulate, unsigned* counter, void* stream);
 int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
                       const void* bits, const float* scale, const float* shift, const float* coef_a,
                       const float* coef_c1, const float* coef_c0, void* dy, void* dres, void* stream);

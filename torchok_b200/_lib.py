@@ -26,7 +26,7 @@ class TokError(RuntimeError):
 
 
 class tokConvDesc(C.Structure):
-    _fields_ = [(k, C.c_int) for k in ('n', 'h', 'w', 'c', 'k', 'r', 's', 'stride', 'pad', 'dil')]
+    _fields_ = [(k, C.c_int) for k in ('n', 'h', 'w', 'c', 'k', 'r', 's', 'stride', 'pad', 'dil', 'wk', 'wc')]
 
 
 class tokPeerArenas(C.Structure):
@@ -46,6 +46,7 @@ _SIGS = {
     'tok_device_ok': (_i, []),
     'tok_debug_conv_profile': (_i, [_vp, _i]),
     'tok_conv_out_hw': (None, [_pd, _pi, _pi]),
+    'tok_conv_halo_caps': (_i, [_pd]),
     'tok_conv_fprop': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'tok_conv_fprop_bn': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_conv_dgrad_workspace_bytes': (_sz, [_pd]),
@@ -67,6 +68,11 @@ _SIGS = {
     'tok_stem_conv_wgrad': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_bn_finalize_train': (_i, [_i, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_finalize_eval': (_i, [_i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    'tok_bn_finalize_train_cv': (_i, [_i, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_bn_finalize_eval_cv': (_i, [_i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    'tok_bn_bwd_finalize_cv': (_i, [_i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'tok_bn_bwd_reduce2_finalize_cv': (_i, [_ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _i, _vp, _vp]),
     'tok_bn_apply': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     'tok_bn_apply_train_supported': (_i, [_ll, _i]),
     'tok_bn_apply_train': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
@@ -140,7 +146,7 @@ _SIGS = {
                            _vp, _vp, _i, _i, _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
 }
-_RAW = {'tok_bn_apply_train_supported', 'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+_RAW = {'tok_conv_halo_caps', 'tok_bn_apply_train_supported', 'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}
 
 

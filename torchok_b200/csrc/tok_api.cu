@@ -27,8 +27,8 @@ int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, 
                         int transposed, void* out, const void* addend, float* col_sum, float* col_sqsum,
                         cudaStream_t st);
 bool conv3x3_wgrad_halo_eligible(int n_img, int H, int W, int Cin, int Cout);
-int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, int W, int Cin, int Cout, float* dw,
-                              cudaStream_t st);
+int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, int W, int Cin, int Cout, int wK, int wC,
+                              float* dw, cudaStream_t st);
 void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
                         int sh, int sw, cudaStream_t st);
 
@@ -128,7 +128,16 @@ static int check_desc(const tokConvDesc* d) {
       d->dil <= 0 || d->pad < 0)
     return set_error(TOK_ERR_INVALID, "bad conv descriptor");
   if ((d->c % 8) || (d->k % 8)) return set_error(TOK_ERR_INVALID, "channel counts must be multiples of 8 (c=%d k=%d)", d->c, d->k);
+  if (d->wk < 0 || d->wc < 0 || d->wk > d->k || d->wc > d->c)
+    return set_error(TOK_ERR_INVALID, "weight dimensions wk=%d wc=%d exceed the activation pitches k=%d c=%d", d->wk, d->wc,
+                     d->k, d->c);
   return TOK_OK;
+}
+static inline int desc_wk(const tokConvDesc* d) { return d->wk ? d->wk : d->k; }
+static inline int desc_wc(const tokConvDesc* d) { return d->wc ? d->wc : d->c; }
+static inline bool desc_unpadded(const tokConvDesc* d) { return desc_wk(d) != d->k || desc_wc(d) != d->c; }
+static inline bool desc_halo_shape(const tokConvDesc* d) {
+  return d->r == 3 && d->s == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && !getenv("TOK_CONV_V1");
 }
 
 static int pick_bn(int n) { return n <= 64 ? 64 : 128; }
@@ -346,6 +355,15 @@ int tok_debug_conv_profile(long long* host_out, int max_entries) {
   return n;
 }
 
+int tok_conv_halo_caps(const tokConvDesc* d) {
+  if (!d || check_desc(d) != TOK_OK || !desc_halo_shape(d)) return 0;
+  int caps = 0;
+  if (conv3x3_halo_eligible(d->n, d->h, d->w, d->c, d->k)) caps |= 1;
+  if (conv3x3_halo_eligible(d->n, d->h, d->w, d->k, d->c)) caps |= 2;
+  if (conv3x3_wgrad_halo_eligible(d->n, d->h, d->w, d->c, d->k)) caps |= 4;
+  return caps;
+}
+
 void tok_conv_out_hw(const tokConvDesc* d, int* p, int* q) {
   *p = (d->h + 2 * d->pad - d->dil * (d->r - 1) - 1) / d->stride + 1;
   *q = (d->w + 2 * d->pad - d->dil * (d->s - 1) - 1) / d->stride + 1;
@@ -370,10 +388,10 @@ static int conv_fprop_impl(const tokConvDesc* d, const void* x, const void* w, v
   p.bias = bias;
   p.relu = relu;
   const long long M = (long long)d->n * P * Q;
-  if (d->r == 3 && d->s == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && !addend && !bias && !relu && !fin &&
-      !getenv("TOK_CONV_V1") && conv3x3_halo_eligible(d->n, d->h, d->w, d->c, d->k))
-    return launch_conv3x3_halo(x, d->n, d->h, d->w, d->c, d->k, w, d->k, d->c, 0, y, nullptr, sum, sqsum,
+  if (desc_halo_shape(d) && !addend && !bias && !relu && !fin && conv3x3_halo_eligible(d->n, d->h, d->w, d->c, d->k))
+    return launch_conv3x3_halo(x, d->n, d->h, d->w, d->c, d->k, w, desc_wk(d), desc_wc(d), 0, y, nullptr, sum, sqsum,
                                static_cast<cudaStream_t>(stream));
+  if (desc_unpadded(d)) return set_error(TOK_ERR_INVALID, "conv_fprop: unpadded weights (wk / wc) need the halo 3x3 path");
   if (fin) {
     p.fin = *fin;
     p.fin.count = (float)M;
@@ -497,9 +515,10 @@ int tok_conv_dgrad(const tokConvDesc* d, const void* dy, const void* w, void* dx
     }
     return run_fwd(dy, d->n, P, Q, d->k, src, (long long)d->n * P * Q, w, d->k, wcols, true, d->c, 0, p, st);
   }
-  if (d->r == 3 && d->s == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && !getenv("TOK_CONV_V1") &&
-      conv3x3_halo_eligible(d->n, d->h, d->w, d->k, d->c))
-    return launch_conv3x3_halo(dy, d->n, d->h, d->w, d->k, d->c, w, d->k, d->c, 1, dx, addend, nullptr, nullptr, st);
+  if (desc_halo_shape(d) && conv3x3_halo_eligible(d->n, d->h, d->w, d->k, d->c))
+    return launch_conv3x3_halo(dy, d->n, d->h, d->w, d->k, d->c, w, desc_wk(d), desc_wc(d), 1, dx, addend, nullptr, nullptr,
+                               st);
+  if (desc_unpadded(d)) return set_error(TOK_ERR_INVALID, "conv_dgrad: unpadded weights (wk / wc) need the halo 3x3 path");
   // RxS filter: stride-1 correlation of (zero-dilated) dy with the flipped filter.
   const int pad_h = (d->r - 1) * d->dil - d->pad;
   const int pad_w = (d->s - 1) * d->dil - d->pad;
@@ -575,9 +594,10 @@ int tok_conv_wgrad(const tokConvDesc* d, const void* x, const void* dy, float* d
   if (rc) return rc;
   int P, Q;
   tok_conv_out_hw(d, &P, &Q);
-  if (d->r == 3 && d->s == 3 && d->stride == 1 && d->pad == 1 && d->dil == 1 && !getenv("TOK_CONV_V1") &&
-      conv3x3_wgrad_halo_eligible(d->n, d->h, d->w, d->c, d->k))
-    return launch_conv3x3_wgrad_halo(x, dy, d->n, d->h, d->w, d->c, d->k, dw, static_cast<cudaStream_t>(stream));
+  if (desc_halo_shape(d) && conv3x3_wgrad_halo_eligible(d->n, d->h, d->w, d->c, d->k))
+    return launch_conv3x3_wgrad_halo(x, dy, d->n, d->h, d->w, d->c, d->k, desc_wk(d), desc_wc(d), dw,
+                                     static_cast<cudaStream_t>(stream));
+  if (desc_unpadded(d)) return set_error(TOK_ERR_INVALID, "conv_wgrad: unpadded weights (wk / wc) need the halo 3x3 path");
   PixelSrc src = conv_src(d, P, Q);
   return run_wgrad(x, d->n, d->h, d->w, d->c, src, dy, (long long)d->n * P * Q, d->k, dw,
                    static_cast<cudaStream_t>(stream));

@@ -182,6 +182,7 @@ struct BwdFin {
   float* dbeta;
   int accumulate;
   int C;
+  int Cv;   // channels that exist in gamma / dgamma / dbeta (C rounded DOWN from the padded pitch); pad lanes: gamma = 0
 };
 
 template <int MASK, bool HAS2>
@@ -268,15 +269,16 @@ bn_bwd_reduce2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ 
         const float sgx = is * (__ldcg(sum_gy + c) - mu * sg);
         sum_g[c] = 0.f;   // consumed: handed back zeroed (see bn_bwd_finalize_kernel)
         sum_gy[c] = 0.f;
-        const float g = fin.gamma ? fin.gamma[c] : 1.f;
+        const bool real = c < fin.Cv;
+        const float g = real ? (fin.gamma ? fin.gamma[c] : 1.f) : 0.f;
         const float a = g * is;
         const float k1 = sg / fin.count;
         const float k2 = sgx / fin.count;
         fin.coef_a[c] = a;
         fin.coef_c1[c] = -a * k2 * is;
         fin.coef_c0[c] = -a * k1 + a * k2 * is * mu;
-        if (fin.dgamma) fin.dgamma[c] = fin.accumulate ? fin.dgamma[c] + sgx : sgx;
-        if (fin.dbeta) fin.dbeta[c] = fin.accumulate ? fin.dbeta[c] + sg : sg;
+        if (fin.dgamma && real) fin.dgamma[c] = fin.accumulate ? fin.dgamma[c] + sgx : sgx;
+        if (fin.dbeta && real) fin.dbeta[c] = fin.accumulate ? fin.dbeta[c] + sg : sg;
       }
       if (threadIdx.x == 0) *fin.counter = 0u;
     }
@@ -826,6 +828,17 @@ int tok_bn_bwd_reduce2_finalize(long long rows, int C, const void* dout, const v
                                 const float* save_mean, const float* save_invstd, const float* gamma, float* coef_a,
                                 float* coef_c1, float* coef_c0, float* dgamma, float* dbeta, int accumulate,
                                 unsigned* counter, void* stream) {
+  return tok_bn_bwd_reduce2_finalize_cv(rows, C, C, dout, dout2, y, mask_mode, bits, scale, shift, sum_g, sum_gy, save_mean,
+                                        save_invstd, gamma, coef_a, coef_c1, coef_c0, dgamma, dbeta, accumulate, counter,
+                                        stream);
+}
+
+int tok_bn_bwd_reduce2_finalize_cv(long long rows, int C, int c_valid, const void* dout, const void* dout2, const void* y,
+                                   int mask_mode, const void* bits, const float* scale, const float* shift, float* sum_g,
+                                   float* sum_gy, const float* save_mean, const float* save_invstd, const float* gamma,
+                                   float* coef_a, float* coef_c1, float* coef_c0, float* dgamma, float* dbeta,
+                                   int accumulate, unsigned* counter, void* stream) {
+  if (c_valid <= 0 || c_valid > C) return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2_finalize: bad valid channel count");
   if (!counter || !save_mean || !save_invstd || !coef_a || !coef_c1 || !coef_c0)
     return set_error(TOK_ERR_INVALID, "bn_bwd_reduce2_finalize: counter, saved statistics and coefficient outputs are required");
   BwdFin fin;
@@ -841,6 +854,7 @@ int tok_bn_bwd_reduce2_finalize(long long rows, int C, const void* dout, const v
   fin.dbeta = dbeta;
   fin.accumulate = accumulate;
   fin.C = C;
+  fin.Cv = c_valid;
   return launch_bwd_reduce2(rows, C, dout, dout2, y, mask_mode, bits, scale, shift, sum_g, sum_gy, fin, stream);
 }
 

@@ -159,8 +159,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const HaloParams p)
             const int kb = t % p.KBLK;
             const int tap = t / p.KBLK;
             const int c = kb * KB + ch * 8;
-            if (n0 + n < p.wK && c < p.wC)
-              v[u] = __ldg(reinterpret_cast<const uint4*>(p.w + (static_cast<long long>(n0 + n) * 9 + tap) * p.wC + c));
+            if (n0 + n < p.wK && c < p.wC) {
+              const __nv_bfloat16* src = p.w + (static_cast<long long>(n0 + n) * 9 + tap) * p.wC + c;
+              if ((p.wC & 7) == 0) {
+                v[u] = __ldg(reinterpret_cast<const uint4*>(src));
+              } else {   // unpadded weights of a channel count that is not a multiple of 8: element loads, zero tail
+                uint32_t w4[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (c + j < p.wC)
+                    w4[j >> 1] |= static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(src) + j)) << ((j & 1) * 16);
+                v[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              }
+            }
             const uint32_t a = slab_s + (tap * p.KBLK + kb) * tile_bytes + n * kRowB + ch * 16;
             dst[u] = a ^ (((a >> 7) & kSwzMask) << 4);
           }
@@ -191,8 +202,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const HaloParams p)
             const int tap = t / p.KBLK;
             const int k = kb * KB + kk;
             const int n = nc * 8;
-            if (k < p.wK && n0 + n < p.wC)
-              v[u] = __ldg(reinterpret_cast<const uint4*>(p.w + (static_cast<long long>(k) * 9 + (8 - tap)) * p.wC + n0 + n));
+            if (k < p.wK && n0 + n < p.wC) {
+              const __nv_bfloat16* src = p.w + (static_cast<long long>(k) * 9 + (8 - tap)) * p.wC + n0 + n;
+              if ((p.wC & 7) == 0) {
+                v[u] = __ldg(reinterpret_cast<const uint4*>(src));
+              } else {
+                uint32_t w4[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (n0 + n + j < p.wC)
+                    w4[j >> 1] |= static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(src) + j)) << ((j & 1) * 16);
+                v[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              }
+            }
             dst[u] = slab_s + (tap * p.KBLK + kb) * tile_bytes + n * kRowB + kk * 2;
           }
         }
@@ -436,7 +458,8 @@ struct HaloWgradParams {
   int dy_stride, x_stride;   // shared-memory bytes reserved per stage for each operand (zero-initialised guard rows included)
   int stages;
   int tmem_cols;
-  float* dw;             // [Cout][9][Cin] fp32, accumulated
+  int wK, wC;            // dimensions of dw (<= Cout / Cin: unpadded gradient of a channel count that is not a multiple of 8)
+  float* dw;             // [wK][9][wC] fp32, accumulated
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -537,14 +560,20 @@ conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
           uint32_t r[16];
           tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tap * p.N + c0, r);
           tmem_ld_wait();
-          if (lane < 16 && co < p.Cout) {
-            float* dst = p.dw + (static_cast<long long>(co) * 9 + tap) * p.Cin + c0;
+          if (lane < 16 && co < p.wK) {
+            float* dst = p.dw + (static_cast<long long>(co) * 9 + tap) * p.wC + c0;
+            if ((p.wC & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              if (c0 + j < p.Cin)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "r"(r[j]), "r"(r[j + 1]),
-                             "r"(r[j + 2]), "r"(r[j + 3])
-                             : "memory");
+              for (int j = 0; j < 16; j += 4)
+                if (c0 + j < p.wC)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "r"(r[j]), "r"(r[j + 1]),
+                               "r"(r[j + 2]), "r"(r[j + 3])
+                               : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.wC) atomicAdd(dst + j, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -799,9 +828,9 @@ static int make_halo_tmap(CUtensorMap* tm, const void* base, int n_img, int H, i
   return TOK_OK;
 }
 
-// x: [n_img][H][W][Cin], dy: [n_img][H][W][Cout] bf16; dw: [Cout][3][3][Cin] fp32, accumulated.
-int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, int W, int Cin, int Cout, float* dw,
-                              cudaStream_t st) {
+// x: [n_img][H][W][Cin], dy: [n_img][H][W][Cout] bf16; dw: [wK][3][3][wC] fp32 (wK <= Cout, wC <= Cin), accumulated.
+int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, int W, int Cin, int Cout, int wK, int wC,
+                              float* dw, cudaStream_t st) {
   const HaloWgradPlan pl = halo_wgrad_plan(n_img, H, W, Cin, Cout);
   if (!pl.ok) return set_error(TOK_ERR_INVALID, "conv3x3 halo wgrad: unsupported shape");
   CUtensorMap tmDY, tmX;
@@ -817,7 +846,7 @@ int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, i
   memset(&p, 0, sizeof(p));
   p.n_img = n_img; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.N = pl.N; p.TR = pl.TR; p.ksteps = pl.ksteps;
   p.dy_bytes = pl.dy_bytes; p.x_bytes = pl.x_bytes; p.dy_stride = pl.dy_stride; p.x_stride = pl.x_stride;
-  p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.dw = dw;
+  p.stages = pl.stages; p.tmem_cols = pl.tmem_cols; p.dw = dw; p.wK = wK; p.wC = wC;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);

@@ -76,7 +76,8 @@ __global__ void bn_finalize_train_kernel(float* __restrict__ sum, float* __restr
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* running_mean, float* running_var,
                                          float* __restrict__ scale, float* __restrict__ shift,
-                                         float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+                                         float* __restrict__ save_mean, float* __restrict__ save_invstd, int C,
+                                         int Cv) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float mean = sum[c] / count;
@@ -85,13 +86,16 @@ __global__ void bn_finalize_train_kernel(float* __restrict__ sum, float* __restr
   sum[c] = 0.f;  // consumed: the accumulators are handed back zeroed for the next step (no memset launches)
   sqsum[c] = 0.f;
   const float invstd = rsqrtf(var + eps);
-  const float g = gamma ? gamma[c] : 1.f;
-  const float b = beta ? beta[c] : 0.f;
+  // c >= Cv: pad lane of a channel count that is not a multiple of 8 (gamma / beta / running buffers hold Cv entries);
+  // gamma = beta = 0 keeps the lane exactly zero
+  const bool real = c < Cv;
+  const float g = real ? (gamma ? gamma[c] : 1.f) : 0.f;
+  const float b = real ? (beta ? beta[c] : 0.f) : 0.f;
   scale[c] = g * invstd;
   shift[c] = b - mean * g * invstd;
   save_mean[c] = mean;
   save_invstd[c] = invstd;
-  if (running_mean) {
+  if (running_mean && real) {
     const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
@@ -99,9 +103,14 @@ __global__ void bn_finalize_train_kernel(float* __restrict__ sum, float* __restr
 }
 __global__ void bn_finalize_eval_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                        float* __restrict__ scale, float* __restrict__ shift, int C) {
+                                        float* __restrict__ scale, float* __restrict__ shift, int C, int Cv) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (c >= Cv) {   // pad lane
+    scale[c] = 0.f;
+    shift[c] = 0.f;
+    return;
+  }
   const float invstd = rsqrtf(running_var[c] + eps);
   const float g = gamma ? gamma[c] : 1.f;
   const float b = beta ? beta[c] : 0.f;
@@ -225,7 +234,7 @@ __global__ void bn_bwd_finalize_kernel(float* __restrict__ sum_g, float* __restr
                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                        const float* __restrict__ gamma, float count, float* __restrict__ coef_a,
                                        float* __restrict__ coef_c1, float* __restrict__ coef_c0, float* dgamma,
-                                       float* dbeta, int accumulate, int C) {
+                                       float* dbeta, int accumulate, int C, int Cv) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sg = sum_g[c];
@@ -234,15 +243,16 @@ __global__ void bn_bwd_finalize_kernel(float* __restrict__ sum_g, float* __restr
   const float sgx = is * (sum_gy[c] - mu * sg);
   sum_g[c] = 0.f;  // consumed (see bn_finalize_train_kernel)
   sum_gy[c] = 0.f;
-  const float g = gamma ? gamma[c] : 1.f;
+  const bool real = c < Cv;
+  const float g = real ? (gamma ? gamma[c] : 1.f) : 0.f;
   const float a = g * is;
   const float k1 = sg / count;
   const float k2 = sgx / count;
   coef_a[c] = a;
   coef_c1[c] = -a * k2 * is;
   coef_c0[c] = -a * k1 + a * k2 * is * mu;
-  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + sgx : sgx;
-  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + sg : sg;
+  if (dgamma && real) dgamma[c] = accumulate ? dgamma[c] + sgx : sgx;
+  if (dbeta && real) dbeta[c] = accumulate ? dbeta[c] + sg : sg;
 }
 
 // Pass 2: dy = a*g + c1*y + c0 ; optionally also stores g (the gradient that flows to the residual branch).
@@ -860,24 +870,35 @@ using namespace tok;
 
 extern "C" {
 
-int tok_bn_finalize_train(int C, double count, float* sum, float* sqsum, const float* gamma,
-                          const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                          float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
-  if (C <= 0 || count <= 0) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
+int tok_bn_finalize_train_cv(int C, int c_valid, double count, float* sum, float* sqsum, const float* gamma,
+                             const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                             float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+  if (C <= 0 || count <= 0 || c_valid <= 0 || c_valid > C) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
   bn_finalize_train_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       sum, sqsum, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
-      save_invstd, C);
+      save_invstd, C, c_valid);
   TOK_CHECK_LAUNCH("bn_finalize_train");
   return TOK_OK;
 }
+int tok_bn_finalize_train(int C, double count, float* sum, float* sqsum, const float* gamma,
+                          const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                          float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+  return tok_bn_finalize_train_cv(C, C, count, sum, sqsum, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                                  shift, save_mean, save_invstd, stream);
+}
 
-int tok_bn_finalize_eval(int C, const float* running_mean, const float* running_var, const float* gamma,
-                         const float* beta, float eps, float* scale, float* shift, void* stream) {
-  if (C <= 0) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
+int tok_bn_finalize_eval_cv(int C, int c_valid, const float* running_mean, const float* running_var,
+                            const float* gamma, const float* beta, float eps, float* scale, float* shift,
+                            void* stream) {
+  if (C <= 0 || c_valid <= 0 || c_valid > C) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
   bn_finalize_eval_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, gamma, beta,
-                                                                               eps, scale, shift, C);
+                                                                               eps, scale, shift, C, c_valid);
   TOK_CHECK_LAUNCH("bn_finalize_eval");
   return TOK_OK;
+}
+int tok_bn_finalize_eval(int C, const float* running_mean, const float* running_var, const float* gamma,
+                         const float* beta, float eps, float* scale, float* shift, void* stream) {
+  return tok_bn_finalize_eval_cv(C, C, running_mean, running_var, gamma, beta, eps, scale, shift, stream);
 }
 
 static int launch_bn_apply(long long rows, int C, const void* y, const float* scale, const float* shift,
@@ -965,15 +986,21 @@ int tok_bn_bwd_reduce(long long rows, int C, const void* dout, const void* dout2
   return TOK_OK;
 }
 
+int tok_bn_bwd_finalize_cv(int C, int c_valid, double count, float* sum_g, float* sum_gy, const float* save_mean,
+                           const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1,
+                           float* coef_c0, float* dgamma, float* dbeta, int accumulate, void* stream) {
+  if (C <= 0 || count <= 0 || c_valid <= 0 || c_valid > C) return set_error(TOK_ERR_INVALID, "bn_bwd_finalize: bad size");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sum_g, sum_gy, save_mean, save_invstd, gamma, (float)count, coef_a, coef_c1, coef_c0, dgamma, dbeta, accumulate,
+      C, c_valid);
+  TOK_CHECK_LAUNCH("bn_bwd_finalize");
+  return TOK_OK;
+}
 int tok_bn_bwd_finalize(int C, double count, float* sum_g, float* sum_gy, const float* save_mean,
                         const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1, float* coef_c0,
                         float* dgamma, float* dbeta, int accumulate, void* stream) {
-  if (C <= 0 || count <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_finalize: bad size");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      sum_g, sum_gy, save_mean, save_invstd, gamma, (float)count, coef_a, coef_c1, coef_c0, dgamma, dbeta, accumulate,
-      C);
-  TOK_CHECK_LAUNCH("bn_bwd_finalize");
-  return TOK_OK;
+  return tok_bn_bwd_finalize_cv(C, C, count, sum_g, sum_gy, save_mean, save_invstd, gamma, coef_a, coef_c1, coef_c0,
+                                dgamma, dbeta, accumulate, stream);
 }
 
 int tok_bn_bwd_apply(long long rows, int C, const void* dout, const void* dout2, const void* out, const void* y,

@@ -223,8 +223,9 @@ def wgrad_async(operands, launch):
 
 
 # ------------------------------------------------------------------------------------------------------ conv
-def conv_desc(n, h, w, c, k, r, s, stride, pad, dil):
-    d = tokConvDesc(n, h, w, c, k, r, s, stride, pad, dil)
+def conv_desc(n, h, w, c, k, r, s, stride, pad, dil, wk=0, wc=0):
+    """`wk` / `wc`: dimensions of an UNPADDED weight tensor (0 = k / c); see include/tokb200.h tokConvDesc."""
+    d = tokConvDesc(n, h, w, c, k, r, s, stride, pad, dil, wk, wc)
     p, q = C.c_int(), C.c_int()
     lib().tok_conv_out_hw(C.byref(d), C.byref(p), C.byref(q))
     return d, p.value, q.value
@@ -249,11 +250,14 @@ def conv_wgrad(d, x, dy, dw):
 class BNState:
     """What a BatchNorm2d module lends to the fused conv+BN unit (torch.nn.BatchNorm2d semantics,
     torchok/models/modules/bricks/convbnact.py:44-46)."""
-    __slots__ = ('weight', 'bias', 'running_mean', 'running_var', 'eps', 'momentum', 'training', 'acc', 'cp')
+    __slots__ = ('weight', 'bias', 'running_mean', 'running_var', 'eps', 'momentum', 'training', 'acc', 'cp', 'cv')
 
-    def __init__(self, weight, bias, running_mean, running_var, eps, momentum, training, acc, cp):
+    def __init__(self, weight, bias, running_mean, running_var, eps, momentum, training, acc, cp, cv=None):
+        """`cp`: channel pitch of the activations (multiple of 8); `cv`: channels that exist in weight / bias / running
+        statistics (HRNet's BatchNorm2d(18): cp 24, cv 18 — the *_cv finalize kernels keep the pad lanes at zero)."""
         self.weight, self.bias, self.running_mean, self.running_var = weight, bias, running_mean, running_var
         self.eps, self.momentum, self.training, self.acc, self.cp = eps, momentum, training, acc, cp
+        self.cv = cp if cv is None else cv
 
 
 MASK_NONE, MASK_Y, MASK_BITS = 0, 1, 2
@@ -288,7 +292,7 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
     rows = n * p * q
     st = _st()
     fused_apply = False
-    if bn.training and bn.acc.shape[0] > 4 and _FUSE_APPLY_FIN and not _FUSE_FWD_FIN and \
+    if bn.training and bn.acc.shape[0] > 4 and _FUSE_APPLY_FIN and not _FUSE_FWD_FIN and bn.cv == kp and \
             (keep and relu and residual is not None or L.tok_bn_apply_train_supported(rows, kp)):
         # conv (+ statistics), then ONE pass that finalizes the statistics and applies them (acc[4] word 2: its ticket)
         acc = bn.acc
@@ -296,19 +300,19 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
         fused_apply = True
     elif bn.training:
         acc = bn.acc
-        if acc.shape[0] > 4 and _FUSE_FWD_FIN:   # conv + statistics + finalize in one launch (acc[4]: ticket counters)
+        if acc.shape[0] > 4 and _FUSE_FWD_FIN and bn.cv == kp:   # conv + statistics + finalize in one launch (acc[4]: ticket counters)
             L.tok_conv_fprop_bn(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias),
                                 bn.eps, bn.momentum, _p(bn.running_mean), _p(bn.running_var), _p(small[0]),
                                 _p(small[1]), _p(small[2]), _p(small[3]), _p(acc[4]), st)
         else:
             L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), None, None, 0, st)
-            L.tok_bn_finalize_train(kp, float(rows), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias), bn.eps,
-                                    bn.momentum, _p(bn.running_mean), _p(bn.running_var), _p(small[0]), _p(small[1]),
-                                    _p(small[2]), _p(small[3]), st)
+            L.tok_bn_finalize_train_cv(kp, bn.cv, float(rows), _p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias), bn.eps,
+                                       bn.momentum, _p(bn.running_mean), _p(bn.running_var), _p(small[0]), _p(small[1]),
+                                       _p(small[2]), _p(small[3]), st)
     else:
         L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), None, None, None, None, 0, st)
-        L.tok_bn_finalize_eval(kp, _p(bn.running_mean), _p(bn.running_var), _p(bn.weight), _p(bn.bias), bn.eps,
-                               _p(small[0]), _p(small[1]), st)
+        L.tok_bn_finalize_eval_cv(kp, bn.cv, _p(bn.running_mean), _p(bn.running_var), _p(bn.weight), _p(bn.bias), bn.eps,
+                                  _p(small[0]), _p(small[1]), st)
     out = torch.empty_like(y) if keep else y
     bits, mode = None, MASK_NONE
     fin_args = ()
@@ -353,10 +357,11 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
             L.tok_bn_bwd_reduce2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                                  _p(acc[2]), _p(acc[3]), st)
             invstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+            cv = bn.cv
             if dgamma is not None:
-                dgamma += (acc[3] - bn.running_mean.float() * acc[2]) * invstd
+                dgamma += (acc[3, :cv] - bn.running_mean.float() * acc[2, :cv]) * invstd
             if dbeta is not None:
-                dbeta += acc[2]
+                dbeta += acc[2, :cv]
             acc[2:4].zero_()
         coefs[0].copy_(small[0])
         coefs[1:].zero_()
@@ -367,14 +372,15 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
         return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
                                    wgrad_direct)
     if acc.shape[0] > 4 and _FUSE_BWD_FIN:   # reduce + finalize in one launch (acc[4]: the layer's ticket counters)
-        L.tok_bn_bwd_reduce2_finalize(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
-                                      _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight), _p(coefs[0]),
-                                      _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, acc[4].data_ptr() + 4, st)
+        L.tok_bn_bwd_reduce2_finalize_cv(rows, kp, bn.cv, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]),
+                                         _p(small[1]), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
+                                         _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1,
+                                         acc[4].data_ptr() + 4, st)
     else:
         L.tok_bn_bwd_reduce2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                              _p(acc[2]), _p(acc[3]), st)
-        L.tok_bn_bwd_finalize(kp, float(rows), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
-                              _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, st)
+        L.tok_bn_bwd_finalize_cv(kp, bn.cv, float(rows), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
+                                 _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, st)
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
     L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),

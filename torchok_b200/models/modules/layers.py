@@ -16,6 +16,8 @@ from ... import kernels as K
 from ..._lib import lib
 
 BF16, F32 = K.BF16, K.F32
+# TOK_DIRECT_HALO=0: A/B aid — padded temporaries around every conv of a channel count that is not a multiple of 8 (r1 path)
+_DIRECT_HALO = __import__('os').environ.get('TOK_DIRECT_HALO', '1') != '0'
 
 
 def _single(v, what):
@@ -58,15 +60,27 @@ class Conv2d(nn.Conv2d):
         self.cin_p = off
         self._descs = {}
 
-    def desc(self, x):
+    def desc(self, x, allow_direct=True):
+        """tokConvDesc for this input.  A padded channel count (18 -> 24) whose three operations all run on the halo
+        3x3 kernels gets the DIRECT form: `wk` / `wc` name the real weight dimensions, so the kernels read the arena's
+        unpadded bf16 shadow and accumulate into the parameter's own fp32 gradient — no padded temporaries, no torch
+        copy kernels around the launch (they were ~26 tiny launches per unit and step in HRNet)."""
         n, _, h, w = x.shape
-        key = (n, h, w)
+        key = (n, h, w, allow_direct)
         hit = self._descs.get(key)
         if hit is None:
             r, s = self.kernel_size
             d, p, q = K.conv_desc(n, h, w, self.cin_p, self.cout_p, r, s, self.tok_stride, self.tok_pad, self.tok_dil)
+            if allow_direct and self.padded and self.tok_in_map is None and _DIRECT_HALO and \
+                    lib().tok_conv_halo_caps(C.byref(d)) == 7:
+                d, p, q = K.conv_desc(n, h, w, self.cin_p, self.cout_p, r, s, self.tok_stride, self.tok_pad, self.tok_dil,
+                                      self.out_channels, self.in_channels)
             hit = self._descs[key] = (d, (p, q))
         return hit
+
+    @staticmethod
+    def is_direct(d):
+        return d is not None and (d.wk != 0 or d.wc != 0)
 
     @property
     def padded(self):
@@ -79,14 +93,14 @@ class Conv2d(nn.Conv2d):
             self.tok_in_map = self.tok_in_map.to(device)
         return self.tok_in_map
 
-    def shadow(self):
-        """bf16 [Kp][R][S][Cp] weights for the kernels."""
+    def shadow(self, d=None):
+        """bf16 [Kp][R][S][Cp] weights for the kernels ([K][R][S][C] unpadded for a direct descriptor)."""
         w = self.weight
         if not K.is_krsc(w):
             w.data = w.data.contiguous(memory_format=torch.channels_last)
             if not K.is_krsc(w):  # 1x1 / single-channel corner cases of torch's stride normalisation
                 w.data = w.data.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
-        if not self.padded:
+        if not self.padded or self.is_direct(d):
             return K.shadow_of(w)
         r, s = self.kernel_size
         full = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=BF16, device=w.device)
@@ -94,12 +108,13 @@ class Conv2d(nn.Conv2d):
         full[:self.out_channels, :, :, self._in_index(w.device)] = tmp.permute(0, 2, 3, 1)
         return full
 
-    def wgrad_target(self):
-        """(buffer the wgrad kernel accumulates into, finish()) — the parameter's own fp32 .grad when unpadded."""
+    def wgrad_target(self, d=None):
+        """(buffer the wgrad kernel accumulates into, finish()) — the parameter's own fp32 .grad when unpadded (or when the
+        descriptor is direct)."""
         if not self.weight.requires_grad:
             return None, None
         g = K.grad_buffer(self.weight)
-        if not self.padded and K.is_krsc(g):
+        if (not self.padded or self.is_direct(d)) and K.is_krsc(g):
             return g, None
         r, s = self.kernel_size
         tmp = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=F32, device=g.device)
@@ -130,8 +145,8 @@ class BatchNorm2d(nn.BatchNorm2d):
 
     def state(self, count_batch=True):
         """BNState for the fused unit.  When the channel count is not a multiple of 8 (HRNet's 18 / 36-channel
-        branches) the kernels see zero-padded copies of weight / bias / running stats (pad lanes: gamma = beta = 0, so
-        they stay exactly zero); `commit()` copies the updated running statistics back."""
+        branches) the activations carry zero pad lanes up to `cp`; weight / bias / running statistics keep their real
+        size `cv` and the *_cv finalize kernels give the pad lanes scale = shift = 0."""
         if self._tok_acc.dtype != F32:
             self._tok_acc = self._tok_acc.float()
         # `track_running_stats` switched off after construction (FreezeUnfreeze's `bn_track_running_stats: false`,
@@ -140,26 +155,12 @@ class BatchNorm2d(nn.BatchNorm2d):
         momentum = self.momentum if self.track_running_stats else 0.0
         if self.training and count_batch and self.track_running_stats:
             self._pending_batches += 1
-        if self.cp == self.num_features:
-            return K.BNState(self.weight, self.bias, self.running_mean, self.running_var, self.eps, momentum,
-                             self.training, self._tok_acc, self.cp)
-        c, dev = self.num_features, self.weight.device
-        pad = torch.zeros((4, self.cp), dtype=F32, device=dev)
-        pad[3].fill_(1.0)
-        pad[0, :c] = self.weight.detach()
-        pad[1, :c] = self.bias.detach()
-        pad[2, :c] = self.running_mean
-        pad[3, :c] = self.running_var
-        self._tok_pad = pad
-        return K.BNState(pad[0], pad[1], pad[2], pad[3], self.eps, momentum, self.training, self._tok_acc,
-                         self.cp)
+        return K.BNState(self.weight, self.bias, self.running_mean, self.running_var, self.eps, momentum,
+                         self.training, self._tok_acc, self.cp, self.num_features)
 
     def commit(self):
-        """Copy running statistics updated on padded temporaries back into the real buffers."""
-        if self.cp != self.num_features and self.training and getattr(self, '_tok_pad', None) is not None:
-            c = self.num_features
-            self.running_mean.copy_(self._tok_pad[2, :c])
-            self.running_var.copy_(self._tok_pad[3, :c])
+        """(r1 copied running statistics back from padded temporaries; the *_cv finalize kernels now work on the real
+        buffers, so there is nothing to do.)"""
 
     def forward(self, x):
         raise NotImplementedError('torchok_b200.BatchNorm2d is executed fused with its producer conv '
@@ -182,30 +183,17 @@ def _bn_grads(bn):
 
 def _unit_fwd(x, conv, bn, relu, residual, keep):
     d, pq = conv.desc(x)
-    res = K.unit_forward(x, d, pq, conv.shadow(), bn.state(), relu, residual, keep)
-    bn.commit()
+    res = K.unit_forward(x, d, pq, conv.shadow(d), bn.state(), relu, residual, keep)
     return res, d
 
 
 def _unit_bwd(saved, d, conv, bn, dout, **kw):
-    wbuf, finish = conv.wgrad_target()
+    wbuf, finish = conv.wgrad_target(d)
     gw, gb = _bn_grads(bn)
-    padded = bn.cp != bn.num_features
-    if padded:
-        st = bn.state(count_batch=False)
-        tmp = torch.zeros((2, bn.cp), dtype=F32, device=dout.device)
-        out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf,
-                              dgamma=tmp[0] if gw is not None else None, dbeta=tmp[1] if gb is not None else None, **kw)
-        c = bn.num_features
-        if gw is not None:
-            gw.add_(tmp[0, :c])
-        if gb is not None:
-            gb.add_(tmp[1, :c])
-    else:
-        st = K.BNState(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, bn.training,
-                       bn._tok_acc, bn.cp)
-        out = K.unit_backward(saved, d, conv.shadow(), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb,
-                              wgrad_direct=finish is None, **kw)
+    st = K.BNState(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, bn.training,
+                   bn._tok_acc, bn.cp, bn.num_features)
+    out = K.unit_backward(saved, d, conv.shadow(d), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb,
+                          wgrad_direct=finish is None, **kw)
     if finish:
         finish()
     K.grad_ready(conv.weight)
@@ -262,7 +250,7 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, conv, relu, weight, bias):
         x = K.to_nhwc(x)
-        d, (p, q) = conv.desc(x)
+        d, (p, q) = conv.desc(x, allow_direct=False)   # bias / ReLU epilogues live in the generic kernel
         w = conv.shadow()
         b = bias
         if bias is not None:
