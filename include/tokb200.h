@@ -178,6 +178,19 @@ int tok_bn_bwd_reduce2_finalize(long long rows, int C, const void* dout, const v
                                 const float* save_mean, const float* save_invstd, const float* gamma, float* coef_a,
                                 float* coef_c1, float* coef_c0, float* dgamma, float* dbeta, int accumulate,
                                 unsigned* counter, void* stream);
+/* "Chain" form of the fused finalize + apply (r2): every CTA derives scale / shift of its channels from the batch sums,
+ * CTA 0 publishes scale / shift / saved mean / invstd and updates the running statistics — and, instead of a ticket to
+ * zero the sums, zeroes the zero_n floats at zero_ptr: the accumulators the PREVIOUS chain launch of the same stream
+ * left behind (NULL / 0 for the first).  The caller keeps that pointer; sum / sqsum of this launch stay non-zero until
+ * the next chain launch (or an explicit memset).  Replaces the single-CTA tok_bn_finalize_train launch per unit. */
+int tok_bn_apply_chain(long long rows, int C, int c_valid, const void* y, float* sum, float* sqsum, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                       float* scale, float* shift, float* save_mean, float* save_invstd, float* zero_ptr, int zero_n,
+                       const void* residual, int relu, void* out, void* stream);
+int tok_bn_apply_bits_chain(long long rows, int C, int c_valid, const void* y, float* sum, float* sqsum,
+                            const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                            float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
+                            float* zero_ptr, int zero_n, const void* residual, void* out, void* bits, void* stream);
 int tok_bn_bwd_reduce2_finalize_cv(long long rows, int C, int c_valid, const void* dout, const void* dout2, const void* y,
                                    int mask_mode, const void* bits, const float* scale, const float* shift, float* sum_g,
                                    float* sum_gy, const float* save_mean, const float* save_invstd, const float* gamma,

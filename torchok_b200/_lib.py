@@ -77,6 +77,8 @@ _SIGS = {
     'tok_bn_apply_train_supported': (_i, [_ll, _i]),
     'tok_bn_apply_train': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     'tok_bn_apply_bits_train': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_bn_apply_chain': (_i, [_ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
+    'tok_bn_apply_bits_chain': (_i, [_ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_reduce': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_finalize': (_i, [_i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'tok_bn_bwd_apply': (_i, [_ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

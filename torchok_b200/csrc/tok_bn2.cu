@@ -122,12 +122,12 @@ bn_apply_bits_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res,
   __shared__ int s_flag;
   const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
   float sc[8], sf[8];
-  if (fin.counter != nullptr) {
+  if (fin.fused) {
     if (m.cv < cvec) applyfin_coefs(fin, m.cv * 8, sc, sf);
     applyfin_publish(fin, blockIdx.x == 0 && blockIdx.y == 0, gridDim.x * gridDim.y, &s_flag);
   }
   if (!m.active) return;
-  if (fin.counter == nullptr) {
+  if (!fin.fused) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sc[j] = __ldg(scale + m.cv * 8 + j);
@@ -680,7 +680,40 @@ int tok_bn_apply_bits_train(long long rows, int C, const void* y, float* sum, fl
   if (!sum || !sqsum || !scale || !shift || !save_mean || !save_invstd || !counter)
     return set_error(TOK_ERR_INVALID, "bn_apply_bits_train: accumulators, outputs and the ticket counter are required");
   ApplyFin fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.fused = 1;
+  fin.Cv = C;
   fin.counter = counter;
+  fin.sum = sum;
+  fin.sqsum = sqsum;
+  fin.count = (float)rows;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.scale = scale;
+  fin.shift = shift;
+  fin.save_mean = save_mean;
+  fin.save_invstd = save_invstd;
+  fin.C = C;
+  return launch_apply_bits(rows, C, y, scale, shift, residual, out, bits, fin, stream);
+}
+
+int tok_bn_apply_bits_chain(long long rows, int C, int c_valid, const void* y, float* sum, float* sqsum,
+                            const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                            float* running_var, float* scale, float* shift, float* save_mean, float* save_invstd,
+                            float* zero_ptr, int zero_n, const void* residual, void* out, void* bits, void* stream) {
+  if (!sum || !sqsum || !scale || !shift || !save_mean || !save_invstd || c_valid <= 0 || c_valid > C || zero_n < 0 ||
+      (zero_n > 0 && !zero_ptr))
+    return set_error(TOK_ERR_INVALID, "bn_apply_bits_chain: accumulators and outputs are required");
+  ApplyFin fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.fused = 1;
+  fin.Cv = c_valid;
+  fin.zero_ptr = zero_ptr;
+  fin.zero_n = zero_n;
   fin.sum = sum;
   fin.sqsum = sqsum;
   fin.count = (float)rows;

@@ -15,8 +15,9 @@ __device__ __forceinline__ void applyfin_coefs(const ApplyFin& f, int c0, float 
     float var = __ldcg(f.sqsum + c) / f.count - mean * mean;
     var = fmaxf(var, 0.f);
     const float invstd = rsqrtf(var + f.eps);
-    const float g = f.gamma ? f.gamma[c] : 1.f;
-    const float b = f.beta ? f.beta[c] : 0.f;
+    const bool real = c < f.Cv;
+    const float g = real ? (f.gamma ? f.gamma[c] : 1.f) : 0.f;
+    const float b = real ? (f.beta ? f.beta[c] : 0.f) : 0.f;
     sc[j] = g * invstd;
     sf[j] = b - mean * g * invstd;
   }
@@ -32,19 +33,23 @@ __device__ __forceinline__ void applyfin_publish(const ApplyFin& f, bool first, 
       float var = __ldcg(f.sqsum + c) / f.count - mean * mean;
       var = fmaxf(var, 0.f);
       const float invstd = rsqrtf(var + f.eps);
-      const float g = f.gamma ? f.gamma[c] : 1.f;
-      const float b = f.beta ? f.beta[c] : 0.f;
+      const bool real = c < f.Cv;
+      const float g = real ? (f.gamma ? f.gamma[c] : 1.f) : 0.f;
+      const float b = real ? (f.beta ? f.beta[c] : 0.f) : 0.f;
       f.scale[c] = g * invstd;
       f.shift[c] = b - mean * g * invstd;
       f.save_mean[c] = mean;
       f.save_invstd[c] = invstd;
-      if (f.running_mean) {
+      if (f.running_mean && real) {
         const float unbiased = f.count > 1.f ? var * f.count / (f.count - 1.f) : var;
         f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
         f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unbiased;
       }
     }
+    // chain mode: the accumulators the previous fused apply of this stream left behind (that kernel has finished)
+    for (int i = threadIdx.x; i < f.zero_n; i += blockDim.x) f.zero_ptr[i] = 0.f;
   }
+  if (f.counter == nullptr) return;   // chain mode: no ticket, the sums are zeroed by the next fused apply
   __syncthreads();   // every thread of this CTA has read the sums
   if (threadIdx.x == 0) {
     __threadfence();

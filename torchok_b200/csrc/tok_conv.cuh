@@ -51,6 +51,12 @@ struct ApplyFin {
   float* save_mean;
   float* save_invstd;
   int C;
+  // r2 "chain" mode (counter == nullptr, fused != 0): no ticket — the sums stay as they are and are zeroed by the NEXT
+  // fused apply launch of the stream (zero_ptr / zero_n name the accumulators the previous launch left behind).
+  int fused;       // != 0: scale / shift are derived from the sums inside the kernel
+  int Cv;          // channels present in gamma / beta / running statistics (<= C; pad lanes get scale = shift = 0)
+  float* zero_ptr;
+  int zero_n;
 };
 
 // Forward / data-gradient implicit GEMM:  out[m, n] = sum_{tap, c} A_tap[m, c] * Wmat[n, wtap*Cin + c]

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
   const bool invariant = (stride % cvec) == 0;   // the host guarantees it when fin.counter != nullptr
   float sc[8], sf[8];
   int cv = (int)(i % cvec);
-  if (fin.counter != nullptr) {
+  if (fin.fused) {
     applyfin_coefs(fin, cv * 8, sc, sf);
     applyfin_publish(fin, blockIdx.x == 0, gridDim.x, &s_flag);
   } else if (invariant) {
@@ -584,6 +584,26 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, __nv_bfloat16* __
     if (hw < HW && c < Cp) dst[(n * HW + hw) * Cp + c] = __float2bfloat16(tile[threadIdx.x][j]);
   }
 }
+// Few channels (Cp <= 32: the RGB image, the 19-class logit gradient): one thread per pixel reads its C planes (coalesced
+// across the warp) and writes Cp / 8 16-byte vectors.  The 32x32 transpose tile above uses 3 of its 32 channel rows for
+// an image: 573 us for the 100 MB input of the HRNet step against 25 us of traffic.
+template <typename T, int CV>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_small_kernel(const T* __restrict__ src, uint4* __restrict__ dst,
+                                                                 int C, long long HW, long long total) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long n = i / HW, hw = i - n * HW;
+    const T* s = src + n * C * HW + hw;
+    uint32_t w[CV * 4];
+#pragma unroll
+    for (int j = 0; j < CV * 4; ++j) {
+      const float lo = 2 * j < C ? (float)s[(2 * j) * HW] : 0.f;
+      const float hi = 2 * j + 1 < C ? (float)s[(2 * j + 1) * HW] : 0.f;
+      w[j] = pack_bf16x2(lo, hi);
+    }
+#pragma unroll
+    for (int v = 0; v < CV; ++v) dst[i * CV + v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+  }
+}
 // NHWC bf16 (pitch Cp) -> NCHW (fp32 or bf16), first C channels.
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, T* __restrict__ dst, int C, int HW,
@@ -908,7 +928,7 @@ static int launch_bn_apply(long long rows, int C, const void* y, const float* sc
   const int cvec = C / 8;
   const long long total = rows * cvec;
   const int grid = elem_grid(total, 256 * 2);
-  if (fin.counter != nullptr && ((long long)grid * 256) % cvec != 0)
+  if (fin.fused && ((long long)grid * 256) % cvec != 0)
     return set_error(TOK_ERR_INVALID, "bn_apply_train: C / 8 = %d does not divide the grid stride", cvec);
   cudaStream_t st = (cudaStream_t)stream;
   const uint4* yp = (const uint4*)y;
@@ -946,7 +966,40 @@ int tok_bn_apply_train(long long rows, int C, const void* y, float* sum, float* 
   if (!sum || !sqsum || !scale || !shift || !save_mean || !save_invstd || !counter)
     return set_error(TOK_ERR_INVALID, "bn_apply_train: accumulators, outputs and the ticket counter are required");
   ApplyFin fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.fused = 1;
+  fin.Cv = C;
   fin.counter = counter;
+  fin.sum = sum;
+  fin.sqsum = sqsum;
+  fin.count = (float)rows;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.gamma = gamma;
+  fin.beta = beta;
+  fin.running_mean = running_mean;
+  fin.running_var = running_var;
+  fin.scale = scale;
+  fin.shift = shift;
+  fin.save_mean = save_mean;
+  fin.save_invstd = save_invstd;
+  fin.C = C;
+  return launch_bn_apply(rows, C, y, scale, shift, residual, relu, out, fin, stream);
+}
+
+int tok_bn_apply_chain(long long rows, int C, int c_valid, const void* y, float* sum, float* sqsum, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                       float* scale, float* shift, float* save_mean, float* save_invstd, float* zero_ptr, int zero_n,
+                       const void* residual, int relu, void* out, void* stream) {
+  if (!sum || !sqsum || !scale || !shift || !save_mean || !save_invstd || c_valid <= 0 || c_valid > C || zero_n < 0 ||
+      (zero_n > 0 && !zero_ptr))
+    return set_error(TOK_ERR_INVALID, "bn_apply_chain: accumulators and outputs are required");
+  ApplyFin fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.fused = 1;
+  fin.Cv = c_valid;
+  fin.zero_ptr = zero_ptr;
+  fin.zero_n = zero_n;
   fin.sum = sum;
   fin.sqsum = sqsum;
   fin.count = (float)rows;
@@ -1085,6 +1138,22 @@ int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const lo
 
 int tok_nchw_to_nhwc(int n, int c, int hw, int cp, int src_is_bf16, const void* src, void* dst, void* stream) {
   if (n <= 0 || c <= 0 || hw <= 0 || cp < c) return set_error(TOK_ERR_INVALID, "nchw_to_nhwc: bad size");
+  if (cp <= 32 && cp % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const long long total = (long long)n * hw;
+    const int g = elem_grid(total, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define TOK_SMALL(T, CV) nchw_to_nhwc_small_kernel<T, CV><<<g, 256, 0, st>>>((const T*)src, (uint4*)dst, c, hw, total)
+    if (src_is_bf16) {
+      if (cp == 8) TOK_SMALL(__nv_bfloat16, 1); else if (cp == 16) TOK_SMALL(__nv_bfloat16, 2);
+      else if (cp == 24) TOK_SMALL(__nv_bfloat16, 3); else TOK_SMALL(__nv_bfloat16, 4);
+    } else {
+      if (cp == 8) TOK_SMALL(float, 1); else if (cp == 16) TOK_SMALL(float, 2);
+      else if (cp == 24) TOK_SMALL(float, 3); else TOK_SMALL(float, 4);
+    }
+#undef TOK_SMALL
+    TOK_CHECK_LAUNCH("nchw_to_nhwc");
+    return TOK_OK;
+  }
   dim3 grid((hw + 31) / 32, (cp + 31) / 32, n), block(32, 8);
   if (src_is_bf16)
     nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src,

@@ -242,6 +242,93 @@ xent_small_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __r
 }
 
 
+// The same with the row held in registers: ld = 8 * LV channels are fetched as LV 16-byte vectors (one pass instead of
+// three passes of 2-byte loads over a 48-byte row: 626 -> ~150 us for the 8.4 M pixels x 19 classes of the HRNet step).
+template <int LV>
+__global__ void __launch_bounds__(256)
+xent_small_vec_kernel(const uint4* __restrict__ logits, const long long* __restrict__ target,
+                      float* __restrict__ loss_sum, float* __restrict__ count, uint4* __restrict__ dlogits,
+                      long long rows, int C, const float* __restrict__ inv_norm_dev, float gscale,
+                      const float* __restrict__ gscale_dev, long long ignore_index) {
+  __shared__ float s_loss[8], s_cnt[8];
+  float my_loss = 0.f, my_cnt = 0.f;
+  if (gscale_dev) gscale *= __ldg(gscale_dev);
+  if (inv_norm_dev && dlogits) gscale *= __ldg(inv_norm_dev);
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    float v[LV * 8];
+#pragma unroll
+    for (int q = 0; q < LV; ++q) {
+      const uint4 u = __ldg(logits + r * LV + q);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[q * 8 + 2 * e] = __uint_as_float(w4[e] << 16);
+        v[q * 8 + 2 * e + 1] = __uint_as_float(w4[e] & 0xFFFF0000u);
+      }
+    }
+    const long long t = target[r];
+    const bool ignored = t == ignore_index;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < LV * 8; ++c)
+      if (c < C) mx = fmaxf(mx, v[c]);
+    float se = 0.f, vt = 0.f;
+#pragma unroll
+    for (int c = 0; c < LV * 8; ++c) {
+      if (c < C) {
+        if (c == t) vt = v[c];
+        v[c] = __expf(v[c] - mx);
+        se += v[c];
+      }
+    }
+    if (!ignored && !dlogits) {
+      my_loss += logf(se) + mx - vt;
+      my_cnt += 1.f;
+    }
+    if (dlogits) {
+      const float inv = 1.f / se;
+#pragma unroll
+      for (int q = 0; q < LV; ++q) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float g2[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = q * 8 + 2 * e + h;
+            g2[h] = (!ignored && c < C) ? (v[c] * inv - (c == t ? 1.f : 0.f)) * gscale : 0.f;
+          }
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(g2[0], g2[1]);
+          w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        dlogits[r * LV + q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+  }
+  if (!dlogits) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      my_loss += __shfl_xor_sync(0xffffffffu, my_loss, o);
+      my_cnt += __shfl_xor_sync(0xffffffffu, my_cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_loss[threadIdx.x >> 5] = my_loss;
+      s_cnt[threadIdx.x >> 5] = my_cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < 8; ++w) {
+        a += s_loss[w];
+        b += s_cnt[w];
+      }
+      atomicAdd(loss_sum, a);
+      atomicAdd(count, b);
+    }
+  }
+}
+
 // ---- Dice loss (multiclass, from logits) ------------------------------------------------------------------------------
 // torchok/losses/segmentation/dice.py:85-188 (DiceLoss, mode='multiclass', from_logits=True) with soft_dice_score
 // (dice.py:23-56) over dims (0, 2): per class c
@@ -429,9 +516,21 @@ int tok_softmax_xent_small(long long rows, int C, int ld, const void* logits, co
                            const float* gscale_dev, long long ignore_index, void* stream) {
   if (rows <= 0 || C <= 0 || C > 64 || ld < C) return set_error(TOK_ERR_INVALID, "softmax_xent_small: 1 <= C <= 64, ld >= C");
   if (!dlogits && (!loss_sum || !count)) return set_error(TOK_ERR_INVALID, "softmax_xent_small: forward needs loss_sum and count");
-  xent_small_kernel<<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)logits, target, loss_sum, count, (__nv_bfloat16*)dlogits, rows, C, ld, inv_count_dev,
-      gscale, gscale_dev, ignore_index);
+  const bool vec = ld % 8 == 0 && ld <= 32 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0;
+#define TOK_XENT_VEC(LV)                                                                                          \
+  xent_small_vec_kernel<LV><<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>(                                    \
+      (const uint4*)logits, target, loss_sum, count, (uint4*)dlogits, rows, C, inv_count_dev, gscale, gscale_dev, \
+      ignore_index)
+  if (vec && ld == 8) TOK_XENT_VEC(1);
+  else if (vec && ld == 16) TOK_XENT_VEC(2);
+  else if (vec && ld == 24) TOK_XENT_VEC(3);
+  else if (vec && ld == 32) TOK_XENT_VEC(4);
+  else
+    xent_small_kernel<<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)logits, target, loss_sum, count, (__nv_bfloat16*)dlogits, rows, C, ld, inv_count_dev,
+        gscale, gscale_dev, ignore_index);
+#undef TOK_XENT_VEC
   TOK_CHECK_LAUNCH("softmax_xent_small");
   return TOK_OK;
 }

@@ -510,6 +510,7 @@ class StreamLoop:
         if self.peer is not None:
             self.peer.begin_step()
         out = self.task.training_step(batch)
+        K.chain_flush()   # close the BatchNorm sum chain inside the step: a captured step must not depend on what ran before it
         out['loss'].backward()
         self.arena.finish()
         if self.peer is None:      # peer-fused: the optimizer ran inside the exchange kernels, bucket by bucket

@@ -274,6 +274,24 @@ _FUSE_BWD_FIN = os.environ.get('TOK_BN_FUSE_BWD', '1') == '1'
 # ResNet-50 step — the apply grids have ~2 400 CTAs and their tickets serialise on one L2 address (~20 ns each), which
 # costs more than the 53 single-CTA finalize launches it removes.  Kept off.
 _FUSE_APPLY_FIN = os.environ.get('TOK_BN_FUSE_APPLY', '0') == '1'
+# r2 "chain" form of the same fusion (opt-in, TOK_BN_FUSE_CHAIN=1): no ticket — the batch sums of a unit are zeroed by the
+# NEXT fused apply launch of the stream (CTA 0 of it), which is ordered after every reader of those sums;
+# `_chain_pending` is the accumulator tensor the last chain launch left non-zero.  It removes the single-CTA finalize
+# launch of every unit (53 per ResNet-50 step, 306 per HRNet step) and the ticket atomics — and is STILL slower, on all
+# three workloads (A/B on one B200, graph replay): ResNet-50 21.70 vs 20.08 ms, HRNet-W18 seg 53.7 vs 48.7 ms,
+# ResNet-18 CIFAR 1.298 vs 1.267 ms.  So it was never the ticket: every CTA of the apply grid paying ~32 dependent L2
+# loads + a rsqrt per thread before its first vector costs more than one 4 us launch.  Kept off.
+_FUSE_CHAIN = os.environ.get('TOK_BN_FUSE_CHAIN', '0') == '1'
+_chain_pending = [None]
+
+
+def chain_flush():
+    """Zero the accumulators the last chain launch left behind (needed only by code that reads / re-uses them outside
+    the chain, e.g. tests that inspect them)."""
+    acc = _chain_pending[0]
+    if acc is not None:
+        acc[0:2].zero_()
+        _chain_pending[0] = None
 
 
 def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
@@ -292,7 +310,14 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
     rows = n * p * q
     st = _st()
     fused_apply = False
-    if bn.training and bn.acc.shape[0] > 4 and _FUSE_APPLY_FIN and not _FUSE_FWD_FIN and bn.cv == kp and \
+    chain = bn.training and _FUSE_CHAIN and not _FUSE_APPLY_FIN and not _FUSE_FWD_FIN and \
+        (keep and relu and residual is not None or L.tok_bn_apply_train_supported(rows, kp))
+    if chain:
+        acc = bn.acc
+        if _chain_pending[0] is acc:     # the same layer twice in a row: its sums must be zero before the conv adds to them
+            chain_flush()
+        L.tok_conv_fprop(C.byref(d), _p(x), _p(w), _p(y), _p(acc[0]), _p(acc[1]), None, None, 0, st)
+    elif bn.training and bn.acc.shape[0] > 4 and _FUSE_APPLY_FIN and not _FUSE_FWD_FIN and bn.cv == kp and \
             (keep and relu and residual is not None or L.tok_bn_apply_train_supported(rows, kp)):
         # conv (+ statistics), then ONE pass that finalizes the statistics and applies them (acc[4] word 2: its ticket)
         acc = bn.acc
@@ -319,17 +344,27 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
     if fused_apply:
         fin_args = (_p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias), bn.eps, bn.momentum, _p(bn.running_mean),
                     _p(bn.running_var), _p(small[0]), _p(small[1]), _p(small[2]), _p(small[3]), acc[4].data_ptr() + 8)
+    if chain:
+        prev = _chain_pending[0]
+        chain_args = (_p(acc[0]), _p(acc[1]), _p(bn.weight), _p(bn.bias), bn.eps, bn.momentum, _p(bn.running_mean),
+                      _p(bn.running_var), _p(small[0]), _p(small[1]), _p(small[2]), _p(small[3]),
+                      _p(prev[0]) if prev is not None else None, 2 * prev.shape[1] if prev is not None else 0)
+        _chain_pending[0] = acc
     if keep and relu and residual is not None:
         bits = torch.empty((rows * kp // 8,), dtype=torch.uint8, device=dev)
         mode = MASK_BITS
-        if fused_apply:
+        if chain:
+            L.tok_bn_apply_bits_chain(rows, kp, bn.cv, _p(y), *chain_args, _p(residual), _p(out), _p(bits), st)
+        elif fused_apply:
             L.tok_bn_apply_bits_train(rows, kp, _p(y), *fin_args, _p(residual), _p(out), _p(bits), st)
         else:
             L.tok_bn_apply_bits(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), _p(out), _p(bits), st)
     else:
         if relu:
             mode = MASK_Y
-        if fused_apply:
+        if chain:
+            L.tok_bn_apply_chain(rows, kp, bn.cv, _p(y), *chain_args, _p(residual), int(relu), _p(out), st)
+        elif fused_apply:
             L.tok_bn_apply_train(rows, kp, _p(y), *fin_args, _p(residual), int(relu), _p(out), st)
         else:
             L.tok_bn_apply(rows, kp, _p(y), _p(small[0]), _p(small[1]), _p(residual), int(relu), _p(out), st)
