@@ -332,6 +332,12 @@ def _call_work(name, a):
     if name in ('tok_bn_bwd_reduce2', 'tok_bn_bwd_reduce2_finalize'):
         rows, c = a[0], a[1]
         return 'bn bwd reduce', 0.0, 2.0 * rows * c * (3 if v(a[3]) else 2) + (rows * c / 8 if v(a[6]) else 0)
+    if name == 'tok_bn_bwd_reduce2_finalize_cv':      # (rows, C, c_valid, dout, dout2, y, mask_mode, bits, ...)
+        rows, c = a[0], a[1]
+        return 'bn bwd reduce', 0.0, 2.0 * rows * c * (3 if v(a[4]) else 2) + (rows * c / 8 if v(a[7]) else 0)
+    if name in ('tok_bn_apply_chain', 'tok_bn_apply_bits_chain'):
+        rows, c = a[0], a[1]
+        return 'bn fwd apply', 0.0, 2.0 * rows * c * (3 if v(a[18]) else 2) + (rows * c / 8 if name.endswith('bits_chain') else 0)
     if name == 'tok_bn_bwd_apply2':
         rows, c = a[0], a[1]
         return 'bn bwd apply', 0.0, 2.0 * rows * c * ((3 if v(a[3]) else 2) + 1 + (1 if v(a[13]) else 0)) + \
