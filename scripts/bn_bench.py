@@ -6,7 +6,7 @@ from torchok_b200.kernels import _p
 
 L = lib()
 dev = 'cuda'
-shapes = [(524288, 24), (131072, 24), (131072, 40), (524288, 64), (524288, 256), (802816, 64)]
+shapes = [(12544, 2048), (50176, 1024), (200704, 512), (802816, 256), (802816, 64), (200704, 128), (50176, 256), (12544, 512)]
 st = torch.cuda.current_stream().cuda_stream
 for rows, c in shapes:
     g = torch.randn(rows, c, device=dev).bfloat16()
@@ -18,8 +18,8 @@ for rows, c in shapes:
     coefs = torch.empty(3, c, device=dev)
     dg, db = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
     cnt = torch.zeros(4, dtype=torch.int32, device=dev)
-    for mode in (0, 1, 2):
-        for fin in (0, 1):
+    for mode in (1, 2):
+        for fin in (1,):
             def run():
                 if fin:
                     L.tok_bn_bwd_reduce2_finalize(rows, c, _p(g), None, _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),

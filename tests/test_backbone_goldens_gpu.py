@@ -55,6 +55,12 @@ def test_product_backbone_replays_reference_wiring(name, idx):
         e, e_amp = rel_err(a, g), rel_err(amp, g)
         print(f'{name}[{idx}] feature {i}: gpu-vs-reference max {e:.4f} l2 {rel_l2(a, g):.4f} | oracle-amp {e_amp:.4f}')
         if c['train']:
-            assert e < 1.5 * e_amp + 5e-3, (i, e, e_amp)
+            # Training-mode features pass through ~30 BatchNorm layers whose batch sums are accumulated with fp32 atomics
+            # (run-to-run order): the MAXIMUM over a tiny map moves between 0.05 and 0.09 on the same inputs (six runs of
+            # hrnet_w18_small, r2), the relative L2 error does not (0.0409-0.0417).  So the stable norm carries the tight
+            # bar and the maximum gets the headroom of its own noise.
+            l2, l2_amp = rel_l2(a, g), rel_l2(amp, g)
+            assert l2 < 1.5 * l2_amp + 5e-3, (i, l2, l2_amp)
+            assert e < 2.0 * e_amp + 5e-3, (i, e, e_amp)
         else:
             assert e < max(1e-2, 1.5 * e_amp) and rel_l2(a, g) < 1e-2, (i, e, e_amp)

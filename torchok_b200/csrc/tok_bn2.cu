@@ -819,6 +819,13 @@ int tok_stem_bwd_apply(int n, int h, int w, int c, const void* dpooled, const vo
     else { KERNEL(MASK_BITS, __VA_ARGS__); }                                                  \
   } while (0)
 
+// column-block width (16-byte vectors) of the backward reduction; TOK_BN_REDUCE_CVB overrides (tuning aid)
+static int reduce_cvb(int C) {
+  static const int forced = getenv("TOK_BN_REDUCE_CVB") ? atoi(getenv("TOK_BN_REDUCE_CVB")) : 0;
+  (void)C;
+  return forced > 0 ? forced : 16;
+}
+
 static int launch_bwd_reduce2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
                               const void* bits, const float* scale, const float* shift, float* sum_g, float* sum_gy,
                               const BwdFin& fin, void* stream) {
@@ -836,7 +843,7 @@ static int launch_bwd_reduce2(long long rows, int C, const void* dout, const voi
     if (occ == 0 &&                                                                                            \
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_reduce2_kernel<M, H2>, 256, 0) != cudaSuccess || occ < 1)) \
       occ = 2;                                                                                                 \
-    const Grid2 g = plan(rows, C, occ, 16);                                                                    \
+    const Grid2 g = plan(rows, C, occ, reduce_cvb(C));                                                        \
     bn_bwd_reduce2_kernel<M, H2><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y, \
                                                          (const uint8_t*)bits, scale, shift, sum_g, sum_gy, rows, \
                                                          g.cvec, g.cvec_b, g.rows_per_cta, fin);                \

@@ -140,14 +140,50 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
       sf[j] = __ldg(shift + cv * 8 + j);
     }
   }
-  for (; i < total; i += stride) {
-    if (!invariant) {
-      cv = (int)(i % cvec);
+  if (invariant) {
+    // four independent 16-byte loads in flight per thread (one load -> compute -> store chain per iteration left the
+    // kernel latency-bound at 0.67-0.77 of the HBM rate; the unrolled bn2 passes reach 0.87-0.94)
+    constexpr int U = 4;
+    for (; i < total; i += stride * U) {
+      uint4 vy[U], vr[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sc[j] = __ldg(scale + cv * 8 + j);
-        sf[j] = __ldg(shift + cv * 8 + j);
+      for (int u = 0; u < U; ++u) {
+        const long long k = i + u * stride;
+        if (k < total) {
+          vy[u] = ldg_stream(y + k);
+          if (HAS_RES) vr[u] = ldg_stream(res + k);
+        }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long k = i + u * stride;
+        if (k < total) {
+          float f[8];
+          unpack8(vy[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sf[j]);
+          if (HAS_RES) {
+            float r[8];
+            unpack8(vr[u], r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += r[j];
+          }
+          if (RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          out[k] = pack8(f);
+        }
+      }
+    }
+    return;
+  }
+  for (; i < total; i += stride) {
+    cv = (int)(i % cvec);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + cv * 8 + j);
+      sf[j] = __ldg(shift + cv * 8 + j);
     }
     float f[8];
     unpack8(ldg_stream(y + i), f);
@@ -927,7 +963,15 @@ static int launch_bn_apply(long long rows, int C, const void* y, const float* sc
   if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_apply: no rows");
   const int cvec = C / 8;
   const long long total = rows * cvec;
-  const int grid = elem_grid(total, 256 * 2);
+  // >= 4 vectors per thread (the unrolled loop), and a grid stride that is a multiple of the channel-vector count so
+  // every thread keeps ONE set of scale / shift registers (HRNet's 3 / 5 / 9-vector rows included)
+  int grid = elem_grid(total, 256 * 4);
+  {
+    int a = cvec, b = 256;
+    while (b) { const int t = a % b; a = b; b = t; }
+    const int m = cvec / a;
+    if (grid >= m) grid = grid / m * m;
+  }
   if (fin.fused && ((long long)grid * 256) % cvec != 0)
     return set_error(TOK_ERR_INVALID, "bn_apply_train: C / 8 = %d does not divide the grid stride", cvec);
   cudaStream_t st = (cudaStream_t)stream;
@@ -956,7 +1000,12 @@ int tok_bn_apply(long long rows, int C, const void* y, const float* scale, const
 int tok_bn_apply_train_supported(long long rows, int C) {
   if (C <= 0 || (C % 8) || rows <= 0) return 0;
   const int cvec = C / 8;
-  return ((long long)elem_grid(rows * cvec, 256 * 2) * 256) % cvec == 0 ? 1 : 0;
+  int grid = elem_grid(rows * cvec, 256 * 4);
+  int a = cvec, b = 256;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int m = cvec / a;
+  if (grid >= m) grid = grid / m * m;
+  return ((long long)grid * 256) % cvec == 0 ? 1 : 0;
 }
 
 int tok_bn_apply_train(long long rows, int C, const void* y, float* sum, float* sqsum, const float* gamma,
