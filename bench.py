@@ -335,6 +335,11 @@ def _call_work(name, a):
     if name == 'tok_bn_bwd_reduce2_finalize_cv':      # (rows, C, c_valid, dout, dout2, y, mask_mode, bits, ...)
         rows, c = a[0], a[1]
         return 'bn bwd reduce', 0.0, 2.0 * rows * c * (3 if v(a[4]) else 2) + (rows * c / 8 if v(a[7]) else 0)
+    if name == 'tok_bn_bwd_fused_cv':   # (rows, C, c_valid, dout, dout2, y, mask_mode, bits, ..., dy [23], dres [24])
+        rows, c = a[0], a[1]
+        n_in = 3 if v(a[4]) else 2
+        return 'bn bwd fused (reduce + apply, L2-sized)', 0.0, \
+            2.0 * rows * c * (n_in + 1 + (1 if v(a[24]) else 0)) + (rows * c / 8 if v(a[7]) else 0)
     if name in ('tok_bn_apply_chain', 'tok_bn_apply_bits_chain'):
         rows, c = a[0], a[1]
         return 'bn fwd apply', 0.0, 2.0 * rows * c * (3 if v(a[18]) else 2) + (rows * c / 8 if name.endswith('bits_chain') else 0)

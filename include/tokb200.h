@@ -196,6 +196,16 @@ int tok_bn_bwd_reduce2_finalize_cv(long long rows, int C, int c_valid, const voi
                                    float* sum_gy, const float* save_mean, const float* save_invstd, const float* gamma,
                                    float* coef_a, float* coef_c1, float* coef_c0, float* dgamma, float* dbeta,
                                    int accumulate, unsigned* counter, void* stream);
+/* tok_bn_bwd_reduce2_finalize_cv + tok_bn_bwd_apply2 in ONE launch, for tensors small enough to stay in L2 between the
+ * two passes: every CTA reduces its rows, the last through the ticket finalizes and flips *release, the others wait for
+ * the flip and apply dy = coef_a g + coef_c1 y + coef_c0 to the rows they already read.  `counter` and `release` are two
+ * zero-initialised 32-bit words owned by the layer (release keeps toggling; no reset needed).  The grid is one resident
+ * wave; the wait is bounded (~4 s, then the context traps). */
+int tok_bn_bwd_fused_cv(long long rows, int C, int c_valid, const void* dout, const void* dout2, const void* y,
+                        int mask_mode, const void* bits, const float* scale, const float* shift, float* sum_g,
+                        float* sum_gy, const float* save_mean, const float* save_invstd, const float* gamma,
+                        float* coef_a, float* coef_c1, float* coef_c0, float* dgamma, float* dbeta, int accumulate,
+                        unsigned* counter, unsigned* release, void* dy, void* dres, void* stream);
 int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2, const void* y, int mask_mode,
                       const void* bits, const float* scale, const float* shift, const float* coef_a,
                       const float* coef_c1, const float* coef_c0, void* dy, void* dres, void* stream);

@@ -86,6 +86,8 @@ _SIGS = {
     'tok_bn_bwd_reduce2': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_reduce2_finalize': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _vp, _i, _vp, _vp]),
+    'tok_bn_bwd_fused_cv': (_i, [_ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     'tok_bn_bwd_apply2': (_i, [_ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_stem_bn_relu_pool_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_stem_bwd_reduce': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -346,6 +346,180 @@ bn_bwd_apply2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ d
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, ONE launch
+// Pass 1 + finalize + pass 2 in one kernel for tensors that fit the L2 (layer3 / layer4 of ResNet-50 at bs256: g and y
+// are 26-100 MB): every CTA reduces its rows, the last one through the ticket turns the sums into the coefficients and
+// flips a release word; the others wait for the flip (bounded spin) and then re-read THE SAME rows — from L2 now — for
+// dy = a g + c1 y + c0.  Against two launches this removes the second HBM read of g and y, one launch and the gap
+// between them; separate launches measured ~20 us each on these tensors whatever their size (ramp + atomics -> fence ->
+// ticket -> finalize tail), i.e. ~1.9 ms of the 8.4 ms of BatchNorm time of a step.
+// The grid is ONE wave of co-resident CTAs by construction (launcher: occupancy API), so the wait cannot deadlock on
+// its own grid; CTAs of other streams only delay it.  flag protocol: every CTA samples the release word BEFORE it takes
+// its ticket; the word changes only after ALL tickets are taken, so all CTAs sample the same value and wait for the
+// other one.
+template <int MASK, bool HAS2, bool DRES>
+__global__ void __launch_bounds__(256)
+bn_bwd_fused_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2, const uint4* __restrict__ y,
+                    const uint8_t* __restrict__ bits, const float* __restrict__ scale, const float* __restrict__ shift,
+                    float* __restrict__ sum_g, float* __restrict__ sum_gy, uint4* __restrict__ dy,
+                    uint4* __restrict__ dres, long long rows, int cvec, int cvec_b, int rows_per_cta, const BwdFin fin,
+                    unsigned* release) {
+  __shared__ float part[256 * 16];
+  __shared__ int s_last;
+  __shared__ unsigned s_seen;
+  const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
+  if (threadIdx.x == 0) s_seen = *reinterpret_cast<volatile unsigned*>(release);
+  float sc[8], sf[8];
+  if (MASK == MASK_Y && m.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(scale + m.cv * 8 + j);
+      sf[j] = __ldg(shift + m.cv * 8 + j);
+    }
+  }
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  const long long step = (long long)m.rlanes * kUnroll;
+  if (m.active) {
+    for (long long r = m.r0 + m.rl; r < m.r1; r += step) {
+      uint4 vg[kUnroll], vy[kUnroll], v2[kUnroll];
+      uint32_t vb[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long rr = r + (long long)u * m.rlanes;
+        const long long idx = rr * cvec + m.cv;
+        if (rr < m.r1) {
+          vg[u] = ldg_stream(dout + idx);
+          vy[u] = ldg_stream(y + idx);
+          if (HAS2) v2[u] = ldg_stream(dout2 + idx);
+          if (MASK == MASK_BITS) vb[u] = ldg_stream_u8(bits + idx);
+        } else {
+          vg[u] = make_uint4(0, 0, 0, 0);
+          vy[u] = make_uint4(0, 0, 0, 0);
+          if (HAS2) v2[u] = make_uint4(0, 0, 0, 0);
+          if (MASK == MASK_BITS) vb[u] = 0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float g[8], yy[8];
+        unpack8(vg[u], g);
+        unpack8(vy[u], yy);
+        if (HAS2) {
+          float g2[8];
+          unpack8(v2[u], g2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += g2[j];
+        }
+        apply_mask<MASK>(g, yy, sc, sf, MASK == MASK_BITS ? vb[u] : 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a1[j] += g[j];
+          a2[j] = fmaf(g[j], yy[j], a2[j]);
+        }
+      }
+    }
+  }
+  float* mine = part + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mine[j] = a1[j];
+    mine[8 + j] = a2[j];
+  }
+  __syncthreads();
+  cta_reduce_red4(part, cvec, cvec_b, sum_g, sum_gy);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  const unsigned seen = s_seen;
+  if (s_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < fin.C; c += 256) {
+      const float sg = __ldcg(sum_g + c);
+      const float mu = fin.mean[c];
+      const float is = fin.invstd[c];
+      const float sgx = is * (__ldcg(sum_gy + c) - mu * sg);
+      sum_g[c] = 0.f;
+      sum_gy[c] = 0.f;
+      const bool real = c < fin.Cv;
+      const float g = real ? (fin.gamma ? fin.gamma[c] : 1.f) : 0.f;
+      const float a = g * is;
+      const float k1 = sg / fin.count;
+      const float k2 = sgx / fin.count;
+      fin.coef_a[c] = a;
+      fin.coef_c1[c] = -a * k2 * is;
+      fin.coef_c0[c] = -a * k1 + a * k2 * is * mu;
+      if (fin.dgamma && real) fin.dgamma[c] = fin.accumulate ? fin.dgamma[c] + sgx : sgx;
+      if (fin.dbeta && real) fin.dbeta[c] = fin.accumulate ? fin.dbeta[c] + sg : sg;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *fin.counter = 0u;
+      __threadfence();
+      atomicExch(release, seen ^ 1u);
+    }
+  } else if (threadIdx.x == 0) {
+    // bounded wait for the release flip (~4 s): a scheduling surprise must end as a launch failure, not a hung GPU
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned*>(release) == seen) {
+      if (clock64() - t0 > 8000000000LL) {
+        printf("tokb200: bn_bwd_fused release wait timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (!m.active) return;
+  // ---- pass 2 on the same rows (L2 hits): coefficients were written by another SM — read them past L1
+  float ca[8], c1[8], c0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ca[j] = __ldcg(fin.coef_a + m.cv * 8 + j);
+    c1[j] = __ldcg(fin.coef_c1 + m.cv * 8 + j);
+    c0[j] = __ldcg(fin.coef_c0 + m.cv * 8 + j);
+  }
+  for (long long r = m.r0 + m.rl; r < m.r1; r += step) {
+    uint4 vg[kUnroll], vy[kUnroll], v2[kUnroll];
+    uint32_t vb[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long rr = r + (long long)u * m.rlanes;
+      const long long idx = rr * cvec + m.cv;
+      if (rr < m.r1) {
+        vg[u] = ldg_stream(dout + idx);
+        vy[u] = ldg_stream(y + idx);
+        if (HAS2) v2[u] = ldg_stream(dout2 + idx);
+        if (MASK == MASK_BITS) vb[u] = ldg_stream_u8(bits + idx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long rr = r + (long long)u * m.rlanes;
+      if (rr < m.r1) {
+        const long long idx = rr * cvec + m.cv;
+        float g[8], yy[8];
+        unpack8(vg[u], g);
+        unpack8(vy[u], yy);
+        if (HAS2) {
+          float g2[8];
+          unpack8(v2[u], g2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += g2[j];
+        }
+        apply_mask<MASK>(g, yy, sc, sf, MASK == MASK_BITS ? vb[u] : 0u);
+        if (DRES) dres[idx] = pack8(g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yy[j] = fmaf(ca[j], g[j], fmaf(c1[j], yy[j], c0[j]));
+        dy[idx] = pack8(yy);
+      }
+    }
+  }
+}
+
 // dst[n, p*s, q*s, :] += src[n, p, q, :]  — merges the compact data gradient of a strided 1x1 (downsample) conv
 // into the full-resolution gradient of the block input (replaces a zero-filled scatter + full-size addend read)
 __global__ void __launch_bounds__(256)
@@ -918,6 +1092,56 @@ int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2
   else TOK_BN2_DISPATCH_MASK(K_APPLY, false, false);
 #undef K_APPLY
   TOK_CHECK_LAUNCH("bn_bwd_apply2");
+  return TOK_OK;
+}
+
+int tok_bn_bwd_fused_cv(long long rows, int C, int c_valid, const void* dout, const void* dout2, const void* y,
+                        int mask_mode, const void* bits, const float* scale, const float* shift, float* sum_g,
+                        float* sum_gy, const float* save_mean, const float* save_invstd, const float* gamma,
+                        float* coef_a, float* coef_c1, float* coef_c0, float* dgamma, float* dbeta, int accumulate,
+                        unsigned* counter, unsigned* release, void* dy, void* dres, void* stream) {
+  if (C <= 0 || (C % 8) || rows <= 0 || c_valid <= 0 || c_valid > C)
+    return set_error(TOK_ERR_INVALID, "bn_bwd_fused: bad shape (rows %lld C %d c_valid %d)", rows, C, c_valid);
+  if (!counter || !release || !save_mean || !save_invstd || !coef_a || !coef_c1 || !coef_c0 || !dy)
+    return set_error(TOK_ERR_INVALID, "bn_bwd_fused: counter, release word, saved statistics, coefficient and dy buffers are required");
+  if (mask_mode < 0 || mask_mode > 2 || (mask_mode == MASK_BITS && !bits) || (mask_mode == MASK_Y && (!scale || !shift)))
+    return set_error(TOK_ERR_INVALID, "bn_bwd_fused: mask_mode %d needs its operands", mask_mode);
+  BwdFin fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.counter = counter;
+  fin.count = (float)rows;
+  fin.mean = save_mean;
+  fin.invstd = save_invstd;
+  fin.gamma = gamma;
+  fin.coef_a = coef_a;
+  fin.coef_c1 = coef_c1;
+  fin.coef_c0 = coef_c0;
+  fin.dgamma = dgamma;
+  fin.dbeta = dbeta;
+  fin.accumulate = accumulate;
+  fin.C = C;
+  fin.Cv = c_valid;
+  cudaStream_t st = (cudaStream_t)stream;
+#define K_FUSED(M, H2, DR)                                                                                          \
+  {                                                                                                                 \
+    static int occ = 0;                                                                                             \
+    if (occ == 0 &&                                                                                                 \
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<M, H2, DR>, 256, 0) != cudaSuccess || \
+         occ < 1))                                                                                                  \
+      occ = 1;                                                                                                      \
+    const Grid2 g = plan(rows, C, occ, 16);                                                                         \
+    if ((long long)g.grid.x * g.grid.y > 148LL * occ)                                                               \
+      return set_error(TOK_ERR_INVALID, "bn_bwd_fused: grid %u x %u exceeds one resident wave", g.grid.x, g.grid.y); \
+    bn_bwd_fused_kernel<M, H2, DR><<<g.grid, 256, 0, st>>>(                                                         \
+        (const uint4*)dout, (const uint4*)dout2, (const uint4*)y, (const uint8_t*)bits, scale, shift, sum_g, sum_gy, \
+        (uint4*)dy, (uint4*)dres, rows, g.cvec, g.cvec_b, g.rows_per_cta, fin, release);                            \
+  }
+  if (dout2 && dres) TOK_BN2_DISPATCH_MASK(K_FUSED, true, true);
+  else if (dout2) TOK_BN2_DISPATCH_MASK(K_FUSED, true, false);
+  else if (dres) TOK_BN2_DISPATCH_MASK(K_FUSED, false, true);
+  else TOK_BN2_DISPATCH_MASK(K_FUSED, false, false);
+#undef K_FUSED
+  TOK_CHECK_LAUNCH("bn_bwd_fused");
   return TOK_OK;
 }
 

@@ -282,6 +282,13 @@ _FUSE_APPLY_FIN = os.environ.get('TOK_BN_FUSE_APPLY', '0') == '1'
 # ResNet-18 CIFAR 1.298 vs 1.267 ms.  So it was never the ticket: every CTA of the apply grid paying ~32 dependent L2
 # loads + a rsqrt per thread before its first vector costs more than one 4 us launch.  Kept off.
 _FUSE_CHAIN = os.environ.get('TOK_BN_FUSE_CHAIN', '0') == '1'
+# r2 experiment (opt-in, TOK_BN_FUSED_BWD_MB=<megabytes>): BatchNorm backward of an L2-sized tensor (g + y up to that size)
+# as ONE launch — reduce, finalize in the last CTA, grid-wide release, apply on the rows each CTA already read
+# (tok_bn_bwd_fused_cv).  Correct (the GPU suite passes with it) and SLOWER on every workload: ResNet-50 19.94 (110 MB) /
+# 20.03 (60 MB) vs 19.85 ms off, HRNet-W18 seg 52.4 vs 48.3 ms, ResNet-18 CIFAR 1.293 vs 1.267 ms; 48 us per fused launch
+# against 20 + 21 us for the pair it replaces — the one-wave grid at 2 CTAs / SM (100-128 registers) waiting for its
+# slowest CTA plus the release round trip costs more than the second read from L2 saves.  Kept off.
+_FUSED_BWD_MB = float(os.environ.get('TOK_BN_FUSED_BWD_MB', '0'))
 _chain_pending = [None]
 
 
@@ -404,6 +411,18 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
         dres = torch.empty_like(y) if want_dres else None
         L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                             _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
+        return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
+                                   wgrad_direct)
+    if acc.shape[0] > 4 and _FUSE_BWD_FIN and _FUSED_BWD_MB > 0 and \
+            rows * kp * 2 * (3 if dout2 is not None else 2) <= _FUSED_BWD_MB * 1e6:
+        # small enough to stay in L2 between the passes: reduce + finalize + apply in ONE launch (acc[4] words 1 / 3:
+        # ticket and release word of the layer)
+        dy = torch.empty_like(y)
+        dres = torch.empty_like(y) if want_dres else None
+        L.tok_bn_bwd_fused_cv(rows, kp, bn.cv, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
+                              _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight), _p(coefs[0]),
+                              _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, acc[4].data_ptr() + 4,
+                              acc[4].data_ptr() + 12, _p(dy), _p(dres), st)
         return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
                                    wgrad_direct)
     if acc.shape[0] > 4 and _FUSE_BWD_FIN:   # reduce + finalize in one launch (acc[4]: the layer's ticket counters)
