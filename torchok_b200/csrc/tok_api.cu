@@ -194,6 +194,8 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
   p.a = src;
   p.flip_taps = flip;
   mn_desc_geometry(&p.mn_lbo, &p.mn_sbo, &p.mn_kadv);
+  static const int defer = getenv("TOK_CONV_DEFER_STATS") ? atoi(getenv("TOK_CONV_DEFER_STATS")) : 1;
+  p.defer_stats = defer;
   // TOK_CONV_PROFILE=1: the epilogue phase counters of every launch land in a static device buffer which
   // tok_debug_conv_profile() copies out (bring-up aid; not part of the production path)
   static const bool want_prof = getenv("TOK_CONV_PROFILE") != nullptr;

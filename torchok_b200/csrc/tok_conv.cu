@@ -499,6 +499,37 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
       }
     };
+    // Statistics pass over a staged tile (see below).  With two staging buffers it is DEFERRED: the pass over tile t runs
+    // in iteration t + 1, between the issue of that tile's first TMEM loads and their wait, so the ~200 instructions of
+    // shared-memory reads and FMAs fill the tcgen05.ld latency instead of following the store (r3: the epilogue, not HBM,
+    // bounds the K <= 256 layers: drain 714 + statistics 931 clocks per 128x128 tile back to back on 8 warps).
+    auto stats_pass = [&](uint32_t cb, int rows_valid) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r2 = lane + rr * 32;
+        uint4 vv[kBlocks];
+#pragma unroll
+        for (int h = 0; h < kBlocks; ++h)
+          vv[h] = r2 < rows_valid ? lds128(cb + h * (kBlockM * 128) + r2 * 128 + ((ew ^ (r2 & 7)) * 16))
+                                  : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int h = 0; h < kBlocks; ++h) {
+          const uint32_t w4[4] = {vv[h].x, vv[h].y, vv[h].z, vv[h].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = bf16_lo(w4[e]), hi = bf16_hi(w4[e]);
+            sacc[h][2 * e] += lo;
+            sacc[h][2 * e + 1] += hi;
+            sacc[h][8 + 2 * e] = fmaf(lo, lo, sacc[h][8 + 2 * e]);
+            sacc[h][8 + 2 * e + 1] = fmaf(hi, hi, sacc[h][8 + 2 * e + 1]);
+          }
+        }
+      }
+    };
+    const bool kDefer = CBUFS == 2 && p.defer_stats != 0;
+    bool pend = false;
+    uint32_t pend_cb = 0;
+    int pend_rows = 0, pend_n0 = -1;
     const bool prof = p.prof != nullptr && (threadIdx.x == 64 || threadIdx.x == 96 + 128);
     long long pt[6] = {0, 0, 0, 0, 0, 0};
     long long tp = prof ? clock64() : 0;
@@ -534,7 +565,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             if (n0 + j * 64 < p.N) tma_load_2d(&tmD, &addend_full_bar[0], cbuf + j * (kBlockM * 128), n0 + j * 64, m0);
         }
       }
-      if (want_stats && prev_n0 >= 0 && prev_n0 != n0) flush_stats(prev_n0);  // rare: a finished n_tile
+      if (!kDefer && want_stats && prev_n0 >= 0 && prev_n0 != n0) flush_stats(prev_n0);  // rare: a finished n_tile
       prev_n0 = n0;
       epi_bar();  // (B) staging buffer free for this tile's writers; statistics slots consistent
       TOK_PROF(0)
@@ -572,6 +603,11 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       for (int cc = 0; cc < kInFlight; ++cc)
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ((c0 + cc) * 2 + half) * 32,
                            r[cc]);
+      if (kDefer && c0 == 0 && pend) {   // the previous tile's statistics, while this tile's first TMEM loads travel
+        stats_pass(pend_cb, pend_rows);
+        pend = false;
+        if (pend_n0 != n0) flush_stats(pend_n0);   // rare: a finished n_tile (every epilogue thread takes this branch)
+      }
       tmem_ld_wait();
       if (c0 + kInFlight >= kChunksPerWarp) {
         // accumulator is in registers: hand the TMEM buffer back to the MMA warp right away
@@ -681,26 +717,13 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           // warp ew owns 16-byte chunk ew of each 64-column block; lane l reads rows l, l+32, l+64, l+96
           int rows_valid = p.M - m0;
           if (rows_valid > kBlockM) rows_valid = kBlockM;
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const int r2 = lane + rr * 32;
-            uint4 vv[kBlocks];
-#pragma unroll
-            for (int h = 0; h < kBlocks; ++h)
-              vv[h] = r2 < rows_valid ? lds128(cbuf_s + h * (kBlockM * 128) + r2 * 128 + ((ew ^ (r2 & 7)) * 16))
-                                      : make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int h = 0; h < kBlocks; ++h) {
-              const uint32_t w4[4] = {vv[h].x, vv[h].y, vv[h].z, vv[h].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float lo = bf16_lo(w4[e]), hi = bf16_hi(w4[e]);
-                sacc[h][2 * e] += lo;
-                sacc[h][2 * e + 1] += hi;
-                sacc[h][8 + 2 * e] = fmaf(lo, lo, sacc[h][8 + 2 * e]);
-                sacc[h][8 + 2 * e + 1] = fmaf(hi, hi, sacc[h][8 + 2 * e + 1]);
-              }
-            }
+          if (kDefer) {
+            pend = true;
+            pend_cb = cbuf_s;
+            pend_rows = rows_valid;
+            pend_n0 = n0;
+          } else {
+            stats_pass(cbuf_s, rows_valid);
           }
         }
         TOK_PROF(5)
@@ -713,6 +736,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
 #undef TOK_PROF
     if (leader) tma_store_wait_all();
+    if (kDefer && pend) stats_pass(pend_cb, pend_rows);
     if (want_stats && prev_n0 >= 0) flush_stats(prev_n0);
     if (want_stats && p.fin.counter != nullptr) {
       // last CTA standing finalizes the BatchNorm statistics (every CTA takes a ticket, also one that had no tile)

@@ -84,6 +84,7 @@ struct ConvFwdParams {
   // bring-up aid (TOK_CONV_PROFILE=1): per-CTA cycle counts of the epilogue phases, 8 slots per CTA
   long long* prof;
   FwdFin fin;   // persistent kernel only
+  int defer_stats;   // persistent kernel, two staging buffers: statistics pass of tile t inside iteration t + 1
 };
 
 // Weight-gradient implicit GEMM:  dW[co, tap*Cin + ci] += sum_{pix in split} dy[pix, co] * x_tap[pix, ci]

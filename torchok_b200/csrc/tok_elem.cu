@@ -965,7 +965,8 @@ static int launch_bn_apply(long long rows, int C, const void* y, const float* sc
   const long long total = rows * cvec;
   // >= 4 vectors per thread (the unrolled loop), and a grid stride that is a multiple of the channel-vector count so
   // every thread keeps ONE set of scale / shift registers (HRNet's 3 / 5 / 9-vector rows included)
-  int grid = elem_grid(total, 256 * 4);
+  static const int per_thread = getenv("TOK_BN_APPLY_VEC") ? atoi(getenv("TOK_BN_APPLY_VEC")) : 4;
+  int grid = elem_grid(total, 256 * per_thread);
   {
     int a = cvec, b = 256;
     while (b) { const int t = a % b; a = b; b = t; }
