@@ -397,6 +397,13 @@ int tok_adam_step_dev_groups(long long n, float* param, float* grad, float* exp_
                              float weight_decay, int decoupled, float grad_scale, int zero_grad, const int* seg_begin,
                              const float* seg_lr_mult, const float* seg_wd_mult, int* seg_steps, int n_segs,
                              void* stream);
+/* Padded operand forms for layers whose channel counts are not multiples of 8 and that do NOT run on the halo kernels
+ * (timm HRNet fuse / transition convs, torchok/models/backbones/hrnet.py:140-192): dst bf16 [Kp][T][Cp] =
+ * zero-padded src fp32 [K][T][C] (T = R*S filter taps; inv_map, nullable: source channel of every padded input position
+ * or -1), and the reverse for the weight gradient: dst fp32 [K][T][C] += src fp32 [K][T][Cp] (map, nullable: padded
+ * position of every input channel). */
+int tok_pad_weight(int K, int T, int C, int Kp, int Cp, const float* src, const int* inv_map, void* dst, void* stream);
+int tok_unpad_wgrad_add(int K, int T, int C, int Cp, const float* src, const int* map, float* dst, void* stream);
 /* `seg_steps` (nullable, n_segs ints on the device): per-parameter Adam step counts (torch.optim.Adam's state['step']);
  * advanced by this call for every segment whose multipliers are not both zero and used for the bias correction, so a
  * parameter thawed by FreezeUnfreeze (torchok/callbacks/freeze_unfreeze.py:51-184) restarts at step 1 as in the

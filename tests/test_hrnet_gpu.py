@@ -120,14 +120,24 @@ def test_hrnet_w18_small_forward_features_and_backward():
         grads[mode] = {k: p.grad.clone() for k, p in o.named_parameters()}
     ym = m(x.cuda())
     sum((y.float() * r.cuda()).sum() for y, r in zip(ym, rs)).backward()
+    # Bars: the AGGREGATE over all parameters is held to the oracle's own bf16-AMP distance (1.25 x its RMS + 1e-2); a
+    # single parameter gets the headroom of its noise (2 x + 2e-2): the gradient of one early BatchNorm weight of this
+    # tiny net (batch 4) sits at 1.4-1.6 x its AMP distance from run to run (fp32 atomics order the batch sums
+    # differently every launch), which a 1.5 x bar turned into an intermittent failure.
     worst = worst_amp = 0.0
+    sq = sq_amp = 0.0
+    n_par = 0
     for k, p in m.named_parameters():
         assert p.grad is not None, k
         e = rel_l2(p.grad, grads['fp32'][k])
         e_amp = rel_l2(grads['amp'][k], grads['fp32'][k])
         worst, worst_amp = max(worst, e), max(worst_amp, e_amp)
-        assert e < 1.5 * e_amp + 2e-2, (k, e, e_amp)
-    print(f'hrnet_w18_small backward: worst rel_l2 gpu-vs-fp32 {worst:.4f} | oracle-amp-vs-fp32 {worst_amp:.4f}')
+        sq, sq_amp, n_par = sq + e * e, sq_amp + e_amp * e_amp, n_par + 1
+        assert e < 2.0 * e_amp + 2e-2, (k, e, e_amp)
+    rms, rms_amp = (sq / n_par) ** 0.5, (sq_amp / n_par) ** 0.5
+    print(f'hrnet_w18_small backward: rel_l2 gpu-vs-fp32 worst {worst:.4f} rms {rms:.4f} | oracle-amp-vs-fp32 worst '
+          f'{worst_amp:.4f} rms {rms_amp:.4f}')
+    assert rms < 1.25 * rms_amp + 1e-2, (rms, rms_amp)
     so, sm = o.state_dict(), m.state_dict()
     for k in so:
         if 'num_batches_tracked' in k:

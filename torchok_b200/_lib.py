@@ -149,6 +149,8 @@ _SIGS = {
     'tok_peer_step': (_i, [C.POINTER(tokPeerArenas), _i, _ll, _ll, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp, _vp,
                            _vp, _vp, _i, _i, _vp]),
     'tok_cast_f32_bf16': (_i, [_ll, _vp, _vp, _vp]),
+    'tok_pad_weight': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'tok_unpad_wgrad_add': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
 _RAW = {'tok_conv_halo_caps', 'tok_bn_apply_train_supported', 'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}

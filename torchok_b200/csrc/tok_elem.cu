@@ -917,6 +917,37 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
     dst[i] = __float2bfloat16(src[i]);
 }
 
+// Conv weights of a layer whose channel counts are not multiples of 8 (HRNet 18 / 36 / 72 ...), for the kernels that need
+// the padded form: dst[k][t][in_pos(c)] = bf16(src[k][t][c]), zero elsewhere.  src: fp32 [K][T][C] (KRSC memory), dst:
+// bf16 [Kp][T][Cp]; in_map (nullable): padded position of every input channel (concatenated, individually padded
+// segments).  One launch instead of torch's zeros + cast + index_put.
+__global__ void pad_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int K, int T, int C,
+                                  int Kp, int Cp, const int* __restrict__ inv_map, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cp = (int)(i % Cp);
+    long long r = i / Cp;
+    const int t = (int)(r % T);
+    const int k = (int)(r / T);
+    const int c = inv_map ? inv_map[cp] : (cp < C ? cp : -1);
+    float v = 0.f;
+    if (k < K && c >= 0) v = src[((long long)k * T + t) * C + c];
+    dst[i] = __float2bfloat16(v);
+  }
+}
+// The reverse for the weight gradient: dst[k][t][c] += src[k][t][in_pos(c)]  (fp32), one launch instead of slice +
+// permute + add_.
+__global__ void unpad_wgrad_add_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int T, int C,
+                                       int Cp, const int* __restrict__ map, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long r = i / C;   // k * T + t
+    const int cp = map ? map[c] : c;
+    dst[i] += src[r * Cp + cp];
+  }
+}
+
 }  // namespace tok
 
 using namespace tok;
@@ -1345,6 +1376,23 @@ int tok_adam_step_dev(long long n, float* param, float* grad, float* exp_avg, fl
                       int decoupled, float grad_scale, int zero_grad, void* stream) {
   return tok_adam_step_dev_groups(n, param, grad, exp_avg, exp_avg_sq, shadow_bf16, lr_dev, step_dev, beta1, beta2, eps,
                                   weight_decay, decoupled, grad_scale, zero_grad, nullptr, nullptr, nullptr, nullptr, 0, stream);
+}
+
+int tok_pad_weight(int K, int T, int C, int Kp, int Cp, const float* src, const int* inv_map, void* dst, void* stream) {
+  if (K <= 0 || T <= 0 || C <= 0 || Kp < K || Cp < C) return set_error(TOK_ERR_INVALID, "pad_weight: bad shape");
+  const long long total = (long long)Kp * T * Cp;
+  pad_weight_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, K, T, C, Kp, Cp,
+                                                                             inv_map, total);
+  TOK_CHECK_LAUNCH("pad_weight");
+  return TOK_OK;
+}
+
+int tok_unpad_wgrad_add(int K, int T, int C, int Cp, const float* src, const int* map, float* dst, void* stream) {
+  if (K <= 0 || T <= 0 || C <= 0 || Cp < C) return set_error(TOK_ERR_INVALID, "unpad_wgrad_add: bad shape");
+  const long long total = (long long)K * T * C;
+  unpad_wgrad_add_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, K, T, C, Cp, map, total);
+  TOK_CHECK_LAUNCH("unpad_wgrad_add");
+  return TOK_OK;
 }
 
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream) {

@@ -103,10 +103,30 @@ class Conv2d(nn.Conv2d):
         if not self.padded or self.is_direct(d):
             return K.shadow_of(w)
         r, s = self.kernel_size
-        full = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=BF16, device=w.device)
-        tmp = K.cast_bf16(w.detach())
-        full[:self.out_channels, :, :, self._in_index(w.device)] = tmp.permute(0, 2, 3, 1)
+        if not K.is_krsc(w) or w.dtype != F32:
+            full = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=BF16, device=w.device)
+            tmp = K.cast_bf16(w.detach())
+            full[:self.out_channels, :, :, self._in_index(w.device)] = tmp.permute(0, 2, 3, 1)
+            return full
+        # one launch: zero pad + cast + (optional) channel scatter
+        full = torch.empty((self.cout_p, r, s, self.cin_p), dtype=BF16, device=w.device)
+        maps = self._maps(w.device)
+        lib().tok_pad_weight(self.out_channels, r * s, self.in_channels, self.cout_p, self.cin_p, K._p(w.detach()),
+                             K._p(maps[1]) if maps is not None else None, K._p(full), K._st())
         return full
+
+    def _maps(self, device):
+        """(padded position of every input channel, source channel of every padded position or -1) as int32 tensors, or
+        None when the input channels are simply the first `in_channels` lanes."""
+        if self.tok_in_map is None:
+            return None
+        hit = getattr(self, '_tok_maps', None)
+        if hit is None or hit[0].device != device:
+            fwd = self.tok_in_map.to(device=device, dtype=torch.int32)
+            inv = torch.full((self.cin_p,), -1, dtype=torch.int32, device=device)
+            inv[fwd.long()] = torch.arange(self.in_channels, dtype=torch.int32, device=device)
+            hit = self._tok_maps = (fwd.contiguous(), inv.contiguous())
+        return hit
 
     def wgrad_target(self, d=None):
         """(buffer the wgrad kernel accumulates into, finish()) — the parameter's own fp32 .grad when unpadded (or when the
@@ -120,7 +140,12 @@ class Conv2d(nn.Conv2d):
         tmp = torch.zeros((self.cout_p, r, s, self.cin_p), dtype=F32, device=g.device)
 
         def finish():
-            g.add_(tmp[:self.out_channels, :, :, self._in_index(g.device)].permute(0, 3, 1, 2))
+            if K.is_krsc(g) and g.dtype == F32:   # one launch: gather the real lanes of the padded gradient and add
+                maps = self._maps(g.device)
+                lib().tok_unpad_wgrad_add(self.out_channels, r * s, self.in_channels, self.cin_p, K._p(tmp),
+                                          K._p(maps[0]) if maps is not None else None, K._p(g), K._st())
+            else:
+                g.add_(tmp[:self.out_channels, :, :, self._in_index(g.device)].permute(0, 3, 1, 2))
         return tmp, finish
 
     def forward(self, x):
@@ -183,7 +208,9 @@ def _bn_grads(bn):
 
 def _unit_fwd(x, conv, bn, relu, residual, keep):
     d, pq = conv.desc(x)
-    res = K.unit_forward(x, d, pq, conv.shadow(d), bn.state(), relu, residual, keep)
+    w = conv.shadow(d)
+    conv._tok_last_shadow = w if (conv.padded and not conv.is_direct(d)) else None   # the backward of this step re-uses it
+    res = K.unit_forward(x, d, pq, w, bn.state(), relu, residual, keep)
     return res, d
 
 
@@ -192,7 +219,10 @@ def _unit_bwd(saved, d, conv, bn, dout, **kw):
     gw, gb = _bn_grads(bn)
     st = K.BNState(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, bn.training,
                    bn._tok_acc, bn.cp, bn.num_features)
-    out = K.unit_backward(saved, d, conv.shadow(d), st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb,
+    w = getattr(conv, '_tok_last_shadow', None)
+    if w is None or conv.is_direct(d):
+        w = conv.shadow(d)
+    out = K.unit_backward(saved, d, w, st, dout, wgrad_into=wbuf, dgamma=gw, dbeta=gb,
                           wgrad_direct=finish is None, **kw)
     if finish:
         finish()
