@@ -32,6 +32,11 @@ int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, i
 void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
                         int sh, int sw, cudaStream_t st);
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("TOK_PDL") && atoi(getenv("TOK_PDL")) == 0);
+  return on;
+}
+
 static thread_local char g_err[512] = "";
 int set_error(int code, const char* fmt, ...) {
   va_list ap;

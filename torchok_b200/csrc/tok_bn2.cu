@@ -120,6 +120,8 @@ bn_apply_bits_kernel(const uint4* __restrict__ y, const uint4* __restrict__ res,
                      uint8_t* __restrict__ bits, const float* __restrict__ scale, const float* __restrict__ shift,
                      long long rows, int cvec, int cvec_b, int rows_per_cta, const ApplyFin fin) {
   __shared__ int s_flag;
+  pdl_wait();
+  pdl_launch();
   const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
   float sc[8], sf[8];
   if (fin.fused) {
@@ -193,6 +195,8 @@ bn_bwd_reduce2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ 
                       long long rows, int cvec, int cvec_b, int rows_per_cta, const BwdFin fin) {
   __shared__ float part[256 * 16];
   __shared__ int s_last;
+  pdl_wait();
+  pdl_launch();
   const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
   float a1[8], a2[8];
 #pragma unroll
@@ -294,6 +298,8 @@ bn_bwd_apply2_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ d
                      const float* __restrict__ shift, const float* __restrict__ coef_a,
                      const float* __restrict__ coef_c1, const float* __restrict__ coef_c0, uint4* __restrict__ dy,
                      uint4* __restrict__ dres, long long rows, int cvec, int cvec_b, int rows_per_cta) {
+  pdl_wait();
+  pdl_launch();
   const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
   if (!m.active) return;
   float sc[8], sf[8], ca[8], c1[8], c0[8];
@@ -364,6 +370,8 @@ bn_bwd_fused_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ do
                     float* __restrict__ sum_g, float* __restrict__ sum_gy, uint4* __restrict__ dy,
                     uint4* __restrict__ dres, long long rows, int cvec, int cvec_b, int rows_per_cta, const BwdFin fin,
                     unsigned* release) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float part[256 * 16];
   __shared__ int s_last;
   __shared__ unsigned s_seen;
@@ -525,6 +533,8 @@ bn_bwd_fused_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ do
 __global__ void __launch_bounds__(256)
 strided_add_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total, int P, int Q, int cvec,
                    int H, int W, int s) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -552,6 +562,8 @@ __global__ void __launch_bounds__(256)
 stem_bn_relu_pool_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
                              const float* __restrict__ shift, uint4* __restrict__ act, uint4* __restrict__ pooled,
                              uint2* __restrict__ arg, long long total, int H, int W, int P, int Q, int cvec) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -642,6 +654,8 @@ stem_bwd_kernel(const uint4* __restrict__ dpooled, const uint2* __restrict__ arg
                 float* __restrict__ sum_g, float* __restrict__ sum_gy, const float* __restrict__ coef_a,
                 const float* __restrict__ coef_c1, const float* __restrict__ coef_c0, uint4* __restrict__ dy,
                 long long rows, int H, int W, int P, int Q, int cvec, int cvec_b, int rows_per_cta) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float part[MODE == 0 ? 256 * 16 : 1];
   const Map m = make_map(rows, cvec, cvec_b, rows_per_cta);
   float a1[8], a2[8], sc[8], sf[8], ca[8], c1[8], c0[8];
@@ -705,6 +719,8 @@ stem_bwd2_kernel(const uint4* __restrict__ dpooled, const uint2* __restrict__ ar
                  float* __restrict__ sum_g, float* __restrict__ sum_gy, const float* __restrict__ coef_a,
                  const float* __restrict__ coef_c1, const float* __restrict__ coef_c0, uint4* __restrict__ dy, int total,
                  int H, int W, int P, int Q, int cvec) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float part[MODE == 0 ? 256 * 16 : 1];
   const int cv = threadIdx.x % cvec;   // constant per thread: 256 and the grid stride are multiples of cvec
   float a1[8], a2[8], sc[8], sf[8], ca[8], c1[8], c0[8];
@@ -833,10 +849,10 @@ static int launch_apply_bits(long long rows, int C, const void* y, const float* 
   if (C <= 0 || (C % 8)) return set_error(TOK_ERR_INVALID, "bn_apply_bits: C must be a positive multiple of 8 (got %d)", C);
   if (rows <= 0 || !residual || !bits) return set_error(TOK_ERR_INVALID, "bn_apply_bits: rows, residual and bits are required");
   const Grid2 g = plan(rows, C, 6);
-  bn_apply_bits_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)y, (const uint4*)residual, (uint4*)out,
-                                                                (uint8_t*)bits, scale, shift, rows, g.cvec, g.cvec_b,
-                                                                g.rows_per_cta, fin);
-  TOK_CHECK_LAUNCH("bn_apply_bits");
+  cudaError_t le = launch_pdl(bn_apply_bits_kernel, g.grid, dim3(256), 0, (cudaStream_t)stream, (const uint4*)y,
+                              (const uint4*)residual, (uint4*)out, (uint8_t*)bits, scale, shift, rows, g.cvec, g.cvec_b,
+                              g.rows_per_cta, fin);
+  if (le != cudaSuccess) return set_error(TOK_ERR_CUDA, "bn_apply_bits: %s", cudaGetErrorString(le));
   return TOK_OK;
 }
 
@@ -912,7 +928,7 @@ int tok_strided_add(int n, int h, int w, int c, int stride, const void* src_comp
   const long long total = (long long)n * P * Q * (c / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  strided_add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src_compact, (uint4*)dst, total,
+  (void)launch_pdl(strided_add_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const uint4*)src_compact, (uint4*)dst, total,
                                                                        P, Q, c / 8, h, w, stride);
   TOK_CHECK_LAUNCH("strided_add");
   return TOK_OK;
@@ -926,7 +942,7 @@ int tok_stem_bn_relu_pool_fwd(int n, int h, int w, int c, const void* y, const f
   const long long total = (long long)n * P * Q * (c / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  stem_bn_relu_pool_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(stem_bn_relu_pool_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, 
       (const uint4*)y, scale, shift, (uint4*)act, (uint4*)pooled, (uint2*)argmax, total, h, w, P, Q, c / 8);
   TOK_CHECK_LAUNCH("stem_bn_relu_pool_fwd");
   return TOK_OK;
@@ -945,14 +961,14 @@ int tok_stem_bwd_reduce(int n, int h, int w, int c, const void* dpooled, const v
       occ = 2;
     int grid = 148 * occ;
     if (grid > (total + 255) / 256) grid = (total + 255) / 256;
-    stem_bwd2_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    (void)launch_pdl(stem_bwd2_kernel<0>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
         (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, sum_g, sum_gy,
         nullptr, nullptr, nullptr, nullptr, total, h, w, P, Q, c / 8);
     TOK_CHECK_LAUNCH("stem_bwd_reduce");
     return TOK_OK;
   }
   const Grid2 g = plan(rows, c, 6);
-  stem_bwd_kernel<0><<<g.grid, 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(stem_bwd_kernel<0>, dim3(g.grid), dim3(256), 0, (cudaStream_t)stream, 
       (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, sum_g, sum_gy,
       nullptr, nullptr, nullptr, nullptr, rows, h, w, P, Q, g.cvec, g.cvec_b, g.rows_per_cta);
   TOK_CHECK_LAUNCH("stem_bwd_reduce");
@@ -972,14 +988,14 @@ int tok_stem_bwd_apply(int n, int h, int w, int c, const void* dpooled, const vo
       occ = 2;
     int grid = 148 * occ * 2;
     if (grid > (total + 255) / 256) grid = (total + 255) / 256;
-    stem_bwd2_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    (void)launch_pdl(stem_bwd2_kernel<1>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
         (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, nullptr, nullptr,
         coef_a, coef_c1, coef_c0, (uint4*)dy, total, h, w, P, Q, c / 8);
     TOK_CHECK_LAUNCH("stem_bwd_apply");
     return TOK_OK;
   }
   const Grid2 g = plan(rows, c, 6);
-  stem_bwd_kernel<1><<<g.grid, 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(stem_bwd_kernel<1>, dim3(g.grid), dim3(256), 0, (cudaStream_t)stream, 
       (const uint4*)dpooled, (const uint2*)argmax, (const uint4*)dact, (const uint4*)y, scale, shift, nullptr, nullptr,
       coef_a, coef_c1, coef_c0, (uint4*)dy, rows, h, w, P, Q, g.cvec, g.cvec_b, g.rows_per_cta);
   TOK_CHECK_LAUNCH("stem_bwd_apply");
@@ -1018,14 +1034,15 @@ static int launch_bwd_reduce2(long long rows, int C, const void* dout, const voi
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_reduce2_kernel<M, H2>, 256, 0) != cudaSuccess || occ < 1)) \
       occ = 2;                                                                                                 \
     const Grid2 g = plan(rows, C, occ, reduce_cvb(C));                                                        \
-    bn_bwd_reduce2_kernel<M, H2><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y, \
-                                                         (const uint8_t*)bits, scale, shift, sum_g, sum_gy, rows, \
-                                                         g.cvec, g.cvec_b, g.rows_per_cta, fin);                \
+    le = launch_pdl(bn_bwd_reduce2_kernel<M, H2>, g.grid, dim3(256), 0, st, (const uint4*)dout, (const uint4*)dout2, \
+                    (const uint4*)y, (const uint8_t*)bits, scale, shift, sum_g, sum_gy, rows, g.cvec, g.cvec_b,     \
+                    g.rows_per_cta, fin);                                                                           \
   }
+  cudaError_t le = cudaSuccess;
   if (dout2) TOK_BN2_DISPATCH_MASK(K_REDUCE, true);
   else TOK_BN2_DISPATCH_MASK(K_REDUCE, false);
 #undef K_REDUCE
-  TOK_CHECK_LAUNCH("bn_bwd_reduce2");
+  if (le != cudaSuccess) return set_error(TOK_ERR_CUDA, "bn_bwd_reduce2: %s", cudaGetErrorString(le));
   return TOK_OK;
 }
 
@@ -1082,16 +1099,16 @@ int tok_bn_bwd_apply2(long long rows, int C, const void* dout, const void* dout2
   const Grid2 g = plan(rows, C, 6);
   cudaStream_t st = (cudaStream_t)stream;
 #define K_APPLY(M, H2, DR)                                                                                          \
-  bn_bwd_apply2_kernel<M, H2, DR><<<g.grid, 256, 0, st>>>((const uint4*)dout, (const uint4*)dout2, (const uint4*)y,  \
-                                                          (const uint8_t*)bits, scale, shift, coef_a, coef_c1,      \
-                                                          coef_c0, (uint4*)dy, (uint4*)dres, rows, g.cvec, g.cvec_b, \
-                                                          g.rows_per_cta)
+  le = launch_pdl(bn_bwd_apply2_kernel<M, H2, DR>, g.grid, dim3(256), 0, st, (const uint4*)dout, (const uint4*)dout2, \
+                  (const uint4*)y, (const uint8_t*)bits, scale, shift, coef_a, coef_c1, coef_c0, (uint4*)dy,         \
+                  (uint4*)dres, rows, g.cvec, g.cvec_b, g.rows_per_cta)
+  cudaError_t le = cudaSuccess;
   if (dout2 && dres) TOK_BN2_DISPATCH_MASK(K_APPLY, true, true);
   else if (dout2) TOK_BN2_DISPATCH_MASK(K_APPLY, true, false);
   else if (dres) TOK_BN2_DISPATCH_MASK(K_APPLY, false, true);
   else TOK_BN2_DISPATCH_MASK(K_APPLY, false, false);
 #undef K_APPLY
-  TOK_CHECK_LAUNCH("bn_bwd_apply2");
+  if (le != cudaSuccess) return set_error(TOK_ERR_CUDA, "bn_bwd_apply2: %s", cudaGetErrorString(le));
   return TOK_OK;
 }
 
@@ -1132,7 +1149,7 @@ int tok_bn_bwd_fused_cv(long long rows, int C, int c_valid, const void* dout, co
     const Grid2 g = plan(rows, C, occ, 16);                                                                         \
     if ((long long)g.grid.x * g.grid.y > 148LL * occ)                                                               \
       return set_error(TOK_ERR_INVALID, "bn_bwd_fused: grid %u x %u exceeds one resident wave", g.grid.x, g.grid.y); \
-    bn_bwd_fused_kernel<M, H2, DR><<<g.grid, 256, 0, st>>>(                                                         \
+    (void)launch_pdl(bn_bwd_fused_kernel<M, H2, DR>, dim3(g.grid), dim3(256), 0, st,                                                          \
         (const uint4*)dout, (const uint4*)dout2, (const uint4*)y, (const uint8_t*)bits, scale, shift, sum_g, sum_gy, \
         (uint4*)dy, (uint4*)dres, rows, g.cvec, g.cvec_b, g.rows_per_cta, fin, release);                            \
   }

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "tok_conv.cuh"
+#include "tok_internal.h"
 #include "tok_ptx.cuh"
 
 namespace tok {
@@ -327,6 +328,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // operands of earlier kernels are touched only below
+  pdl_launch();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -827,6 +830,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -965,9 +970,8 @@ static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& t
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS, BRES><<<grid, kPersistThreads, smem, st>>>(tmA, tmB, tmC,
-                                                                                                    tmD, p);
-  return cudaGetLastError();
+  return launch_pdl(conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS, BRES>, dim3(grid), dim3(kPersistThreads), smem,
+                    st, tmA, tmB, tmC, tmD, p);
 }
 
 // Tile configurations (shared memory: operand ring + staging + addend buffers):
@@ -1054,8 +1058,7 @@ static cudaError_t launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tm
   const int m_tiles = (p.Cout + kBlockM - 1) / kBlockM;
   const int n_tiles = (p.Cin + BN - 1) / BN;
   dim3 grid(taps * m_tiles * n_tiles, splits);
-  conv_wgrad_kernel<BN, STAGES><<<grid, kNumThreads, smem, st>>>(tmDY, tmX, p);
-  return cudaGetLastError();
+  return launch_pdl(conv_wgrad_kernel<BN, STAGES>, grid, dim3(kNumThreads), smem, st, tmDY, tmX, p);
 }
 
 cudaError_t launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const ConvWgradParams& p, int bn,

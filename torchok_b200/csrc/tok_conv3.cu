@@ -132,6 +132,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const HaloParams p)
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
+  // The padded shadow of a non-direct layer is written by the kernel launched right before this one: nothing of an
+  // earlier kernel is read before the wait (barrier init and the TMEM allocation above overlap the predecessor's tail).
+  pdl_wait();
+  pdl_launch();
   // ---- weight slab: tile (tap, kb) = BN rows (output channel of the GEMM) x KB reduction channels, K-major, swizzled
   {
     const uint32_t slab_s = smem_u32(smem_w);
@@ -516,6 +520,8 @@ conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // the 200 KB zero fill above ran while the previous kernel drained
+  pdl_launch();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -759,7 +765,8 @@ int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, 
                                 232448);                                                                         \
       configured = e0 == cudaSuccess;                                                                            \
     }                                                                                                            \
-    if (e0 == cudaSuccess) conv3x3_halo_kernel<KBV, ST, AD><<<grid, kHaloThreads, pl.smem, st>>>(tmA, p);        \
+    if (e0 == cudaSuccess)                                                                                      \
+      e0 = launch_pdl(conv3x3_halo_kernel<KBV, ST, AD>, dim3(grid), dim3(kHaloThreads), pl.smem, st, tmA, p);   \
   }
   if (pl.kb == 64) {
     if (stats) TOK_HALO_LAUNCH(64, true, false)
@@ -868,8 +875,7 @@ int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, i
   }
   const long long tiles = (long long)n_img * ((H + pl.TR - 1) / pl.TR);
   const int grid = tiles < num_sms() ? (int)tiles : num_sms();
-  conv3x3_wgrad_halo_kernel<<<grid, 192, pl.smem, st>>>(tmDY, tmX, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(conv3x3_wgrad_halo_kernel, dim3(grid), dim3(192), pl.smem, st, tmDY, tmX, p);
   if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "conv3x3 halo wgrad launch: %s", cudaGetErrorString(e));
   return TOK_OK;
 }

@@ -50,6 +50,8 @@ static inline int elem_grid(long long work_items, int block) {
 // dst[n, p*sh, q*sw, :] = src[n, p, q, :]  (dst pre-zeroed): zero-dilation of an output gradient.
 __global__ void dilate_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total, int P,
                                    int Q, int cvec, int H, int W, int sh, int sw) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -64,7 +66,7 @@ __global__ void dilate_rows_kernel(const uint4* __restrict__ src, uint4* __restr
 void launch_dilate_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int n, int p, int q, int c, int H, int W,
                         int sh, int sw, cudaStream_t st) {
   const long long total = (long long)n * p * q * (c / 8);
-  dilate_rows_kernel<<<elem_grid(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
+  (void)launch_pdl(dilate_rows_kernel, dim3(elem_grid(total, 256)), dim3(256), 0, st, reinterpret_cast<const uint4*>(src),
                                                             reinterpret_cast<uint4*>(dst), total, p, q, c / 8, H, W,
                                                             sh, sw);
 }
@@ -78,6 +80,8 @@ __global__ void bn_finalize_train_kernel(float* __restrict__ sum, float* __restr
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ save_mean, float* __restrict__ save_invstd, int C,
                                          int Cv) {
+  pdl_wait();
+  pdl_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float mean = sum[c] / count;
@@ -104,6 +108,8 @@ __global__ void bn_finalize_train_kernel(float* __restrict__ sum, float* __restr
 __global__ void bn_finalize_eval_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                         float* __restrict__ scale, float* __restrict__ shift, int C, int Cv) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (c >= Cv) {   // pad lane
@@ -125,6 +131,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        const float* __restrict__ shift, long long total, int cvec,
                                                        const ApplyFin fin) {
   __shared__ int s_flag;
+  pdl_wait();
+  pdl_launch();
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool invariant = (stride % cvec) == 0;   // the host guarantees it when fin.counter != nullptr
@@ -210,6 +218,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ dout2, const uint4* __restrict__ out,
                      const uint4* __restrict__ y, float* __restrict__ sum_g, float* __restrict__ sum_gy,
                      long long rows, int cvec, int cvec_b, int rows_per_cta) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ float red[];  // [cvec_b*8][2]
   const int rlanes = 256 / cvec_b;
   const int cl = threadIdx.x % cvec_b;
@@ -271,6 +281,8 @@ __global__ void bn_bwd_finalize_kernel(float* __restrict__ sum_g, float* __restr
                                        const float* __restrict__ gamma, float count, float* __restrict__ coef_a,
                                        float* __restrict__ coef_c1, float* __restrict__ coef_c0, float* dgamma,
                                        float* dbeta, int accumulate, int C, int Cv) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sg = sum_g[c];
@@ -297,6 +309,8 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ do
                     const uint4* __restrict__ y, const float* __restrict__ coef_a, const float* __restrict__ coef_c1,
                     const float* __restrict__ coef_c0, uint4* __restrict__ dy, uint4* __restrict__ dres,
                     long long total, int cvec) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool invariant = (stride % cvec) == 0;
@@ -347,6 +361,8 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ do
 // ATen's max_pool2d; the winner's window slot (r*k + s) is stored for the backward pass.
 __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, uint2* __restrict__ arg,
                                    long long total, int H, int W, int P, int Q, int cvec, int k, int s, int pd) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -389,6 +405,8 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restric
 __global__ void maxpool_bwd_kernel(const uint4* __restrict__ dout, const uint2* __restrict__ arg,
                                    uint4* __restrict__ dx, long long total, int H, int W, int P, int Q, int cvec,
                                    int k, int s, int pd) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -433,6 +451,8 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ dout, const uint2* 
 // mode 0 avg, 1 max, 2 avgmax = 0.5*(avg+max).  (timm SelectAdaptivePool2d, pooling.py:8-12)
 __global__ void gap_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int N, int HW, int cvec,
                                int mode) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)N * cvec) return;
   const int cv = (int)(i % cvec);
@@ -463,6 +483,8 @@ __global__ void gap_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ 
 // Backward of the average pool: dx[n, r, c] = dout[n, c] / HW.
 __global__ void gap_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ dx, long long total, int HW,
                                int cvec) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const float inv = 1.f / HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -480,6 +502,8 @@ __global__ void gap_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict
 // the whole max-path gradient).  One thread per (n, 8-channel vector): pass 1 finds the arg-max rows, pass 2 writes dx.
 __global__ void gap_bwd_max_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ x, uint4* __restrict__ dx,
                                    int N, int HW, int cvec, int mode) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)N * cvec) return;
   const int cv = (int)(i % cvec);
@@ -521,6 +545,8 @@ softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const long long* _
                     float* __restrict__ loss_sum, __nv_bfloat16* __restrict__ dlogits, int C, long long ld,
                     float inv_norm, float gscale, const float* __restrict__ gscale_dev, long long ignore_index,
                     int* __restrict__ correct) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float sred[32];
   if (gscale_dev) gscale *= __ldg(gscale_dev);
   __shared__ int sidx[32];
@@ -607,6 +633,8 @@ softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const long long* _
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW,
                                     int Cp) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float tile[32][33];
   const long long n = blockIdx.z;
   const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -626,6 +654,8 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, __nv_bfloat16* __
 template <typename T, int CV>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_small_kernel(const T* __restrict__ src, uint4* __restrict__ dst,
                                                                  int C, long long HW, long long total) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long n = i / HW, hw = i - n * HW;
     const T* s = src + n * C * HW + hw;
@@ -644,6 +674,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_small_kernel(const T* __rest
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, T* __restrict__ dst, int C, int HW,
                                     int Cp) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float tile[32][33];
   const long long n = blockIdx.z;
   const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -666,6 +698,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, T* __
 template <typename T>
 __global__ void stem_s2d_pack_kernel(const T* __restrict__ src, uint4* __restrict__ dst, int N, int C, int H, int W,
                                      int H2, int W2, int pad) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const long long total = (long long)N * H2 * W2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -698,6 +732,8 @@ __global__ void stem_s2d_pack_kernel(const T* __restrict__ src, uint4* __restric
 // Stem weights: fp32 [K][7][7][C] (channels_last OIHW) -> bf16 [K][4][4][16] matching stem_s2d_pack_kernel.
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int K, int R,
                                         int S, int C) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int total = K * 256;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / 256, rem = i % 256;
@@ -712,6 +748,8 @@ __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat
 // Inverse gather for the gradient: dw[K][7][7][C] (+)= dwp[K][4][4][16].
 __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int K, int R, int S,
                                          int C, int accumulate) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int total = K * R * S * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % C;
@@ -731,6 +769,8 @@ __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dwp, float* _
 __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
                                 __nv_bfloat16* __restrict__ shadow, long long n, float lr, float mu, float wd,
                                 float damp, int nesterov, float gscale, int first) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float w = p[i];
@@ -750,6 +790,8 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
                                  float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float lr,
                                  float b1, float b2, float eps, float wd, int decoupled, float bc1, float bc2,
                                  float gscale) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const float step = lr / bc1;
   const float rbc2 = rsqrtf(bc2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -771,9 +813,13 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
 }
 // Graph-replayable variants: lr and the step counter are read from device memory (the counter is advanced by
 // step_advance_kernel just before), and the consumed gradient is zeroed for the next step's atomic accumulation.
-__global__ void step_advance_kernel(int* step) { *step += 1; }
+__global__ void step_advance_kernel(int* step) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch(); *step += 1; }
 // per-parameter Adam step counts: advance where the parameter is being optimised (lr multiplier != 0)
 __global__ void seg_steps_advance_kernel(int* steps, const float* lr_mult, const float* wd_mult, int n) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && !(lr_mult[i] == 0.f && wd_mult[i] == 0.f)) steps[i] += 1;
 }
@@ -785,6 +831,8 @@ sgd_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restr
                     __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
                     const int* __restrict__ step_dev, float mu, float wd, float damp, int nesterov, float gscale,
                     int zero_grad, const ParamSegs segs) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   SgdArgs a;
   a.lr = __ldg(lr_dev);
   const float lr0 = a.lr;
@@ -841,6 +889,8 @@ adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __rest
                      __nv_bfloat16* __restrict__ shadow, long long n, const float* __restrict__ lr_dev,
                      const int* __restrict__ step_dev, float b1, float b2, float eps, float wd, int decoupled,
                      float gscale, int zero_grad, const ParamSegs segs) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   AdamArgs a;
   a.lr = __ldg(lr_dev);
   const float lr0 = a.lr;
@@ -912,6 +962,8 @@ adam_step_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __rest
   }
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16(src[i]);
@@ -923,6 +975,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 // segments).  One launch instead of torch's zeros + cast + index_put.
 __global__ void pad_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int K, int T, int C,
                                   int Kp, int Cp, const int* __restrict__ inv_map, long long total) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cp = (int)(i % Cp);
@@ -939,6 +993,8 @@ __global__ void pad_weight_kernel(const float* __restrict__ src, __nv_bfloat16* 
 // permute + add_.
 __global__ void unpad_wgrad_add_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int T, int C,
                                        int Cp, const int* __restrict__ map, long long total) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -961,10 +1017,10 @@ int tok_bn_finalize_train_cv(int C, int c_valid, double count, float* sum, float
                              const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                              float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
   if (C <= 0 || count <= 0 || c_valid <= 0 || c_valid > C) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
-  bn_finalize_train_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      sum, sqsum, (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
-      save_invstd, C, c_valid);
-  TOK_CHECK_LAUNCH("bn_finalize_train");
+  cudaError_t le = launch_pdl(bn_finalize_train_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, sum, sqsum,
+                              (float)count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
+                              save_invstd, C, c_valid);
+  if (le != cudaSuccess) return set_error(TOK_ERR_CUDA, "bn_finalize_train: %s", cudaGetErrorString(le));
   return TOK_OK;
 }
 int tok_bn_finalize_train(int C, double count, float* sum, float* sqsum, const float* gamma,
@@ -978,7 +1034,7 @@ int tok_bn_finalize_eval_cv(int C, int c_valid, const float* running_mean, const
                             const float* gamma, const float* beta, float eps, float* scale, float* shift,
                             void* stream) {
   if (C <= 0 || c_valid <= 0 || c_valid > C) return set_error(TOK_ERR_INVALID, "bn_finalize: bad size");
-  bn_finalize_eval_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, gamma, beta,
+  (void)launch_pdl(bn_finalize_eval_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, running_mean, running_var, gamma, beta,
                                                                                eps, scale, shift, C, c_valid);
   TOK_CHECK_LAUNCH("bn_finalize_eval");
   return TOK_OK;
@@ -1010,15 +1066,16 @@ static int launch_bn_apply(long long rows, int C, const void* y, const float* sc
   const uint4* yp = (const uint4*)y;
   const uint4* rp = (const uint4*)residual;
   uint4* op = (uint4*)out;
+  cudaError_t le;
   if (residual && relu)
-    bn_apply_kernel<true, true><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec, fin);
+    le = launch_pdl(bn_apply_kernel<true, true>, dim3(grid), dim3(256), 0, st, yp, rp, op, scale, shift, total, cvec, fin);
   else if (residual)
-    bn_apply_kernel<true, false><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec, fin);
+    le = launch_pdl(bn_apply_kernel<true, false>, dim3(grid), dim3(256), 0, st, yp, rp, op, scale, shift, total, cvec, fin);
   else if (relu)
-    bn_apply_kernel<false, true><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec, fin);
+    le = launch_pdl(bn_apply_kernel<false, true>, dim3(grid), dim3(256), 0, st, yp, rp, op, scale, shift, total, cvec, fin);
   else
-    bn_apply_kernel<false, false><<<grid, 256, 0, st>>>(yp, rp, op, scale, shift, total, cvec, fin);
-  TOK_CHECK_LAUNCH("bn_apply");
+    le = launch_pdl(bn_apply_kernel<false, false>, dim3(grid), dim3(256), 0, st, yp, rp, op, scale, shift, total, cvec, fin);
+  if (le != cudaSuccess) return set_error(TOK_ERR_CUDA, "bn_apply: %s", cudaGetErrorString(le));
   return TOK_OK;
 }
 
@@ -1113,7 +1170,7 @@ int tok_bn_bwd_reduce(long long rows, int C, const void* dout, const void* dout2
   if (rows_per_cta < min_rows) rows_per_cta = min_rows;
   ctas = (rows + rows_per_cta - 1) / rows_per_cta;
   dim3 grid((unsigned)ctas, gy);
-  bn_bwd_reduce_kernel<<<grid, 256, cvec_b * 16 * sizeof(float), (cudaStream_t)stream>>>(
+  (void)launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), cvec_b * 16 * sizeof(float), (cudaStream_t)stream, 
       (const uint4*)dout, (const uint4*)dout2, (const uint4*)out, (const uint4*)y, sum_g, sum_gy, rows, cvec, cvec_b,
       (int)rows_per_cta);
   TOK_CHECK_LAUNCH("bn_bwd_reduce");
@@ -1124,7 +1181,7 @@ int tok_bn_bwd_finalize_cv(int C, int c_valid, double count, float* sum_g, float
                            const float* save_invstd, const float* gamma, float* coef_a, float* coef_c1,
                            float* coef_c0, float* dgamma, float* dbeta, int accumulate, void* stream) {
   if (C <= 0 || count <= 0 || c_valid <= 0 || c_valid > C) return set_error(TOK_ERR_INVALID, "bn_bwd_finalize: bad size");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(bn_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 
       sum_g, sum_gy, save_mean, save_invstd, gamma, (float)count, coef_a, coef_c1, coef_c0, dgamma, dbeta, accumulate,
       C, c_valid);
   TOK_CHECK_LAUNCH("bn_bwd_finalize");
@@ -1144,7 +1201,7 @@ int tok_bn_bwd_apply(long long rows, int C, const void* dout, const void* dout2,
   if (rows <= 0) return set_error(TOK_ERR_INVALID, "bn_bwd_apply: no rows");
   const int cvec = C / 8;
   const long long total = rows * cvec;
-  bn_bwd_apply_kernel<<<elem_grid(total, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(bn_bwd_apply_kernel, dim3(elem_grid(total, 256 * 2)), dim3(256), 0, (cudaStream_t)stream, 
       (const uint4*)dout, (const uint4*)dout2, (const uint4*)out, (const uint4*)y, coef_a, coef_c1, coef_c0,
       (uint4*)dy, (uint4*)dres, total, cvec);
   TOK_CHECK_LAUNCH("bn_bwd_apply");
@@ -1157,7 +1214,7 @@ int tok_maxpool_fwd(int n, int h, int w, int c, int k, int s, int pad, const voi
   if (k <= 0 || k > 15 || s <= 0) return set_error(TOK_ERR_INVALID, "maxpool: bad window");
   const int P = (h + 2 * pad - k) / s + 1, Q = (w + 2 * pad - k) / s + 1;
   const long long total = (long long)n * P * Q * (c / 8);
-  maxpool_fwd_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out,
+  (void)launch_pdl(maxpool_fwd_kernel, dim3(elem_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)out,
                                                                              (uint2*)argmax, total, h, w, P, Q, c / 8,
                                                                              k, s, pad);
   TOK_CHECK_LAUNCH("maxpool_fwd");
@@ -1170,7 +1227,7 @@ int tok_maxpool_bwd(int n, int h, int w, int c, int k, int s, int pad, const voi
   if (k <= 0 || k > 15 || s <= 0) return set_error(TOK_ERR_INVALID, "maxpool: bad window");
   const int P = (h + 2 * pad - k) / s + 1, Q = (w + 2 * pad - k) / s + 1;
   const long long total = (long long)n * h * w * (c / 8);
-  maxpool_bwd_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint2*)argmax,
+  (void)launch_pdl(maxpool_bwd_kernel, dim3(elem_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)dout, (const uint2*)argmax,
                                                                              (uint4*)dx, total, h, w, P, Q, c / 8, k,
                                                                              s, pad);
   TOK_CHECK_LAUNCH("maxpool_bwd");
@@ -1181,7 +1238,7 @@ int tok_gap_fwd(int n, int hw, int c, int mode, const void* x, void* out, void* 
   TOK_VEC_CHECK(c);
   if (mode < 0 || mode > 2) return set_error(TOK_ERR_INVALID, "gap: mode must be 0 (avg), 1 (max) or 2 (avgmax)");
   const long long total = (long long)n * (c / 8);
-  gap_fwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, n,
+  (void)launch_pdl(gap_fwd_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)out, n,
                                                                                    hw, c / 8, mode);
   TOK_CHECK_LAUNCH("gap_fwd");
   return TOK_OK;
@@ -1190,7 +1247,7 @@ int tok_gap_fwd(int n, int hw, int c, int mode, const void* x, void* out, void* 
 int tok_gap_bwd(int n, int hw, int c, const void* dout, void* dx, void* stream) {
   TOK_VEC_CHECK(c);
   const long long total = (long long)n * hw * (c / 8);
-  gap_bwd_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (uint4*)dx, total, hw,
+  (void)launch_pdl(gap_bwd_kernel, dim3(elem_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)dout, (uint4*)dx, total, hw,
                                                                          c / 8);
   TOK_CHECK_LAUNCH("gap_bwd");
   return TOK_OK;
@@ -1200,7 +1257,7 @@ int tok_gap_bwd_max(int n, int hw, int c, int mode, const void* dout, const void
   TOK_VEC_CHECK(c);
   if (mode != 1 && mode != 2) return set_error(TOK_ERR_INVALID, "gap_bwd_max: mode must be 1 (max) or 2 (avgmax)");
   const long long total = (long long)n * (c / 8);
-  gap_bwd_max_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(gap_bwd_max_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, 
       (const uint4*)dout, (const uint4*)x, (uint4*)dx, n, hw, c / 8, mode);
   TOK_CHECK_LAUNCH("gap_bwd_max");
   return TOK_OK;
@@ -1210,7 +1267,7 @@ int tok_softmax_xent(int rows, int C, long long ld, const void* logits, const lo
                      void* dlogits, float inv_norm, float gscale, const float* gscale_dev, long long ignore_index,
                      int* correct, void* stream) {
   if (rows <= 0 || C <= 0) return set_error(TOK_ERR_INVALID, "softmax_xent: bad size");
-  softmax_xent_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, loss_sum,
+  (void)launch_pdl(softmax_xent_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)logits, target, loss_sum,
                                                              (__nv_bfloat16*)dlogits, C, ld, inv_norm, gscale,
                                                              gscale_dev, ignore_index, correct);
   TOK_CHECK_LAUNCH("softmax_xent");
@@ -1223,7 +1280,7 @@ int tok_nchw_to_nhwc(int n, int c, int hw, int cp, int src_is_bf16, const void* 
     const long long total = (long long)n * hw;
     const int g = elem_grid(total, 256);
     cudaStream_t st = (cudaStream_t)stream;
-#define TOK_SMALL(T, CV) nchw_to_nhwc_small_kernel<T, CV><<<g, 256, 0, st>>>((const T*)src, (uint4*)dst, c, hw, total)
+#define TOK_SMALL(T, CV) (void)launch_pdl(nchw_to_nhwc_small_kernel<T, CV>, dim3(g), dim3(256), 0, st, (const T*)src, (uint4*)dst, c, hw, total)
     if (src_is_bf16) {
       if (cp == 8) TOK_SMALL(__nv_bfloat16, 1); else if (cp == 16) TOK_SMALL(__nv_bfloat16, 2);
       else if (cp == 24) TOK_SMALL(__nv_bfloat16, 3); else TOK_SMALL(__nv_bfloat16, 4);
@@ -1237,10 +1294,10 @@ int tok_nchw_to_nhwc(int n, int c, int hw, int cp, int src_is_bf16, const void* 
   }
   dim3 grid((hw + 31) / 32, (cp + 31) / 32, n), block(32, 8);
   if (src_is_bf16)
-    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src,
+    (void)launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src,
                                                                                  (__nv_bfloat16*)dst, c, hw, cp);
   else
-    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, (__nv_bfloat16*)dst, c, hw,
+    (void)launch_pdl(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const float*)src, (__nv_bfloat16*)dst, c, hw,
                                                                          cp);
   TOK_CHECK_LAUNCH("nchw_to_nhwc");
   return TOK_OK;
@@ -1250,10 +1307,10 @@ int tok_nhwc_to_nchw(int n, int c, int hw, int cp, int dst_is_bf16, const void* 
   if (n <= 0 || c <= 0 || hw <= 0 || cp < c) return set_error(TOK_ERR_INVALID, "nhwc_to_nchw: bad size");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
   if (dst_is_bf16)
-    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src,
+    (void)launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src,
                                                                                  (__nv_bfloat16*)dst, c, hw, cp);
   else
-    nhwc_to_nchw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (float*)dst, c, hw,
+    (void)launch_pdl(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, (float*)dst, c, hw,
                                                                          cp);
   TOK_CHECK_LAUNCH("nhwc_to_nchw");
   return TOK_OK;
@@ -1264,10 +1321,10 @@ int tok_stem_pack_input(int n, int c, int h, int w, int src_is_bf16, const void*
   const int P = (h - 1) / 2 + 1, Q = (w - 1) / 2 + 1, H2 = P + 3, W2 = Q + 3;
   const long long total = (long long)n * H2 * W2;
   if (src_is_bf16)
-    stem_s2d_pack_kernel<__nv_bfloat16><<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    (void)launch_pdl(stem_s2d_pack_kernel<__nv_bfloat16>, dim3(elem_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)src, (uint4*)dst, n, c, h, w, H2, W2, 3);
   else
-    stem_s2d_pack_kernel<float><<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)src, (uint4*)dst,
+    (void)launch_pdl(stem_s2d_pack_kernel<float>, dim3(elem_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const float*)src, (uint4*)dst,
                                                                                         n, c, h, w, H2, W2, 3);
   TOK_CHECK_LAUNCH("stem_pack_input");
   return TOK_OK;
@@ -1275,14 +1332,14 @@ int tok_stem_pack_input(int n, int c, int h, int w, int src_is_bf16, const void*
 
 int tok_stem_pack_weight(int k, int c, const float* w, void* wp, void* stream) {
   if (k <= 0 || c <= 0 || c > 4) return set_error(TOK_ERR_INVALID, "stem_pack_weight: needs 1..4 channels");
-  stem_pack_weight_kernel<<<(k * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, k, 7, 7, c);
+  (void)launch_pdl(stem_pack_weight_kernel, dim3((k * 256 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, w, (__nv_bfloat16*)wp, k, 7, 7, c);
   TOK_CHECK_LAUNCH("stem_pack_weight");
   return TOK_OK;
 }
 
 int tok_stem_unpack_wgrad(int k, int c, const float* dwp, float* dw, int accumulate, void* stream) {
   if (k <= 0 || c <= 0 || c > 4) return set_error(TOK_ERR_INVALID, "stem_unpack_wgrad: needs 1..4 channels");
-  stem_unpack_wgrad_kernel<<<(k * 49 * c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dwp, dw, k, 7, 7, c,
+  (void)launch_pdl(stem_unpack_wgrad_kernel, dim3((k * 49 * c + 255) / 256), dim3(256), 0, (cudaStream_t)stream, dwp, dw, k, 7, 7, c,
                                                                                       accumulate);
   TOK_CHECK_LAUNCH("stem_unpack_wgrad");
   return TOK_OK;
@@ -1292,7 +1349,7 @@ int tok_sgd_step(long long n, float* param, const float* grad, float* momentum_b
                  float momentum, float weight_decay, float dampening, int nesterov, float grad_scale, int first_step,
                  void* stream) {
   if (n <= 0) return TOK_OK;
-  sgd_step_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf,
+  (void)launch_pdl(sgd_step_kernel, dim3(elem_grid(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, param, grad, momentum_buf,
                                                                           (__nv_bfloat16*)shadow_bf16, n, lr, momentum,
                                                                           weight_decay, dampening, nesterov,
                                                                           grad_scale, first_step);
@@ -1306,7 +1363,7 @@ int tok_adam_step(long long n, float* param, const float* grad, float* exp_avg, 
   if (n <= 0) return TOK_OK;
   if (step <= 0) return set_error(TOK_ERR_INVALID, "adam: step must be >= 1");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  adam_step_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(adam_step_kernel, dim3(elem_grid(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, 
       param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, decoupled,
       bc1, bc2, grad_scale);
   TOK_CHECK_LAUNCH("adam_step");
@@ -1333,8 +1390,8 @@ int tok_sgd_step_dev_groups(long long n, float* param, float* grad, float* momen
   ParamSegs segs;
   int rc = check_segs(&segs, seg_begin, seg_lr_mult, seg_wd_mult, n_segs, "sgd_step_dev_groups");
   if (rc) return rc;
-  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
-  sgd_step_dev_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(step_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev);
+  (void)launch_pdl(sgd_step_dev_kernel, dim3(elem_grid(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, 
       param, grad, momentum_buf, (__nv_bfloat16*)shadow_bf16, n, lr_dev, step_dev, momentum, weight_decay, dampening,
       nesterov, grad_scale, zero_grad, segs);
   TOK_CHECK_LAUNCH("sgd_step_dev");
@@ -1358,13 +1415,13 @@ int tok_adam_step_dev_groups(long long n, float* param, float* grad, float* exp_
   ParamSegs segs;
   int rc = check_segs(&segs, seg_begin, seg_lr_mult, seg_wd_mult, n_segs, "adam_step_dev_groups");
   if (rc) return rc;
-  step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  (void)launch_pdl(step_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev);
   if (seg_steps && n_segs > 0) {
-    seg_steps_advance_kernel<<<(n_segs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seg_steps, seg_lr_mult, seg_wd_mult,
+    (void)launch_pdl(seg_steps_advance_kernel, dim3((n_segs + 255) / 256), dim3(256), 0, (cudaStream_t)stream, seg_steps, seg_lr_mult, seg_wd_mult,
                                                                                    n_segs);
     segs.steps = seg_steps;
   }
-  adam_step_dev_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(adam_step_dev_kernel, dim3(elem_grid(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, 
       param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr_dev, step_dev, beta1, beta2, eps,
       weight_decay, decoupled, grad_scale, zero_grad, segs);
   TOK_CHECK_LAUNCH("adam_step_dev");
@@ -1381,7 +1438,7 @@ int tok_adam_step_dev(long long n, float* param, float* grad, float* exp_avg, fl
 int tok_pad_weight(int K, int T, int C, int Kp, int Cp, const float* src, const int* inv_map, void* dst, void* stream) {
   if (K <= 0 || T <= 0 || C <= 0 || Kp < K || Cp < C) return set_error(TOK_ERR_INVALID, "pad_weight: bad shape");
   const long long total = (long long)Kp * T * Cp;
-  pad_weight_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, K, T, C, Kp, Cp,
+  (void)launch_pdl(pad_weight_kernel, dim3(elem_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, K, T, C, Kp, Cp,
                                                                              inv_map, total);
   TOK_CHECK_LAUNCH("pad_weight");
   return TOK_OK;
@@ -1390,14 +1447,14 @@ int tok_pad_weight(int K, int T, int C, int Kp, int Cp, const float* src, const 
 int tok_unpad_wgrad_add(int K, int T, int C, int Cp, const float* src, const int* map, float* dst, void* stream) {
   if (K <= 0 || T <= 0 || C <= 0 || Cp < C) return set_error(TOK_ERR_INVALID, "unpad_wgrad_add: bad shape");
   const long long total = (long long)K * T * C;
-  unpad_wgrad_add_kernel<<<elem_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, K, T, C, Cp, map, total);
+  (void)launch_pdl(unpad_wgrad_add_kernel, dim3(elem_grid(total, 256)), dim3(256), 0, (cudaStream_t)stream, src, dst, K, T, C, Cp, map, total);
   TOK_CHECK_LAUNCH("unpad_wgrad_add");
   return TOK_OK;
 }
 
 int tok_cast_f32_bf16(long long n, const float* src, void* dst, void* stream) {
   if (n <= 0) return TOK_OK;
-  cast_f32_bf16_kernel<<<elem_grid(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  (void)launch_pdl(cast_f32_bf16_kernel, dim3(elem_grid(n, 256 * 4)), dim3(256), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, n);
   TOK_CHECK_LAUNCH("cast_f32_bf16");
   return TOK_OK;
 }

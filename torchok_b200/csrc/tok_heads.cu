@@ -35,6 +35,8 @@ __device__ __forceinline__ float ld_any(const void* p, long long i, int is_bf16)
 __global__ void __launch_bounds__(128)
 rownorm_fwd_kernel(int rows, int d, const void* __restrict__ x, int x_is_bf16, float scale,
                    __nv_bfloat16* __restrict__ xhat, int ldo, float* __restrict__ inv_norm) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -58,6 +60,8 @@ __global__ void __launch_bounds__(128)
 rownorm_bwd_kernel(int rows, int d, const void* __restrict__ x, int x_is_bf16, const float* __restrict__ inv_norm,
                    float scale, const void* __restrict__ g, int g_is_bf16, int ldg, void* __restrict__ dx,
                    int dx_is_bf16, int accumulate) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -98,6 +102,8 @@ __global__ void __launch_bounds__(128)
 arcface_margin_fwd_kernel(int rows, int d, int ldx, const __nv_bfloat16* __restrict__ xs,
                           const __nv_bfloat16* __restrict__ wh, const long long* __restrict__ target, int num_classes,
                           __nv_bfloat16* __restrict__ logits, long long ldl, Margin m, float* __restrict__ cos_t) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -117,6 +123,8 @@ arcface_margin_fwd_kernel(int rows, int d, int ldx, const __nv_bfloat16* __restr
 __global__ void arcface_margin_bwd_kernel(int rows, const long long* __restrict__ target, int num_classes,
                                           const float* __restrict__ cos_t, __nv_bfloat16* __restrict__ dlogits,
                                           long long ldl, Margin m) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const long long t = target[r];
@@ -132,6 +140,8 @@ __global__ void arcface_margin_bwd_kernel(int rows, const long long* __restrict_
 __global__ void __launch_bounds__(256)
 contrastive_fwd_kernel(int B, int M, int d, const float* __restrict__ e1, const float* __restrict__ e2,
                        const float* __restrict__ R, float margin, float* __restrict__ S, float* __restrict__ Lrow) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ float a[];  // emb1 row
   __shared__ float part[8];
   const int i = blockIdx.x;
@@ -172,6 +182,8 @@ __global__ void __launch_bounds__(256)
 contrastive_bwd_kernel(int B, int M, int d, const float* __restrict__ e1, const float* __restrict__ e2,
                        const float* __restrict__ R, const float* __restrict__ S, const float* __restrict__ gL,
                        float margin, int which, float* __restrict__ out) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ float coef[];  // M (which 0) or B (which 1) coefficients
   const int row = blockIdx.x;
   const int n_other = which == 0 ? M : B;
@@ -214,7 +226,7 @@ int tok_rownorm_fwd(int rows, int d, const void* x, int x_is_bf16, float scale, 
                     float* inv_norm, void* stream) {
   if (rows <= 0 || d <= 0 || ld_out < d) return set_error(TOK_ERR_INVALID, "rownorm_fwd: bad shape");
   const long long threads = (long long)rows * 32;
-  rownorm_fwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(rownorm_fwd_kernel, dim3((unsigned)((threads + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, 
       rows, d, x, x_is_bf16, scale, (__nv_bfloat16*)xhat_bf16, ld_out, inv_norm);
   TOK_CHECK_LAUNCH("rownorm_fwd");
   return TOK_OK;
@@ -224,7 +236,7 @@ int tok_rownorm_bwd(int rows, int d, const void* x, int x_is_bf16, const float* 
                     int g_is_bf16, int ld_g, void* dx, int dx_is_bf16, int accumulate, void* stream) {
   if (rows <= 0 || d <= 0 || ld_g < d) return set_error(TOK_ERR_INVALID, "rownorm_bwd: bad shape");
   const long long threads = (long long)rows * 32;
-  rownorm_bwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(rownorm_bwd_kernel, dim3((unsigned)((threads + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, 
       rows, d, x, x_is_bf16, inv_norm, scale, g, g_is_bf16, ld_g, dx, dx_is_bf16, accumulate);
   TOK_CHECK_LAUNCH("rownorm_bwd");
   return TOK_OK;
@@ -246,7 +258,7 @@ int tok_arcface_margin_fwd(int rows, int d, int ld_x, const void* xs_bf16, const
                            float scale, float margin, int easy_margin, float* cos_t, void* stream) {
   if (rows <= 0 || d <= 0 || num_classes <= 0 || !cos_t) return set_error(TOK_ERR_INVALID, "arcface_margin_fwd: bad arguments");
   const long long threads = (long long)rows * 32;
-  arcface_margin_fwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(arcface_margin_fwd_kernel, dim3((unsigned)((threads + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, 
       rows, d, ld_x, (const __nv_bfloat16*)xs_bf16, (const __nv_bfloat16*)wh_bf16, target, num_classes,
       (__nv_bfloat16*)logits_bf16, ld_logits, make_margin(scale, margin, easy_margin), cos_t);
   TOK_CHECK_LAUNCH("arcface_margin_fwd");
@@ -257,7 +269,7 @@ int tok_arcface_margin_bwd(int rows, const long long* target, int num_classes, c
                            void* dlogits_bf16, long long ld_logits, float scale, float margin, int easy_margin,
                            void* stream) {
   if (rows <= 0 || num_classes <= 0) return set_error(TOK_ERR_INVALID, "arcface_margin_bwd: bad arguments");
-  arcface_margin_bwd_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(arcface_margin_bwd_kernel, dim3((rows + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 
       rows, target, num_classes, cos_t, (__nv_bfloat16*)dlogits_bf16, ld_logits, make_margin(scale, margin, easy_margin));
   TOK_CHECK_LAUNCH("arcface_margin_bwd");
   return TOK_OK;
@@ -266,7 +278,7 @@ int tok_arcface_margin_bwd(int rows, const long long* target, int num_classes, c
 int tok_contrastive_fwd(int B, int M, int d, const float* emb1, const float* emb2, const float* R, float margin,
                         float* S, float* loss_rows, void* stream) {
   if (B <= 0 || M <= 0 || d <= 0 || d > 8192) return set_error(TOK_ERR_INVALID, "contrastive_fwd: bad shape");
-  contrastive_fwd_kernel<<<B, 256, d * sizeof(float), (cudaStream_t)stream>>>(B, M, d, emb1, emb2, R, margin, S,
+  (void)launch_pdl(contrastive_fwd_kernel, dim3(B), dim3(256), d * sizeof(float), (cudaStream_t)stream, B, M, d, emb1, emb2, R, margin, S,
                                                                              loss_rows);
   TOK_CHECK_LAUNCH("contrastive_fwd");
   return TOK_OK;
@@ -277,9 +289,9 @@ int tok_contrastive_bwd(int B, int M, int d, const float* emb1, const float* emb
   if (B <= 0 || M <= 0 || d <= 0 || B > 8192 || M > 8192) return set_error(TOK_ERR_INVALID, "contrastive_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (d_emb1)
-    contrastive_bwd_kernel<<<B, 256, M * sizeof(float), st>>>(B, M, d, emb1, emb2, R, S, grad_rows, margin, 0, d_emb1);
+    (void)launch_pdl(contrastive_bwd_kernel, dim3(B), dim3(256), M * sizeof(float), st, B, M, d, emb1, emb2, R, S, grad_rows, margin, 0, d_emb1);
   if (d_emb2)
-    contrastive_bwd_kernel<<<M, 256, B * sizeof(float), st>>>(B, M, d, emb1, emb2, R, S, grad_rows, margin, 1, d_emb2);
+    (void)launch_pdl(contrastive_bwd_kernel, dim3(M), dim3(256), B * sizeof(float), st, B, M, d, emb1, emb2, R, S, grad_rows, margin, 1, d_emb2);
   TOK_CHECK_LAUNCH("contrastive_bwd");
   return TOK_OK;
 }

@@ -49,6 +49,8 @@ __device__ __forceinline__ float bf(float v) { return __bfloat162float(__float2b
 __global__ void __launch_bounds__(256)
 nearest_fwd_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total, int hi, int wi, int ho, int wo,
                    int cvec, int dvec, int doff) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -65,6 +67,8 @@ nearest_fwd_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long 
 __global__ void __launch_bounds__(256)
 nearest_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ dsrc, long long total, int hi, int wi, int ho,
                    int wo, int cvec, int dvec, int doff) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -93,6 +97,8 @@ nearest_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ dsrc, lon
 __global__ void __launch_bounds__(256)
 channel_scale_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, uint4* __restrict__ out,
                      long long total, long long hw, int cvec) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -111,6 +117,8 @@ channel_scale_kernel(const uint4* __restrict__ x, const float* __restrict__ scal
 // one 8-class vector of the logits per position (online max / sum), then the CTA merges its 256 partial pairs.
 __global__ void __launch_bounds__(256)
 gather_stats_kernel(const uint4* __restrict__ logits, float* __restrict__ stats, int hw, int kvec, int K) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int b = blockIdx.x, kv = blockIdx.y;
   __shared__ float sm[256][8], ss[256][8];
   float m[8], s[8];
@@ -156,6 +164,8 @@ gather_stats_kernel(const uint4* __restrict__ logits, float* __restrict__ stats,
 __global__ void __launch_bounds__(256)
 gather_ctx_kernel(const uint4* __restrict__ feats, const __nv_bfloat16* __restrict__ logits,
                   const float* __restrict__ stats, float* __restrict__ ctx, int hw, int cvec, int kp, int K, int per_split) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int b = blockIdx.x, k0 = blockIdx.y * 8;
   const int lanes = 256 / cvec;
   const int cv = threadIdx.x % cvec, pl = threadIdx.x / cvec;
@@ -206,6 +216,8 @@ gather_ctx_kernel(const uint4* __restrict__ feats, const __nv_bfloat16* __restri
 }
 
 __global__ void cast_f32_bf16_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16(src[i]);
 }
@@ -217,6 +229,8 @@ gather_bwd_kernel(const __nv_bfloat16* __restrict__ feats, const __nv_bfloat16* 
                   const float* __restrict__ stats, const __nv_bfloat16* __restrict__ ctx,
                   const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dfeats,
                   __nv_bfloat16* __restrict__ dlogits, int hw, int C, int kp, int K, int rows_per_cta) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ float sh[];
   float* s_d = sh;               // [K][C] dctx as fp32
   float* s_D = sh + K * C;       // [K]
@@ -303,6 +317,8 @@ object_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
                    const __nv_bfloat16* __restrict__ value, __nv_bfloat16* __restrict__ out,
                    const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dq, float* __restrict__ dkey,
                    float* __restrict__ dvalue, int hw, int Kc, int K, float scale, int rows_per_cta) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ float sh[];
   float* s_key = sh;                    // [K][Kc]
   float* s_val = s_key + K * Kc;        // [K][Kc]
@@ -417,7 +433,7 @@ int tok_nearest_fwd(int n, int hi, int wi, int c, int ho, int wo, const void* sr
       dst_c_offset + c > dst_c)
     return set_error(TOK_ERR_INVALID, "nearest_fwd: bad shape (channel counts and offsets must be multiples of 8)");
   const long long total = (long long)n * ho * wo * (c / 8);
-  nearest_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, total, hi, wi, ho,
+  (void)launch_pdl(nearest_fwd_kernel, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)src, (uint4*)dst, total, hi, wi, ho,
                                                                        wo, c / 8, dst_c / 8, dst_c_offset / 8);
   TOK_CHECK_LAUNCH("nearest_fwd");
   return TOK_OK;
@@ -429,7 +445,7 @@ int tok_nearest_bwd(int n, int hi, int wi, int c, int ho, int wo, const void* do
       dout_c_offset + c > dout_c)
     return set_error(TOK_ERR_INVALID, "nearest_bwd: bad shape (channel counts and offsets must be multiples of 8)");
   const long long total = (long long)n * hi * wi * (c / 8);
-  nearest_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (uint4*)dsrc, total, hi, wi,
+  (void)launch_pdl(nearest_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)dout, (uint4*)dsrc, total, hi, wi,
                                                                        ho, wo, c / 8, dout_c / 8, dout_c_offset / 8);
   TOK_CHECK_LAUNCH("nearest_bwd");
   return TOK_OK;
@@ -438,7 +454,7 @@ int tok_nearest_bwd(int n, int hi, int wi, int c, int ho, int wo, const void* do
 int tok_channel_scale(int n, long long hw, int c, const void* x, const float* scale, void* out, void* stream) {
   if (n <= 0 || hw <= 0 || c <= 0 || (c % 8)) return set_error(TOK_ERR_INVALID, "channel_scale: bad shape");
   const long long total = (long long)n * hw * (c / 8);
-  channel_scale_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, scale, (uint4*)out, total, hw,
+  (void)launch_pdl(channel_scale_kernel, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, scale, (uint4*)out, total, hw,
                                                                          c / 8);
   TOK_CHECK_LAUNCH("channel_scale");
   return TOK_OK;
@@ -450,7 +466,7 @@ int tok_spatial_gather_fwd(int b, int hw, int c, int k, int kp, const void* feat
     return set_error(TOK_ERR_INVALID, "spatial_gather_fwd: need C %% 8 == 0, C <= 2048, class pitch %% 8 == 0");
   cudaStream_t st = (cudaStream_t)stream;
   const int cvec = c / 8;
-  gather_stats_kernel<<<dim3(b, kp / 8), 256, 0, st>>>((const uint4*)logits, stats, hw, kp / 8, k);
+  (void)launch_pdl(gather_stats_kernel, dim3(dim3(b, kp / 8)), dim3(256), 0, st, (const uint4*)logits, stats, hw, kp / 8, k);
   cudaMemsetAsync(ctx_f32, 0, (size_t)b * k * c * 4, st);
   const int kgroups = (k + 7) / 8;
   int splits = (148 * 4 + b * kgroups - 1) / (b * kgroups);
@@ -460,10 +476,10 @@ int tok_spatial_gather_fwd(int b, int hw, int c, int k, int kp, const void* feat
   if (splits < 1) splits = 1;
   const int per_split = (hw + splits - 1) / splits;
   if (cvec > 256) return set_error(TOK_ERR_INVALID, "spatial_gather_fwd: C too large");
-  gather_ctx_kernel<<<dim3(b, kgroups, splits), 256, 0, st>>>((const uint4*)feats, (const __nv_bfloat16*)logits, stats,
+  (void)launch_pdl(gather_ctx_kernel, dim3(dim3(b, kgroups, splits)), dim3(256), 0, st, (const uint4*)feats, (const __nv_bfloat16*)logits, stats,
                                                              ctx_f32, hw, cvec, kp, k, per_split);
   const long long n = (long long)b * k * c;
-  cast_f32_bf16_rows_kernel<<<grid_for(n), 256, 0, st>>>(ctx_f32, (__nv_bfloat16*)ctx, n);
+  (void)launch_pdl(cast_f32_bf16_rows_kernel, dim3(grid_for(n)), dim3(256), 0, st, ctx_f32, (__nv_bfloat16*)ctx, n);
   TOK_CHECK_LAUNCH("spatial_gather_fwd");
   return TOK_OK;
 }
@@ -480,7 +496,7 @@ int tok_spatial_gather_bwd(int b, int hw, int c, int k, int kp, const void* feat
   int gy = (148 * 2 + b - 1) / b;
   if (gy > (hw + 7) / 8) gy = (hw + 7) / 8;
   const int rows_per_cta = (hw + gy - 1) / gy;
-  gather_bwd_kernel<<<dim3(b, gy), 256, smem, (cudaStream_t)stream>>>(
+  (void)launch_pdl(gather_bwd_kernel, dim3(dim3(b, gy)), dim3(256), smem, (cudaStream_t)stream, 
       (const __nv_bfloat16*)feats, (const __nv_bfloat16*)logits, stats, (const __nv_bfloat16*)ctx,
       (const __nv_bfloat16*)dctx, (__nv_bfloat16*)dfeats, (__nv_bfloat16*)dlogits, hw, c, kp, k, rows_per_cta);
   TOK_CHECK_LAUNCH("spatial_gather_bwd");
@@ -509,7 +525,7 @@ int tok_object_attn_fwd(int b, int hw, int kc, int k, float scale, const void* q
   if (rc) return rc;
   cudaError_t e = cudaFuncSetAttribute(object_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "object_attn_fwd: %s", cudaGetErrorString(e));
-  object_attn_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  (void)launch_pdl(object_attn_kernel<false>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, 
       (const __nv_bfloat16*)q, (const __nv_bfloat16*)key, (const __nv_bfloat16*)value, (__nv_bfloat16*)out, nullptr,
       nullptr, nullptr, nullptr, hw, kc, k, scale, rpc);
   TOK_CHECK_LAUNCH("object_attn_fwd");
@@ -530,11 +546,11 @@ int tok_object_attn_bwd(int b, int hw, int kc, int k, float scale, const void* q
   const long long n = (long long)b * k * kc;
   cudaMemsetAsync(dkey_f32, 0, n * 4, st);
   cudaMemsetAsync(dvalue_f32, 0, n * 4, st);
-  object_attn_kernel<true><<<grid, 256, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)key,
+  (void)launch_pdl(object_attn_kernel<true>, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)key,
                                                     (const __nv_bfloat16*)value, nullptr, (const __nv_bfloat16*)dout,
                                                     (__nv_bfloat16*)dq, dkey_f32, dvalue_f32, hw, kc, k, scale, rpc);
-  cast_f32_bf16_rows_kernel<<<grid_for(n), 256, 0, st>>>(dkey_f32, (__nv_bfloat16*)dkey, n);
-  cast_f32_bf16_rows_kernel<<<grid_for(n), 256, 0, st>>>(dvalue_f32, (__nv_bfloat16*)dvalue, n);
+  (void)launch_pdl(cast_f32_bf16_rows_kernel, dim3(grid_for(n)), dim3(256), 0, st, dkey_f32, (__nv_bfloat16*)dkey, n);
+  (void)launch_pdl(cast_f32_bf16_rows_kernel, dim3(grid_for(n)), dim3(256), 0, st, dvalue_f32, (__nv_bfloat16*)dvalue, n);
   TOK_CHECK_LAUNCH("object_attn_bwd");
   return TOK_OK;
 }

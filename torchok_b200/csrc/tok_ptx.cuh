@@ -23,6 +23,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ----------------------------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization (tok_internal.h: launch_pdl) may be scheduled
+// while the previous kernel of its stream is still draining.  pdl_wait(): everything the previous kernels wrote is
+// visible after it — nothing produced (or still read) by them may be touched before.  pdl_launch(): lets the NEXT
+// kernel's CTAs be scheduled early; called right after the wait, so a dependent never starts before its predecessor has
+// itself seen its predecessors complete.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -46,6 +46,8 @@ struct FuseTerms {
 __global__ void __launch_bounds__(256)
 fuse_sum_fwd_kernel(FuseTerms t, uint4* __restrict__ out, uint8_t* __restrict__ bits, long long total, int H, int W,
                     int cvec, int relu) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % cvec);
@@ -80,6 +82,8 @@ fuse_sum_fwd_kernel(FuseTerms t, uint4* __restrict__ out, uint8_t* __restrict__ 
 __global__ void __launch_bounds__(256)
 fuse_sum_bwd_kernel(const uint4* __restrict__ dout, const uint8_t* __restrict__ bits, uint4* __restrict__ dterm,
                     long long total, int H, int W, int cvec, int shift) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int Hs = H >> shift, Ws = W >> shift, f = 1 << shift;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -120,6 +124,8 @@ __device__ __forceinline__ void bilinear_taps(int o, float scale, int in_size, i
 __global__ void __launch_bounds__(256)
 bilinear_fwd_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long total, int Hi, int Wi, int Ho,
                     int Wo, int scvec, int dcvec, int coff_vec, float sh, float sw) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % scvec);
@@ -149,6 +155,8 @@ bilinear_fwd_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long
 __global__ void __launch_bounds__(256)
 bilinear_bwd_kernel(const uint4* __restrict__ dout, uint4* __restrict__ dsrc, long long total, int Hi, int Wi, int Ho,
                     int Wo, int scvec, int dcvec, int coff_vec, float sh, float sw) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int fh = (int)ceilf(1.f / sh) + 1, fw = (int)ceilf(1.f / sw) + 1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -191,6 +199,8 @@ xent_small_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __r
                   float* __restrict__ loss_sum, float* __restrict__ count, __nv_bfloat16* __restrict__ dlogits,
                   long long rows, int C, int ld, const float* __restrict__ inv_norm_dev, float gscale,
                   const float* __restrict__ gscale_dev, long long ignore_index) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float s_loss[8], s_cnt[8];
   float my_loss = 0.f, my_cnt = 0.f;
   if (gscale_dev) gscale *= __ldg(gscale_dev);
@@ -250,6 +260,8 @@ xent_small_vec_kernel(const uint4* __restrict__ logits, const long long* __restr
                       float* __restrict__ loss_sum, float* __restrict__ count, uint4* __restrict__ dlogits,
                       long long rows, int C, const float* __restrict__ inv_norm_dev, float gscale,
                       const float* __restrict__ gscale_dev, long long ignore_index) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float s_loss[8], s_cnt[8];
   float my_loss = 0.f, my_cnt = 0.f;
   if (gscale_dev) gscale *= __ldg(gscale_dev);
@@ -340,6 +352,8 @@ xent_small_vec_kernel(const uint4* __restrict__ logits, const long long* __restr
 __global__ void __launch_bounds__(256)
 dice_stats_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ target,
                   float* __restrict__ stats /* [3][64]: I, sum p, count */, long long rows, int C, int ld) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float sh[3][64];
   for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) (&sh[0][0])[i] = 0.f;
   __syncthreads();
@@ -381,6 +395,8 @@ dice_stats_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __r
 
 __global__ void dice_finalize_kernel(const float* __restrict__ stats, int C, float smooth, float eps, int log_loss,
                                      float* __restrict__ loss, float* __restrict__ coef /* [2][64]: a, b */) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int c = threadIdx.x;  // 64 threads
   float l = 0.f;
   if (c < C) {
@@ -415,6 +431,8 @@ __global__ void __launch_bounds__(256)
 dice_bwd_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ target,
                 const float* __restrict__ coef, const float* __restrict__ gscale_dev,
                 __nv_bfloat16* __restrict__ dlogits, long long rows, int C, int ld) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float sa[64], sb[64];
   if (threadIdx.x < 64) {
     sa[threadIdx.x] = coef[threadIdx.x];
@@ -469,7 +487,7 @@ int tok_fuse_sum_fwd(int n, int h, int w, int c, int nterms, const void* const* 
     t.dst[k] = nullptr;
   }
   const long long total = (long long)n * h * w * (c / 8);
-  fuse_sum_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(t, (uint4*)out, (uint8_t*)bits, total, h, w,
+  (void)launch_pdl(fuse_sum_fwd_kernel, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, t, (uint4*)out, (uint8_t*)bits, total, h, w,
                                                                         c / 8, relu);
   TOK_CHECK_LAUNCH("fuse_sum_fwd");
   return TOK_OK;
@@ -479,7 +497,7 @@ int tok_fuse_sum_bwd(int n, int h, int w, int c, int shift, const void* dout, co
                      void* stream) {
   if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8) || shift < 0) return set_error(TOK_ERR_INVALID, "fuse_sum_bwd: bad shape");
   const long long total = (long long)n * (h >> shift) * (w >> shift) * (c / 8);
-  fuse_sum_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint8_t*)bits,
+  (void)launch_pdl(fuse_sum_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)dout, (const uint8_t*)bits,
                                                                         (uint4*)dterm, total, h, w, c / 8, shift);
   TOK_CHECK_LAUNCH("fuse_sum_bwd");
   return TOK_OK;
@@ -491,7 +509,7 @@ int tok_bilinear_fwd(int n, int hi, int wi, int c, int ho, int wo, const void* s
       dst_c_offset + c > dst_c)
     return set_error(TOK_ERR_INVALID, "bilinear_fwd: bad shape (channel counts and offsets must be multiples of 8)");
   const long long total = (long long)n * ho * wo * (c / 8);
-  bilinear_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(bilinear_fwd_kernel, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
       (const uint4*)src, (uint4*)dst, total, hi, wi, ho, wo, c / 8, dst_c / 8, dst_c_offset / 8, (float)hi / ho,
       (float)wi / wo);
   TOK_CHECK_LAUNCH("bilinear_fwd");
@@ -504,7 +522,7 @@ int tok_bilinear_bwd(int n, int hi, int wi, int c, int ho, int wo, const void* d
       (dout_c_offset % 8) || dout_c_offset + c > dout_c)
     return set_error(TOK_ERR_INVALID, "bilinear_bwd: bad shape (channel counts and offsets must be multiples of 8)");
   const long long total = (long long)n * hi * wi * (c / 8);
-  bilinear_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+  (void)launch_pdl(bilinear_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, (cudaStream_t)stream, 
       (const uint4*)dout, (uint4*)dsrc, total, hi, wi, ho, wo, c / 8, dout_c / 8, dout_c_offset / 8, (float)hi / ho,
       (float)wi / wo);
   TOK_CHECK_LAUNCH("bilinear_bwd");
@@ -519,7 +537,7 @@ int tok_softmax_xent_small(long long rows, int C, int ld, const void* logits, co
   const bool vec = ld % 8 == 0 && ld <= 32 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0;
 #define TOK_XENT_VEC(LV)                                                                                          \
-  xent_small_vec_kernel<LV><<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>(                                    \
+  (void)launch_pdl(xent_small_vec_kernel<LV>, dim3(grid_for(rows)), dim3(256), 0, (cudaStream_t)stream,                                     \
       (const uint4*)logits, target, loss_sum, count, (uint4*)dlogits, rows, C, inv_count_dev, gscale, gscale_dev, \
       ignore_index)
   if (vec && ld == 8) TOK_XENT_VEC(1);
@@ -527,7 +545,7 @@ int tok_softmax_xent_small(long long rows, int C, int ld, const void* logits, co
   else if (vec && ld == 24) TOK_XENT_VEC(3);
   else if (vec && ld == 32) TOK_XENT_VEC(4);
   else
-    xent_small_kernel<<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>(
+    (void)launch_pdl(xent_small_kernel, dim3(grid_for(rows)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)logits, target, loss_sum, count, (__nv_bfloat16*)dlogits, rows, C, ld, inv_count_dev,
         gscale, gscale_dev, ignore_index);
 #undef TOK_XENT_VEC
@@ -538,7 +556,7 @@ int tok_softmax_xent_small(long long rows, int C, int ld, const void* logits, co
 int tok_dice_stats(long long rows, int C, int ld, const void* logits, const long long* target, float* stats,
                    void* stream) {
   if (rows <= 0 || C <= 0 || C > 64 || ld < C || !stats) return set_error(TOK_ERR_INVALID, "dice_stats: 1 <= C <= 64, ld >= C");
-  dice_stats_kernel<<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, stats, rows, C, ld);
+  (void)launch_pdl(dice_stats_kernel, dim3(grid_for(rows)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)logits, target, stats, rows, C, ld);
   TOK_CHECK_LAUNCH("dice_stats");
   return TOK_OK;
 }
@@ -546,7 +564,7 @@ int tok_dice_stats(long long rows, int C, int ld, const void* logits, const long
 int tok_dice_finalize(int C, const float* stats, float smooth, float eps, int log_loss, float* loss, float* coef,
                       void* stream) {
   if (C <= 0 || C > 64 || !stats || !loss || !coef) return set_error(TOK_ERR_INVALID, "dice_finalize: 1 <= C <= 64");
-  dice_finalize_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(stats, C, smooth, eps, log_loss, loss, coef);
+  (void)launch_pdl(dice_finalize_kernel, dim3(1), dim3(64), 0, (cudaStream_t)stream, stats, C, smooth, eps, log_loss, loss, coef);
   TOK_CHECK_LAUNCH("dice_finalize");
   return TOK_OK;
 }
@@ -554,7 +572,7 @@ int tok_dice_finalize(int C, const float* stats, float smooth, float eps, int lo
 int tok_dice_bwd(long long rows, int C, int ld, const void* logits, const long long* target, const float* coef,
                  const float* gscale_dev, void* dlogits, void* stream) {
   if (rows <= 0 || C <= 0 || C > 64 || ld < C || !coef || !dlogits) return set_error(TOK_ERR_INVALID, "dice_bwd: 1 <= C <= 64, ld >= C");
-  dice_bwd_kernel<<<grid_for(rows), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, target, coef, gscale_dev,
+  (void)launch_pdl(dice_bwd_kernel, dim3(grid_for(rows)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)logits, target, coef, gscale_dev,
                                                                   (__nv_bfloat16*)dlogits, rows, C, ld);
   TOK_CHECK_LAUNCH("dice_bwd");
   return TOK_OK;

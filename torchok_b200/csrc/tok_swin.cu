@@ -41,6 +41,8 @@ layernorm_fwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ res,
                      const float* __restrict__ rowscale, int rows_per_sample, __nv_bfloat16* __restrict__ out,
                      float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -86,6 +88,8 @@ layernorm_bwd_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
                      const __nv_bfloat16* __restrict__ dout, const float* __restrict__ rowscale, int rows_per_sample,
                      __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      int rows_per_cta) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ float sh[];  // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
@@ -162,6 +166,8 @@ layernorm_fwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
                          const float* __restrict__ beta, float eps, const __nv_bfloat16* __restrict__ res,
                          const float* __restrict__ rowscale, int rows_per_sample, __nv_bfloat16* __restrict__ out,
                          float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   constexpr int C = 8 * CH * G;
   constexpr int RPW = 32 / G;  // rows per warp pass
   const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
@@ -226,6 +232,8 @@ layernorm_bwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
                          const __nv_bfloat16* __restrict__ dout, const float* __restrict__ rowscale, int rows_per_sample,
                          __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          float* __restrict__ dxsum) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   constexpr int C = 8 * CH * G;
   constexpr int RPW = 32 / G;
   extern __shared__ float sh[];  // [3][C]
@@ -355,6 +363,8 @@ __device__ __forceinline__ float gelu_grad(float v) {
   return fmaf(v * 0.39894228f, ex, cdf);
 }
 __global__ void gelu_fwd_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloat162* __restrict__ y, long long n2) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const float2 v = __bfloat1622float2(x[i]);
     y[i] = __floats2bfloat162_rn(gelu_value(v.x), gelu_value(v.y));
@@ -362,6 +372,8 @@ __global__ void gelu_fwd_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloa
 }
 __global__ void gelu_bwd_kernel(const __nv_bfloat162* __restrict__ x, const __nv_bfloat162* __restrict__ dy,
                                 __nv_bfloat162* __restrict__ dx, long long n2) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const float2 v = __bfloat1622float2(x[i]);
     const float2 g = __bfloat1622float2(dy[i]);
@@ -371,6 +383,8 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat162* __restrict__ x, const __nv
 // 16-byte version (n % 8 == 0)
 __global__ void __launch_bounds__(256)
 gelu_fwd_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long n8) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   for (; i + 3 * stride < n8; i += 4 * stride) {   // four independent 16-byte loads in flight per thread
@@ -400,6 +414,8 @@ gelu_fwd_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long lon
 __global__ void __launch_bounds__(256)
 gelu_bwd_vec_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                     __nv_bfloat16* __restrict__ dx, float* __restrict__ dbias) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float sh[16][129];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int c0 = blockIdx.x * 128 + tx * 8;
@@ -479,6 +495,8 @@ __device__ __forceinline__ void pe_load_patches(const float* __restrict__ img, i
 __global__ void __launch_bounds__(512)
 patch_embed_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                        int B, int H, int W, int E, int sO, int sC, int sH, int sW, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ __align__(16) float sp[];
   const int TH = H / 4, TW = W / 4;
   const int o = threadIdx.x % E, half = threadIdx.x / E;
@@ -514,6 +532,8 @@ patch_embed_fwd_kernel(const float* __restrict__ img, const float* __restrict__ 
 __global__ void __launch_bounds__(512)
 patch_embed_bwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dy, int B, int H, int W, int E,
                        int sO, int sC, int sH, int sW, float* __restrict__ dw, float* __restrict__ dbias) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ __align__(16) float sp[];
   const int TH = H / 4, TW = W / 4;
   __nv_bfloat16* sg = reinterpret_cast<__nv_bfloat16*>(sp + TW * kPePitch);   // [TW][E]
@@ -569,6 +589,8 @@ patch_embed_bwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __res
 // 8 zero-fills + 8 strided copies + 3 accumulations for it).
 __global__ void __launch_bounds__(256)
 patch_merge_kernel(int B, int H, int W, int C8, const uint4* __restrict__ src, uint4* __restrict__ dst, int inverse) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int H2 = H / 2, W2 = W / 2;
   const long long total = (long long)B * H2 * W2 * 4 * C8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -639,6 +661,8 @@ __device__ __forceinline__ long long token_row(const AttnGeom& g, int b, int wy,
 __global__ void __launch_bounds__(64)
 window_attn_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ logit_scale,
                        const float* __restrict__ bias /* [heads][N][N] */, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ __align__(16) float sk[kMaxN][kPitch], sv[kMaxN][kPitch];
   __shared__ int sreg[kMaxN];
   const int N = g.ws * g.ws;
@@ -753,6 +777,8 @@ __device__ __forceinline__ float normalize32(float (&v)[kHd]) {   // v <- v / ma
 __global__ void __launch_bounds__(kBigThreads)
 window_attn_big_fwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ logit_scale,
                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ __align__(16) float dyn[];
   const int N = g.ws * g.ws;
   float (*sk)[kPitch] = reinterpret_cast<float (*)[kPitch]>(dyn);
@@ -816,6 +842,8 @@ window_attn_big_bwd_kernel(AttnGeom g, const __nv_bfloat16* __restrict__ qkv, co
                            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ dout,
                            __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
                            float* __restrict__ dlogit_scale) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ __align__(16) float dyn[];
   const int N = g.ws * g.ws;
   float (*sa)[kPitch] = reinterpret_cast<float (*)[kPitch]>(dyn);   // sweep 1-2: K-hat     sweep 3: Q-hat
@@ -976,6 +1004,8 @@ __global__ void __launch_bounds__(kTcThreads)
 window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
                           const float* __restrict__ logit_scale, const float* __restrict__ bias,
                           __nv_bfloat16* __restrict__ out) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                 // [128][128 B]  K-major A of S
@@ -1202,6 +1232,8 @@ __global__ void __launch_bounds__(kTc2Threads, 2)
 window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
                            const float* __restrict__ logit_scale, const float* __restrict__ bias,
                            __nv_bfloat16* __restrict__ out) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t aQ = smem_u32(smem), aK = aQ + 16384, aV = aK + 16384, aP = aV + 16384;
@@ -1428,6 +1460,8 @@ window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__
                        const float* __restrict__ logit_scale, const float* __restrict__ bias,
                        const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
                        float* __restrict__ dbias, float* __restrict__ dlogit_scale) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ __align__(16) float dyn[];
   float (*sq)[kPitch] = reinterpret_cast<float (*)[kPitch]>(dyn);
   float (*sk)[kPitch] = sq + kMaxN;
@@ -1611,6 +1645,8 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
                           const float* __restrict__ logit_scale, const float* __restrict__ bias,
                           const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
                           float* __restrict__ dbias, float* __restrict__ dlogit_scale, float* __restrict__ dcolsum) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t aQ = smem_u32(smem), aK = aQ + 16384, aV = aK + 16384, aDO = aV + 16384;
@@ -1951,6 +1987,8 @@ constexpr int kCpbHidden = 512;
 __global__ void __launch_bounds__(128)
 cpb_table_kernel(const float* __restrict__ coords, const float* __restrict__ w1, const float* __restrict__ b1,
                  const float* __restrict__ w2, float* __restrict__ hidden, float* __restrict__ table, int heads) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float sh[kCpbHidden];
   __shared__ float red[4];
   const int e = blockIdx.x;
@@ -1980,6 +2018,8 @@ __device__ __forceinline__ int cpb_entry(int i, int j, int ws) {
 // bias[h][i][j] = 16 * sigmoid(table[e(i, j)][h])
 __global__ void __launch_bounds__(256)
 cpb_gather_kernel(const float* __restrict__ table, float* __restrict__ bias, int heads, int ws) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   const int N = ws * ws;
   const long long total = (long long)heads * N * N;
   for (long long o = blockIdx.x * 256LL + threadIdx.x; o < total; o += gridDim.x * 256LL) {
@@ -1995,6 +2035,8 @@ cpb_gather_kernel(const float* __restrict__ table, float* __restrict__ bias, int
 __global__ void __launch_bounds__(128)
 cpb_scatter_kernel(const float* __restrict__ dbias, const float* __restrict__ table, float* __restrict__ dtable,
                    int heads, int ws) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float red[4];
   const int N = ws * ws;
   const int e = blockIdx.x;
@@ -2027,6 +2069,8 @@ __global__ void __launch_bounds__(128)
 cpb_mlp_bwd_kernel(const float* __restrict__ dtable, const float* __restrict__ hidden, const float* __restrict__ coords,
                    const float* __restrict__ w2, float* __restrict__ dw1, float* __restrict__ db1,
                    float* __restrict__ dw2, int T, int heads) {
+  pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
+  pdl_launch();
   __shared__ float red[4][4];
   const int k = blockIdx.x;
   float a0 = 0.f, a1 = 0.f, ab = 0.f;
@@ -2079,8 +2123,8 @@ int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, 
     const long long rows_per_cta = 8LL * (32 / G);
     const long long want = (rows + rows_per_cta - 1) / rows_per_cta;
 #define TOK_LN_FWD_V(GG, CC)                                                                                      \
-  layernorm_fwd_vec_kernel<GG, CC><<<(unsigned)(want < ln_fwd_ctas<GG, CC>() ? want : ln_fwd_ctas<GG, CC>()), 256, 0,    \
-                                     (cudaStream_t)stream>>>(                                                      \
+  (void)launch_pdl(layernorm_fwd_vec_kernel<GG, CC>, dim3((unsigned)(want < ln_fwd_ctas<GG, CC>() ? want : ln_fwd_ctas<GG, CC>())), dim3(256), 0, \
+                                     (cudaStream_t)stream,                                                       \
       rows, (const __nv_bfloat16*)x, gamma, beta, eps, (const __nv_bfloat16*)residual, rowscale,                   \
       rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)out, mean, rstd)
 #define TOK_LN_FWD_G(CC)                                                                                          \
@@ -2102,7 +2146,7 @@ int tok_layernorm_fwd(long long rows, int C, const void* x, const float* gamma, 
   const long long threads = rows * 32;
   const unsigned grid = (unsigned)((threads + 127) / 128);
 #define TOK_LN_FWD(P)                                                                                              \
-  layernorm_fwd_kernel<P><<<grid, 128, 0, (cudaStream_t)stream>>>(                                                  \
+  (void)launch_pdl(layernorm_fwd_kernel<P>, dim3(grid), dim3(128), 0, (cudaStream_t)stream,                                                   \
       rows, C, (const __nv_bfloat16*)x, gamma, beta, eps, (const __nv_bfloat16*)residual, rowscale,                \
       rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)out, mean, rstd)
   if (C <= 128) TOK_LN_FWD(4);
@@ -2128,8 +2172,8 @@ int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, 
     const long long rows_per_pass = 4LL * (32 / G);
     const long long want = (rows + rows_per_pass - 1) / rows_per_pass;
 #define TOK_LN_BWD_V(GG, CC)                                                                                      \
-  layernorm_bwd_vec_kernel<GG, CC><<<(unsigned)(want < ln_bwd_ctas<GG, CC>() ? want : ln_bwd_ctas<GG, CC>()), 128,       \
-                                     3 * C * sizeof(float), (cudaStream_t)stream>>>(                               \
+  (void)launch_pdl(layernorm_bwd_vec_kernel<GG, CC>, dim3((unsigned)(want < ln_bwd_ctas<GG, CC>() ? want : ln_bwd_ctas<GG, CC>())), dim3(128), \
+                                     3 * C * sizeof(float), (cudaStream_t)stream,                                \
       rows, (const __nv_bfloat16*)x, gamma, mean, rstd, (const __nv_bfloat16*)dout, rowscale,                      \
       rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum)
 #define TOK_LN_BWD_G(CC)                                                                                          \
@@ -2154,7 +2198,7 @@ int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, 
   if (rpc < 4) rpc = 4;
   ctas = (rows + rpc - 1) / rpc;
 #define TOK_LN_BWD(P)                                                                                              \
-  layernorm_bwd_kernel<P><<<(unsigned)ctas, 128, 2 * C * sizeof(float), (cudaStream_t)stream>>>(                    \
+  (void)launch_pdl(layernorm_bwd_kernel<P>, dim3((unsigned)ctas), dim3(128), 2 * C * sizeof(float), (cudaStream_t)stream,                     \
       rows, C, (const __nv_bfloat16*)x, gamma, mean, rstd, (const __nv_bfloat16*)dout, rowscale,                   \
       rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)dx, dgamma, dbeta, (int)rpc)
   if (C <= 128) TOK_LN_BWD(4);
@@ -2172,13 +2216,13 @@ int tok_gelu_fwd(long long n, const void* x, void* y, void* stream) {
     long long blocks = (n / 8 + 255) / 256;
     static const int wave = full_wave_ctas(gelu_fwd_vec_kernel, 256, 0);
     if (blocks > wave) blocks = wave;
-    gelu_fwd_vec_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, n / 8);
+    (void)launch_pdl(gelu_fwd_vec_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)y, n / 8);
     TOK_CHECK_LAUNCH("gelu_fwd_vec");
     return TOK_OK;
   }
   long long blocks = (n / 2 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gelu_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)x, (__nv_bfloat162*)y, n / 2);
+  (void)launch_pdl(gelu_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat162*)x, (__nv_bfloat162*)y, n / 2);
   TOK_CHECK_LAUNCH("gelu_fwd");
   return TOK_OK;
 }
@@ -2191,7 +2235,7 @@ int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, fl
     long long gy = wave / gx;   // never more CTAs than one resident wave
     if (gy < 1) gy = 1;
     if (gy > (rows + 15) / 16) gy = (rows + 15) / 16;
-    gelu_bwd_vec_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(
+    (void)launch_pdl(gelu_bwd_vec_kernel, dim3(dim3((unsigned)gx, (unsigned)gy)), dim3(256), 0, (cudaStream_t)stream, 
         rows, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, dbias);
     TOK_CHECK_LAUNCH("gelu_bwd_vec");
     return TOK_OK;
@@ -2199,7 +2243,7 @@ int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, fl
   if (dbias) return set_error(TOK_ERR_INVALID, "gelu_bwd: the fused bias gradient needs C %% 128 == 0 (C=%d)", C);
   long long blocks = (n / 2 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gelu_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162*)x, (const __nv_bfloat162*)dy,
+  (void)launch_pdl(gelu_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat162*)x, (const __nv_bfloat162*)dy,
                                                                      (__nv_bfloat162*)dx, n / 2);
   TOK_CHECK_LAUNCH("gelu_bwd");
   return TOK_OK;
@@ -2232,7 +2276,7 @@ int tok_patch_embed_fwd(int B, int H, int W, int E, const float* image, const fl
   }
   long long ctas = (long long)B * (H / 4);
   if (ctas > 148 * 3) ctas = 148 * 3;
-  patch_embed_fwd_kernel<<<(unsigned)ctas, 2 * E, smem, (cudaStream_t)stream>>>(
+  (void)launch_pdl(patch_embed_fwd_kernel, dim3((unsigned)ctas), dim3(2 * E), smem, (cudaStream_t)stream, 
       image, weight, bias, B, H, W, E, wstride[0], wstride[1], wstride[2], wstride[3], (__nv_bfloat16*)tokens);
   TOK_CHECK_LAUNCH("patch_embed_fwd");
   return TOK_OK;
@@ -2251,7 +2295,7 @@ int tok_patch_embed_bwd(int B, int H, int W, int E, const float* image, const vo
   }
   long long ctas = (long long)B * (H / 4);
   if (ctas > 148 * 3) ctas = 148 * 3;
-  patch_embed_bwd_kernel<<<(unsigned)ctas, 2 * E, smem, (cudaStream_t)stream>>>(
+  (void)launch_pdl(patch_embed_bwd_kernel, dim3((unsigned)ctas), dim3(2 * E), smem, (cudaStream_t)stream, 
       image, (const __nv_bfloat16*)dtokens, B, H, W, E, wstride[0], wstride[1], wstride[2], wstride[3], dweight, dbias);
   TOK_CHECK_LAUNCH("patch_embed_bwd");
   return TOK_OK;
@@ -2264,7 +2308,7 @@ int tok_patch_merge(int B, int H, int W, int C, const void* src, void* dst, int 
   long long blocks = (total + 255) / 256;
   static const int wave = full_wave_ctas(patch_merge_kernel, 256, 0);
   if (blocks > wave) blocks = wave;
-  patch_merge_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, H, W, C / 8, (const uint4*)src, (uint4*)dst, inverse);
+  (void)launch_pdl(patch_merge_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, B, H, W, C / 8, (const uint4*)src, (uint4*)dst, inverse);
   TOK_CHECK_LAUNCH("patch_merge");
   return TOK_OK;
 }
@@ -2294,7 +2338,7 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
       configured_big = kBigSmem;
     }
     const long long ctas = (long long)B * g.nwy * g.nwx * heads;
-    window_attn_big_fwd_kernel<<<(unsigned)ctas, kBigThreads, smem, (cudaStream_t)stream>>>(
+    (void)launch_pdl(window_attn_big_fwd_kernel, dim3((unsigned)ctas), dim3(kBigThreads), smem, (cudaStream_t)stream, 
         g, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out);
     TOK_CHECK_LAUNCH("window_attn_big_fwd");
     return TOK_OK;
@@ -2312,7 +2356,7 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
     int groups = (148 * 2) / heads;   // two CTAs per SM (shared memory, registers); one more CTA would be a second wave
     if (groups < 1) groups = 1;
     if (groups > pairs) groups = pairs;
-    window_attn_fwd_tc2_kernel<<<(unsigned)(groups * heads), kTc2Threads, kTc2Smem, (cudaStream_t)stream>>>(
+    (void)launch_pdl(window_attn_fwd_tc2_kernel, dim3((unsigned)(groups * heads)), dim3(kTc2Threads), kTc2Smem, (cudaStream_t)stream, 
         g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out);
     TOK_CHECK_LAUNCH("window_attn_fwd_tc2");
     return TOK_OK;
@@ -2328,13 +2372,13 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
     int groups = (148 * 2) / heads;   // two CTAs per SM (shared memory); one more CTA would be a second wave
     if (groups < 1) groups = 1;
     if (groups > pairs) groups = pairs;
-    window_attn_fwd_tc_kernel<<<(unsigned)(groups * heads), kTcThreads, kTcSmem, (cudaStream_t)stream>>>(
+    (void)launch_pdl(window_attn_fwd_tc_kernel, dim3((unsigned)(groups * heads)), dim3(kTcThreads), kTcSmem, (cudaStream_t)stream, 
         g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out);
     TOK_CHECK_LAUNCH("window_attn_fwd_tc");
     return TOK_OK;
   }
   const long long ctas = (long long)B * g.nwy * g.nwx * heads;
-  window_attn_fwd_kernel<<<(unsigned)ctas, 64, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)qkv, logit_scale, bias,
+  (void)launch_pdl(window_attn_fwd_kernel, dim3((unsigned)ctas), dim3(64), 0, (cudaStream_t)stream, g, (const __nv_bfloat16*)qkv, logit_scale, bias,
                                                                          (__nv_bfloat16*)out);
   TOK_CHECK_LAUNCH("window_attn_fwd");
   return TOK_OK;
@@ -2358,7 +2402,7 @@ int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift
       if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_bwd(big): %s", cudaGetErrorString(e));
       configured_big = true;
     }
-    window_attn_big_bwd_kernel<<<(unsigned)((long long)windows * heads), kBigThreads, smem, (cudaStream_t)stream>>>(
+    (void)launch_pdl(window_attn_big_bwd_kernel, dim3((unsigned)((long long)windows * heads)), dim3(kBigThreads), smem, (cudaStream_t)stream, 
         g, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
         dlogit_scale);
     TOK_CHECK_LAUNCH("window_attn_big_bwd");
@@ -2376,7 +2420,7 @@ int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift
     int groups = 148 / heads;   // one CTA per SM (shared memory), never a second wave
     if (groups < 1) groups = 1;
     if (groups > pairs) groups = pairs;
-    window_attn_bwd_tc_kernel<<<(unsigned)(groups * heads), kBwThreads, kBwSmem, (cudaStream_t)stream>>>(
+    (void)launch_pdl(window_attn_bwd_tc_kernel, dim3((unsigned)(groups * heads)), dim3(kBwThreads), kBwSmem, (cudaStream_t)stream, 
         g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
         dlogit_scale, dqkv_colsum);
     TOK_CHECK_LAUNCH("window_attn_bwd_tc");
@@ -2391,7 +2435,7 @@ int tok_window_attn_bwd(int B, int H, int W, int C, int heads, int ws, int shift
     if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_bwd: %s", cudaGetErrorString(e));
     configured = true;
   }
-  window_attn_bwd_kernel<<<(unsigned)(groups * heads), 64, kAttnBwdSmem, (cudaStream_t)stream>>>(
+  (void)launch_pdl(window_attn_bwd_kernel, dim3((unsigned)(groups * heads)), dim3(64), kAttnBwdSmem, (cudaStream_t)stream, 
       g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, dbias,
       dlogit_scale);
   TOK_CHECK_LAUNCH("window_attn_bwd");
@@ -2404,11 +2448,11 @@ int tok_cpb_bias_fwd(int ws, int heads, int hidden_dim, const float* coords, con
     return set_error(TOK_ERR_INVALID, "cpb_bias: the cpb MLP of timm's WindowAttention has 512 hidden units");
   const int T = (2 * ws - 1) * (2 * ws - 1);
   cudaStream_t st = (cudaStream_t)stream;
-  cpb_table_kernel<<<T, 128, 0, st>>>(coords, w1, b1, w2, hidden, table, heads);
+  (void)launch_pdl(cpb_table_kernel, dim3(T), dim3(128), 0, st, coords, w1, b1, w2, hidden, table, heads);
   const long long total = (long long)heads * ws * ws * ws * ws;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  cpb_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(table, bias, heads, ws);
+  (void)launch_pdl(cpb_gather_kernel, dim3((unsigned)blocks), dim3(256), 0, st, table, bias, heads, ws);
   TOK_CHECK_LAUNCH("cpb_bias_fwd");
   return TOK_OK;
 }
@@ -2420,8 +2464,8 @@ int tok_cpb_bias_bwd(int ws, int heads, int hidden_dim, const float* coords, con
     return set_error(TOK_ERR_INVALID, "cpb_bias: the cpb MLP of timm's WindowAttention has 512 hidden units");
   const int T = (2 * ws - 1) * (2 * ws - 1);
   cudaStream_t st = (cudaStream_t)stream;
-  cpb_scatter_kernel<<<T, 128, 0, st>>>(dbias, table, dtable, heads, ws);
-  cpb_mlp_bwd_kernel<<<kCpbHidden, 128, 0, st>>>(dtable, hidden, coords, w2, dw1, db1, dw2, T, heads);
+  (void)launch_pdl(cpb_scatter_kernel, dim3(T), dim3(128), 0, st, dbias, table, dtable, heads, ws);
+  (void)launch_pdl(cpb_mlp_bwd_kernel, dim3(kCpbHidden), dim3(128), 0, st, dtable, hidden, coords, w2, dw1, db1, dw2, T, heads);
   TOK_CHECK_LAUNCH("cpb_bias_bwd");
   return TOK_OK;
 }
