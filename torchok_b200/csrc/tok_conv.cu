@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
                         const ConvFwdParams p) {
-  static_assert(CBUFS == 1 || CBUFS == 2, "staging buffers");
+  static_assert(CBUFS >= 1 && CBUFS <= 3, "staging buffers");
   static_assert(ABUFS == 0 || ABUFS == 2, "addend buffers");
   constexpr int kBTile = BN * kBlockK * 2;
   constexpr int kStage = kATile + (BRES > 0 ? 0 : kBTile);
@@ -529,7 +529,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
       }
     };
-    const bool kDefer = CBUFS == 2 && p.defer_stats != 0;
+    const bool kDefer = CBUFS >= 2 && p.defer_stats != 0;
     bool pend = false;
     uint32_t pend_cb = 0;
     int pend_rows = 0, pend_n0 = -1;
@@ -548,14 +548,15 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int buf = li & 1;
       const int m = m0 + row;
       const bool row_ok = m < p.M;
-      uint8_t* cbuf = smem_c + (CBUFS == 2 ? (li & 1) * kCTile : 0);
+      uint8_t* cbuf = smem_c + (CBUFS >= 2 ? (li % CBUFS) * kCTile : 0);
       // (A) single staging buffer: every epilogue thread must have finished reading it (statistics pass of the
       //     previous tile).  With two buffers the readers of this buffer (two tiles ago) are behind barrier (B) of
       //     the previous tile already.
       if (CBUFS == 1) epi_bar();
       if (leader) {
         // the TMA store that last read this staging buffer must have drained it
-        if (CBUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (CBUFS == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+        else if (CBUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         else tma_store_wait_read();
         if (ABUFS == 0 && has_addend) {
           uint32_t bytes = 0;
@@ -1009,6 +1010,15 @@ cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& t
     if (bres128 && reuse && slab <= 65536)
       return b_mn ? launch_persist_t<128, 5, true, 2, 0, 65536>(tmA, tmB, tmC, tmD, p, st)
                   : launch_persist_t<128, 5, false, 2, 0, 65536>(tmA, tmB, tmC, tmD, p, st);
+    // r3 experiment (opt-in, TOK_CONV_CBUFS3=1): three staging tiles and a 3-stage ring (192 KB either way).  The short-
+    // reduction layers wait ~570 clk per tile for the store two tiles back to release its staging buffer (phase profile,
+    // profiles/r2_logs) — but a third buffer does not help (64->256 @56: 134 vs 133 us) and the shallower ring costs
+    // the 4-k-block layers (256->1024 @14: 52 vs 44 us): that wait is HBM write back-pressure, not a missing buffer.
+    static const bool cb3 = getenv("TOK_CONV_CBUFS3") && atoi(getenv("TOK_CONV_CBUFS3")) == 1;
+    const long long kblocks = (long long)p.a.R * p.a.S * ((p.Cin + kBlockK - 1) / kBlockK);
+    if (cb3 && kblocks <= 4)
+      return b_mn ? launch_persist_t<128, 3, true, 3, 0>(tmA, tmB, tmC, tmD, p, st)
+                  : launch_persist_t<128, 3, false, 3, 0>(tmA, tmB, tmC, tmD, p, st);
     return b_mn ? launch_persist_t<128, 4, true, 2, 0>(tmA, tmB, tmC, tmD, p, st)
                 : launch_persist_t<128, 4, false, 2, 0>(tmA, tmB, tmC, tmD, p, st);
   }
