@@ -81,6 +81,15 @@ size_t tok_conv_dgrad_workspace_bytes(const tokConvDesc* d);
 int tok_conv_dgrad(const tokConvDesc* d, const void* dy, const void* w, void* dx, const void* addend, void* ws,
                    void* stream);
 
+/* tok_conv_dgrad whose addend is masked on the fly: dx = dgrad(dy) + addend * [bit set], addend_bits = the 1-bit-per-
+ * element ReLU mask tok_bn_apply_bits wrote for the block output ([pixels][c / 8], 8 channels per byte).  The gradient that
+ * enters a residual block's input through the identity shortcut is dout * [block output > 0] (timm BasicBlock /
+ * Bottleneck `x += shortcut; x = act(x)`, built by torchok/models/backbones/resnet.py:363-405): with this form the
+ * BatchNorm backward of the block tail does not write that product (8 -> 6 bytes per element on 75 % of a ResNet's
+ * BatchNorm-backward traffic).  Stride 1 only; see tok_conv_dgrad_masked_supported. */
+int tok_conv_dgrad_masked_supported(const tokConvDesc* d);
+int tok_conv_dgrad_masked(const tokConvDesc* d, const void* dy, const void* w, void* dx, const void* addend,
+                          const void* addend_bits, void* ws, void* stream);
 /* dw[k,r,s,c] += sum_pixels dy[n,p,q,k] * x[n, ..., c]   (fp32, atomically accumulated; caller zero-fills). */
 int tok_conv_wgrad(const tokConvDesc* d, const void* x, const void* dy, float* dw, void* stream);
 

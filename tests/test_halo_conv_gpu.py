@@ -130,3 +130,30 @@ def test_halo_equals_generic_kernel_bit_for_bit():
         del os.environ['TOK_CONV_HALO']
     assert torch.equal(y, y0)
     assert torch.equal(dx, dx0)
+
+
+@pytest.mark.parametrize('n,c,h,w_,k,r', [(4, 64, 24, 24, 64, 3), (2, 24, 17, 31, 40, 3), (8, 256, 14, 14, 64, 1),
+                                           (4, 1024, 7, 7, 256, 1), (4, 256, 14, 14, 256, 3)])
+def test_dgrad_masked_addend_equals_explicit_product(n, c, h, w_, k, r):
+    """tok_conv_dgrad_masked (dx = dgrad(dy) + addend * [bit]) against tok_conv_dgrad fed the materialised product — the
+    residual-gradient path of a block (timm `x += shortcut; x = act(x)`, resnet.py:363-405) on the halo kernel and on the
+    generic kernel (1x1, 3x3 with Cin > 128).  Same fp32 sums, same single rounding: bit-identical."""
+    import ctypes as C
+    from torchok_b200 import kernels as K
+    from torchok_b200._lib import lib
+    dev = torch.device('cuda')
+    torch.manual_seed(n * 100 + c)
+    pad = r // 2
+    d, p, q = K.conv_desc(n, h, w_, c, k, r, r, 1, pad, 1)
+    assert lib().tok_conv_dgrad_masked_supported(C.byref(d)) == 1
+    wk = (torch.randn(k, r, r, c, device=dev) / (c * r * r) ** 0.5).to(torch.bfloat16)
+    dy = torch.randn(n, h, w_, k, device=dev).to(torch.bfloat16)
+    add = torch.randn(n, h, w_, c, device=dev).to(torch.bfloat16)
+    bits = torch.randint(0, 256, (n * h * w_ * c // 8,), dtype=torch.uint8, device=dev)
+    mask = torch.stack([(bits >> j) & 1 for j in range(8)], dim=-1).reshape(n, h, w_, c).to(torch.bfloat16)
+    ref = torch.empty(n, h, w_, c, device=dev, dtype=torch.bfloat16)
+    K.conv_dgrad(d, dy, wk, ref, (add * mask).contiguous())
+    got = torch.full_like(ref, float('nan'))
+    K.conv_dgrad(d, dy, wk, got, add, bits)
+    torch.cuda.synchronize()
+    assert torch.equal(ref, got)

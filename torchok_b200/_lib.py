@@ -51,6 +51,8 @@ _SIGS = {
     'tok_conv_fprop_bn': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_conv_dgrad_workspace_bytes': (_sz, [_pd]),
     'tok_conv_dgrad': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tok_conv_dgrad_masked_supported': (_i, [_pd]),
+    'tok_conv_dgrad_masked': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_conv_wgrad': (_i, [_pd, _vp, _vp, _vp, _vp]),
     'tok_linear_fwd': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'tok_linear_dgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -152,7 +154,7 @@ _SIGS = {
     'tok_pad_weight': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_unpad_wgrad_add': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
-_RAW = {'tok_conv_halo_caps', 'tok_bn_apply_train_supported', 'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+_RAW = {'tok_conv_halo_caps', 'tok_conv_dgrad_masked_supported', 'tok_bn_apply_train_supported', 'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}
 
 

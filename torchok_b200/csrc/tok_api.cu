@@ -24,8 +24,8 @@ cudaError_t launch_conv_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, c
 // tok_conv3.cu: halo formulation of the 3x3 / stride 1 / pad 1 convolution for Cin <= 128
 bool conv3x3_halo_eligible(int n_img, int H, int W, int Cin, int N);
 int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, const void* w, int wK, int wC,
-                        int transposed, void* out, const void* addend, float* col_sum, float* col_sqsum,
-                        cudaStream_t st);
+                        int transposed, void* out, const void* addend, const void* addend_bits, float* col_sum,
+                        float* col_sqsum, cudaStream_t st);
 bool conv3x3_wgrad_halo_eligible(int n_img, int H, int W, int Cin, int Cout);
 int launch_conv3x3_wgrad_halo(const void* x, const void* dy, int n_img, int H, int W, int Cin, int Cout, int wK, int wC,
                               float* dw, cudaStream_t st);
@@ -396,7 +396,7 @@ static int conv_fprop_impl(const tokConvDesc* d, const void* x, const void* w, v
   p.relu = relu;
   const long long M = (long long)d->n * P * Q;
   if (desc_halo_shape(d) && !addend && !bias && !relu && !fin && conv3x3_halo_eligible(d->n, d->h, d->w, d->c, d->k))
-    return launch_conv3x3_halo(x, d->n, d->h, d->w, d->c, d->k, w, desc_wk(d), desc_wc(d), 0, y, nullptr, sum, sqsum,
+    return launch_conv3x3_halo(x, d->n, d->h, d->w, d->c, d->k, w, desc_wk(d), desc_wc(d), 0, y, nullptr, nullptr, sum, sqsum,
                                static_cast<cudaStream_t>(stream));
   if (desc_unpadded(d)) return set_error(TOK_ERR_INVALID, "conv_fprop: unpadded weights (wk / wc) need the halo 3x3 path");
   if (fin) {
@@ -485,8 +485,35 @@ size_t tok_conv_dgrad_workspace_bytes(const tokConvDesc* d) {
   return 0;
 }
 
+// The masked addend needs 32-channel words of the bit mask per (row, 32-column chunk): N % 32 == 0 on the generic kernel,
+// any multiple of 8 on the halo kernel; the scatter forms (strided 1x1 / parity classes) have no addend path for it.
+int tok_conv_dgrad_masked_supported(const tokConvDesc* d) {
+  if (!d || check_desc(d) != TOK_OK || d->stride != 1 || getenv("TOK_CONV_V1")) return 0;
+  if (desc_halo_shape(d) && conv3x3_halo_eligible(d->n, d->h, d->w, d->k, d->c)) return 1;
+  if (desc_unpadded(d)) return 0;
+  if (d->r == 1 && d->s == 1) return d->pad == 0 && (d->c % 32) == 0;
+  return (d->c % 32) == 0 && ((d->r - 1) * d->dil - d->pad) == ((d->s - 1) * d->dil - d->pad) &&
+         ((d->r - 1) * d->dil - d->pad) >= 0;
+}
+
+static int conv_dgrad_impl(const tokConvDesc* d, const void* dy, const void* w, void* dx, const void* addend,
+                           const void* addend_bits, void* ws, void* stream);
+
 int tok_conv_dgrad(const tokConvDesc* d, const void* dy, const void* w, void* dx, const void* addend, void* ws,
                    void* stream) {
+  return conv_dgrad_impl(d, dy, w, dx, addend, nullptr, ws, stream);
+}
+
+int tok_conv_dgrad_masked(const tokConvDesc* d, const void* dy, const void* w, void* dx, const void* addend,
+                          const void* addend_bits, void* ws, void* stream) {
+  if (!addend || !addend_bits) return set_error(TOK_ERR_INVALID, "conv_dgrad_masked: addend and its bit mask are required");
+  if (!tok_conv_dgrad_masked_supported(d))
+    return set_error(TOK_ERR_INVALID, "conv_dgrad_masked: unsupported convolution (see tok_conv_dgrad_masked_supported)");
+  return conv_dgrad_impl(d, dy, w, dx, addend, addend_bits, ws, stream);
+}
+
+static int conv_dgrad_impl(const tokConvDesc* d, const void* dy, const void* w, void* dx, const void* addend,
+                           const void* addend_bits, void* ws, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   int P, Q;
@@ -497,6 +524,7 @@ int tok_conv_dgrad(const tokConvDesc* d, const void* dy, const void* w, void* dx
   p.out = static_cast<__nv_bfloat16*>(dx);
   p.ldo = d->c;
   p.addend = static_cast<const __nv_bfloat16*>(addend);
+  p.addend_bits = static_cast<const uint8_t*>(addend_bits);
   const long long wcols = (long long)d->r * d->s * d->c;
   if (d->r == 1 && d->s == 1) {
     if (d->pad != 0) return set_error(TOK_ERR_INVALID, "1x1 conv with padding is not supported");
@@ -523,8 +551,8 @@ int tok_conv_dgrad(const tokConvDesc* d, const void* dy, const void* w, void* dx
     return run_fwd(dy, d->n, P, Q, d->k, src, (long long)d->n * P * Q, w, d->k, wcols, true, d->c, 0, p, st);
   }
   if (desc_halo_shape(d) && conv3x3_halo_eligible(d->n, d->h, d->w, d->k, d->c))
-    return launch_conv3x3_halo(dy, d->n, d->h, d->w, d->k, d->c, w, desc_wk(d), desc_wc(d), 1, dx, addend, nullptr, nullptr,
-                               st);
+    return launch_conv3x3_halo(dy, d->n, d->h, d->w, d->k, d->c, w, desc_wk(d), desc_wc(d), 1, dx, addend, addend_bits,
+                               nullptr, nullptr, st);
   if (desc_unpadded(d)) return set_error(TOK_ERR_INVALID, "conv_dgrad: unpadded weights (wk / wc) need the halo 3x3 path");
   // RxS filter: stride-1 correlation of (zero-dilated) dy with the flipped filter.
   const int pad_h = (d->r - 1) * d->dil - d->pad;

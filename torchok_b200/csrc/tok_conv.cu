@@ -607,6 +607,17 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       for (int cc = 0; cc < kInFlight; ++cc)
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + ((c0 + cc) * 2 + half) * 32,
                            r[cc]);
+      uint32_t mbits[kInFlight];
+#pragma unroll
+      for (int cc = 0; cc < kInFlight; ++cc) {
+        mbits[cc] = 0xffffffffu;
+        if (has_addend && p.addend_bits != nullptr && row_ok) {
+          const int col0 = n0 + ((c0 + cc) * 2 + half) * 32;
+          if (col0 < p.N)
+            mbits[cc] = __ldg(reinterpret_cast<const unsigned int*>(p.addend_bits + static_cast<long long>(m) * (p.ldo >> 3) +
+                                                                    (col0 >> 3)));
+        }
+      }
       if (kDefer && c0 == 0 && pend) {   // the previous tile's statistics, while this tile's first TMEM loads travel
         stats_pass(pend_cb, pend_rows);
         pend = false;
@@ -653,10 +664,11 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const int chunk = ((c & 1) * 4 + g) ^ (row & 7);
             const uint4 a = lds128(abuf_s + blk_off + chunk * 16);
             const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+            const uint32_t mb = mbits[cc] >> (g * 8);   // byte g of the word: channels g*8 .. g*8+7 of this chunk
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              v[g * 8 + 2 * e] += bf16_lo(aw[e]);
-              v[g * 8 + 2 * e + 1] += bf16_hi(aw[e]);
+              v[g * 8 + 2 * e] += (mb >> (2 * e)) & 1u ? bf16_lo(aw[e]) : 0.f;
+              v[g * 8 + 2 * e + 1] += (mb >> (2 * e + 1)) & 1u ? bf16_hi(aw[e]) : 0.f;
             }
           }
         }

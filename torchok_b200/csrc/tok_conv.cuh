@@ -70,6 +70,10 @@ struct ConvFwdParams {
   __nv_bfloat16* out;
   long long ldo;              // elements between consecutive output rows
   const __nv_bfloat16* addend;  // optional, read at the same (row, col) as out before the store
+  // optional ReLU bit mask of the addend (1 bit per element, 8 channels per byte in vector order, [rows][ldo / 8]): the
+  // gradient that reaches a residual block's input through the identity shortcut is dout * [block output > 0]; reading
+  // dout + the forward's bits here means the BatchNorm backward of the block tail need not materialise that product
+  const uint8_t* addend_bits;
   float* col_sum;             // optional per-column sum of the *stored* (bf16-rounded) values
   float* col_sqsum;           // optional per-column sum of squares
   const float* bias;          // optional per-column bias added before rounding

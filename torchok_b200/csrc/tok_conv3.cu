@@ -59,6 +59,7 @@ struct HaloParams {
   const __nv_bfloat16* w;
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
+  const uint8_t* addend_bits;   // optional ReLU mask of the addend: 1 bit per element, [pixels][N / 8] (tok_conv.cuh)
   float* col_sum;
   float* col_sqsum;
 };
@@ -355,6 +356,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const HaloParams p)
         // latency hides behind them (loaded inside the copy-out loop it doubled the kernel: 59 vs 29 us, HRNet 18->18).
         int item_off[4];
         uint4 item_add[4];
+        uint32_t item_msk[4];
         {
           const int pos0 = mt * 128 + crow;
           int prow = static_cast<int>((static_cast<float>(pos0) + 0.5f) * inv_wp);   // exact: pos0 < 2^15, Wp <= 256
@@ -365,7 +367,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const HaloParams p)
             item_off[i4] = -1;
             if (cact && rr < 128 && pcol < p.W && prow < rows_valid) {
               item_off[i4] = (prow * p.W + pcol) * p.N;   // inside one image: < 2^31
-              if (ADDEND) item_add[i4] = __ldg(reinterpret_cast<const uint4*>(add_t + item_off[i4]));
+              if (ADDEND) {
+                item_add[i4] = __ldg(reinterpret_cast<const uint4*>(add_t + item_off[i4]));
+                item_msk[i4] = 0xffu;
+                if (p.addend_bits != nullptr)
+                  item_msk[i4] = __ldg(p.addend_bits + ((tile_off + item_off[i4]) >> 3));
+              }
             }
             pcol += step_col;
             prow += step_row;
@@ -406,10 +413,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const HaloParams p)
           uint4 v = lds128(cbuf_s + rr * srb + chunk * 16);
           if (ADDEND) {
             const uint4 a = item_add[i4];
-            v.x = pack_bf16x2(bf16_lo(v.x) + bf16_lo(a.x), bf16_hi(v.x) + bf16_hi(a.x));
-            v.y = pack_bf16x2(bf16_lo(v.y) + bf16_lo(a.y), bf16_hi(v.y) + bf16_hi(a.y));
-            v.z = pack_bf16x2(bf16_lo(v.z) + bf16_lo(a.z), bf16_hi(v.z) + bf16_hi(a.z));
-            v.w = pack_bf16x2(bf16_lo(v.w) + bf16_lo(a.w), bf16_hi(v.w) + bf16_hi(a.w));
+            const uint32_t mk = item_msk[i4];
+            v.x = pack_bf16x2(bf16_lo(v.x) + (mk & 1u ? bf16_lo(a.x) : 0.f), bf16_hi(v.x) + (mk & 2u ? bf16_hi(a.x) : 0.f));
+            v.y = pack_bf16x2(bf16_lo(v.y) + (mk & 4u ? bf16_lo(a.y) : 0.f), bf16_hi(v.y) + (mk & 8u ? bf16_hi(a.y) : 0.f));
+            v.z = pack_bf16x2(bf16_lo(v.z) + (mk & 16u ? bf16_lo(a.z) : 0.f), bf16_hi(v.z) + (mk & 32u ? bf16_hi(a.z) : 0.f));
+            v.w = pack_bf16x2(bf16_lo(v.w) + (mk & 64u ? bf16_lo(a.w) : 0.f), bf16_hi(v.w) + (mk & 128u ? bf16_hi(a.w) : 0.f));
           }
           *reinterpret_cast<uint4*>(out_t + item_off[i4]) = v;
           if (STATS) {
@@ -715,8 +723,8 @@ bool conv3x3_halo_eligible(int n_img, int H, int W, int Cin, int N) {
 
 // x: [n_img][H][W][Cin] bf16; w: [wK][3][3][wC] bf16; out / addend: [n_img][H][W][N] bf16.
 int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, const void* w, int wK, int wC,
-                        int transposed, void* out, const void* addend, float* col_sum, float* col_sqsum,
-                        cudaStream_t st) {
+                        int transposed, void* out, const void* addend, const void* addend_bits, float* col_sum,
+                        float* col_sqsum, cudaStream_t st) {
   const HaloPlan pl = halo_plan(n_img, H, W, Cin, N);
   if (!pl.ok) return set_error(TOK_ERR_INVALID, "conv3x3 halo path: unsupported shape");
   static const bool debug = getenv("TOK_HALO_DEBUG") != nullptr;
@@ -748,6 +756,7 @@ int launch_conv3x3_halo(const void* x, int n_img, int H, int W, int Cin, int N, 
   p.w = static_cast<const __nv_bfloat16*>(w);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.addend = static_cast<const __nv_bfloat16*>(addend);
+  p.addend_bits = static_cast<const uint8_t*>(addend_bits);
   p.col_sum = col_sum;
   p.col_sqsum = col_sqsum;
   const long long pix_tiles = (long long)n_img * ((H + pl.TR - 1) / pl.TR);

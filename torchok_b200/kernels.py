@@ -236,10 +236,22 @@ def conv_fprop(d, x, w, y, stats=None, addend=None, bias=None, relu=False):
                          _p(stats[1]) if stats is not None else None, _p(addend), _p(bias), int(relu), _st())
 
 
-def conv_dgrad(d, dy, w, dx, addend=None):
+def conv_dgrad(d, dy, w, dx, addend=None, addend_bits=None):
+    """`addend_bits`: 1-bit ReLU mask of `addend` (tok_conv_dgrad_masked: dx = dgrad(dy) + addend * mask)."""
     nbytes = lib().tok_conv_dgrad_workspace_bytes(C.byref(d))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device) if nbytes else None
-    lib().tok_conv_dgrad(C.byref(d), _p(dy), _p(w), _p(dx), _p(addend), _p(ws), _st())
+    if addend_bits is not None:
+        lib().tok_conv_dgrad_masked(C.byref(d), _p(dy), _p(w), _p(dx), _p(addend), _p(addend_bits), _p(ws), _st())
+    else:
+        lib().tok_conv_dgrad(C.byref(d), _p(dy), _p(w), _p(dx), _p(addend), _p(ws), _st())
+
+
+# TOK_MASKED_ADDEND=0: the residual gradient of a block is materialised by the tail's BatchNorm backward (r2 path)
+_MASKED_ADDEND = os.environ.get('TOK_MASKED_ADDEND', '1') != '0'
+
+
+def dgrad_masked_supported(d):
+    return _MASKED_ADDEND and bool(lib().tok_conv_dgrad_masked_supported(C.byref(d)))
 
 
 def conv_wgrad(d, x, dy, dw):
@@ -380,7 +392,7 @@ def unit_forward(x, d, pq, w, bn, relu, residual=None, keep=True):
 
 
 def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=None, want_dres=False,
-                  wgrad_into=None, dgamma=None, dbeta=None, compact_dx=False, wgrad_direct=False):
+                  wgrad_into=None, dgamma=None, dbeta=None, compact_dx=False, wgrad_direct=False, dx_addend_bits=None):
     """Backward of `unit_forward`.  Returns (dx or None, dres or None).  Parameter gradients are ACCUMULATED into
     wgrad_into / dgamma / dbeta (fp32, may be None for frozen parameters)."""
     L = lib()
@@ -412,7 +424,7 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
         L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                             _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
         return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
-                                   wgrad_direct)
+                                   wgrad_direct, dx_addend_bits)
     if acc.shape[0] > 4 and _FUSE_BWD_FIN and _FUSED_BWD_MB > 0 and \
             rows * kp * 2 * (3 if dout2 is not None else 2) <= _FUSED_BWD_MB * 1e6:
         # small enough to stay in L2 between the passes: reduce + finalize + apply in ONE launch (acc[4] words 1 / 3:
@@ -424,7 +436,7 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
                               _p(coefs[1]), _p(coefs[2]), _p(dgamma), _p(dbeta), 1, acc[4].data_ptr() + 4,
                               acc[4].data_ptr() + 12, _p(dy), _p(dres), st)
         return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
-                                   wgrad_direct)
+                                   wgrad_direct, dx_addend_bits)
     if acc.shape[0] > 4 and _FUSE_BWD_FIN:   # reduce + finalize in one launch (acc[4]: the layer's ticket counters)
         L.tok_bn_bwd_reduce2_finalize_cv(rows, kp, bn.cv, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]),
                                          _p(small[1]), _p(acc[2]), _p(acc[3]), _p(small[2]), _p(small[3]), _p(bn.weight),
@@ -440,11 +452,11 @@ def unit_backward(saved, d, w, bn, dout, dout2=None, need_dx=True, dx_addend=Non
     L.tok_bn_bwd_apply2(rows, kp, _p(dout), _p(dout2), _p(y), mode, _p(bits), _p(small[0]), _p(small[1]),
                         _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(dy), _p(dres), st)
     return _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
-                               wgrad_direct)
+                               wgrad_direct, dx_addend_bits)
 
 
 def _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_addend, wgrad_into, rows, kp, dev,
-                        wgrad_direct=False):
+                        wgrad_direct=False, dx_addend_bits=None):
     """Data and weight gradients of the conv once dy (the gradient at the conv output) is known."""
     dx = None
     if need_dx and compact_dx:
@@ -455,7 +467,7 @@ def _unit_backward_tail(L, st, d, w, x, y, dy, dres, need_dx, compact_dx, dx_add
         L.tok_linear_dgrad(rows, kp, d.c, _p(dy), _p(w), _p(dx), st)
     elif need_dx:
         dx = torch.empty((d.n, d.h, d.w, d.c), dtype=BF16, device=dev)
-        conv_dgrad(d, dy, w, dx, dx_addend)
+        conv_dgrad(d, dy, w, dx, dx_addend, dx_addend_bits)
         dx = dx.permute(0, 3, 1, 2)
     if wgrad_into is not None:
         if wgrad_direct:

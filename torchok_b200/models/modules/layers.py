@@ -380,24 +380,36 @@ class ResidualBlockFn(torch.autograd.Function):
         saved_all = [tuple(next(it) if present else None for present in lay) + (mode,) for lay, mode in ctx.layout]
         off = 1 if ds is not None else 0
         dout = K._dense_grad(dout, descs[-1].k)
-        # last unit: ReLU mask from the block output, g flows to the shortcut
+        # last unit: ReLU mask from the block output.  The gradient that flows to the shortcut is g = dout * mask; r3: it
+        # is not materialised — its consumers read dout and the forward's mask bits themselves (the identity shortcut
+        # through the masked addend of the first conv's dgrad, a downsample unit through MASK_BITS of its own BatchNorm
+        # backward), so the tail's backward apply writes 2 of its 8 bytes per element less.
         conv, bn = units[-1]
-        dh, g = _unit_bwd(saved_all[-1], descs[-1], conv, bn, dout, want_dres=True)
+        tail_bits = saved_all[-1][2] if saved_all[-1][4] == K.MASK_BITS else None
+        need_dx = ctx.needs_input_grad[0]
+        lazy_g = tail_bits is not None and (
+            (ds is None and need_dx and K.dgrad_masked_supported(descs[off])) or (ds is not None and K._MASKED_ADDEND))
+        dh, g = _unit_bwd(saved_all[-1], descs[-1], conv, bn, dout, want_dres=not lazy_g)
         for i in range(len(units) - 2, 0, -1):
             conv, bn = units[i]
             dh, _ = _unit_bwd(saved_all[off + i], descs[off + i], conv, bn, dh)
-        need_dx = ctx.needs_input_grad[0]
-        addend, compact = g, None
+        addend, addend_bits, compact = g, None, None
         if ds is not None:
             dd = descs[0]
+            sv = saved_all[0]
+            if lazy_g:   # the downsample unit has no activation of its own: its incoming gradient is dout under the tail's mask
+                sv, g = (sv[0], sv[1], tail_bits, sv[3], K.MASK_BITS), dout
             if dd.stride > 1 and dd.r == 1 and dd.s == 1 and dd.pad == 0:
                 # strided 1x1 shortcut: compact GEMM now, merged into dx below (no zero-filled scatter tensor)
-                compact, _ = _unit_bwd(saved_all[0], dd, ds[0], ds[1], g, need_dx=need_dx, compact_dx=True)
+                compact, _ = _unit_bwd(sv, dd, ds[0], ds[1], g, need_dx=need_dx, compact_dx=True)
                 addend = None
             else:
-                addend, _ = _unit_bwd(saved_all[0], dd, ds[0], ds[1], g, need_dx=need_dx)
+                addend, _ = _unit_bwd(sv, dd, ds[0], ds[1], g, need_dx=need_dx)
+        elif lazy_g:
+            addend, addend_bits = dout, tail_bits
         conv, bn = units[0]
-        dx, _ = _unit_bwd(saved_all[off], descs[off], conv, bn, dh, need_dx=need_dx, dx_addend=addend)
+        dx, _ = _unit_bwd(saved_all[off], descs[off], conv, bn, dh, need_dx=need_dx, dx_addend=addend,
+                          dx_addend_bits=addend_bits)
         if compact is not None and dx is not None:
             K.strided_add(dx, compact, descs[0].stride)
         if dx is not None and dx.shape[1] != ctx.cin:
