@@ -303,7 +303,7 @@ def _call_work(name, a):
         x_elems = m * d.c if (d.r == 1 and d.s == 1) else d.n * d.h * d.w * d.c
         add = m * d.k if (name == 'tok_conv_fprop' and v(a[6])) else 0
         return 'conv fprop', 2.0 * m * d.k * d.r * d.s * d.c, 2.0 * (x_elems + m * d.k + d.k * d.r * d.s * d.c + add)
-    if name == 'tok_conv_dgrad':
+    if name in ('tok_conv_dgrad', 'tok_conv_dgrad_masked'):
         d, p, q = _desc(a[0])
         m = d.n * p * q
         dx = d.n * d.h * d.w * d.c
@@ -372,7 +372,7 @@ def _call_writes(name, a, w):
     if name in ('tok_conv_fprop', 'tok_conv_fprop_bn'):
         d, p, q = _desc(a[0])
         return 2.0 * d.n * p * q * d.k
-    if name == 'tok_conv_dgrad':
+    if name in ('tok_conv_dgrad', 'tok_conv_dgrad_masked'):
         d, p, q = _desc(a[0])
         return 2.0 * d.n * d.h * d.w * d.c
     if name == 'tok_conv_wgrad':

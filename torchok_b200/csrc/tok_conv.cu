@@ -583,6 +583,45 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         out_row = (static_cast<long long>(img) * p.sc_H + static_cast<long long>(pp) * p.sc_sh + p.sc_oh) * p.sc_W +
                   static_cast<long long>(qq) * p.sc_sw + p.sc_ow;
       }
+      // ReLU mask bits of the addend row (tok_conv.cuh: addend_bits): up to 32 bytes per row and tile, fetched with 16-byte
+      // loads BEFORE the accumulator wait (4-byte loads per chunk inside the loop cost 8 sectors per useful one and sat
+      // on the critical path: +30 % on the 512 -> 128 @28 dgrad)
+      uint4 mine = make_uint4(~0u, ~0u, ~0u, ~0u);   // mask words of THIS warp's chunks: chunk (2 i + half) -> component i
+      // (instantiations that never see an addend — ABUFS == 0 below the 256-wide tile — compile the mask away)
+      if ((ABUFS == 2 || BN == 256) && has_addend && p.addend_bits != nullptr && row_ok) {
+        const uint8_t* bp = p.addend_bits + static_cast<long long>(m) * (p.ldo >> 3) + (n0 >> 3);
+        int nbytes = (p.N - n0) >> 3;
+        if (nbytes > BN / 8) nbytes = BN / 8;
+        uint4 t0 = make_uint4(~0u, ~0u, ~0u, ~0u), t1 = t0;
+        if ((reinterpret_cast<uintptr_t>(bp) & 15) == 0 && nbytes >= 16) {
+          t0 = __ldg(reinterpret_cast<const uint4*>(bp));
+          if (BN == 256 && nbytes >= 32) t1 = __ldg(reinterpret_cast<const uint4*>(bp) + 1);
+          else if (BN == 256 && nbytes > 16) {
+            const unsigned int* wp = reinterpret_cast<const unsigned int*>(bp) + 4;
+            if (nbytes >= 20) t1.x = __ldg(wp);
+            if (nbytes >= 24) t1.y = __ldg(wp + 1);
+            if (nbytes >= 28) t1.z = __ldg(wp + 2);
+          }
+        } else {
+          const unsigned int* wp = reinterpret_cast<const unsigned int*>(bp);
+          if (nbytes >= 4) t0.x = __ldg(wp);
+          if (nbytes >= 8) t0.y = __ldg(wp + 1);
+          if (nbytes >= 12) t0.z = __ldg(wp + 2);
+          if (nbytes >= 16) t0.w = __ldg(wp + 3);
+          if (BN == 256) {
+            if (nbytes >= 20) t1.x = __ldg(wp + 4);
+            if (nbytes >= 24) t1.y = __ldg(wp + 5);
+            if (nbytes >= 28) t1.z = __ldg(wp + 6);
+            if (nbytes >= 32) t1.w = __ldg(wp + 7);
+          }
+        }
+        mine.x = half ? t0.y : t0.x;
+        mine.y = half ? t0.w : t0.z;
+        if (BN == 256) {
+          mine.z = half ? t1.y : t1.x;
+          mine.w = half ? t1.w : t1.z;
+        }
+      }
       mbar_wait(&tmem_full_bar[buf], (li >> 1) & 1);
       tc_fence_after();
       TOK_PROF(1)
@@ -610,13 +649,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint32_t mbits[kInFlight];
 #pragma unroll
       for (int cc = 0; cc < kInFlight; ++cc) {
-        mbits[cc] = 0xffffffffu;
-        if (has_addend && p.addend_bits != nullptr && row_ok) {
-          const int col0 = n0 + ((c0 + cc) * 2 + half) * 32;
-          if (col0 < p.N)
-            mbits[cc] = __ldg(reinterpret_cast<const unsigned int*>(p.addend_bits + static_cast<long long>(m) * (p.ldo >> 3) +
-                                                                    (col0 >> 3)));
-        }
+        const int w = c0 + cc;                        // this warp's (c0 + cc)-th chunk: word w of `mine`
+        mbits[cc] = w == 0 ? mine.x : (w == 1 ? mine.y : (w == 2 ? mine.z : mine.w));
       }
       if (kDefer && c0 == 0 && pend) {   // the previous tile's statistics, while this tile's first TMEM loads travel
         stats_pass(pend_cb, pend_rows);
