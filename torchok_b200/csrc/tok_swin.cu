@@ -175,18 +175,32 @@ layernorm_fwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   // the trip count is warp-uniform (the group shuffles need every lane); rows past the end are computed on row
   // `rows - 1` and not stored
+  // software pipeline: the rows of the NEXT pass (x and the residual) are in flight while this pass reduces and stores
+  // (r3: one load -> reduce -> load residual -> store chain per pass left the kernel at 0.58 of the HBM rate)
+  uint4 nx[CH], nr[CH];
+  auto fetch = [&](long long b) {
+    const long long rr = b + sub < rows ? b + sub : rows - 1;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      nx[i] = __ldg(reinterpret_cast<const uint4*>(x + rr * C) + l + i * G);
+      if (res) nr[i] = __ldg(reinterpret_cast<const uint4*>(res + rr * C) + l + i * G);
+    }
+  };
+  if (warp_id * RPW < rows) fetch(warp_id * RPW);
   for (long long base = warp_id * RPW; base < rows; base += warps * RPW) {
     const bool live = base + sub < rows;
     const long long r = live ? base + sub : rows - 1;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + r * C);
     float v[CH][8];
+    uint4 rraw[CH];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
-      unpack8(__ldg(xr + l + i * G), v[i]);
+      unpack8(nx[i], v[i]);
+      if (res) rraw[i] = nr[i];
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += v[i][e];
     }
+    if (base + warps * RPW < rows) fetch(base + warps * RPW);
     const float mu = group_sum<G>(s) * (1.f / C);
     float q = 0.f;
 #pragma unroll
@@ -210,7 +224,7 @@ layernorm_fwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
       for (int e = 0; e < 8; ++e) y[e] = fmaf((v[i][e] - mu) * rs, gm[e], bt[e]);
       if (res) {
         float rr[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(res + r * C) + l + i * G), rr);
+        unpack8(rraw[i], rr);
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = fmaf(sc, y[e], rr[e]);
       }
