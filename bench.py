@@ -79,7 +79,7 @@ WORKLOADS = {
             'backbone_name': 'hrnet_w18', 'backbone_params': {'pretrained': False, 'in_channels': 3},
             'neck_name': 'HRNetSegmentationNeck', 'head_name': 'SegmentationHead', 'head_params': {'num_classes': 19}}},
             'joint_loss': CE, 'optimization': [{'optimizer': {'name': 'SGD', 'params': {'lr': 0.01, 'momentum': 0.9}}}]},
-        batch=32, size=512, classes=19, seg=True, flop_per_img=None,
+        batch=32, size=512, classes=19, seg=True, flop_per_img=110.32e9,   # scripts/count_flops_hrnet.py
         metric='images/sec fwd+bwd HRNet-W18 + seg neck/head 512² bs32; 1/2/4/8 GPU scaling',
         name='HRNet-W18 + HRNetSegmentationNeck + SegmentationHead synthetic 3x512x512 bs32/GPU bf16, SGD step (C4)',
         oracle=None),
