@@ -276,6 +276,10 @@ int tok_layernorm_has_dxsum(int C);
  * addressed through `wstride` = their four element strides (the masters live in channels_last memory).  Backward
  * ACCUMULATES dweight / dbias (no image gradient: the image is the network input).  E % 32 == 0, E <= 256. */
 int tok_patch_embed_supported(int Cin, int patch, int H, int W, int E);
+/* im2col of the non-overlapping 4x4 patches of an NCHW image (fp32 or bf16) into a bf16 [B*H/4*W/4][48] matrix with the
+ * columns in (dy, dx, c) order = the memory order of the [E][4][4][3] conv weight, so PatchEmbed.proj is tok_linear_fwd /
+ * tok_linear_wgrad on it (tensor cores) instead of the CUDA-core tok_patch_embed_* kernels. */
+int tok_patchify(int B, int C, int H, int W, int patch, int src_is_bf16, const void* image, void* dst, void* stream);
 int tok_patch_embed_fwd(int B, int H, int W, int E, const float* image, const float* weight, const float* bias,
                         const int* wstride, void* tokens, void* stream);
 int tok_patch_embed_bwd(int B, int H, int W, int E, const float* image, const void* dtokens, const int* wstride,

@@ -84,8 +84,10 @@ def test_patch_embed(b, hw, e):
     from torchok_b200 import kernels as K
     assert K.patch_embed_supported(3, 4, hw, hw, e)
     torch.manual_seed(e + hw)
-    x = torch.randn(b, 3, hw, hw)
-    w = torch.randn(e, 3, 4, 4) * 0.2
+    # bf16-representable image and weights: the tensor-core path (r3: tok_patchify + tok_linear_*) multiplies bf16 operands
+    # like the reference's precision-16 mode does, so on these inputs it is as exact as the fp32 CUDA-core kernels
+    x = _bf(torch.randn(b, 3, hw, hw))
+    w = _bf(torch.randn(e, 3, 4, 4) * 0.2)
     bias = torch.randn(e) * 0.1
     wo, bo = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
     ref = F.conv2d(x, wo, bo, stride=4).flatten(2).transpose(1, 2).reshape(-1, e)

@@ -58,6 +58,7 @@ _SIGS = {
     'tok_linear_dgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_linear_dgrad_add': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'tok_patch_embed_supported': (_i, [_i, _i, _i, _i, _i]),
+    'tok_patchify': (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'tok_patch_embed_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_patch_embed_bwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_patch_merge': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),

@@ -595,6 +595,46 @@ patch_embed_bwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __res
   }
 }
 
+// ---- patch embedding on the tensor cores (r3): im2col of the non-overlapping P x P patches of an NCHW image into a bf16
+// [B*H/P*W/P][P*P*C] matrix in the weight's own memory order (dy, dx, c) — the [E][P][P][C] conv weight IS the [E][K]
+// matrix of a linear layer then, so timm's PatchEmbed.proj (torchok/models/backbones/swin.py:71-81) runs as tok_linear_fwd /
+// tok_linear_wgrad.  One thread per token row of P pixels x C channels; 503 + 357 us of CUDA-core convolution per Swin-T
+// step become ~50 us of layout pass plus two epilogue-bound GEMMs.
+template <typename T, int P, int C>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ dst, int B, int H, int W, long long total) {
+  pdl_wait();
+  pdl_launch();
+  const int Wp = W / P, Hp = H / P;
+  constexpr int K = P * P * C;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    // i = ((b * Hp + ph) * Wp + pw) * P + dy : one image row segment of a patch per thread, P pixels x C channels
+    const int dy = (int)(i % P);
+    long long t = i / P;
+    const int pw = (int)(t % Wp);
+    t /= Wp;
+    const int ph = (int)(t % Hp);
+    const long long b = t / Hp;
+    float v[C][P];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const T* s = img + ((b * C + c) * H + (ph * P + dy)) * (long long)W + pw * P;
+#pragma unroll
+      for (int dx = 0; dx < P; ++dx) v[c][dx] = (float)s[dx];
+    }
+    __nv_bfloat16* d = dst + ((b * Hp + ph) * (long long)Wp + pw) * K + dy * (P * C);
+    float f[P * C];
+#pragma unroll
+    for (int dx = 0; dx < P; ++dx)
+#pragma unroll
+      for (int c = 0; c < C; ++c) f[dx * C + c] = v[c][dx];
+    static_assert((P * C) % 4 == 0, "a row segment is stored as 8-byte vectors");
+#pragma unroll
+    for (int j = 0; j < P * C / 4; ++j)   // byte offset dy * 2 * P * C: 8-byte aligned
+      reinterpret_cast<uint2*>(d)[j] = make_uint2(pack_bf16x2(f[4 * j], f[4 * j + 1]), pack_bf16x2(f[4 * j + 2], f[4 * j + 3]));
+  }
+}
+
 // ---- PatchMerging gather -----------------------------------------------------------------------------------------
 // timm PatchMerging (used by torchok/models/backbones/swin.py:71-81 through BasicLayer.downsample):
 //   cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)  on a (B, H, W, C) tensor.
@@ -2267,6 +2307,22 @@ int tok_gelu_bwd(long long n, int C, const void* x, const void* dy, void* dx, fl
 static int pe_smem_bytes(int W, int E) {
   const int a = (W / 4) * kPePitch * 4 + (W / 4) * E * 2, b = E * (kPeK + 1) * 4;
   return a > b ? a : b;
+}
+
+int tok_patchify(int B, int C, int H, int W, int patch, int src_is_bf16, const void* image, void* dst, void* stream) {
+  if (B <= 0 || C != 3 || patch != 4 || H <= 0 || W <= 0 || (H % 4) || (W % 4))
+    return set_error(TOK_ERR_INVALID, "patchify: 3-channel images and 4x4 patches (got C=%d patch=%d H=%d W=%d)", C, patch, H, W);
+  const long long total = (long long)B * (H / 4) * (W / 4) * 4;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (src_is_bf16)
+    (void)launch_pdl(patchify_kernel<__nv_bfloat16, 4, 3>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                     (const __nv_bfloat16*)image, (__nv_bfloat16*)dst, B, H, W, total);
+  else
+    (void)launch_pdl(patchify_kernel<float, 4, 3>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                     (const float*)image, (__nv_bfloat16*)dst, B, H, W, total);
+  TOK_CHECK_LAUNCH("patchify");
+  return TOK_OK;
 }
 
 int tok_patch_embed_supported(int Cin, int patch, int H, int W, int E) {

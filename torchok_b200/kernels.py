@@ -1409,23 +1409,43 @@ def patch_merge(x, b, h, w):
     return PatchMergeFn.apply(x, b, h, w)
 
 
+_PATCH_GEMM = os.environ.get('TOK_PATCH_EMBED_GEMM', '1') != '0'   # 0: the r2 CUDA-core patch-embedding kernels
+
+
 class PatchEmbedFn(torch.autograd.Function):
     """timm PatchEmbed.proj (Conv2d(3, E, 4, stride 4)) + flatten(2).transpose(1, 2) on the NCHW image: (B*H/4*W/4, E)
-    bf16 tokens.  Reads the fp32 NCHW batch directly (no layout pass); weight / bias gradients are accumulated into
-    `.grad`; the image gets no gradient."""
+    bf16 tokens.  r3: the patches are laid out once as a bf16 [tokens][48] matrix in the weight's memory order
+    (tok_patchify) and the projection / its weight gradient run as tensor-core GEMMs (tok_linear_fwd / tok_linear_wgrad on
+    the [E][4][4][3] weight seen as [E][48]); the bias gradient is the column sum of the incoming gradient.  The image gets
+    no gradient.  TOK_PATCH_EMBED_GEMM=0 keeps the CUDA-core kernels that read the fp32 image directly."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         require_cuda(x, 'image')
         b, c, h, w = x.shape
         e = weight.shape[0]
+        gemm = _PATCH_GEMM and c == 3 and e % 8 == 0 and is_krsc(weight) and weight.shape[2] == 4 and weight.shape[3] == 4
+        ctx.gemm = gemm
+        ctx.params = (weight, bias)
+        ctx.geom = (b, h, w, e)
+        if gemm:
+            x = x.detach()
+            if x.dtype not in (F32, BF16):
+                x = x.float()
+            x = x.contiguous()
+            m = b * (h // 4) * (w // 4)
+            patches = torch.empty((m, 48), dtype=BF16, device=x.device)
+            lib().tok_patchify(b, c, h, w, 4, int(x.dtype == BF16), _p(x), _p(patches), _st())
+            out = torch.empty((m, e), dtype=BF16, device=x.device)
+            bvec = bias.detach().float() if bias is not None else None
+            lib().tok_linear_fwd(m, e, 48, _p(patches), _p(shadow_of(weight)), _p(bvec), _p(out), _st())
+            ctx.save_for_backward(patches)
+            return out
         x = x.detach().float().contiguous()
         wst = (C.c_int * 4)(*weight.stride())
         out = torch.empty((b * (h // 4) * (w // 4), e), dtype=BF16, device=x.device)
         lib().tok_patch_embed_fwd(b, h, w, e, _p(x), _p(weight), _p(bias), wst, _p(out), _st())
         ctx.save_for_backward(x)
-        ctx.params = (weight, bias)
-        ctx.geom = (b, h, w, e)
         return out
 
     @staticmethod
@@ -1438,8 +1458,18 @@ class PatchEmbedFn(torch.autograd.Function):
         if gw.stride() != weight.stride():
             raise RuntimeError('patch_embed: gradient buffer and weight must share their memory layout')
         gb = grad_buffer(bias) if bias is not None and bias.requires_grad else None
-        wst = (C.c_int * 4)(*weight.stride())
-        lib().tok_patch_embed_bwd(b, h, w, e, _p(x), _p(g), wst, _p(gw), _p(gb), _st())
+        if ctx.gemm:
+            m = x.shape[0]
+            L, st = lib(), _st()
+            if weight.requires_grad:
+                wgrad_async((x, g, gw), lambda s: L.tok_linear_wgrad(m, e, 48, _p(x), _p(g), _p(gw), s))
+            if gb is not None:
+                acc = torch.zeros((2, e), dtype=F32, device=g.device)
+                L.tok_bn_bwd_reduce(m, e, _p(g), None, None, _p(g), _p(acc[0]), _p(acc[1]), st)
+                gb.add_(acc[0])
+        else:
+            wst = (C.c_int * 4)(*weight.stride())
+            lib().tok_patch_embed_bwd(b, h, w, e, _p(x), _p(g), wst, _p(gw), _p(gb), _st())
         grad_ready(weight)
         if bias is not None:
             grad_ready(bias)
