@@ -201,6 +201,23 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
   mn_desc_geometry(&p.mn_lbo, &p.mn_sbo, &p.mn_kadv);
   static const int defer = getenv("TOK_CONV_DEFER_STATS") ? atoi(getenv("TOK_CONV_DEFER_STATS")) : 1;
   p.defer_stats = defer;
+  // Tile order of the persistent kernel (tok_conv.cu: decode_tile).  Several column strips over an A operand that does
+  // not stay in L2 between strips: walk groups of m-tiles whose A rows total <= 16 MB.  Measured r5 (one B200, A/B in one
+  // box): Swin-T linear fwd 4.64 -> 4.46 ms, linear dgrad 4.40 -> 4.19 ms, step 27.36 -> 26.62 ms; ResNet-50 conv dgrad
+  // 4.08 -> 3.95 ms.  With BatchNorm sums a group change costs a flush of the register partials and the forward convs
+  // measured no gain (3.78 vs 3.80 ms), so launches with sums keep whole strips.  TOK_CONV_MGROUP=0: off, =n: n x 148
+  // m-tiles per group for every launch.
+  {
+    static const int mg_env = getenv("TOK_CONV_MGROUP") ? atoi(getenv("TOK_CONV_MGROUP")) : -1;
+    const long long a_bytes = M * (long long)ac * 2;
+    const int strips = (N + bn - 1) / bn;
+    p.m_group = 0;
+    if (mg_env != 0 && strips > 1 && a_bytes > (24LL << 20)) {
+      long long k = mg_env > 0 ? mg_env : (16LL << 20) / (148LL * 128 * ac * 2);
+      if (k < 1) k = 1;
+      if (p.col_sum == nullptr || mg_env > 0) p.m_group = (int)(148 * k);
+    }
+  }
   // TOK_CONV_PROFILE=1: the epilogue phase counters of every launch land in a static device buffer which
   // tok_debug_conv_profile() copies out (bring-up aid; not part of the production path)
   static const bool want_prof = getenv("TOK_CONV_PROFILE") != nullptr;

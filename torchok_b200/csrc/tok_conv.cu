@@ -293,6 +293,22 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int n_tiles = (p.N + BN - 1) / BN;
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int total_tiles = n_tiles * m_tiles;
+  // Tile order.  Default (m_group == 0): n-tile major — every m-tile of one 128/256-column strip, then the next strip, so
+  // the BatchNorm partial sums of a strip stay in registers and a resident weight slab is loaded once per strip.  With
+  // several strips that re-reads the A operand once per strip, from HBM when it is larger than L2 (Swin stage-1 qkv:
+  // 154 MB x 3).  m_group = G > 0 walks groups of G m-tiles, strip by strip inside a group, so the group's A tiles are
+  // still in L2 when the next strip wants them.
+  const int mg = (BRES == 0 && p.m_group > 0 && p.m_group < m_tiles) ? p.m_group : m_tiles;
+  const int group_tiles = mg * n_tiles;
+  auto decode_tile = [&](int t, int& n0, int& m0) {
+    const int g = t / group_tiles;
+    const int r = t - g * group_tiles;
+    const int left = m_tiles - g * mg;
+    const int gm = left < mg ? left : mg;
+    const int nt = r / gm;
+    n0 = nt * BN;
+    m0 = (g * mg + (r - nt * gm)) * kBlockM;
+  };
   const int cin_chunks = (p.Cin + kBlockK - 1) / kBlockK;
   const int taps = p.a.R * p.a.S;
   const int num_kb = taps * cin_chunks;
@@ -338,8 +354,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       int wres_n0 = -1;
       uint32_t wres_gen = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
-        const int n0 = (t / m_tiles) * BN;
-        const int m0 = (t % m_tiles) * kBlockM;
+        int n0, m0;
+        decode_tile(t, n0, m0);
         if (ABUFS == 2 && has_addend) {
           // addend tile of THIS output tile; the epilogue is at most two tiles behind, so this runs a tile ahead
           const int ab = li & 1;
@@ -543,8 +559,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     tp = now;                            \
   }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
-      const int n0 = (t / m_tiles) * BN;
-      const int m0 = (t % m_tiles) * kBlockM;
+      int n0, m0;
+      decode_tile(t, n0, m0);
       const int buf = li & 1;
       const int m = m0 + row;
       const bool row_ok = m < p.M;

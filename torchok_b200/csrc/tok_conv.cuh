@@ -88,6 +88,7 @@ struct ConvFwdParams {
   // bring-up aid (TOK_CONV_PROFILE=1): per-CTA cycle counts of the epilogue phases, 8 slots per CTA
   long long* prof;
   FwdFin fin;   // persistent kernel only
+  int m_group;       // persistent kernel tile order: m-tiles per group (0 = whole strips; tok_conv.cu: decode_tile)
   int defer_stats;   // persistent kernel, two staging buffers: statistics pass of tile t inside iteration t + 1
 };
 
