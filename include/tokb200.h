@@ -39,6 +39,7 @@ int tok_device_ok(void);
  * of its epilogue phases (16 int64 per CTA: two observer threads x 8 slots); this copies the last launch's counters
  * to the host and returns the number of entries written (0 when profiling is off). */
 int tok_debug_conv_profile(long long* host_out, int max_entries);
+int tok_debug_attn_profile(long long* host_out, int max_entries);   /* TOK_ATTN_PROFILE=1: window-attention forward */
 
 /* ---- convolution (torch.nn.Conv2d inside ConvBnAct, torchok/models/modules/bricks/convbnact.py:38-53; timm
  *      BasicBlock/Bottleneck convs built by torchok/models/backbones/resnet.py:363-405) ------------------------- */

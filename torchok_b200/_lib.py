@@ -45,6 +45,7 @@ _SIGS = {
     'tok_last_error': (C.c_char_p, []),
     'tok_device_ok': (_i, []),
     'tok_debug_conv_profile': (_i, [_vp, _i]),
+    'tok_debug_attn_profile': (_i, [_vp, _i]),
     'tok_conv_out_hw': (None, [_pd, _pi, _pi]),
     'tok_conv_halo_caps': (_i, [_pd]),
     'tok_conv_fprop': (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
@@ -155,7 +156,7 @@ _SIGS = {
     'tok_pad_weight': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_unpad_wgrad_add': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
-_RAW = {'tok_conv_halo_caps', 'tok_conv_dgrad_masked_supported', 'tok_bn_apply_train_supported', 'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
+_RAW = {'tok_conv_halo_caps', 'tok_conv_dgrad_masked_supported', 'tok_bn_apply_train_supported', 'tok_peer_flag_bytes', 'tok_debug_conv_profile', 'tok_debug_attn_profile', 'tok_layernorm_has_dxsum', 'tok_patch_embed_supported', 'tok_version', 'tok_last_error', 'tok_device_ok', 'tok_conv_out_hw', 'tok_conv_dgrad_workspace_bytes',
         'tok_stem_geometry'}
 
 

@@ -1274,28 +1274,120 @@ window_attn_fwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   if (warp == 0) tmem_dealloc(tmem_s, 256);
 }
 
+// Walks the windows w0, w0 + step, w0 + 2 step, ... of one row slot t of the stacked pair without per-iteration divisions
+// (r5: the five runtime divisions of token_row cost 800-1700 clocks per pair on the critical path of the tcgen05
+// kernels): (b, wy, wx) advance by the pre-split step with carries, (ty, tx) are fixed per thread.
+struct WindowWalker {
+  int b, wy, wx, sb, swy, swx, ty, tx;
+  __device__ __forceinline__ void init(const AttnGeom& g, int w0, int step, int t) {
+    wx = w0 % g.nwx;
+    wy = (w0 / g.nwx) % g.nwy;
+    b = w0 / (g.nwx * g.nwy);
+    swx = step % g.nwx;
+    swy = (step / g.nwx) % g.nwy;
+    sb = step / (g.nwx * g.nwy);
+    ty = t / g.ws;
+    tx = t - ty * g.ws;
+  }
+  __device__ __forceinline__ bool in_range(const AttnGeom& g) const { return b < g.B; }
+  __device__ __forceinline__ long long row(const AttnGeom& g, int& region) const {
+    const int ys = wy * g.ws + ty, xs = wx * g.ws + tx;
+    int ry = 0, rx = 0;
+    if (g.shift > 0) {
+      ry = ys < g.H - g.ws ? 0 : (ys < g.H - g.shift ? 1 : 2);
+      rx = xs < g.W - g.ws ? 0 : (xs < g.W - g.shift ? 1 : 2);
+    }
+    region = ry * 3 + rx;
+    int y = ys + g.shift, x = xs + g.shift;
+    if (y >= g.H) y -= g.H;
+    if (x >= g.W) x -= g.W;
+    return ((long long)b * g.H + y) * g.W + x;
+  }
+  __device__ __forceinline__ void advance(const AttnGeom& g) {
+    wx += swx;
+    if (wx >= g.nwx) { wx -= g.nwx; ++wy; }
+    wy += swy;
+    if (wy >= g.nwy) { wy -= g.nwy; ++b; }
+    b += sb;
+  }
+};
+
+// Softmax inputs of the two kernels below.  The bias table lives in shared memory at a pitch of 68 floats (16-byte rows,
+// conflict-free LDS.128 for consecutive rows), pre-multiplied by log2(e) so the exponentials are bare ex2; the columns
+// of keys that do not exist (N .. 63) hold -inf, the rows of tokens that do not exist hold 0, so the per-key loop needs
+// neither a bounds test nor a branch (r5: the branchy scalar version compiled to ~47 instructions and two dependent
+// shared-memory round trips per key — half of the forward kernel's time per window pair, scripts/attn_one.py).
+constexpr int kBiasPitch = 68;
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void fill_bias_table(uint32_t aBias, const float* __restrict__ bias_head, int N, int tid,
+                                                int nthreads) {
+  for (int i = tid; i < kMaxN * kBiasPitch; i += nthreads) {
+    const int tr = i / kBiasPitch, tc = i - tr * kBiasPitch;
+    float v = 0.f;
+    if (tc >= N) v = -INFINITY;
+    else if (tr < N) v = bias_head[tr * N + tc] * kLog2e;
+    sts_f32(aBias + i * 4, v);
+  }
+}
+// logits of keys [key0, key0 + 4 NV) of one row: e[j] = s[j] * scale2 + bias2[key0 + j] (+ shift mask), returns their max
+template <int NV>
+__device__ __forceinline__ float logits_row(const uint32_t* sraw, float* e, uint32_t brow, uint32_t rrow, float scale2,
+                                            int region, bool shifted) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const uint4 b4 = lds128(brow + c * 16);
+    const float bb[4] = {__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z), __uint_as_float(b4.w)};
+    float mk[4] = {0.f, 0.f, 0.f, 0.f};
+    if (shifted) {   // uniform: the -100 of timm's shifted-window mask, in log2 units
+      const uint4 r4 = lds128(rrow + c * 16);
+      const int rg[4] = {(int)r4.x, (int)r4.y, (int)r4.z, (int)r4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mk[q] = rg[q] != region ? -100.f * kLog2e : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float sc = fmaf(__uint_as_float(sraw[c * 4 + q]), scale2, bb[q]) + mk[q];
+      e[c * 4 + q] = sc;
+      mx = fmaxf(mx, sc);
+    }
+  }
+  return fmaxf(mx, -1e30f);   // a quarter made of absent keys only: keeps exp2(-inf - mx) = 0 instead of NaN
+}
+
 // Forward, second layout: the same UMMA chains, but TWO threads per row (256 threads, warps 0-3 own key columns 0-31 of
 // the row's window, warps 4-7 columns 32-63) and two CTAs per SM, so sixteen warps hide each other's latencies where
 // the one-thread-per-row kernel above was issue-bound (2300 instructions per row and iteration on 8 warps per SM).
 // The two halves of a row merge their (max, sum) once through shared memory (online-softmax merge).  Gather roles:
 // half 0 stages q (hi | lo) and v, half 1 stages k (hi | hi, lo into the v rows); O columns are split 16 / 16.
 constexpr int kTc2Threads = 256;
-constexpr int kTc2Smem = 3 * 16384 + 32768 + kMaxN * kMaxN * 4 + 128 * 2 * 8 + 128 * 4 + 64 + 1024;
+constexpr int kTc2Smem = 3 * 16384 + 32768 + kMaxN * kBiasPitch * 4 + 128 * 2 * 8 + 128 * 4 + 64 + 1024;
 
-__global__ void __launch_bounds__(kTc2Threads, 2)
+__device__ __forceinline__ uint4 ldg_na(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+template <bool PROF>
+__global__ void __launch_bounds__(kTc2Threads + 32, 2)
 window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
                            const float* __restrict__ logit_scale, const float* __restrict__ bias,
-                           __nv_bfloat16* __restrict__ out) {
+                           __nv_bfloat16* __restrict__ out, long long* __restrict__ prof, int dbg) {
   pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
   pdl_launch();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t aQ = smem_u32(smem), aK = aQ + 16384, aV = aK + 16384, aP = aV + 16384;
-  const uint32_t aBias = aP + 32768;               // float [N][N]
-  const uint32_t aX = aBias + kMaxN * kMaxN * 4;   // float2 [128 rows][2 halves]: (max, sum)
+  const uint32_t aBias = aP + 32768;               // float [64][kBiasPitch]: fill_bias_table
+  const uint32_t aX = aBias + kMaxN * kBiasPitch * 4;   // float2 [128 rows][2 halves]: (max, sum)
   const uint32_t aReg = aX + 128 * 2 * 8;          // int [128]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (aReg - aQ) + 128 * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (aReg - aQ) + 128 * 4);   // [0] S ready, [1] O ready (UMMA commits),
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 4);                  // [2] operands staged, [3] P staged (workers)
 
   const int N = g.ws * g.ws;
   const int head = blockIdx.x % g.heads;
@@ -1306,15 +1398,17 @@ window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restri
   const int r = (warp & 3) * 32 + (tid & 31);   // stacked row = TMEM lane
   const int prob = r >> 6;
   const int t = r & 63;
-  const float scale = __expf(fminf(logit_scale[head], 4.6051702f));
+  const float scale2 = __expf(fminf(logit_scale[head], 4.6051702f)) * kLog2e;
   const int total_windows = g.B * g.nwy * g.nwx;
   const int total_pairs = (total_windows + 1) / 2;
 
-  for (int i = tid; i < (3 * 16384 + 32768) / 16; i += kTc2Threads) sts128(aQ + i * 16, make_uint4(0, 0, 0, 0));
-  for (int i = tid; i < N * N; i += kTc2Threads) sts_f32(aBias + i * 4, bias[(long long)head * N * N + i]);
+  for (int i = tid; i < (3 * 16384 + 32768) / 16; i += kTc2Threads + 32) sts128(aQ + i * 16, make_uint4(0, 0, 0, 0));
+  fill_bias_table(aBias, bias + (long long)head * N * N, N, tid, kTc2Threads + 32);
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], kTc2Threads / 32);   // one arrival per worker warp
+    mbar_init(&bar[3], kTc2Threads / 32);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -1330,130 +1424,178 @@ window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restri
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
 
-  // the next pair's rows are fetched while P . V and the output store of the current pair run (registers are free then)
+  // ---- warp 8: the UMMA issuer.  r5: issued from a worker warp, the two UMMA chains blocked that warp for their whole
+  // execution (~1300 clocks per pair: the shared-memory operand fetch of the 14 instructions) and every other warp then
+  // waited for it at the CTA barriers; here the workers only arrive on mbarriers and go on.
+  if (warp == kTc2Threads / 32) {
+    if (elect_one()) {
+      uint32_t ph = 0;
+      for (int pair = grp; pair < total_pairs; pair += groups, ph ^= 1) {
+        mbar_wait(&bar[2], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
+                    idesc_s, k);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                    make_smem_desc_sw128(aV + (k + 2) * 32, 16, 1024), idesc_s, 1u);
+        umma_commit(&bar[0]);
+        mbar_wait(&bar[3], ph);
+        tc_fence_after();
+        // O = [P_A; 0] . V_A + [0; P_B] . V_B
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_o, make_smem_desc_sw128(aP + kb * 16384 + k * 32, 16, 1024),
+                      make_smem_desc_sw128(aV + kb * 8192 + k * 2048, 8192, 1024), idesc_o, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar[1]);
+      }
+      // the last commit has completed before any worker leaves its loop; TMEM is released by warp 0 below
+    }
+    return;
+  }
+
+  // The next pair's rows are fetched while P . V runs.  Each row's home position is worked out by the thread that owns the
+  // row (softmax, output store); the LOADS are dealt the other way round: lane l moves 16-byte chunk (l & 3) of the four
+  // rows R0 + rmap(l >> 2) + 8 i of its warp's 32-row block, so one warp instruction covers 8 rows x 64 contiguous bytes
+  // instead of 32 rows x 16 bytes (r5: the row-per-lane loads kept the LSU busy for ~20 clocks per instruction, 1000-2000
+  // clocks per pair and CTA).  rmap interleaves rows {0, 4, 1, 5, ...} so the eight lanes of a 16-byte shared-memory
+  // store phase hit eight different swizzled columns.
+  const int lane = tid & 31;
+  const int lc = lane & 3;
+  const int lrow8 = ((lane >> 2) & 1) * 4 + (lane >> 3);
+  const int crow0 = (warp & 3) * 32 + lrow8;     // stacked row of this lane's chunk i: crow0 + 8 i
   uint4 xr[4], vr[4];
   long long nrow = 0;
   int nregion = 0;
   bool nvalid = false;
-  auto fetch = [&](int pair) {
-    const int w = pair * 2 + prob;
-    nvalid = t < N && pair < total_pairs && w < total_windows;
+  WindowWalker ww;
+  ww.init(g, grp * 2 + prob, groups * 2, t);
+  auto fetch = [&]() {
+    nvalid = t < N && ww.in_range(g);
     nrow = 0;
     nregion = 0;
-    if (nvalid) {
-      const int wx = w % g.nwx, wy = (w / g.nwx) % g.nwy, b = w / (g.nwx * g.nwy);
-      nrow = token_row(g, b, wy, wx, t, nregion);
-      const uint4* base = reinterpret_cast<const uint4*>(qkv + nrow * 3 * g.C + head * kHd);
-      const int cstep = g.C / 8;
+    if (nvalid) nrow = ww.row(g, nregion);
+    ww.advance(g);
+    const int mine = nvalid ? static_cast<int>(nrow) : -1;
+    const int cstep = g.C / 8;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        xr[c] = __ldg(base + h * cstep + c);            // q (half 0) or k (half 1)
-        if (h == 0) vr[c] = __ldg(base + 2 * cstep + c);
+    for (int i = 0; i < 4; ++i) {
+      const int gr = __shfl_sync(0xffffffffu, mine, lrow8 + 8 * i);
+      xr[i] = make_uint4(0, 0, 0, 0);
+      vr[i] = make_uint4(0, 0, 0, 0);
+      if (gr >= 0) {
+        const uint4* base = reinterpret_cast<const uint4*>(qkv + (long long)gr * 3 * g.C + head * kHd) + lc;
+        if (PROF && dbg == 2) continue;   // timing experiment: no loads at all (results are garbage)
+        if (PROF && dbg == 1) {           // timing experiment: loads that do not allocate in L1
+          xr[i] = ldg_na(base + h * cstep);
+          if (h == 0) vr[i] = ldg_na(base + 2 * cstep);
+          continue;
+        }
+        xr[i] = __ldg(base + h * cstep);            // q (half 0) or k (half 1)
+        if (h == 0) vr[i] = __ldg(base + 2 * cstep);
       }
     }
   };
-  fetch(grp);
+  fetch();
 
+  // TOK_ATTN_PROFILE=1 (bring-up aid): clock64 phase sums of CTA 0, threads 0 (UMMA issuer) and 128, read back by
+  // tok_debug_attn_profile()
+  const bool profiling = PROF && prof != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 128);
+  long long pt[PROF ? 14 : 1] = {0};
+  long long tp = profiling ? clock64() : 0;
+#define TOK_APROF(i)                   \
+  if (PROF && profiling) {                     \
+    const long long now = clock64();   \
+    pt[i] += now - tp;                 \
+    tp = now;                          \
+  }
   uint32_t phase = 0;
   for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
     const bool valid = nvalid;
     const long long my_row = nrow;
     const int region = nregion;
-    if (valid) {
-      float ss = 0.f;
+    {
+      // cosine normalisation: the four lanes holding a row's chunks add their partial sums of squares (absent rows were
+      // fetched as zeros and stage zeros)
+      float inv_norm[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t wv[4] = {xr[c].x, xr[c].y, xr[c].z, xr[c].w};
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t wv[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
+        float ss = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) ss = fmaf(bf16_lo(wv[e]), bf16_lo(wv[e]), fmaf(bf16_hi(wv[e]), bf16_hi(wv[e]), ss));
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        inv_norm[i] = rsqrtf(fmaxf(ss, 1e-24f));   // 1 / max(|x|, 1e-12) (F.normalize), one MUFU
       }
-      const float inv_norm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      if (PROF && profiling && inv_norm[0] == 123.f) pt[0] = 1;   // keeps the stamp below after the first use of the loads
+      TOK_APROF(13)
       // split-bf16 cosine operands (see window_attn_fwd_tc_kernel): sQ = [q_hi | q_lo], sK = [k_hi | k_hi], sV = [v | k_lo]
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t wv[4] = {xr[c].x, xr[c].y, xr[c].z, xr[c].w};
+      for (int i = 0; i < 4; ++i) {
+        const int cr = crow0 + 8 * i;
+        const uint32_t wv[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
         uint32_t o[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float x0 = bf16_lo(wv[e]) * inv_norm, x1 = bf16_hi(wv[e]) * inv_norm;
+          const float x0 = bf16_lo(wv[e]) * inv_norm[i], x1 = bf16_hi(wv[e]) * inv_norm[i];
           o[e] = pack_bf16x2(x0, x1);
           lo[e] = pack_bf16x2(x0 - bf16_lo(o[e]), x1 - bf16_hi(o[e]));
         }
         if (h == 0) {
-          sts128(aQ + sw128_off(r, c), make_uint4(o[0], o[1], o[2], o[3]));
-          sts128(aQ + sw128_off(r, c + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
-          sts128(aV + sw128_off(r, c), vr[c]);
+          sts128(aQ + sw128_off(cr, lc), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(aQ + sw128_off(cr, lc + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          sts128(aV + sw128_off(cr, lc), vr[i]);
         } else {
-          sts128(aK + sw128_off(r, c), make_uint4(o[0], o[1], o[2], o[3]));
-          sts128(aK + sw128_off(r, c + 4), make_uint4(o[0], o[1], o[2], o[3]));
-          sts128(aV + sw128_off(r, c + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
-        }
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (h == 0) {
-          sts128(aQ + sw128_off(r, c), make_uint4(0, 0, 0, 0));
-          sts128(aQ + sw128_off(r, c + 4), make_uint4(0, 0, 0, 0));
-          sts128(aV + sw128_off(r, c), make_uint4(0, 0, 0, 0));
-        } else {
-          sts128(aK + sw128_off(r, c), make_uint4(0, 0, 0, 0));
-          sts128(aK + sw128_off(r, c + 4), make_uint4(0, 0, 0, 0));
-          sts128(aV + sw128_off(r, c + 4), make_uint4(0, 0, 0, 0));
+          sts128(aK + sw128_off(cr, lc), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(aK + sw128_off(cr, lc + 4), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(aV + sw128_off(cr, lc + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
         }
       }
     }
     if (h == 0) sts_f32(aReg + r * 4, __int_as_float(region));
+    TOK_APROF(0)
     fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
-                  idesc_s, k);
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        umma_bf16(tmem_s, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aV + (k + 2) * 32, 16, 1024),
-                  idesc_s, 1u);
-      umma_commit(&bar[0]);
-    }
+    tc_fence_before();   // this thread's TMEM reads of the previous pair are ordered before the issuer's next UMMAs
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar[2]);
+    TOK_APROF(1)
+    TOK_APROF(10)
     mbar_wait(&bar[0], phase);
     tc_fence_after();
+    TOK_APROF(2)
     // ---- softmax of this half-row, merged with the other half
     float e[32];
-    float mx = -INFINITY;
+    float mx;
     {
       uint32_t sraw[32];
       tmem_ld_32x32b_x32(tmem_s + lane_addr + prob * 64 + h * 32, sraw);
       tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int key = h * 32 + j;
-        float sc = -INFINITY;
-        if (valid && key < N) {
-          const int kreg = __float_as_int(lds_f32(aReg + (prob * 64 + key) * 4));
-          sc = fmaf(__uint_as_float(sraw[j]), scale, lds_f32(aBias + (t * N + key) * 4)) + (kreg != region ? -100.f : 0.f);
-        }
-        e[j] = sc;
-        mx = fmaxf(mx, sc);
-      }
+      mx = logits_row<8>(sraw, e, aBias + (t * kBiasPitch + h * 32) * 4, aReg + (prob * 64 + h * 32) * 4, scale2, region,
+                         g.shift != 0);
     }
     float lsum = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      e[j] = mx > -INFINITY ? __expf(e[j] - mx) : 0.f;
+      e[j] = ex2_approx(e[j] - mx);
       lsum += e[j];
     }
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(aX + (r * 2 + h) * 8), "f"(mx), "f"(lsum) : "memory");
-    __syncthreads();
+    TOK_APROF(3)
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the two halves of every row have published (max, sum)
+    TOK_APROF(4)
+
     float factor = 0.f;
     {
       float m0, l0, m1, l1;
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m0), "=f"(l0), "=f"(m1), "=f"(l1) : "r"(aX + r * 16));
       const float m = fmaxf(m0, m1);
-      const float f0 = m0 > -INFINITY ? __expf(m0 - m) : 0.f, f1 = m1 > -INFINITY ? __expf(m1 - m) : 0.f;
+      const float f0 = ex2_approx(m0 - m), f1 = ex2_approx(m1 - m);
       const float l = l0 * f0 + l1 * f1;
       if (valid && l > 0.f) factor = (h == 0 ? f0 : f1) / l;
     }
@@ -1464,24 +1606,17 @@ window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restri
       for (int q2 = 0; q2 < 4; ++q2) o4[q2] = pack_bf16x2(e[c * 8 + 2 * q2] * factor, e[c * 8 + 2 * q2 + 1] * factor);
       sts128(aP + prob * 16384 + sw128_off(r, 4 * h + c), make_uint4(o4[0], o4[1], o4[2], o4[3]));
     }
+    TOK_APROF(5)
     fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- O = [P_A; 0] . V_A + [0; P_B] . V_B
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_o, make_smem_desc_sw128(aP + kb * 16384 + k * 32, 16, 1024),
-                    make_smem_desc_sw128(aV + kb * 8192 + k * 2048, 8192, 1024), idesc_o, (kb | k) != 0 ? 1u : 0u);
-      }
-      umma_commit(&bar[1]);
-    }
-    fetch(pair + groups);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar[3]);
+    TOK_APROF(6)
+    TOK_APROF(11)
+    fetch();
+    TOK_APROF(12)
     mbar_wait(&bar[1], phase);
     tc_fence_after();
+    TOK_APROF(7)
     {
       uint32_t acc[16];
       tmem_ld_32x32b_x16(tmem_o + lane_addr + h * 16, acc);
@@ -1496,10 +1631,17 @@ window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restri
                              pack_bf16x2(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7])));
       }
     }
-    tc_fence_before();
-    __syncthreads();  // TMEM and the operand tiles are free for the next pair
-    tc_fence_after();
+    TOK_APROF(8)
+    // no CTA barrier here: this thread has seen O ready, so both UMMA chains of the pair are complete and the operand
+    // tiles may be restaged; the S / O accumulators are rewritten only after every worker warp has arrived again
   }
+#undef TOK_APROF
+  if (PROF && profiling) {
+#pragma unroll
+    for (int i = 0; i < (PROF ? 14 : 1); ++i) prof[(tid >> 7) * 14 + i] = pt[i];
+  }
+  tc_fence_before();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   if (warp == 0) tmem_dealloc(tmem_s, 256);
 }
 
@@ -1692,8 +1834,11 @@ window_attn_bwd_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__
 // The next pair's rows are prefetched into registers while round 2 runs.
 constexpr int kBwThreads = 512;
 constexpr int kBwTiles = 8 * 16384;  // sQ sK sV sDO, sP[2], sDS[2]
-constexpr int kBwSmem = kBwTiles + kMaxN * kMaxN * 4 + 128 * 4 * 16 + 128 * 4 + 64 + 32 * 256 * 4 + 1024;
+constexpr int kBwSmem = kBwTiles + kMaxN * kBiasPitch * 4 + 128 * 4 * 16 + 128 * 4 + 64 + 32 * 256 * 4 + 1024;
 
+// The UMMA issuer is the elected lane of warp 12 (dO role: no epilogue work), not a 17th warp: a fifth warp on one SM
+// sub-partition caps the kernel at 96 registers per thread (16384 / (5 x 32); 112 and 120 do not launch) and the spills
+// cost more than the dedicated warp gains (r5: 1078 vs 905 us for stage 1 at bs256).
 __global__ void __launch_bounds__(kBwThreads, 1)
 window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restrict__ qkv,
                           const float* __restrict__ logit_scale, const float* __restrict__ bias,
@@ -1705,11 +1850,11 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t aQ = smem_u32(smem), aK = aQ + 16384, aV = aK + 16384, aDO = aV + 16384;
   const uint32_t aP = aDO + 16384, aDS = aP + 32768;
-  const uint32_t aBias = aDS + 32768;                 // float [N][N]
-  const uint32_t aX = aBias + kMaxN * kMaxN * 4;      // float4 [128 rows][4 quarters]: (max, sum, sum p~ dP, -)
+  const uint32_t aBias = aDS + 32768;                 // float [64][kBiasPitch]: fill_bias_table
+  const uint32_t aX = aBias + kMaxN * kBiasPitch * 4;  // float4 [128 rows][4 quarters]: (max, sum, sum p~ dP, -)
   const uint32_t aReg = aX + 128 * 4 * 16;            // int [128]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (aReg - aQ) + 128 * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 4);   // bar: [0] round 1 done, [1] round 2 done, [2] operands staged, [3] P / dS staged
   // column sums of dq / dv over every token this CTA sees (= the q_bias / v_bias gradients): float [32][256],
   // slot = (dv ? 128 : 0) + row, owned by one thread each
   const uint32_t aCol = aReg + 128 * 4 + 64;
@@ -1725,15 +1870,18 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   const int t = r & 63;
   const float ls = logit_scale[head];
   const float scale = __expf(fminf(ls, 4.6051702f));
+  const float scale2 = scale * kLog2e;
   const int total_windows = g.B * g.nwy * g.nwx;
   const int total_pairs = (total_windows + 1) / 2;
 
   for (int i = tid; i < kBwTiles / 16; i += kBwThreads) sts128(aQ + i * 16, make_uint4(0, 0, 0, 0));
   for (int i = tid; i < 32 * 256 / 4; i += kBwThreads) sts128(aCol + i * 16, make_uint4(0, 0, 0, 0));
-  for (int i = tid; i < N * N; i += kBwThreads) sts_f32(aBias + i * 4, bias[(long long)head * N * N + i]);
+  fill_bias_table(aBias, bias + (long long)head * N * N, N, tid, kBwThreads);
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], kBwThreads / 32);   // one arrival per worker warp
+    mbar_init(&bar[3], kBwThreads / 32);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -1750,95 +1898,120 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   constexpr uint32_t idesc_km = make_idesc_bf16(128, 64, false, true);
   const uint32_t my_tile = aQ + h * 16384;  // tile this thread fills in the gather (q, k, v, dO by role)
 
+
   float db[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) db[j] = 0.f;
   float dls = 0.f;
 
-  // ---- rows of a pair: token position, validity, mask region; raw 64 bytes of this role's tensor
+  // ---- rows of a pair: token position, validity, mask region by the thread that owns the row; the 64 bytes of this
+  // role's tensor are LOADED chunk-wise (lane l: 16-byte chunk l & 3 of the rows R0 + rmap(l >> 2) + 8 i — see the forward
+  // kernel: 8 rows x 64 contiguous bytes per warp instruction)
+  const int lane = tid & 31;
+  const int lc = lane & 3;
+  const int lrow8 = ((lane >> 2) & 1) * 4 + (lane >> 3);
+  const int crow0 = (warp & 3) * 32 + lrow8;
+  // the lanes that hold the chunks of THIS lane's own row (for the norm of roles 0, 1): row lane = rmap(j) + 8 i
+  const int own_i = lane >> 3;
+  const int own_src = (((lane & 7) >> 2) + ((lane & 3) << 1)) << 2;
   uint4 raw[4];
   long long nrow = 0;
   int nregion = 0;
   bool nvalid = false;
-  auto fetch = [&](int pair) {
-    const int w = pair * 2 + prob;
-    nvalid = t < N && pair < total_pairs && w < total_windows;
+  WindowWalker ww;
+  ww.init(g, grp * 2 + prob, groups * 2, t);
+  auto fetch = [&]() {
+    nvalid = t < N && ww.in_range(g);
     nrow = 0;
     nregion = 0;
-    if (nvalid) {
-      const int wx = w % g.nwx, wy = (w / g.nwx) % g.nwy, b = w / (g.nwx * g.nwy);
-      nrow = token_row(g, b, wy, wx, t, nregion);
-      const uint4* src = h < 3 ? reinterpret_cast<const uint4*>(qkv + nrow * 3 * g.C + h * g.C + head * kHd)
-                               : reinterpret_cast<const uint4*>(dout + nrow * g.C + head * kHd);
+    if (nvalid) nrow = ww.row(g, nregion);
+    ww.advance(g);
+    const int mine = nvalid ? static_cast<int>(nrow) : -1;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) raw[c] = __ldg(src + c);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) raw[c] = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < 4; ++i) {
+      const int gr = __shfl_sync(0xffffffffu, mine, lrow8 + 8 * i);
+      raw[i] = make_uint4(0, 0, 0, 0);
+      if (gr >= 0) {
+        const uint4* src = h < 3 ? reinterpret_cast<const uint4*>(qkv + (long long)gr * 3 * g.C + h * g.C + head * kHd)
+                                 : reinterpret_cast<const uint4*>(dout + (long long)gr * g.C + head * kHd);
+        raw[i] = __ldg(src + lc);
+      }
     }
   };
-  fetch(grp);
+  fetch();
 
   uint32_t phase = 0;
   for (int pair = grp; pair < total_pairs; pair += groups, phase ^= 1) {
     const long long row = nrow;
     const int region = nregion;
     const bool valid = nvalid;
-    float inv_norm = 0.f;  // 1 / |q| or 1 / |k| (roles 0, 1)
-    // ---- stage this role's operand row (q and k normalised)
+    float inv_norm = 0.f;  // 1 / |q| or 1 / |k| of this thread's own row (roles 0, 1)
+    // ---- stage this role's operand rows (q and k normalised; absent rows were fetched as zeros)
     if (h < 2) {
-      float ss = 0.f;
+      float inv[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t wv[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t wv[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+        float ss = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) ss = fmaf(bf16_lo(wv[e]), bf16_lo(wv[e]), fmaf(bf16_hi(wv[e]), bf16_hi(wv[e]), ss));
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        inv[i] = rsqrtf(fmaxf(ss, 1e-24f));   // 1 / max(|x|, 1e-12) (F.normalize), one MUFU
       }
-      inv_norm = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float v = __shfl_sync(0xffffffffu, inv[i], own_src);
+        if (own_i == i) inv_norm = v;
+      }
       // split-bf16 operands exactly as in the forward kernel: sQ = [q_hi | q_lo], sK = [k_hi | k_hi], sV = [v | k_lo]
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t wv[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+      for (int i = 0; i < 4; ++i) {
+        const int cr = crow0 + 8 * i;
+        const uint32_t wv[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
         uint32_t o[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float x0 = bf16_lo(wv[e]) * inv_norm, x1 = bf16_hi(wv[e]) * inv_norm;
+          const float x0 = bf16_lo(wv[e]) * inv[i], x1 = bf16_hi(wv[e]) * inv[i];
           o[e] = pack_bf16x2(x0, x1);
           lo[e] = pack_bf16x2(x0 - bf16_lo(o[e]), x1 - bf16_hi(o[e]));
         }
-        sts128(my_tile + sw128_off(r, c), make_uint4(o[0], o[1], o[2], o[3]));
+        sts128(my_tile + sw128_off(cr, lc), make_uint4(o[0], o[1], o[2], o[3]));
         if (h == 0) {
-          sts128(aQ + sw128_off(r, c + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          sts128(aQ + sw128_off(cr, lc + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
         } else {
-          sts128(aK + sw128_off(r, c + 4), make_uint4(o[0], o[1], o[2], o[3]));
-          sts128(aV + sw128_off(r, c + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          sts128(aK + sw128_off(cr, lc + 4), make_uint4(o[0], o[1], o[2], o[3]));
+          sts128(aV + sw128_off(cr, lc + 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
         }
       }
       if (h == 0) sts_f32(aReg + r * 4, __int_as_float(region));
     } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) sts128(my_tile + sw128_off(r, c), raw[c]);
+      for (int i = 0; i < 4; ++i) sts128(my_tile + sw128_off(crow0 + 8 * i, lc), raw[i]);
     }
     fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- round 1: S = Qhat Khat^T, dP = dO V^T
-    if (tid == 0) {
+    tc_fence_before();   // orders this thread's TMEM reads of the previous pair before the issuer's next UMMAs
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar[2]);
+    if (warp == 12 && elect_one()) {   // this warp waits for round 1 anyway: the blocking UMMA issue costs it nothing
+      mbar_wait(&bar[2], phase);
       tc_fence_after();
+      // round 1: S = Qhat Khat^T, dP = dO V^T
 #pragma unroll
       for (int k = 0; k < 4; ++k)   // [q_hi | q_lo] . [k_hi | k_hi]
         umma_bf16(tmem, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024),
                   idesc_kk, k);
 #pragma unroll
       for (int k = 0; k < 2; ++k)   // q_hi . k_lo
-        umma_bf16(tmem, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aV + (k + 2) * 32, 16, 1024),
-                  idesc_kk, 1u);
+        umma_bf16(tmem, make_smem_desc_sw128(aQ + k * 32, 16, 1024),
+                  make_smem_desc_sw128(aV + (k + 2) * 32, 16, 1024), idesc_kk, 1u);
 #pragma unroll
       for (int k = 0; k < 2; ++k)
-        umma_bf16(tmem + 128, make_smem_desc_sw128(aDO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024),
-                  idesc_kk, k);
+        umma_bf16(tmem + 128, make_smem_desc_sw128(aDO + k * 32, 16, 1024),
+                  make_smem_desc_sw128(aV + k * 32, 16, 1024), idesc_kk, k);
       umma_commit(&bar[0]);
     }
+    __syncwarp();
     mbar_wait(&bar[0], phase);
     tc_fence_after();
     // ---- softmax statistics of this quarter-row, merged across the four quarters
@@ -1847,27 +2020,17 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
     tmem_ld_32x32b_x16(tmem + 128 + lane_addr + prob * 64 + h * 16, graw);
     tmem_ld_wait();
     float e[16];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int key = h * 16 + j;
-      float sc = -INFINITY;
-      if (valid && key < N) {
-        const int kreg = __float_as_int(lds_f32(aReg + (prob * 64 + key) * 4));
-        sc = fmaf(__uint_as_float(sraw[j]), scale, lds_f32(aBias + (t * N + key) * 4)) + (kreg != region ? -100.f : 0.f);
-      }
-      e[j] = sc;
-      mx = fmaxf(mx, sc);
-    }
+    const float mx = logits_row<4>(sraw, e, aBias + (t * kBiasPitch + h * 16) * 4, aReg + (prob * 64 + h * 16) * 4, scale2,
+                                   region, g.shift != 0);
     float lsum = 0.f, dsum = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      e[j] = mx > -INFINITY ? __expf(e[j] - mx) : 0.f;   // exp(-inf) = 0 for the padded / foreign keys
+      e[j] = ex2_approx(e[j] - mx);   // 0 for the padded keys (-inf in the bias table)
       lsum += e[j];
       dsum = fmaf(e[j], __uint_as_float(graw[j]), dsum);
     }
     sts128(aX + (r * 4 + h) * 16, make_uint4(__float_as_uint(mx), __float_as_uint(lsum), __float_as_uint(dsum), 0u));
-    __syncthreads();
+    asm volatile("bar.sync 1, 512;" ::: "memory");   // workers only: the four quarters of every row have published
     float factor = 0.f, delta = 0.f;
     {
       uint4 x[4];
@@ -1879,15 +2042,14 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
       float l = 0.f, d = 0.f;
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        const float mq = __uint_as_float(x[q4].x);
-        const float f = mq > -INFINITY ? __expf(mq - m) : 0.f;
+        const float f = ex2_approx(__uint_as_float(x[q4].x) - m);
         l = fmaf(__uint_as_float(x[q4].y), f, l);
         d = fmaf(__uint_as_float(x[q4].z), f, d);
       }
       if (valid && l > 0.f) {
         const float inv = 1.f / l;
         delta = d * inv;
-        factor = mx > -INFINITY ? __expf(mx - m) * inv : 0.f;
+        factor = ex2_approx(mx - m) * inv;
       }
     }
     // ---- P and dS of this quarter-row: bf16 tiles for round 2, dbias / dlogit_scale partials in registers
@@ -1910,11 +2072,12 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
       }
     }
     fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- round 2
-    if (tid == 0) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar[3]);
+    if (warp == 12 && elect_one()) {
+      mbar_wait(&bar[3], phase);
       tc_fence_after();
+      // round 2
 #pragma unroll
       for (int k = 0; k < 8; ++k)   // dV = P^T dO: K = the 128 stacked query rows
         umma_bf16(tmem + 384, make_smem_desc_sw128(aP + k * 2048, 16384, 1024),
@@ -1924,14 +2087,16 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
         umma_bf16(tmem + 320, make_smem_desc_sw128(aDS + k * 2048, 16384, 1024),
                   make_smem_desc_sw128(aQ + k * 2048, 8192, 1024), idesc_mm, k);
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb)   // dQhat = dS Khat, block-diagonal halves
+      for (int kb = 0; kb < 2; ++kb) {   // dQhat = dS Khat, block-diagonal halves
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem + 256, make_smem_desc_sw128(aDS + kb * 16384 + k * 32, 16, 1024),
                     make_smem_desc_sw128(aK + kb * 8192 + k * 2048, 8192, 1024), idesc_km, (kb | k) != 0 ? 1u : 0u);
+      }
       umma_commit(&bar[1]);
     }
-    fetch(pair + groups);   // the next pair's rows travel while round 2 runs
+    __syncwarp();
+    fetch();   // the next pair's rows travel while round 2 runs
     mbar_wait(&bar[1], phase);
     tc_fence_after();
     if (h < 3) {
@@ -1968,8 +2133,13 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
         if (dcolsum != nullptr && h != 1) {
           const uint32_t slot = aCol + ((h >> 1) * 128 + r) * 4;
 #pragma unroll
-          for (int e2 = 0; e2 < 32; ++e2)
-            sts_f32(slot + e2 * 1024, lds_f32(slot + e2 * 1024) + __uint_as_float(acc[e2]) * mul);
+          for (int e0 = 0; e0 < 32; e0 += 8) {   // loads of a batch back to back: the asm statements keep their order
+            float cur[8];
+#pragma unroll
+            for (int e2 = 0; e2 < 8; ++e2) cur[e2] = lds_f32(slot + (e0 + e2) * 1024);
+#pragma unroll
+            for (int e2 = 0; e2 < 8; ++e2) sts_f32(slot + (e0 + e2) * 1024, fmaf(__uint_as_float(acc[e0 + e2]), mul, cur[e2]));
+          }
         }
         uint4* dst = reinterpret_cast<uint4*>(dqkv + row * 3 * g.C + h * g.C + head * kHd);
 #pragma unroll
@@ -1980,10 +2150,12 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
                               pack_bf16x2(__uint_as_float(acc[c * 8 + 6]) * mul, __uint_as_float(acc[c * 8 + 7]) * mul));
       }
     }
-    tc_fence_before();
-    __syncthreads();  // TMEM and every operand tile are free for the next pair
-    tc_fence_after();
+    // no CTA barrier: this thread has seen round 2 complete, so the operand tiles may be restaged; the lanes of a warp
+    // restage each other's rows, hence the warp barrier after the epilogue's reads of the own row
+    __syncwarp();
   }
+  tc_fence_before();
+  asm volatile("bar.sync 1, 512;" ::: "memory");   // workers: column-sum slots complete, TMEM reads done
   // ---- flush the on-chip accumulators: d bias[head][t][key], d logit_scale[head] (zero while the clamp is active)
   if (t < N) {
 #pragma unroll
@@ -2393,6 +2565,15 @@ static int attn_geom(AttnGeom* g, int B, int H, int W, int C, int heads, int ws,
   return TOK_OK;
 }
 
+static long long* g_attn_prof = nullptr;   // TOK_ATTN_PROFILE=1: phase clocks of the last forward launch (bring-up aid)
+int tok_debug_attn_profile(long long* host_out, int max_entries) {
+  if (!g_attn_prof || max_entries <= 0) return 0;
+  const int n = max_entries < 64 ? max_entries : 64;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+  if (cudaMemcpy(host_out, g_attn_prof, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return n;
+}
+
 int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift, const void* qkv,
                         const float* logit_scale, const float* bias, void* out, void* stream) {
   AttnGeom g;
@@ -2418,7 +2599,9 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
   if (!use_cuda_cores && !use_v1 && (C % 8) == 0) {
     static bool configured2 = false;
     if (!configured2) {
-      cudaError_t e = cudaFuncSetAttribute(window_attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem);
+      cudaError_t e = cudaFuncSetAttribute(window_attn_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(window_attn_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTc2Smem);
       if (e != cudaSuccess) return set_error(TOK_ERR_CUDA, "window_attn_fwd: %s", cudaGetErrorString(e));
       configured2 = true;
     }
@@ -2426,8 +2609,19 @@ int tok_window_attn_fwd(int B, int H, int W, int C, int heads, int ws, int shift
     int groups = (148 * 2) / heads;   // two CTAs per SM (shared memory, registers); one more CTA would be a second wave
     if (groups < 1) groups = 1;
     if (groups > pairs) groups = pairs;
-    (void)launch_pdl(window_attn_fwd_tc2_kernel, dim3((unsigned)(groups * heads)), dim3(kTc2Threads), kTc2Smem, (cudaStream_t)stream, 
-        g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out);
+    static const bool want_prof = getenv("TOK_ATTN_PROFILE") != nullptr;
+    if (want_prof && !g_attn_prof) {
+      cudaMalloc(&g_attn_prof, 64 * sizeof(long long));
+      cudaMemset(g_attn_prof, 0, 64 * sizeof(long long));
+    }
+    if (want_prof)
+      (void)launch_pdl(window_attn_fwd_tc2_kernel<true>, dim3((unsigned)(groups * heads)), dim3(kTc2Threads + 32), kTc2Smem,
+                       (cudaStream_t)stream, g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out,
+                       g_attn_prof, getenv("TOK_ATTN_DBG") ? atoi(getenv("TOK_ATTN_DBG")) : 0);
+    else
+      (void)launch_pdl(window_attn_fwd_tc2_kernel<false>, dim3((unsigned)(groups * heads)), dim3(kTc2Threads + 32), kTc2Smem,
+                       (cudaStream_t)stream, g, groups, (const __nv_bfloat16*)qkv, logit_scale, bias, (__nv_bfloat16*)out,
+                       (long long*)nullptr, 0);
     TOK_CHECK_LAUNCH("window_attn_fwd_tc2");
     return TOK_OK;
   }
