@@ -1422,7 +1422,7 @@ window_attn_fwd_tc2_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restri
   const uint32_t tmem_o = tmem_s + 128;    // O: columns [128, 192)
   const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
-  constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+  constexpr uint32_t idesc_o = make_idesc_bf16(128, 32, false, true);   // N = the 32 head dims: the k_lo half of the V rows is not fetched
 
   // ---- warp 8: the UMMA issuer.  r5: issued from a worker warp, the two UMMA chains blocked that warp for their whole
   // execution (~1300 clocks per pair: the shared-memory operand fetch of the 14 instructions) and every other warp then
@@ -1894,8 +1894,8 @@ window_attn_bwd_tc_kernel(AttnGeom g, int groups, const __nv_bfloat16* __restric
   const uint32_t tmem = *tmem_slot;  // S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
   const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
   constexpr uint32_t idesc_kk = make_idesc_bf16(128, 128, false, false);
-  constexpr uint32_t idesc_mm = make_idesc_bf16(128, 64, true, true);
-  constexpr uint32_t idesc_km = make_idesc_bf16(128, 64, false, true);
+  constexpr uint32_t idesc_mm = make_idesc_bf16(128, 32, true, true);    // N = 32: only the data half of the 128-byte B rows is fetched
+  constexpr uint32_t idesc_km = make_idesc_bf16(128, 32, false, true);
   const uint32_t my_tile = aQ + h * 16384;  // tile this thread fills in the gather (q, k, v, dO by role)
 
 
