@@ -103,6 +103,12 @@ int tok_linear_dgrad(int m, int n, int k, const void* dy, const void* w, void* d
 /* dx[m,k] = sum_n dy[m,n] * w[n,k] + addend[m,k]: the residual-branch gradient of a transformer block
  * (x + f(x), timm SwinTransformerBlock) joins the branch gradient in the GEMM epilogue instead of a separate add pass. */
 int tok_linear_dgrad_add(int m, int n, int k, const void* dy, const void* w, const void* addend, void* dx, void* stream);
+/* dx[m,k] = gelu'(h[m,k]) * bf16(sum_n dy[m,n] * w[n,k]); colsum[k] += sum_m dx[m,k] (optional): the backward of
+ * timm Mlp's `fc2(act(h))` with respect to h in one launch — the exact-erf GELU derivative is applied in the dgrad epilogue,
+ * and the column sums are the bias gradient of the layer that produced h (fc1).  Same rounding points as
+ * tok_linear_dgrad followed by tok_gelu_bwd. */
+int tok_linear_dgrad_gelu(int m, int n, int k, const void* dy, const void* w, const void* h, void* dx, float* colsum,
+                          void* stream);
 /* dw[n,k] += sum_m dy[m,n] * x[m,k]  (fp32, atomically accumulated) */
 int tok_linear_wgrad(int m, int n, int k, const void* x, const void* dy, float* dw, void* stream);
 

@@ -57,6 +57,47 @@ def test_gelu(rows, c):
         assert rel_err(bias.grad, xo.grad.sum(0)) < 1e-2
 
 
+@pytest.mark.parametrize('m,hidden,out', [(300, 384, 96), (1000, 768, 192), (77, 40, 24), (4096, 3072, 768)])
+def test_mlp_tail_fused_gelu_backward(m, hidden, out):
+    """fc2(GELU(h)) (timm Mlp, built by torchok/models/backbones/swin.py:71-81): the opt-in fused node — gelu' in the
+    epilogue of fc2's data-gradient GEMM, tok_linear_dgrad_gelu (measured slower than the two passes, so off by default:
+    kernels.py) — against fp32 autograd (1e-2 of the maximum) and against the two-launch sequence it replaces,
+    tok_linear_dgrad + tok_gelu_bwd (same rounding points: bit-identical dh)."""
+    from torchok_b200 import kernels as K
+    from torchok_b200._lib import lib
+    from torchok_b200.kernels import _p, _st
+    torch.manual_seed(hidden + out)
+    h = _bf(torch.randn(m, hidden) * 1.5)
+    w = _bf(torch.randn(out, hidden) / hidden ** 0.5)
+    b = torch.randn(out) * 0.1
+    g = _bf(torch.randn(m, out))
+    ho, wo, bo = (t.clone().requires_grad_(True) for t in (h, w, b))
+    (F.linear(F.gelu(ho), wo, bo) * g).sum().backward()
+    hm = h.cuda().to(torch.bfloat16).requires_grad_(True)
+    wm, bm = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    fc1_bias = torch.zeros(hidden, device='cuda', requires_grad=True)
+    y = K.GeluLinearFn.apply(hm, wm, bm, fc1_bias, False)   # the opt-in node (TOK_GELU_DGRAD=1), called directly
+    (y.float() * g.cuda()).sum().backward()
+    assert rel_err(y, F.linear(F.gelu(h), w, b)) < 1e-2
+    assert rel_err(hm.grad, ho.grad) < 1e-2
+    assert rel_err(wm.grad, wo.grad) < 1e-2 and rel_err(bm.grad, bo.grad) < 1e-2
+    assert rel_err(fc1_bias.grad, ho.grad.sum(0)) < 1e-2
+    # the two launches it replaces
+    L = lib()
+    gb, wb, hb = g.cuda().to(torch.bfloat16), w.cuda().to(torch.bfloat16), h.cuda().to(torch.bfloat16)
+    da = torch.empty(m, hidden, device='cuda', dtype=torch.bfloat16)
+    L.tok_linear_dgrad(m, out, hidden, _p(gb), _p(wb), _p(da), _st())
+    dh2 = torch.empty_like(da)
+    L.tok_gelu_bwd(da.numel(), hidden, _p(hb), _p(da), _p(dh2), None, _st())
+    dh1 = torch.full_like(da, float('nan'))
+    col = torch.zeros(hidden, device='cuda')
+    L.tok_linear_dgrad_gelu(m, out, hidden, _p(gb), _p(wb), _p(hb), _p(dh1), _p(col), _st())
+    torch.cuda.synchronize()
+    assert torch.equal(dh1, dh2)
+    ref = dh2.float().sum(0)
+    assert float((col - ref).abs().max()) <= 1e-3 * float(ref.abs().max()) + 1e-4
+
+
 @pytest.mark.parametrize('rows,c', [(70, 96), (33, 384), (9, 1024)])
 def test_layernorm_colsum(rows, c):
     """LayerNorm backward also accumulates the column sums of dx into the bias of the linear layer feeding it."""

@@ -63,6 +63,7 @@ _SIGS = {
     'tok_patch_embed_fwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_patch_embed_bwd': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_patch_merge': (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    'tok_linear_dgrad_gelu': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tok_linear_wgrad': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     'tok_stem_geometry': (None, [_i, _i, _pi, _pi, _pi, _pi]),
     'tok_stem_pack_input': (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -186,7 +186,8 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
                       cudaStream_t st) {
   CUtensorMap tmB;
   static const bool v1 = getenv("TOK_CONV_V1") != nullptr;  // bring-up aid: the one-tile-per-CTA kernel
-  const int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N, (long long)src.R * src.S * ac, src.im2col && src.R * src.S == 1);
+  int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N, (long long)src.R * src.S * ac, src.im2col && src.R * src.S == 1);
+  if (p.addend_mode == 1 && !v1) bn = 128;   // the GELU-backward epilogue exists for the 128-wide tile only
   // Opt-in CTA-pair kernel (unverified on hardware as a conv; the default path is untouched unless the variable is
   // set): a 256x256 tile per pair of SMs, each CTA fetches half of the weight tile, hence the 128-row boxes.
   static const bool pair_env = getenv("TOK_CONV_2CTA") != nullptr;
@@ -215,7 +216,9 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
     if (mg_env != 0 && strips > 1 && a_bytes > (24LL << 20)) {
       long long k = mg_env > 0 ? mg_env : (16LL << 20) / (148LL * 128 * ac * 2);
       if (k < 1) k = 1;
-      if (p.col_sum == nullptr || mg_env > 0) p.m_group = (int)(148 * k);
+      // (the fused GELU-backward dgrad also carries sums, but its A operand — 154 MB at Swin stage 1, read once per
+      // 128-column strip of the 4x wider output — is exactly the case the grouping is for)
+      if (p.col_sum == nullptr || mg_env > 0 || (p.addend_mode == 1 && k >= 2)) p.m_group = (int)(148 * k);
     }
   }
   // TOK_CONV_PROFILE=1: the epilogue phase counters of every launch land in a static device buffer which
@@ -718,6 +721,38 @@ int tok_linear_dgrad_add(int m, int n, int k, const void* dy, const void* w, con
   p.out = static_cast<__nv_bfloat16*>(dx);
   p.ldo = k;
   p.addend = static_cast<const __nv_bfloat16*>(addend);
+  return run_fwd(dy, 1, 1, m, n, flat_src(), m, w, n, k, true, k, 0, p, static_cast<cudaStream_t>(stream));
+}
+
+int tok_linear_dgrad_gelu(int m, int n, int k, const void* dy, const void* w, const void* h, void* dx, float* colsum,
+                          void* stream) {
+  if (m <= 0 || n <= 0 || k <= 0 || (n % 8) || (k % 8)) return set_error(TOK_ERR_INVALID, "linear: n and k must be positive multiples of 8");
+  if (h == nullptr) return set_error(TOK_ERR_INVALID, "linear_dgrad_gelu: the GELU input is required");
+  static const bool v1 = getenv("TOK_CONV_V1") != nullptr;
+  if (v1) return set_error(TOK_ERR_INVALID, "linear_dgrad_gelu: persistent kernel only (TOK_CONV_V1 is set)");
+  ConvFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = static_cast<__nv_bfloat16*>(dx);
+  p.ldo = k;
+  p.addend = static_cast<const __nv_bfloat16*>(h);
+  p.addend_mode = 1;
+  if (colsum != nullptr) {
+    // the kernel's column statistics come as (sum, sum of squares); the squares land in a scratch row nobody reads
+    static float* sq_scratch = nullptr;
+    static int sq_cap = 0;
+    if (sq_cap < k) {
+      if (sq_scratch) cudaFree(sq_scratch);
+      sq_cap = k < 8192 ? 8192 : k;
+      if (cudaMalloc(&sq_scratch, sq_cap * sizeof(float)) != cudaSuccess) {
+        sq_scratch = nullptr;
+        sq_cap = 0;
+        return set_error(TOK_ERR_CUDA, "linear_dgrad_gelu: scratch allocation failed");
+      }
+      cudaMemsetAsync(sq_scratch, 0, sq_cap * sizeof(float), static_cast<cudaStream_t>(stream));
+    }
+    p.col_sum = colsum;
+    p.col_sqsum = sq_scratch;
+  }
   return run_fwd(dy, 1, 1, m, n, flat_src(), m, w, n, k, true, k, 0, p, static_cast<cudaStream_t>(stream));
 }
 

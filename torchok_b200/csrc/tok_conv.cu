@@ -259,7 +259,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 // while the CTA walks the m-tiles of that n-tile; the ring then carries the pixel operand only.  ncu r2
 // (profiles/r2_conv3x3_c64_kernel.md): the short-reduction layers are bound by what an SM can ingest (~27-40 B/clk), and
 // re-fetching the 8-32 KB weight tile with every k-block was a third to a half of it.
-template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS, int BRES>
+template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS, int BRES, int EPI = 0>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
@@ -715,6 +715,17 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const uint4 a = lds128(abuf_s + blk_off + chunk * 16);
             const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
             const uint32_t mb = mbits[cc] >> (g * 8);   // byte g of the word: channels g*8 .. g*8+7 of this chunk
+            if (EPI == 1) {
+              // GELU backward: the "addend" tile is the GELU input h; out = bf16(dgrad) * gelu'(h), the product the separate
+              // tok_gelu_bwd pass formed from the stored bf16 gradient (same rounding points)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t r2 = pack_bf16x2(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                v[g * 8 + 2 * e] = bf16_lo(r2) * gelu_grad(bf16_lo(aw[e]));
+                v[g * 8 + 2 * e + 1] = bf16_hi(r2) * gelu_grad(bf16_hi(aw[e]));
+              }
+              continue;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               v[g * 8 + 2 * e] += (mb >> (2 * e)) & 1u ? bf16_lo(aw[e]) : 0.f;
@@ -1017,14 +1028,14 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS, int BRES = 0>
+template <int BN, int STAGES, bool B_MN, int CBUFS, int ABUFS, int BRES = 0, int EPI = 0>
 static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                     const CUtensorMap& tmD, const ConvFwdParams& p, cudaStream_t st) {
   constexpr int smem = conv_persist_smem_bytes<BN, STAGES, CBUFS, ABUFS, BRES>();
   static_assert(smem <= 232448, "persistent conv kernel exceeds the 227 KB shared-memory limit");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS, BRES>,
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS, BRES, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -1033,7 +1044,7 @@ static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& t
   const int n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  return launch_pdl(conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS, BRES>, dim3(grid), dim3(kPersistThreads), smem,
+  return launch_pdl(conv_fwd_persist_kernel<BN, STAGES, B_MN, CBUFS, ABUFS, BRES, EPI>, dim3(grid), dim3(kPersistThreads), smem,
                     st, tmA, tmB, tmC, tmD, p);
 }
 
@@ -1045,6 +1056,10 @@ cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& t
                                     const CUtensorMap& tmD, const ConvFwdParams& p, int bn, bool b_mn,
                                     cudaStream_t st) {
   const bool add = p.addend != nullptr && !p.scatter;
+  if (p.addend_mode == 1) {   // GELU backward in the epilogue: one instantiation (MN-major weights, 128-wide tile)
+    if (!(add && bn == 128 && b_mn)) return cudaErrorInvalidValue;
+    return launch_persist_t<128, 3, true, 2, 2, 0, 1>(tmA, tmB, tmC, tmD, p, st);
+  }
   // weight slab of one n-tile (all taps x channel blocks): resident when it fits next to the ring (TOK_CONV_BRES=0: off)
   static const bool bres_on = !(getenv("TOK_CONV_BRES") && atoi(getenv("TOK_CONV_BRES")) == 0);
   const long long num_kb = (long long)p.a.R * p.a.S * ((p.Cin + kBlockK - 1) / kBlockK);

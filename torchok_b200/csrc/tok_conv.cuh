@@ -88,6 +88,9 @@ struct ConvFwdParams {
   // bring-up aid (TOK_CONV_PROFILE=1): per-CTA cycle counts of the epilogue phases, 8 slots per CTA
   long long* prof;
   FwdFin fin;   // persistent kernel only
+  // 0: out += addend.  1: out = bf16(acc) * gelu'(addend) — the GELU backward folded into the dgrad of the layer behind it
+  // (timm Mlp: fc1 -> GELU -> fc2; persistent kernel, 128-wide tile with addend buffers only)
+  int addend_mode;
   int m_group;       // persistent kernel tile order: m-tiles per group (0 = whole strips; tok_conv.cu: decode_tile)
   int defer_stats;   // persistent kernel, two staging buffers: statistics pass of tile t inside iteration t + 1
 };

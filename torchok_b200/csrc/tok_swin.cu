@@ -346,36 +346,7 @@ inline bool ln_vec_shape(int C, int* G, int* CH) {
   return false;
 }
 
-// ---- GELU (exact, erf) ---------------------------------------------------------------------------------------------
-// erf through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution): one reciprocal, one exp2 and
-// five FMAs instead of the ~30-instruction erff, which made these passes compute-bound.  exp(-v^2/2) is shared
-// between erf(v / sqrt 2) and the Gaussian density of the derivative.
-// With q = 0.5 * poly(t) * t (the 0.5 folded into the coefficients) and ex = exp(-v^2/2):
-//   Phi(v) = 1 - q ex (v >= 0),  q ex (v < 0);   gelu(v) = v Phi(v) = max(v, 0) - |v| q ex;   gelu'(v) = Phi(v) + v phi(v).
-// 12 FP32 operations + 2 MUFU per element: at ~19 the passes were bound by the FP32 pipe, not by HBM.
-__device__ __forceinline__ void gelu_parts(float v, float& av, float& q, float& ex) {
-  av = fabsf(v);
-  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678f, av, 1.f));
-  const float ap = av * 0.8493218f;   // sqrt(log2(e) / 2): exp(-v^2/2) = 2^(-ap^2)
-  ex = exp2f(-ap * ap);
-  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-  poly = fmaf(poly, t, 0.5f * 1.421413741f);
-  poly = fmaf(poly, t, 0.5f * -0.284496736f);
-  poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  q = poly * t;
-}
-__device__ __forceinline__ float gelu_value(float v) {
-  float av, q, ex;
-  gelu_parts(v, av, q, ex);
-  return fmaf(-(av * q), ex, fmaxf(v, 0.f));
-}
-__device__ __forceinline__ float gelu_grad(float v) {
-  float av, q, ex;
-  gelu_parts(v, av, q, ex);
-  const float qe = q * ex;
-  const float cdf = v >= 0.f ? 1.f - qe : qe;
-  return fmaf(v * 0.39894228f, ex, cdf);
-}
+// ---- GELU (exact, erf): gelu_parts / gelu_value / gelu_grad live in tok_ptx.cuh (shared with the linear-dgrad epilogue)
 __global__ void gelu_fwd_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloat162* __restrict__ y, long long n2) {
   pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
   pdl_launch();

@@ -1247,6 +1247,82 @@ def gelu(x, colsum_param=None):
     return GeluFn.apply(x, colsum_param)
 
 
+# timm Mlp tail `fc2(act(h))` as ONE autograd node: the forward is the GELU pass + the fc2 GEMM as before; the backward
+# applies gelu'(h) in the epilogue of fc2's data-gradient GEMM (tok_linear_dgrad_gelu) instead of writing the gradient of
+# the activation, reading it back together with h and writing the product (three passes over the widest tensor of the
+# block).  MEASURED SLOWER (r5, Swin-T bs256, same box): the 12 fused launches take 4.88 ms against 1.29 ms (plain dgrad)
+# + 1.97 ms (tok_gelu_bwd) for the launches they replace, step 26.6 vs 25.2 ms — the derivative costs ~14 instructions
+# and 2 MUFU per element, and in the GEMM epilogue only the 8 epilogue warps of the CTA (2 per scheduler) execute it,
+# while the stand-alone pass spreads the same work over 64 warps per SM and runs at 4.2 TB/s.  So the default is the
+# two-node form; TOK_GELU_DGRAD=1 selects the fused node (kept correct by tests/test_swin_gpu.py).
+_GELU_DGRAD = os.environ.get('TOK_GELU_DGRAD', '0') == '1'
+
+
+class GeluLinearFn(torch.autograd.Function):
+    """y = Linear(GELU(h)): h (M, K) bf16 = the fc1 output, weight (N, K) fp32 master, bias (N,) fp32.
+    `colsum_param`: fc1's bias — its gradient is the column sum of dh, accumulated by the fused kernel.
+    `bias_grad_external`: as in LinearFn (the LayerNorm behind fc2 accumulates fc2's bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, colsum_param, bias_grad_external):
+        require_cuda(h, 'gelu-linear input')
+        m, k = h.shape
+        n = weight.shape[0]
+        h = h.to(BF16).contiguous()
+        a = torch.empty_like(h)
+        L = lib()
+        st = _st()
+        L.tok_gelu_fwd(h.numel(), _p(h), _p(a), st)
+        w = shadow_of(weight)
+        b = bias.detach().float() if bias is not None else None
+        y = torch.empty((m, n), dtype=BF16, device=h.device)
+        L.tok_linear_fwd(m, n, k, _p(a), _p(w), _p(b), _p(y), st)
+        ctx.save_for_backward(h, a, w)
+        ctx.params = (weight, bias, colsum_param)
+        ctx.bias_grad_external = bool(bias_grad_external)
+        ctx.dims = (m, n, k)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        h, a, w = ctx.saved_tensors
+        weight, bias, cp = ctx.params
+        m, n, k = ctx.dims
+        L = lib()
+        st = _st()
+        g = g.to(BF16).contiguous()
+        dh = None
+        if ctx.needs_input_grad[0]:
+            dh = torch.empty((m, k), dtype=BF16, device=g.device)
+            gx = grad_buffer(cp) if cp is not None and cp.requires_grad else None
+            L.tok_linear_dgrad_gelu(m, n, k, _p(g), _p(w), _p(h), _p(dh), _p(gx), st)
+        if weight.requires_grad:
+            gw = grad_buffer(weight)
+            wgrad_async((a, g, gw), lambda s: L.tok_linear_wgrad(m, n, k, _p(a), _p(g), _p(gw), s))
+        if bias is not None and bias.requires_grad and not ctx.bias_grad_external:
+            acc = torch.zeros((2, n), dtype=F32, device=g.device)
+            L.tok_bn_bwd_reduce(m, n, _p(g), None, None, _p(g), _p(acc[0]), _p(acc[1]), st)
+            grad_buffer(bias).add_(acc[0])
+        grad_ready(weight)
+        if bias is not None:
+            grad_ready(bias)
+        return dh, None, None, None, None
+
+
+def gelu_dgrad_fused(hidden, out_features):
+    """True when `gelu_linear` runs as the fused node (then the bias gradient of the layer in front of the GELU always
+    comes out of its backward, whatever the hidden width)."""
+    return _GELU_DGRAD and hidden % 8 == 0 and out_features % 8 == 0
+
+
+def gelu_linear(h, weight, bias, colsum_param=None, bias_grad_external=False):
+    """fc2(GELU(h)) with the fused backward when the shapes allow it (both widths multiples of 8)."""
+    n, k = weight.shape
+    if gelu_dgrad_fused(k, n) and h.dim() == 2:
+        return GeluLinearFn.apply(h, weight, bias, colsum_param, bias_grad_external)
+    return linear(gelu(h, colsum_param), weight, bias, bias_grad_external)
+
+
 class WindowAttnFn(torch.autograd.Function):
     """timm WindowAttention core on the (B*H*W, 3C) qkv matrix: cosine attention + logit scale + bias + shift mask ->
     (B*H*W, C).  `bias` (heads, N, N) fp32 is an autograd input (its gradient flows back to the cpb MLP);

@@ -55,9 +55,11 @@ class Mlp(nn.Module):
     def forward(self, x, fc2_bias_external=False, res_link=None):
         # the bias gradients of fc1 / fc2 are the column sums of the GELU / LayerNorm input gradients: those backward
         # kernels accumulate them on the way instead of a separate pass over dy per linear layer
-        ext1 = self.fc1.bias is not None and K.gelu_fuses_colsum(self.fc1.out_features)
-        h = K.gelu(self.fc1(x, ext1, res_link), self.fc1.bias if ext1 else None)
-        return self.fc2(h, fc2_bias_external)
+        # ... and the GELU backward itself runs in the epilogue of fc2's data-gradient GEMM (K.gelu_linear)
+        hid = self.fc1.out_features
+        ext1 = self.fc1.bias is not None and (K.gelu_dgrad_fused(hid, self.fc2.out_features) or K.gelu_fuses_colsum(hid))
+        h = self.fc1(x, ext1, res_link)
+        return K.gelu_linear(h, self.fc2.weight, self.fc2.bias, self.fc1.bias if ext1 else None, fc2_bias_external)
 
 
 class WindowAttention(nn.Module):
