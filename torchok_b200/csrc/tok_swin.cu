@@ -2531,6 +2531,7 @@ static int attn_geom(AttnGeom* g, int B, int H, int W, int C, int heads, int ws,
   if (C != heads * kHd) return set_error(TOK_ERR_INVALID, "window_attn: head dimension must be 32 (C=%d heads=%d)", C, heads);
   if (ws * ws > kBigMaxN) return set_error(TOK_ERR_INVALID, "window_attn: window %d exceeds the 24x24 limit", ws);
   if ((H % ws) || (W % ws) || shift < 0 || shift >= ws) return set_error(TOK_ERR_INVALID, "window_attn: H, W must be multiples of the window; 0 <= shift < window");
+  if ((long long)B * H * W >= (1LL << 31)) return set_error(TOK_ERR_INVALID, "window_attn: B*H*W must be below 2^31 (token rows are exchanged as 32-bit indices)");
   g->B = B; g->H = H; g->W = W; g->C = C; g->heads = heads; g->ws = ws; g->shift = shift;
   g->nwy = H / ws; g->nwx = W / ws;
   return TOK_OK;
