@@ -286,7 +286,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint64_t* wres_full_bar = addend_empty_bar + 2; // [1] slab landed
   uint64_t* wres_empty_bar = wres_full_bar + 1;   // [1] every UMMA of the slab's n-tile has retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_empty_bar + 1);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);  // [sum | sqsum][BN], one owner lane per slot
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);  // [sum | sqsum][BN], one owner lane per slot; 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -477,6 +477,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int ew = warp - 2;                // 0..7: 16-byte chunk owned in the statistics pass
     const int row = q * 32 + lane;
     const bool want_stats = p.col_sum != nullptr;
+    const bool bias_smem = p.bias != nullptr && !want_stats && !p.scatter;   // bias table in the statistics slots
     const bool leader = threadIdx.x == 64;
     int li = 0;
     int prev_n0 = -1;
@@ -586,6 +587,11 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
       }
       if (!kDefer && want_stats && prev_n0 >= 0 && prev_n0 != n0) flush_stats(prev_n0);  // rare: a finished n_tile
+      if (bias_smem && prev_n0 != n0) {
+        // new strip: its bias into the (otherwise unused) statistics slots; every reader of the old values is behind
+        // barrier (C) of the previous tile, barrier (B) below publishes the new ones
+        for (int i = threadIdx.x - 64; i < BN; i += 32 * kEpiWarps) s_stat[i] = n0 + i < p.N ? __ldg(p.bias + n0 + i) : 0.f;
+      }
       prev_n0 = n0;
       epi_bar();  // (B) staging buffer free for this tile's writers; statistics slots consistent
       TOK_PROF(0)
@@ -687,7 +693,17 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[cc][j]);
-        if (p.bias != nullptr) {
+        if (bias_smem) {
+          // this strip's bias from shared memory (filled at the strip change below): the 8 LDG.128 per chunk that used to
+          // stand here sat behind tcgen05.wait::ld on the epilogue's critical path — +38 % on the Swin stage-1 qkv
+          // projection, +25 % on fc1 (r5: scripts/linear_shapes.py, bias vs no bias)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 b4 = lds128(s_stat_s + (c * 32 + 4 * j) * 4);
+            fadd2(v[4 * j], v[4 * j + 1], __uint_as_float(b4.x), __uint_as_float(b4.y));
+            fadd2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(b4.z), __uint_as_float(b4.w));
+          }
+        } else if (p.bias != nullptr) {
           if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
             // 8 x LDG.128 instead of 32 scalar loads per thread and chunk (the linear layers of the Swin blocks spent
             // as many instructions fetching the bias as converting the tile)
@@ -695,10 +711,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b4 = __ldg(bp + j);
-              v[4 * j] += b4.x;
-              v[4 * j + 1] += b4.y;
-              v[4 * j + 2] += b4.z;
-              v[4 * j + 3] += b4.w;
+              fadd2(v[4 * j], v[4 * j + 1], b4.x, b4.y);   // packed fp32 adds: the bias costs the short-K linear layers
+              fadd2(v[4 * j + 2], v[4 * j + 3], b4.z, b4.w);   // 20-27 % of their time on the 8 epilogue warps (r5)
             }
           } else {
 #pragma unroll
