@@ -1,3 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_swin_gpu.py tests/test_heads_gpu.py tests/test_big_conv_gpu.py -m gpu -q -x 2>&1 | tail -3
-PYTHONPATH=. timeout 300 python scripts/linear_shapes.py 2>&1 | tail -16 | cut -c1-100
+PYTHONPATH=. timeout 300 python scripts/linear_shapes.py 2>&1 | tail -8 | cut -c1-130
+timeout 400 python bench.py --workload swin_t --skip-cpu --skip-torch 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('swin_t', d['ms_per_step'], d['value'], d['clocks'])"
+timeout 400 python bench.py --workload resnet50 --skip-cpu --skip-torch 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('resnet50', d['ms_per_step'], d['value'], d['clocks'])"

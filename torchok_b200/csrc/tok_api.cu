@@ -158,8 +158,11 @@ static int pick_bn_persist(long long M, int N, long long k_total, bool gather_a)
   // staging (and addend) tiles so stores drain behind the next tile, which the 128x256 tile has no room for.  Exception:
   // a strided (im2col-gathered) A operand is expensive to fetch, and the wider tile fetches it half as often
   // (measured r2, 1x1 s2 256->512 @56: 91 us vs 109 us).
+  // r5 (scripts/linear_shapes.py, Swin stage 3: M = 50176, K = 384): with N a multiple of 256 the wide tile already wins at
+  // K = 384 (fc1 forward 95 -> 89 us, fc2 dgrad 100 -> 78 us), so such layers go on to the wave model below; ragged N at
+  // that depth does not (qkv N = 1152: 72 -> 76 us).
   static const long long small_k = getenv("TOK_CONV_SMALLK") ? atoll(getenv("TOK_CONV_SMALLK")) : 512;
-  if (k_total < small_k && !gather_a) return 128;
+  if (k_total < small_k && !gather_a && !(k_total >= 384 && N % 256 == 0)) return 128;
   // Waves of the persistent grid x relative tile time.  A 128x256 tile moves 1.5x the operand bytes of a 128x128 tile for
   // 2x the MACs and measures ~1.25x its time on the long reductions (r2 selftest: 3x3 512->512 @7, 196 tiles in 2 waves
   // = 69 us against 392 tiles in 3 waves = 95 us).
