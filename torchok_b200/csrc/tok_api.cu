@@ -190,6 +190,15 @@ static int run_fwd_tm(const CUtensorMap& tmA, int ac, const PixelSrc& src, long 
   CUtensorMap tmB;
   static const bool v1 = getenv("TOK_CONV_V1") != nullptr;  // bring-up aid: the one-tile-per-CTA kernel
   int bn = v1 ? pick_bn(N) : pick_bn_persist(M, N, (long long)src.R * src.S * ac, src.im2col && src.R * src.S == 1);
+  {
+    // 192-wide strips when they tile N with no more padding than 128-wide ones and N is not a multiple of 256: plain
+    // GEMM launches only (no BatchNorm sums, no addend, no scatter) — the transformer linear layers.  TOK_CONV_BN192=0: off.
+    static const bool bn192 = !(getenv("TOK_CONV_BN192") && atoi(getenv("TOK_CONV_BN192")) == 0);
+    static const bool forced = getenv("TOK_CONV_BN") != nullptr;
+    if (bn192 && !forced && !v1 && N > 128 && (N % 256) != 0 && p.col_sum == nullptr && p.addend == nullptr && !p.scatter &&
+        ((N + 191) / 192) * 192 <= ((N + 127) / 128) * 128)
+      bn = 192;
+  }
   if (p.addend_mode == 1 && !v1) bn = 128;   // the GELU-backward epilogue exists for the 128-wide tile only
   // Opt-in CTA-pair kernel (unverified on hardware as a conv; the default path is untouched unless the variable is
   // set): a 256x256 tile per pair of SMs, each CTA fetches half of the weight tile, hence the 128-row boxes.

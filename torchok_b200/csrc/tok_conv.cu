@@ -272,6 +272,8 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   constexpr int kBlocks = BN / 64;              // 64-column staging blocks per tile
   constexpr int kChunks = BN / 32;              // 32-column TMEM chunks per tile
   constexpr int kChunksPerWarp = kChunks / 2;
+  constexpr int kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // allocations are powers of two
+  static_assert(BN % 64 == 0 && 2 * BN <= 512, "tile width");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem + STAGES * kStage;     // resident weight slab (BRES bytes)
@@ -334,7 +336,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   if (warp >= 2) {
@@ -660,7 +662,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       TOK_PROF(2)
       // TMEM loads are issued two at a time before the wait (the chunks are independent; two keeps the register
       // footprint of the 256-column tile inside the 168-register budget of a 320-thread CTA)
-      constexpr int kInFlight = kChunksPerWarp < 2 ? kChunksPerWarp : 2;
+      constexpr int kInFlight = (kChunksPerWarp % 2) ? 1 : 2;   // the 192-wide tile has three chunks per warp
 #pragma unroll 1
       for (int c0 = 0; c0 < kChunksPerWarp; c0 += kInFlight) {
       uint32_t r[kInFlight][32];
@@ -864,7 +866,7 @@ conv_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1116,6 +1118,12 @@ cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& t
   if (bn == 256)
     return b_mn ? launch_persist_t<256, 3, true, 1, 0>(tmA, tmB, tmC, tmD, p, st)
                 : launch_persist_t<256, 3, false, 1, 0>(tmA, tmB, tmC, tmD, p, st);
+  // 128x192: the Swin widths are multiples of 96, so 128- and 256-wide strips leave a ragged one (N = 288, 576, 1152) or
+  // run the long reductions at the 128-wide tile's operand-fetch cap (N = 384).  3 x 40 KB ring, 2 x 48 KB staging.
+  // Launches without an addend only.
+  if (bn == 192 && !add)
+    return b_mn ? launch_persist_t<192, 3, true, 2, 0>(tmA, tmB, tmC, tmD, p, st)
+                : launch_persist_t<192, 3, false, 2, 0>(tmA, tmB, tmC, tmD, p, st);
   return cudaErrorInvalidValue;
 }
 
