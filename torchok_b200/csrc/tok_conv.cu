@@ -1068,6 +1068,7 @@ static cudaError_t launch_persist_t(const CUtensorMap& tmA, const CUtensorMap& t
 //   BN  64: 6 x 24 KB ring, 2 staging, 2 addend (when the launch has an addend)          = 208 KB
 //   BN 128: 4 x 32 KB ring, 2 staging            | 3 x 32 KB ring, 2 staging, 2 addend   = 192 / 224 KB
 //   BN 256: 3 x 48 KB ring, 1 staging, addend loaded in place                            = 208 KB
+//   BN 192: 3 x 40 KB ring, 2 x 48 KB staging, no addend (plain GEMM launches, N a multiple of 96)  = 216 KB
 cudaError_t launch_conv_fwd_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                     const CUtensorMap& tmD, const ConvFwdParams& p, int bn, bool b_mn,
                                     cudaStream_t st) {
