@@ -253,9 +253,13 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
 // 12 FP32 operations + 2 MUFU per element: at ~19 the passes were bound by the FP32 pipe, not by HBM.
 __device__ __forceinline__ void gelu_parts(float v, float& av, float& q, float& ex) {
   av = fabsf(v);
-  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678f, av, 1.f));
+  // rcp.approx / ex2.approx (1 ulp / 2 ulp): the denominator is >= 1 and the exponent <= 0, so neither needs the special-case
+  // paths of __frcp_rn / exp2f — which compiled to a subroutine call and ~33 instructions per element (r5: the GELU passes
+  // ran at 0.64 of the HBM rate, bound by instruction issue)
+  float t, den = fmaf(0.3275911f * 0.70710678f, av, 1.f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(den));
   const float ap = av * 0.8493218f;   // sqrt(log2(e) / 2): exp(-v^2/2) = 2^(-ap^2)
-  ex = exp2f(-ap * ap);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-ap * ap));
   float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
   poly = fmaf(poly, t, 0.5f * 1.421413741f);
   poly = fmaf(poly, t, 0.5f * -0.284496736f);
