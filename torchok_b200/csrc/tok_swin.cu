@@ -250,9 +250,7 @@ layernorm_bwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
   pdl_launch();
   constexpr int C = 8 * CH * G;
   constexpr int RPW = 32 / G;
-  extern __shared__ float sh[];  // [3][C]
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  extern __shared__ __align__(16) float sh[];  // [warps][3][C]: column-sum slices, written once at the end
   const int lane = threadIdx.x & 31, l = lane % G, sub = lane / G;
   const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -312,20 +310,53 @@ layernorm_bwd_vec_kernel(long long rows, const __nv_bfloat16* __restrict__ x, co
       if (live) reinterpret_cast<uint4*>(dx + r * C)[l + i * G] = pack8(d);
     }
   }
+  // Column sums of the CTA.  The lanes of a warp that share a column group (same l, RPW of them) add up with shuffles,
+  // each warp owns a [3][C] slice of shared memory (plain stores), the slices are summed and leave with 16-byte vector
+  // reds.  r5: the float atomicAdd on shared memory this replaces is a load / add / compare-and-swap spin loop — 72 of them
+  // per thread with up to 8-way contention at the end of every CTA, which dominated the stage 3 / 4 launches (2-4 row
+  // iterations per warp).
+  const int wslice = (threadIdx.x >> 5) * 3 * C;
 #pragma unroll
   for (int i = 0; i < CH; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int c = (l + i * G) * 8 + e;
-      atomicAdd(&sh[c], ag[i][e]);
-      atomicAdd(&sh[C + c], ab[i][e]);
-      if (dxsum) atomicAdd(&sh[2 * C + c], ax[i][e]);
+      float a = ag[i][e], b = ab[i][e], x2 = ax[i][e];
+#pragma unroll
+      for (int s2 = G; s2 < 32; s2 <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, s2);
+        b += __shfl_xor_sync(0xffffffffu, b, s2);
+        if (dxsum) x2 += __shfl_xor_sync(0xffffffffu, x2, s2);
+      }
+      if (sub == 0) {
+        const int c = (l + i * G) * 8 + e;
+        sh[wslice + c] = a;
+        sh[wslice + C + c] = b;
+        sh[wslice + 2 * C + c] = x2;
+      }
     }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + c, sh[c]);
-    if (dbeta) atomicAdd(dbeta + c, sh[C + c]);
-    if (dxsum) atomicAdd(dxsum + c, sh[2 * C + c]);
+  const int nw = blockDim.x >> 5;
+  for (int c4 = threadIdx.x; c4 < 3 * C / 4; c4 += blockDim.x) {   // C % 8 == 0: a float4 never straddles two of the arrays
+    float4 t = *reinterpret_cast<const float4*>(sh + c4 * 4);
+    for (int w = 1; w < nw; ++w) {
+      const float4 u = *reinterpret_cast<const float4*>(sh + w * 3 * C + c4 * 4);
+      t.x += u.x;
+      t.y += u.y;
+      t.z += u.z;
+      t.w += u.w;
+    }
+    const int which = (c4 * 4) / C, c = c4 * 4 - which * C;
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
+    if (dst == nullptr) continue;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w)
+                   : "memory");
+    } else {   // a gradient slice that does not start on a 16-byte boundary
+      atomicAdd(dst + c, t.x);
+      atomicAdd(dst + c + 1, t.y);
+      atomicAdd(dst + c + 2, t.z);
+      atomicAdd(dst + c + 3, t.w);
+    }
   }
 }
 
@@ -2167,7 +2198,7 @@ static long long ln_fwd_ctas() {
 }
 template <int G, int CH>
 static long long ln_bwd_ctas() {
-  static const int n = full_wave_ctas(layernorm_bwd_vec_kernel<G, CH>, 128, 3 * 8 * CH * G * sizeof(float));
+  static const int n = full_wave_ctas(layernorm_bwd_vec_kernel<G, CH>, 128, 4 * 3 * 8 * CH * G * sizeof(float));
   return n;
 }
 
@@ -2370,7 +2401,7 @@ int tok_layernorm_bwd(long long rows, int C, const void* x, const float* gamma, 
     const long long want = (rows + rows_per_pass - 1) / rows_per_pass;
 #define TOK_LN_BWD_V(GG, CC)                                                                                      \
   (void)launch_pdl(layernorm_bwd_vec_kernel<GG, CC>, dim3((unsigned)(want < ln_bwd_ctas<GG, CC>() ? want : ln_bwd_ctas<GG, CC>())), dim3(128), \
-                                     3 * C * sizeof(float), (cudaStream_t)stream,                                \
+                                     4 * 3 * C * sizeof(float), (cudaStream_t)stream,                            \
       rows, (const __nv_bfloat16*)x, gamma, mean, rstd, (const __nv_bfloat16*)dout, rowscale,                      \
       rows_per_sample > 0 ? rows_per_sample : 1, (__nv_bfloat16*)dx, dgamma, dbeta, dxsum)
 #define TOK_LN_BWD_G(CC)                                                                                          \

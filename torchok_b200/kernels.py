@@ -1254,7 +1254,9 @@ def gelu(x, colsum_param=None):
 # + 1.97 ms (tok_gelu_bwd) for the launches they replace, step 26.6 vs 25.2 ms — the derivative costs ~14 instructions
 # and 2 MUFU per element, and in the GEMM epilogue only the 8 epilogue warps of the CTA (2 per scheduler) execute it,
 # while the stand-alone pass spreads the same work over 64 warps per SM and runs at 4.2 TB/s.  So the default is the
-# two-node form; TOK_GELU_DGRAD=1 selects the fused node (kept correct by tests/test_swin_gpu.py).
+# two-node form; TOK_GELU_DGRAD=1 selects the fused node (kept correct by tests/test_swin_gpu.py).  Re-measured after the
+# derivative went from ~33 to ~14 instructions per element (rcp.approx / ex2.approx): 2.92 ms fused against 1.14 + 1.53 ms,
+# step 24.08 vs 24.05 ms — even, so the default stays.
 _GELU_DGRAD = os.environ.get('TOK_GELU_DGRAD', '0') == '1'
 
 
