@@ -2218,7 +2218,6 @@ cpb_table_kernel(const float* __restrict__ coords, const float* __restrict__ w1,
   pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
   pdl_launch();
   __shared__ float sh[kCpbHidden];
-  __shared__ float red[4];
   const int e = blockIdx.x;
   const float c0 = coords[2 * e], c1 = coords[2 * e + 1];
   for (int k = threadIdx.x; k < kCpbHidden; k += 128) {
@@ -2227,14 +2226,15 @@ cpb_table_kernel(const float* __restrict__ coords, const float* __restrict__ w1,
     hidden[(long long)e * kCpbHidden + k] = v;
   }
   __syncthreads();
-  for (int h = 0; h < heads; ++h) {
+  // one warp per head (r5: the head loop used to run on the whole CTA with two barriers per head — 48 barriers and as many
+  // dependent L2 round trips for 24 heads in a kernel whose whole job is 169 x 512 x heads FMAs)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = warp; h < heads; h += 4) {
     float t = 0.f;
-    for (int k = threadIdx.x; k < kCpbHidden; k += 128) t = fmaf(w2[(long long)h * kCpbHidden + k], sh[k], t);
+#pragma unroll 4
+    for (int k = lane; k < kCpbHidden; k += 32) t = fmaf(w2[(long long)h * kCpbHidden + k], sh[k], t);
     t = warp_sum(t);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
-    __syncthreads();
-    if (threadIdx.x == 0) table[(long long)e * heads + h] = red[0] + red[1] + red[2] + red[3];
-    __syncthreads();
+    if (lane == 0) table[(long long)e * heads + h] = t;
   }
 }
 
@@ -2265,28 +2265,25 @@ cpb_scatter_kernel(const float* __restrict__ dbias, const float* __restrict__ ta
                    int heads, int ws) {
   pdl_wait();   // programmatic dependent launch: see tok_ptx.cuh
   pdl_launch();
-  __shared__ float red[4];
   const int N = ws * ws;
   const int e = blockIdx.x;
   const int dy = e / (2 * ws - 1) - (ws - 1), dx = e % (2 * ws - 1) - (ws - 1);
   // token j = (yj, xj) pairs with i = (yj + dy, xj + dx) when that is inside the window
   const int y0 = max(0, -dy), y1 = min(ws, ws - dy), x0 = max(0, -dx), x1 = min(ws, ws - dx);
   const int ny = y1 - y0, nx = x1 - x0, cnt = ny > 0 && nx > 0 ? ny * nx : 0;
-  for (int h = 0; h < heads; ++h) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = warp; h < heads; h += 4) {   // one warp per head, no CTA barriers
     float acc = 0.f;
-    for (int t = threadIdx.x; t < cnt; t += 128) {
+    for (int t = lane; t < cnt; t += 32) {
       const int yj = y0 + t / nx, xj = x0 + t % nx;
       const int j = yj * ws + xj, i = (yj + dy) * ws + (xj + dx);
       acc += dbias[((long long)h * N + i) * N + j];
     }
     acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
       const float s = 1.f / (1.f + __expf(-table[(long long)e * heads + h]));
-      dtable[(long long)e * heads + h] = 16.f * s * (1.f - s) * (red[0] + red[1] + red[2] + red[3]);
+      dtable[(long long)e * heads + h] = 16.f * s * (1.f - s) * acc;
     }
-    __syncthreads();
   }
 }
 
@@ -2326,14 +2323,12 @@ cpb_mlp_bwd_kernel(const float* __restrict__ dtable, const float* __restrict__ h
     dw1[2 * k + 1] += red[0][1] + red[1][1] + red[2][1] + red[3][1];
     db1[k] += red[0][2] + red[1][2] + red[2][2] + red[3][2];
   }
-  for (int h = 0; h < heads; ++h) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = warp; h < heads; h += 4) {   // one warp per head, no CTA barriers
     float t = 0.f;
-    for (int e = threadIdx.x; e < T; e += 128) t = fmaf(dtable[(long long)e * heads + h], hidden[(long long)e * kCpbHidden + k], t);
+    for (int e = lane; e < T; e += 32) t = fmaf(dtable[(long long)e * heads + h], hidden[(long long)e * kCpbHidden + k], t);
     t = warp_sum(t);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][3] = t;
-    __syncthreads();
-    if (threadIdx.x == 0) dw2[(long long)h * kCpbHidden + k] += red[0][3] + red[1][3] + red[2][3] + red[3][3];
+    if (lane == 0) dw2[(long long)h * kCpbHidden + k] += t;
   }
 }
 }  // namespace
